@@ -1,0 +1,238 @@
+"""ctypes binding of libgrr_b200.so (include/grr_b200.h).
+
+This is the ONLY compute path of the package: if the shared library is missing or a call fails the
+error is raised -- there is no CPU or PyTorch fallback.  PyTorch is used for device memory and
+streams only; every pointer handed to the library is `tensor.data_ptr()`.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libgrr_b200.so")
+
+GRR_F32, GRR_F64 = 0, 1
+GRR_FREE, GRR_FIXED, GRR_VARIABLE = 0, 1, 2
+IK_OK, IK_STALL, IK_CONVX, IK_MAXIT = 0, 1, 2, 3
+CNT_IK_SOLVES, CNT_IK_ITERS, CNT_IK_EVALS, CNT_PAIRS, CNT_VALID, CNT_IK_OK, CNT_SLOTS = 0, 1, 2, 3, 4, 5, 8
+MAX_JOINTS = 32
+
+# every symbol include/grr_b200.h declares (checked by tests/test_cabi_symbols.py)
+EXPORTS = [
+    "grr_last_error", "grr_abi_version", "grr_chain_create", "grr_chain_destroy", "grr_task_set",
+    "grr_chain_num_joints", "grr_fk_batch", "grr_ik_solve_batch", "grr_ik_sample", "grr_dedup",
+    "grr_edges_build", "grr_edges_compact", "grr_valid_edge_batch", "grr_gather_node_blocks",
+    "grr_scatter_node_blocks", "grr_fp32_peak",
+]
+
+
+class GrrError(RuntimeError):
+    pass
+
+
+class ChainDesc(C.Structure):
+    _fields_ = [
+        ("n", C.c_int32), ("mode", C.c_int32), ("nlinks_eps", C.c_int32), ("max_iters", C.c_int32),
+        ("tol", C.c_double), ("lambda_", C.c_double),
+        ("Rp", C.POINTER(C.c_double)), ("tp", C.POINTER(C.c_double)), ("axis", C.POINTER(C.c_double)),
+        ("qmin", C.POINTER(C.c_double)), ("qmax", C.POINTER(C.c_double)),
+        ("ee_local", C.c_double * 3), ("R_tail", C.c_double * 9), ("R_goal", C.c_double * 9),
+    ]
+
+
+_lib = None
+
+
+def lib():
+    """Load libgrr_b200.so (built by __graft_entry__.build() / csrc/Makefile).  Fails loudly."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise GrrError(
+            "libgrr_b200.so not found at %s: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(or `make -C globalredundancyresolution_b200/csrc`). There is no CPU fallback." % LIB_PATH)
+    L = C.CDLL(LIB_PATH)
+    vp, i32, i64, u64, dbl = C.c_void_p, C.c_int32, C.c_int64, C.c_uint64, C.c_double
+    L.grr_last_error.restype = C.c_char_p
+    L.grr_last_error.argtypes = []
+    L.grr_abi_version.restype = C.c_int
+    L.grr_chain_create.argtypes = [C.POINTER(ChainDesc), C.c_int, C.POINTER(vp)]
+    L.grr_chain_destroy.argtypes = [vp]
+    L.grr_task_set.argtypes = [vp, C.c_int, C.POINTER(C.c_double)]
+    L.grr_chain_num_joints.argtypes = [vp]
+    L.grr_fk_batch.argtypes = [vp, C.c_int, i64, vp, vp, vp, vp]
+    L.grr_ik_solve_batch.argtypes = [vp, C.c_int, i64, vp, vp, vp, vp, vp, vp, vp]
+    L.grr_ik_sample.argtypes = [vp, C.c_int, i64, i32, i32, vp, vp, u64, i32, vp, vp, vp, vp, vp]
+    L.grr_dedup.argtypes = [vp, C.c_int, i64, i32, i32, vp, vp, dbl, i32, vp, vp, vp, vp, vp]
+    L.grr_edges_build.argtypes = [vp, C.c_int, i64, vp, vp, vp, vp, vp, i32, i32, dbl, vp, vp, vp, vp]
+    L.grr_edges_compact.argtypes = [i64, i32, vp, vp, vp, vp]
+    L.grr_valid_edge_batch.argtypes = [vp, C.c_int, i64, vp, vp, vp, vp, dbl, vp, vp, vp, vp]
+    L.grr_gather_node_blocks.argtypes = [C.c_int, i64, vp, i32, i32, vp, vp, vp, vp, vp]
+    L.grr_scatter_node_blocks.argtypes = [C.c_int, i64, vp, i32, i32, vp, vp, vp, vp, vp]
+    L.grr_fp32_peak.argtypes = [C.c_int, C.POINTER(C.c_double)]
+    for name in EXPORTS:
+        if name not in ("grr_last_error",):
+            getattr(L, name).restype = C.c_int
+    _lib = L
+    return L
+
+
+def check(rc, what):
+    if rc != 0:
+        raise GrrError("%s failed (%d): %s" % (what, rc, lib().grr_last_error().decode()))
+
+
+def _ptr(t):
+    """Device (or None) pointer of a torch tensor."""
+    if t is None:
+        return None
+    assert t.is_contiguous(), "C ABI buffers must be contiguous"
+    return C.c_void_p(t.data_ptr())
+
+
+def _stream(device):
+    import torch
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def dtype_code(torch_dtype):
+    import torch
+    if torch_dtype == torch.float32:
+        return GRR_F32
+    if torch_dtype == torch.float64:
+        return GRR_F64
+    raise GrrError("unsupported dtype %r (float32 = product path, float64 = verification)" % (torch_dtype,))
+
+
+def round_up4(nq):
+    return (int(nq) + 3) // 4 * 4
+
+
+class ChainHandle:
+    """Opaque (device, chain) handle: grr_chain_create / grr_chain_destroy."""
+
+    def __init__(self, chain_arrays, mode, R_goal=None, nlinks_eps=None, tol=1e-3, max_iters=50, lam=0.01, device=0):
+        """chain_arrays: dict with Rp [n,9], tp [n,3], axis [n,3], qmin [n], qmax [n], ee_local [3], R_tail [9]
+        (numpy float64; produced by robot.RobotChain.fold())."""
+        L = lib()
+        self.n = int(chain_arrays["qmin"].shape[0])
+        self.mode = int(mode)
+        self.device = int(device)
+        self._keep = {k: np.ascontiguousarray(np.asarray(chain_arrays[k], dtype=np.float64))
+                      for k in ("Rp", "tp", "axis", "qmin", "qmax", "ee_local", "R_tail")}
+        d = ChainDesc()
+        d.n = self.n
+        d.mode = self.mode
+        d.nlinks_eps = int(nlinks_eps if nlinks_eps is not None else self.n)
+        d.max_iters = int(max_iters)
+        d.tol = float(tol)
+        d.lambda_ = float(lam)
+        dp = C.POINTER(C.c_double)
+        for k in ("Rp", "tp", "axis", "qmin", "qmax"):
+            setattr(d, k, self._keep[k].ctypes.data_as(dp))
+        d.ee_local[:] = list(self._keep["ee_local"].reshape(3))
+        d.R_tail[:] = list(self._keep["R_tail"].reshape(9))
+        rg = np.eye(3).reshape(9) if R_goal is None else np.asarray(R_goal, dtype=np.float64).reshape(9)
+        d.R_goal[:] = list(rg)
+        self.nlinks_eps = d.nlinks_eps
+        self.tol, self.max_iters, self.lam = d.tol, d.max_iters, d.lambda_
+        h = C.c_void_p()
+        check(L.grr_chain_create(C.byref(d), self.device, C.byref(h)), "grr_chain_create")
+        self._h = h
+
+    @property
+    def dw(self):
+        return 6 if self.mode == GRR_VARIABLE else 3
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().grr_chain_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def task_set(self, mode, R_goal=None):
+        rg = None
+        if R_goal is not None:
+            arr = (C.c_double * 9)(*[float(v) for v in np.asarray(R_goal).reshape(9)])
+            rg = C.cast(arr, C.POINTER(C.c_double))
+        check(lib().grr_task_set(self._h, int(mode), rg), "grr_task_set")
+        self.mode = int(mode)
+
+    # ---- thin wrappers: torch tensors in, status checked --------------------------------------
+    def fk_batch(self, q, out_p, out_R=None):
+        P = q.shape[1]
+        check(lib().grr_fk_batch(self._h, dtype_code(q.dtype), P, _ptr(q), _ptr(out_p), _ptr(out_R),
+                                 _stream(q.device)), "grr_fk_batch")
+
+    def ik_solve_batch(self, targets, q, status, iters=None, resid=None, counters=None):
+        P = q.shape[1]
+        check(lib().grr_ik_solve_batch(self._h, dtype_code(q.dtype), P, _ptr(targets), _ptr(q), _ptr(status),
+                                       _ptr(iters), _ptr(resid), _ptr(counters), _stream(q.device)),
+              "grr_ik_solve_batch")
+
+    def ik_sample(self, params, node_uid, seed, q_raw, status, iters=None, counters=None, Nq=None, sample_offset=0):
+        Nw, n, Nqp = q_raw.shape
+        Nq = Nqp if Nq is None else int(Nq)
+        check(lib().grr_ik_sample(self._h, dtype_code(q_raw.dtype), Nw, Nq, Nqp, _ptr(params), _ptr(node_uid),
+                                  C.c_uint64(int(seed) & (2 ** 64 - 1)), int(sample_offset), _ptr(q_raw),
+                                  _ptr(status), _ptr(iters), _ptr(counters), _stream(q_raw.device)),
+              "grr_ik_sample")
+
+    def dedup(self, q_raw, status, thresh, q_kept, count, Nq=None, count_in=None, keep_idx=None):
+        Nw, n, Nqp = q_raw.shape
+        Nq = Nqp if Nq is None else int(Nq)
+        check(lib().grr_dedup(self._h, dtype_code(q_raw.dtype), Nw, Nq, Nqp, _ptr(q_raw), _ptr(status),
+                              float(thresh), q_kept.shape[2], _ptr(q_kept), _ptr(count_in), _ptr(keep_idx),
+                              _ptr(count), _stream(q_raw.device)), "grr_dedup")
+
+    def edges_build(self, wedges, params, q_kept, count, Nq, epsilon, mask, edge_stats=None, counters=None,
+                    old_count=None):
+        E = wedges.shape[0]
+        Nqp = q_kept.shape[2]
+        check(lib().grr_edges_build(self._h, dtype_code(q_kept.dtype), E, _ptr(wedges), _ptr(params),
+                                    _ptr(q_kept), _ptr(count), _ptr(old_count), int(Nq), Nqp, float(epsilon),
+                                    _ptr(mask), _ptr(edge_stats), _ptr(counters), _stream(q_kept.device)),
+              "grr_edges_build")
+
+    def valid_edge_batch(self, qa, qb, wa, wb, epsilon, valid, info=None, counters=None):
+        P = qa.shape[1]
+        check(lib().grr_valid_edge_batch(self._h, dtype_code(qa.dtype), P, _ptr(qa), _ptr(qb), _ptr(wa), _ptr(wb),
+                                         float(epsilon), _ptr(valid), _ptr(info), _ptr(counters),
+                                         _stream(qa.device)), "grr_valid_edge_batch")
+
+
+def edges_compact(mask, Nq, offsets, out):
+    E = mask.shape[0]
+    check(lib().grr_edges_compact(E, int(Nq), _ptr(mask), _ptr(offsets), _ptr(out), _stream(mask.device)),
+          "grr_edges_compact")
+
+
+def gather_node_blocks(idx, q, count, packed, packed_count):
+    K = idx.shape[0]
+    _, n, Nqp = q.shape
+    check(lib().grr_gather_node_blocks(dtype_code(q.dtype), K, _ptr(idx), n, Nqp, _ptr(q), _ptr(count),
+                                       _ptr(packed), _ptr(packed_count), _stream(q.device)),
+          "grr_gather_node_blocks")
+
+
+def scatter_node_blocks(idx, packed, packed_count, q, count):
+    K = idx.shape[0]
+    _, n, Nqp = q.shape
+    check(lib().grr_scatter_node_blocks(dtype_code(q.dtype), K, _ptr(idx), n, Nqp, _ptr(packed),
+                                        _ptr(packed_count), _ptr(q), _ptr(count), _stream(q.device)),
+          "grr_scatter_node_blocks")
+
+
+def fp32_peak(device=0):
+    out = C.c_double(0.0)
+    check(lib().grr_fp32_peak(int(device), C.byref(out)), "grr_fp32_peak")
+    return out.value

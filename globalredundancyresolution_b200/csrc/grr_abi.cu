@@ -1,0 +1,357 @@
+// grr_abi.cu -- the extern "C" boundary of libgrr_b200.so (see include/grr_b200.h) plus the
+// kernels that do not depend on the joint count: duplicate filter, bitmask -> edge-list
+// compaction, FK, node-block gather/scatter for the halo exchange, FP32 peak microbenchmark.
+#include <stdarg.h>
+#include <stdio.h>
+#include <new>
+#include "grr_device.cuh"
+#include "grr_host.h"
+#include "grr_fill.cuh"
+
+namespace grr {
+
+static thread_local char g_err[512] = "";
+void set_error(const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof g_err, fmt, ap);
+  va_end(ap);
+}
+
+static inline int launch_ok(const char *what) {
+  cudaError_t err = cudaGetLastError();
+  if (err != cudaSuccess) { set_error("%s: %s", what, cudaGetErrorString(err)); return -2; }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// S3: greedy first-wins duplicate filter, one CTA per workspace node
+// (solver.py:802-813,824-835,886-897: keep q iff robot.distance(q,q') >= 1e-2 for all kept q')
+// ------------------------------------------------------------------------------------------
+template <typename Real>
+__global__ void __launch_bounds__(128)
+k_dedup(int n, int Nq, int Nqp, const Real *__restrict__ q_raw, const uint8_t *__restrict__ status, Real thresh,
+        int Nqp_kept, Real *q_kept, const int32_t *__restrict__ count_in, int32_t *__restrict__ keep_idx,
+        int32_t *__restrict__ count) {
+  const long long node = blockIdx.x;
+  const Real *raw = q_raw + node * n * (long long)Nqp;
+  Real *out = q_kept + node * n * (long long)Nqp_kept;
+  const uint8_t *st = status + node * Nqp;
+  int kept = count_in ? count_in[node] : 0;
+  const int kept0 = kept;
+  for (int s = 0; s < Nq; s++) {
+    if (st[s] != 0) continue;                     // failed IK: q is None (solver.py:800,822,885)
+    int same = 0;
+    for (int k = threadIdx.x; k < kept; k += blockDim.x) {
+      Real d2 = 0;
+      for (int j = 0; j < n; j++) { Real d = raw[j * Nqp + s] - out[j * Nqp_kept + k]; d2 += d * d; }
+      if (sqrt_(d2) < thresh) same = 1;
+    }
+    same = __syncthreads_or(same);
+    if (!same && kept < Nqp_kept) {
+      for (int j = threadIdx.x; j < n; j += blockDim.x) out[j * Nqp_kept + kept] = raw[j * Nqp + s];
+      if (threadIdx.x == 0 && keep_idx) keep_idx[node * Nq + (kept - kept0)] = s;
+      kept++;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) count[node] = kept;
+  if (keep_idx)
+    for (int k = (kept - kept0) + threadIdx.x; k < Nq; k += blockDim.x) keep_idx[node * Nq + k] = -1;
+}
+
+// ------------------------------------------------------------------------------------------
+// bitmask -> (iq,jq) lists, one CTA per workspace edge, ballot-free ordered compaction:
+// block-wide exclusive scan of the mask words' popcounts, then each thread expands its word.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+k_edges_compact(int Nq, const uint32_t *__restrict__ mask, const long long *__restrict__ offsets, int32_t *__restrict__ out) {
+  const long long e = blockIdx.x;
+  const int Wd = (Nq + 31) >> 5, words = Nq * Wd;
+  const uint32_t *m = mask + e * (long long)words;
+  __shared__ int s_warp[4];
+  __shared__ long long s_base;
+  if (threadIdx.x == 0) s_base = offsets[e];
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int w0 = 0; w0 < words; w0 += blockDim.x) {
+    const int wi = w0 + threadIdx.x;
+    const uint32_t word = wi < words ? m[wi] : 0u;
+    const int c = __popc(word);
+    int incl = c;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { int t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += t; }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    int wbase = 0, total = 0;
+    for (int k = 0; k < 4; k++) { if (k < warp) wbase += s_warp[k]; total += s_warp[k]; }
+    long long pos = s_base + wbase + incl - c;
+    if (c) {
+      const int a = wi / Wd, b0 = (wi - a * Wd) * 32;
+      uint32_t bits = word;
+      while (bits) {
+        const int b = __ffs(bits) - 1;
+        bits &= bits - 1;
+        out[2 * pos] = a; out[2 * pos + 1] = b0 + b;
+        pos++;
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) s_base += total;
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// FK on a batch (API: ikError / getIKParameters; graph.py:747-756,887-893)
+// ------------------------------------------------------------------------------------------
+template <typename Real>
+__global__ void k_fk_batch(const __grid_constant__ ChainDev<Real, kMaxJ> c, long long P, const Real *__restrict__ q,
+                           Real *__restrict__ out_p, Real *__restrict__ out_R) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= P) return;
+  Real x[kMaxJ], p[3], R[9];
+  for (int j = 0; j < c.n; j++) x[j] = q[(long long)j * P + t];
+  chain_fk<Real, kMaxJ>(c, x, p, R);
+  out_p[3 * t] = p[0]; out_p[3 * t + 1] = p[1]; out_p[3 * t + 2] = p[2];
+  if (out_R) for (int k = 0; k < 9; k++) out_R[9 * t + k] = R[k];
+}
+
+// ------------------------------------------------------------------------------------------
+// halo exchange support: whole node blocks <-> packed message buffer
+// ------------------------------------------------------------------------------------------
+template <typename Real, bool GATHER>
+__global__ void k_node_blocks(long long K, const int32_t *__restrict__ idx, int blk, Real *q, int32_t *count, Real *packed,
+                              int32_t *packed_count) {
+  const long long k = blockIdx.x;
+  const long long node = idx[k];
+  Real *a = q + node * blk, *b = packed + k * blk;
+  for (int i = threadIdx.x; i < blk; i += blockDim.x) { if (GATHER) b[i] = a[i]; else a[i] = b[i]; }
+  if (threadIdx.x == 0) { if (GATHER) packed_count[k] = count[node]; else count[node] = packed_count[k]; }
+}
+
+// ------------------------------------------------------------------------------------------
+// FP32 FMA peak (roofline denominator for the IK / edge kernels)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_fma_peak(float *out, int iters, float a, float b) {
+  float x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+  for (int i = 0; i < iters; i++) {
+#pragma unroll
+    for (int u = 0; u < 16; u++) {
+      x0 = fmaf(x0, a, b); x1 = fmaf(x1, a, b); x2 = fmaf(x2, a, b); x3 = fmaf(x3, a, b);
+      x4 = fmaf(x4, a, b); x5 = fmaf(x5, a, b); x6 = fmaf(x6, a, b); x7 = fmaf(x7, a, b);
+    }
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+}
+
+static const Ops *pick_ops(int dtype, int mode) {
+  const bool m6 = (mode != GRR_FREE);
+  if (dtype == GRR_F32) return m6 ? ops_f32_m6() : ops_f32_m3();
+  if (dtype == GRR_F64) return m6 ? ops_f64_m6() : ops_f64_m3();
+  return nullptr;
+}
+
+}  // namespace grr
+
+using namespace grr;
+
+struct grr_handle_s {
+  HostChain hc;
+};
+
+#define GRR_CHECK_HANDLE(h)                                   \
+  if (!(h)) { set_error("null handle"); return -1; }          \
+  { cudaError_t e_ = cudaSetDevice((h)->hc.device);           \
+    if (e_ != cudaSuccess) { set_error("cudaSetDevice(%d): %s", (h)->hc.device, cudaGetErrorString(e_)); return -2; } }
+
+extern "C" {
+
+const char *grr_last_error(void) { return g_err; }
+int grr_abi_version(void) { return 1; }
+
+int grr_chain_create(const grr_chain_desc *d, int device, grr_handle_t *out) {
+  if (!d || !out) { set_error("grr_chain_create: null argument"); return -1; }
+  if (d->n < 1 || d->n > GRR_MAX_JOINTS) { set_error("grr_chain_create: n=%d outside 1..%d", d->n, GRR_MAX_JOINTS); return -1; }
+  if (d->mode < GRR_FREE || d->mode > GRR_VARIABLE) { set_error("grr_chain_create: bad mode %d", d->mode); return -1; }
+  if (!d->Rp || !d->tp || !d->axis || !d->qmin || !d->qmax) { set_error("grr_chain_create: null chain arrays"); return -1; }
+  if (!(d->tol > 0) || d->max_iters < 0 || d->max_iters > 250 || !(d->lambda >= 0)) { set_error("grr_chain_create: bad solver parameters"); return -1; }
+  if (d->nlinks_eps < 1) { set_error("grr_chain_create: nlinks_eps must be >= 1"); return -1; }
+  grr_handle_s *h = new (std::nothrow) grr_handle_s;
+  if (!h) { set_error("out of memory"); return -3; }
+  memset(h, 0, sizeof *h);
+  HostChain &c = h->hc;
+  c.n = d->n; c.mode = d->mode; c.nlinks_eps = d->nlinks_eps; c.max_iters = d->max_iters; c.device = device;
+  c.tol = d->tol; c.lambda = d->lambda;
+  memcpy(c.Rp, d->Rp, sizeof(double) * 9 * d->n);
+  memcpy(c.tp, d->tp, sizeof(double) * 3 * d->n);
+  memcpy(c.axis, d->axis, sizeof(double) * 3 * d->n);
+  memcpy(c.qmin, d->qmin, sizeof(double) * d->n);
+  memcpy(c.qmax, d->qmax, sizeof(double) * d->n);
+  memcpy(c.ee_local, d->ee_local, sizeof c.ee_local);
+  memcpy(c.R_tail, d->R_tail, sizeof c.R_tail);
+  memcpy(c.R_goal, d->R_goal, sizeof c.R_goal);
+  for (int j = 0; j < c.n; j++) {
+    const double *a = c.axis + 3 * j;
+    const double nn = a[0] * a[0] + a[1] * a[1] + a[2] * a[2];
+    if (!(nn > 0.999 && nn < 1.001)) { set_error("grr_chain_create: axis %d is not unit", j); delete h; return -1; }
+    if (!(c.qmin[j] <= c.qmax[j])) { set_error("grr_chain_create: qmin>qmax at joint %d", j); delete h; return -1; }
+  }
+  *out = h;
+  return 0;
+}
+
+int grr_chain_destroy(grr_handle_t h) {
+  delete h;
+  return 0;
+}
+
+int grr_task_set(grr_handle_t h, int mode, const double *R_goal9) {
+  if (!h) { set_error("null handle"); return -1; }
+  if (mode < GRR_FREE || mode > GRR_VARIABLE) { set_error("grr_task_set: bad mode %d", mode); return -1; }
+  h->hc.mode = mode;
+  if (R_goal9) memcpy(h->hc.R_goal, R_goal9, sizeof h->hc.R_goal);
+  return 0;
+}
+
+int grr_chain_num_joints(grr_handle_t h) { return h ? h->hc.n : -1; }
+
+int grr_fk_batch(grr_handle_t h, int dtype, int64_t P, const void *q, void *out_p, void *out_R, void *stream) {
+  GRR_CHECK_HANDLE(h);
+  if (P <= 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  const unsigned blocks = (unsigned)((P + 127) / 128);
+  if (dtype == GRR_F32) {
+    ChainDev<float, kMaxJ> c;
+    fill_chain(h->hc, c);
+    k_fk_batch<float><<<blocks, 128, 0, st>>>(c, P, (const float *)q, (float *)out_p, (float *)out_R);
+  } else if (dtype == GRR_F64) {
+    ChainDev<double, kMaxJ> c;
+    fill_chain(h->hc, c);
+    k_fk_batch<double><<<blocks, 128, 0, st>>>(c, P, (const double *)q, (double *)out_p, (double *)out_R);
+  } else { set_error("bad dtype %d", dtype); return -1; }
+  return launch_ok("k_fk_batch");
+}
+
+int grr_ik_solve_batch(grr_handle_t h, int dtype, int64_t P, const void *targets, void *q, uint8_t *status,
+                       uint8_t *iters, void *resid, uint64_t *counters, void *stream) {
+  GRR_CHECK_HANDLE(h);
+  const Ops *ops = pick_ops(dtype, h->hc.mode);
+  if (!ops) { set_error("bad dtype %d", dtype); return -1; }
+  if (P < 0 || (P > 0 && (!targets || !q || !status))) { set_error("grr_ik_solve_batch: null buffer"); return -1; }
+  return ops->ik_solve_batch(h->hc, P, targets, q, status, iters, resid, (unsigned long long *)counters, (cudaStream_t)stream);
+}
+
+int grr_ik_sample(grr_handle_t h, int dtype, int64_t Nw, int32_t Nq, int32_t Nqp, const void *params,
+                  const int32_t *node_uid, uint64_t seed, int32_t sample_offset, void *q_raw, uint8_t *status,
+                  uint8_t *iters, uint64_t *counters, void *stream) {
+  GRR_CHECK_HANDLE(h);
+  const Ops *ops = pick_ops(dtype, h->hc.mode);
+  if (!ops) { set_error("bad dtype %d", dtype); return -1; }
+  if (Nw < 0 || Nq < 0 || Nqp < Nq) { set_error("grr_ik_sample: bad sizes Nw=%lld Nq=%d Nqp=%d", (long long)Nw, Nq, Nqp); return -1; }
+  if (Nw * (int64_t)Nq > 0 && (!params || !node_uid || !q_raw || !status)) { set_error("grr_ik_sample: null buffer"); return -1; }
+  return ops->ik_sample(h->hc, Nw, Nq, Nqp, params, node_uid, seed, sample_offset, q_raw, status, iters,
+                        (unsigned long long *)counters, (cudaStream_t)stream);
+}
+
+int grr_dedup(grr_handle_t h, int dtype, int64_t Nw, int32_t Nq, int32_t Nqp, const void *q_raw, const uint8_t *status,
+              double thresh, int32_t Nqp_kept, void *q_kept, const int32_t *count_in, int32_t *keep_idx, int32_t *count,
+              void *stream) {
+  GRR_CHECK_HANDLE(h);
+  if (Nw <= 0) return 0;
+  if (!q_raw || !status || !q_kept || !count) { set_error("grr_dedup: null buffer"); return -1; }
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == GRR_F32)
+    k_dedup<float><<<(unsigned)Nw, 128, 0, st>>>(h->hc.n, Nq, Nqp, (const float *)q_raw, status, (float)thresh, Nqp_kept,
+                                                 (float *)q_kept, count_in, keep_idx, count);
+  else if (dtype == GRR_F64)
+    k_dedup<double><<<(unsigned)Nw, 128, 0, st>>>(h->hc.n, Nq, Nqp, (const double *)q_raw, status, thresh, Nqp_kept,
+                                                  (double *)q_kept, count_in, keep_idx, count);
+  else { set_error("bad dtype %d", dtype); return -1; }
+  return launch_ok("k_dedup");
+}
+
+int grr_edges_build(grr_handle_t h, int dtype, int64_t E, const int32_t *wedges, const void *params, const void *q_kept,
+                    const int32_t *count, const int32_t *old_count, int32_t Nq, int32_t Nqp, double epsilon,
+                    uint32_t *mask, uint32_t *edge_stats, uint64_t *counters, void *stream) {
+  GRR_CHECK_HANDLE(h);
+  const Ops *ops = pick_ops(dtype, h->hc.mode);
+  if (!ops) { set_error("bad dtype %d", dtype); return -1; }
+  if (E < 0 || Nq < 1 || Nqp < Nq) { set_error("grr_edges_build: bad sizes"); return -1; }
+  if (E > 0 && (!wedges || !params || !q_kept || !count || !mask)) { set_error("grr_edges_build: null buffer"); return -1; }
+  return ops->edges_build(h->hc, E, wedges, params, q_kept, count, old_count, Nq, Nqp, epsilon, mask, edge_stats,
+                          (unsigned long long *)counters, (cudaStream_t)stream);
+}
+
+int grr_edges_compact(int64_t E, int32_t Nq, const uint32_t *mask, const int64_t *offsets, int32_t *out, void *stream) {
+  if (E <= 0) return 0;
+  if (!mask || !offsets || !out) { set_error("grr_edges_compact: null buffer"); return -1; }
+  k_edges_compact<<<(unsigned)E, 128, 0, (cudaStream_t)stream>>>(Nq, mask, (const long long *)offsets, out);
+  return launch_ok("k_edges_compact");
+}
+
+int grr_valid_edge_batch(grr_handle_t h, int dtype, int64_t P, const void *qa, const void *qb, const void *wa,
+                         const void *wb, double epsilon, uint8_t *valid, int32_t *info, uint64_t *counters, void *stream) {
+  GRR_CHECK_HANDLE(h);
+  const Ops *ops = pick_ops(dtype, h->hc.mode);
+  if (!ops) { set_error("bad dtype %d", dtype); return -1; }
+  if (P > 0 && (!qa || !qb || !wa || !wb || !valid)) { set_error("grr_valid_edge_batch: null buffer"); return -1; }
+  return ops->valid_edge_batch(h->hc, P, qa, qb, wa, wb, epsilon, valid, info, (unsigned long long *)counters,
+                               (cudaStream_t)stream);
+}
+
+int grr_gather_node_blocks(int dtype, int64_t K, const int32_t *idx, int32_t n, int32_t Nqp, const void *q,
+                           const int32_t *count, void *packed, int32_t *packed_count, void *stream) {
+  if (K <= 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == GRR_F32)
+    k_node_blocks<float, true><<<(unsigned)K, 128, 0, st>>>(K, idx, n * Nqp, (float *)q, (int32_t *)count, (float *)packed, packed_count);
+  else if (dtype == GRR_F64)
+    k_node_blocks<double, true><<<(unsigned)K, 128, 0, st>>>(K, idx, n * Nqp, (double *)q, (int32_t *)count, (double *)packed, packed_count);
+  else { set_error("bad dtype %d", dtype); return -1; }
+  return launch_ok("k_node_blocks<gather>");
+}
+
+int grr_scatter_node_blocks(int dtype, int64_t K, const int32_t *idx, int32_t n, int32_t Nqp, const void *packed,
+                            const int32_t *packed_count, void *q, int32_t *count, void *stream) {
+  if (K <= 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == GRR_F32)
+    k_node_blocks<float, false><<<(unsigned)K, 128, 0, st>>>(K, idx, n * Nqp, (float *)q, count, (float *)packed, (int32_t *)packed_count);
+  else if (dtype == GRR_F64)
+    k_node_blocks<double, false><<<(unsigned)K, 128, 0, st>>>(K, idx, n * Nqp, (double *)q, count, (double *)packed, (int32_t *)packed_count);
+  else { set_error("bad dtype %d", dtype); return -1; }
+  return launch_ok("k_node_blocks<scatter>");
+}
+
+int grr_fp32_peak(int device, double *tflops_out) {
+  if (!tflops_out) { set_error("null argument"); return -1; }
+  cudaError_t e = cudaSetDevice(device);
+  if (e != cudaSuccess) { set_error("cudaSetDevice: %s", cudaGetErrorString(e)); return -2; }
+  int sms = 0;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+  const int blocks = sms * 8, threads = 256, iters = 4096;
+  float *buf = nullptr;
+  if (cudaMalloc(&buf, sizeof(float) * blocks * threads) != cudaSuccess) { set_error("cudaMalloc failed"); return -3; }
+  cudaEvent_t a, b;
+  cudaEventCreate(&a); cudaEventCreate(&b);
+  double best = 0;
+  for (int rep = 0; rep < 5; rep++) {
+    cudaEventRecord(a);
+    k_fma_peak<<<blocks, threads>>>(buf, iters, 0.999f, 0.001f);
+    cudaEventRecord(b);
+    cudaEventSynchronize(b);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, a, b);
+    const double flops = 2.0 * 8 * 16 * (double)iters * blocks * threads;
+    const double tf = flops / (ms * 1e-3) / 1e12;
+    if (rep > 0 && tf > best) best = tf;
+  }
+  cudaEventDestroy(a); cudaEventDestroy(b);
+  cudaFree(buf);
+  int rc = launch_ok("k_fma_peak");
+  *tflops_out = best;
+  return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,40 @@
+// grr_host.h -- host-side glue shared by the C-ABI unit and the kernel instantiation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string.h>
+#include <limits>
+#include "../../include/grr_b200.h"
+
+namespace grr {
+
+struct HostChain {
+  int n, mode, nlinks_eps, max_iters, device;
+  double tol, lambda;
+  double Rp[GRR_MAX_JOINTS * 9], tp[GRR_MAX_JOINTS * 3], axis[GRR_MAX_JOINTS * 3];
+  double qmin[GRR_MAX_JOINTS], qmax[GRR_MAX_JOINTS];
+  double ee_local[3], R_tail[9], R_goal[9];
+};
+
+void set_error(const char *fmt, ...);
+
+// One table of launchers per (precision, residual rows); each entry dispatches on the joint count.
+struct Ops {
+  int (*ik_sample)(const HostChain &, long long Nw, int Nq, int Nqp, const void *params, const int32_t *uid,
+                   unsigned long long seed, int sample_offset, void *q_raw, uint8_t *status, uint8_t *iters,
+                   unsigned long long *counters, cudaStream_t st);
+  int (*ik_solve_batch)(const HostChain &, long long P, const void *targets, void *q, uint8_t *status, uint8_t *iters,
+                        void *resid, unsigned long long *counters, cudaStream_t st);
+  int (*valid_edge_batch)(const HostChain &, long long P, const void *qa, const void *qb, const void *wa, const void *wb,
+                          double epsilon, uint8_t *valid, int32_t *info, unsigned long long *counters, cudaStream_t st);
+  int (*edges_build)(const HostChain &, long long E, const int32_t *wedges, const void *params, const void *q_kept,
+                     const int32_t *count, const int32_t *old_count, int Nq, int Nqp, double epsilon, uint32_t *mask,
+                     uint32_t *edge_stats, unsigned long long *counters, cudaStream_t st);
+};
+
+const Ops *ops_f32_m3();
+const Ops *ops_f32_m6();
+const Ops *ops_f64_m3();
+const Ops *ops_f64_m6();
+
+}  // namespace grr

@@ -1,0 +1,462 @@
+"""RedundancyResolver -- host-side mirror of the reference's roadmap builder (grr/solver.py:210-982)
+for the stage the B200 kernels replace: configuration sampling and the basic solver's all-pairs
+C-space edge construction.
+
+The roadmap lives on the device:
+    Q      [Nw][n][Nqp]      kept configurations, node-blocked SoA (chain coordinates)
+    count  [Nw]              configurations per workspace node
+    mask   [E][Nq][W] u32    per workspace edge (iw<jw) an Nq x Nq bitmask: bit (iq,jq) <=> C-space edge
+and `Gw.node[i]['qlist']` / `Gw.edge[i][j]['qlist']` are lazy views in the reference's format
+(list of full configs / set of (iq,jq), solver.py:267-270,458).
+
+Deviation, stated once: the reference's sampleConfigurationSpace seeds part of each node's samples
+from lower-numbered neighbours in a sequential Gauss-Seidel sweep driven by Python's unseeded global
+`random` (solver.py:773-815).  The device path draws every start from a counter-based Philox stream
+keyed by (node, sample) -- the semantics of the reference's own order-independent
+parallelQSamplingAtP (solver.py:875-897) -- so that CPU oracle and GPU see identical seeds.
+Visibility-graph / self-motion options are out of scope and raise NotImplementedError.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import _cabi
+from .graph import DEFAULT_EDGE_CHECK_TOLERANCE
+
+DEDUP_THRESHOLD = 1e-2      # solver.py:805,827,889
+
+
+class _NodeView(dict):
+    """Gw.node[i]: {'params': [...], 'qlist': lazily materialised list of full configs}."""
+
+    def __init__(self, rr, i):
+        dict.__init__(self)
+        self._rr, self._i = rr, i
+        dict.__setitem__(self, "params", rr.resolution.Gw.node[i]["params"])
+
+    def __getitem__(self, k):
+        if k == "qlist":
+            return self._rr._node_qlist(self._i)
+        return dict.__getitem__(self, k)
+
+    def get(self, k, default=None):
+        if k == "qlist":
+            return self._rr._node_qlist(self._i)
+        return dict.get(self, k, default)
+
+    def __contains__(self, k):
+        return k == "qlist" or dict.__contains__(self, k)
+
+
+class _EdgeView(dict):
+    def __init__(self, rr, e):
+        dict.__init__(self)
+        self._rr, self._e = rr, e
+
+    def __getitem__(self, k):
+        if k == "qlist":
+            return self._rr._edge_qlist(self._e)
+        return dict.__getitem__(self, k)
+
+    def get(self, k, default=None):
+        if k == "qlist":
+            return self._rr._edge_qlist(self._e)
+        return dict.get(self, k, default)
+
+    def __contains__(self, k):
+        return k == "qlist" or dict.__contains__(self, k)
+
+
+class _Index:
+    def __init__(self, fn, n):
+        self._fn, self._n = fn, n
+
+    def __getitem__(self, i):
+        return self._fn(i)
+
+    def __len__(self):
+        return self._n
+
+
+class RoadmapView:
+    """networkx-1.x-flavoured read view of the device roadmap (node / edge / *_iter / neighbors)."""
+
+    def __init__(self, rr):
+        self._rr = rr
+        self._nodes = {}
+        self._edges = {}
+        self.node = _Index(self._node, rr.Nw)
+        self.edge = _Index(lambda i: _Index(lambda j: self._edge(i, j), rr.Nw), rr.Nw)
+
+    def _node(self, i):
+        i = int(i)
+        if i not in self._nodes:
+            if not (0 <= i < self._rr.Nw):
+                raise KeyError(i)
+            self._nodes[i] = _NodeView(self._rr, i)
+        return self._nodes[i]
+
+    def _edge(self, i, j):
+        e = self._rr.edge_index(i, j)
+        if e not in self._edges:
+            self._edges[e] = _EdgeView(self._rr, e)
+        return self._edges[e]
+
+    def number_of_nodes(self):
+        return self._rr.Nw
+
+    def number_of_edges(self):
+        return self._rr.E
+
+    def has_edge(self, i, j):
+        return (min(i, j), max(i, j)) in self._rr._eidx
+
+    def neighbors(self, i):
+        return self._rr.resolution.Gw.neighbors(i)
+
+    def nodes_iter(self, data=False):
+        for i in range(self._rr.Nw):
+            yield (i, self._node(i)) if data else i
+
+    def edges_iter(self, data=False):
+        for e, (i, j) in enumerate(self._rr._edges_host):
+            yield (i, j, self._edge(i, j)) if data else (i, j)
+
+    def nodes(self, data=False):
+        return list(self.nodes_iter(data))
+
+    def edges(self, data=False):
+        return list(self.edges_iter(data))
+
+
+class RedundancyResolver:
+    def __init__(self, resolution, cache=20000, cacheloc=None, seed=0):
+        """`cache` / `cacheloc` are accepted for signature compatibility (solver.py:239); the disk-backed
+        CGraph they configure is replaced by device tensors."""
+        self.resolution = resolution
+        self.robot = resolution.robot
+        self.cachesize = cache
+        self.cacheloc = cacheloc
+        self.seed = int(seed)
+        self.Qsubgraph = dict()
+        self.QccSubgraph = dict()
+        self.stats = {}
+        self.initWorkspaceGraph()
+
+    # ---- device state ---------------------------------------------------------------------------
+    def initWorkspaceGraph(self, clear=False):
+        """solver.py:254-272: copy the workspace graph structure, empty qlists."""
+        res = self.resolution
+        if res.ws_params is None:
+            # graph assembled by hand through addWorkspaceNode/Edge
+            n = res.Gw.number_of_nodes()
+            res.ws_params = np.asarray([res.Gw.node[i]["params"] for i in range(n)], dtype=np.float64).reshape(n, -1)
+            res.ws_edges = np.asarray(sorted((min(i, j), max(i, j)) for i, j in res.Gw.edges_iter()), dtype=np.int64).reshape(-1, 2)
+        self.Nw = int(res.ws_params.shape[0])
+        self.E = int(res.ws_edges.shape[0])
+        self._edges_host = [tuple(e) for e in res.ws_edges.tolist()]
+        self._eidx = {e: k for k, e in enumerate(self._edges_host)}
+        self.node_uid = np.arange(self.Nw, dtype=np.int32)     # RNG key of each node (global id when sharded)
+        self.Nq = 0                  # capacity (configs per node)
+        self.attempts = 0            # IK attempts made so far per node (Philox sample offset)
+        self._dev = None
+        self._qcache = {}
+        self._ecache = {}
+        self.Gw = RoadmapView(self)
+        if clear:
+            res.clearResolution()
+
+    def edge_index(self, iw, jw):
+        key = (min(int(iw), int(jw)), max(int(iw), int(jw)))
+        if key not in self._eidx:
+            raise KeyError("no workspace edge %r" % (key,))
+        return self._eidx[key]
+
+    def _ensure_device(self, Nq):
+        """(Re)allocate device buffers with capacity Nq configs per node, preserving contents."""
+        torch = self.resolution._torch()
+        res = self.resolution
+        dev, dt = res.torch_device, res.torch_dtype
+        n = res.chain.n
+        if self._dev is None:
+            self._dev = {
+                "params": torch.as_tensor(res.ws_params, dtype=dt, device=dev).contiguous(),
+                "uid": torch.as_tensor(self.node_uid, dtype=torch.int32, device=dev),
+                "wedges": torch.as_tensor(res.ws_edges, dtype=torch.int32, device=dev).contiguous(),
+                "count": torch.zeros(self.Nw, dtype=torch.int32, device=dev),
+                "counters": torch.zeros(_cabi.CNT_SLOTS, dtype=torch.int64, device=dev),
+            }
+        d = self._dev
+        if Nq > self.Nq:
+            Nqp, W = _cabi.round_up4(Nq), (Nq + 31) // 32
+            Q = torch.zeros((self.Nw, n, Nqp), dtype=dt, device=dev)
+            mask = torch.zeros((self.E, Nq, W), dtype=torch.int32, device=dev)
+            if self.Nq > 0:
+                Q[:, :, :d["Q"].shape[2]] = d["Q"]
+                mask[:, :self.Nq, :d["mask"].shape[2]] = d["mask"]
+            d["Q"], d["mask"] = Q, mask
+            d["edge_stats"] = torch.zeros((self.E, 2), dtype=torch.int32, device=dev)
+            self.Nq = Nq
+        return d
+
+    def _invalidate(self):
+        self._qcache.clear()
+        self._ecache.clear()
+
+    # ---- views ----------------------------------------------------------------------------------
+    def _node_qlist(self, i):
+        if self._dev is None or self.Nq == 0:
+            return []
+        if i not in self._qcache:
+            c = int(self._dev["count"][i].item())
+            qc = self._dev["Q"][i, :, :c].T.double().cpu().numpy()
+            self._qcache[i] = [[float(v) for v in row] for row in self.resolution.to_full(qc)] if c else []
+        return self._qcache[i]
+
+    def _edge_qlist(self, e):
+        if self._dev is None or self.Nq == 0:
+            return set()
+        if e not in self._ecache:
+            m = self._dev["mask"][e].cpu().numpy().view(np.uint32)
+            bits = np.unpackbits(m.view(np.uint8).reshape(m.shape[0], -1), axis=1, bitorder="little")
+            iq, jq = np.nonzero(bits)
+            self._ecache[e] = set(zip(iq.tolist(), jq.tolist()))
+        return self._ecache[e]
+
+    def counts(self):
+        if self._dev is None:
+            return np.zeros(self.Nw, dtype=np.int32)
+        return self._dev["count"].cpu().numpy()
+
+    def numConfigurations(self):
+        return int(self.counts().sum())
+
+    def numCSpaceEdges(self):
+        if self._dev is None or self.Nq == 0:
+            return 0
+        torch = self.resolution._torch()
+        m = self._dev["mask"].view(torch.uint8)
+        lut = torch.tensor([bin(v).count("1") for v in range(256)], dtype=torch.int64, device=m.device)
+        return int(lut[m.long()].sum().item())
+
+    def edge_lists(self):
+        """All C-space edges as (offsets [E+1], pairs [total,2]) materialised by the compaction kernel."""
+        torch = self.resolution._torch()
+        d = self._dev
+        m8 = d["mask"].view(torch.uint8)
+        lut = torch.tensor([bin(v).count("1") for v in range(256)], dtype=torch.int64, device=m8.device)
+        per_edge = lut[m8.long()].reshape(self.E, -1).sum(dim=1)
+        offsets = torch.zeros(self.E + 1, dtype=torch.int64, device=m8.device)
+        offsets[1:] = torch.cumsum(per_edge, 0)
+        total = int(offsets[-1].item())
+        out = torch.empty((max(total, 1), 2), dtype=torch.int32, device=m8.device)
+        _cabi.edges_compact(d["mask"], self.Nq, offsets, out)
+        return offsets, out[:total]
+
+    # ---- container API (solver.py:435-473) --------------------------------------------------------
+    def addNode(self, iw, q):
+        assert iw < self.Nw
+        torch = self.resolution._torch()
+        c = int(self.counts()[iw])
+        d = self._ensure_device(max(self.Nq, c + 1))
+        qc = torch.as_tensor(self.resolution.to_chain(np.asarray(q)), dtype=d["Q"].dtype, device=d["Q"].device)
+        d["Q"][iw, :, c] = qc
+        d["count"][iw] = c + 1
+        self._invalidate()
+        return c
+
+    def _bit(self, iw, iq, jw, jq):
+        if iw > jw:
+            iw, iq, jw, jq = jw, jq, iw, iq
+        return self.edge_index(iw, jw), int(iq), int(jq)
+
+    def addEdge(self, iw, iq, jw, jq):
+        assert iw != jw, "Can't handle self-motion manifold edges in addEdge"
+        e, a, b = self._bit(iw, iq, jw, jq)
+        cnt = self.counts()
+        ew = self._edges_host[e]
+        assert a < cnt[ew[0]] and b < cnt[ew[1]]
+        d = self._dev
+        bit = (1 << (b % 32))
+        if bit >= 2 ** 31:
+            bit -= 2 ** 32
+        d["mask"][e, a, b // 32] |= bit
+        self._ecache.pop(e, None)
+
+    def hasEdge(self, iw, iq, jw, jq):
+        e, a, b = self._bit(iw, iq, jw, jq)
+        return (a, b) in self._edge_qlist(e)
+
+    def removeEdge(self, iw, iq, jw, jq):
+        assert iw != jw
+        e, a, b = self._bit(iw, iq, jw, jq)
+        assert (a, b) in self._edge_qlist(e)
+        bit = (1 << (b % 32))
+        if bit >= 2 ** 31:
+            bit -= 2 ** 32
+        self._dev["mask"][e, a, b // 32] &= ~bit
+        self._ecache.pop(e, None)
+
+    # ---- sampling (solver.py:757-873, 875-897) ------------------------------------------------------
+    def sampleConfigurationSpace(self, NConfigsPerPoint=100, connect=True, biased=False, seedFromAdjacent=True,
+                                 visibility=False, k=None):
+        """Per workspace node: NConfigsPerPoint random-start IK attempts, greedy 1e-2 dedup against the
+        node's existing configs, then (connect=True) all-pairs edge tests on every workspace edge for the
+        pairs with at least one new endpoint.  Returns (t_sample, t_connect) in seconds (device time)."""
+        if visibility:
+            raise NotImplementedError("visibility-graph solver is out of scope of the B200 roadmap path")
+        torch = self.resolution._torch()
+        old_counts = self._dev["count"].clone() if self._dev is not None and self.Nq > 0 else None
+        start_total = self.numConfigurations()
+        if biased and start_total != 0:
+            raise NotImplementedError("biased re-sampling (solver.py:780-785) is not implemented on the device path")
+        N = int(NConfigsPerPoint)
+        prev_cap = self.Nq
+        d = self._ensure_device(prev_cap + N)
+        res = self.resolution
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        Nqp_raw = _cabi.round_up4(N)
+        q_raw = torch.empty((self.Nw, res.chain.n, Nqp_raw), dtype=res.torch_dtype, device=res.torch_device)
+        status = torch.empty((self.Nw, Nqp_raw), dtype=torch.uint8, device=res.torch_device)
+        iters = torch.empty((self.Nw, Nqp_raw), dtype=torch.uint8, device=res.torch_device)
+        d["counters"].zero_()
+        ev[0].record()
+        res.chain.ik_sample(d["params"], d["uid"], self.seed, q_raw, status, iters, d["counters"], Nq=N,
+                            sample_offset=self.attempts)
+        count_in = d["count"].clone()
+        res.chain.dedup(q_raw, status, DEDUP_THRESHOLD, d["Q"], d["count"], Nq=N, count_in=count_in)
+        ev[1].record()
+        self.attempts += N
+        self._last_raw = (q_raw, status, iters)
+        if connect:
+            res.chain.edges_build(d["wedges"], d["params"], d["Q"], d["count"], self.Nq, DEFAULT_EDGE_CHECK_TOLERANCE,
+                                  d["mask"], d["edge_stats"], d["counters"], old_count=old_counts)
+        ev[2].record()
+        torch.cuda.synchronize(res.torch_device)
+        self._invalidate()
+        t_sample = ev[0].elapsed_time(ev[1]) * 1e-3
+        t_connect = ev[1].elapsed_time(ev[2]) * 1e-3
+        c = d["counters"].cpu().numpy()
+        self.stats = {"ik_solves": int(c[_cabi.CNT_IK_SOLVES]), "ik_iters": int(c[_cabi.CNT_IK_ITERS]),
+                      "ik_evals": int(c[_cabi.CNT_IK_EVALS]), "pairs": int(c[_cabi.CNT_PAIRS]),
+                      "valid": int(c[_cabi.CNT_VALID]), "sampled": self.numConfigurations() - start_total,
+                      "attempts": self.Nw * N, "t_sample": t_sample, "t_connect": t_connect}
+        return t_sample, t_connect
+
+    def parallelQSamplingAtP(self, params, NConfigs=100, selfmotion=True, k=None, uid=None):
+        """solver.py:875-947 for one workspace point: returns (configs, qccs, qcc_parents).  Self-motion
+        manifolds (selfmotion=True) belong to the visibility solver and are out of scope; with
+        selfmotion=False every config is its own component (qccs singletons, parents -1)."""
+        if selfmotion:
+            raise NotImplementedError("self-motion manifold construction is out of scope; pass selfmotion=False")
+        torch = self.resolution._torch()
+        res = self.resolution
+        N = int(NConfigs)
+        Nqp = _cabi.round_up4(N)
+        if uid is None:
+            uid = 0
+        p = res._dev(np.asarray([params], dtype=np.float64))
+        u = torch.tensor([uid], dtype=torch.int32, device=res.torch_device)
+        q_raw = torch.empty((1, res.chain.n, Nqp), dtype=res.torch_dtype, device=res.torch_device)
+        status = torch.empty((1, Nqp), dtype=torch.uint8, device=res.torch_device)
+        res.chain.ik_sample(p, u, self.seed, q_raw, status, None, None, Nq=N)
+        q_kept = torch.zeros_like(q_raw)
+        count = torch.zeros(1, dtype=torch.int32, device=res.torch_device)
+        res.chain.dedup(q_raw, status, DEDUP_THRESHOLD, q_kept, count, Nq=N)
+        c = int(count.item())
+        configs = [[float(v) for v in row] for row in res.to_full(q_kept[0, :, :c].T.double().cpu().numpy())] if c else []
+        return configs, [[i] for i in range(c)], [-1] * c
+
+    # ---- connection (solver.py:484-501, 689-755) ---------------------------------------------------
+    def testAndConnect(self, iw, iq, jw, jq):
+        if iw > jw:
+            return self.testAndConnect(jw, jq, iw, iq)
+        cnt = self.counts()
+        assert 0 <= iq < cnt[iw]
+        assert 0 <= jq < cnt[jw]
+        assert self.Gw.has_edge(iw, jw)
+        if self.hasEdge(iw, iq, jw, jq):
+            return True
+        a = self._node_qlist(iw)[iq]
+        b = self._node_qlist(jw)[jq]
+        res = self.resolution
+        if res.validEdge(a, b, res.Gw.node[iw]["params"], res.Gw.node[jw]["params"]):
+            self.addEdge(iw, iq, jw, jq)
+            return True
+        return False
+
+    def testAndConnectAll(self, iw, jw):
+        return self.connectConfigurationSpaceOnEdge(iw, jw) > 0
+
+    def _connect(self, edge_ids, old_counts):
+        torch = self.resolution._torch()
+        res = self.resolution
+        d = self._dev
+        if d is None or self.Nq == 0:
+            return np.zeros((len(edge_ids), 2), dtype=np.int64)
+        eid = torch.as_tensor(np.asarray(edge_ids, dtype=np.int64), device=res.torch_device)
+        wedges = d["wedges"][eid].contiguous()
+        sub_mask = d["mask"][eid].contiguous()
+        stats = torch.zeros((len(edge_ids), 2), dtype=torch.int32, device=res.torch_device)
+        oc = None
+        if old_counts is not None:
+            oc = torch.as_tensor(np.asarray(old_counts, dtype=np.int32), device=res.torch_device)
+        res.chain.edges_build(wedges, d["params"], d["Q"], d["count"], self.Nq, DEFAULT_EDGE_CHECK_TOLERANCE,
+                              sub_mask, stats, d["counters"], old_count=oc)
+        d["mask"][eid] = sub_mask
+        for e in edge_ids:
+            self._ecache.pop(int(e), None)
+        return stats.cpu().numpy().astype(np.int64)
+
+    def connectConfigurationSpaceOnEdge(self, iw, jw, istart=0, jstart=0):
+        """solver.py:689-697.  Returns the number of (not both-old) pairs that are connected."""
+        if iw > jw:
+            iw, jw, istart, jstart = jw, iw, jstart, istart
+        e = self.edge_index(iw, jw)
+        old = None
+        if istart or jstart:
+            old = np.zeros(self.Nw, dtype=np.int32)
+            old[iw], old[jw] = istart, jstart
+        before = set(self._edge_qlist(e)) if old is not None else set()
+        self._connect([e], old)
+        after = self._edge_qlist(e)
+        if old is None:
+            return len(after)
+        return sum(1 for (a, b) in after if not (a < istart and b < jstart))
+
+    def connectConfigurationSpace(self, visibility=False, k=None, counts=None):
+        """solver.py:700-755 batch variant over every workspace edge.  Returns
+        (numNondegenerateEdges, numWorkspaceEdges, self_motion_time, inter_wnode_time)."""
+        if visibility:
+            raise NotImplementedError("visibility-graph solver is out of scope of the B200 roadmap path")
+        torch = self.resolution._torch()
+        res = self.resolution
+        d = self._dev
+        if d is None or self.Nq == 0:
+            return 0, self.E, 0, 0.0
+        oc = None
+        if counts is not None:
+            oc = torch.as_tensor(np.asarray(counts, dtype=np.int32), device=res.torch_device)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        d["counters"].zero_()
+        e0.record()
+        res.chain.edges_build(d["wedges"], d["params"], d["Q"], d["count"], self.Nq, DEFAULT_EDGE_CHECK_TOLERANCE,
+                              d["mask"], d["edge_stats"], d["counters"], old_count=oc)
+        e1.record()
+        torch.cuda.synchronize(res.torch_device)
+        self._ecache.clear()
+        m8 = d["mask"].view(torch.uint8).reshape(self.E, -1)
+        nondeg = int((m8 != 0).any(dim=1).sum().item())
+        c = d["counters"].cpu().numpy()
+        self.stats.update({"pairs": int(c[_cabi.CNT_PAIRS]), "valid": int(c[_cabi.CNT_VALID]),
+                           "edge_ik_solves": int(c[_cabi.CNT_IK_SOLVES]), "edge_ik_iters": int(c[_cabi.CNT_IK_ITERS]),
+                           "edge_ik_evals": int(c[_cabi.CNT_IK_EVALS])})
+        return nondeg, self.E, 0, e0.elapsed_time(e1) * 1e-3
+
+    # ---- sanity (solver.py:365-383) -------------------------------------------------------------------
+    def sanityCheck(self):
+        cnt = self.counts()
+        for e, (iw, jw) in enumerate(self._edges_host):
+            for (a, b) in self._edge_qlist(e):
+                assert a < cnt[iw] and b < cnt[jw], "edge qlist index out of range on workspace edge %d-%d" % (iw, jw)
+        return True

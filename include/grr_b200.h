@@ -1,0 +1,157 @@
+/*
+ * grr_b200.h -- C ABI of libgrr_b200.so: the B200 (sm_100a) roadmap-construction hot path of
+ * GlobalRedundancyResolution (per-workspace-node IK configuration sampling + the basic solver's
+ * all-pairs C-space edge construction).
+ *
+ * The reference (krishauser/GlobalRedundancyResolution) has no FFI / plugin interface: the path
+ * sits behind Python methods that call Klamp't/IKDB one instance at a time.  Each entry point
+ * below states the reference interface (file:line under the reference root) it replaces.  The
+ * Python classes in globalredundancyresolution_b200/{graph,solver}.py keep the reference's method
+ * names and call these through ctypes (see INTEGRATION.md for the binding a maintainer would add
+ * to the reference itself).
+ *
+ * Conventions
+ *   - every function returns 0 on success, <0 on error; grr_last_error() gives the message
+ *     (thread-local).  Nothing throws.
+ *   - all array arguments marked [dev] are caller-owned DEVICE pointers (e.g. torch tensors'
+ *     data_ptr()); [host] are host pointers.  `stream` is a cudaStream_t (0 = default stream).
+ *     Calls are asynchronous on `stream` unless stated otherwise.
+ *   - `dtype` selects the arithmetic type of the path and of every "Real" buffer:
+ *     GRR_F32 (the product path, FP32 SIMT) or GRR_F64 (verification build of the same kernels).
+ *   - rotation matrices are ROW-major 3x3.
+ *   - config storage ("node-blocked SoA"): Q[node][dof][Nqp], Nqp = Nq rounded up to a multiple
+ *     of 4; a node's block is one contiguous n*Nqp chunk (one bulk copy into shared memory, one
+ *     message in the halo exchange).  Batches of unrelated configs use plain SoA q[dof][P].
+ *   - workspace parameters: params[node][dw], dw = 3 (free, fixed) or 6 (variable: position +
+ *     rotation moment), as produced by sampleWorkspace (grr/graph.py:1110-1123,1151-1164).
+ */
+#ifndef GRR_B200_H_
+#define GRR_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GRR_MAX_JOINTS 32
+
+enum { GRR_F32 = 0, GRR_F64 = 1 };
+enum { GRR_FREE = 0, GRR_FIXED = 1, GRR_VARIABLE = 2 };          /* IKTask orientation, graph.py:59-74 */
+enum { GRR_IK_OK = 0, GRR_IK_STALL = 1, GRR_IK_CONVX = 2, GRR_IK_MAXIT = 3, GRR_IK_SKIPPED = 255 };
+
+typedef struct grr_handle_s *grr_handle_t;
+
+/* Serial kinematic chain from the robot base to the goal link with inactive links folded into
+ * the constant transforms; replaces the Klamp't RobotModel + IKObjective + IKDB IKProblem /
+ * IKSolverParams objects built in grr/graph.py:494-509,518-640. */
+typedef struct {
+  int32_t n;            /* active revolute joints, 1..GRR_MAX_JOINTS                              */
+  int32_t mode;         /* GRR_FREE / GRR_FIXED / GRR_VARIABLE                                    */
+  int32_t nlinks_eps;   /* "nlinks" of validEdgeLinear, graph.py:944                              */
+  int32_t max_iters;    /* IKSolverParams.numIters                                                */
+  double tol;           /* IKSolverParams.tol                                                     */
+  double lambda;        /* Newton damping                                                         */
+  const double *Rp;     /* [host] [n][9] constant rotation preceding joint j                       */
+  const double *tp;     /* [host] [n][3] constant translation preceding joint j                    */
+  const double *axis;   /* [host] [n][3] unit joint axis, local                                    */
+  const double *qmin;   /* [host] [n]                                                              */
+  const double *qmax;   /* [host] [n]                                                              */
+  double ee_local[3];   /* constrained point in the last active joint's frame (graph.py:60,65,72)  */
+  double R_tail[9];     /* goal-link frame relative to the last active joint's frame               */
+  double R_goal[9];     /* fixed orientation goal (graph.py:71), ignored unless mode==GRR_FIXED    */
+} grr_chain_desc;
+
+/* Counters accumulated (atomically) by the kernels; layout of the `counters` arguments. */
+enum {
+  GRR_CNT_IK_SOLVES = 0,   /* IK instances run                                  */
+  GRR_CNT_IK_ITERS = 1,    /* Newton iterations                                 */
+  GRR_CNT_IK_EVALS = 2,    /* FK/residual(+Jacobian) passes                     */
+  GRR_CNT_PAIRS = 3,       /* validEdge calls (pair tests)                      */
+  GRR_CNT_VALID = 4,       /* pair tests that returned True                     */
+  GRR_CNT_IK_OK = 5,       /* IK instances that converged                       */
+  GRR_CNT_SLOTS = 8        /* length of a counters array (uint64)               */
+};
+
+const char *grr_last_error(void);
+int grr_abi_version(void);
+
+/* -- chain / task ------------------------------------------------------------------------- */
+/* replaces RedundancyResolutionGraph.__init__ + readJsonSetup (graph.py:494-509,518-640) */
+int grr_chain_create(const grr_chain_desc *desc, int device, grr_handle_t *out);
+int grr_chain_destroy(grr_handle_t h);
+/* replaces IKTask.__init__ orientation selection (graph.py:59-80); R_goal9 may be NULL */
+int grr_task_set(grr_handle_t h, int mode, const double *R_goal9);
+int grr_chain_num_joints(grr_handle_t h);
+
+/* -- K: forward kinematics (Klamp't robot.setConfig + link.getTransform; graph.py:747-756,887-893)
+ * q [dev] Real [n][P]; out_p [dev] Real [P][3]; out_R [dev] Real [P][9] (may be NULL). */
+int grr_fk_batch(grr_handle_t h, int dtype, int64_t P, const void *q, void *out_p, void *out_R, void *stream);
+
+/* -- V2/K3/K4: seeded IK solves (RedundancyResolutionGraph.solve, graph.py:779-790 ->
+ * ikTemplate.solve).  targets [dev] Real [P][dw]; q [dev] Real [n][P] in: seeds, out: result;
+ * status [dev] u8 [P]; iters [dev] u8 [P] (nullable); resid [dev] Real [P] max|F| (nullable);
+ * counters [dev] u64[GRR_CNT_SLOTS] (nullable). */
+int grr_ik_solve_batch(grr_handle_t h, int dtype, int64_t P, const void *targets, void *q, uint8_t *status,
+                       uint8_t *iters, void *resid, uint64_t *counters, void *stream);
+
+/* -- S2: per-node random-start sampling (parallelQSamplingAtP, solver.py:875-885; the random
+ * phase of sampleConfigurationSpace, solver.py:817-821).  For node i, sample s: seed drawn from
+ * Philox4x32-10(key=seed, ctr=(node_uid[i], s, dof/4, 0)) uniformly in [qmin,qmax], then one IK
+ * solve toward params[i].  q_raw [dev] Real [Nw][n][Nqp]; status/iters [dev] u8 [Nw][Nqp]
+ * (iters nullable); counters nullable.  sample_offset shifts s (incremental growth). */
+int grr_ik_sample(grr_handle_t h, int dtype, int64_t Nw, int32_t Nq, int32_t Nqp, const void *params,
+                  const int32_t *node_uid, uint64_t seed, int32_t sample_offset, void *q_raw,
+                  uint8_t *status, uint8_t *iters, uint64_t *counters, void *stream);
+
+/* -- S3: greedy first-wins duplicate filter (solver.py:802-813,824-835,886-897).  Keeps sample s
+ * iff status==OK and distance to every previously kept config of the node >= thresh.  Existing
+ * configs (count_in[i] of them already at the front of q_kept's block; count_in nullable = 0)
+ * take part in the test.  q_kept [dev] Real [Nw][n][Nqp_kept]; keep_idx [dev] i32 [Nw][Nq] (sample
+ * index of each newly kept config, nullable); count [dev] i32 [Nw] out (total kept, capped at
+ * Nqp_kept). */
+int grr_dedup(grr_handle_t h, int dtype, int64_t Nw, int32_t Nq, int32_t Nqp, const void *q_raw,
+              const uint8_t *status, double thresh, int32_t Nqp_kept, void *q_kept, const int32_t *count_in,
+              int32_t *keep_idx, int32_t *count, void *stream);
+
+/* -- E1/E3 + V1: all-pairs edge construction (connectConfigurationSpace ->
+ * connectConfigurationSpaceOnEdge -> testAndConnect -> validEdgeLinear; solver.py:700-755,689-697,
+ * 484-501; graph.py:938-1006).  For every workspace edge e=(iw,jw), iw<jw, and every pair
+ * (a<count[iw], b<count[jw]) not both older than old_count (nullable), runs the validEdge
+ * predicate and sets bit b of mask[e][a][b/32].  mask [dev] u32 [E][Nq][W], W=(Nq+31)/32, is
+ * fully overwritten for the edges given.  edge_stats [dev] u32 [E][2] = {pairs tested, valid}
+ * (nullable); counters nullable. */
+int grr_edges_build(grr_handle_t h, int dtype, int64_t E, const int32_t *wedges, const void *params,
+                    const void *q_kept, const int32_t *count, const int32_t *old_count, int32_t Nq,
+                    int32_t Nqp, double epsilon, uint32_t *mask, uint32_t *edge_stats, uint64_t *counters,
+                    void *stream);
+
+/* Materialise (iq,jq) lists from the bitmask (the Gw.edge[iw][jw]['qlist'] sets, solver.py:458).
+ * offsets [dev] i64 [E+1] = exclusive scan of edge_stats[:,1] (caller computes); out [dev] i32
+ * [total][2] (iq,jq) in row-major pair order. */
+int grr_edges_compact(int64_t E, int32_t Nq, const uint32_t *mask, const int64_t *offsets, int32_t *out,
+                      void *stream);
+
+/* -- V1 on explicit pairs (RedundancyResolutionGraph.validEdge, graph.py:1051-1053; backs
+ * testAndConnect and the worker's 'test' / 'test-multi' tasks, solver.py:2386-2397).
+ * qa,qb [dev] Real [n][P]; wa,wb [dev] Real [P][dw]; valid [dev] u8 [P];
+ * info [dev] i32 [P][4] = {Ndivs, ik solves run, fail kind (0 none,1 IK,2 leaf distance), iters} nullable */
+int grr_valid_edge_batch(grr_handle_t h, int dtype, int64_t P, const void *qa, const void *qb, const void *wa,
+                         const void *wb, double epsilon, uint8_t *valid, int32_t *info, uint64_t *counters,
+                         void *stream);
+
+/* -- halo exchange support (multi-GPU): gather / scatter whole node blocks so that
+ * the boundary nodes' (count, Q) travel as one contiguous NCCL message per peer.
+ * idx [dev] i32 [K] node indices; packed [dev] Real [K][n][Nqp]. */
+int grr_gather_node_blocks(int dtype, int64_t K, const int32_t *idx, int32_t n, int32_t Nqp, const void *q,
+                           const int32_t *count, void *packed, int32_t *packed_count, void *stream);
+int grr_scatter_node_blocks(int dtype, int64_t K, const int32_t *idx, int32_t n, int32_t Nqp, const void *packed,
+                            const int32_t *packed_count, void *q, int32_t *count, void *stream);
+
+/* -- measurement support: FP32 FMA peak microbenchmark (returns achieved TFLOP/s; synchronous). */
+int grr_fp32_peak(int device, double *tflops_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GRR_B200_H_ */

@@ -1,0 +1,113 @@
+"""Host-side logic that needs no GPU: problem files, options, so3 parsing, .rob round trip, API errors."""
+import math
+import os
+
+import numpy as np
+import pytest
+
+import globalredundancyresolution_b200 as grr
+from globalredundancyresolution_b200 import problems, so3
+from globalredundancyresolution_b200.workspace import Graph
+
+
+def test_parse_orientation_without_eval():
+    R = so3.parse_orientation("so3.rotation([0,1,0],math.pi)")          # problems/baxter/Rdown.json:8
+    np.testing.assert_allclose(so3.matrix(R), np.diag([-1.0, 1.0, -1.0]), atol=1e-12)
+    R = so3.parse_orientation("so3.rotation([0,0,1], -math.pi/2)")
+    np.testing.assert_allclose(so3.apply(R, [1, 0, 0]), [0, -1, 0], atol=1e-12)
+    for bad in ("__import__('os').system('true')", "open('x')", "so3.rotation.__class__", "math.exp(1)"):
+        with pytest.raises((ValueError, SyntaxError)):
+            so3.parse_orientation(bad)
+
+
+def test_so3_column_major_convention():
+    R = so3.rotation([0, 0, 1], math.pi / 2)
+    # column-major: first column is the image of x = (0,1,0)
+    np.testing.assert_allclose(R[:3], [0, 1, 0], atol=1e-12)
+    np.testing.assert_allclose(so3.mul(R, so3.inv(R)), so3.identity(), atol=1e-12)
+    m = so3.moment(R)
+    np.testing.assert_allclose(m, [0, 0, math.pi / 2], atol=1e-12)
+    assert abs(so3.distance(so3.identity(), R) - math.pi / 2) < 1e-12
+
+
+def test_rob_roundtrip_and_reference_layout(tmp_path):
+    for n in (2, 3, 5, 10, 20):
+        r = grr.planar_robot(n)
+        p = tmp_path / ("planar_%dR.rob" % n)
+        p.write_text(r.to_rob())
+        r2 = grr.RobotChain.from_rob(str(p))
+        assert r2.numLinks() == n
+        np.testing.assert_array_equal(r2.tparent, r.tparent)
+        np.testing.assert_array_equal(r2.axis, r.axis)
+        np.testing.assert_array_equal(r2.qmin, r.qmin)
+    # the layout of the reference's own files (line continuations, tabs, comments, quoted geometry)
+    txt = ("### A 2R planar robot ###\nTParent 1 0 0   0 1 0   0 0 1   0 0 0     \\\n1 0 0   0 1 0   0 0 1   1 0 0\n"
+           "axis\t0 1 0\t0 1 0\njointtype\tr r\n#qMin\t-9 -9\nqMin\t-3 -3\nqMax\t3 3\nq\t0 0\n"
+           "geometry\t \"objects/thincube.tri\"  \"objects/thincube.tri\"\nmass\t1 1\nautomass\njoint normal 0\njoint normal 1\n")
+    r = grr.RobotChain.from_rob(txt)
+    assert r.numLinks() == 2 and r.qmin[0] == -3 and r.tparent[1, 0] == 1.0 and r.joint_kind == ["normal", "normal"]
+
+
+def test_problem_options_and_overrides():
+    pdef = problems.read_options("planar_20R", "Rfree.json", problems.parse_overrides(["Nq=100", "workspace_graph=grid", "Nw=500"]))
+    assert pdef["Nq"] == 100 and pdef["workspace_graph"] == "grid" and pdef["Nw"] == 500
+    assert pdef["eelocal"] == [0.1, 0, 0]
+    pdef = problems.read_options("planar_3R")
+    assert pdef["Nq"] == 100 and pdef["workspace_graph"] == "staggered_grid"      # defaults
+    with pytest.raises(ValueError):
+        problems.parse_overrides(["useCollision=False"])                           # JSON-only (visualization.py:590)
+
+
+def test_read_json_setup_semantics():
+    robot = grr.synthetic_arm("baxter")
+    res = grr.RedundancyResolutionGraph(robot)
+    pdef = problems.read_options("baxter", "Rdown.json")
+    res.readJsonSetup(pdef)
+    assert res.chain.n == 7 and res.chain.mode == 1 and res.chain.nlinks_eps == 7
+    assert res.ikTaskSpace[0].numConstraints == 3
+    # default useCollision=True is refused, explicitly ignorable
+    p2 = dict(pdef); p2.pop("useCollision")
+    with pytest.raises(NotImplementedError, match="useCollision"):
+        grr.RedundancyResolutionGraph(robot).readJsonSetup(p2)
+    grr.RedundancyResolutionGraph(robot).readJsonSetup(p2, ignore_collision=True)
+    # without `links`: all movable ancestors are active and nlinks = numLinks (graph.py:944)
+    p3 = dict(pdef); p3.pop("links")
+    r3 = grr.RedundancyResolutionGraph(robot); r3.readJsonSetup(p3)
+    assert r3.chain.n == 8 and r3.chain.nlinks_eps == robot.numLinks()
+    # variable orientation extends a 3-D domain to 6-D with the reference's [-pi,-pi] quirk (graph.py:635)
+    p4 = dict(pdef); p4["orientation"] = "variable"; p4.pop("fixedOrientation")
+    r4 = grr.RedundancyResolutionGraph(robot); r4.readJsonSetup(p4)
+    assert len(r4.domain[0]) == 6 and r4.domain[0][3:] == [-math.pi] * 3 and r4.domain[1][3:] == [-math.pi] * 3
+    assert r4.ikTaskSpace[0].numConstraints == 6 and r4.chain.dw == 6
+    with pytest.raises(ValueError):
+        p5 = dict(pdef); p5["orientation"] = "sideways"
+        grr.RedundancyResolutionGraph(robot).readJsonSetup(p5)
+    with pytest.raises(AssertionError):
+        p6 = dict(pdef); p6["link"] = "no_such_link"
+        grr.RedundancyResolutionGraph(robot).readJsonSetup(p6)
+
+
+def test_make_program_builds_reference_sized_graphs():
+    pdef, res, rr = grr.make_program("planar_3R", "baseline_cfg1.json")
+    assert (rr.Nw, rr.E) == (1024, 1984)
+    assert rr.Gw.number_of_nodes() == 1024 and rr.Gw.number_of_edges() == 1984
+    assert rr.numConfigurations() == 0 and rr.numCSpaceEdges() == 0
+    assert rr.Gw.node[5]["qlist"] == [] and rr.Gw.edge[0][1]["qlist"] == set()
+    assert rr.Gw.node[5]["params"] == res.Gw.node[5]["params"]
+    with pytest.raises(KeyError):
+        rr.Gw.edge[0][500]
+    with pytest.raises(NotImplementedError):
+        rr.sampleConfigurationSpace(4, visibility=True)
+    with pytest.raises(NotImplementedError):
+        rr.parallelQSamplingAtP([1, 0, 1], 4)          # selfmotion=True default -> out of scope
+
+
+def test_graph_class_is_networkx1_flavoured():
+    G = Graph()
+    G.add_node(0, params=[1]); G.add_node(1); G.add_edge(0, 1, qlist=set()); G.add_edge(1, 2)
+    assert G.number_of_nodes() == 3 and G.number_of_edges() == 2
+    assert G.edge[0][1] is G.edge[1][0]
+    assert sorted(G.edges_iter()) == [(0, 1), (1, 2)]
+    assert [n for n, d in G.nodes_iter(data=True)] == [0, 1, 2]
+    G.remove_edge(0, 1)
+    assert not G.has_edge(1, 0)
