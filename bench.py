@@ -1,0 +1,348 @@
+#!/usr/bin/env python
+"""bench.py -- roadmap-construction throughput on B200 (BASELINE.json metric).
+
+A "step" is one full pass of the hot path over one synthetic workspace graph: Nw*Nq random-start IK
+solves (sampling) + greedy dedup + the basic solver's all-pairs C-space edge construction over every
+workspace edge.  Default workload = BASELINE config 2 (planar_20R, staggered_grid, Nw=10000, Nq=100),
+the configuration the metric is quoted on; it fits one GPU.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--nw NW] [--nq NQ] [--problem P/J]
+
+value   = C-space pair tests (validEdge calls) per second over the K timed steps, inputs resident in HBM
+e2e     = same metric through the reference-facing API (problem -> RedundancyResolver ->
+          sampleConfigurationSpace) with HOST buffers: workspace params / edges / node ids are copied
+          host->device and kept configs, counts and edge bitmasks device->host inside the timed region
+roofline= counted algorithmic FP32 flops of the edge kernel / its CUDA-event duration, against the FP32
+          FMA peak measured in the same run (MEASURED_PEAKS.json has no FP32 SIMT figure)
+cpu_baseline = the CPU oracle (oracle/, a port: the reference cannot run here) on a bounded sample of the
+          same workload on all host threads
+With N > 1 (torchrun, one rank per GPU) the workspace grid is sharded by node ranges, boundary nodes'
+config blocks are exchanged over NCCL, every rank builds the edges it owns; value = all ranks' pair tests
+/ max-over-ranks time ("weak" is not claimed: the graph is fixed, so scaling is "strong").
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "IK configs/s + C-space edges tested/s (planar_20R, Jaco) at 1/2/4/8 B200"
+UNIT = "C-space edges tested/s"
+
+
+def flops_model(n, m, iters, evals, pairs, leaf_dists):
+    """SURVEY 8(d) algorithmic work model."""
+    f_fk = 108 * n + 18
+    f_jac = 30 * n + (18 * n if m == 6 else 0)
+    f_res = 3 + (60 if m == 6 else 0)
+    f_solve = m * (m + 1) * n + 2 * m * n + m ** 3 / 3.0 + 2 * m * m
+    return iters * (f_jac + f_solve) + evals * (f_fk + f_res) + pairs * (3 * n + 2) + leaf_dists * 3 * n
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        # under load = upper half of the samples
+        sm_sorted = sorted(sm)
+        load = sm_sorted[len(sm_sorted) // 2:] if sm_sorted else []
+        return {"sm_mhz": float(np.median(load)) if load else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def problem_setup(args):
+    import globalredundancyresolution_b200 as grr
+    name, jf = args.problem.split("/")
+    over = {}
+    if args.nw:
+        over["Nw"] = args.nw
+    if args.nq:
+        over["Nq"] = args.nq
+    pdef = grr.problems.read_options(name, jf, over)
+    return grr, name, jf, over, pdef
+
+
+def workload_name(pdef, Nw, E):
+    return "%s %s Nw=%d (-> %d nodes, %d workspace edges) Nq=%d orientation=%s useCollision=false" % (
+        os.path.basename(pdef["filename"]).replace(".rob", ""), pdef["workspace_graph"], pdef["Nw"], Nw, E, pdef["Nq"],
+        pdef.get("orientation", "free"))
+
+
+# --------------------------------------------------------------------------------------------------
+# reference arm: the CPU oracle port on a bounded sample, all host threads
+# --------------------------------------------------------------------------------------------------
+def cpu_sample_run(res, o, Nq, seed, n_nodes_target, rng):
+    """One bounded CPU pass: pick a connected patch of workspace nodes, sample them, connect the induced
+    workspace edges.  Returns (attempts, pairs, t_sample, t_connect)."""
+    Nw = res.ws_params.shape[0]
+    start = int(rng.integers(0, max(1, Nw - n_nodes_target)))
+    nodes = np.arange(start, min(Nw, start + n_nodes_target))
+    t0 = time.perf_counter()
+    out = o.sample_nodes(res.ws_params[nodes], nodes.astype(np.int32), Nq, seed, raw=False)
+    t1 = time.perf_counter()
+    e = res.ws_edges
+    sel = (e[:, 0] >= nodes[0]) & (e[:, 1] <= nodes[-1])
+    sub = (e[sel] - nodes[0]).astype(np.int32)
+    _, stats = o.connect_edges(sub, res.ws_params[nodes], out["q_kept"], out["count"], Nq, want_mask=False)
+    t2 = time.perf_counter()
+    return nodes.size * Nq, int(stats[:, 0].sum()), t1 - t0, t2 - t1, int(stats[:, 2].sum())
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from helpers import oracle_for
+    from oracle import oracle as O
+    grr, name, jf, over, pdef = problem_setup(args)
+    pdef2, res = grr.load_problem(name, jf, overrides=over)
+    res.sampleWorkspace(pdef["Nw"], method=pdef["workspace_graph"])
+    o = oracle_for(res)
+    cores = O.num_threads()
+    rng = np.random.default_rng(0)
+    # size the per-step sample: ~ a few seconds of CPU work on this box
+    probe = cpu_sample_run(res, o, pdef["Nq"], 0, 64, rng)
+    per_node = (probe[2] + probe[3]) / 64.0
+    n_nodes = int(max(64, min(res.ws_params.shape[0], args.cpu_seconds / max(per_node, 1e-6))))
+    for _ in range(args.warmup):
+        cpu_sample_run(res, o, pdef["Nq"], 0, max(64, n_nodes // 8), rng)
+    tot_pairs = tot_attempts = 0
+    t_s = t_c = 0.0
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        a, p, ts, tc, _ = cpu_sample_run(res, o, pdef["Nq"], 0, n_nodes, rng)
+        tot_attempts += a; tot_pairs += p; t_s += ts; t_c += tc
+    wall = time.perf_counter() - t0
+    value = tot_pairs / wall
+    sample = "contiguous patch of %d of %d workspace nodes per step (sampling + all induced workspace edges), %d steps" % (
+        n_nodes, res.ws_params.shape[0], args.steps)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * wall / args.steps, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(pdef, res.ws_params.shape[0], res.ws_edges.shape[0]), "seed": 0},
+            "ik_configs_per_s": tot_attempts / max(t_s, 1e-12),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                             "note": "CPU oracle (oracle/grr_oracle.c, OpenMP); the reference itself is Python 2 + Klamp't/IKDB and cannot run here"},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------------
+# CUDA arm
+# --------------------------------------------------------------------------------------------------
+def run_cuda(args):
+    import torch
+    import torch.distributed as dist
+    from globalredundancyresolution_b200 import _cabi
+    from globalredundancyresolution_b200 import sharding
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (there is no CPU fallback; use --impl reference for the CPU baseline)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    grr, name, jf, over, pdef = problem_setup(args)
+    dev = torch.device("cuda", local)
+
+    def make_rr():
+        pd, res = grr.load_problem(name, jf, overrides=over, device=local)
+        res.sampleWorkspace(pd["Nw"], method=pd["workspace_graph"])
+        if world > 1:
+            return res, sharding.ShardedResolver(res, rank, world, seed=0)
+        return res, grr.RedundancyResolver(res, seed=0)
+
+    res, rr = make_rr()
+    Nq = pdef["Nq"]
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def step():
+        rr.initWorkspaceGraph()          # drops the previous roadmap (device buffers are re-used below)
+        flush.fill_(1.0)                 # L2 flush between steps (inside the timed region, ~40 us)
+        return rr.sampleConfigurationSpace(Nq)
+
+    # keep device buffers across steps: initWorkspaceGraph() resets host views only when asked to
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    _cabi.LAUNCHES = 0
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_sample = t_connect = 0.0
+    agg = {"pairs": 0, "valid": 0, "ik_solves": 0, "ik_iters": 0, "ik_evals": 0, "attempts": 0}
+    ev0.record()
+    for _ in range(args.steps):
+        ts, tc = step()
+        t_sample += ts; t_connect += tc
+        for k in agg:
+            agg[k] += rr.stats[k]
+    ev1.record()
+    barrier()
+    launches = _cabi.LAUNCHES
+    clk = clocks.stop() if rank == 0 else None
+    ms = torch.tensor([ev0.elapsed_time(ev1), t_sample * 1e3, t_connect * 1e3], dtype=torch.float64, device=dev)
+    cnts = torch.tensor([agg[k] for k in sorted(agg)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(cnts, op=dist.ReduceOp.SUM)
+    total_ms, ts_ms, tc_ms = [float(v) for v in ms.cpu()]
+    tot = dict(zip(sorted(agg), [float(v) for v in cnts.cpu()]))
+    value = tot["pairs"] / (total_ms * 1e-3)
+
+    # ---- e2e through the public API with host buffers --------------------------------------------
+    barrier()
+    h2d = d2h = 0
+    e0 = time.perf_counter()
+    e2e_pairs = 0
+    for _ in range(args.steps):
+        res2, rr2 = make_rr() if args.e2e_rebuild else (res, rr)
+        rr2.initWorkspaceGraph(drop_device=True)
+        flush.fill_(1.0)
+        rr2.sampleConfigurationSpace(Nq)           # uploads params / edges / ids from host numpy (pinned staging)
+        out = rr2.download()                       # kept configs, counts, edge bitmasks -> host
+        e2e_pairs += rr2.stats["pairs"]
+        h2d, d2h = rr2.h2d_bytes, out["bytes"]
+    barrier()
+    e2e_s = torch.tensor([time.perf_counter() - e0], dtype=torch.float64, device=dev)
+    e2e_p = torch.tensor([float(e2e_pairs)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+        dist.all_reduce(e2e_p, op=dist.ReduceOp.SUM)
+    e2e_value = float(e2e_p.item()) / float(e2e_s.item())
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    n, m = res.chain.n, (3 if res.chain.mode == 0 else 6)
+    # edge-kernel roofline (dominant kernel): counted work of the edge phase / its event time.
+    # sampling's share of the counters is removed with its own attempt count (all sampling solves are
+    # counted in ik_solves; the edge phase's are the rest).
+    peak_tf = _cabi.fp32_peak(local)
+    st = rr.stats
+    edge_flops = flops_model(n, m, st["edge_ik_iters"], st["edge_ik_evals"], st["pairs"], st["edge_ik_solves"] + st["pairs"])
+    edge_s = st["t_connect"]
+    achieved_tf = edge_flops / edge_s / 1e12
+    alg_bytes = (2 * n * Nq * 4 + Nq * ((Nq + 31) // 32) * 4 + 8) * float(rr.E)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    roofline = {"bound": "fp32_simt", "kernel": "k_edges_build", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
+                "frac": achieved_tf / peak_tf, "traffic": None,
+                "peak_source": "FP32 FMA microbenchmark (grr_fp32_peak) measured in this run; MEASURED_PEAKS.json carries no FP32 SIMT figure",
+                "flops_per_launch": edge_flops, "launch_s": edge_s,
+                "hbm": {"achieved": alg_bytes / edge_s / 1e9, "peak": hbm_peak, "unit": "GB/s", "frac": alg_bytes / edge_s / 1e9 / hbm_peak,
+                        "peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback"},
+                "note": "compute-bound path (SURVEY 8d): arithmetic intensity >> ridge; HBM fraction reported as secondary"}
+
+    # ---- CPU baseline beside it (bounded sample, all host threads) ----------------------------------
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        from helpers import oracle_for
+        from oracle import oracle as O
+        o = oracle_for(res)
+        rng = np.random.default_rng(0)
+        probe = cpu_sample_run(res, o, Nq, 0, 64, rng)
+        per_node = (probe[2] + probe[3]) / 64.0
+        n_nodes = int(max(64, min(rr.Nw, args.cpu_seconds / max(per_node, 1e-6))))
+        a, p, ts, tc, _ = cpu_sample_run(res, o, Nq, 0, n_nodes, rng)
+        cpu = {"value": p / (ts + tc), "unit": UNIT, "cores": O.num_threads(), "kind": "port",
+               "sample": "contiguous patch of %d of %d workspace nodes (sampling + induced workspace edges), %.1f s of wall time" % (
+                   n_nodes, rr.Nw, ts + tc),
+               "ik_configs_per_s": a / max(ts, 1e-12), "edges_only_per_s": p / max(tc, 1e-12)}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32 (edge phase) / f64 (sampling)", "data": "synthetic",
+            "config": {"workload": workload_name(pdef, res.ws_params.shape[0], res.ws_edges.shape[0]), "seed": 0,
+                       "l2": "256 MiB flush write between steps, inside the timed region",
+                       "parallelism": "1 GPU" if world == 1 else "workspace nodes sharded over %d ranks + NCCL halo exchange" % world},
+            "ik_configs_per_s": tot["attempts"] / (ts_ms * 1e-3), "edges_tested_per_s_edge_phase_only": tot["pairs"] / (tc_ms * 1e-3),
+            "pairs_per_step": tot["pairs"] / args.steps, "valid_fraction": tot["valid"] / max(tot["pairs"], 1.0),
+            "ik_solves_per_step": tot["ik_solves"] / args.steps, "ik_iters_per_step": tot["ik_iters"] / args.steps,
+            "sample_ms_per_step": ts_ms / args.steps, "connect_ms_per_step": tc_ms / args.steps,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+            "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "cpu_baseline": cpu}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--problem", default="planar_20R/baseline_cfg2.json")
+    ap.add_argument("--nw", type=int, default=0, help="override Nw (profiling runs; reported in config.workload)")
+    ap.add_argument("--nq", type=int, default=0)
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU work per reference step / cpu_baseline sample")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--e2e-rebuild", action="store_true", help="rebuild the problem objects inside the e2e region")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_cuda(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -44,6 +44,7 @@ class ChainDesc(C.Structure):
 
 
 _lib = None
+LAUNCHES = 0      # kernels of this library launched since last reset (bench.py: gpu_launches)
 
 
 def lib():
@@ -82,6 +83,9 @@ def lib():
 
 
 def check(rc, what):
+    global LAUNCHES
+    if what not in ("grr_chain_create", "grr_task_set", "grr_fp32_peak"):
+        LAUNCHES += 1
     if rc != 0:
         raise GrrError("%s failed (%d): %s" % (what, rc, lib().grr_last_error().decode()))
 

@@ -1,0 +1,199 @@
+"""Multi-GPU roadmap construction: one process per GPU, workspace nodes sharded by contiguous id
+ranges, one halo exchange of boundary nodes' config blocks over NCCL, then every rank tests the
+workspace edges it owns.
+
+The reference's own data-parallel path is a multiprocessing master/worker pool that pickles whole
+qlists over OS pipes per task (grr/solver.py:2232-2400).  Here:
+
+  1. sampling   rank r samples nodes [n_r, n_{r+1}) -- node-independent work, identical cost per node,
+                RNG keyed by the GLOBAL node id, so the result does not depend on the world size;
+  2. counts     one all-reduce of the (zero-padded) count vector: every rank knows every node's count;
+  3. edge plan  workspace edges are sorted by (iw, jw); they are cut into `world` contiguous ranges of
+                equal PAIR-TEST load (sum of count[iw]*count[jw], minus both-old pairs) -- a large share
+                of a grid is unreachable, so balancing by node or edge count would not balance work;
+  4. halo       rank r needs the config blocks of the nodes its edge range touches, a contiguous id
+                window; in the node-blocked layout Q[node][dof][Nqp] a node range is ONE contiguous
+                slab, so the exchange is one send/recv per overlapping (owner, user) pair with no
+                pack/unpack kernel (batched isend/irecv -> ncclSend/ncclRecv groups over NVLink);
+  5. edges      rank r builds the bitmasks of its edge range; no collective in the edge phase.
+
+The planning functions below are pure (numpy / torch-on-any-device) and are exercised on CPU with the
+gloo backend in tests/test_sharding.py; the compute calls go through the same C ABI as the 1-GPU path.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import _cabi
+from .solver import RedundancyResolver
+
+
+def node_ranges(Nw, world):
+    """Contiguous, near-equal node ranges: rank r owns [b[r], b[r+1])."""
+    b = [(Nw * r) // world for r in range(world + 1)]
+    return b
+
+
+def owner_of(nodes, bounds):
+    return np.searchsorted(np.asarray(bounds[1:]), nodes, side="right")
+
+
+def edge_ranges(edges, count, world, old_count=None):
+    """Cut the (sorted) workspace edge list into `world` contiguous ranges of near-equal pair-test load.
+    Returns bounds [world+1] into the edge list."""
+    c = np.asarray(count, dtype=np.int64)
+    load = c[edges[:, 0]] * c[edges[:, 1]]
+    if old_count is not None:
+        oc = np.asarray(old_count, dtype=np.int64)
+        load = load - oc[edges[:, 0]] * oc[edges[:, 1]]
+    cum = np.concatenate([[0], np.cumsum(load)])
+    total = cum[-1]
+    if total == 0:
+        return [(edges.shape[0] * r) // world for r in range(world + 1)]
+    targets = [total * r / float(world) for r in range(1, world)]
+    cuts = [int(np.searchsorted(cum, t, side="left")) for t in targets]
+    b = [0] + cuts + [edges.shape[0]]
+    for i in range(1, len(b)):
+        b[i] = max(b[i], b[i - 1])
+    return b
+
+
+def node_window(edges, e0, e1):
+    """Smallest node id window [lo, hi) covering every endpoint of edges[e0:e1]."""
+    if e1 <= e0:
+        return 0, 0
+    sub = edges[e0:e1]
+    return int(sub.min()), int(sub.max()) + 1
+
+
+def halo_plan(nbounds, windows):
+    """For every (owner p, user r) pair with p != r, the node slab [a,b) that p must send to r:
+    the overlap of r's node window with p's owned range.  Returns {(p, r): (a, b)}."""
+    plan = {}
+    world = len(windows)
+    for r, (lo, hi) in enumerate(windows):
+        for p in range(world):
+            if p == r:
+                continue
+            a, b = max(lo, nbounds[p]), min(hi, nbounds[p + 1])
+            if b > a:
+                plan[(p, r)] = (a, b)
+    return plan
+
+
+def exchange_halo(Q, rank, plan, dist):
+    """Execute the halo plan on the node-blocked tensor Q (any device / backend)."""
+    ops, nbytes = [], 0
+    for (p, r), (a, b) in sorted(plan.items()):
+        if p == rank:
+            ops.append(dist.P2POp(dist.isend, Q[a:b], r))
+        elif r == rank:
+            ops.append(dist.P2POp(dist.irecv, Q[a:b], p))
+            nbytes += Q[a:b].numel() * Q.element_size()
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+    return nbytes
+
+
+class ShardedResolver(RedundancyResolver):
+    """RedundancyResolver over `world` ranks.  Every rank keeps full-size node arrays (config 5 is
+    0.56 GB in FP32) but fills only its node window, and holds the bitmasks of its own edge range
+    (`edge_lo`, `edge_hi`).  `gather_masks()` assembles the full roadmap on rank 0."""
+
+    def __init__(self, resolution, rank, world, seed=0, sample_dtype="float64"):
+        self.rank, self.world = int(rank), int(world)
+        self.edge_lo, self.edge_hi = 0, 0
+        self.halo_bytes = 0
+        RedundancyResolver.__init__(self, resolution, seed=seed, sample_dtype=sample_dtype)
+        self.nbounds = node_ranges(self.Nw, self.world)
+
+    def initWorkspaceGraph(self, clear=False, drop_device=False):
+        RedundancyResolver.initWorkspaceGraph(self, clear, drop_device)
+        self.nbounds = node_ranges(self.Nw, getattr(self, "world", 1))
+        self.edge_lo, self.edge_hi = 0, 0
+
+    def _alloc_mask(self, Nq, W):
+        # bitmasks only for the edge range this rank can own at most (allocated lazily per plan)
+        torch = self.resolution._torch()
+        return torch.zeros((0, Nq, W), dtype=torch.int32, device=self.resolution.torch_device)
+
+    def sampleConfigurationSpace(self, NConfigsPerPoint=100, connect=True, biased=False, seedFromAdjacent=True,
+                                 visibility=False, k=None):
+        if visibility:
+            raise NotImplementedError("visibility-graph solver is out of scope of the B200 roadmap path")
+        import torch.distributed as dist
+        torch = self.resolution._torch()
+        res = self.resolution
+        if self.Nq > 0:
+            raise NotImplementedError("incremental growth is single-GPU only in this round")
+        N = int(NConfigsPerPoint)
+        d = self._ensure_device(N)
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        d["counters"].zero_(); d["counters_e"].zero_()
+        lo, hi = self.nbounds[self.rank], self.nbounds[self.rank + 1]
+        ev[0].record()
+        d["count"].zero_()
+        self._sample_phase(d, N, lo, hi)
+        dist.all_reduce(d["count"])                       # every rank learns every node's count
+        ev[1].record()
+        self.attempts += N
+        if connect:
+            cnt = d["count"].cpu().numpy()
+            eb = edge_ranges(res.ws_edges, cnt, self.world)
+            windows = [node_window(res.ws_edges, eb[r], eb[r + 1]) for r in range(self.world)]
+            plan = halo_plan(self.nbounds, windows)
+            self.halo_bytes = exchange_halo(d["Qs"], self.rank, plan, dist)
+            e0, e1 = eb[self.rank], eb[self.rank + 1]
+            self.edge_lo, self.edge_hi = e0, e1
+            W = (self.Nq + 31) // 32
+            d["mask"] = torch.zeros((e1 - e0, self.Nq, W), dtype=torch.int32, device=res.torch_device)
+            d["edge_stats"] = torch.zeros((e1 - e0, 2), dtype=torch.int32, device=res.torch_device)
+            if d["Qs"] is not d["Q"]:
+                wl, wh = windows[self.rank]
+                d["Q"][wl:wh].copy_(d["Qs"][wl:wh])
+            if e1 > e0:
+                res.chain.edges_build(d["wedges"][e0:e1], d["params"], d["Q"], d["count"], self.Nq,
+                                      0.05, d["mask"], d["edge_stats"], d["counters_e"])
+        ev[2].record()
+        torch.cuda.synchronize(res.torch_device)
+        self._invalidate()
+        self._collect_stats(d, ev, N, 0, n_nodes=hi - lo)
+        self.stats["halo_bytes"] = self.halo_bytes
+        self.stats["sampled"] = int(d["count"][lo:hi].sum().item())
+        return self.stats["t_sample"], self.stats["t_connect"]
+
+    def _edge_qlist(self, e):
+        if not (self.edge_lo <= e < self.edge_hi):
+            raise KeyError("workspace edge %d is owned by another rank" % e)
+        if e not in self._ecache:
+            m = self._dev["mask"][e - self.edge_lo].cpu().numpy().view(np.uint32)
+            bits = np.unpackbits(m.view(np.uint8).reshape(m.shape[0], -1), axis=1, bitorder="little")
+            iq, jq = np.nonzero(bits)
+            self._ecache[e] = set(zip(iq.tolist(), jq.tolist()))
+        return self._ecache[e]
+
+    def download(self):
+        torch = self.resolution._torch()
+        d = self._dev
+        lo, hi = self.nbounds[self.rank], self.nbounds[self.rank + 1]
+        out, nbytes = {}, 0
+        for k, t in (("Qs", d["Qs"][lo:hi]), ("count", d["count"][lo:hi]), ("mask", d["mask"])):
+            h = torch.empty(t.shape, dtype=t.dtype, device="cpu", pin_memory=True)
+            h.copy_(t, non_blocking=True)
+            out[k] = h
+            nbytes += t.numel() * t.element_size()
+        torch.cuda.synchronize(self.resolution.torch_device)
+        out = {k: v.numpy() for k, v in out.items()}
+        out["bytes"] = nbytes
+        return out
+
+    def gather_masks(self):
+        """Full [E][Nq][W] bitmask on every rank (all-reduce of zero-padded slices; used by tests / small runs)."""
+        import torch.distributed as dist
+        torch = self.resolution._torch()
+        W = (self.Nq + 31) // 32
+        full = torch.zeros((self.E, self.Nq, W), dtype=torch.int32, device=self.resolution.torch_device)
+        full[self.edge_lo:self.edge_hi] = self._dev["mask"]
+        dist.all_reduce(full)
+        return full

@@ -130,10 +130,16 @@ class RoadmapView:
 
 
 class RedundancyResolver:
-    def __init__(self, resolution, cache=20000, cacheloc=None, seed=0):
+    def __init__(self, resolution, cache=20000, cacheloc=None, seed=0, sample_dtype="float64"):
         """`cache` / `cacheloc` are accepted for signature compatibility (solver.py:239); the disk-backed
-        CGraph they configure is replaced by device tensors."""
+        CGraph they configure is replaced by device tensors.
+
+        Precision: the Nw*Nq random-start sampling solves (<1 % of the work, long Newton runs whose
+        round-off is amplified by up to 50 iterations) run in `sample_dtype` (default float64, so the kept
+        joint values agree with the FP64 reference arithmetic to ~1e-12); the O(D Nw Nq^2) edge phase runs
+        in the resolution's dtype (default float32, the FP32 SIMT product path)."""
         self.resolution = resolution
+        self.sample_dtype = sample_dtype
         self.robot = resolution.robot
         self.cachesize = cache
         self.cacheloc = cacheloc
@@ -144,21 +150,28 @@ class RedundancyResolver:
         self.initWorkspaceGraph()
 
     # ---- device state ---------------------------------------------------------------------------
-    def initWorkspaceGraph(self, clear=False):
-        """solver.py:254-272: copy the workspace graph structure, empty qlists."""
+    def initWorkspaceGraph(self, clear=False, drop_device=False):
+        """solver.py:254-272: copy the workspace graph structure, empty qlists.  The static device copies
+        of the workspace graph (params, node ids, workspace edges) stay resident unless drop_device=True."""
         res = self.resolution
         if res.ws_params is None:
             # graph assembled by hand through addWorkspaceNode/Edge
             n = res.Gw.number_of_nodes()
             res.ws_params = np.asarray([res.Gw.node[i]["params"] for i in range(n)], dtype=np.float64).reshape(n, -1)
             res.ws_edges = np.asarray(sorted((min(i, j), max(i, j)) for i, j in res.Gw.edges_iter()), dtype=np.int64).reshape(-1, 2)
+        same_graph = getattr(self, "_graph_id", None) == (id(res.ws_params), id(res.ws_edges))
         self.Nw = int(res.ws_params.shape[0])
         self.E = int(res.ws_edges.shape[0])
-        self._edges_host = [tuple(e) for e in res.ws_edges.tolist()]
-        self._eidx = {e: k for k, e in enumerate(self._edges_host)}
-        self.node_uid = np.arange(self.Nw, dtype=np.int32)     # RNG key of each node (global id when sharded)
+        if not same_graph:
+            self._edges_host = [tuple(e) for e in res.ws_edges.tolist()]
+            self._eidx = {e: k for k, e in enumerate(self._edges_host)}
+            self.node_uid = np.arange(self.Nw, dtype=np.int32)     # RNG key of each node = global node id
+            self._graph_id = (id(res.ws_params), id(res.ws_edges))
         self.Nq = 0                  # capacity (configs per node)
         self.attempts = 0            # IK attempts made so far per node (Philox sample offset)
+        if drop_device or not same_graph:
+            self._static = None
+            self.h2d_bytes = 0
         self._dev = None
         self._qcache = {}
         self._ecache = {}
@@ -172,6 +185,25 @@ class RedundancyResolver:
             raise KeyError("no workspace edge %r" % (key,))
         return self._eidx[key]
 
+    def _upload(self, arr, dtype):
+        """host numpy -> device through pinned staging memory; counted in h2d_bytes."""
+        torch = self.resolution._torch()
+        t = torch.from_numpy(np.ascontiguousarray(arr)).to(dtype).pin_memory()
+        self.h2d_bytes += t.numel() * t.element_size()
+        return t.to(self.resolution.torch_device, non_blocking=True)
+
+    def _ensure_static(self):
+        torch = self.resolution._torch()
+        res = self.resolution
+        if getattr(self, "_static", None) is None:
+            self.h2d_bytes = 0
+            st = {"params": self._upload(res.ws_params, res.torch_dtype),
+                  "uid": self._upload(self.node_uid, torch.int32),
+                  "wedges": self._upload(res.ws_edges, torch.int32)}
+            st["params_s"] = st["params"] if self._sdt() == res.torch_dtype else self._upload(res.ws_params, self._sdt())
+            self._static = st
+        return self._static
+
     def _ensure_device(self, Nq):
         """(Re)allocate device buffers with capacity Nq configs per node, preserving contents."""
         torch = self.resolution._torch()
@@ -179,25 +211,52 @@ class RedundancyResolver:
         dev, dt = res.torch_device, res.torch_dtype
         n = res.chain.n
         if self._dev is None:
-            self._dev = {
-                "params": torch.as_tensor(res.ws_params, dtype=dt, device=dev).contiguous(),
-                "uid": torch.as_tensor(self.node_uid, dtype=torch.int32, device=dev),
-                "wedges": torch.as_tensor(res.ws_edges, dtype=torch.int32, device=dev).contiguous(),
+            self._dev = dict(self._ensure_static())
+            self._dev.update({
                 "count": torch.zeros(self.Nw, dtype=torch.int32, device=dev),
                 "counters": torch.zeros(_cabi.CNT_SLOTS, dtype=torch.int64, device=dev),
-            }
+                "counters_e": torch.zeros(_cabi.CNT_SLOTS, dtype=torch.int64, device=dev),
+            })
         d = self._dev
         if Nq > self.Nq:
             Nqp, W = _cabi.round_up4(Nq), (Nq + 31) // 32
             Q = torch.zeros((self.Nw, n, Nqp), dtype=dt, device=dev)
-            mask = torch.zeros((self.E, Nq, W), dtype=torch.int32, device=dev)
+            Qs = torch.zeros((self.Nw, n, Nqp), dtype=self._sdt(), device=dev) if self._sdt() != dt else Q
+            mask = self._alloc_mask(Nq, W)
             if self.Nq > 0:
                 Q[:, :, :d["Q"].shape[2]] = d["Q"]
+                if Qs is not Q:
+                    Qs[:, :, :d["Qs"].shape[2]] = d["Qs"]
                 mask[:, :self.Nq, :d["mask"].shape[2]] = d["mask"]
-            d["Q"], d["mask"] = Q, mask
-            d["edge_stats"] = torch.zeros((self.E, 2), dtype=torch.int32, device=dev)
+            d["Q"], d["Qs"], d["mask"] = Q, Qs, mask
+            d["edge_stats"] = torch.zeros((mask.shape[0], 2), dtype=torch.int32, device=dev)
             self.Nq = Nq
         return d
+
+    def _alloc_mask(self, Nq, W):
+        torch = self.resolution._torch()
+        return torch.zeros((self.E, Nq, W), dtype=torch.int32, device=self.resolution.torch_device)
+
+    def download(self):
+        """Device -> host copy of the roadmap (kept configs in sampling precision, counts, edge bitmasks)
+        through pinned buffers.  Returns a dict of numpy arrays plus 'bytes'."""
+        torch = self.resolution._torch()
+        d = self._dev
+        out, nbytes = {}, 0
+        for k in ("Qs", "count", "mask"):
+            t = d[k]
+            h = torch.empty(t.shape, dtype=t.dtype, device="cpu", pin_memory=True)
+            h.copy_(t, non_blocking=True)
+            out[k] = h
+            nbytes += t.numel() * t.element_size()
+        torch.cuda.synchronize(self.resolution.torch_device)
+        out = {k: v.numpy() for k, v in out.items()}
+        out["bytes"] = nbytes
+        return out
+
+    def _sdt(self):
+        import torch
+        return {"float32": torch.float32, "float64": torch.float64}[self.sample_dtype]
 
     def _invalidate(self):
         self._qcache.clear()
@@ -209,7 +268,7 @@ class RedundancyResolver:
             return []
         if i not in self._qcache:
             c = int(self._dev["count"][i].item())
-            qc = self._dev["Q"][i, :, :c].T.double().cpu().numpy()
+            qc = self._dev["Qs"][i, :, :c].T.double().cpu().numpy()
             self._qcache[i] = [[float(v) for v in row] for row in self.resolution.to_full(qc)] if c else []
         return self._qcache[i]
 
@@ -259,8 +318,9 @@ class RedundancyResolver:
         torch = self.resolution._torch()
         c = int(self.counts()[iw])
         d = self._ensure_device(max(self.Nq, c + 1))
-        qc = torch.as_tensor(self.resolution.to_chain(np.asarray(q)), dtype=d["Q"].dtype, device=d["Q"].device)
-        d["Q"][iw, :, c] = qc
+        qc = torch.as_tensor(self.resolution.to_chain(np.asarray(q)), dtype=torch.float64, device=d["Q"].device)
+        d["Qs"][iw, :, c] = qc.to(d["Qs"].dtype)
+        d["Q"][iw, :, c] = qc.to(d["Q"].dtype)
         d["count"][iw] = c + 1
         self._invalidate()
         return c
@@ -298,6 +358,29 @@ class RedundancyResolver:
         self._ecache.pop(e, None)
 
     # ---- sampling (solver.py:757-873, 875-897) ------------------------------------------------------
+    def _sample_phase(self, d, N, lo, hi):
+        """Random-start IK + dedup for workspace nodes [lo,hi) (parallelQSamplingAtP semantics)."""
+        torch = self.resolution._torch()
+        res = self.resolution
+        sdt = self._sdt()
+        Nqp_raw = _cabi.round_up4(N)
+        nn = hi - lo
+        q_raw = torch.empty((nn, res.chain.n, Nqp_raw), dtype=sdt, device=res.torch_device)
+        status = torch.empty((nn, Nqp_raw), dtype=torch.uint8, device=res.torch_device)
+        iters = torch.empty((nn, Nqp_raw), dtype=torch.uint8, device=res.torch_device)
+        res.chain.ik_sample(d["params_s"][lo:hi], d["uid"][lo:hi], self.seed, q_raw, status, iters, d["counters"], Nq=N,
+                            sample_offset=self.attempts)
+        count_in = d["count"][lo:hi].clone()
+        res.chain.dedup(q_raw, status, DEDUP_THRESHOLD, d["Qs"][lo:hi], d["count"][lo:hi], Nq=N, count_in=count_in)
+        self._last_raw = (q_raw, status, iters)
+
+    def _connect_phase(self, d, old_counts):
+        res = self.resolution
+        if d["Qs"] is not d["Q"]:
+            d["Q"].copy_(d["Qs"])            # edge phase reads the kept configs in its own precision
+        res.chain.edges_build(d["wedges"], d["params"], d["Q"], d["count"], self.Nq, DEFAULT_EDGE_CHECK_TOLERANCE,
+                              d["mask"], d["edge_stats"], d["counters_e"], old_count=old_counts)
+
     def sampleConfigurationSpace(self, NConfigsPerPoint=100, connect=True, biased=False, seedFromAdjacent=True,
                                  visibility=False, k=None):
         """Per workspace node: NConfigsPerPoint random-start IK attempts, greedy 1e-2 dedup against the
@@ -307,41 +390,42 @@ class RedundancyResolver:
             raise NotImplementedError("visibility-graph solver is out of scope of the B200 roadmap path")
         torch = self.resolution._torch()
         old_counts = self._dev["count"].clone() if self._dev is not None and self.Nq > 0 else None
-        start_total = self.numConfigurations()
+        start_total = int(old_counts.sum().item()) if old_counts is not None else 0
         if biased and start_total != 0:
             raise NotImplementedError("biased re-sampling (solver.py:780-785) is not implemented on the device path")
         N = int(NConfigsPerPoint)
-        prev_cap = self.Nq
-        d = self._ensure_device(prev_cap + N)
+        d = self._ensure_device(self.Nq + N)
         res = self.resolution
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
-        Nqp_raw = _cabi.round_up4(N)
-        q_raw = torch.empty((self.Nw, res.chain.n, Nqp_raw), dtype=res.torch_dtype, device=res.torch_device)
-        status = torch.empty((self.Nw, Nqp_raw), dtype=torch.uint8, device=res.torch_device)
-        iters = torch.empty((self.Nw, Nqp_raw), dtype=torch.uint8, device=res.torch_device)
         d["counters"].zero_()
+        d["counters_e"].zero_()
         ev[0].record()
-        res.chain.ik_sample(d["params"], d["uid"], self.seed, q_raw, status, iters, d["counters"], Nq=N,
-                            sample_offset=self.attempts)
-        count_in = d["count"].clone()
-        res.chain.dedup(q_raw, status, DEDUP_THRESHOLD, d["Q"], d["count"], Nq=N, count_in=count_in)
+        self._sample_phase(d, N, 0, self.Nw)
         ev[1].record()
         self.attempts += N
-        self._last_raw = (q_raw, status, iters)
         if connect:
-            res.chain.edges_build(d["wedges"], d["params"], d["Q"], d["count"], self.Nq, DEFAULT_EDGE_CHECK_TOLERANCE,
-                                  d["mask"], d["edge_stats"], d["counters"], old_count=old_counts)
+            self._connect_phase(d, old_counts)
         ev[2].record()
         torch.cuda.synchronize(res.torch_device)
         self._invalidate()
+        self._collect_stats(d, ev, N, start_total)
+        return self.stats["t_sample"], self.stats["t_connect"]
+
+    def _collect_stats(self, d, ev, N, start_total, n_nodes=None):
         t_sample = ev[0].elapsed_time(ev[1]) * 1e-3
         t_connect = ev[1].elapsed_time(ev[2]) * 1e-3
         c = d["counters"].cpu().numpy()
-        self.stats = {"ik_solves": int(c[_cabi.CNT_IK_SOLVES]), "ik_iters": int(c[_cabi.CNT_IK_ITERS]),
-                      "ik_evals": int(c[_cabi.CNT_IK_EVALS]), "pairs": int(c[_cabi.CNT_PAIRS]),
-                      "valid": int(c[_cabi.CNT_VALID]), "sampled": self.numConfigurations() - start_total,
-                      "attempts": self.Nw * N, "t_sample": t_sample, "t_connect": t_connect}
-        return t_sample, t_connect
+        ce = d["counters_e"].cpu().numpy()
+        self.stats = {"sample_ik_solves": int(c[_cabi.CNT_IK_SOLVES]), "sample_ik_iters": int(c[_cabi.CNT_IK_ITERS]),
+                      "sample_ik_evals": int(c[_cabi.CNT_IK_EVALS]), "sample_ik_ok": int(c[_cabi.CNT_IK_OK]),
+                      "edge_ik_solves": int(ce[_cabi.CNT_IK_SOLVES]), "edge_ik_iters": int(ce[_cabi.CNT_IK_ITERS]),
+                      "edge_ik_evals": int(ce[_cabi.CNT_IK_EVALS]),
+                      "ik_solves": int(c[_cabi.CNT_IK_SOLVES] + ce[_cabi.CNT_IK_SOLVES]),
+                      "ik_iters": int(c[_cabi.CNT_IK_ITERS] + ce[_cabi.CNT_IK_ITERS]),
+                      "ik_evals": int(c[_cabi.CNT_IK_EVALS] + ce[_cabi.CNT_IK_EVALS]),
+                      "pairs": int(ce[_cabi.CNT_PAIRS]), "valid": int(ce[_cabi.CNT_VALID]),
+                      "sampled": int(d["count"].sum().item()) - start_total,
+                      "attempts": (self.Nw if n_nodes is None else n_nodes) * N, "t_sample": t_sample, "t_connect": t_connect}
 
     def parallelQSamplingAtP(self, params, NConfigs=100, selfmotion=True, k=None, uid=None):
         """solver.py:875-947 for one workspace point: returns (configs, qccs, qcc_parents).  Self-motion
@@ -355,9 +439,9 @@ class RedundancyResolver:
         Nqp = _cabi.round_up4(N)
         if uid is None:
             uid = 0
-        p = res._dev(np.asarray([params], dtype=np.float64))
+        p = res._dev(np.asarray([params], dtype=np.float64), dtype=self._sdt())
         u = torch.tensor([uid], dtype=torch.int32, device=res.torch_device)
-        q_raw = torch.empty((1, res.chain.n, Nqp), dtype=res.torch_dtype, device=res.torch_device)
+        q_raw = torch.empty((1, res.chain.n, Nqp), dtype=self._sdt(), device=res.torch_device)
         status = torch.empty((1, Nqp), dtype=torch.uint8, device=res.torch_device)
         res.chain.ik_sample(p, u, self.seed, q_raw, status, None, None, Nq=N)
         q_kept = torch.zeros_like(q_raw)
@@ -401,8 +485,10 @@ class RedundancyResolver:
         oc = None
         if old_counts is not None:
             oc = torch.as_tensor(np.asarray(old_counts, dtype=np.int32), device=res.torch_device)
+        if d["Qs"] is not d["Q"]:
+            d["Q"].copy_(d["Qs"])
         res.chain.edges_build(wedges, d["params"], d["Q"], d["count"], self.Nq, DEFAULT_EDGE_CHECK_TOLERANCE,
-                              sub_mask, stats, d["counters"], old_count=oc)
+                              sub_mask, stats, d["counters_e"], old_count=oc)
         d["mask"][eid] = sub_mask
         for e in edge_ids:
             self._ecache.pop(int(e), None)
@@ -438,17 +524,16 @@ class RedundancyResolver:
         if counts is not None:
             oc = torch.as_tensor(np.asarray(counts, dtype=np.int32), device=res.torch_device)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        d["counters"].zero_()
+        d["counters_e"].zero_()
         e0.record()
-        res.chain.edges_build(d["wedges"], d["params"], d["Q"], d["count"], self.Nq, DEFAULT_EDGE_CHECK_TOLERANCE,
-                              d["mask"], d["edge_stats"], d["counters"], old_count=oc)
+        self._connect_phase(d, oc)
         e1.record()
         torch.cuda.synchronize(res.torch_device)
         self._ecache.clear()
         m8 = d["mask"].view(torch.uint8).reshape(self.E, -1)
         nondeg = int((m8 != 0).any(dim=1).sum().item())
-        c = d["counters"].cpu().numpy()
-        self.stats.update({"pairs": int(c[_cabi.CNT_PAIRS]), "valid": int(c[_cabi.CNT_VALID]),
+        c = d["counters_e"].cpu().numpy()
+        self.stats.update({"pairs": int(c[_cabi.CNT_PAIRS]), "valid": int(c[_cabi.CNT_VALID]), "t_connect": e0.elapsed_time(e1) * 1e-3,
                            "edge_ik_solves": int(c[_cabi.CNT_IK_SOLVES]), "edge_ik_iters": int(c[_cabi.CNT_IK_ITERS]),
                            "edge_ik_evals": int(c[_cabi.CNT_IK_EVALS])})
         return nondeg, self.E, 0, e0.elapsed_time(e1) * 1e-3

@@ -1,0 +1,297 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on identical inputs.
+
+Tolerances (written here on purpose):
+  * FP64 build of the kernels: same status on >= 99.5 % of IK instances, identical iteration counts,
+    joint values within 1e-8, identical edge masks (<= 1e-3 of pairs may flip) -- this proves the CUDA
+    formulation (backward chain walk, goal-link-frame normal equations, state-machine Newton) is the
+    same algorithm as the oracle's literal restatement.
+  * product path (FP64 sampling, FP32 edge phase): kept joint values within 1e-5 (north_star) of the
+    oracle (observed ~1e-7: they are FP64 results rounded to FP32 storage), identical per-node counts,
+    edge sets bit-exact except pairs counted and reported as borderline: at most 2e-3 of tested pairs.
+  * all-FP32 sampling is characterised (not required to hit 1e-5: up to 50 Newton iterations amplify
+    round-off): converged set equal on >= 97 % of instances, median |dq| < 1e-5.
+"""
+import numpy as np
+import pytest
+
+import globalredundancyresolution_b200 as grr
+from globalredundancyresolution_b200 import _cabi
+from helpers import oracle_for, small_problem, unpack_mask
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+CASES = {
+    "planar_3R_free": ("planar_3R", "baseline_cfg1.json", 100, "grid"),
+    "planar_20R_free": ("planar_20R", "baseline_cfg2.json", 150, "staggered_grid"),
+    "jaco_free": ("jaco", "baseline_cfg3.json", 150, "staggered_grid"),
+    "baxter_fixed": ("baxter", "Rdown.json", 150, "staggered_grid"),
+    "robonaut2_fixed": ("robonaut2", "baseline_cfg5.json", 150, "staggered_grid"),
+    "atlas_free_generic_n": ("atlas", "Rfree.json", 150, "staggered_grid"),
+}
+NQ = 12
+SEED = 5
+
+
+def _raw_vs_oracle(res, dtype):
+    """Run grr_ik_sample in `dtype` and the oracle on the same (node, sample) seeds."""
+    dev = res.torch_device
+    n, Nw = res.chain.n, res.ws_params.shape[0]
+    Nqp = _cabi.round_up4(NQ)
+    params = torch.as_tensor(res.ws_params, dtype=dtype, device=dev).contiguous()
+    uid = torch.arange(Nw, dtype=torch.int32, device=dev)
+    q_raw = torch.zeros((Nw, n, Nqp), dtype=dtype, device=dev)
+    status = torch.zeros((Nw, Nqp), dtype=torch.uint8, device=dev)
+    iters = torch.zeros((Nw, Nqp), dtype=torch.uint8, device=dev)
+    counters = torch.zeros(_cabi.CNT_SLOTS, dtype=torch.int64, device=dev)
+    res.chain.ik_sample(params, uid, SEED, q_raw, status, iters, counters, Nq=NQ)
+    torch.cuda.synchronize()
+    o = oracle_for(res)
+    ref = o.sample_nodes(res.ws_params, np.arange(Nw), NQ, seed=SEED)
+    st = status[:, :NQ].cpu().numpy().astype(np.int32)
+    it = iters[:, :NQ].cpu().numpy().astype(np.int32)
+    q = np.transpose(q_raw[:, :, :NQ].double().cpu().numpy(), (0, 2, 1))
+    c = counters.cpu().numpy()
+    assert c[_cabi.CNT_IK_SOLVES] == Nw * NQ and c[_cabi.CNT_IK_ITERS] == it.sum() and c[_cabi.CNT_IK_OK] == (st == 0).sum()
+    return o, ref, st, it, q
+
+
+@pytest.mark.parametrize("case", list(CASES))
+def test_ik_sample_fp64_matches_oracle(built, case):
+    pdef, res = small_problem(*CASES[case], dtype="float64")
+    o, ref, st, it, q = _raw_vs_oracle(res, torch.float64)
+    agree = (st == ref["status"])
+    assert agree.mean() >= 0.995, "status agreement %.4f" % agree.mean()
+    both = (st == 0) & (ref["status"] == 0)
+    assert both.sum() > 0
+    assert (it[both] == ref["iters"][both]).all()
+    dq = np.abs(q - ref["q_raw"]).max(axis=2)
+    assert dq[both].max() < 1e-8, "max |dq| = %g" % dq[both].max()
+    # every converged config satisfies the reference's invariants
+    lo, hi = res.fold["qmin"], res.fold["qmax"]
+    Q = q[st == 0]
+    assert (Q >= lo - 1e-12).all() and (Q <= hi + 1e-12).all()
+    W = np.repeat(res.ws_params[:, None, :], NQ, axis=1)[st == 0]
+    for k in range(0, Q.shape[0], max(1, Q.shape[0] // 50)):
+        assert np.abs(o.residual(W[k], Q[k])).max() < 1e-3
+
+
+@pytest.mark.parametrize("case", list(CASES))
+def test_ik_sample_fp32_characterised(built, case):
+    pdef, res = small_problem(*CASES[case], dtype="float32")
+    o, ref, st, it, q = _raw_vs_oracle(res, torch.float32)
+    ok_same = ((st == 0) == (ref["status"] == 0))
+    assert ok_same.mean() >= 0.97, "converged-set agreement %.4f" % ok_same.mean()
+    both = (st == 0) & (ref["status"] == 0) & (it == ref["iters"])
+    dq = np.abs(q - ref["q_raw"]).max(axis=2)[both]
+    assert np.median(dq) < 1e-5
+    frac = float((dq > 1e-5).mean())
+    print("\n[%s fp32 sampling] instances=%d both-converged=%d median|dq|=%.2e p99=%.2e max=%.2e frac>1e-5=%.3f"
+          % (case, st.size, both.sum(), np.median(dq), np.quantile(dq, 0.99), dq.max(), frac))
+    # a converged fp32 result is still a solution of the IK problem
+    W = np.repeat(res.ws_params[:, None, :], NQ, axis=1)[st == 0]
+    Q = q[st == 0]
+    for k in range(0, Q.shape[0], max(1, Q.shape[0] // 50)):
+        assert np.abs(o.residual(W[k], Q[k])).max() < 1.05e-3
+
+
+def _classify_mismatches(o, res, q_dev, cnt, mask_dev, mask_ref):
+    """Report borderline classes for pairs whose verdict differs (north_star: 'counted and reported')."""
+    band = ikflip = 0
+    thr = 5e-2 * np.sqrt(o.c.nlinks_eps) * o.c.nlinks_eps
+    for e, a, b in zip(*np.nonzero(mask_dev != mask_ref)):
+        iw, jw = res.ws_edges[e]
+        ok, info = o.valid_edge(q_dev[iw, a], q_dev[jw, b], res.ws_params[iw], res.ws_params[jw], closed=True)
+        if abs(info.max_leaf - thr) / thr < 1e-3 or info.ndivs_margin < 1e-3:
+            band += 1
+        else:
+            ikflip += 1
+    return band, ikflip
+
+
+@pytest.mark.parametrize("case", list(CASES))
+@pytest.mark.parametrize("dtype", ["float64", "float32"])
+def test_roadmap_build_matches_oracle(built, case, dtype):
+    """End to end through RedundancyResolver: sampling (FP64) + dedup + all-pairs edge construction."""
+    pdef, res = small_problem(*CASES[case], dtype=dtype)
+    rr = grr.RedundancyResolver(res, seed=SEED)
+    rr.sampleConfigurationSpace(NQ)
+    o = oracle_for(res)
+    ref = o.sample_nodes(res.ws_params, rr.node_uid, NQ, seed=SEED)
+    cnt = rr.counts()
+    np.testing.assert_array_equal(cnt, ref["count"])
+    Qs = np.transpose(rr._dev["Qs"][:, :, :NQ].double().cpu().numpy(), (0, 2, 1))
+    Q = np.transpose(rr._dev["Q"][:, :, :NQ].double().cpu().numpy(), (0, 2, 1))
+    for i in range(rr.Nw):
+        c = cnt[i]
+        if c:
+            assert np.abs(Qs[i, :c] - ref["q_kept"][i, :c]).max() < 1e-8
+            assert np.abs(Q[i, :c] - ref["q_kept"][i, :c]).max() < 1e-5           # north_star tolerance
+    # edges: oracle on the device's own (rounded) configs, so only the edge arithmetic is compared
+    mask_ref, stats = o.connect_edges(res.ws_edges, res.ws_params, Q.copy(), cnt, NQ)
+    mask_ref = mask_ref.astype(bool)
+    mask_dev = unpack_mask(rr._dev["mask"].cpu().numpy(), NQ)
+    tested = int(stats[:, 0].sum())
+    assert rr.stats["pairs"] == tested
+    mism = int((mask_dev != mask_ref).sum())
+    band, ikflip = _classify_mismatches(o, res, Q, cnt, mask_dev, mask_ref)
+    print("\n[%s %s] pairs=%d valid=%d mismatches=%d (threshold-band=%d, ik-path=%d)"
+          % (case, dtype, tested, int(mask_ref.sum()), mism, band, ikflip))
+    budget = 1e-3 if dtype == "float64" else 2e-3
+    assert mism <= max(1, int(budget * tested)), "%d of %d pair verdicts differ" % (mism, tested)
+    # orientation + range invariants of the stored edge sets (solver.py:450-452,486-487)
+    rr.sanityCheck()
+    es = rr._dev["edge_stats"].cpu().numpy()
+    np.testing.assert_array_equal(es[:, 0], stats[:, 0])
+    np.testing.assert_array_equal(es[:, 1], mask_dev.reshape(rr.E, -1).sum(axis=1))
+
+
+def test_variable_orientation_roadmap(built):
+    """6-D workspace (position x SO(3)): explicit small product grid, orientation='variable'."""
+    pdef, res = grr.load_problem("baxter", "baseline_cfg4.json", dtype="float32")
+    from globalredundancyresolution_b200.workspace import explicit_product_graph
+    params, edges, info = explicit_product_graph(res.domain, [2, 2, 2], 1)
+    # keep only positions the arm reaches comfortably to get configs on both ends of some edges
+    res.setWorkspaceGraph(params, edges, info)
+    rr = grr.RedundancyResolver(res, seed=SEED)
+    rr.sampleConfigurationSpace(24)
+    o = oracle_for(res)
+    ref = o.sample_nodes(res.ws_params, rr.node_uid, 24, seed=SEED)
+    cnt = rr.counts()
+    np.testing.assert_array_equal(cnt, ref["count"])
+    Q = np.transpose(rr._dev["Q"][:, :, :24].double().cpu().numpy(), (0, 2, 1))
+    mask_ref, stats = o.connect_edges(res.ws_edges, res.ws_params, Q.copy(), cnt, 24)
+    mask_dev = unpack_mask(rr._dev["mask"].cpu().numpy(), 24)
+    tested = int(stats[:, 0].sum())
+    mism = int((mask_dev != mask_ref.astype(bool)).sum())
+    print("\n[variable] nodes=%d configs=%d pairs=%d valid=%d mismatches=%d" % (rr.Nw, cnt.sum(), tested, mask_ref.sum(), mism))
+    assert mism <= max(1, int(2e-3 * tested))
+
+
+def test_valid_edge_and_solve_api(built):
+    """RedundancyResolutionGraph.solve / validEdge / ikError / getIKParameters vs the oracle (graph.py:779-790,1051,887)."""
+    pdef, res = small_problem("planar_3R", "baseline_cfg1.json", 100, "grid")
+    o = oracle_for(res)
+    w = [1.5, 0.0, 0.5]
+    q = res.solve([0.1, 0.2, 0.3], w)
+    xr, st, it, ev, rs = o.ik_solve(w, [0.1, 0.2, 0.3])
+    assert st == 0 and q is not None
+    np.testing.assert_allclose(q, xr, atol=1e-5)
+    assert res.solve([0.0, 0.0, 0.0], [9.0, 0.0, 0.0]) is None                 # unreachable -> None, never raises
+    assert abs(res.ikError(q, w) - o.ik_error(w, q)) < 1e-5
+    np.testing.assert_allclose(res.getIKParameters(q), o.fk(np.asarray(q))[0], atol=1e-5)
+    assert res.validEdge(q, q, w, w) is True                                   # Ndivs = 0
+    w2 = [1.7, 0.0, 0.5]
+    q2 = res.solve(q, w2)
+    v_ref, info = o.valid_edge(q, q2, w, w2)
+    assert res.validEdge(q, q2, w, w2) == v_ref
+    # a pair on different IK branches (elbow up / down) must be rejected on both sides
+    qb = res.solve([-1.0, 1.9, -0.5], w2)
+    qa = res.solve([1.0, -1.9, 0.5], w)
+    if qa is not None and qb is not None:
+        assert res.validEdge(qa, qb, w, w2) == o.valid_edge(qa, qb, w, w2)[0]
+    with pytest.raises(AssertionError):
+        res.setIKProblem([1.0, 2.0])                                           # wrong parameter count (graph.py:745)
+
+
+def test_incremental_growth_matches_single_shot_rules(built):
+    """Second sampleConfigurationSpace call appends configs and only tests pairs with a new endpoint
+    (start_node_counts, solver.py:759,850; skip rule :694); verdicts of old pairs are preserved."""
+    pdef, res = small_problem("planar_3R", "baseline_cfg1.json", 100, "grid")
+    rr = grr.RedundancyResolver(res, seed=SEED)
+    rr.sampleConfigurationSpace(6)
+    c1 = rr.counts().copy()
+    m1 = unpack_mask(rr._dev["mask"].cpu().numpy(), rr.Nq)
+    p1 = rr.stats["pairs"]
+    rr.sampleConfigurationSpace(6)
+    c2 = rr.counts()
+    assert (c2 >= c1).all() and c2.sum() > c1.sum()
+    m2 = unpack_mask(rr._dev["mask"].cpu().numpy(), rr.Nq)
+    assert (m2[:, :6, :6] == m1).all()                                        # old verdicts kept
+    e = res.ws_edges
+    expect_new = int((c2[e[:, 0]].astype(np.int64) * c2[e[:, 1]] - c1[e[:, 0]].astype(np.int64) * c1[e[:, 1]]).sum())
+    assert rr.stats["pairs"] == expect_new                                    # solver.py:715
+    # full re-test of everything gives the same mask (edge predicate is deterministic)
+    nondeg, nE, _, _ = rr.connectConfigurationSpace()
+    m3 = unpack_mask(rr._dev["mask"].cpu().numpy(), rr.Nq)
+    assert (m3 == m2).all() and nE == rr.E and nondeg == int(m3.reshape(rr.E, -1).any(axis=1).sum())
+    # oracle on the final roadmap
+    o = oracle_for(res)
+    Q = np.transpose(rr._dev["Q"][:, :, :rr.Nq].double().cpu().numpy(), (0, 2, 1))
+    mask_ref, stats = o.connect_edges(e, res.ws_params, Q.copy(), c2, rr.Nq)
+    assert int((m3 != mask_ref.astype(bool)).sum()) <= max(1, int(2e-3 * stats[:, 0].sum()))
+
+
+def test_container_api_and_views(built):
+    """addNode/addEdge/hasEdge/removeEdge/testAndConnect/connectConfigurationSpaceOnEdge and the Gw views
+    (solver.py:429-501,689-697)."""
+    pdef, res = small_problem("planar_3R", "baseline_cfg1.json", 100, "grid")
+    rr = grr.RedundancyResolver(res, seed=SEED)
+    rr.sampleConfigurationSpace(8, connect=False)
+    assert rr.numCSpaceEdges() == 0
+    cnt = rr.counts()
+    assert rr.numConfigurations() == int(cnt.sum())
+    e = next(k for k, (i, j) in enumerate(rr._edges_host) if cnt[i] > 1 and cnt[j] > 1)
+    iw, jw = rr._edges_host[e]
+    ql = rr.Gw.node[iw]["qlist"]
+    assert len(ql) == cnt[iw] and len(ql[0]) == res.robot.numLinks()
+    n = rr.connectConfigurationSpaceOnEdge(iw, jw)
+    qs = rr.Gw.edge[iw][jw]["qlist"]
+    assert n == len(qs) and all(a < cnt[iw] and b < cnt[jw] for a, b in qs)
+    assert rr.Gw.edge[jw][iw]["qlist"] == qs                                    # one set per workspace edge, iw<jw
+    o = oracle_for(res)
+    for a in range(cnt[iw]):
+        for b in range(cnt[jw]):
+            v = o.valid_edge(res.to_chain(rr.Gw.node[iw]["qlist"][a]), res.to_chain(rr.Gw.node[jw]["qlist"][b]),
+                             res.ws_params[iw], res.ws_params[jw])[0]
+            assert v == ((a, b) in qs) == rr.hasEdge(iw, a, jw, b) == rr.hasEdge(jw, b, iw, a)
+            assert rr.testAndConnect(jw, b, iw, a) == v                        # swapped arguments canonicalise
+    if qs:
+        a, b = sorted(qs)[0]
+        rr.removeEdge(iw, a, jw, b)
+        assert not rr.hasEdge(iw, a, jw, b)
+        rr.addEdge(jw, b, iw, a)
+        assert rr.hasEdge(iw, a, jw, b)
+    k = rr.addNode(iw, ql[0])
+    assert k == cnt[iw] and rr.counts()[iw] == cnt[iw] + 1
+    np.testing.assert_allclose(rr.Gw.node[iw]["qlist"][k], ql[0], atol=1e-12)
+    # edge lists from the compaction kernel == bitmask expansion
+    rr.connectConfigurationSpace()
+    offsets, pairs = rr.edge_lists()
+    offsets, pairs = offsets.cpu().numpy(), pairs.cpu().numpy()
+    assert offsets[-1] == rr.numCSpaceEdges() == pairs.shape[0]
+    for ee in range(0, rr.E, 7):
+        got = [tuple(p) for p in pairs[offsets[ee]:offsets[ee + 1]].tolist()]
+        assert got == sorted(rr._edge_qlist(ee))
+    configs, qccs, parents = rr.parallelQSamplingAtP(res.ws_params[iw], 8, selfmotion=False, uid=int(iw))
+    assert len(configs) == cnt[iw] and qccs == [[i] for i in range(len(configs))] and parents == [-1] * len(configs)
+    np.testing.assert_allclose(configs, ql, atol=1e-12)
+
+
+def test_full_size_properties_cfg1(built):
+    """BASELINE config 1 at full size: size-independent properties (no oracle): every kept config solves
+    its node's IK problem inside the joint box; kept configs pairwise >= 1e-2 apart; validEdge is
+    symmetric under swapping the endpoints with the workspace edge; rebuild is idempotent."""
+    pdef, res, rr = grr.make_program("planar_3R", "baseline_cfg1.json", seed=1)
+    rr.sampleConfigurationSpace(pdef["Nq"])
+    cnt = rr.counts()
+    assert rr.Nw == 1024 and rr.E == 1984 and cnt.max() <= pdef["Nq"]
+    Q = rr._dev["Qs"]
+    n = res.chain.n
+    flat = Q.permute(1, 0, 2).reshape(n, -1).contiguous()
+    p = torch.empty((flat.shape[1], 3), dtype=flat.dtype, device=flat.device)
+    res.chain.fk_batch(flat, p)
+    p = p.reshape(rr.Nw, -1, 3).cpu().numpy()
+    lo, hi = res.fold["qmin"], res.fold["qmax"]
+    Qh = np.transpose(Q.cpu().numpy(), (0, 2, 1))
+    for i in range(rr.Nw):
+        c = cnt[i]
+        if c == 0:
+            continue
+        assert np.abs(p[i, :c] - res.ws_params[i]).max() < 1e-3
+        assert (Qh[i, :c] >= lo - 1e-9).all() and (Qh[i, :c] <= hi + 1e-9).all()
+        d = np.linalg.norm(Qh[i, :c, None, :] - Qh[i, None, :c, :], axis=2) + np.eye(c)
+        assert d.min() >= 1e-2
+    m1 = rr._dev["mask"].clone()
+    rr.connectConfigurationSpace()
+    assert torch.equal(m1, rr._dev["mask"])
