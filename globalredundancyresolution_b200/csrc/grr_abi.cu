@@ -158,7 +158,21 @@ using namespace grr;
 
 struct grr_handle_s {
   HostChain hc;
+  unsigned long long *d_work;   // ring of device work counters for the persistent-lane kernels
+  unsigned next_work;
 };
+static const unsigned kWorkRing = 64;
+
+// next work counter of the handle's ring (allocated on first use, on the handle's device)
+static unsigned long long *work_slot(grr_handle_s *h) {
+  if (!h->d_work) {
+    if (cudaMalloc(&h->d_work, sizeof(unsigned long long) * kWorkRing) != cudaSuccess) {
+      set_error("cudaMalloc(work counters) failed: %s", cudaGetErrorString(cudaGetLastError()));
+      return nullptr;
+    }
+  }
+  return h->d_work + (h->next_work++ % kWorkRing);
+}
 
 #define GRR_CHECK_HANDLE(h)                                   \
   if (!(h)) { set_error("null handle"); return -1; }          \
@@ -202,6 +216,7 @@ int grr_chain_create(const grr_chain_desc *d, int device, grr_handle_t *out) {
 }
 
 int grr_chain_destroy(grr_handle_t h) {
+  if (h && h->d_work) { cudaSetDevice(h->hc.device); cudaFree(h->d_work); }
   delete h;
   return 0;
 }
@@ -239,7 +254,10 @@ int grr_ik_solve_batch(grr_handle_t h, int dtype, int64_t P, const void *targets
   const Ops *ops = pick_ops(dtype, h->hc.mode);
   if (!ops) { set_error("bad dtype %d", dtype); return -1; }
   if (P < 0 || (P > 0 && (!targets || !q || !status))) { set_error("grr_ik_solve_batch: null buffer"); return -1; }
-  return ops->ik_solve_batch(h->hc, P, targets, q, status, iters, resid, (unsigned long long *)counters, (cudaStream_t)stream);
+  if (P == 0) return 0;
+  unsigned long long *work = work_slot(h);
+  if (!work) return -3;
+  return ops->ik_solve_batch(h->hc, P, targets, q, status, iters, resid, work, (unsigned long long *)counters, (cudaStream_t)stream);
 }
 
 int grr_ik_sample(grr_handle_t h, int dtype, int64_t Nw, int32_t Nq, int32_t Nqp, const void *params,
@@ -250,7 +268,10 @@ int grr_ik_sample(grr_handle_t h, int dtype, int64_t Nw, int32_t Nq, int32_t Nqp
   if (!ops) { set_error("bad dtype %d", dtype); return -1; }
   if (Nw < 0 || Nq < 0 || Nqp < Nq) { set_error("grr_ik_sample: bad sizes Nw=%lld Nq=%d Nqp=%d", (long long)Nw, Nq, Nqp); return -1; }
   if (Nw * (int64_t)Nq > 0 && (!params || !node_uid || !q_raw || !status)) { set_error("grr_ik_sample: null buffer"); return -1; }
-  return ops->ik_sample(h->hc, Nw, Nq, Nqp, params, node_uid, seed, sample_offset, q_raw, status, iters,
+  if (Nw * (int64_t)Nq == 0) return 0;
+  unsigned long long *work = work_slot(h);
+  if (!work) return -3;
+  return ops->ik_sample(h->hc, Nw, Nq, Nqp, params, node_uid, seed, sample_offset, q_raw, status, iters, work,
                         (unsigned long long *)counters, (cudaStream_t)stream);
 }
 
@@ -296,7 +317,10 @@ int grr_valid_edge_batch(grr_handle_t h, int dtype, int64_t P, const void *qa, c
   const Ops *ops = pick_ops(dtype, h->hc.mode);
   if (!ops) { set_error("bad dtype %d", dtype); return -1; }
   if (P > 0 && (!qa || !qb || !wa || !wb || !valid)) { set_error("grr_valid_edge_batch: null buffer"); return -1; }
-  return ops->valid_edge_batch(h->hc, P, qa, qb, wa, wb, epsilon, valid, info, (unsigned long long *)counters,
+  if (P <= 0) return 0;
+  unsigned long long *work = work_slot(h);
+  if (!work) return -3;
+  return ops->valid_edge_batch(h->hc, P, qa, qb, wa, wb, epsilon, valid, info, work, (unsigned long long *)counters,
                                (cudaStream_t)stream);
 }
 

@@ -1,10 +1,9 @@
 // grr_device.cuh -- device-side building blocks of the B200 roadmap-construction path.
 //
 // Everything is templated on the arithmetic type (float = product path on the FP32 SIMT pipe,
-// double = verification build), on the number of active joints N (compile-time so that the
-// per-thread joint arrays live in registers and every chain constant is a constant-bank
-// operand; N = 0 selects the runtime-n fallback), and on the residual rows M (3 = free
-// orientation, 6 = fixed / variable).
+// double = verification build) and on the residual rows M (3 = free orientation, 6 = fixed /
+// variable).  The joint count is a run-time value (<= 32): the joint loop is rolled on purpose,
+// see grr_lane.cuh.
 //
 // What is restated here (reference file:line in the reference repository):
 //   * IK residual / Jacobian of a serial chain  (Klamp't RobotIKFunction; call sites
@@ -18,8 +17,7 @@
 // goal-link rotation and every Jacobian column expressed in the goal-link frame in a single
 // pass with O(1) live state (v, G), so no per-joint frames are stored; the damped step
 // p = -J^T (J J^T + lambda^2 I)^-1 F is invariant under that change of frame.  The Newton
-// iteration is written as a resumable state machine (one chain pass per "trip") so that a
-// lane that finishes an instance can start the next one without waiting for its warp.
+// iteration itself (a resumable per-lane state machine) is in grr_lane.cuh.
 #pragma once
 #include <cuda_runtime.h>
 #include <math_constants.h>
@@ -188,87 +186,7 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
   out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
-// ------------------------------------------------------------------------------------------
-// chain pass: residual, merit and (optionally) Jacobian columns + normal matrix, one backward walk
-// ------------------------------------------------------------------------------------------
-template <int N> struct NA_ { static constexpr int v = (N > 0 ? N : kMaxJ); };
-
-template <typename Real, int N, int M>
-struct PassOut {
-  Real Fw[M];            // residual, world frame (stopping test is max|Fw|)
-  Real FL[M];            // residual, goal-link frame (used by the solve)
-  Real f;                // 0.5 |F|^2
-  Real cp[NA_<N>::v][3]; // position Jacobian columns, goal-link frame
-  Real cr[M == 6 ? NA_<N>::v : 1][3];  // raw rotation columns (G_j^T axis_j), goal-link frame
-  Real S[M * (M + 1) / 2];             // packed lower triangle of [cp;cr][cp;cr]^T summed over joints
-};
-
-__host__ __device__ constexpr int tri(int r, int c) { return r * (r + 1) / 2 + c; }  // r >= c
-
-template <typename Real, int N, int M, int NJ, bool WITH_J>
-__device__ __forceinline__ void chain_pass(const ChainDev<Real, NJ> &c, const Real *x, const Target<Real, M> &tg,
-                                           PassOut<Real, N, M> &o) {
-  const int n = (N > 0 ? N : c.n);
-  Real v[3] = {c.ee[0], c.ee[1], c.ee[2]};
-  Real G[9];
-  constexpr bool needG = WITH_J || (M == 6);
-  if (needG) {
-#pragma unroll
-    for (int k = 0; k < 9; k++) G[k] = c.Rtail[k];
-  }
-  if (WITH_J) {
-#pragma unroll
-    for (int k = 0; k < M * (M + 1) / 2; k++) o.S[k] = 0;
-  }
-#pragma unroll
-  for (int jj = 0; jj < NA_<N>::v; jj++) {
-    const int j = n - 1 - jj;
-    if (N == 0 && j < 0) break;
-    Real s, co;
-    sincos_(x[j], &s, &co);
-    Real Mj[9];
-#pragma unroll
-    for (int k = 0; k < 9; k++) Mj[k] = c.A[j][k] + s * c.B[j][k] - co * c.C[j][k];
-    if (WITH_J) {
-      Real w[3] = {c.ax[j][1] * v[2] - c.ax[j][2] * v[1], c.ax[j][2] * v[0] - c.ax[j][0] * v[2],
-                   c.ax[j][0] * v[1] - c.ax[j][1] * v[0]};
-      Real col[6];
-      m3_Tvec(G, w, col);
-      o.cp[j][0] = col[0]; o.cp[j][1] = col[1]; o.cp[j][2] = col[2];
-      if (M == 6) {
-        Real a[3] = {c.ax[j][0], c.ax[j][1], c.ax[j][2]};
-        m3_Tvec(G, a, col + 3);
-        o.cr[j][0] = col[3]; o.cr[j][1] = col[4]; o.cr[j][2] = col[5];
-      }
-#pragma unroll
-      for (int r = 0; r < M; r++)
-#pragma unroll
-        for (int q = 0; q <= r; q++) o.S[tri(r, q)] += col[r] * col[q];
-    }
-    Real nv[3];
-    m3_vec(Mj, v, nv);
-    v[0] = nv[0] + c.tp[j][0]; v[1] = nv[1] + c.tp[j][1]; v[2] = nv[2] + c.tp[j][2];
-    if (needG) {
-      Real nG[9];
-      m3_mul(Mj, G, nG);
-#pragma unroll
-      for (int k = 0; k < 9; k++) G[k] = nG[k];
-    }
-  }
-  o.Fw[0] = v[0] - tg.x[0]; o.Fw[1] = v[1] - tg.x[1]; o.Fw[2] = v[2] - tg.x[2];
-  Real f = o.Fw[0] * o.Fw[0] + o.Fw[1] * o.Fw[1] + o.Fw[2] * o.Fw[2];
-  if (needG) m3_Tvec(G, o.Fw, o.FL);
-  if (M == 6) {
-    Real Re[9], e[3], ew[3];
-    m3_Tmul(tg.R, G, Re);          // R_goal^T R_link
-    so3_log(Re, e);
-    m3_vec(G, e, ew);              // world-frame rotation error = log(R_link R_goal^T)
-    o.FL[M - 3] = e[0]; o.FL[M - 2] = e[1]; o.FL[M - 1] = e[2];
-    o.Fw[M - 3] = ew[0]; o.Fw[M - 2] = ew[1]; o.Fw[M - 1] = ew[2];
-    f += e[0] * e[0] + e[1] * e[1] + e[2] * e[2];
-  }
-  o.f = Real(0.5) * f;
-}
+__host__ __device__ constexpr int tri(int r, int c) { return r * (r + 1) / 2 + c; }  // packed lower triangle, r >= c
 
 // forward-facing FK for the API (EE point + goal-link rotation), same backward walk
 template <typename Real, int NJ>
@@ -320,203 +238,7 @@ __device__ __forceinline__ void chol_solve(Real (&A)[M * (M + 1) / 2], const Rea
   }
 }
 
-// ------------------------------------------------------------------------------------------
-// IK lane: resumable NewtonRoot::GlobalSolve
-// ------------------------------------------------------------------------------------------
 enum : int { IK_RUNNING = -1, IK_OK = 0, IK_STALL = 1, IK_CONVX = 2, IK_MAXIT = 3 };
-
-template <typename Real, int N, int M>
-struct IkLane {
-  static constexpr int NA = NA_<N>::v;
-  Real x[NA];       // current (trial) point
-  Real xold[NA];    // start of the current line search
-  Real p[NA];       // current Newton direction
-  Real fold, slope, alam, alam2, f2, alamin, stpmax, resid;
-  int it;           // completed Newton iterations
-  int evals;        // chain passes
-  int phase;        // 0 = first evaluation at the seed, 1 = line-search trial
-};
-
-// Clamp the seed into the joint box and reset the state machine (IKDB solve, startRandom=False
-// path: robot.setConfig(seed) then solver.solve(); graph.py:783-790).
-template <typename Real, int N, int M, int NJ>
-__device__ __forceinline__ void ik_begin(const ChainDev<Real, NJ> &c, IkLane<Real, N, M> &L) {
-  const int n = (N > 0 ? N : c.n);
-#pragma unroll
-  for (int j = 0; j < IkLane<Real, N, M>::NA; j++) {
-    if (N == 0 && j >= n) break;
-    L.x[j] = min_(max_(L.x[j], c.bmin[j]), c.bmax[j]);
-  }
-  L.it = 0; L.evals = 0; L.phase = 0;
-  L.alam = 1; L.alam2 = 0; L.f2 = 0; L.fold = 0; L.slope = 0; L.alamin = 0; L.stpmax = 0; L.resid = 0;
-}
-
-// One trip = one chain pass at L.x + the state-machine transition.  Returns IK_RUNNING or a final
-// status; on return with a final status L.x holds the result configuration.
-template <typename Real, int N, int M, int NJ>
-__device__ __forceinline__ int ik_trip(const ChainDev<Real, NJ> &c, const Target<Real, M> &tg, IkLane<Real, N, M> &L) {
-  constexpr int NA = IkLane<Real, N, M>::NA;
-  const int n = (N > 0 ? N : c.n);
-  const Real tolf = c.tol, tolx = Real(0.01) * c.tol, ALF = Real(1e-4);
-  PassOut<Real, N, M> o;
-  chain_pass<Real, N, M, NJ, true>(c, L.x, tg, o);
-  L.evals++;
-  Real fmax = 0;
-#pragma unroll
-  for (int r = 0; r < M; r++) fmax = max_(fmax, abs_(o.Fw[r]));
-  L.resid = fmax;
-
-  if (L.phase == 0) {
-    if (fmax < tolf) return IK_OK;
-    if (c.max_iters <= 0) return IK_MAXIT;
-    Real xn = 0;
-#pragma unroll
-    for (int j = 0; j < NA; j++) { if (N == 0 && j >= n) break; xn += L.x[j] * L.x[j]; }
-    L.stpmax = Real(10) * max_(sqrt_(xn), Real(n));
-  } else {
-    if (L.alam < L.alamin) {           // line search stalled: x <- xold, failure
-#pragma unroll
-      for (int j = 0; j < NA; j++) { if (N == 0 && j >= n) break; L.x[j] = L.xold[j]; }
-      L.it++;
-      return IK_STALL;
-    }
-    if (!(o.f <= L.fold + ALF * L.alam * L.slope)) {
-      // backtrack (Numerical Recipes lnsrch)
-      Real tmplam;
-      if (L.alam == Real(1)) tmplam = -L.slope / (Real(2) * (o.f - L.fold - L.slope));
-      else {
-        Real rhs1 = o.f - L.fold - L.alam * L.slope, rhs2 = L.f2 - L.fold - L.alam2 * L.slope;
-        Real a = (rhs1 / (L.alam * L.alam) - rhs2 / (L.alam2 * L.alam2)) / (L.alam - L.alam2);
-        Real b = (-L.alam2 * rhs1 / (L.alam * L.alam) + L.alam * rhs2 / (L.alam2 * L.alam2)) / (L.alam - L.alam2);
-        if (a == Real(0)) tmplam = -L.slope / (Real(2) * b);
-        else {
-          Real disc = b * b - Real(3) * a * L.slope;
-          if (disc < Real(0)) tmplam = Real(0.5) * L.alam;
-          else if (b <= Real(0)) tmplam = (-b + sqrt_(disc)) / (Real(3) * a);
-          else tmplam = -L.slope / (b + sqrt_(disc));
-        }
-        if (tmplam > Real(0.5) * L.alam) tmplam = Real(0.5) * L.alam;
-      }
-      L.alam2 = L.alam; L.f2 = o.f;
-      L.alam = max_(tmplam, Real(0.1) * L.alam);
-#pragma unroll
-      for (int j = 0; j < NA; j++) {
-        if (N == 0 && j >= n) break;
-        L.x[j] = min_(max_(L.xold[j] + L.alam * L.p[j], c.bmin[j]), c.bmax[j]);
-      }
-      return IK_RUNNING;
-    }
-    // trial accepted: iteration complete
-    L.it++;
-    if (fmax < tolf) return IK_OK;
-    Real test = 0;
-#pragma unroll
-    for (int j = 0; j < NA; j++) {
-      if (N == 0 && j >= n) break;
-      test = max_(test, abs_(L.x[j] - L.xold[j]) / max_(abs_(L.x[j]), Real(1)));
-    }
-    if (test < tolx) return IK_CONVX;
-    if (L.it >= c.max_iters) return IK_MAXIT;
-  }
-
-  // ---- new Newton step at x (Jacobian columns of this pass) ----
-  Real y[M];
-  {
-    Real A[M * (M + 1) / 2];
-    const Real l2 = c.lambda * c.lambda;
-    if (M == 3) {
-#pragma unroll
-      for (int k = 0; k < 6; k++) A[k] = o.S[k];
-    } else {
-      // rows 3..5 of J are D * cr with D = Jl^-1(e): transform the raw normal matrix
-      Real D[9];
-      so3_Jl_inv(&o.FL[M - 3], D);
-      // Scc stays; Scr' = Scr D^T (stored as lower block rows 3..5, cols 0..2: (D Src)); Srr' = D Srr D^T
-      Real Src[9], Srr[9];   // Src[r][q] = S[3+r][q], full Srr
-#pragma unroll
-      for (int r = 0; r < 3; r++)
-#pragma unroll
-        for (int q = 0; q < 3; q++) {
-          Src[3 * r + q] = o.S[tri(3 + r, q)];
-          Srr[3 * r + q] = (r >= q) ? o.S[tri(3 + r, 3 + q)] : o.S[tri(3 + q, 3 + r)];
-        }
-      Real DSrc[9], DSrr[9];
-      m3_mul(D, Src, DSrc);
-      m3_mul(D, Srr, DSrr);
-#pragma unroll
-      for (int r = 0; r < 3; r++)
-#pragma unroll
-        for (int q = 0; q <= r; q++) A[tri(r, q)] = o.S[tri(r, q)];
-#pragma unroll
-      for (int r = 0; r < 3; r++)
-#pragma unroll
-        for (int q = 0; q < 3; q++) A[tri(3 + r, q)] = DSrc[3 * r + q];
-#pragma unroll
-      for (int r = 0; r < 3; r++)
-#pragma unroll
-        for (int q = 0; q <= r; q++)
-          A[tri(3 + r, 3 + q)] = DSrr[3 * r] * D[3 * q] + DSrr[3 * r + 1] * D[3 * q + 1] + DSrr[3 * r + 2] * D[3 * q + 2];
-      // z = D^T y_r is applied after the solve
-      (void)Src;
-    }
-#pragma unroll
-    for (int r = 0; r < M; r++) A[tri(r, r)] += l2;
-    chol_solve<Real, M>(A, o.FL, y);
-    if (M == 6) {
-      Real D[9], z[3];
-      so3_Jl_inv(&o.FL[M - 3], D);
-      m3_Tvec(D, &y[M - 3], z);
-      y[M - 3] = z[0]; y[M - 2] = z[1]; y[M - 1] = z[2];
-    }
-  }
-  Real pn = 0, slope = 0, test = 0;
-#pragma unroll
-  for (int j = 0; j < NA; j++) {
-    if (N == 0 && j >= n) break;
-    Real pj = o.cp[j][0] * y[0] + o.cp[j][1] * y[1] + o.cp[j][2] * y[2];
-    Real gj = o.cp[j][0] * o.FL[0] + o.cp[j][1] * o.FL[1] + o.cp[j][2] * o.FL[2];
-    if (M == 6) {
-      pj += o.cr[j][0] * y[M - 3] + o.cr[j][1] * y[M - 2] + o.cr[j][2] * y[M - 1];
-      gj += o.cr[j][0] * o.FL[M - 3] + o.cr[j][1] * o.FL[M - 2] + o.cr[j][2] * o.FL[M - 1];
-    }
-    pj = -pj;
-    L.p[j] = pj;
-    pn += pj * pj;
-    slope += gj * pj;
-  }
-  pn = sqrt_(pn);
-  if (pn > L.stpmax) {
-    const Real sc = L.stpmax / pn;
-#pragma unroll
-    for (int j = 0; j < NA; j++) { if (N == 0 && j >= n) break; L.p[j] *= sc; }
-    slope *= sc;
-  }
-  if (!(slope < Real(0))) { L.it++; return IK_STALL; }
-#pragma unroll
-  for (int j = 0; j < NA; j++) {
-    if (N == 0 && j >= n) break;
-    test = max_(test, abs_(L.p[j]) / max_(abs_(L.x[j]), Real(1)));
-  }
-  L.alamin = tolx / test;
-  L.fold = o.f; L.slope = slope; L.alam = 1; L.alam2 = 0; L.f2 = 0;
-#pragma unroll
-  for (int j = 0; j < NA; j++) {
-    if (N == 0 && j >= n) break;
-    L.xold[j] = L.x[j];
-    L.x[j] = min_(max_(L.x[j] + L.p[j], c.bmin[j]), c.bmax[j]);
-  }
-  L.phase = 1;
-  return IK_RUNNING;
-}
-
-// Run one instance to completion (seed in L.x).
-template <typename Real, int N, int M, int NJ>
-__device__ __forceinline__ int ik_solve(const ChainDev<Real, NJ> &c, const Target<Real, M> &tg, IkLane<Real, N, M> &L) {
-  ik_begin<Real, N, M, NJ>(c, L);
-  int st;
-  do { st = ik_trip<Real, N, M, NJ>(c, tg, L); } while (st == IK_RUNNING);
-  return st;
-}
 
 // ------------------------------------------------------------------------------------------
 // workspace targets: setIKProblem (graph.py:737-745) and workspaceInterpolate (graph.py:768-777)

@@ -18,15 +18,17 @@ struct HostChain {
 
 void set_error(const char *fmt, ...);
 
-// One table of launchers per (precision, residual rows); each entry dispatches on the joint count.
+// One table of launchers per (precision, residual rows).  `work` is a zero-initialised-by-the-launcher
+// device counter from which persistent lanes pull their next instance.
 struct Ops {
   int (*ik_sample)(const HostChain &, long long Nw, int Nq, int Nqp, const void *params, const int32_t *uid,
                    unsigned long long seed, int sample_offset, void *q_raw, uint8_t *status, uint8_t *iters,
-                   unsigned long long *counters, cudaStream_t st);
+                   unsigned long long *work, unsigned long long *counters, cudaStream_t st);
   int (*ik_solve_batch)(const HostChain &, long long P, const void *targets, void *q, uint8_t *status, uint8_t *iters,
-                        void *resid, unsigned long long *counters, cudaStream_t st);
+                        void *resid, unsigned long long *work, unsigned long long *counters, cudaStream_t st);
   int (*valid_edge_batch)(const HostChain &, long long P, const void *qa, const void *qb, const void *wa, const void *wb,
-                          double epsilon, uint8_t *valid, int32_t *info, unsigned long long *counters, cudaStream_t st);
+                          double epsilon, uint8_t *valid, int32_t *info, unsigned long long *work,
+                          unsigned long long *counters, cudaStream_t st);
   int (*edges_build)(const HostChain &, long long E, const int32_t *wedges, const void *params, const void *q_kept,
                      const int32_t *count, const int32_t *old_count, int Nq, int Nqp, double epsilon, uint32_t *mask,
                      uint32_t *edge_stats, unsigned long long *counters, cudaStream_t st);

@@ -2,5 +2,4 @@
 #define GRR_REAL double
 #define GRR_M 3
 #define GRR_OPS_FN ops_f64_m3
-#define GRR_FOR_EACH_N(X) X(3) X(20)
 #include "grr_inst.inc"

@@ -1,270 +1,347 @@
-// grr_kernels.cuh -- kernels of the roadmap-construction path + their launchers.
+// grr_kernels.cuh -- kernels of the roadmap-construction path + their launchers (v2: lane machines).
 // Included by the per-(precision, residual-rows) instantiation units grr_inst_*.cu.
 #pragma once
 #include "grr_device.cuh"
+#include "grr_lane.cuh"
 #include "grr_host.h"
 #include "grr_fill.cuh"
 
 namespace grr {
 
 // ------------------------------------------------------------------------------------------
-// warp-aggregated counter update
+// warp-aggregated counter update (all 32 lanes must call)
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ void warp_add(unsigned long long *ctr, int slot, unsigned v) {
   unsigned tot = __reduce_add_sync(0xffffffffu, v);
   if ((threadIdx.x & 31) == 0 && tot) atomicAdd(ctr + slot, (unsigned long long)tot);
 }
 
+struct LaneCounters {
+  unsigned solves = 0, iters = 0, evals = 0, ok = 0, pairs = 0, valid = 0;
+  __device__ __forceinline__ void flush(unsigned long long *counters) const {
+    if (!counters) return;
+    warp_add(counters, GRR_CNT_IK_SOLVES, solves);
+    warp_add(counters, GRR_CNT_IK_ITERS, iters);
+    warp_add(counters, GRR_CNT_IK_EVALS, evals);
+    warp_add(counters, GRR_CNT_IK_OK, ok);
+    warp_add(counters, GRR_CNT_PAIRS, pairs);
+    warp_add(counters, GRR_CNT_VALID, valid);
+  }
+};
+
 // ------------------------------------------------------------------------------------------
-// S2: random-start IK sampling, one thread per (node, sample) slot
-// (parallelQSamplingAtP solver.py:875-885; random phase of sampleConfigurationSpace :817-821)
+// S2 + V2: IK instances pulled from a global work counter, one lane machine per lane.
+//   MODE 0: random-start sampling over (node, sample) slots
+//           (parallelQSamplingAtP solver.py:875-885; random phase of sampleConfigurationSpace :817-821)
+//   MODE 1: explicit (target, seed) instances, SoA q[n][P]  (RedundancyResolutionGraph.solve, graph.py:779-790)
 // ------------------------------------------------------------------------------------------
-template <typename Real, int N, int M, int NJ>
-__global__ void __launch_bounds__(128)
-k_ik_sample(const __grid_constant__ ChainDev<Real, NJ> c, long long Nw, int Nq, int Nqp, const Real *__restrict__ params,
-            const int32_t *__restrict__ uid, unsigned long long seed, int sample_offset, Real *__restrict__ q_raw,
-            uint8_t *__restrict__ status, uint8_t *__restrict__ iters, unsigned long long *counters) {
-  const int n = (N > 0 ? N : c.n);
-  const int dw = (c.mode == 2 ? 6 : 3);
-  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const bool live = t < Nw * (long long)Nq;
-  unsigned ok = 0, its = 0, evs = 0;
-  if (live) {
-    const long long node = t / Nq;
-    const int s = (int)(t - node * Nq);
-    IkLane<Real, N, M> L;
-    // random start: Philox(key=seed, ctr=(uid, sample, dof/4, 0)), u = (r>>8) 2^-24, fp32 fma
-    const uint32_t id = (uint32_t)uid[node], smp = (uint32_t)(s + sample_offset);
+template <typename Real, int M, int MODE>
+__global__ void __launch_bounds__(256)
+k_ik_instances(const __grid_constant__ ChainDev<Real, kMaxJ> c, long long total, int Nq, int Nqp,
+               const Real *__restrict__ params, const int32_t *__restrict__ uid, unsigned long long seed, int sample_offset,
+               Real *__restrict__ q, uint8_t *__restrict__ status, uint8_t *__restrict__ iters, Real *__restrict__ resid,
+               unsigned long long *work, unsigned long long *counters) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int n = c.n, dw = (c.mode == 2 ? 6 : 3);
+  LaneMem<Real, M> mem{reinterpret_cast<Real *>(smem_raw) + threadIdx.x, (int)blockDim.x, n};
+  LaneIK<Real, M> L;
+  Target<Real, M> tg;
+  LaneCounters cnt;
+  long long inst = -1;
+  bool done = false;
+  for (;;) {
+    if (inst < 0 && !done) {
+      const long long t = (long long)atomicAdd(work, 1ull);
+      if (t >= total) done = true;
+      else {
+        inst = t;
+        Real w[6];
+        if (MODE == 0) {
+          const long long node = t / Nq;
+          const int s = (int)(t - node * Nq);
+          const uint32_t id = (uint32_t)uid[node], smp = (uint32_t)(s + sample_offset);
+          for (int jb = 0; jb * 4 < n; jb++) {
+            uint32_t r[4];
+            philox4x32_10(id, smp, (uint32_t)jb, 0u, (uint32_t)seed, (uint32_t)(seed >> 32), r);
 #pragma unroll
-    for (int jb = 0; jb < (IkLane<Real, N, M>::NA + 3) / 4; jb++) {
-      if (N == 0 && jb * 4 >= n) break;
-      uint32_t r[4];
-      philox4x32_10(id, smp, (uint32_t)jb, 0u, (uint32_t)seed, (uint32_t)(seed >> 32), r);
-#pragma unroll
-      for (int k = 0; k < 4; k++) {
-        const int j = jb * 4 + k;
-        if (j < IkLane<Real, N, M>::NA && (N > 0 || j < n)) {
-          float u = (float)(r[k] >> 8) * (1.0f / 16777216.0f);
-          L.x[j] = (Real)fmaf(u, c.srange[j], c.slo[j]);
+            for (int k = 0; k < 4; k++) {
+              const int j = jb * 4 + k;
+              if (j < n) {
+                const float u = (float)(r[k] >> 8) * (1.0f / 16777216.0f);
+                mem.xold(j) = (Real)fmaf(u, c.srange[j], c.slo[j]);
+                mem.p(j) = 0;
+              }
+            }
+          }
+          for (int k = 0; k < dw; k++) w[k] = params[node * dw + k];
+        } else {
+          for (int j = 0; j < n; j++) { mem.xold(j) = q[(long long)j * total + t]; mem.p(j) = 0; }
+          for (int k = 0; k < dw; k++) w[k] = params[t * dw + k];
         }
+        target_from_params<Real, M, kMaxJ>(c, w, tg);
+        lane_begin<Real, M>(L);
       }
     }
-    Target<Real, M> tg;
-    Real w[6];
-    for (int k = 0; k < dw; k++) w[k] = params[node * dw + k];
-    target_from_params<Real, M, NJ>(c, w, tg);
-    const int st = ik_solve<Real, N, M, NJ>(c, tg, L);
-    Real *dst = q_raw + (node * n) * (long long)Nqp + s;
-#pragma unroll
-    for (int j = 0; j < IkLane<Real, N, M>::NA; j++) {
-      if (N == 0 && j >= n) break;
-      dst[(long long)j * Nqp] = L.x[j];
+    if (__all_sync(0xffffffffu, done && inst < 0)) break;
+    if (inst >= 0) {
+      const int st = lane_trip<Real, M>(c, tg, L, mem);
+      if (st != IK_RUNNING) {
+        long long base, stride, sidx;
+        if (MODE == 0) {
+          const long long node = inst / Nq;
+          const int s = (int)(inst - node * Nq);
+          base = node * n * (long long)Nqp + s; stride = Nqp; sidx = node * Nqp + s;
+        } else { base = inst; stride = total; sidx = inst; }
+        for (int j = 0; j < n; j++) q[base + j * stride] = lane_x<Real>(c, mem.xold(j), mem.p(j), L.alam, j);
+        status[sidx] = (uint8_t)st;
+        if (iters) iters[sidx] = (uint8_t)L.it;
+        if (resid) resid[sidx] = L.resid;
+        cnt.solves++; cnt.iters += L.it; cnt.evals += L.evals; cnt.ok += (st == IK_OK);
+        inst = -1;
+      }
     }
-    status[node * Nqp + s] = (uint8_t)st;
-    if (iters) iters[node * Nqp + s] = (uint8_t)L.it;
-    ok = (st == IK_OK); its = L.it; evs = L.evals;
   }
-  if (counters) {
-    warp_add(counters, GRR_CNT_IK_SOLVES, live ? 1u : 0u);
-    warp_add(counters, GRR_CNT_IK_ITERS, its);
-    warp_add(counters, GRR_CNT_IK_EVALS, evs);
-    warp_add(counters, GRR_CNT_IK_OK, ok);
-  }
+  cnt.flush(counters);
 }
 
 // ------------------------------------------------------------------------------------------
-// V2: seeded IK on explicit (target, seed) instances, SoA q[n][P]
-// (RedundancyResolutionGraph.solve, graph.py:779-790)
-// ------------------------------------------------------------------------------------------
-template <typename Real, int N, int M, int NJ>
-__global__ void __launch_bounds__(128)
-k_ik_solve_batch(const __grid_constant__ ChainDev<Real, NJ> c, long long P, const Real *__restrict__ targets,
-                 Real *__restrict__ q, uint8_t *__restrict__ status, uint8_t *__restrict__ iters,
-                 Real *__restrict__ resid, unsigned long long *counters) {
-  const int n = (N > 0 ? N : c.n);
-  const int dw = (c.mode == 2 ? 6 : 3);
-  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const bool live = t < P;
-  unsigned ok = 0, its = 0, evs = 0;
-  if (live) {
-    IkLane<Real, N, M> L;
-#pragma unroll
-    for (int j = 0; j < IkLane<Real, N, M>::NA; j++) { if (N == 0 && j >= n) break; L.x[j] = q[(long long)j * P + t]; }
-    Target<Real, M> tg;
-    Real w[6];
-    for (int k = 0; k < dw; k++) w[k] = targets[t * dw + k];
-    target_from_params<Real, M, NJ>(c, w, tg);
-    const int st = ik_solve<Real, N, M, NJ>(c, tg, L);
-#pragma unroll
-    for (int j = 0; j < IkLane<Real, N, M>::NA; j++) { if (N == 0 && j >= n) break; q[(long long)j * P + t] = L.x[j]; }
-    status[t] = (uint8_t)st;
-    if (iters) iters[t] = (uint8_t)L.it;
-    if (resid) resid[t] = L.resid;
-    ok = (st == IK_OK); its = L.it; evs = L.evals;
-  }
-  if (counters) {
-    warp_add(counters, GRR_CNT_IK_SOLVES, live ? 1u : 0u);
-    warp_add(counters, GRR_CNT_IK_ITERS, its);
-    warp_add(counters, GRR_CNT_IK_EVALS, evs);
-    warp_add(counters, GRR_CNT_IK_OK, ok);
-  }
-}
-
-// ------------------------------------------------------------------------------------------
-// V1: validEdgeLinear for one pair held by one lane (graph.py:938-1006), closed form:
+// V1 state of one pair held by one lane: validEdgeLinear (graph.py:938-1006) in closed form:
 // valid <=> every interpolated IK k=1..Ndivs (seed lerp(qa,qb,u_k), target winterp(wa,wb,u_k))
-// converges and every consecutive distance (qa, q_1, ..., q_Ndivs, qb) is <= thr.  The BFS order
-// of the reference only changes which failure is met first, never the verdict.
-// QA/QB are accessors returning dof j of the two endpoint configs.
+// converges and every consecutive distance (qa, q_1, ..., q_Ndivs, qb) is <= thr.  The BFS order of
+// the reference only changes which failure is met first, never the verdict.
 // ------------------------------------------------------------------------------------------
-struct PairInfo { int ndivs, solves, fail, iters, evals; };
+struct PairLane {
+  int k, ndivs;       // current interpolation index, graph.py:946
+  int solves, iters;  // diagnostics
+};
 
-template <typename Real, int N, int M, int NJ, typename QA, typename QB>
-__device__ __forceinline__ bool valid_edge_lane(const ChainDev<Real, NJ> &c, const WInterp<Real, M> &W, QA qa, QB qb,
-                                                Real eps, Real thr, PairInfo &pi) {
-  constexpr int NA = IkLane<Real, N, M>::NA;
-  const int n = (N > 0 ? N : c.n);
+// Begin pair: distance -> Ndivs, prev <- qa, seed of k=1.  Returns false if the pair is decided already.
+template <typename Real, int M, typename ChainT, typename QA, typename QB>
+__device__ __forceinline__ bool pair_begin(const ChainT &c, const LaneMem<Real, M> &mem, QA qa, QB qb, Real eps,
+                                           PairLane &P, LaneIK<Real, M> &L) {
+  const int n = c.n;
   Real d2 = 0;
-#pragma unroll
-  for (int j = 0; j < NA; j++) { if (N == 0 && j >= n) break; Real d = qa(j) - qb(j); d2 += d * d; }
-  const int Ndivs = (int)ceil_(sqrt_(d2) / eps);                 // graph.py:946
-  pi.ndivs = Ndivs; pi.solves = 0; pi.fail = 0; pi.iters = 0; pi.evals = 0;
-  const Real thr2 = thr * thr;
-  Real prev[NA];
-#pragma unroll
-  for (int j = 0; j < NA; j++) { if (N == 0 && j >= n) break; prev[j] = qa(j); }
-  IkLane<Real, N, M> L;
-  for (int k = 1; k <= Ndivs; k++) {
-    const Real u = Real(k) / Real(Ndivs + 1);                     // graph.py:961
-#pragma unroll
-    for (int j = 0; j < NA; j++) { if (N == 0 && j >= n) break; L.x[j] = qa(j) + u * (qb(j) - qa(j)); }   // :962
-    Target<Real, M> tg;
-    winterp_at<Real, M>(W, u, tg);
-    const int st = ik_solve<Real, N, M, NJ>(c, tg, L);            // :963
-    pi.solves++; pi.iters += L.it; pi.evals += L.evals;
-    if (st != IK_OK) { pi.fail = 1; return false; }               // :964-966
-    Real s2 = 0;
-#pragma unroll
-    for (int j = 0; j < NA; j++) { if (N == 0 && j >= n) break; Real d = L.x[j] - prev[j]; s2 += d * d; prev[j] = L.x[j]; }
-    if (s2 > thr2) { pi.fail = 2; return false; }                 // :954-959 (leaf)
+  for (int j = 0; j < n; j++) { const Real d = qa(j) - qb(j); d2 += d * d; }
+  P.ndivs = (int)ceil_(sqrt_(d2) / eps);                         // graph.py:946
+  P.k = 1; P.solves = 0; P.iters = 0;
+  if (P.ndivs <= 0) return false;                                // dist == 0: single leaf of length 0 -> valid
+  const Real u = Real(1) / Real(P.ndivs + 1);                    // graph.py:961
+  for (int j = 0; j < n; j++) {
+    const Real a = qa(j);
+    mem.prev(j) = a;
+    mem.xold(j) = a + u * (qb(j) - a);                           // graph.py:962
+    mem.p(j) = 0;
   }
-  Real s2 = 0;
-#pragma unroll
-  for (int j = 0; j < NA; j++) { if (N == 0 && j >= n) break; Real d = qb(j) - prev[j]; s2 += d * d; }
-  if (s2 > thr2) { pi.fail = 2; return false; }
+  lane_begin<Real, M>(L);
   return true;
 }
 
-// explicit pairs, SoA qa[n][P], qb[n][P]  (validEdge, graph.py:1051-1053)
-template <typename Real, int N, int M, int NJ>
-__global__ void __launch_bounds__(128)
-k_valid_edge_batch(const __grid_constant__ ChainDev<Real, NJ> c, long long P, const Real *__restrict__ qa,
+// One interpolated solve finished with IK_OK: leaf test against prev, advance.  Returns +1 valid,
+// 0 invalid, -1 continue with the next k (seed armed).
+template <typename Real, int M, typename ChainT, typename QA, typename QB>
+__device__ __forceinline__ int pair_advance(const ChainT &c, const LaneMem<Real, M> &mem, QA qa, QB qb, Real thr2,
+                                            PairLane &P, LaneIK<Real, M> &L) {
+  const int n = c.n;
+  const bool last = (P.k == P.ndivs);
+  const Real u = Real(P.k + 1) / Real(P.ndivs + 1);
+  Real s2 = 0, e2 = 0;
+  for (int j = 0; j < n; j++) {
+    const Real x = lane_x<Real>(c, mem.xold(j), mem.p(j), L.alam, j);
+    const Real d = x - mem.prev(j);
+    s2 += d * d;
+    const Real a = qa(j), b = qb(j);
+    const Real e = b - x;
+    e2 += e * e;
+    mem.prev(j) = x;
+    mem.xold(j) = a + u * (b - a);
+    mem.p(j) = 0;
+  }
+  if (s2 > thr2) return 0;                                       // graph.py:954-959 (leaf)
+  if (last) return (e2 > thr2) ? 0 : 1;
+  P.k++;
+  lane_begin<Real, M>(L);
+  return -1;
+}
+
+// explicit pairs, SoA qa[n][P], qb[n][P]  (validEdge, graph.py:1051-1053), work-fetching lanes
+template <typename Real, int M>
+__global__ void __launch_bounds__(256)
+k_valid_edge_batch(const __grid_constant__ ChainDev<Real, kMaxJ> c, long long total, const Real *__restrict__ qa,
                    const Real *__restrict__ qb, const Real *__restrict__ wa, const Real *__restrict__ wb, Real epsilon,
-                   uint8_t *__restrict__ valid, int32_t *__restrict__ info, unsigned long long *counters) {
-  const int dw = (c.mode == 2 ? 6 : 3);
-  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const bool live = t < P;
-  PairInfo pi = {0, 0, 0, 0, 0};
-  bool ok = false;
-  if (live) {
-    const Real eps = epsilon * sqrt_(Real(c.nlinks_eps));         // graph.py:945
-    const Real thr = eps * Real(c.nlinks_eps);                    // graph.py:947
-    Real a6[6], b6[6];
-    for (int k = 0; k < dw; k++) { a6[k] = wa[t * dw + k]; b6[k] = wb[t * dw + k]; }
-    WInterp<Real, M> W;
-    winterp_begin<Real, M, NJ>(c, a6, b6, W);
-    auto fa = [&](int j) { return qa[(long long)j * P + t]; };
-    auto fb = [&](int j) { return qb[(long long)j * P + t]; };
-    ok = valid_edge_lane<Real, N, M, NJ>(c, W, fa, fb, eps, thr, pi);
-    valid[t] = ok ? 1 : 0;
-    if (info) { info[4 * t] = pi.ndivs; info[4 * t + 1] = pi.solves; info[4 * t + 2] = pi.fail; info[4 * t + 3] = pi.iters; }
+                   uint8_t *__restrict__ valid, int32_t *__restrict__ info, unsigned long long *work,
+                   unsigned long long *counters) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int n = c.n, dw = (c.mode == 2 ? 6 : 3);
+  LaneMem<Real, M> mem{reinterpret_cast<Real *>(smem_raw) + threadIdx.x, (int)blockDim.x, n};
+  const Real eps = epsilon * sqrt_(Real(c.nlinks_eps));          // graph.py:945
+  const Real thr = eps * Real(c.nlinks_eps);                     // graph.py:947
+  const Real thr2 = thr * thr;
+  LaneIK<Real, M> L;
+  PairLane P;
+  WInterp<Real, M> W;
+  Target<Real, M> tg;
+  LaneCounters cnt;
+  long long t = -1;
+  bool done = false;
+  for (;;) {
+    int verdict = -1, fail = 0;
+    if (t < 0 && !done) {
+      const long long nt = (long long)atomicAdd(work, 1ull);
+      if (nt >= total) done = true;
+      else {
+        t = nt;
+        Real a6[6], b6[6];
+        for (int k = 0; k < dw; k++) { a6[k] = wa[t * dw + k]; b6[k] = wb[t * dw + k]; }
+        winterp_begin<Real, M, kMaxJ>(c, a6, b6, W);
+        auto fa = [&](int j) { return qa[(long long)j * total + t]; };
+        auto fb = [&](int j) { return qb[(long long)j * total + t]; };
+        if (!pair_begin<Real, M>(c, mem, fa, fb, eps, P, L)) verdict = 1;
+        else winterp_at<Real, M>(W, Real(1) / Real(P.ndivs + 1), tg);
+      }
+    }
+    if (__all_sync(0xffffffffu, done && t < 0)) break;
+    if (t >= 0 && verdict < 0) {
+      const int st = lane_trip<Real, M>(c, tg, L, mem);
+      if (st != IK_RUNNING) {
+        P.solves++; P.iters += L.it;
+        cnt.solves++; cnt.iters += L.it; cnt.evals += L.evals; cnt.ok += (st == IK_OK);
+        if (st != IK_OK) { verdict = 0; fail = 1; }               // graph.py:964-966
+        else {
+          auto fa = [&](int j) { return qa[(long long)j * total + t]; };
+          auto fb = [&](int j) { return qb[(long long)j * total + t]; };
+          verdict = pair_advance<Real, M>(c, mem, fa, fb, thr2, P, L);
+          if (verdict == 0) fail = 2;
+          if (verdict < 0) winterp_at<Real, M>(W, Real(P.k) / Real(P.ndivs + 1), tg);
+        }
+      }
+    }
+    if (t >= 0 && verdict >= 0) {
+      valid[t] = (uint8_t)verdict;
+      if (info) { info[4 * t] = P.ndivs; info[4 * t + 1] = P.solves; info[4 * t + 2] = fail; info[4 * t + 3] = P.iters; }
+      cnt.pairs++; cnt.valid += verdict;
+      t = -1;
+    }
   }
-  if (counters) {
-    warp_add(counters, GRR_CNT_PAIRS, live ? 1u : 0u);
-    warp_add(counters, GRR_CNT_VALID, ok ? 1u : 0u);
-    warp_add(counters, GRR_CNT_IK_SOLVES, (unsigned)pi.solves);
-    warp_add(counters, GRR_CNT_IK_ITERS, (unsigned)pi.iters);
-    warp_add(counters, GRR_CNT_IK_EVALS, (unsigned)pi.evals);
-  }
+  cnt.flush(counters);
 }
 
 // ------------------------------------------------------------------------------------------
 // E1/E3: all-pairs edge construction, one CTA per workspace edge
 // (connectConfigurationSpaceOnEdge solver.py:689-697 under connectConfigurationSpace :700-755).
-// Both endpoint nodes' config blocks are staged in shared memory; a warp owns one 32-pair strip
-// (row a, columns 32w..32w+31) at a time so the verdicts of a strip are one ballot = one mask word.
+// Both endpoint nodes' config blocks are staged in shared memory; lanes pull pair indices from a
+// shared-memory counter and run their pairs as independent lane machines; verdict bits are OR-ed into
+// a shared-memory Nq x Nq bitmask that is written out once.
 // ------------------------------------------------------------------------------------------
-template <typename Real, int N, int M, int NJ>
-__global__ void __launch_bounds__(128)
-k_edges_build(const __grid_constant__ ChainDev<Real, NJ> c, const int32_t *__restrict__ wedges,
+template <typename Real, int M>
+__global__ void __launch_bounds__(sizeof(Real) == 4 ? 512 : 256)
+k_edges_build(const __grid_constant__ ChainDev<Real, kMaxJ> c, const int32_t *__restrict__ wedges,
               const Real *__restrict__ params, const Real *__restrict__ q_kept, const int32_t *__restrict__ count,
-              const int32_t *__restrict__ old_count, int Nq, int Nqp, Real epsilon, uint32_t *__restrict__ mask,
+              const int32_t *__restrict__ old_count, int Nq, int Nqp, Real epsilon, uint32_t *mask,
               uint32_t *__restrict__ edge_stats, unsigned long long *counters) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int n = c.n, dw = (c.mode == 2 ? 6 : 3);
+  const int Wd = (Nq + 31) >> 5;
   Real *sa = reinterpret_cast<Real *>(smem_raw);
-  const int n = (N > 0 ? N : c.n);
   Real *sb = sa + n * Nqp;
-  __shared__ unsigned s_tested, s_valid;
+  uint32_t *smask = reinterpret_cast<uint32_t *>(sb + n * Nqp);
+  Real *lanes = reinterpret_cast<Real *>(smask + ((Nq * Wd + 3) & ~3));
+  __shared__ unsigned s_next, s_tested, s_valid, s_bits;
   const long long e = blockIdx.x;
   const int iw = wedges[2 * e], jw = wedges[2 * e + 1];
   const int ca = count[iw], cb = count[jw];
   const int oa = old_count ? old_count[iw] : 0, ob = old_count ? old_count[jw] : 0;
-  const int dw = (c.mode == 2 ? 6 : 3);
-  if (threadIdx.x == 0) { s_tested = 0; s_valid = 0; }
-  // stage both node blocks (contiguous n*Nqp chunks)
-  {
+  uint32_t *mrow = mask + e * (long long)Nq * Wd;
+  const unsigned total = (unsigned)ca * (unsigned)cb;
+  if (threadIdx.x == 0) { s_next = 0; s_tested = 0; s_valid = 0; s_bits = 0; }
+  // mask in shared memory: old verdicts of both-old pairs are kept (incremental growth, solver.py:694)
+  for (int k = threadIdx.x; k < Nq * Wd; k += blockDim.x) {
+    uint32_t w = 0;
+    if (old_count) {
+      const int a = k / Wd, b0 = (k - a * Wd) * 32;
+      if (a < oa && b0 < ob) { w = mrow[k]; if (ob - b0 < 32) w &= (1u << (ob - b0)) - 1u; }
+    }
+    smask[k] = w;
+  }
+  if (total) {
     const Real *ga = q_kept + (long long)iw * n * Nqp, *gb = q_kept + (long long)jw * n * Nqp;
     for (int k = threadIdx.x; k < n * Nqp; k += blockDim.x) { sa[k] = ga[k]; sb[k] = gb[k]; }
   }
   __syncthreads();
-  const Real eps = epsilon * sqrt_(Real(c.nlinks_eps));
-  const Real thr = eps * Real(c.nlinks_eps);
-  WInterp<Real, M> W;
-  {
-    Real a6[6], b6[6];
-    for (int k = 0; k < dw; k++) { a6[k] = params[(long long)iw * dw + k]; b6[k] = params[(long long)jw * dw + k]; }
-    winterp_begin<Real, M, NJ>(c, a6, b6, W);
-  }
-  const int Wd = (Nq + 31) >> 5;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-  unsigned tested = 0, nvalid = 0, solves = 0, its = 0, evs = 0;
-  uint32_t *mrow = mask + e * (long long)Nq * Wd;
-  for (int tile = warp; tile < Nq * Wd; tile += nwarps) {
-    const int a = tile / Wd, w = tile - a * Wd;
-    const int b = w * 32 + lane;
-    bool act = (a < ca) && (b < cb) && !(a < oa && b < ob);      // solver.py:694
-    bool ok = false;
-    if (a < ca && w * 32 < cb) {
-      if (act) {
-        PairInfo pi;
-        auto fa = [&](int j) { return sa[j * Nqp + a]; };
-        auto fb = [&](int j) { return sb[j * Nqp + b]; };
-        ok = valid_edge_lane<Real, N, M, NJ>(c, W, fa, fb, eps, thr, pi);
-        tested++; nvalid += ok; solves += pi.solves; its += pi.iters; evs += pi.evals;
+  LaneCounters cnt;
+  if (total) {
+    LaneMem<Real, M> mem{lanes + threadIdx.x, (int)blockDim.x, n};
+    const Real eps = epsilon * sqrt_(Real(c.nlinks_eps));
+    const Real thr = eps * Real(c.nlinks_eps);
+    const Real thr2 = thr * thr;
+    WInterp<Real, M> W;
+    {
+      Real a6[6], b6[6];
+      for (int k = 0; k < dw; k++) { a6[k] = params[(long long)iw * dw + k]; b6[k] = params[(long long)jw * dw + k]; }
+      winterp_begin<Real, M, kMaxJ>(c, a6, b6, W);
+    }
+    LaneIK<Real, M> L;
+    PairLane P;
+    Target<Real, M> tg;
+    int a = -1, b = 0;
+    bool done = false;
+    for (;;) {
+      int verdict = -1;
+      if (a < 0 && !done) {
+        for (;;) {                                              // next pair that is not both-old
+          const unsigned t = atomicAdd(&s_next, 1u);
+          if (t >= total) { done = true; break; }
+          const int ta = (int)(t / (unsigned)cb), tb = (int)(t - (unsigned)ta * (unsigned)cb);
+          if (ta < oa && tb < ob) continue;                     // solver.py:694
+          a = ta; b = tb;
+          break;
+        }
+        if (a >= 0) {
+          auto fa = [&](int j) { return sa[j * Nqp + a]; };
+          auto fb = [&](int j) { return sb[j * Nqp + b]; };
+          if (!pair_begin<Real, M>(c, mem, fa, fb, eps, P, L)) verdict = 1;
+          else winterp_at<Real, M>(W, Real(1) / Real(P.ndivs + 1), tg);
+        }
+      }
+      if (__all_sync(0xffffffffu, done && a < 0)) break;
+      if (a >= 0 && verdict < 0) {
+        const int st = lane_trip<Real, M>(c, tg, L, mem);
+        if (st != IK_RUNNING) {
+          cnt.solves++; cnt.iters += L.it; cnt.evals += L.evals; cnt.ok += (st == IK_OK);
+          if (st != IK_OK) verdict = 0;                         // graph.py:964-966
+          else {
+            auto fa = [&](int j) { return sa[j * Nqp + a]; };
+            auto fb = [&](int j) { return sb[j * Nqp + b]; };
+            verdict = pair_advance<Real, M>(c, mem, fa, fb, thr2, P, L);
+            if (verdict < 0) winterp_at<Real, M>(W, Real(P.k) / Real(P.ndivs + 1), tg);
+          }
+        }
+      }
+      if (a >= 0 && verdict >= 0) {
+        if (verdict) atomicOr(&smask[a * Wd + (b >> 5)], 1u << (b & 31));
+        cnt.pairs++; cnt.valid += verdict;
+        a = -1;
       }
     }
-    unsigned word = __ballot_sync(0xffffffffu, ok);
-    if (old_count) {   // incremental growth: verdicts of pairs whose endpoints are both old are kept (solver.py:694)
-      const unsigned keep = __ballot_sync(0xffffffffu, (a < oa) && (b < ob));
-      if (lane == 0) word |= mrow[tile] & keep;
-    }
-    if (lane == 0) mrow[tile] = word;
   }
-  atomicAdd(&s_tested, tested);
-  atomicAdd(&s_valid, nvalid);
-  if (counters) {
-    warp_add(counters, GRR_CNT_PAIRS, tested);
-    warp_add(counters, GRR_CNT_VALID, nvalid);
-    warp_add(counters, GRR_CNT_IK_SOLVES, solves);
-    warp_add(counters, GRR_CNT_IK_ITERS, its);
-    warp_add(counters, GRR_CNT_IK_EVALS, evs);
+  {
+    const unsigned tp = __reduce_add_sync(0xffffffffu, cnt.pairs), tv = __reduce_add_sync(0xffffffffu, cnt.valid);
+    if ((threadIdx.x & 31) == 0 && tp) { atomicAdd(&s_tested, tp); atomicAdd(&s_valid, tv); }
   }
+  cnt.flush(counters);
   __syncthreads();
-  if (threadIdx.x == 0 && edge_stats) { edge_stats[2 * e] = s_tested; edge_stats[2 * e + 1] = s_valid; }
+  unsigned nbits = 0;
+  for (int k = threadIdx.x; k < Nq * Wd; k += blockDim.x) { const uint32_t w = smask[k]; mrow[k] = w; nbits += __popc(w); }
+  if (edge_stats) {
+    // {pairs tested in this call, valid bits now stored for the edge}
+    const unsigned wbits = __reduce_add_sync(0xffffffffu, nbits);
+    if ((threadIdx.x & 31) == 0 && wbits) atomicAdd(&s_bits, wbits);
+    __syncthreads();
+    if (threadIdx.x == 0) { edge_stats[2 * e] = s_tested; edge_stats[2 * e + 1] = s_bits; }
+  }
 }
 
 // ------------------------------------------------------------------------------------------
-// launchers (one set per <Real, M>; N dispatched at run time over the instantiated list)
+// launchers
 // ------------------------------------------------------------------------------------------
 inline int check_launch(const char *what) {
   cudaError_t err = cudaGetLastError();
@@ -272,54 +349,112 @@ inline int check_launch(const char *what) {
   return 0;
 }
 
-template <typename Real, int N, int M>
+inline int sm_count(int device) {
+  static int cached[64] = {0};
+  if (device < 0 || device >= 64) device = 0;
+  if (!cached[device]) cudaDeviceGetAttribute(&cached[device], cudaDevAttrMultiProcessorCount, device);
+  return cached[device] > 0 ? cached[device] : 148;
+}
+
+constexpr size_t kSmemBudget = 226 * 1024;   // per SM, leaving the static part and the reserved 1 KB
+
+template <typename Kern>
+inline int set_smem(Kern kern, size_t smem, const char *what) {
+  if (smem > 48 * 1024) {
+    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err != cudaSuccess) { set_error("%s: dynamic shared memory %zu B: %s", what, smem, cudaGetErrorString(err)); return -2; }
+  }
+  return 0;
+}
+
+template <typename Real, int M>
 struct Impl {
-  static constexpr int NJ = (N > 0 ? N : kMaxJ);
-  using Chain = ChainDev<Real, NJ>;
+  using Chain = ChainDev<Real, kMaxJ>;
+
+  // persistent lanes: threads per CTA and CTAs so that every SM holds as many lanes as shared memory allows
+  static void lane_geometry(const HostChain &h, size_t fixed_bytes, int max_threads, int &threads, int &ctas_per_sm) {
+    const size_t per_lane = (size_t)lane_reals<M>(h.n) * sizeof(Real);
+    ctas_per_sm = 2;
+    size_t per_cta = kSmemBudget / 2 - 1024;
+    long t = per_cta > fixed_bytes ? (long)((per_cta - fixed_bytes) / per_lane) : 0;
+    if (t < 64) { ctas_per_sm = 1; per_cta = kSmemBudget - 1024; t = per_cta > fixed_bytes ? (long)((per_cta - fixed_bytes) / per_lane) : 0; }
+    if (t > max_threads) t = max_threads;
+    threads = (int)(t / 32) * 32;
+  }
+
+  static int ik_instances(int mode, const HostChain &h, long long total, int Nq, int Nqp, const void *params,
+                          const int32_t *uid, unsigned long long seed, int sample_offset, void *q, uint8_t *status,
+                          uint8_t *iters, void *resid, unsigned long long *work, unsigned long long *counters,
+                          cudaStream_t st) {
+    if (total <= 0) return 0;
+    Chain c; fill_chain(h, c);
+    int threads, per_sm;
+    lane_geometry(h, 0, 256, threads, per_sm);
+    if (threads < 32) { set_error("ik: chain too large for shared memory"); return -2; }
+    const size_t smem = (size_t)threads * lane_reals<M>(h.n) * sizeof(Real);
+    long long ctas = (long long)sm_count(h.device) * per_sm;
+    const long long need = (total + threads - 1) / threads;
+    if (ctas > need) ctas = need;
+    cudaMemsetAsync(work, 0, sizeof(unsigned long long), st);
+    if (mode == 0) {
+      auto kern = k_ik_instances<Real, M, 0>;
+      if (set_smem(kern, smem, "k_ik_instances")) return -2;
+      kern<<<(unsigned)ctas, threads, smem, st>>>(c, total, Nq, Nqp, (const Real *)params, uid, seed, sample_offset, (Real *)q,
+                                                  status, iters, (Real *)resid, work, counters);
+    } else {
+      auto kern = k_ik_instances<Real, M, 1>;
+      if (set_smem(kern, smem, "k_ik_instances")) return -2;
+      kern<<<(unsigned)ctas, threads, smem, st>>>(c, total, Nq, Nqp, (const Real *)params, uid, seed, sample_offset, (Real *)q,
+                                                  status, iters, (Real *)resid, work, counters);
+    }
+    return check_launch("k_ik_instances");
+  }
 
   static int ik_sample(const HostChain &h, long long Nw, int Nq, int Nqp, const void *params, const int32_t *uid,
                        unsigned long long seed, int sample_offset, void *q_raw, uint8_t *status, uint8_t *iters,
-                       unsigned long long *counters, cudaStream_t st) {
-    Chain c; fill_chain(h, c);
-    const long long T = Nw * (long long)Nq;
-    if (T == 0) return 0;
-    const int bs = 128;
-    k_ik_sample<Real, N, M, NJ><<<(unsigned)((T + bs - 1) / bs), bs, 0, st>>>(
-        c, Nw, Nq, Nqp, (const Real *)params, uid, seed, sample_offset, (Real *)q_raw, status, iters, counters);
-    return check_launch("k_ik_sample");
+                       unsigned long long *work, unsigned long long *counters, cudaStream_t st) {
+    return ik_instances(0, h, Nw * (long long)Nq, Nq, Nqp, params, uid, seed, sample_offset, q_raw, status, iters, nullptr,
+                        work, counters, st);
   }
   static int ik_solve_batch(const HostChain &h, long long P, const void *targets, void *q, uint8_t *status,
-                            uint8_t *iters, void *resid, unsigned long long *counters, cudaStream_t st) {
-    Chain c; fill_chain(h, c);
-    if (P == 0) return 0;
-    const int bs = 128;
-    k_ik_solve_batch<Real, N, M, NJ><<<(unsigned)((P + bs - 1) / bs), bs, 0, st>>>(
-        c, P, (const Real *)targets, (Real *)q, status, iters, (Real *)resid, counters);
-    return check_launch("k_ik_solve_batch");
+                            uint8_t *iters, void *resid, unsigned long long *work, unsigned long long *counters,
+                            cudaStream_t st) {
+    return ik_instances(1, h, P, 1, 1, targets, nullptr, 0, 0, q, status, iters, resid, work, counters, st);
   }
   static int valid_edge_batch(const HostChain &h, long long P, const void *qa, const void *qb, const void *wa,
-                              const void *wb, double epsilon, uint8_t *valid, int32_t *info,
+                              const void *wb, double epsilon, uint8_t *valid, int32_t *info, unsigned long long *work,
                               unsigned long long *counters, cudaStream_t st) {
+    if (P <= 0) return 0;
     Chain c; fill_chain(h, c);
-    if (P == 0) return 0;
-    const int bs = 128;
-    k_valid_edge_batch<Real, N, M, NJ><<<(unsigned)((P + bs - 1) / bs), bs, 0, st>>>(
-        c, P, (const Real *)qa, (const Real *)qb, (const Real *)wa, (const Real *)wb, (Real)epsilon, valid, info, counters);
+    int threads, per_sm;
+    lane_geometry(h, 0, 256, threads, per_sm);
+    if (threads < 32) { set_error("valid_edge: chain too large for shared memory"); return -2; }
+    const size_t smem = (size_t)threads * lane_reals<M>(h.n) * sizeof(Real);
+    long long ctas = (long long)sm_count(h.device) * per_sm;
+    const long long need = (P + threads - 1) / threads;
+    if (ctas > need) ctas = need;
+    auto kern = k_valid_edge_batch<Real, M>;
+    if (set_smem(kern, smem, "k_valid_edge_batch")) return -2;
+    cudaMemsetAsync(work, 0, sizeof(unsigned long long), st);
+    kern<<<(unsigned)ctas, threads, smem, st>>>(c, P, (const Real *)qa, (const Real *)qb, (const Real *)wa, (const Real *)wb,
+                                                (Real)epsilon, valid, info, work, counters);
     return check_launch("k_valid_edge_batch");
   }
   static int edges_build(const HostChain &h, long long E, const int32_t *wedges, const void *params, const void *q_kept,
                          const int32_t *count, const int32_t *old_count, int Nq, int Nqp, double epsilon,
                          uint32_t *mask, uint32_t *edge_stats, unsigned long long *counters, cudaStream_t st) {
+    if (E <= 0) return 0;
     Chain c; fill_chain(h, c);
-    if (E == 0) return 0;
-    const size_t smem = 2 * (size_t)h.n * Nqp * sizeof(Real);
-    auto kern = k_edges_build<Real, N, M, NJ>;
-    if (smem > 48 * 1024) {
-      cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      if (err != cudaSuccess) { set_error("edges_build: shared memory %zu B: %s", smem, cudaGetErrorString(err)); return -2; }
-    }
-    kern<<<(unsigned)E, 128, smem, st>>>(c, wedges, (const Real *)params, (const Real *)q_kept, count, old_count, Nq, Nqp,
-                                         (Real)epsilon, mask, edge_stats, counters);
+    const int Wd = (Nq + 31) / 32;
+    const size_t fixed = 2 * (size_t)h.n * Nqp * sizeof(Real) + (size_t)((Nq * Wd + 3) & ~3) * sizeof(uint32_t);
+    int threads, per_sm;
+    lane_geometry(h, fixed, sizeof(Real) == 4 ? 512 : 256, threads, per_sm);
+    if (threads < 32) { set_error("edges_build: Nq=%d, n=%d does not fit shared memory", Nq, h.n); return -2; }
+    const size_t smem = fixed + (size_t)threads * lane_reals<M>(h.n) * sizeof(Real);
+    auto kern = k_edges_build<Real, M>;
+    if (set_smem(kern, smem, "k_edges_build")) return -2;
+    kern<<<(unsigned)E, threads, smem, st>>>(c, wedges, (const Real *)params, (const Real *)q_kept, count, old_count, Nq, Nqp,
+                                             (Real)epsilon, mask, edge_stats, counters);
     return check_launch("k_edges_build");
   }
 };

@@ -119,8 +119,9 @@ int grr_dedup(grr_handle_t h, int dtype, int64_t Nw, int32_t Nq, int32_t Nqp, co
  * 484-501; graph.py:938-1006).  For every workspace edge e=(iw,jw), iw<jw, and every pair
  * (a<count[iw], b<count[jw]) not both older than old_count (nullable), runs the validEdge
  * predicate and sets bit b of mask[e][a][b/32].  mask [dev] u32 [E][Nq][W], W=(Nq+31)/32, is
- * fully overwritten for the edges given.  edge_stats [dev] u32 [E][2] = {pairs tested, valid}
- * (nullable); counters nullable. */
+ * fully overwritten for the edges given (bits of both-old pairs are carried over when old_count is
+ * given).  edge_stats [dev] u32 [E][2] = {pairs tested by this call, valid bits now stored for the
+ * edge} (nullable); counters nullable. */
 int grr_edges_build(grr_handle_t h, int dtype, int64_t E, const int32_t *wedges, const void *params,
                     const void *q_kept, const int32_t *count, const int32_t *old_count, int32_t Nq,
                     int32_t Nqp, double epsilon, uint32_t *mask, uint32_t *edge_stats, uint64_t *counters,
