@@ -60,6 +60,7 @@ struct ChainDev {
   Real tp[NJ][3];
   Real ax[NJ][3];
   Real bmin[NJ], bmax[NJ];     // +-inf for revolute joints with range >= 2 pi
+  int kind[NJ];                // 0 generic; 1/2/3: identity preceding rotation and axis = +-e_x / e_y / e_z
   float slo[NJ], srange[NJ];   // random-start sampling box, single precision by specification
   Real ee[3];
   Real Rtail[9];

@@ -2,6 +2,7 @@
 #pragma once
 #include "grr_device.cuh"
 #include "grr_host.h"
+#include <math.h>
 
 namespace grr {
 
@@ -21,6 +22,15 @@ void fill_chain(const HostChain &h, ChainDev<Real, NJ> &d) {
     }
     for (int k = 0; k < 9; k++) { d.A[j][k] = (Real)(R[k] + RK2[k]); d.B[j][k] = (Real)RK[k]; d.C[j][k] = (Real)RK2[k]; }
     for (int k = 0; k < 3; k++) { d.tp[j][k] = (Real)h.tp[3 * j + k]; d.ax[j][k] = (Real)a[k]; }
+    {
+      bool ident = true;
+      for (int k = 0; k < 9; k++) ident = ident && (fabs(R[k] - ((k % 4 == 0) ? 1.0 : 0.0)) < 1e-14);
+      int kind = 0;
+      for (int k = 0; k < 3; k++)
+        if (ident && fabs(fabs(a[k]) - 1.0) < 1e-14 && fabs(a[(k + 1) % 3]) < 1e-14 && fabs(a[(k + 2) % 3]) < 1e-14) kind = k + 1;
+      d.kind[j] = kind;
+      if (kind) for (int k = 0; k < 3; k++) d.ax[j][k] = (Real)(k == kind - 1 ? (a[k] > 0 ? 1.0 : -1.0) : 0.0);
+    }
     const bool unbounded = (h.qmax[j] - h.qmin[j]) >= 2.0 * 3.14159265358979323846;
     d.bmin[j] = unbounded ? -std::numeric_limits<Real>::infinity() : (Real)h.qmin[j];
     d.bmax[j] = unbounded ? std::numeric_limits<Real>::infinity() : (Real)h.qmax[j];

@@ -45,7 +45,11 @@ k_ik_instances(const __grid_constant__ ChainDev<Real, kMaxJ> c, long long total,
   const int n = c.n, dw = (c.mode == 2 ? 6 : 3);
   LaneMem<Real, M> mem{reinterpret_cast<Real *>(smem_raw) + threadIdx.x, (int)blockDim.x, n};
   LaneIK<Real, M> L;
+  lane_begin_mem<Real, M>(L, mem);
   Target<Real, M> tg;
+  tg.x[0] = tg.x[1] = tg.x[2] = 0;
+  if (M == 6) { for (int k = 0; k < 9; k++) tg.R[k] = (k % 4 == 0) ? Real(1) : Real(0); }
+  for (int j = 0; j < n; j++) { mem.xold()[j * mem.T] = 0; mem.p()[j * mem.T] = 0; }
   LaneCounters cnt;
   long long inst = -1;
   bool done = false;
@@ -56,6 +60,7 @@ k_ik_instances(const __grid_constant__ ChainDev<Real, kMaxJ> c, long long total,
       else {
         inst = t;
         Real w[6];
+        Real *xo = mem.xold();
         if (MODE == 0) {
           const long long node = t / Nq;
           const int s = (int)(t - node * Nq);
@@ -68,23 +73,24 @@ k_ik_instances(const __grid_constant__ ChainDev<Real, kMaxJ> c, long long total,
               const int j = jb * 4 + k;
               if (j < n) {
                 const float u = (float)(r[k] >> 8) * (1.0f / 16777216.0f);
-                mem.xold(j) = (Real)fmaf(u, c.srange[j], c.slo[j]);
-                mem.p(j) = 0;
+                xo[j * mem.T] = (Real)fmaf(u, c.srange[j], c.slo[j]);
               }
             }
           }
           for (int k = 0; k < dw; k++) w[k] = params[node * dw + k];
         } else {
-          for (int j = 0; j < n; j++) { mem.xold(j) = q[(long long)j * total + t]; mem.p(j) = 0; }
+          for (int j = 0; j < n; j++) xo[j * mem.T] = q[(long long)j * total + t];
           for (int k = 0; k < dw; k++) w[k] = params[t * dw + k];
         }
         target_from_params<Real, M, kMaxJ>(c, w, tg);
-        lane_begin<Real, M>(L);
+        lane_begin_mem<Real, M>(L, mem);
       }
     }
-    if (__all_sync(0xffffffffu, done && inst < 0)) break;
+    if (__all_sync(0xffffffffu, inst < 0)) break;
+    PassOut<Real, M> o;
+    lane_pass<Real, M>(c, tg, L.src, mem, o);
     if (inst >= 0) {
-      const int st = lane_trip<Real, M>(c, tg, L, mem);
+      const int st = lane_step<Real, M>(c, L, mem, o);
       if (st != IK_RUNNING) {
         long long base, stride, sidx;
         if (MODE == 0) {
@@ -92,7 +98,7 @@ k_ik_instances(const __grid_constant__ ChainDev<Real, kMaxJ> c, long long total,
           const int s = (int)(inst - node * Nq);
           base = node * n * (long long)Nqp + s; stride = Nqp; sidx = node * Nqp + s;
         } else { base = inst; stride = total; sidx = inst; }
-        for (int j = 0; j < n; j++) q[base + j * stride] = lane_x<Real>(c, mem.xold(j), mem.p(j), L.alam, j);
+        for (int j = 0; j < n; j++) q[base + j * stride] = src_x<Real>(c, L.src, j);
         status[sidx] = (uint8_t)st;
         if (iters) iters[sidx] = (uint8_t)L.it;
         if (resid) resid[sidx] = L.resid;
@@ -109,57 +115,51 @@ k_ik_instances(const __grid_constant__ ChainDev<Real, kMaxJ> c, long long total,
 // valid <=> every interpolated IK k=1..Ndivs (seed lerp(qa,qb,u_k), target winterp(wa,wb,u_k))
 // converges and every consecutive distance (qa, q_1, ..., q_Ndivs, qb) is <= thr.  The BFS order of
 // the reference only changes which failure is met first, never the verdict.
+// The endpoint configs are read in place: qa[j*sa], qb[j*sb].
 // ------------------------------------------------------------------------------------------
+template <typename Real>
 struct PairLane {
+  const Real *qa, *qb;
+  int sa, sb;
   int k, ndivs;       // current interpolation index, graph.py:946
   int solves, iters;  // diagnostics
 };
 
-// Begin pair: distance -> Ndivs, prev <- qa, seed of k=1.  Returns false if the pair is decided already.
-template <typename Real, int M, typename ChainT, typename QA, typename QB>
-__device__ __forceinline__ bool pair_begin(const ChainT &c, const LaneMem<Real, M> &mem, QA qa, QB qb, Real eps,
-                                           PairLane &P, LaneIK<Real, M> &L) {
+// Begin pair: distance -> Ndivs, arm the seed of k=1.  Returns false if the pair is decided already.
+template <typename Real, int M, typename ChainT>
+__device__ __forceinline__ bool pair_begin(const ChainT &c, Real eps, PairLane<Real> &P, LaneIK<Real, M> &L) {
   const int n = c.n;
   Real d2 = 0;
-  for (int j = 0; j < n; j++) { const Real d = qa(j) - qb(j); d2 += d * d; }
+  for (int j = 0; j < n; j++) { const Real d = P.qa[j * P.sa] - P.qb[j * P.sb]; d2 += d * d; }
   P.ndivs = (int)ceil_(sqrt_(d2) / eps);                         // graph.py:946
   P.k = 1; P.solves = 0; P.iters = 0;
   if (P.ndivs <= 0) return false;                                // dist == 0: single leaf of length 0 -> valid
-  const Real u = Real(1) / Real(P.ndivs + 1);                    // graph.py:961
-  for (int j = 0; j < n; j++) {
-    const Real a = qa(j);
-    mem.prev(j) = a;
-    mem.xold(j) = a + u * (qb(j) - a);                           // graph.py:962
-    mem.p(j) = 0;
-  }
-  lane_begin<Real, M>(L);
+  lane_begin_lerp<Real, M>(L, P.qa, P.sa, P.qb, P.sb, Real(1) / Real(P.ndivs + 1));   // graph.py:961-962
   return true;
 }
 
-// One interpolated solve finished with IK_OK: leaf test against prev, advance.  Returns +1 valid,
-// 0 invalid, -1 continue with the next k (seed armed).
-template <typename Real, int M, typename ChainT, typename QA, typename QB>
-__device__ __forceinline__ int pair_advance(const ChainT &c, const LaneMem<Real, M> &mem, QA qa, QB qb, Real thr2,
-                                            PairLane &P, LaneIK<Real, M> &L) {
-  const int n = c.n;
+// One interpolated solve finished with IK_OK: leaf test against the previous solution, advance.
+// Returns +1 valid, 0 invalid, -1 continue with the next k (seed armed).
+template <typename Real, int M, typename ChainT>
+__device__ __forceinline__ int pair_advance(const ChainT &c, const LaneMem<Real, M> &mem, Real thr2, PairLane<Real> &P,
+                                            LaneIK<Real, M> &L) {
+  const int n = c.n, T = mem.T;
   const bool last = (P.k == P.ndivs);
-  const Real u = Real(P.k + 1) / Real(P.ndivs + 1);
+  const Real *pv = (P.k == 1) ? P.qa : mem.prev();               // q_0 = qa
+  const int sv = (P.k == 1) ? P.sa : T;
+  Real *pw = mem.prev();
   Real s2 = 0, e2 = 0;
   for (int j = 0; j < n; j++) {
-    const Real x = lane_x<Real>(c, mem.xold(j), mem.p(j), L.alam, j);
-    const Real d = x - mem.prev(j);
+    const Real x = src_x<Real>(c, L.src, j);
+    const Real d = x - pv[j * sv];
     s2 += d * d;
-    const Real a = qa(j), b = qb(j);
-    const Real e = b - x;
-    e2 += e * e;
-    mem.prev(j) = x;
-    mem.xold(j) = a + u * (b - a);
-    mem.p(j) = 0;
+    if (last) { const Real e = P.qb[j * P.sb] - x; e2 += e * e; }
+    pw[j * T] = x;
   }
   if (s2 > thr2) return 0;                                       // graph.py:954-959 (leaf)
   if (last) return (e2 > thr2) ? 0 : 1;
   P.k++;
-  lane_begin<Real, M>(L);
+  lane_begin_lerp<Real, M>(L, P.qa, P.sa, P.qb, P.sb, Real(P.k) / Real(P.ndivs + 1));
   return -1;
 }
 
@@ -177,9 +177,13 @@ k_valid_edge_batch(const __grid_constant__ ChainDev<Real, kMaxJ> c, long long to
   const Real thr = eps * Real(c.nlinks_eps);                     // graph.py:947
   const Real thr2 = thr * thr;
   LaneIK<Real, M> L;
-  PairLane P;
+  lane_begin_mem<Real, M>(L, mem);
+  for (int j = 0; j < n; j++) { mem.xold()[j * mem.T] = 0; mem.p()[j * mem.T] = 0; }
+  PairLane<Real> P;
   WInterp<Real, M> W;
   Target<Real, M> tg;
+  tg.x[0] = tg.x[1] = tg.x[2] = 0;
+  if (M == 6) { for (int k = 0; k < 9; k++) tg.R[k] = (k % 4 == 0) ? Real(1) : Real(0); }
   LaneCounters cnt;
   long long t = -1;
   bool done = false;
@@ -193,23 +197,23 @@ k_valid_edge_batch(const __grid_constant__ ChainDev<Real, kMaxJ> c, long long to
         Real a6[6], b6[6];
         for (int k = 0; k < dw; k++) { a6[k] = wa[t * dw + k]; b6[k] = wb[t * dw + k]; }
         winterp_begin<Real, M, kMaxJ>(c, a6, b6, W);
-        auto fa = [&](int j) { return qa[(long long)j * total + t]; };
-        auto fb = [&](int j) { return qb[(long long)j * total + t]; };
-        if (!pair_begin<Real, M>(c, mem, fa, fb, eps, P, L)) verdict = 1;
+        P.qa = qa + t; P.qb = qb + t; P.sa = (int)total; P.sb = (int)total;
+        if (!pair_begin<Real, M>(c, eps, P, L)) verdict = 1;
         else winterp_at<Real, M>(W, Real(1) / Real(P.ndivs + 1), tg);
       }
     }
-    if (__all_sync(0xffffffffu, done && t < 0)) break;
-    if (t >= 0 && verdict < 0) {
-      const int st = lane_trip<Real, M>(c, tg, L, mem);
+    const bool running = (t >= 0 && verdict < 0);
+    if (__all_sync(0xffffffffu, t < 0)) break;
+    PassOut<Real, M> o;
+    if (__any_sync(0xffffffffu, running)) lane_pass<Real, M>(c, tg, L.src, mem, o);
+    if (running) {
+      const int st = lane_step<Real, M>(c, L, mem, o);
       if (st != IK_RUNNING) {
         P.solves++; P.iters += L.it;
         cnt.solves++; cnt.iters += L.it; cnt.evals += L.evals; cnt.ok += (st == IK_OK);
         if (st != IK_OK) { verdict = 0; fail = 1; }               // graph.py:964-966
         else {
-          auto fa = [&](int j) { return qa[(long long)j * total + t]; };
-          auto fb = [&](int j) { return qb[(long long)j * total + t]; };
-          verdict = pair_advance<Real, M>(c, mem, fa, fb, thr2, P, L);
+          verdict = pair_advance<Real, M>(c, mem, thr2, P, L);
           if (verdict == 0) fail = 2;
           if (verdict < 0) winterp_at<Real, M>(W, Real(P.k) / Real(P.ndivs + 1), tg);
         }
@@ -220,6 +224,7 @@ k_valid_edge_batch(const __grid_constant__ ChainDev<Real, kMaxJ> c, long long to
       if (info) { info[4 * t] = P.ndivs; info[4 * t + 1] = P.solves; info[4 * t + 2] = fail; info[4 * t + 3] = P.iters; }
       cnt.pairs++; cnt.valid += verdict;
       t = -1;
+      lane_begin_mem<Real, M>(L, mem);     // idle lanes keep walking valid memory
     }
   }
   cnt.flush(counters);
@@ -266,10 +271,11 @@ k_edges_build(const __grid_constant__ ChainDev<Real, kMaxJ> c, const int32_t *__
     const Real *ga = q_kept + (long long)iw * n * Nqp, *gb = q_kept + (long long)jw * n * Nqp;
     for (int k = threadIdx.x; k < n * Nqp; k += blockDim.x) { sa[k] = ga[k]; sb[k] = gb[k]; }
   }
+  LaneMem<Real, M> mem{lanes + threadIdx.x, (int)blockDim.x, n};
+  for (int j = 0; j < n; j++) { mem.xold()[j * mem.T] = 0; mem.p()[j * mem.T] = 0; }
   __syncthreads();
   LaneCounters cnt;
   if (total) {
-    LaneMem<Real, M> mem{lanes + threadIdx.x, (int)blockDim.x, n};
     const Real eps = epsilon * sqrt_(Real(c.nlinks_eps));
     const Real thr = eps * Real(c.nlinks_eps);
     const Real thr2 = thr * thr;
@@ -280,8 +286,11 @@ k_edges_build(const __grid_constant__ ChainDev<Real, kMaxJ> c, const int32_t *__
       winterp_begin<Real, M, kMaxJ>(c, a6, b6, W);
     }
     LaneIK<Real, M> L;
-    PairLane P;
+    lane_begin_mem<Real, M>(L, mem);
+    PairLane<Real> P;
     Target<Real, M> tg;
+    tg.x[0] = tg.x[1] = tg.x[2] = 0;
+    if (M == 6) { for (int k = 0; k < 9; k++) tg.R[k] = (k % 4 == 0) ? Real(1) : Real(0); }
     int a = -1, b = 0;
     bool done = false;
     for (;;) {
@@ -296,22 +305,22 @@ k_edges_build(const __grid_constant__ ChainDev<Real, kMaxJ> c, const int32_t *__
           break;
         }
         if (a >= 0) {
-          auto fa = [&](int j) { return sa[j * Nqp + a]; };
-          auto fb = [&](int j) { return sb[j * Nqp + b]; };
-          if (!pair_begin<Real, M>(c, mem, fa, fb, eps, P, L)) verdict = 1;
+          P.qa = sa + a; P.qb = sb + b; P.sa = Nqp; P.sb = Nqp;
+          if (!pair_begin<Real, M>(c, eps, P, L)) verdict = 1;
           else winterp_at<Real, M>(W, Real(1) / Real(P.ndivs + 1), tg);
         }
       }
-      if (__all_sync(0xffffffffu, done && a < 0)) break;
-      if (a >= 0 && verdict < 0) {
-        const int st = lane_trip<Real, M>(c, tg, L, mem);
+      const bool running = (a >= 0 && verdict < 0);
+      if (__all_sync(0xffffffffu, a < 0)) break;
+      PassOut<Real, M> o;
+      if (__any_sync(0xffffffffu, running)) lane_pass<Real, M>(c, tg, L.src, mem, o);
+      if (running) {
+        const int st = lane_step<Real, M>(c, L, mem, o);
         if (st != IK_RUNNING) {
           cnt.solves++; cnt.iters += L.it; cnt.evals += L.evals; cnt.ok += (st == IK_OK);
           if (st != IK_OK) verdict = 0;                         // graph.py:964-966
           else {
-            auto fa = [&](int j) { return sa[j * Nqp + a]; };
-            auto fb = [&](int j) { return sb[j * Nqp + b]; };
-            verdict = pair_advance<Real, M>(c, mem, fa, fb, thr2, P, L);
+            verdict = pair_advance<Real, M>(c, mem, thr2, P, L);
             if (verdict < 0) winterp_at<Real, M>(W, Real(P.k) / Real(P.ndivs + 1), tg);
           }
         }
@@ -320,6 +329,7 @@ k_edges_build(const __grid_constant__ ChainDev<Real, kMaxJ> c, const int32_t *__
         if (verdict) atomicOr(&smask[a * Wd + (b >> 5)], 1u << (b & 31));
         cnt.pairs++; cnt.valid += verdict;
         a = -1;
+        lane_begin_mem<Real, M>(L, mem);   // idle lanes keep walking valid memory
       }
     }
   }

@@ -1,16 +1,24 @@
 // grr_lane.cuh -- the per-lane IK machine used by every kernel of the path.
 //
-// Design (B200-first; measured motivation in profiles/r01_edge_v1_ncu.md):
+// Design (B200-first; measured motivation in profiles/r01_edge_kernel.md):
 //   * one lane = one IK instance at a time, advanced one "trip" (= one backward chain pass + the
 //     Newton / line-search transition) per loop iteration.  Lanes of a warp are never in lock step on
 //     an instance: a lane that finishes fetches its next instance immediately, so the only divergent
 //     code is the short transition logic, never the chain pass (v1: 8.3 of 32 lanes active).
-//   * the joint loop is ROLLED.  A fully unrolled 20-joint pass is ~100 KB of SASS and ran at a 51 %
-//     instruction-cache hit rate; rolled it is a few KB.  Per-lane joint vectors (line-search origin
-//     xold, direction p, previous interpolated solution prev, Jacobian columns) live in shared memory
-//     in [element][lane] order (bank = lane: conflict-free), indexed by the rolled joint counter; the
-//     chain constants are read from the constant bank with a warp-uniform index.
-//   * the trial point is never stored: x_j = clamp(xold_j + alam * p_j) is recomputed where needed.
+//   * the joint loop is ROLLED and executed by every lane of the warp unconditionally, so the joint
+//     counter is warp-uniform and the chain constants come straight from the constant bank through
+//     the uniform datapath.  (v1, fully unrolled over 20 joints, was ~100 KB of SASS and ran at a 51 %
+//     instruction-cache hit rate.)  Per-lane joint vectors (line-search origin xold, direction p,
+//     previous interpolated solution prev, Jacobian columns) live in shared memory in [element][lane]
+//     order (bank = lane: conflict-free) and are walked with running pointers.
+//   * joints whose preceding constant rotation is the identity and whose axis is a coordinate axis
+//     (every joint of the planar robots, most joints of the arms) take a short path: the joint
+//     transform touches two rows / two components only.
+//   * the trial point is never stored: x_j = clamp(base_j + t * dir_j), with (base, dir, t) =
+//     (xold, p, alam) during a line search and (qa, qb - qa, u) for the first evaluation of an
+//     interpolated solve, so starting an instance needs no seed-writing loop.
+//   * single precision uses a branch-free Cody-Waite + minimax sincos and MUFU-based reciprocal /
+//     rsqrt in the transition logic (IEEE division's slow path was 11 % of all issued instructions).
 //
 // Restates (reference file:line in the reference repository): NewtonRoot::GlobalSolve as driven by
 // IKDB/Klamp't (call sites grr/graph.py:779-790, grr/solver.py:799,821,884).
@@ -19,123 +27,255 @@
 
 namespace grr {
 
-using Chain32f = ChainDev<float, kMaxJ>;
+// ---- fast scalar helpers (float: MUFU based; double: exact) ---------------------------------
+__device__ __forceinline__ float fdiv_(float a, float b) { return __fdividef(a, b); }
+__device__ __forceinline__ double fdiv_(double a, double b) { return a / b; }
+__device__ __forceinline__ float rsqrt_(float a) { return rsqrtf(a); }
+__device__ __forceinline__ double rsqrt_(double a) { return 1.0 / sqrt(a); }
 
-// floats (Reals) of shared memory one lane needs
+// sin/cos for joint angles (|x| << 2^22): Cody-Waite reduction to [-pi/4, pi/4] with the
+// round-to-nearest magic constant (no F2I / I2F), cephes minimax polynomials, quadrant fix-up.
+__device__ __forceinline__ void sincos_joint(float x, float *s, float *c) {
+  const float t = fmaf(x, 0.636619772367581343f, 12582912.0f);
+  const int q = __float_as_int(t);
+  const float k = t - 12582912.0f;
+  float r = fmaf(k, -1.5707962512969970703f, x);
+  r = fmaf(k, -7.5497894158615963534e-08f, r);
+  r = fmaf(k, -5.3903029534742383927e-15f, r);
+  const float r2 = r * r;
+  float sp = fmaf(r2, -1.9515295891e-4f, 8.3321608736e-3f);
+  sp = fmaf(sp, r2, -1.6666654611e-1f);
+  sp = fmaf(sp * r2, r, r);
+  float cp = fmaf(r2, 2.443315711809948e-5f, -1.388731625493765e-3f);
+  cp = fmaf(cp, r2, 4.166664568298827e-2f);
+  cp = fmaf(cp * r2, r2, fmaf(r2, -0.5f, 1.0f));
+  const float ss = (q & 1) ? cp : sp;
+  const float cc = (q & 1) ? sp : cp;
+  *s = (q & 2) ? -ss : ss;
+  *c = ((q + 1) & 2) ? -cc : cc;
+}
+__device__ __forceinline__ void sincos_joint(double x, double *s, double *c) { sincos(x, s, c); }
+
+// floats (Reals) of shared memory one lane needs: xold, p, prev, columns
 template <int M> __host__ __device__ constexpr int lane_reals(int n) { return n * (3 + M); }
 
-// Shared-memory view of one lane's joint vectors.  Element k of array `arr` of lane `tid` lives at
-// base[(off_arr + k) * T + tid].
+// Shared-memory view of one lane's joint vectors: element k of an array lives at ptr[k * T].
 template <typename Real, int M>
 struct LaneMem {
   Real *base;   // already offset by tid
   int T;        // lanes per CTA (stride)
   int n;
-  __device__ __forceinline__ Real &xold(int j) const { return base[j * T]; }
-  __device__ __forceinline__ Real &p(int j) const { return base[(n + j) * T]; }
-  __device__ __forceinline__ Real &prev(int j) const { return base[(2 * n + j) * T]; }
-  __device__ __forceinline__ Real &col(int j, int r) const { return base[(3 * n + j * M + r) * T]; }
+  __device__ __forceinline__ Real *xold() const { return base; }
+  __device__ __forceinline__ Real *p() const { return base + n * T; }
+  __device__ __forceinline__ Real *prev() const { return base + 2 * n * T; }
+  __device__ __forceinline__ Real *cols() const { return base + 3 * n * T; }   // [j][r], r < M
+};
+
+// Where the current trial point comes from: x_j = clamp(a[j*sa] + t * (lerp ? b[j*sb] - a[j*sa] : b[j*sb])).
+template <typename Real>
+struct XSrc {
+  const Real *a, *b;
+  int sa, sb;
+  Real t;
+  bool lerp;
 };
 
 template <typename Real, int M>
 struct LaneIK {
   Real fold, slope, alam, alam2, f2, alamin, stpmax, resid;
   int it, evals, phase;
+  XSrc<Real> src;
 };
 
-// Start an instance: the seed must already be in mem.xold; p is zeroed so that x = clamp(seed).
 template <typename Real, int M>
-__device__ __forceinline__ void lane_begin(LaneIK<Real, M> &L) {
+__device__ __forceinline__ void lane_reset(LaneIK<Real, M> &L) {
   L.it = 0; L.evals = 0; L.phase = 0;
   L.alam = 0; L.alam2 = 0; L.f2 = 0; L.fold = 0; L.slope = 0; L.alamin = 0; L.stpmax = 0; L.resid = 0;
 }
-
-template <typename Real, typename ChainT>
-__device__ __forceinline__ Real lane_x(const ChainT &c, Real xold, Real p, Real alam, int j) {
-  return min_(max_(xold + alam * p, c.bmin[j]), c.bmax[j]);
+// Start an instance whose seed is lerp(qa, qb, u) read from (a, b) with strides (sa, sb).
+template <typename Real, int M>
+__device__ __forceinline__ void lane_begin_lerp(LaneIK<Real, M> &L, const Real *a, int sa, const Real *b, int sb, Real u) {
+  lane_reset(L);
+  L.src.a = a; L.src.b = b; L.src.sa = sa; L.src.sb = sb; L.src.t = u; L.src.lerp = true;
+}
+// Start an instance whose seed has been written to mem.xold (mem.p is ignored: t = 0).
+template <typename Real, int M>
+__device__ __forceinline__ void lane_begin_mem(LaneIK<Real, M> &L, const LaneMem<Real, M> &mem) {
+  lane_reset(L);
+  L.src.a = mem.xold(); L.src.b = mem.p(); L.src.sa = mem.T; L.src.sb = mem.T; L.src.t = 0; L.src.lerp = false;
 }
 
-// One trip.  Returns IK_RUNNING or the final status.  After a final status the solution is
-// x_j = lane_x(xold_j, p_j, alam) (for IK_STALL the caller must use xold).
+template <typename Real, typename ChainT>
+__device__ __forceinline__ Real src_x(const ChainT &c, const XSrc<Real> &s, int j) {
+  const Real av = s.a[j * s.sa], bv = s.b[j * s.sb];
+  const Real dir = s.lerp ? bv - av : bv;
+  return min_(max_(av + s.t * dir, c.bmin[j]), c.bmax[j]);
+}
+
+// short joint: identity preceding rotation, axis = sgn * e_K.  (I1, I2) are the two components the
+// rotation mixes: new_I1 = c a_I1 - s a_I2, new_I2 = s a_I1 + c a_I2.
+template <typename Real, int M, int K>
+__device__ __forceinline__ void joint_axis(Real s, Real co, Real sgn, Real *v, Real *G, Real *col) {
+  constexpr int I1 = (K + 1) % 3, I2 = (K + 2) % 3;
+  // column: G^T (axis x v), axis x v has components I1: -sgn v_I2, I2: +sgn v_I1
+  const Real w1 = -sgn * v[I2], w2 = sgn * v[I1];
+#pragma unroll
+  for (int r = 0; r < 3; r++) col[r] = G[3 * I1 + r] * w1 + G[3 * I2 + r] * w2;
+  if (M == 6) {
+#pragma unroll
+    for (int r = 0; r < 3; r++) col[3 + r] = sgn * G[3 * K + r];
+  }
+  const Real a1 = v[I1], a2 = v[I2];
+  v[I1] = co * a1 - s * a2;
+  v[I2] = s * a1 + co * a2;
+#pragma unroll
+  for (int r = 0; r < 3; r++) {
+    const Real g1 = G[3 * I1 + r], g2 = G[3 * I2 + r];
+    G[3 * I1 + r] = co * g1 - s * g2;
+    G[3 * I2 + r] = s * g1 + co * g2;
+  }
+}
+
+// ---- the chain pass: executed by EVERY lane of the warp (uniform joint counter) ----------------
+template <typename Real, int M>
+struct PassOut {
+  Real Fw[M], FL[M], f, fmax, xn2;
+  Real S[M * (M + 1) / 2];
+};
+
 template <typename Real, int M, typename ChainT>
-__device__ __forceinline__ int lane_trip(const ChainT &c, const Target<Real, M> &tg, LaneIK<Real, M> &L,
-                                         const LaneMem<Real, M> &mem) {
+__device__ __forceinline__ void lane_pass(const ChainT &c, const Target<Real, M> &tg, const XSrc<Real> &src,
+                                          const LaneMem<Real, M> &mem, PassOut<Real, M> &o) {
   const int n = c.n;
-  const Real tolf = c.tol, tolx = Real(0.01) * c.tol, ALF = Real(1e-4);
-  // ---- backward chain pass at x = clamp(xold + alam p) ----
-  Real v0 = c.ee[0], v1 = c.ee[1], v2 = c.ee[2];
+  Real v[3] = {c.ee[0], c.ee[1], c.ee[2]};
   Real G[9];
 #pragma unroll
   for (int k = 0; k < 9; k++) G[k] = c.Rtail[k];
-  Real S[M * (M + 1) / 2];
 #pragma unroll
-  for (int k = 0; k < M * (M + 1) / 2; k++) S[k] = 0;
+  for (int k = 0; k < M * (M + 1) / 2; k++) o.S[k] = 0;
   Real xn2 = 0;
+  const int T = mem.T;
+  const Real *pa = src.a + (n - 1) * src.sa, *pb = src.b + (n - 1) * src.sb;
+  Real *pc = mem.cols() + (n - 1) * M * T;
 #pragma unroll 1
   for (int j = n - 1; j >= 0; --j) {
-    const Real xj = lane_x<Real>(c, mem.xold(j), mem.p(j), L.alam, j);
+    const Real av = *pa, bv = *pb;
+    pa -= src.sa; pb -= src.sb;
+    const Real dir = src.lerp ? bv - av : bv;
+    const Real xj = min_(max_(av + src.t * dir, c.bmin[j]), c.bmax[j]);
     xn2 += xj * xj;
     Real s, co;
-    sincos_(xj, &s, &co);
-    Real Mj[9];
-#pragma unroll
-    for (int k = 0; k < 9; k++) Mj[k] = c.A[j][k] + s * c.B[j][k] - co * c.C[j][k];
-    const Real a0 = c.ax[j][0], a1 = c.ax[j][1], a2 = c.ax[j][2];
-    const Real w0 = a1 * v2 - a2 * v1, w1 = a2 * v0 - a0 * v2, w2 = a0 * v1 - a1 * v0;
+    sincos_joint(xj, &s, &co);
     Real col[M];
+    const int kind = c.kind[j];
+    if (kind == 0) {
+      Real Mj[9];
 #pragma unroll
-    for (int r = 0; r < 3; r++) col[r] = G[r] * w0 + G[3 + r] * w1 + G[6 + r] * w2;      // G^T (axis x v)
-    if (M == 6) {
+      for (int k = 0; k < 9; k++) Mj[k] = c.A[j][k] + s * c.B[j][k] - co * c.C[j][k];
+      const Real a0 = c.ax[j][0], a1 = c.ax[j][1], a2 = c.ax[j][2];
+      const Real w0 = a1 * v[2] - a2 * v[1], w1 = a2 * v[0] - a0 * v[2], w2 = a0 * v[1] - a1 * v[0];
 #pragma unroll
-      for (int r = 0; r < 3; r++) col[3 + r] = G[r] * a0 + G[3 + r] * a1 + G[6 + r] * a2;  // G^T axis
+      for (int r = 0; r < 3; r++) col[r] = G[r] * w0 + G[3 + r] * w1 + G[6 + r] * w2;      // G^T (axis x v)
+      if (M == 6) {
+#pragma unroll
+        for (int r = 0; r < 3; r++) col[3 + r] = G[r] * a0 + G[3 + r] * a1 + G[6 + r] * a2;  // G^T axis
+      }
+      const Real n0 = Mj[0] * v[0] + Mj[1] * v[1] + Mj[2] * v[2];
+      const Real n1 = Mj[3] * v[0] + Mj[4] * v[1] + Mj[5] * v[2];
+      const Real n2 = Mj[6] * v[0] + Mj[7] * v[1] + Mj[8] * v[2];
+      v[0] = n0; v[1] = n1; v[2] = n2;
+      Real nG[9];
+      m3_mul(Mj, G, nG);
+#pragma unroll
+      for (int k = 0; k < 9; k++) G[k] = nG[k];
+    } else {
+      const Real sgn = c.ax[j][0] + c.ax[j][1] + c.ax[j][2];          // +-1 (axis = sgn e_K)
+      const Real ss = sgn * s;
+      if (kind == 1) joint_axis<Real, M, 0>(ss, co, sgn, v, G, col);
+      else if (kind == 2) joint_axis<Real, M, 1>(ss, co, sgn, v, G, col);
+      else joint_axis<Real, M, 2>(ss, co, sgn, v, G, col);
     }
+    v[0] += c.tp[j][0]; v[1] += c.tp[j][1]; v[2] += c.tp[j][2];
 #pragma unroll
     for (int r = 0; r < M; r++) {
-      mem.col(j, r) = col[r];
+      pc[r * T] = col[r];
 #pragma unroll
-      for (int q = 0; q <= r; q++) S[tri(r, q)] += col[r] * col[q];
+      for (int q = 0; q <= r; q++) o.S[tri(r, q)] += col[r] * col[q];
     }
-    const Real n0 = Mj[0] * v0 + Mj[1] * v1 + Mj[2] * v2 + c.tp[j][0];
-    const Real n1 = Mj[3] * v0 + Mj[4] * v1 + Mj[5] * v2 + c.tp[j][1];
-    const Real n2 = Mj[6] * v0 + Mj[7] * v1 + Mj[8] * v2 + c.tp[j][2];
-    v0 = n0; v1 = n1; v2 = n2;
-    Real nG[9];
-    m3_mul(Mj, G, nG);
-#pragma unroll
-    for (int k = 0; k < 9; k++) G[k] = nG[k];
+    pc -= M * T;
   }
-  L.evals++;
-  Real Fw[M], FL[M];
-  Fw[0] = v0 - tg.x[0]; Fw[1] = v1 - tg.x[1]; Fw[2] = v2 - tg.x[2];
-  Real f = Fw[0] * Fw[0] + Fw[1] * Fw[1] + Fw[2] * Fw[2];
-  m3_Tvec(G, Fw, FL);
+  o.xn2 = xn2;
+  o.Fw[0] = v[0] - tg.x[0]; o.Fw[1] = v[1] - tg.x[1]; o.Fw[2] = v[2] - tg.x[2];
+  Real f = o.Fw[0] * o.Fw[0] + o.Fw[1] * o.Fw[1] + o.Fw[2] * o.Fw[2];
+  m3_Tvec(G, o.Fw, o.FL);
   if (M == 6) {
     Real Re[9], e[3], ew[3];
     m3_Tmul(tg.R, G, Re);
     so3_log(Re, e);
     m3_vec(G, e, ew);
-    FL[M - 3] = e[0]; FL[M - 2] = e[1]; FL[M - 1] = e[2];
-    Fw[M - 3] = ew[0]; Fw[M - 2] = ew[1]; Fw[M - 1] = ew[2];
+    o.FL[M - 3] = e[0]; o.FL[M - 2] = e[1]; o.FL[M - 1] = e[2];
+    o.Fw[M - 3] = ew[0]; o.Fw[M - 2] = ew[1]; o.Fw[M - 1] = ew[2];
     f += e[0] * e[0] + e[1] * e[1] + e[2] * e[2];
   }
-  f *= Real(0.5);
+  o.f = Real(0.5) * f;
   Real fmax = 0;
 #pragma unroll
-  for (int r = 0; r < M; r++) fmax = max_(fmax, abs_(Fw[r]));
-  L.resid = fmax;
+  for (int r = 0; r < M; r++) fmax = max_(fmax, abs_(o.Fw[r]));
+  o.fmax = fmax;
+}
 
+// Cholesky solve of the packed SPD matrix A (lower) with reciprocal square roots.
+template <typename Real, int M>
+__device__ __forceinline__ void chol_solve_fast(Real (&A)[M * (M + 1) / 2], const Real *b, Real *y) {
+  Real inv[M];
+#pragma unroll
+  for (int r = 0; r < M; r++) {
+#pragma unroll
+    for (int s = 0; s <= r; s++) {
+      Real acc = A[tri(r, s)];
+#pragma unroll
+      for (int k = 0; k < s; k++) acc -= A[tri(r, k)] * A[tri(s, k)];
+      if (r == s) { inv[r] = rsqrt_(acc); A[tri(r, r)] = acc * inv[r]; }
+      else A[tri(r, s)] = acc * inv[s];
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < M; r++) {
+    Real acc = b[r];
+#pragma unroll
+    for (int k = 0; k < r; k++) acc -= A[tri(r, k)] * y[k];
+    y[r] = acc * inv[r];
+  }
+#pragma unroll
+  for (int r = M - 1; r >= 0; r--) {
+    Real acc = y[r];
+#pragma unroll
+    for (int k = r + 1; k < M; k++) acc -= A[tri(k, r)] * y[k];
+    y[r] = acc * inv[r];
+  }
+}
+
+// ---- the transition: line search bookkeeping and, if a new iteration starts, the Newton step ----
+// Returns IK_RUNNING or the final status.  After a final status the solution is src_x(c, L.src, j).
+template <typename Real, int M, typename ChainT>
+__device__ __forceinline__ int lane_step(const ChainT &c, LaneIK<Real, M> &L, const LaneMem<Real, M> &mem,
+                                         const PassOut<Real, M> &o) {
+  const int n = c.n;
+  const Real tolf = c.tol, tolx = Real(0.01) * c.tol, ALF = Real(1e-4);
+  L.evals++;
+  L.resid = o.fmax;
   bool check_convx = false;
   if (L.phase == 0) {
-    if (fmax < tolf) return IK_OK;
+    if (o.fmax < tolf) return IK_OK;
     if (c.max_iters <= 0) return IK_MAXIT;
-    L.stpmax = Real(10) * max_(sqrt_(xn2), Real(n));
+    L.stpmax = Real(10) * max_(sqrt_(o.xn2), Real(n));
   } else {
-    if (L.alam < L.alamin) { L.it++; L.alam = 0; return IK_STALL; }   // x <- xold
-    if (!(f <= L.fold + ALF * L.alam * L.slope)) {
+    if (L.alam < L.alamin) { L.it++; L.alam = 0; L.src.t = 0; return IK_STALL; }   // x <- xold
+    if (!(o.f <= L.fold + ALF * L.alam * L.slope)) {
       Real tmplam;
-      if (L.alam == Real(1)) tmplam = -L.slope / (Real(2) * (f - L.fold - L.slope));
+      if (L.alam == Real(1)) tmplam = -L.slope / (Real(2) * (o.f - L.fold - L.slope));
       else {
-        const Real rhs1 = f - L.fold - L.alam * L.slope, rhs2 = L.f2 - L.fold - L.alam2 * L.slope;
+        const Real rhs1 = o.f - L.fold - L.alam * L.slope, rhs2 = L.f2 - L.fold - L.alam2 * L.slope;
         const Real a = (rhs1 / (L.alam * L.alam) - rhs2 / (L.alam2 * L.alam2)) / (L.alam - L.alam2);
         const Real b = (-L.alam2 * rhs1 / (L.alam * L.alam) + L.alam * rhs2 / (L.alam2 * L.alam2)) / (L.alam - L.alam2);
         if (a == Real(0)) tmplam = -L.slope / (Real(2) * b);
@@ -147,12 +287,13 @@ __device__ __forceinline__ int lane_trip(const ChainT &c, const Target<Real, M> 
         }
         if (tmplam > Real(0.5) * L.alam) tmplam = Real(0.5) * L.alam;
       }
-      L.alam2 = L.alam; L.f2 = f;
+      L.alam2 = L.alam; L.f2 = o.f;
       L.alam = max_(tmplam, Real(0.1) * L.alam);
+      L.src.t = L.alam;
       return IK_RUNNING;
     }
     L.it++;
-    if (fmax < tolf) return IK_OK;
+    if (o.fmax < tolf) return IK_OK;
     check_convx = true;
   }
 
@@ -163,26 +304,26 @@ __device__ __forceinline__ int lane_trip(const ChainT &c, const Target<Real, M> 
     const Real l2 = c.lambda * c.lambda;
     if (M == 3) {
 #pragma unroll
-      for (int k = 0; k < 6; k++) A[k] = S[k];
+      for (int k = 0; k < 6; k++) A[k] = o.S[k];
 #pragma unroll
       for (int r = 0; r < M; r++) A[tri(r, r)] += l2;
-      chol_solve<Real, M>(A, FL, y);
+      chol_solve_fast<Real, M>(A, o.FL, y);
     } else {
       Real D[9], Src[9], Srr[9], DSrc[9], DSrr[9];
-      so3_Jl_inv(&FL[M - 3], D);
+      so3_Jl_inv(&o.FL[M - 3], D);
 #pragma unroll
       for (int r = 0; r < 3; r++)
 #pragma unroll
         for (int q = 0; q < 3; q++) {
-          Src[3 * r + q] = S[tri(3 + r, q)];
-          Srr[3 * r + q] = (r >= q) ? S[tri(3 + r, 3 + q)] : S[tri(3 + q, 3 + r)];
+          Src[3 * r + q] = o.S[tri(3 + r, q)];
+          Srr[3 * r + q] = (r >= q) ? o.S[tri(3 + r, 3 + q)] : o.S[tri(3 + q, 3 + r)];
         }
       m3_mul(D, Src, DSrc);
       m3_mul(D, Srr, DSrr);
 #pragma unroll
       for (int r = 0; r < 3; r++)
 #pragma unroll
-        for (int q = 0; q <= r; q++) A[tri(r, q)] = S[tri(r, q)];
+        for (int q = 0; q <= r; q++) A[tri(r, q)] = o.S[tri(r, q)];
 #pragma unroll
       for (int r = 0; r < 3; r++)
 #pragma unroll
@@ -194,29 +335,41 @@ __device__ __forceinline__ int lane_trip(const ChainT &c, const Target<Real, M> 
           A[tri(3 + r, 3 + q)] = DSrr[3 * r] * D[3 * q] + DSrr[3 * r + 1] * D[3 * q + 1] + DSrr[3 * r + 2] * D[3 * q + 2];
 #pragma unroll
       for (int r = 0; r < M; r++) A[tri(r, r)] += l2;
-      chol_solve<Real, M>(A, FL, y);
+      chol_solve_fast<Real, M>(A, o.FL, y);
       Real z[3];
       m3_Tvec(D, &y[M - 3], z);
       y[M - 3] = z[0]; y[M - 2] = z[1]; y[M - 1] = z[2];
     }
   }
   Real pn = 0, slope = 0, test = 0, testx = 0;
+  {
+    const int T = mem.T;
+    const Real *pa = L.src.a, *pb = L.src.b;
+    Real *px = mem.xold(), *pp = mem.p();
+    const Real *pc = mem.cols();
 #pragma unroll 1
-  for (int j = 0; j < n; j++) {
-    const Real xo = mem.xold(j);
-    const Real xj = lane_x<Real>(c, xo, mem.p(j), L.alam, j);
-    testx = max_(testx, abs_(xj - xo) / max_(abs_(xj), Real(1)));
-    Real pj = 0, gj = 0;
+    for (int j = 0; j < n; j++) {
+      const Real av = *pa, bv = *pb;
+      pa += L.src.sa; pb += L.src.sb;
+      const Real dir = L.src.lerp ? bv - av : bv;
+      const Real xj = min_(max_(av + L.src.t * dir, c.bmin[j]), c.bmax[j]);
+      const Real rinv = fdiv_(Real(1), max_(abs_(xj), Real(1)));
+      testx = max_(testx, abs_(xj - av) * rinv);      // only meaningful in phase 1 (av = xold)
+      Real pj = 0, gj = 0;
 #pragma unroll
-    for (int r = 0; r < M; r++) { const Real cj = mem.col(j, r); pj += cj * y[r]; gj += cj * FL[r]; }
-    pj = -pj;
-    mem.xold(j) = xj;
-    mem.p(j) = pj;
-    pn += pj * pj;
-    slope += gj * pj;
-    test = max_(test, abs_(pj) / max_(abs_(xj), Real(1)));
+      for (int r = 0; r < M; r++) { const Real cj = pc[r * T]; pj += cj * y[r]; gj += cj * o.FL[r]; }
+      pc += M * T;
+      pj = -pj;
+      *px = xj; *pp = pj;
+      px += T; pp += T;
+      pn += pj * pj;
+      slope += gj * pj;
+      test = max_(test, abs_(pj) * rinv);
+    }
   }
-  L.alam = 0;                                     // x == xold (the accepted point) until the next trial is armed
+  // from here on the trial point is x = xold + alam p in lane memory
+  L.alam = 0;
+  L.src.a = mem.xold(); L.src.b = mem.p(); L.src.sa = mem.T; L.src.sb = mem.T; L.src.t = 0; L.src.lerp = false;
   if (check_convx) {
     if (testx < tolx) return IK_CONVX;
     if (L.it >= c.max_iters) return IK_MAXIT;
@@ -225,17 +378,21 @@ __device__ __forceinline__ int lane_trip(const ChainT &c, const Target<Real, M> 
   if (pn > L.stpmax) {
     const Real sc = L.stpmax / pn;
     test = 0;
+    const int T = mem.T;
+    Real *pp = mem.p();
+    const Real *px = mem.xold();
 #pragma unroll 1
     for (int j = 0; j < n; j++) {
-      const Real pj = mem.p(j) * sc;
-      mem.p(j) = pj;
-      test = max_(test, abs_(pj) / max_(abs_(mem.xold(j)), Real(1)));
+      const Real pj = pp[j * T] * sc;
+      pp[j * T] = pj;
+      test = max_(test, abs_(pj) / max_(abs_(px[j * T]), Real(1)));
     }
     slope *= sc;
   }
   if (!(slope < Real(0))) { L.it++; return IK_STALL; }
-  L.alamin = tolx / test;
-  L.fold = f; L.slope = slope; L.alam = 1; L.alam2 = 0; L.f2 = 0;
+  L.alamin = fdiv_(tolx, test);
+  L.fold = o.f; L.slope = slope; L.alam = 1; L.alam2 = 0; L.f2 = 0;
+  L.src.t = 1;
   L.phase = 1;
   return IK_RUNNING;
 }
