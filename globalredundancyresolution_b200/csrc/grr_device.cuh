@@ -51,6 +51,16 @@ template <> __device__ __forceinline__ double inf_<double>() { return CUDART_INF
 // ------------------------------------------------------------------------------------------
 // chain constants (kernel parameter, __grid_constant__: lives in the constant bank)
 // ------------------------------------------------------------------------------------------
+// per-joint constants every joint kind needs, packed for two 16-byte constant loads
+template <typename Real>
+struct alignas(16) JointConst {
+  Real tp[3];      // translation preceding the joint
+  Real sgn;        // +-1 for the short kinds (axis = sgn e_K)
+  Real bmin, bmax; // joint box (+-inf for revolute joints with range >= 2 pi)
+  int kind;        // 0 generic; 1/2/3: identity preceding rotation and axis = +-e_x / e_y / e_z
+  int pad;
+};
+
 template <typename Real, int NJ>
 struct ChainDev {
   int n, mode, nlinks_eps, max_iters;
@@ -60,7 +70,7 @@ struct ChainDev {
   Real tp[NJ][3];
   Real ax[NJ][3];
   Real bmin[NJ], bmax[NJ];     // +-inf for revolute joints with range >= 2 pi
-  int kind[NJ];                // 0 generic; 1/2/3: identity preceding rotation and axis = +-e_x / e_y / e_z
+  JointConst<Real> jc[NJ];
   float slo[NJ], srange[NJ];   // random-start sampling box, single precision by specification
   Real ee[3];
   Real Rtail[9];

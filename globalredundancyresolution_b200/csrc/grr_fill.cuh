@@ -28,8 +28,9 @@ void fill_chain(const HostChain &h, ChainDev<Real, NJ> &d) {
       int kind = 0;
       for (int k = 0; k < 3; k++)
         if (ident && fabs(fabs(a[k]) - 1.0) < 1e-14 && fabs(a[(k + 1) % 3]) < 1e-14 && fabs(a[(k + 2) % 3]) < 1e-14) kind = k + 1;
-      d.kind[j] = kind;
-      if (kind) for (int k = 0; k < 3; k++) d.ax[j][k] = (Real)(k == kind - 1 ? (a[k] > 0 ? 1.0 : -1.0) : 0.0);
+      d.jc[j].kind = kind;
+      d.jc[j].sgn = (Real)(kind ? (a[kind - 1] > 0 ? 1.0 : -1.0) : 0.0);
+      d.jc[j].pad = 0;
     }
     const bool unbounded = (h.qmax[j] - h.qmin[j]) >= 2.0 * 3.14159265358979323846;
     d.bmin[j] = unbounded ? -std::numeric_limits<Real>::infinity() : (Real)h.qmin[j];
@@ -37,6 +38,8 @@ void fill_chain(const HostChain &h, ChainDev<Real, NJ> &d) {
     float lo = (float)h.qmin[j], hi = (float)h.qmax[j];
     if (unbounded) { lo = -3.14159265358979f; hi = 3.14159265358979f; }
     d.slo[j] = lo; d.srange[j] = hi - lo;
+    d.jc[j].bmin = d.bmin[j]; d.jc[j].bmax = d.bmax[j];
+    for (int k = 0; k < 3; k++) d.jc[j].tp[k] = d.tp[j][k];
   }
   for (int k = 0; k < 3; k++) d.ee[k] = (Real)h.ee_local[k];
   for (int k = 0; k < 9; k++) { d.Rtail[k] = (Real)h.R_tail[k]; d.Rgoal[k] = (Real)h.R_goal[k]; }

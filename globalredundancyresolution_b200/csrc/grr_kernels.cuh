@@ -43,13 +43,14 @@ k_ik_instances(const __grid_constant__ ChainDev<Real, kMaxJ> c, long long total,
                unsigned long long *work, unsigned long long *counters) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int n = c.n, dw = (c.mode == 2 ? 6 : 3);
-  LaneMem<Real, M> mem{reinterpret_cast<Real *>(smem_raw) + threadIdx.x, (int)blockDim.x, n};
+  LaneMem<Real, M> mem;
+  mem.init(reinterpret_cast<Real *>(smem_raw) + threadIdx.x, (int)blockDim.x, n);
   LaneIK<Real, M> L;
   lane_begin_mem<Real, M>(L, mem);
   Target<Real, M> tg;
   tg.x[0] = tg.x[1] = tg.x[2] = 0;
   if (M == 6) { for (int k = 0; k < 9; k++) tg.R[k] = (k % 4 == 0) ? Real(1) : Real(0); }
-  for (int j = 0; j < n; j++) { mem.xold()[j * mem.T] = 0; mem.p()[j * mem.T] = 0; }
+  for (int j = 0; j < 4 * n; j++) mem.base[j * mem.T] = 0;
   LaneCounters cnt;
   long long inst = -1;
   bool done = false;
@@ -88,9 +89,9 @@ k_ik_instances(const __grid_constant__ ChainDev<Real, kMaxJ> c, long long total,
     }
     if (__all_sync(0xffffffffu, inst < 0)) break;
     PassOut<Real, M> o;
-    lane_pass<Real, M>(c, tg, L.src, mem, o);
+    lane_pass<Real, M, false>(c, tg, L.src, mem, nullptr, 0, o);
+    const int st = lane_step<Real, M>(c, L, mem, o, inst >= 0);
     if (inst >= 0) {
-      const int st = lane_step<Real, M>(c, L, mem, o);
       if (st != IK_RUNNING) {
         long long base, stride, sidx;
         if (MODE == 0) {
@@ -98,12 +99,13 @@ k_ik_instances(const __grid_constant__ ChainDev<Real, kMaxJ> c, long long total,
           const int s = (int)(inst - node * Nq);
           base = node * n * (long long)Nqp + s; stride = Nqp; sidx = node * Nqp + s;
         } else { base = inst; stride = total; sidx = inst; }
-        for (int j = 0; j < n; j++) q[base + j * stride] = src_x<Real>(c, L.src, j);
+        for (int j = 0; j < n; j++) q[base + j * stride] = L.res[j * mem.T];
         status[sidx] = (uint8_t)st;
         if (iters) iters[sidx] = (uint8_t)L.it;
         if (resid) resid[sidx] = L.resid;
         cnt.solves++; cnt.iters += L.it; cnt.evals += L.evals; cnt.ok += (st == IK_OK);
         inst = -1;
+        lane_begin_mem<Real, M>(L, mem);     // idle lanes keep walking valid memory
       }
     }
   }
@@ -138,26 +140,20 @@ __device__ __forceinline__ bool pair_begin(const ChainT &c, Real eps, PairLane<R
   return true;
 }
 
-// One interpolated solve finished with IK_OK: leaf test against the previous solution, advance.
-// Returns +1 valid, 0 invalid, -1 continue with the next k (seed armed).
+// One interpolated solve finished with IK_OK; s2 = |q_k - q_{k-1}|^2 was accumulated by the final
+// pass.  Leaf test, then either the closing leaf (q_Ndivs, qb) or the next k: the solution buffer
+// becomes `prev` by swapping roles.  Returns +1 valid, 0 invalid, -1 continue (seed armed).
 template <typename Real, int M, typename ChainT>
-__device__ __forceinline__ int pair_advance(const ChainT &c, const LaneMem<Real, M> &mem, Real thr2, PairLane<Real> &P,
+__device__ __forceinline__ int pair_advance(const ChainT &c, LaneMem<Real, M> &mem, Real s2, Real thr2, PairLane<Real> &P,
                                             LaneIK<Real, M> &L) {
-  const int n = c.n, T = mem.T;
-  const bool last = (P.k == P.ndivs);
-  const Real *pv = (P.k == 1) ? P.qa : mem.prev();               // q_0 = qa
-  const int sv = (P.k == 1) ? P.sa : T;
-  Real *pw = mem.prev();
-  Real s2 = 0, e2 = 0;
-  for (int j = 0; j < n; j++) {
-    const Real x = src_x<Real>(c, L.src, j);
-    const Real d = x - pv[j * sv];
-    s2 += d * d;
-    if (last) { const Real e = P.qb[j * P.sb] - x; e2 += e * e; }
-    pw[j * T] = x;
-  }
   if (s2 > thr2) return 0;                                       // graph.py:954-959 (leaf)
-  if (last) return (e2 > thr2) ? 0 : 1;
+  if (P.k == P.ndivs) {
+    const int n = c.n, T = mem.T;
+    Real e2 = 0;
+    for (int j = 0; j < n; j++) { const Real e = P.qb[j * P.sb] - L.res[j * T]; e2 += e * e; }
+    return (e2 > thr2) ? 0 : 1;
+  }
+  { const int t = mem.o_prev; mem.o_prev = mem.o_xcur; mem.o_xcur = t; }   // IK_OK leaves the solution in xcur
   P.k++;
   lane_begin_lerp<Real, M>(L, P.qa, P.sa, P.qb, P.sb, Real(P.k) / Real(P.ndivs + 1));
   return -1;
@@ -172,13 +168,14 @@ k_valid_edge_batch(const __grid_constant__ ChainDev<Real, kMaxJ> c, long long to
                    unsigned long long *counters) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int n = c.n, dw = (c.mode == 2 ? 6 : 3);
-  LaneMem<Real, M> mem{reinterpret_cast<Real *>(smem_raw) + threadIdx.x, (int)blockDim.x, n};
+  LaneMem<Real, M> mem;
+  mem.init(reinterpret_cast<Real *>(smem_raw) + threadIdx.x, (int)blockDim.x, n);
   const Real eps = epsilon * sqrt_(Real(c.nlinks_eps));          // graph.py:945
   const Real thr = eps * Real(c.nlinks_eps);                     // graph.py:947
   const Real thr2 = thr * thr;
   LaneIK<Real, M> L;
   lane_begin_mem<Real, M>(L, mem);
-  for (int j = 0; j < n; j++) { mem.xold()[j * mem.T] = 0; mem.p()[j * mem.T] = 0; }
+  for (int j = 0; j < 4 * n; j++) mem.base[j * mem.T] = 0;
   PairLane<Real> P;
   WInterp<Real, M> W;
   Target<Real, M> tg;
@@ -204,16 +201,17 @@ k_valid_edge_batch(const __grid_constant__ ChainDev<Real, kMaxJ> c, long long to
     }
     const bool running = (t >= 0 && verdict < 0);
     if (__all_sync(0xffffffffu, t < 0)) break;
-    PassOut<Real, M> o;
-    if (__any_sync(0xffffffffu, running)) lane_pass<Real, M>(c, tg, L.src, mem, o);
-    if (running) {
-      const int st = lane_step<Real, M>(c, L, mem, o);
-      if (st != IK_RUNNING) {
+    if (__any_sync(0xffffffffu, running)) {
+      PassOut<Real, M> o;
+      const bool first = running && P.k == 1;
+      lane_pass<Real, M, true>(c, tg, L.src, mem, first ? P.qa : mem.prev(), first ? P.sa : mem.T, o);
+      const int st = lane_step<Real, M>(c, L, mem, o, running);
+      if (running && st != IK_RUNNING) {
         P.solves++; P.iters += L.it;
         cnt.solves++; cnt.iters += L.it; cnt.evals += L.evals; cnt.ok += (st == IK_OK);
         if (st != IK_OK) { verdict = 0; fail = 1; }               // graph.py:964-966
         else {
-          verdict = pair_advance<Real, M>(c, mem, thr2, P, L);
+          verdict = pair_advance<Real, M>(c, mem, o.s2, thr2, P, L);
           if (verdict == 0) fail = 2;
           if (verdict < 0) winterp_at<Real, M>(W, Real(P.k) / Real(P.ndivs + 1), tg);
         }
@@ -271,8 +269,9 @@ k_edges_build(const __grid_constant__ ChainDev<Real, kMaxJ> c, const int32_t *__
     const Real *ga = q_kept + (long long)iw * n * Nqp, *gb = q_kept + (long long)jw * n * Nqp;
     for (int k = threadIdx.x; k < n * Nqp; k += blockDim.x) { sa[k] = ga[k]; sb[k] = gb[k]; }
   }
-  LaneMem<Real, M> mem{lanes + threadIdx.x, (int)blockDim.x, n};
-  for (int j = 0; j < n; j++) { mem.xold()[j * mem.T] = 0; mem.p()[j * mem.T] = 0; }
+  LaneMem<Real, M> mem;
+  mem.init(lanes + threadIdx.x, (int)blockDim.x, n);
+  for (int j = 0; j < 4 * n; j++) mem.base[j * mem.T] = 0;
   __syncthreads();
   LaneCounters cnt;
   if (total) {
@@ -312,15 +311,16 @@ k_edges_build(const __grid_constant__ ChainDev<Real, kMaxJ> c, const int32_t *__
       }
       const bool running = (a >= 0 && verdict < 0);
       if (__all_sync(0xffffffffu, a < 0)) break;
-      PassOut<Real, M> o;
-      if (__any_sync(0xffffffffu, running)) lane_pass<Real, M>(c, tg, L.src, mem, o);
-      if (running) {
-        const int st = lane_step<Real, M>(c, L, mem, o);
-        if (st != IK_RUNNING) {
+      if (__any_sync(0xffffffffu, running)) {
+        PassOut<Real, M> o;
+        const bool first = running && P.k == 1;
+        lane_pass<Real, M, true>(c, tg, L.src, mem, first ? P.qa : mem.prev(), first ? P.sa : mem.T, o);
+        const int st = lane_step<Real, M>(c, L, mem, o, running);
+        if (running && st != IK_RUNNING) {
           cnt.solves++; cnt.iters += L.it; cnt.evals += L.evals; cnt.ok += (st == IK_OK);
           if (st != IK_OK) verdict = 0;                         // graph.py:964-966
           else {
-            verdict = pair_advance<Real, M>(c, mem, thr2, P, L);
+            verdict = pair_advance<Real, M>(c, mem, o.s2, thr2, P, L);
             if (verdict < 0) winterp_at<Real, M>(W, Real(P.k) / Real(P.ndivs + 1), tg);
           }
         }

@@ -56,19 +56,26 @@ __device__ __forceinline__ void sincos_joint(float x, float *s, float *c) {
 }
 __device__ __forceinline__ void sincos_joint(double x, double *s, double *c) { sincos(x, s, c); }
 
-// floats (Reals) of shared memory one lane needs: xold, p, prev, columns
-template <int M> __host__ __device__ constexpr int lane_reals(int n) { return n * (3 + M); }
+// Reals of shared memory one lane needs: three rotating config buffers (line-search origin xold,
+// trial point xcur, previous interpolated solution prev), the direction p and the Jacobian columns.
+template <int M> __host__ __device__ constexpr int lane_reals(int n) { return n * (4 + M); }
 
 // Shared-memory view of one lane's joint vectors: element k of an array lives at ptr[k * T].
+// The three config buffers change roles by swapping offsets, never by copying.
 template <typename Real, int M>
 struct LaneMem {
   Real *base;   // already offset by tid
   int T;        // lanes per CTA (stride)
   int n;
-  __device__ __forceinline__ Real *xold() const { return base; }
-  __device__ __forceinline__ Real *p() const { return base + n * T; }
-  __device__ __forceinline__ Real *prev() const { return base + 2 * n * T; }
-  __device__ __forceinline__ Real *cols() const { return base + 3 * n * T; }   // [j][r], r < M
+  int o_xold, o_xcur, o_prev;   // element offsets of the three config buffers
+  __device__ __forceinline__ void init(Real *b, int T_, int n_) {
+    base = b; T = T_; n = n_; o_xold = 0; o_xcur = n_ * T_; o_prev = 2 * n_ * T_;
+  }
+  __device__ __forceinline__ Real *xold() const { return base + o_xold; }
+  __device__ __forceinline__ Real *xcur() const { return base + o_xcur; }
+  __device__ __forceinline__ Real *prev() const { return base + o_prev; }
+  __device__ __forceinline__ Real *p() const { return base + 3 * n * T; }
+  __device__ __forceinline__ Real *cols() const { return base + 4 * n * T; }   // [j][r], r < M
 };
 
 // Where the current trial point comes from: x_j = clamp(a[j*sa] + t * (lerp ? b[j*sb] - a[j*sa] : b[j*sb])).
@@ -85,6 +92,7 @@ struct LaneIK {
   Real fold, slope, alam, alam2, f2, alamin, stpmax, resid;
   int it, evals, phase;
   XSrc<Real> src;
+  const Real *res;   // after a final status: the solution, res[j * T]
 };
 
 template <typename Real, int M>
@@ -98,18 +106,12 @@ __device__ __forceinline__ void lane_begin_lerp(LaneIK<Real, M> &L, const Real *
   lane_reset(L);
   L.src.a = a; L.src.b = b; L.src.sa = sa; L.src.sb = sb; L.src.t = u; L.src.lerp = true;
 }
-// Start an instance whose seed has been written to mem.xold (mem.p is ignored: t = 0).
+// Start an instance whose seed has been written to mem.xold() (t = 0: the direction is ignored).
 template <typename Real, int M>
 __device__ __forceinline__ void lane_begin_mem(LaneIK<Real, M> &L, const LaneMem<Real, M> &mem) {
   lane_reset(L);
   L.src.a = mem.xold(); L.src.b = mem.p(); L.src.sa = mem.T; L.src.sb = mem.T; L.src.t = 0; L.src.lerp = false;
-}
-
-template <typename Real, typename ChainT>
-__device__ __forceinline__ Real src_x(const ChainT &c, const XSrc<Real> &s, int j) {
-  const Real av = s.a[j * s.sa], bv = s.b[j * s.sb];
-  const Real dir = s.lerp ? bv - av : bv;
-  return min_(max_(av + s.t * dir, c.bmin[j]), c.bmax[j]);
+  L.res = mem.xold();
 }
 
 // short joint: identity preceding rotation, axis = sgn * e_K.  (I1, I2) are the two components the
@@ -140,12 +142,15 @@ __device__ __forceinline__ void joint_axis(Real s, Real co, Real sgn, Real *v, R
 template <typename Real, int M>
 struct PassOut {
   Real Fw[M], FL[M], f, fmax, xn2;
+  Real s2;                         // |x - xref|^2 when a reference config is given
   Real S[M * (M + 1) / 2];
 };
 
-template <typename Real, int M, typename ChainT>
+// xref (stride sref): config against which the joint-space distance of the trial point is accumulated
+// (the previous interpolated solution of a pair); nullptr = none.
+template <typename Real, int M, bool WITH_REF, typename ChainT>
 __device__ __forceinline__ void lane_pass(const ChainT &c, const Target<Real, M> &tg, const XSrc<Real> &src,
-                                          const LaneMem<Real, M> &mem, PassOut<Real, M> &o) {
+                                          const LaneMem<Real, M> &mem, const Real *xref, int sref, PassOut<Real, M> &o) {
   const int n = c.n;
   Real v[3] = {c.ee[0], c.ee[1], c.ee[2]};
   Real G[9];
@@ -153,22 +158,26 @@ __device__ __forceinline__ void lane_pass(const ChainT &c, const Target<Real, M>
   for (int k = 0; k < 9; k++) G[k] = c.Rtail[k];
 #pragma unroll
   for (int k = 0; k < M * (M + 1) / 2; k++) o.S[k] = 0;
-  Real xn2 = 0;
+  Real xn2 = 0, s2 = 0;
   const int T = mem.T;
   const Real *pa = src.a + (n - 1) * src.sa, *pb = src.b + (n - 1) * src.sb;
+  const Real *pr = WITH_REF ? xref + (n - 1) * sref : nullptr;
   Real *pc = mem.cols() + (n - 1) * M * T;
+  Real *px = mem.xcur() + (n - 1) * T;
 #pragma unroll 1
   for (int j = n - 1; j >= 0; --j) {
     const Real av = *pa, bv = *pb;
     pa -= src.sa; pb -= src.sb;
+    const JointConst<Real> jc = c.jc[j];
     const Real dir = src.lerp ? bv - av : bv;
-    const Real xj = min_(max_(av + src.t * dir, c.bmin[j]), c.bmax[j]);
+    const Real xj = min_(max_(av + src.t * dir, jc.bmin), jc.bmax);
+    *px = xj; px -= T;
     xn2 += xj * xj;
+    if (WITH_REF) { const Real d = xj - *pr; pr -= sref; s2 += d * d; }
     Real s, co;
     sincos_joint(xj, &s, &co);
     Real col[M];
-    const int kind = c.kind[j];
-    if (kind == 0) {
+    if (jc.kind == 0) {
       Real Mj[9];
 #pragma unroll
       for (int k = 0; k < 9; k++) Mj[k] = c.A[j][k] + s * c.B[j][k] - co * c.C[j][k];
@@ -189,13 +198,12 @@ __device__ __forceinline__ void lane_pass(const ChainT &c, const Target<Real, M>
 #pragma unroll
       for (int k = 0; k < 9; k++) G[k] = nG[k];
     } else {
-      const Real sgn = c.ax[j][0] + c.ax[j][1] + c.ax[j][2];          // +-1 (axis = sgn e_K)
-      const Real ss = sgn * s;
-      if (kind == 1) joint_axis<Real, M, 0>(ss, co, sgn, v, G, col);
-      else if (kind == 2) joint_axis<Real, M, 1>(ss, co, sgn, v, G, col);
-      else joint_axis<Real, M, 2>(ss, co, sgn, v, G, col);
+      const Real ss = jc.sgn * s;
+      if (jc.kind == 1) joint_axis<Real, M, 0>(ss, co, jc.sgn, v, G, col);
+      else if (jc.kind == 2) joint_axis<Real, M, 1>(ss, co, jc.sgn, v, G, col);
+      else joint_axis<Real, M, 2>(ss, co, jc.sgn, v, G, col);
     }
-    v[0] += c.tp[j][0]; v[1] += c.tp[j][1]; v[2] += c.tp[j][2];
+    v[0] += jc.tp[0]; v[1] += jc.tp[1]; v[2] += jc.tp[2];
 #pragma unroll
     for (int r = 0; r < M; r++) {
       pc[r * T] = col[r];
@@ -204,7 +212,7 @@ __device__ __forceinline__ void lane_pass(const ChainT &c, const Target<Real, M>
     }
     pc -= M * T;
   }
-  o.xn2 = xn2;
+  o.xn2 = xn2; o.s2 = s2;
   o.Fw[0] = v[0] - tg.x[0]; o.Fw[1] = v[1] - tg.x[1]; o.Fw[2] = v[2] - tg.x[2];
   Real f = o.Fw[0] * o.Fw[0] + o.Fw[1] * o.Fw[1] + o.Fw[2] * o.Fw[2];
   m3_Tvec(G, o.Fw, o.FL);
@@ -256,23 +264,28 @@ __device__ __forceinline__ void chol_solve_fast(Real (&A)[M * (M + 1) / 2], cons
 }
 
 // ---- the transition: line search bookkeeping and, if a new iteration starts, the Newton step ----
-// Returns IK_RUNNING or the final status.  After a final status the solution is src_x(c, L.src, j).
+// Called by ALL lanes of the warp (`active` = this lane holds a running instance) so that the lanes
+// that start a new iteration execute the step loop together whatever path took them there.
+// Returns IK_RUNNING or the final status; after a final status the solution is L.res[j * T].
 template <typename Real, int M, typename ChainT>
-__device__ __forceinline__ int lane_step(const ChainT &c, LaneIK<Real, M> &L, const LaneMem<Real, M> &mem,
-                                         const PassOut<Real, M> &o) {
+__device__ __forceinline__ int lane_step(const ChainT &c, LaneIK<Real, M> &L, LaneMem<Real, M> &mem,
+                                         const PassOut<Real, M> &o, bool active) {
   const int n = c.n;
   const Real tolf = c.tol, tolx = Real(0.01) * c.tol, ALF = Real(1e-4);
-  L.evals++;
-  L.resid = o.fmax;
-  bool check_convx = false;
-  if (L.phase == 0) {
-    if (o.fmax < tolf) return IK_OK;
-    if (c.max_iters <= 0) return IK_MAXIT;
-    L.stpmax = Real(10) * max_(sqrt_(o.xn2), Real(n));
-  } else {
-    if (L.alam < L.alamin) { L.it++; L.alam = 0; L.src.t = 0; return IK_STALL; }   // x <- xold
-    if (!(o.f <= L.fold + ALF * L.alam * L.slope)) {
-      Real tmplam;
+  int st = IK_RUNNING;
+  bool newstep = false, check_convx = false;
+  if (active) {
+    L.evals++;
+    L.resid = o.fmax;
+    L.res = mem.xcur();
+    if (L.phase == 0) {
+      if (o.fmax < tolf) st = IK_OK;
+      else if (c.max_iters <= 0) st = IK_MAXIT;
+      else { L.stpmax = Real(10) * max_(sqrt_(o.xn2), Real(n)); newstep = true; }
+    } else if (L.alam < L.alamin) {
+      L.it++; L.res = mem.xold(); st = IK_STALL;                        // x <- xold
+    } else if (!(o.f <= L.fold + ALF * L.alam * L.slope)) {
+      Real tmplam;                                                       // backtrack (Numerical Recipes lnsrch)
       if (L.alam == Real(1)) tmplam = -L.slope / (Real(2) * (o.f - L.fold - L.slope));
       else {
         const Real rhs1 = o.f - L.fold - L.alam * L.slope, rhs2 = L.f2 - L.fold - L.alam2 * L.slope;
@@ -290,111 +303,114 @@ __device__ __forceinline__ int lane_step(const ChainT &c, LaneIK<Real, M> &L, co
       L.alam2 = L.alam; L.f2 = o.f;
       L.alam = max_(tmplam, Real(0.1) * L.alam);
       L.src.t = L.alam;
-      return IK_RUNNING;
-    }
-    L.it++;
-    if (o.fmax < tolf) return IK_OK;
-    check_convx = true;
-  }
-
-  // ---- new Newton step from the columns of this pass ----
-  Real y[M];
-  {
-    Real A[M * (M + 1) / 2];
-    const Real l2 = c.lambda * c.lambda;
-    if (M == 3) {
-#pragma unroll
-      for (int k = 0; k < 6; k++) A[k] = o.S[k];
-#pragma unroll
-      for (int r = 0; r < M; r++) A[tri(r, r)] += l2;
-      chol_solve_fast<Real, M>(A, o.FL, y);
     } else {
-      Real D[9], Src[9], Srr[9], DSrc[9], DSrr[9];
-      so3_Jl_inv(&o.FL[M - 3], D);
+      L.it++;
+      if (o.fmax < tolf) st = IK_OK;
+      else { newstep = true; check_convx = true; }
+    }
+  }
+  __syncwarp();
+  if (newstep) {
+    // the accepted point (in xcur) becomes the origin of the next line search: swap roles, no copy
+    { const int t = mem.o_xold; mem.o_xold = mem.o_xcur; mem.o_xcur = t; }
+    Real y[M];
+    {
+      Real A[M * (M + 1) / 2];
+      const Real l2 = c.lambda * c.lambda;
+      if (M == 3) {
 #pragma unroll
-      for (int r = 0; r < 3; r++)
+        for (int k = 0; k < 6; k++) A[k] = o.S[k];
 #pragma unroll
-        for (int q = 0; q < 3; q++) {
-          Src[3 * r + q] = o.S[tri(3 + r, q)];
-          Srr[3 * r + q] = (r >= q) ? o.S[tri(3 + r, 3 + q)] : o.S[tri(3 + q, 3 + r)];
+        for (int r = 0; r < M; r++) A[tri(r, r)] += l2;
+        chol_solve_fast<Real, M>(A, o.FL, y);
+      } else {
+        Real D[9], Src[9], Srr[9], DSrc[9], DSrr[9];
+        so3_Jl_inv(&o.FL[M - 3], D);
+#pragma unroll
+        for (int r = 0; r < 3; r++)
+#pragma unroll
+          for (int q = 0; q < 3; q++) {
+            Src[3 * r + q] = o.S[tri(3 + r, q)];
+            Srr[3 * r + q] = (r >= q) ? o.S[tri(3 + r, 3 + q)] : o.S[tri(3 + q, 3 + r)];
+          }
+        m3_mul(D, Src, DSrc);
+        m3_mul(D, Srr, DSrr);
+#pragma unroll
+        for (int r = 0; r < 3; r++)
+#pragma unroll
+          for (int q = 0; q <= r; q++) A[tri(r, q)] = o.S[tri(r, q)];
+#pragma unroll
+        for (int r = 0; r < 3; r++)
+#pragma unroll
+          for (int q = 0; q < 3; q++) A[tri(3 + r, q)] = DSrc[3 * r + q];
+#pragma unroll
+        for (int r = 0; r < 3; r++)
+#pragma unroll
+          for (int q = 0; q <= r; q++)
+            A[tri(3 + r, 3 + q)] = DSrr[3 * r] * D[3 * q] + DSrr[3 * r + 1] * D[3 * q + 1] + DSrr[3 * r + 2] * D[3 * q + 2];
+#pragma unroll
+        for (int r = 0; r < M; r++) A[tri(r, r)] += l2;
+        chol_solve_fast<Real, M>(A, o.FL, y);
+        Real z[3];
+        m3_Tvec(D, &y[M - 3], z);
+        y[M - 3] = z[0]; y[M - 2] = z[1]; y[M - 1] = z[2];
+      }
+    }
+    Real pn = 0, slope = 0, test = 0, testx = 0;
+    {
+      const int T = mem.T;
+      const Real *px = mem.xold();          // accepted point
+      const Real *po = mem.xcur();          // origin of the search that just ended (phase 1 only)
+      Real *pp = mem.p();
+      const Real *pc = mem.cols();
+#pragma unroll 1
+      for (int j = 0; j < n; j++) {
+        const Real xj = *px, xo = *po;
+        px += T; po += T;
+        const Real rinv = fdiv_(Real(1), max_(abs_(xj), Real(1)));
+        testx = max_(testx, abs_(xj - xo) * rinv);
+        Real pj = 0, gj = 0;
+#pragma unroll
+        for (int r = 0; r < M; r++) { const Real cj = pc[r * T]; pj += cj * y[r]; gj += cj * o.FL[r]; }
+        pc += M * T;
+        pj = -pj;
+        *pp = pj; pp += T;
+        pn += pj * pj;
+        slope += gj * pj;
+        test = max_(test, abs_(pj) * rinv);
+      }
+    }
+    L.alam = 0;
+    L.src.a = mem.xold(); L.src.b = mem.p(); L.src.sa = mem.T; L.src.sb = mem.T; L.src.t = 0; L.src.lerp = false;
+    L.res = mem.xold();
+    if (check_convx && testx < tolx) st = IK_CONVX;
+    else if (check_convx && L.it >= c.max_iters) st = IK_MAXIT;
+    else {
+      pn = sqrt_(pn);
+      if (pn > L.stpmax) {
+        const Real sc = L.stpmax / pn;
+        test = 0;
+        const int T = mem.T;
+        Real *pp = mem.p();
+        const Real *px = mem.xold();
+#pragma unroll 1
+        for (int j = 0; j < n; j++) {
+          const Real pj = pp[j * T] * sc;
+          pp[j * T] = pj;
+          test = max_(test, abs_(pj) / max_(abs_(px[j * T]), Real(1)));
         }
-      m3_mul(D, Src, DSrc);
-      m3_mul(D, Srr, DSrr);
-#pragma unroll
-      for (int r = 0; r < 3; r++)
-#pragma unroll
-        for (int q = 0; q <= r; q++) A[tri(r, q)] = o.S[tri(r, q)];
-#pragma unroll
-      for (int r = 0; r < 3; r++)
-#pragma unroll
-        for (int q = 0; q < 3; q++) A[tri(3 + r, q)] = DSrc[3 * r + q];
-#pragma unroll
-      for (int r = 0; r < 3; r++)
-#pragma unroll
-        for (int q = 0; q <= r; q++)
-          A[tri(3 + r, 3 + q)] = DSrr[3 * r] * D[3 * q] + DSrr[3 * r + 1] * D[3 * q + 1] + DSrr[3 * r + 2] * D[3 * q + 2];
-#pragma unroll
-      for (int r = 0; r < M; r++) A[tri(r, r)] += l2;
-      chol_solve_fast<Real, M>(A, o.FL, y);
-      Real z[3];
-      m3_Tvec(D, &y[M - 3], z);
-      y[M - 3] = z[0]; y[M - 2] = z[1]; y[M - 1] = z[2];
+        slope *= sc;
+      }
+      if (!(slope < Real(0))) { L.it++; st = IK_STALL; }
+      else {
+        L.alamin = fdiv_(tolx, test);
+        L.fold = o.f; L.slope = slope; L.alam = 1; L.alam2 = 0; L.f2 = 0;
+        L.src.t = 1;
+        L.phase = 1;
+      }
     }
   }
-  Real pn = 0, slope = 0, test = 0, testx = 0;
-  {
-    const int T = mem.T;
-    const Real *pa = L.src.a, *pb = L.src.b;
-    Real *px = mem.xold(), *pp = mem.p();
-    const Real *pc = mem.cols();
-#pragma unroll 1
-    for (int j = 0; j < n; j++) {
-      const Real av = *pa, bv = *pb;
-      pa += L.src.sa; pb += L.src.sb;
-      const Real dir = L.src.lerp ? bv - av : bv;
-      const Real xj = min_(max_(av + L.src.t * dir, c.bmin[j]), c.bmax[j]);
-      const Real rinv = fdiv_(Real(1), max_(abs_(xj), Real(1)));
-      testx = max_(testx, abs_(xj - av) * rinv);      // only meaningful in phase 1 (av = xold)
-      Real pj = 0, gj = 0;
-#pragma unroll
-      for (int r = 0; r < M; r++) { const Real cj = pc[r * T]; pj += cj * y[r]; gj += cj * o.FL[r]; }
-      pc += M * T;
-      pj = -pj;
-      *px = xj; *pp = pj;
-      px += T; pp += T;
-      pn += pj * pj;
-      slope += gj * pj;
-      test = max_(test, abs_(pj) * rinv);
-    }
-  }
-  // from here on the trial point is x = xold + alam p in lane memory
-  L.alam = 0;
-  L.src.a = mem.xold(); L.src.b = mem.p(); L.src.sa = mem.T; L.src.sb = mem.T; L.src.t = 0; L.src.lerp = false;
-  if (check_convx) {
-    if (testx < tolx) return IK_CONVX;
-    if (L.it >= c.max_iters) return IK_MAXIT;
-  }
-  pn = sqrt_(pn);
-  if (pn > L.stpmax) {
-    const Real sc = L.stpmax / pn;
-    test = 0;
-    const int T = mem.T;
-    Real *pp = mem.p();
-    const Real *px = mem.xold();
-#pragma unroll 1
-    for (int j = 0; j < n; j++) {
-      const Real pj = pp[j * T] * sc;
-      pp[j * T] = pj;
-      test = max_(test, abs_(pj) / max_(abs_(px[j * T]), Real(1)));
-    }
-    slope *= sc;
-  }
-  if (!(slope < Real(0))) { L.it++; return IK_STALL; }
-  L.alamin = fdiv_(tolx, test);
-  L.fold = o.f; L.slope = slope; L.alam = 1; L.alam2 = 0; L.f2 = 0;
-  L.src.t = 1;
-  L.phase = 1;
-  return IK_RUNNING;
+  return st;
 }
 
 }  // namespace grr
