@@ -24,7 +24,7 @@ MAX_JOINTS = 32
 EXPORTS = [
     "grr_last_error", "grr_abi_version", "grr_chain_create", "grr_chain_destroy", "grr_task_set",
     "grr_chain_num_joints", "grr_fk_batch", "grr_ik_solve_batch", "grr_ik_sample", "grr_dedup",
-    "grr_edges_build", "grr_edges_compact", "grr_valid_edge_batch", "grr_gather_node_blocks",
+    "grr_edges_build", "grr_edges_cost", "grr_edges_compact", "grr_valid_edge_batch", "grr_gather_node_blocks",
     "grr_scatter_node_blocks", "grr_fp32_peak",
 ]
 
@@ -70,6 +70,7 @@ def lib():
     L.grr_ik_sample.argtypes = [vp, C.c_int, i64, i32, i32, vp, vp, u64, i32, vp, vp, vp, vp, vp]
     L.grr_dedup.argtypes = [vp, C.c_int, i64, i32, i32, vp, vp, dbl, i32, vp, vp, vp, vp, vp]
     L.grr_edges_build.argtypes = [vp, C.c_int, i64, vp, vp, vp, vp, vp, i32, i32, dbl, vp, vp, vp, vp]
+    L.grr_edges_cost.argtypes = [vp, C.c_int, i64, vp, vp, vp, vp, i32, dbl, vp, vp]
     L.grr_edges_compact.argtypes = [i64, i32, vp, vp, vp, vp]
     L.grr_valid_edge_batch.argtypes = [vp, C.c_int, i64, vp, vp, vp, vp, dbl, vp, vp, vp, vp]
     L.grr_gather_node_blocks.argtypes = [C.c_int, i64, vp, i32, i32, vp, vp, vp, vp, vp]
@@ -206,6 +207,12 @@ class ChainHandle:
                                     _ptr(q_kept), _ptr(count), _ptr(old_count), int(Nq), Nqp, float(epsilon),
                                     _ptr(mask), _ptr(edge_stats), _ptr(counters), _stream(q_kept.device)),
               "grr_edges_build")
+
+    def edges_cost(self, wedges, q_kept, count, epsilon, cost, old_count=None):
+        E = wedges.shape[0]
+        check(lib().grr_edges_cost(self._h, dtype_code(q_kept.dtype), E, _ptr(wedges), _ptr(q_kept), _ptr(count),
+                                   _ptr(old_count), q_kept.shape[2], float(epsilon), _ptr(cost), _stream(q_kept.device)),
+              "grr_edges_cost")
 
     def valid_edge_batch(self, qa, qb, wa, wb, epsilon, valid, info=None, counters=None):
         P = qa.shape[1]

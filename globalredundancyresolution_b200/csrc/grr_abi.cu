@@ -103,6 +103,45 @@ k_edges_compact(int Nq, const uint32_t *__restrict__ mask, const long long *__re
 }
 
 // ------------------------------------------------------------------------------------------
+// Work estimate per workspace edge: sum over its (not both-old) pairs of Ndivs + 1 = ceil(dist/eps) + 1
+// (graph.py:944-946), i.e. the number of interpolated IK solves + leaf tests the edge kernel will run.
+// Used to balance shards across GPUs by work instead of by pair count.  One CTA per workspace edge.
+// ------------------------------------------------------------------------------------------
+template <typename Real>
+__global__ void __launch_bounds__(256)
+k_edges_cost(int n, int nlinks_eps, const int32_t *__restrict__ wedges, const Real *__restrict__ q_kept,
+             const int32_t *__restrict__ count, const int32_t *__restrict__ old_count, int Nqp, Real epsilon,
+             unsigned long long *__restrict__ cost) {
+  extern __shared__ __align__(16) unsigned char smem_cost[];
+  Real *sa = reinterpret_cast<Real *>(smem_cost), *sb = sa + n * Nqp;
+  __shared__ unsigned long long s_sum;
+  const long long e = blockIdx.x;
+  const int iw = wedges[2 * e], jw = wedges[2 * e + 1];
+  const int ca = count[iw], cb = count[jw];
+  const int oa = old_count ? old_count[iw] : 0, ob = old_count ? old_count[jw] : 0;
+  if (threadIdx.x == 0) s_sum = 0;
+  const unsigned total = (unsigned)ca * (unsigned)cb;
+  if (total) {
+    const Real *ga = q_kept + (long long)iw * n * Nqp, *gb = q_kept + (long long)jw * n * Nqp;
+    for (int k = threadIdx.x; k < n * Nqp; k += blockDim.x) { sa[k] = ga[k]; sb[k] = gb[k]; }
+  }
+  __syncthreads();
+  const Real eps = epsilon * sqrt_(Real(nlinks_eps));
+  unsigned long long acc = 0;
+  for (unsigned t = threadIdx.x; t < total; t += blockDim.x) {
+    const int a = (int)(t / (unsigned)cb), b = (int)(t - (unsigned)a * (unsigned)cb);
+    if (a < oa && b < ob) continue;
+    Real d2 = 0;
+    for (int j = 0; j < n; j++) { const Real d = sa[j * Nqp + a] - sb[j * Nqp + b]; d2 += d * d; }
+    acc += (unsigned long long)ceil_(sqrt_(d2) / eps) + 1ull;
+  }
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0 && acc) atomicAdd(&s_sum, acc);
+  __syncthreads();
+  if (threadIdx.x == 0) cost[e] = s_sum;
+}
+
+// ------------------------------------------------------------------------------------------
 // FK on a batch (API: ikError / getIKParameters; graph.py:747-756,887-893)
 // ------------------------------------------------------------------------------------------
 template <typename Real>
@@ -302,6 +341,28 @@ int grr_edges_build(grr_handle_t h, int dtype, int64_t E, const int32_t *wedges,
   if (E > 0 && (!wedges || !params || !q_kept || !count || !mask)) { set_error("grr_edges_build: null buffer"); return -1; }
   return ops->edges_build(h->hc, E, wedges, params, q_kept, count, old_count, Nq, Nqp, epsilon, mask, edge_stats,
                           (unsigned long long *)counters, (cudaStream_t)stream);
+}
+
+int grr_edges_cost(grr_handle_t h, int dtype, int64_t E, const int32_t *wedges, const void *q_kept, const int32_t *count,
+                   const int32_t *old_count, int32_t Nqp, double epsilon, uint64_t *cost, void *stream) {
+  GRR_CHECK_HANDLE(h);
+  if (E <= 0) return 0;
+  if (!wedges || !q_kept || !count || !cost) { set_error("grr_edges_cost: null buffer"); return -1; }
+  cudaStream_t st = (cudaStream_t)stream;
+  const int n = h->hc.n;
+  const size_t smem = 2 * (size_t)n * Nqp * (dtype == GRR_F64 ? 8 : 4);
+  if (dtype == GRR_F32) {
+    auto kern = k_edges_cost<float>;
+    if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    kern<<<(unsigned)E, 256, smem, st>>>(n, h->hc.nlinks_eps, wedges, (const float *)q_kept, count, old_count, Nqp, (float)epsilon,
+                                         (unsigned long long *)cost);
+  } else if (dtype == GRR_F64) {
+    auto kern = k_edges_cost<double>;
+    if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    kern<<<(unsigned)E, 256, smem, st>>>(n, h->hc.nlinks_eps, wedges, (const double *)q_kept, count, old_count, Nqp, epsilon,
+                                         (unsigned long long *)cost);
+  } else { set_error("bad dtype %d", dtype); return -1; }
+  return launch_ok("k_edges_cost");
 }
 
 int grr_edges_compact(int64_t E, int32_t Nq, const uint32_t *mask, const int64_t *offsets, int32_t *out, void *stream) {

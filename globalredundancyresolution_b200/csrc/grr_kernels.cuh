@@ -5,6 +5,7 @@
 #include "grr_lane.cuh"
 #include "grr_host.h"
 #include "grr_fill.cuh"
+#include <stdlib.h>
 
 namespace grr {
 
@@ -35,7 +36,7 @@ struct LaneCounters {
 //           (parallelQSamplingAtP solver.py:875-885; random phase of sampleConfigurationSpace :817-821)
 //   MODE 1: explicit (target, seed) instances, SoA q[n][P]  (RedundancyResolutionGraph.solve, graph.py:779-790)
 // ------------------------------------------------------------------------------------------
-template <typename Real, int M, int MODE>
+template <typename Real, int M, int MODE, bool PL>
 __global__ void __launch_bounds__(256)
 k_ik_instances(const __grid_constant__ ChainDev<Real, kMaxJ> c, long long total, int Nq, int Nqp,
                const Real *__restrict__ params, const int32_t *__restrict__ uid, unsigned long long seed, int sample_offset,
@@ -43,10 +44,10 @@ k_ik_instances(const __grid_constant__ ChainDev<Real, kMaxJ> c, long long total,
                unsigned long long *work, unsigned long long *counters) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int n = c.n, dw = (c.mode == 2 ? 6 : 3);
-  LaneMem<Real, M> mem;
+  LaneMem<Real, col_rows(M, PL)> mem;
   mem.init(reinterpret_cast<Real *>(smem_raw) + threadIdx.x, (int)blockDim.x, n);
   LaneIK<Real, M> L;
-  lane_begin_mem<Real, M>(L, mem);
+  lane_begin_mem(L, mem);
   Target<Real, M> tg;
   tg.x[0] = tg.x[1] = tg.x[2] = 0;
   if (M == 6) { for (int k = 0; k < 9; k++) tg.R[k] = (k % 4 == 0) ? Real(1) : Real(0); }
@@ -84,13 +85,14 @@ k_ik_instances(const __grid_constant__ ChainDev<Real, kMaxJ> c, long long total,
           for (int k = 0; k < dw; k++) w[k] = params[t * dw + k];
         }
         target_from_params<Real, M, kMaxJ>(c, w, tg);
-        lane_begin_mem<Real, M>(L, mem);
+        lane_begin_mem(L, mem);
       }
     }
     if (__all_sync(0xffffffffu, inst < 0)) break;
     PassOut<Real, M> o;
-    lane_pass<Real, M, false>(c, tg, L.src, mem, nullptr, 0, o);
-    const int st = lane_step<Real, M>(c, L, mem, o, inst >= 0);
+    if constexpr (PL) lane_pass_planar<Real, false>(c, tg, L.src, mem, nullptr, 0, o);
+    else lane_pass<Real, M, false>(c, tg, L.src, mem, nullptr, 0, o);
+    const int st = lane_step<Real, M, PL>(c, L, mem, o, inst >= 0);
     if (inst >= 0) {
       if (st != IK_RUNNING) {
         long long base, stride, sidx;
@@ -105,7 +107,7 @@ k_ik_instances(const __grid_constant__ ChainDev<Real, kMaxJ> c, long long total,
         if (resid) resid[sidx] = L.resid;
         cnt.solves++; cnt.iters += L.it; cnt.evals += L.evals; cnt.ok += (st == IK_OK);
         inst = -1;
-        lane_begin_mem<Real, M>(L, mem);     // idle lanes keep walking valid memory
+        lane_begin_mem(L, mem);     // idle lanes keep walking valid memory
       }
     }
   }
@@ -143,8 +145,8 @@ __device__ __forceinline__ bool pair_begin(const ChainT &c, Real eps, PairLane<R
 // One interpolated solve finished with IK_OK; s2 = |q_k - q_{k-1}|^2 was accumulated by the final
 // pass.  Leaf test, then either the closing leaf (q_Ndivs, qb) or the next k: the solution buffer
 // becomes `prev` by swapping roles.  Returns +1 valid, 0 invalid, -1 continue (seed armed).
-template <typename Real, int M, typename ChainT>
-__device__ __forceinline__ int pair_advance(const ChainT &c, LaneMem<Real, M> &mem, Real s2, Real thr2, PairLane<Real> &P,
+template <typename Real, int M, int MC, typename ChainT>
+__device__ __forceinline__ int pair_advance(const ChainT &c, LaneMem<Real, MC> &mem, Real s2, Real thr2, PairLane<Real> &P,
                                             LaneIK<Real, M> &L) {
   if (s2 > thr2) return 0;                                       // graph.py:954-959 (leaf)
   if (P.k == P.ndivs) {
@@ -160,7 +162,7 @@ __device__ __forceinline__ int pair_advance(const ChainT &c, LaneMem<Real, M> &m
 }
 
 // explicit pairs, SoA qa[n][P], qb[n][P]  (validEdge, graph.py:1051-1053), work-fetching lanes
-template <typename Real, int M>
+template <typename Real, int M, bool PL>
 __global__ void __launch_bounds__(256)
 k_valid_edge_batch(const __grid_constant__ ChainDev<Real, kMaxJ> c, long long total, const Real *__restrict__ qa,
                    const Real *__restrict__ qb, const Real *__restrict__ wa, const Real *__restrict__ wb, Real epsilon,
@@ -168,13 +170,13 @@ k_valid_edge_batch(const __grid_constant__ ChainDev<Real, kMaxJ> c, long long to
                    unsigned long long *counters) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int n = c.n, dw = (c.mode == 2 ? 6 : 3);
-  LaneMem<Real, M> mem;
+  LaneMem<Real, col_rows(M, PL)> mem;
   mem.init(reinterpret_cast<Real *>(smem_raw) + threadIdx.x, (int)blockDim.x, n);
   const Real eps = epsilon * sqrt_(Real(c.nlinks_eps));          // graph.py:945
   const Real thr = eps * Real(c.nlinks_eps);                     // graph.py:947
   const Real thr2 = thr * thr;
   LaneIK<Real, M> L;
-  lane_begin_mem<Real, M>(L, mem);
+  lane_begin_mem(L, mem);
   for (int j = 0; j < 4 * n; j++) mem.base[j * mem.T] = 0;
   PairLane<Real> P;
   WInterp<Real, M> W;
@@ -204,14 +206,15 @@ k_valid_edge_batch(const __grid_constant__ ChainDev<Real, kMaxJ> c, long long to
     if (__any_sync(0xffffffffu, running)) {
       PassOut<Real, M> o;
       const bool first = running && P.k == 1;
-      lane_pass<Real, M, true>(c, tg, L.src, mem, first ? P.qa : mem.prev(), first ? P.sa : mem.T, o);
-      const int st = lane_step<Real, M>(c, L, mem, o, running);
+      if constexpr (PL) lane_pass_planar<Real, true>(c, tg, L.src, mem, first ? P.qa : mem.prev(), first ? P.sa : mem.T, o);
+      else lane_pass<Real, M, true>(c, tg, L.src, mem, first ? P.qa : mem.prev(), first ? P.sa : mem.T, o);
+      const int st = lane_step<Real, M, PL>(c, L, mem, o, running);
       if (running && st != IK_RUNNING) {
         P.solves++; P.iters += L.it;
         cnt.solves++; cnt.iters += L.it; cnt.evals += L.evals; cnt.ok += (st == IK_OK);
         if (st != IK_OK) { verdict = 0; fail = 1; }               // graph.py:964-966
         else {
-          verdict = pair_advance<Real, M>(c, mem, o.s2, thr2, P, L);
+          verdict = pair_advance(c, mem, o.s2, thr2, P, L);
           if (verdict == 0) fail = 2;
           if (verdict < 0) winterp_at<Real, M>(W, Real(P.k) / Real(P.ndivs + 1), tg);
         }
@@ -222,7 +225,7 @@ k_valid_edge_batch(const __grid_constant__ ChainDev<Real, kMaxJ> c, long long to
       if (info) { info[4 * t] = P.ndivs; info[4 * t + 1] = P.solves; info[4 * t + 2] = fail; info[4 * t + 3] = P.iters; }
       cnt.pairs++; cnt.valid += verdict;
       t = -1;
-      lane_begin_mem<Real, M>(L, mem);     // idle lanes keep walking valid memory
+      lane_begin_mem(L, mem);     // idle lanes keep walking valid memory
     }
   }
   cnt.flush(counters);
@@ -235,7 +238,7 @@ k_valid_edge_batch(const __grid_constant__ ChainDev<Real, kMaxJ> c, long long to
 // shared-memory counter and run their pairs as independent lane machines; verdict bits are OR-ed into
 // a shared-memory Nq x Nq bitmask that is written out once.
 // ------------------------------------------------------------------------------------------
-template <typename Real, int M>
+template <typename Real, int M, bool PL>
 __global__ void __launch_bounds__(sizeof(Real) == 4 ? 512 : 256)
 k_edges_build(const __grid_constant__ ChainDev<Real, kMaxJ> c, const int32_t *__restrict__ wedges,
               const Real *__restrict__ params, const Real *__restrict__ q_kept, const int32_t *__restrict__ count,
@@ -269,7 +272,7 @@ k_edges_build(const __grid_constant__ ChainDev<Real, kMaxJ> c, const int32_t *__
     const Real *ga = q_kept + (long long)iw * n * Nqp, *gb = q_kept + (long long)jw * n * Nqp;
     for (int k = threadIdx.x; k < n * Nqp; k += blockDim.x) { sa[k] = ga[k]; sb[k] = gb[k]; }
   }
-  LaneMem<Real, M> mem;
+  LaneMem<Real, col_rows(M, PL)> mem;
   mem.init(lanes + threadIdx.x, (int)blockDim.x, n);
   for (int j = 0; j < 4 * n; j++) mem.base[j * mem.T] = 0;
   __syncthreads();
@@ -285,7 +288,7 @@ k_edges_build(const __grid_constant__ ChainDev<Real, kMaxJ> c, const int32_t *__
       winterp_begin<Real, M, kMaxJ>(c, a6, b6, W);
     }
     LaneIK<Real, M> L;
-    lane_begin_mem<Real, M>(L, mem);
+    lane_begin_mem(L, mem);
     PairLane<Real> P;
     Target<Real, M> tg;
     tg.x[0] = tg.x[1] = tg.x[2] = 0;
@@ -314,13 +317,14 @@ k_edges_build(const __grid_constant__ ChainDev<Real, kMaxJ> c, const int32_t *__
       if (__any_sync(0xffffffffu, running)) {
         PassOut<Real, M> o;
         const bool first = running && P.k == 1;
-        lane_pass<Real, M, true>(c, tg, L.src, mem, first ? P.qa : mem.prev(), first ? P.sa : mem.T, o);
-        const int st = lane_step<Real, M>(c, L, mem, o, running);
+        if constexpr (PL) lane_pass_planar<Real, true>(c, tg, L.src, mem, first ? P.qa : mem.prev(), first ? P.sa : mem.T, o);
+        else lane_pass<Real, M, true>(c, tg, L.src, mem, first ? P.qa : mem.prev(), first ? P.sa : mem.T, o);
+        const int st = lane_step<Real, M, PL>(c, L, mem, o, running);
         if (running && st != IK_RUNNING) {
           cnt.solves++; cnt.iters += L.it; cnt.evals += L.evals; cnt.ok += (st == IK_OK);
           if (st != IK_OK) verdict = 0;                         // graph.py:964-966
           else {
-            verdict = pair_advance<Real, M>(c, mem, o.s2, thr2, P, L);
+            verdict = pair_advance(c, mem, o.s2, thr2, P, L);
             if (verdict < 0) winterp_at<Real, M>(W, Real(P.k) / Real(P.ndivs + 1), tg);
           }
         }
@@ -329,7 +333,7 @@ k_edges_build(const __grid_constant__ ChainDev<Real, kMaxJ> c, const int32_t *__
         if (verdict) atomicOr(&smask[a * Wd + (b >> 5)], 1u << (b & 31));
         cnt.pairs++; cnt.valid += verdict;
         a = -1;
-        lane_begin_mem<Real, M>(L, mem);   // idle lanes keep walking valid memory
+        lane_begin_mem(L, mem);   // idle lanes keep walking valid memory
       }
     }
   }
@@ -377,13 +381,31 @@ inline int set_smem(Kern kern, size_t smem, const char *what) {
   return 0;
 }
 
+// planar-y chain: every joint of the short kind about +-e_y, goal-link frame = last joint frame, free orientation
+inline bool is_planar_y(const HostChain &h) {
+  if (h.mode != GRR_FREE) return false;
+  for (int k = 0; k < 9; k++) if (fabs(h.R_tail[k] - ((k % 4 == 0) ? 1.0 : 0.0)) > 1e-14) return false;
+  for (int j = 0; j < h.n; j++) {
+    const double *R = h.Rp + 9 * j, *a = h.axis + 3 * j;
+    for (int k = 0; k < 9; k++) if (fabs(R[k] - ((k % 4 == 0) ? 1.0 : 0.0)) > 1e-14) return false;
+    if (fabs(fabs(a[1]) - 1.0) > 1e-14 || fabs(a[0]) > 1e-14 || fabs(a[2]) > 1e-14) return false;
+  }
+  return true;
+}
+
 template <typename Real, int M>
 struct Impl {
   using Chain = ChainDev<Real, kMaxJ>;
+  static constexpr bool kHasPlanar = (M == 3);
+  static bool planar(const HostChain &h) {
+    static const bool off = getenv("GRR_NO_PLANAR") != nullptr;   // A/B switch for profiling
+    return kHasPlanar && !off && is_planar_y(h);
+  }
+  static int mc(const HostChain &h) { return planar(h) ? 2 : M; }
 
   // persistent lanes: threads per CTA and CTAs so that every SM holds as many lanes as shared memory allows
   static void lane_geometry(const HostChain &h, size_t fixed_bytes, int max_threads, int &threads, int &ctas_per_sm) {
-    const size_t per_lane = (size_t)lane_reals<M>(h.n) * sizeof(Real);
+    const size_t per_lane = (size_t)h.n * (4 + mc(h)) * sizeof(Real);
     ctas_per_sm = 2;
     size_t per_cta = kSmemBudget / 2 - 1024;
     long t = per_cta > fixed_bytes ? (long)((per_cta - fixed_bytes) / per_lane) : 0;
@@ -401,22 +423,23 @@ struct Impl {
     int threads, per_sm;
     lane_geometry(h, 0, 256, threads, per_sm);
     if (threads < 32) { set_error("ik: chain too large for shared memory"); return -2; }
-    const size_t smem = (size_t)threads * lane_reals<M>(h.n) * sizeof(Real);
+    const size_t smem = (size_t)threads * h.n * (4 + mc(h)) * sizeof(Real);
     long long ctas = (long long)sm_count(h.device) * per_sm;
     const long long need = (total + threads - 1) / threads;
     if (ctas > need) ctas = need;
     cudaMemsetAsync(work, 0, sizeof(unsigned long long), st);
-    if (mode == 0) {
-      auto kern = k_ik_instances<Real, M, 0>;
+    auto launch = [&](auto kern) -> int {
       if (set_smem(kern, smem, "k_ik_instances")) return -2;
       kern<<<(unsigned)ctas, threads, smem, st>>>(c, total, Nq, Nqp, (const Real *)params, uid, seed, sample_offset, (Real *)q,
                                                   status, iters, (Real *)resid, work, counters);
-    } else {
-      auto kern = k_ik_instances<Real, M, 1>;
-      if (set_smem(kern, smem, "k_ik_instances")) return -2;
-      kern<<<(unsigned)ctas, threads, smem, st>>>(c, total, Nq, Nqp, (const Real *)params, uid, seed, sample_offset, (Real *)q,
-                                                  status, iters, (Real *)resid, work, counters);
-    }
+      return 0;
+    };
+    int rc;
+    if constexpr (kHasPlanar) {
+      if (planar(h)) rc = (mode == 0) ? launch(k_ik_instances<Real, M, 0, true>) : launch(k_ik_instances<Real, M, 1, true>);
+      else rc = (mode == 0) ? launch(k_ik_instances<Real, M, 0, false>) : launch(k_ik_instances<Real, M, 1, false>);
+    } else rc = (mode == 0) ? launch(k_ik_instances<Real, M, 0, false>) : launch(k_ik_instances<Real, M, 1, false>);
+    if (rc) return rc;
     return check_launch("k_ik_instances");
   }
 
@@ -439,15 +462,21 @@ struct Impl {
     int threads, per_sm;
     lane_geometry(h, 0, 256, threads, per_sm);
     if (threads < 32) { set_error("valid_edge: chain too large for shared memory"); return -2; }
-    const size_t smem = (size_t)threads * lane_reals<M>(h.n) * sizeof(Real);
+    const size_t smem = (size_t)threads * h.n * (4 + mc(h)) * sizeof(Real);
     long long ctas = (long long)sm_count(h.device) * per_sm;
     const long long need = (P + threads - 1) / threads;
     if (ctas > need) ctas = need;
-    auto kern = k_valid_edge_batch<Real, M>;
-    if (set_smem(kern, smem, "k_valid_edge_batch")) return -2;
     cudaMemsetAsync(work, 0, sizeof(unsigned long long), st);
-    kern<<<(unsigned)ctas, threads, smem, st>>>(c, P, (const Real *)qa, (const Real *)qb, (const Real *)wa, (const Real *)wb,
-                                                (Real)epsilon, valid, info, work, counters);
+    auto launch = [&](auto kern) -> int {
+      if (set_smem(kern, smem, "k_valid_edge_batch")) return -2;
+      kern<<<(unsigned)ctas, threads, smem, st>>>(c, P, (const Real *)qa, (const Real *)qb, (const Real *)wa, (const Real *)wb,
+                                                  (Real)epsilon, valid, info, work, counters);
+      return 0;
+    };
+    int rc;
+    if constexpr (kHasPlanar) rc = planar(h) ? launch(k_valid_edge_batch<Real, M, true>) : launch(k_valid_edge_batch<Real, M, false>);
+    else rc = launch(k_valid_edge_batch<Real, M, false>);
+    if (rc) return rc;
     return check_launch("k_valid_edge_batch");
   }
   static int edges_build(const HostChain &h, long long E, const int32_t *wedges, const void *params, const void *q_kept,
@@ -460,11 +489,17 @@ struct Impl {
     int threads, per_sm;
     lane_geometry(h, fixed, sizeof(Real) == 4 ? 512 : 256, threads, per_sm);
     if (threads < 32) { set_error("edges_build: Nq=%d, n=%d does not fit shared memory", Nq, h.n); return -2; }
-    const size_t smem = fixed + (size_t)threads * lane_reals<M>(h.n) * sizeof(Real);
-    auto kern = k_edges_build<Real, M>;
-    if (set_smem(kern, smem, "k_edges_build")) return -2;
-    kern<<<(unsigned)E, threads, smem, st>>>(c, wedges, (const Real *)params, (const Real *)q_kept, count, old_count, Nq, Nqp,
-                                             (Real)epsilon, mask, edge_stats, counters);
+    const size_t smem = fixed + (size_t)threads * h.n * (4 + mc(h)) * sizeof(Real);
+    auto launch = [&](auto kern) -> int {
+      if (set_smem(kern, smem, "k_edges_build")) return -2;
+      kern<<<(unsigned)E, threads, smem, st>>>(c, wedges, (const Real *)params, (const Real *)q_kept, count, old_count, Nq, Nqp,
+                                               (Real)epsilon, mask, edge_stats, counters);
+      return 0;
+    };
+    int rc;
+    if constexpr (kHasPlanar) rc = planar(h) ? launch(k_edges_build<Real, M, true>) : launch(k_edges_build<Real, M, false>);
+    else rc = launch(k_edges_build<Real, M, false>);
+    if (rc) return rc;
     return check_launch("k_edges_build");
   }
 };

@@ -55,14 +55,27 @@ __device__ __forceinline__ void sincos_joint(float x, float *s, float *c) {
   *c = ((q + 1) & 2) ? -cc : cc;
 }
 __device__ __forceinline__ void sincos_joint(double x, double *s, double *c) { sincos(x, s, c); }
+// every joint limit of the chain lies inside [-pi/4, pi/4] (planar 10R / 20R): no reduction, no fix-up
+__device__ __forceinline__ void sincos_small(float r, float *s, float *c) {
+  const float r2 = r * r;
+  float sp = fmaf(r2, -1.9515295891e-4f, 8.3321608736e-3f);
+  sp = fmaf(sp, r2, -1.6666654611e-1f);
+  *s = fmaf(sp * r2, r, r);
+  float cp = fmaf(r2, 2.443315711809948e-5f, -1.388731625493765e-3f);
+  cp = fmaf(cp, r2, 4.166664568298827e-2f);
+  *c = fmaf(cp * r2, r2, fmaf(r2, -0.5f, 1.0f));
+}
+__device__ __forceinline__ void sincos_small(double x, double *s, double *c) { sincos(x, s, c); }
 
 // Reals of shared memory one lane needs: three rotating config buffers (line-search origin xold,
 // trial point xcur, previous interpolated solution prev), the direction p and the Jacobian columns.
-template <int M> __host__ __device__ constexpr int lane_reals(int n) { return n * (4 + M); }
+// MC = rows of a stored Jacobian column: M in general, 2 for the planar-y specialisation (PL)
+__host__ __device__ constexpr int col_rows(int M, bool PL) { return PL ? 2 : M; }
+template <int MC> __host__ __device__ constexpr int lane_reals(int n) { return n * (4 + MC); }
 
 // Shared-memory view of one lane's joint vectors: element k of an array lives at ptr[k * T].
 // The three config buffers change roles by swapping offsets, never by copying.
-template <typename Real, int M>
+template <typename Real, int MC>
 struct LaneMem {
   Real *base;   // already offset by tid
   int T;        // lanes per CTA (stride)
@@ -75,7 +88,7 @@ struct LaneMem {
   __device__ __forceinline__ Real *xcur() const { return base + o_xcur; }
   __device__ __forceinline__ Real *prev() const { return base + o_prev; }
   __device__ __forceinline__ Real *p() const { return base + 3 * n * T; }
-  __device__ __forceinline__ Real *cols() const { return base + 4 * n * T; }   // [j][r], r < M
+  __device__ __forceinline__ Real *cols() const { return base + 4 * n * T; }   // [j][r], r < MC
 };
 
 // Where the current trial point comes from: x_j = clamp(a[j*sa] + t * (lerp ? b[j*sb] - a[j*sa] : b[j*sb])).
@@ -107,8 +120,8 @@ __device__ __forceinline__ void lane_begin_lerp(LaneIK<Real, M> &L, const Real *
   L.src.a = a; L.src.b = b; L.src.sa = sa; L.src.sb = sb; L.src.t = u; L.src.lerp = true;
 }
 // Start an instance whose seed has been written to mem.xold() (t = 0: the direction is ignored).
-template <typename Real, int M>
-__device__ __forceinline__ void lane_begin_mem(LaneIK<Real, M> &L, const LaneMem<Real, M> &mem) {
+template <typename Real, int M, int MC>
+__device__ __forceinline__ void lane_begin_mem(LaneIK<Real, M> &L, const LaneMem<Real, MC> &mem) {
   lane_reset(L);
   L.src.a = mem.xold(); L.src.b = mem.p(); L.src.sa = mem.T; L.src.sb = mem.T; L.src.t = 0; L.src.lerp = false;
   L.res = mem.xold();
@@ -148,6 +161,66 @@ struct PassOut {
 
 // xref (stride sref): config against which the joint-space distance of the trial point is accumulated
 // (the previous interpolated solution of a pair); nullptr = none.
+// ---- planar-y specialisation: every joint has identity preceding rotation and axis +-e_y, and the
+// goal-link frame equals the last joint frame (the reference's planar_{2,3,5,10,20}R robots).  G stays a
+// rotation about y, kept as (cos, sin); columns have two in-plane components (x, z); the normal matrix is
+// 2x2.  Same algorithm, a third of the arithmetic.
+template <typename Real, bool WITH_REF, typename ChainT>
+__device__ __forceinline__ void lane_pass_planar(const ChainT &c, const Target<Real, 3> &tg, const XSrc<Real> &src,
+                                                 const LaneMem<Real, 2> &mem, const Real *xref, int sref,
+                                                 PassOut<Real, 3> &o) {
+  const int n = c.n;
+  // in-plane components: I1 = z (index 2), I2 = x (index 0); Rot_y(t): z' = c z - s x, x' = s z + c x
+  Real vz = c.ee[2], vx = c.ee[0], vy = c.ee[1];
+  Real gc = 1, gs = 0;                       // G = Rot_y(phi): (cos phi, sin phi)
+  Real S11 = 0, S12 = 0, S22 = 0, xn2 = 0, s2 = 0;
+  const int T = mem.T;
+  const Real *pa = src.a + (n - 1) * src.sa, *pb = src.b + (n - 1) * src.sb;
+  const Real *pr = WITH_REF ? xref + (n - 1) * sref : nullptr;
+  Real *pc = mem.cols() + (n - 1) * 2 * T;
+  Real *px = mem.xcur() + (n - 1) * T;
+  JointConst<Real> jn = c.jc[n - 1];
+  Real av_n = *pa, bv_n = *pb, rv_n = WITH_REF ? *pr : Real(0);
+  const bool small = c.small_angles != 0;
+#pragma unroll 1
+  for (int j = n - 1; j >= 0; --j) {
+    const JointConst<Real> jc = jn;
+    const Real av = av_n, bv = bv_n, rv = rv_n;
+    if (j > 0) {
+      jn = c.jc[j - 1];
+      pa -= src.sa; pb -= src.sb;
+      av_n = *pa; bv_n = *pb;
+      if (WITH_REF) { pr -= sref; rv_n = *pr; }
+    }
+    const Real dir = src.lerp ? bv - av : bv;
+    const Real xj = min_(max_(av + src.t * dir, jc.bmin), jc.bmax);
+    *px = xj; px -= T;
+    xn2 += xj * xj;
+    if (WITH_REF) { const Real d = xj - rv; s2 += d * d; }
+    Real s, co;
+    if (small) sincos_small(xj, &s, &co); else sincos_joint(xj, &s, &co);
+    s *= jc.sgn;
+    // column = G^T (axis x v): axis x v = sgn (-v_x e_z + v_z e_x); G^T rotates by -phi
+    const Real w1 = -jc.sgn * vx, w2 = jc.sgn * vz;
+    const Real c1 = gc * w1 + gs * w2, c2 = gc * w2 - gs * w1;
+    pc[0] = c1; pc[T] = c2; pc -= 2 * T;
+    S11 += c1 * c1; S12 += c1 * c2; S22 += c2 * c2;
+    const Real nz = co * vz - s * vx, nx = s * vz + co * vx;
+    vz = nz + jc.tp[2]; vx = nx + jc.tp[0]; vy += jc.tp[1];
+    const Real ngc = co * gc - s * gs, ngs = s * gc + co * gs;
+    gc = ngc; gs = ngs;
+  }
+  o.xn2 = xn2; o.s2 = s2;
+  o.Fw[0] = vx - tg.x[0]; o.Fw[1] = vy - tg.x[1]; o.Fw[2] = vz - tg.x[2];
+  o.f = Real(0.5) * (o.Fw[0] * o.Fw[0] + o.Fw[1] * o.Fw[1] + o.Fw[2] * o.Fw[2]);
+  // goal-link frame residual, in-plane part: (z, x) rotated by -phi
+  o.FL[0] = gc * o.Fw[2] + gs * o.Fw[0];       // component along I1 (z)
+  o.FL[1] = gc * o.Fw[0] - gs * o.Fw[2];       // component along I2 (x)
+  o.FL[2] = o.Fw[1];
+  o.S[0] = S11; o.S[1] = S12; o.S[2] = S22;
+  o.fmax = max_(max_(abs_(o.Fw[0]), abs_(o.Fw[1])), abs_(o.Fw[2]));
+}
+
 template <typename Real, int M, bool WITH_REF, typename ChainT>
 __device__ __forceinline__ void lane_pass(const ChainT &c, const Target<Real, M> &tg, const XSrc<Real> &src,
                                           const LaneMem<Real, M> &mem, const Real *xref, int sref, PassOut<Real, M> &o) {
@@ -164,18 +237,28 @@ __device__ __forceinline__ void lane_pass(const ChainT &c, const Target<Real, M>
   const Real *pr = WITH_REF ? xref + (n - 1) * sref : nullptr;
   Real *pc = mem.cols() + (n - 1) * M * T;
   Real *px = mem.xcur() + (n - 1) * T;
+  // software pipeline: the next joint's constants (an indexed constant-bank load with ~100+ cycles of
+  // latency) and operands are fetched while the current joint is computed
+  JointConst<Real> jn = c.jc[n - 1];
+  Real av_n = *pa, bv_n = *pb, rv_n = WITH_REF ? *pr : Real(0);
+  const bool small = c.small_angles != 0;
 #pragma unroll 1
   for (int j = n - 1; j >= 0; --j) {
-    const Real av = *pa, bv = *pb;
-    pa -= src.sa; pb -= src.sb;
-    const JointConst<Real> jc = c.jc[j];
+    const JointConst<Real> jc = jn;
+    const Real av = av_n, bv = bv_n, rv = rv_n;
+    if (j > 0) {
+      jn = c.jc[j - 1];
+      pa -= src.sa; pb -= src.sb;
+      av_n = *pa; bv_n = *pb;
+      if (WITH_REF) { pr -= sref; rv_n = *pr; }
+    }
     const Real dir = src.lerp ? bv - av : bv;
     const Real xj = min_(max_(av + src.t * dir, jc.bmin), jc.bmax);
     *px = xj; px -= T;
     xn2 += xj * xj;
-    if (WITH_REF) { const Real d = xj - *pr; pr -= sref; s2 += d * d; }
+    if (WITH_REF) { const Real d = xj - rv; s2 += d * d; }
     Real s, co;
-    sincos_joint(xj, &s, &co);
+    if (small) sincos_small(xj, &s, &co); else sincos_joint(xj, &s, &co);
     Real col[M];
     if (jc.kind == 0) {
       Real Mj[9];
@@ -267,9 +350,10 @@ __device__ __forceinline__ void chol_solve_fast(Real (&A)[M * (M + 1) / 2], cons
 // Called by ALL lanes of the warp (`active` = this lane holds a running instance) so that the lanes
 // that start a new iteration execute the step loop together whatever path took them there.
 // Returns IK_RUNNING or the final status; after a final status the solution is L.res[j * T].
-template <typename Real, int M, typename ChainT>
-__device__ __forceinline__ int lane_step(const ChainT &c, LaneIK<Real, M> &L, LaneMem<Real, M> &mem,
+template <typename Real, int M, bool PL, typename ChainT>
+__device__ __forceinline__ int lane_step(const ChainT &c, LaneIK<Real, M> &L, LaneMem<Real, col_rows(M, PL)> &mem,
                                          const PassOut<Real, M> &o, bool active) {
+  constexpr int MC = col_rows(M, PL);
   const int n = c.n;
   const Real tolf = c.tol, tolx = Real(0.01) * c.tol, ALF = Real(1e-4);
   int st = IK_RUNNING;
@@ -314,7 +398,15 @@ __device__ __forceinline__ int lane_step(const ChainT &c, LaneIK<Real, M> &L, La
     // the accepted point (in xcur) becomes the origin of the next line search: swap roles, no copy
     { const int t = mem.o_xold; mem.o_xold = mem.o_xcur; mem.o_xcur = t; }
     Real y[M];
-    {
+    if (PL) {
+      // 2x2 in-plane normal equations (the out-of-plane row has no Jacobian)
+      const Real l2 = c.lambda * c.lambda;
+      const Real a11 = o.S[0] + l2, a12 = o.S[1], a22 = o.S[2] + l2;
+      const Real idet = fdiv_(Real(1), a11 * a22 - a12 * a12);
+      y[0] = (a22 * o.FL[0] - a12 * o.FL[1]) * idet;
+      y[1] = (a11 * o.FL[1] - a12 * o.FL[0]) * idet;
+      if (M > 2) y[2] = 0;
+    } else {
       Real A[M * (M + 1) / 2];
       const Real l2 = c.lambda * c.lambda;
       if (M == 3) {
@@ -371,8 +463,8 @@ __device__ __forceinline__ int lane_step(const ChainT &c, LaneIK<Real, M> &L, La
         testx = max_(testx, abs_(xj - xo) * rinv);
         Real pj = 0, gj = 0;
 #pragma unroll
-        for (int r = 0; r < M; r++) { const Real cj = pc[r * T]; pj += cj * y[r]; gj += cj * o.FL[r]; }
-        pc += M * T;
+        for (int r = 0; r < MC; r++) { const Real cj = pc[r * T]; pj += cj * y[r]; gj += cj * o.FL[r]; }
+        pc += MC * T;
         pj = -pj;
         *pp = pj; pp += T;
         pn += pj * pj;

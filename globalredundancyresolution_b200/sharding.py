@@ -15,6 +15,11 @@ qlists over OS pipes per task (grr/solver.py:2232-2400).  Here:
                 window; in the node-blocked layout Q[node][dof][Nqp] a node range is ONE contiguous
                 slab, so the exchange is one send/recv per overlapping (owner, user) pair with no
                 pack/unpack kernel (batched isend/irecv -> ncclSend/ncclRecv groups over NVLink);
+  4b. rebalance the work of a pair is its Ndivs (interpolated solves), which varies across the workspace
+                (measured: a 50/50 split by pair count was 58/42 by flops).  Each rank computes the exact
+                work estimate sum(Ndivs+1) of the edges of its preliminary range (grr_edges_cost, ~1 ms),
+                the per-edge costs are all-reduced (E integers), the ranges are re-cut by cost and the
+                few nodes that changed hands are exchanged with the same slab mechanism;
   5. edges      rank r builds the bitmasks of its edge range; no collective in the edge phase.
 
 The planning functions below are pure (numpy / torch-on-any-device) and are exercised on CPU with the
@@ -53,6 +58,21 @@ def edge_ranges(edges, count, world, old_count=None):
     targets = [total * r / float(world) for r in range(1, world)]
     cuts = [int(np.searchsorted(cum, t, side="left")) for t in targets]
     b = [0] + cuts + [edges.shape[0]]
+    for i in range(1, len(b)):
+        b[i] = max(b[i], b[i - 1])
+    return b
+
+
+def ranges_by_cost(cost, world):
+    """Cut a list of per-edge costs into `world` contiguous ranges of near-equal total cost."""
+    cost = np.asarray(cost, dtype=np.float64)
+    cum = np.concatenate([[0.0], np.cumsum(cost)])
+    total = cum[-1]
+    E = cost.shape[0]
+    if total <= 0:
+        return [(E * r) // world for r in range(world + 1)]
+    cuts = [int(np.searchsorted(cum, total * r / float(world), side="left")) for r in range(1, world)]
+    b = [0] + cuts + [E]
     for i in range(1, len(b)):
         b[i] = max(b[i], b[i - 1])
     return b
@@ -101,8 +121,9 @@ class ShardedResolver(RedundancyResolver):
     0.56 GB in FP32) but fills only its node window, and holds the bitmasks of its own edge range
     (`edge_lo`, `edge_hi`).  `gather_masks()` assembles the full roadmap on rank 0."""
 
-    def __init__(self, resolution, rank, world, seed=0, sample_dtype="float64"):
+    def __init__(self, resolution, rank, world, seed=0, sample_dtype="float64", rebalance=True):
         self.rank, self.world = int(rank), int(world)
+        self.rebalance = bool(rebalance)
         self.edge_lo, self.edge_hi = 0, 0
         self.halo_bytes = 0
         RedundancyResolver.__init__(self, resolution, seed=seed, sample_dtype=sample_dtype)
@@ -144,6 +165,20 @@ class ShardedResolver(RedundancyResolver):
             windows = [node_window(res.ws_edges, eb[r], eb[r + 1]) for r in range(self.world)]
             plan = halo_plan(self.nbounds, windows)
             self.halo_bytes = exchange_halo(d["Qs"], self.rank, plan, dist)
+            if self.rebalance and self.world > 1:
+                # 4b: exact work estimate on the preliminary range, then re-cut by cost
+                e0, e1 = eb[self.rank], eb[self.rank + 1]
+                wl, wh = windows[self.rank]
+                if d["Qs"] is not d["Q"]:
+                    d["Q"][wl:wh].copy_(d["Qs"][wl:wh])
+                cost = torch.zeros(self.E, dtype=torch.int64, device=res.torch_device)
+                if e1 > e0:
+                    res.chain.edges_cost(d["wedges"][e0:e1], d["Q"], d["count"], 0.05, cost[e0:e1])
+                dist.all_reduce(cost)
+                eb = ranges_by_cost(cost.cpu().numpy(), self.world)
+                windows = [node_window(res.ws_edges, eb[r], eb[r + 1]) for r in range(self.world)]
+                plan = halo_plan(self.nbounds, windows)
+                self.halo_bytes += exchange_halo(d["Qs"], self.rank, plan, dist)
             e0, e1 = eb[self.rank], eb[self.rank + 1]
             self.edge_lo, self.edge_hi = e0, e1
             W = (self.Nq + 31) // 32
@@ -179,7 +214,7 @@ class ShardedResolver(RedundancyResolver):
         lo, hi = self.nbounds[self.rank], self.nbounds[self.rank + 1]
         out, nbytes = {}, 0
         for k, t in (("Qs", d["Qs"][lo:hi]), ("count", d["count"][lo:hi]), ("mask", d["mask"])):
-            h = torch.empty(t.shape, dtype=t.dtype, device="cpu", pin_memory=True)
+            h = self._pinned_like(k, t)
             h.copy_(t, non_blocking=True)
             out[k] = h
             nbytes += t.numel() * t.element_size()

@@ -237,6 +237,16 @@ class RedundancyResolver:
         torch = self.resolution._torch()
         return torch.zeros((self.E, Nq, W), dtype=torch.int32, device=self.resolution.torch_device)
 
+    def _pinned_like(self, key, t):
+        """Pinned host staging buffer, cached across calls (pinning 200 MB costs tens of ms)."""
+        torch = self.resolution._torch()
+        cache = self.__dict__.setdefault("_pinned", {})
+        h = cache.get(key)
+        if h is None or h.shape != t.shape or h.dtype != t.dtype:
+            h = torch.empty(t.shape, dtype=t.dtype, device="cpu", pin_memory=True)
+            cache[key] = h
+        return h
+
     def download(self):
         """Device -> host copy of the roadmap (kept configs in sampling precision, counts, edge bitmasks)
         through pinned buffers.  Returns a dict of numpy arrays plus 'bytes'."""
@@ -245,7 +255,7 @@ class RedundancyResolver:
         out, nbytes = {}, 0
         for k in ("Qs", "count", "mask"):
             t = d[k]
-            h = torch.empty(t.shape, dtype=t.dtype, device="cpu", pin_memory=True)
+            h = self._pinned_like(k, t)
             h.copy_(t, non_blocking=True)
             out[k] = h
             nbytes += t.numel() * t.element_size()

@@ -127,6 +127,13 @@ int grr_edges_build(grr_handle_t h, int dtype, int64_t E, const int32_t *wedges,
                     int32_t Nqp, double epsilon, uint32_t *mask, uint32_t *edge_stats, uint64_t *counters,
                     void *stream);
 
+/* Work estimate of grr_edges_build per workspace edge: sum over the pairs it will test of
+ * Ndivs + 1 = ceil(robot.distance(qa,qb) / eps) + 1 (graph.py:944-946), i.e. interpolated IK solves +
+ * leaf tests.  Used to cut the edge list into equal-work shards (multi-GPU) -- pair counts alone
+ * mis-balance by ~15 % because Ndivs varies across the workspace.  cost [dev] u64 [E]. */
+int grr_edges_cost(grr_handle_t h, int dtype, int64_t E, const int32_t *wedges, const void *q_kept, const int32_t *count,
+                   const int32_t *old_count, int32_t Nqp, double epsilon, uint64_t *cost, void *stream);
+
 /* Materialise (iq,jq) lists from the bitmask (the Gw.edge[iw][jw]['qlist'] sets, solver.py:458).
  * offsets [dev] i64 [E+1] = exclusive scan of edge_stats[:,1] (caller computes); out [dev] i32
  * [total][2] (iq,jq) in row-major pair order. */

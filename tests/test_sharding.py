@@ -47,6 +47,12 @@ def test_partition_properties(world):
         assert have[need].all()
     own = sharding.owner_of(np.arange(Nw), nb)
     assert all(nb[o] <= i < nb[o + 1] for i, o in enumerate(own))
+    # cost-based re-cut (step 4b): contiguous, covering, balanced within one edge's cost
+    cost = load * (3 + (np.arange(E) % 7))
+    cb = sharding.ranges_by_cost(cost, world)
+    assert cb[0] == 0 and cb[-1] == E and all(b >= a for a, b in zip(cb, cb[1:]))
+    perc = [cost[cb[r]:cb[r + 1]].sum() for r in range(world)]
+    assert sum(perc) == cost.sum() and (world == 1 or max(perc) <= cost.sum() / world + cost.max() + 1)
     # incremental load excludes both-old pairs
     eb2 = sharding.edge_ranges(edges, count, world, old_count=count)
     assert eb2[0] == 0 and eb2[-1] == E
