@@ -314,6 +314,26 @@ int grr_ik_sample(grr_handle_t h, int dtype, int64_t Nw, int32_t Nq, int32_t Nqp
                         (unsigned long long *)counters, (cudaStream_t)stream);
 }
 
+int grr_ik_sample_level(grr_handle_t h, int dtype, int phase, int64_t L, const int32_t *node_list, int32_t Nq, int32_t Nqr,
+                        int32_t col_off, const void *params, const int32_t *node_uid, const int32_t *lower_ptr,
+                        const int32_t *lower_idx, const int32_t *degree, const void *q_kept, int32_t Nqp_kept,
+                        const int32_t *count, uint64_t seed, int32_t sample_offset, int32_t seed_from_adjacent, void *q_raw,
+                        uint8_t *status, uint8_t *iters, uint64_t *counters, void *stream) {
+  GRR_CHECK_HANDLE(h);
+  const Ops *ops = pick_ops(dtype, h->hc.mode);
+  if (!ops) { set_error("bad dtype %d", dtype); return -1; }
+  if (L <= 0 || Nq <= 0) return 0;
+  if (phase < 0 || phase > 1 || Nqr < col_off + Nq || col_off < 0) { set_error("grr_ik_sample_level: bad phase / column layout"); return -1; }
+  if (!node_list || !params || !node_uid || !lower_ptr || !lower_idx || !degree || !q_kept || !count || !q_raw || !status) {
+    set_error("grr_ik_sample_level: null buffer"); return -1;
+  }
+  unsigned long long *work = work_slot(h);
+  if (!work) return -3;
+  return ops->ik_level(phase, h->hc, L, node_list, Nq, Nqr, col_off, params, node_uid, lower_ptr, lower_idx, degree, q_kept,
+                       Nqp_kept, count, seed, sample_offset, seed_from_adjacent, q_raw, status, iters, work,
+                       (unsigned long long *)counters, (cudaStream_t)stream);
+}
+
 int grr_dedup(grr_handle_t h, int dtype, int64_t Nw, int32_t Nq, int32_t Nqp, const void *q_raw, const uint8_t *status,
               double thresh, int32_t Nqp_kept, void *q_kept, const int32_t *count_in, int32_t *keep_idx, int32_t *count,
               void *stream) {

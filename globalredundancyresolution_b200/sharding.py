@@ -139,10 +139,14 @@ class ShardedResolver(RedundancyResolver):
         torch = self.resolution._torch()
         return torch.zeros((0, Nq, W), dtype=torch.int32, device=self.resolution.torch_device)
 
-    def sampleConfigurationSpace(self, NConfigsPerPoint=100, connect=True, biased=False, seedFromAdjacent=True,
-                                 visibility=False, k=None):
+    def sampleConfigurationSpace(self, NConfigsPerPoint=100, connect=True, biased=False, seedFromAdjacent=False,
+                                 visibility=False, k=None, order_independent=True):
+        """Sharded build: order-independent sampling only (parallelQSamplingAtP semantics, solver.py:875-897);
+        the seeded Gauss-Seidel sweep does not shard."""
         if visibility:
             raise NotImplementedError("visibility-graph solver is out of scope of the B200 roadmap path")
+        if not order_independent:
+            raise NotImplementedError("the seeded sweep is single-GPU; shard with order_independent=True")
         import torch.distributed as dist
         torch = self.resolution._torch()
         res = self.resolution

@@ -169,6 +169,8 @@ class RedundancyResolver:
             self._graph_id = (id(res.ws_params), id(res.ws_edges))
         self.Nq = 0                  # capacity (configs per node)
         self.attempts = 0            # IK attempts made so far per node (Philox sample offset)
+        if not same_graph:
+            self._levels = None
         if drop_device or not same_graph:
             self._static = None
             self.h2d_bytes = 0
@@ -391,11 +393,76 @@ class RedundancyResolver:
         res.chain.edges_build(d["wedges"], d["params"], d["Q"], d["count"], self.Nq, DEFAULT_EDGE_CHECK_TOLERANCE,
                               d["mask"], d["edge_stats"], d["counters_e"], old_count=old_counts)
 
+    def _sweep_levels(self):
+        """Wavefront schedule of the sequential sweep of solver.py:773: node i needs the final qlists of its
+        lower-numbered neighbours only, so level(i) = 1 + max(level(j), j in N(i), j < i).  Returns the CSR of
+        lower neighbours (increasing id), the degrees and the list of node-id arrays per level (device)."""
+        if getattr(self, "_levels", None) is not None:
+            return self._levels
+        torch = self.resolution._torch()
+        e = self.resolution.ws_edges
+        Nw = self.Nw
+        order = np.lexsort((e[:, 0], e[:, 1]))                     # by upper endpoint, then lower id
+        lower_idx = e[order, 0].astype(np.int32)
+        cnt_lower = np.bincount(e[:, 1], minlength=Nw)
+        lower_ptr = np.concatenate([[0], np.cumsum(cnt_lower)]).astype(np.int32)
+        degree = (np.bincount(e[:, 0], minlength=Nw) + cnt_lower).astype(np.int32)
+        level = np.zeros(Nw, dtype=np.int64)
+        for i in range(Nw):
+            a, b = lower_ptr[i], lower_ptr[i + 1]
+            if b > a:
+                level[i] = level[lower_idx[a:b]].max() + 1
+        by_level = np.argsort(level, kind="stable").astype(np.int32)
+        bounds = np.concatenate([[0], np.cumsum(np.bincount(level))]).astype(np.int64)
+        dev = self.resolution.torch_device
+        self._levels = {
+            "lower_ptr": torch.as_tensor(lower_ptr, device=dev), "lower_idx": torch.as_tensor(lower_idx, device=dev),
+            "degree": torch.as_tensor(degree, device=dev), "order": torch.as_tensor(by_level, device=dev),
+            "bounds": bounds, "host": (lower_ptr, lower_idx, degree, level),
+        }
+        return self._levels
+
+    def _sample_phase_seeded(self, d, N, seed_from_adjacent):
+        """solver.py:757-835 as wavefronts: per level, seeded attempts, random attempts, dedup in attempt order."""
+        torch = self.resolution._torch()
+        res = self.resolution
+        lv = self._sweep_levels()
+        sdt, dev, n = self._sdt(), res.torch_device, res.chain.n
+        Nqp = _cabi.round_up4(N)
+        bounds = lv["bounds"]
+        Lmax = int(np.diff(bounds).max())
+        cap = d["Qs"].shape[2]
+        q_raw = torch.empty((Lmax, n, 2 * Nqp), dtype=sdt, device=dev)
+        status = torch.empty((Lmax, 2 * Nqp), dtype=torch.uint8, device=dev)
+        kept = torch.empty((Lmax, n, cap), dtype=sdt, device=dev)
+        kcount = torch.empty(Lmax, dtype=torch.int32, device=dev)
+        for l in range(len(bounds) - 1):
+            a, b = int(bounds[l]), int(bounds[l + 1])
+            L = b - a
+            nodes = lv["order"][a:b]
+            status[:L].fill_(255)
+            for phase in (0, 1):
+                if phase == 0 and (not seed_from_adjacent or l == 0):
+                    continue
+                res.chain.ik_sample_level(phase, nodes, N, Nqp, d["params_s"], d["uid"], lv["lower_ptr"], lv["lower_idx"],
+                                          lv["degree"], d["Qs"], d["count"], self.seed, self.attempts, seed_from_adjacent,
+                                          q_raw[:L], status[:L], None, d["counters"])
+            _cabi.gather_node_blocks(nodes, d["Qs"], d["count"], kept[:L], kcount[:L])
+            cin = kcount[:L].clone()
+            res.chain.dedup(q_raw[:L], status[:L], DEDUP_THRESHOLD, kept[:L], kcount[:L], Nq=2 * Nqp, count_in=cin)
+            _cabi.scatter_node_blocks(nodes, kept[:L], kcount[:L], d["Qs"], d["count"])
+
     def sampleConfigurationSpace(self, NConfigsPerPoint=100, connect=True, biased=False, seedFromAdjacent=True,
-                                 visibility=False, k=None):
-        """Per workspace node: NConfigsPerPoint random-start IK attempts, greedy 1e-2 dedup against the
-        node's existing configs, then (connect=True) all-pairs edge tests on every workspace edge for the
-        pairs with at least one new endpoint.  Returns (t_sample, t_connect) in seconds (device time)."""
+                                 visibility=False, k=None, order_independent=False):
+        """solver.py:757-873.  Per workspace node NConfigsPerPoint IK attempts, greedy 1e-2 dedup against the
+        node's existing configs, then (connect=True) all-pairs edge tests on every workspace edge for the pairs
+        with at least one new endpoint.  Returns (t_sample, t_connect) in seconds (device time).
+
+        Default = the reference's sweep: numAdjacent attempts seeded from lower-numbered neighbours' configs,
+        the rest (plus failed seeded attempts) from random starts, executed as wavefronts over the dependency
+        DAG with results equal to the sequential sweep.  order_independent=True selects the semantics of the
+        reference's own data-parallel path parallelQSamplingAtP (solver.py:875-897): every attempt is a random
+        start, nodes are independent (one launch; this is what shards across GPUs)."""
         if visibility:
             raise NotImplementedError("visibility-graph solver is out of scope of the B200 roadmap path")
         torch = self.resolution._torch()
@@ -409,8 +476,13 @@ class RedundancyResolver:
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
         d["counters"].zero_()
         d["counters_e"].zero_()
+        if not order_independent:
+            self._sweep_levels()            # host-side schedule (cached), outside the timed region
         ev[0].record()
-        self._sample_phase(d, N, 0, self.Nw)
+        if order_independent:
+            self._sample_phase(d, N, 0, self.Nw)
+        else:
+            self._sample_phase_seeded(d, N, bool(seedFromAdjacent))
         ev[1].record()
         self.attempts += N
         if connect:
@@ -435,7 +507,7 @@ class RedundancyResolver:
                       "ik_evals": int(c[_cabi.CNT_IK_EVALS] + ce[_cabi.CNT_IK_EVALS]),
                       "pairs": int(ce[_cabi.CNT_PAIRS]), "valid": int(ce[_cabi.CNT_VALID]),
                       "sampled": int(d["count"].sum().item()) - start_total,
-                      "attempts": (self.Nw if n_nodes is None else n_nodes) * N, "t_sample": t_sample, "t_connect": t_connect}
+                      "attempts": int(c[_cabi.CNT_IK_SOLVES]), "t_sample": t_sample, "t_connect": t_connect}
 
     def parallelQSamplingAtP(self, params, NConfigs=100, selfmotion=True, k=None, uid=None):
         """solver.py:875-947 for one workspace point: returns (configs, qccs, qcc_parents).  Self-motion

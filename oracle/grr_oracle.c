@@ -503,6 +503,66 @@ void orc_sample_nodes(const orc_chain *c, int64_t Nw, const double *params, cons
   }
 }
 
+
+/* ------------------------------------------------------------------------------------- */
+/* S1: sampleConfigurationSpace with seedFromAdjacent (solver.py:757-835), the sequential   */
+/* Gauss-Seidel sweep over nodes in id order.  Python's unseeded `random` is replaced by   */
+/* Philox streams: seeded attempt s of node i draws (neighbour, config) from               */
+/* ctr=(uid, sample_offset+s, 0, 1): j = adj[r0 % |adj|], q = qlist_j[r1 % |qlist_j|];      */
+/* random attempts use the S2 stream (orc_random_seed).                                     */
+/* lower_ptr/lower_idx: CSR of each node's neighbours with a smaller id, in increasing id  */
+/* order; degree[i] = len(Gw.neighbors(i)).  q_kept/count are in-out (incremental growth:  */
+/* existing configs take part in the dedup; solver.py:759).  cap = slots per node.          */
+/* ------------------------------------------------------------------------------------- */
+void orc_sample_seeded(const orc_chain *c, int64_t Nw, const double *params, const int32_t *node_uid,
+                       const int32_t *lower_ptr, const int32_t *lower_idx, const int32_t *degree, int32_t Nq,
+                       uint64_t seed, int32_t sample_offset, int32_t seed_from_adjacent, double dedup_thresh,
+                       int32_t cap, double *q_kept, int32_t *count, int64_t *stats /* [4]: adj tries, adj ok, rnd tries, rnd ok */) {
+  const int n = c->n, dw = wdim(c);
+  int64_t st_adj = 0, st_adj_ok = 0, st_rnd = 0, st_rnd_ok = 0;
+  for (int64_t i = 0; i < Nw; i++) {
+    int adj[64], na = 0;
+    for (int k = lower_ptr[i]; k < lower_ptr[i + 1]; k++)
+      if (count[lower_idx[k]] > 0 && na < 64) adj[na++] = lower_idx[k];            /* solver.py:776 */
+    const double frac = degree[i] > 0 ? (double)na / (double)degree[i] : 0.0;      /* :777 */
+    const int numAdjacent = (int)(frac * Nq);                                      /* :778 */
+    const int numRandom = Nq - numAdjacent;                                        /* :779 */
+    int numFailed = 0, kept = count[i];
+    if (seed_from_adjacent) {
+      for (int s = 0; s < numAdjacent; s++) {                                      /* :794-815 */
+        uint32_t r[4];
+        philox4x32_10((uint32_t)node_uid[i], (uint32_t)(sample_offset + s), 0u, 1u, (uint32_t)seed, (uint32_t)(seed >> 32), r);
+        const int j = adj[r[0] % (uint32_t)na];
+        const int cfg = (int)(r[1] % (uint32_t)count[j]);
+        double x[ORC_MAXJ]; orc_ikinfo info;
+        memcpy(x, q_kept + ((int64_t)j * cap + cfg) * n, sizeof(double) * n);
+        orc_ik_solve(c, params + i * dw, x, &info);
+        st_adj++;
+        if (info.status != ORC_OK) { numFailed++; continue; }
+        st_adj_ok++;
+        int same = 0;
+        for (int k = 0; k < kept; k++)
+          if (orc_distance(c, x, q_kept + (i * cap + k) * n) < dedup_thresh) { same = 1; break; }
+        if (!same && kept < cap) { memcpy(q_kept + (i * cap + kept) * n, x, sizeof(double) * n); kept++; }
+      }
+    }
+    for (int s = 0; s < numRandom + numFailed; s++) {                              /* :817-835 */
+      double x[ORC_MAXJ]; orc_ikinfo info;
+      orc_random_seed(c, seed, (uint32_t)node_uid[i], (uint32_t)(sample_offset + s), x);
+      orc_ik_solve(c, params + i * dw, x, &info);
+      st_rnd++;
+      if (info.status != ORC_OK) continue;
+      st_rnd_ok++;
+      int same = 0;
+      for (int k = 0; k < kept; k++)
+        if (orc_distance(c, x, q_kept + (i * cap + k) * n) < dedup_thresh) { same = 1; break; }
+      if (!same && kept < cap) { memcpy(q_kept + (i * cap + kept) * n, x, sizeof(double) * n); kept++; }
+    }
+    count[i] = kept;
+  }
+  if (stats) { stats[0] = st_adj; stats[1] = st_adj_ok; stats[2] = st_rnd; stats[3] = st_rnd_ok; }
+}
+
 /* ------------------------------------------------------------------------------------- */
 /* V4: workspaceInterpolate (graph.py:768-777 -> IKTask.interpolate :143-164)              */
 /* ------------------------------------------------------------------------------------- */

@@ -157,6 +157,22 @@ class Oracle:
         return {"q_raw": q_raw, "status": st, "iters": it, "evals": ev, "q_kept": q_kept, "keep_idx": keep_idx,
                 "count": count}
 
+    def sample_seeded(self, params, node_uid, lower_ptr, lower_idx, degree, Nq, seed, cap=None, sample_offset=0,
+                      seed_from_adjacent=True, dedup=1e-2, q_kept=None, count=None):
+        """solver.py:757-835 sequential sweep.  Returns dict(q_kept [Nw][cap][n], count [Nw], stats [4])."""
+        params, node_uid = f64(params), i32(node_uid)
+        Nw = params.shape[0]
+        cap = int(cap or Nq)
+        q_kept = np.zeros((Nw, cap, self.n)) if q_kept is None else f64(q_kept).copy()
+        count = np.zeros(Nw, dtype=np.int32) if count is None else i32(count).copy()
+        stats = np.zeros(4, dtype=np.int64)
+        lp, li, dg = i32(lower_ptr), i32(lower_idx), i32(degree)
+        self.L.orc_sample_seeded(self.ref, C.c_int64(Nw), _p(params), _p(node_uid, C.c_int32), _p(lp, C.c_int32),
+                                 _p(li, C.c_int32), _p(dg, C.c_int32), C.c_int32(Nq), C.c_uint64(seed),
+                                 C.c_int32(sample_offset), C.c_int32(1 if seed_from_adjacent else 0), C.c_double(dedup),
+                                 C.c_int32(cap), _p(q_kept), _p(count, C.c_int32), _p(stats, C.c_int64))
+        return {"q_kept": q_kept, "count": count, "stats": stats}
+
     def workspace_interpolate(self, wa, wb, u):
         w = np.zeros(self.dw)
         self.L.orc_workspace_interpolate(self.ref, _p(f64(wa)), _p(f64(wb)), C.c_double(u), _p(w))

@@ -115,7 +115,7 @@ def test_roadmap_build_matches_oracle(built, case, dtype):
     """End to end through RedundancyResolver: sampling (FP64) + dedup + all-pairs edge construction."""
     pdef, res = small_problem(*CASES[case], dtype=dtype)
     rr = grr.RedundancyResolver(res, seed=SEED)
-    rr.sampleConfigurationSpace(NQ)
+    rr.sampleConfigurationSpace(NQ, order_independent=True)
     o = oracle_for(res)
     ref = o.sample_nodes(res.ws_params, rr.node_uid, NQ, seed=SEED)
     cnt = rr.counts()
@@ -165,7 +165,7 @@ def test_variable_orientation_roadmap(built):
     res.setWorkspaceGraph(np.asarray(nodes), np.asarray(edges))
     NQv = 600
     rr = grr.RedundancyResolver(res, seed=SEED)
-    rr.sampleConfigurationSpace(NQv)
+    rr.sampleConfigurationSpace(NQv, order_independent=True)
     ref = o.sample_nodes(res.ws_params, rr.node_uid, NQv, seed=SEED)
     cnt = rr.counts()
     np.testing.assert_array_equal(cnt, ref["count"])
@@ -213,11 +213,11 @@ def test_incremental_growth_matches_single_shot_rules(built):
     (start_node_counts, solver.py:759,850; skip rule :694); verdicts of old pairs are preserved."""
     pdef, res = small_problem("planar_3R", "baseline_cfg1.json", 100, "grid")
     rr = grr.RedundancyResolver(res, seed=SEED)
-    rr.sampleConfigurationSpace(6)
+    rr.sampleConfigurationSpace(6, order_independent=True)
     c1 = rr.counts().copy()
     m1 = unpack_mask(rr._dev["mask"].cpu().numpy(), rr.Nq)
     p1 = rr.stats["pairs"]
-    rr.sampleConfigurationSpace(6)
+    rr.sampleConfigurationSpace(6, order_independent=True)
     c2 = rr.counts()
     assert (c2 >= c1).all() and c2.sum() > c1.sum()
     m2 = unpack_mask(rr._dev["mask"].cpu().numpy(), rr.Nq)
@@ -245,7 +245,7 @@ def test_container_api_and_views(built):
     (solver.py:429-501,689-697)."""
     pdef, res = small_problem("planar_3R", "baseline_cfg1.json", 100, "grid")
     rr = grr.RedundancyResolver(res, seed=SEED)
-    rr.sampleConfigurationSpace(8, connect=False)
+    rr.sampleConfigurationSpace(8, connect=False, order_independent=True)
     assert rr.numCSpaceEdges() == 0
     cnt = rr.counts()
     assert rr.numConfigurations() == int(cnt.sum())
@@ -291,7 +291,7 @@ def test_full_size_properties_cfg1(built):
     its node's IK problem inside the joint box; kept configs pairwise >= 1e-2 apart; validEdge is
     symmetric under swapping the endpoints with the workspace edge; rebuild is idempotent."""
     pdef, res, rr = grr.make_program("planar_3R", "baseline_cfg1.json", seed=1)
-    rr.sampleConfigurationSpace(pdef["Nq"])
+    rr.sampleConfigurationSpace(pdef["Nq"], order_independent=True)
     cnt = rr.counts()
     assert rr.Nw == 1024 and rr.E == 1984 and cnt.max() <= pdef["Nq"]
     Q = rr._dev["Qs"]
@@ -313,3 +313,58 @@ def test_full_size_properties_cfg1(built):
     m1 = rr._dev["mask"].clone()
     rr.connectConfigurationSpace()
     assert torch.equal(m1, rr._dev["mask"])
+
+
+def _lower_csr(res):
+    e = res.ws_edges
+    Nw = res.ws_params.shape[0]
+    order = np.lexsort((e[:, 0], e[:, 1]))
+    lower_idx = e[order, 0].astype(np.int32)
+    cnt_lower = np.bincount(e[:, 1], minlength=Nw)
+    lower_ptr = np.concatenate([[0], np.cumsum(cnt_lower)]).astype(np.int32)
+    degree = (np.bincount(e[:, 0], minlength=Nw) + cnt_lower).astype(np.int32)
+    return lower_ptr, lower_idx, degree
+
+
+@pytest.mark.parametrize("case", ["planar_3R_free", "planar_20R_free", "jaco_free", "baxter_fixed"])
+@pytest.mark.parametrize("seed_adj", [True, False])
+def test_seeded_sweep_equals_sequential_oracle(built, case, seed_adj):
+    """sampleConfigurationSpace's default path (solver.py:757-835): the GPU runs the Gauss-Seidel sweep as
+    wavefronts over the 'lower-numbered neighbour' DAG; the oracle runs it sequentially in node order.  Same
+    Philox draws => same roadmap (FP64 sampling: joint values within 1e-8, identical counts)."""
+    pdef, res = small_problem(*CASES[case], dtype="float32")
+    rr = grr.RedundancyResolver(res, seed=SEED)
+    rr.sampleConfigurationSpace(NQ, connect=False, seedFromAdjacent=seed_adj)
+    o = oracle_for(res)
+    lp, li, dg = _lower_csr(res)
+    ref = o.sample_seeded(res.ws_params, rr.node_uid, lp, li, dg, NQ, seed=SEED, seed_from_adjacent=seed_adj)
+    cnt = rr.counts()
+    np.testing.assert_array_equal(cnt, ref["count"])
+    Qs = np.transpose(rr._dev["Qs"][:, :, :NQ].double().cpu().numpy(), (0, 2, 1))
+    worst = max((np.abs(Qs[i, :cnt[i]] - ref["q_kept"][i, :cnt[i]]).max() for i in range(rr.Nw) if cnt[i]), default=0.0)
+    assert worst < 1e-8
+    st = ref["stats"]
+    assert rr.stats["sample_ik_solves"] == st[0] + st[2]
+    assert rr.stats["sample_ik_ok"] == st[1] + st[3]
+    if seed_adj:
+        assert st[0] > 0 and st[1] / st[0] > st[3] / max(st[2], 1)   # seeded attempts succeed more often than random ones
+    # second call grows the roadmap incrementally, still equal to the oracle's second sweep
+    rr.sampleConfigurationSpace(NQ, connect=False, seedFromAdjacent=seed_adj)
+    ref2 = o.sample_seeded(res.ws_params, rr.node_uid, lp, li, dg, NQ, seed=SEED, cap=2 * NQ, sample_offset=NQ,
+                           seed_from_adjacent=seed_adj,
+                           q_kept=np.concatenate([ref["q_kept"], np.zeros_like(ref["q_kept"])], axis=1), count=ref["count"])
+    np.testing.assert_array_equal(rr.counts(), ref2["count"])
+
+
+def test_seeded_sweep_rescues_6d_problems(built):
+    """Random starts converge on ~1 % of attempts for a 7-DOF arm with a 6-D task; seeding from neighbours is
+    what makes such roadmaps non-empty in the reference.  Fixed-orientation Baxter-like arm, small grid."""
+    pdef, res = small_problem("baxter", "Rdown.json", 400, "staggered_grid", dtype="float32")
+    rr_s = grr.RedundancyResolver(res, seed=SEED)
+    rr_s.sampleConfigurationSpace(40, connect=True)
+    rr_r = grr.RedundancyResolver(res, seed=SEED)
+    rr_r.sampleConfigurationSpace(40, connect=True, order_independent=True)
+    ns, nr = rr_s.numConfigurations(), rr_r.numConfigurations()
+    print("\n[6-D seeded vs random] configs %d vs %d, C-space edges %d vs %d" % (ns, nr, rr_s.numCSpaceEdges(), rr_r.numCSpaceEdges()))
+    assert ns > nr
+    rr_s.sanityCheck()

@@ -12,13 +12,13 @@ name, jf, Nw, Nq = "planar_20R", "baseline_cfg2.json", 600, 24
 pdef, res = grr.load_problem(name, jf, overrides={"Nw": Nw}, device=local)
 res.sampleWorkspace(Nw, method=pdef["workspace_graph"])
 sr = sharding.ShardedResolver(res, rank, world, seed=3)
-ts, tc = sr.sampleConfigurationSpace(Nq)
+ts, tc = sr.sampleConfigurationSpace(Nq, order_independent=True)
 full = sr.gather_masks()
 cnt = sr._dev["count"].clone()
 pairs = torch.tensor([float(sr.stats["pairs"])], device="cuda"); dist.all_reduce(pairs)
 if rank == 0:
     rr = grr.RedundancyResolver(res, seed=3)
-    rr.sampleConfigurationSpace(Nq)
+    rr.sampleConfigurationSpace(Nq, order_independent=True)
     assert torch.equal(cnt, rr._dev["count"]), "counts differ"
     assert torch.equal(full, rr._dev["mask"]), "edge masks differ"
     lo, hi = sr.nbounds[0], sr.nbounds[1]

@@ -22,7 +22,7 @@ for name, jf, Nw, method, over in CASES:
         res.sampleWorkspace(pdef["Nw"], method=pdef["workspace_graph"])
         rr = grr.RedundancyResolver(res, seed=5)
         t0 = time.time()
-        ts, tc = rr.sampleConfigurationSpace(Nq)
+        ts, tc = rr.sampleConfigurationSpace(Nq, order_independent=True)
         wall = time.time() - t0
         o = oracle_for(res)
         t0 = time.time()

@@ -10,7 +10,7 @@ pdef, res, rr = grr.make_program(name, jf, overrides=over)
 for rep in range(2):
     rr.initWorkspaceGraph()
     t0 = time.time()
-    ts, tc = rr.sampleConfigurationSpace(pdef["Nq"])
+    ts, tc = rr.sampleConfigurationSpace(pdef["Nq"], order_independent=True)
     wall = time.time() - t0
     s = rr.stats
     print(json.dumps({"cfg": name + "/" + jf, "Nw": rr.Nw, "E": rr.E, "Nq": pdef["Nq"], "t_sample": ts, "t_connect": tc, "wall": wall,
