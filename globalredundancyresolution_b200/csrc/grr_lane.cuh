@@ -30,6 +30,8 @@ namespace grr {
 // ---- fast scalar helpers (float: MUFU based; double: exact) ---------------------------------
 __device__ __forceinline__ float fdiv_(float a, float b) { return __fdividef(a, b); }
 __device__ __forceinline__ double fdiv_(double a, double b) { return a / b; }
+__device__ __forceinline__ float rcp_ge1_(float a) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a)); return r; }  // a >= 1
+__device__ __forceinline__ double rcp_ge1_(double a) { return 1.0 / a; }
 __device__ __forceinline__ float rsqrt_(float a) { return rsqrtf(a); }
 __device__ __forceinline__ double rsqrt_(double a) { return 1.0 / sqrt(a); }
 
@@ -459,7 +461,7 @@ __device__ __forceinline__ int lane_step(const ChainT &c, LaneIK<Real, M> &L, La
       for (int j = 0; j < n; j++) {
         const Real xj = *px, xo = *po;
         px += T; po += T;
-        const Real rinv = fdiv_(Real(1), max_(abs_(xj), Real(1)));
+        const Real rinv = rcp_ge1_(max_(abs_(xj), Real(1)));
         testx = max_(testx, abs_(xj - xo) * rinv);
         Real pj = 0, gj = 0;
 #pragma unroll
