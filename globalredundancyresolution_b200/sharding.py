@@ -15,6 +15,8 @@ qlists over OS pipes per task (grr/solver.py:2232-2400).  Here:
                 window; in the node-blocked layout Q[node][dof][Nqp] a node range is ONE contiguous
                 slab, so the exchange is one send/recv per overlapping (owner, user) pair with no
                 pack/unpack kernel (batched isend/irecv -> ncclSend/ncclRecv groups over NVLink);
+  3b. chunks    each rank owns several (default 4) contiguous chunks spread over the grid (chunk c -> rank
+                c % world) rather than one range, so regional bias of the work estimate averages out;
   4b. rebalance the work of a pair is its Ndivs (interpolated solves), which varies across the workspace
                 (measured: a 50/50 split by pair count was 58/42 by flops).  Each rank computes the exact
                 work estimate sum(Ndivs+1) of the edges of its preliminary range (grr_edges_cost, ~1 ms),
@@ -86,30 +88,55 @@ def node_window(edges, e0, e1):
     return int(sub.min()), int(sub.max()) + 1
 
 
+def rank_chunks(bounds, world, chunks_per_rank):
+    """Chunk c of the world*chunks_per_rank contiguous chunks goes to rank c % world: every rank gets
+    `chunks_per_rank` slices spread over the whole grid, so regional errors of the work estimate average out.
+    Returns per rank the list of (e0, e1)."""
+    out = [[] for _ in range(world)]
+    for c in range(world * chunks_per_rank):
+        out[c % world].append((int(bounds[c]), int(bounds[c + 1])))
+    return out
+
+
 def halo_plan(nbounds, windows):
-    """For every (owner p, user r) pair with p != r, the node slab [a,b) that p must send to r:
-    the overlap of r's node window with p's owned range.  Returns {(p, r): (a, b)}."""
+    """windows[r] = list of node windows rank r needs.  For every (owner p, user r) pair with p != r, the node
+    slabs [a,b) that p must send to r: the overlaps of r's windows with p's owned range, merged.
+    Returns {(p, r): [(a, b), ...]}."""
     plan = {}
     world = len(windows)
-    for r, (lo, hi) in enumerate(windows):
+    for r, wins in enumerate(windows):
+        if isinstance(wins, tuple):
+            wins = [wins]
         for p in range(world):
             if p == r:
                 continue
-            a, b = max(lo, nbounds[p]), min(hi, nbounds[p + 1])
-            if b > a:
-                plan[(p, r)] = (a, b)
+            segs = []
+            for (lo, hi) in wins:
+                a, b = max(lo, nbounds[p]), min(hi, nbounds[p + 1])
+                if b > a:
+                    segs.append((a, b))
+            segs.sort()
+            merged = []
+            for a, b in segs:
+                if merged and a <= merged[-1][1]:
+                    merged[-1] = (merged[-1][0], max(merged[-1][1], b))
+                else:
+                    merged.append((a, b))
+            if merged:
+                plan[(p, r)] = merged
     return plan
 
 
 def exchange_halo(Q, rank, plan, dist):
-    """Execute the halo plan on the node-blocked tensor Q (any device / backend)."""
+    """Execute the halo plan on the node-blocked tensor Q (any device / backend): one isend/irecv per slab."""
     ops, nbytes = [], 0
-    for (p, r), (a, b) in sorted(plan.items()):
-        if p == rank:
-            ops.append(dist.P2POp(dist.isend, Q[a:b], r))
-        elif r == rank:
-            ops.append(dist.P2POp(dist.irecv, Q[a:b], p))
-            nbytes += Q[a:b].numel() * Q.element_size()
+    for (p, r), segs in sorted(plan.items()):
+        for (a, b) in segs:
+            if p == rank:
+                ops.append(dist.P2POp(dist.isend, Q[a:b], r))
+            elif r == rank:
+                ops.append(dist.P2POp(dist.irecv, Q[a:b], p))
+                nbytes += Q[a:b].numel() * Q.element_size()
     if ops:
         for w in dist.batch_isend_irecv(ops):
             w.wait()
@@ -119,12 +146,14 @@ def exchange_halo(Q, rank, plan, dist):
 class ShardedResolver(RedundancyResolver):
     """RedundancyResolver over `world` ranks.  Every rank keeps full-size node arrays (config 5 is
     0.56 GB in FP32) but fills only its node window, and holds the bitmasks of its own edge range
-    (`edge_lo`, `edge_hi`).  `gather_masks()` assembles the full roadmap on rank 0."""
+    chunks (`edge_ids`: global ids of the local mask rows).  `gather_masks()` assembles the full roadmap."""
 
-    def __init__(self, resolution, rank, world, seed=0, sample_dtype="float64", rebalance=True):
+    def __init__(self, resolution, rank, world, seed=0, sample_dtype="float64", rebalance=True, chunks_per_rank=4):
         self.rank, self.world = int(rank), int(world)
+        self._local_of = {}
         self.rebalance = bool(rebalance)
-        self.edge_lo, self.edge_hi = 0, 0
+        self.chunks_per_rank = int(chunks_per_rank)
+        self.edge_ids = np.zeros(0, dtype=np.int64)
         self.halo_bytes = 0
         RedundancyResolver.__init__(self, resolution, seed=seed, sample_dtype=sample_dtype)
         self.nbounds = node_ranges(self.Nw, self.world)
@@ -132,7 +161,8 @@ class ShardedResolver(RedundancyResolver):
     def initWorkspaceGraph(self, clear=False, drop_device=False):
         RedundancyResolver.initWorkspaceGraph(self, clear, drop_device)
         self.nbounds = node_ranges(self.Nw, getattr(self, "world", 1))
-        self.edge_lo, self.edge_hi = 0, 0
+        self.edge_ids = np.zeros(0, dtype=np.int64)
+        self._local_of = {}
 
     def _alloc_mask(self, Nq, W):
         # bitmasks only for the edge range this rank can own at most (allocated lazily per plan)
@@ -164,35 +194,39 @@ class ShardedResolver(RedundancyResolver):
         ev[1].record()
         self.attempts += N
         if connect:
+            K = self.chunks_per_rank
             cnt = d["count"].cpu().numpy()
-            eb = edge_ranges(res.ws_edges, cnt, self.world)
-            windows = [node_window(res.ws_edges, eb[r], eb[r + 1]) for r in range(self.world)]
-            plan = halo_plan(self.nbounds, windows)
-            self.halo_bytes = exchange_halo(d["Qs"], self.rank, plan, dist)
+            eb = edge_ranges(res.ws_edges, cnt, self.world * K)                       # preliminary: by pair count
+            chunks = rank_chunks(eb, self.world, K)
+            windows = [[node_window(res.ws_edges, a, b) for (a, b) in chunks[r]] for r in range(self.world)]
+            self.halo_bytes = exchange_halo(d["Qs"], self.rank, halo_plan(self.nbounds, windows), dist)
             if self.rebalance and self.world > 1:
-                # 4b: exact work estimate on the preliminary range, then re-cut by cost
-                e0, e1 = eb[self.rank], eb[self.rank + 1]
-                wl, wh = windows[self.rank]
+                # 4b: exact work estimate on the preliminary chunks, then re-cut by cost
                 if d["Qs"] is not d["Q"]:
-                    d["Q"][wl:wh].copy_(d["Qs"][wl:wh])
+                    for (wl, wh) in windows[self.rank]:
+                        d["Q"][wl:wh].copy_(d["Qs"][wl:wh])
                 cost = torch.zeros(self.E, dtype=torch.int64, device=res.torch_device)
-                if e1 > e0:
-                    res.chain.edges_cost(d["wedges"][e0:e1], d["Q"], d["count"], 0.05, cost[e0:e1])
+                for (a, b) in chunks[self.rank]:
+                    if b > a:
+                        res.chain.edges_cost(d["wedges"][a:b], d["Q"], d["count"], 0.05, cost[a:b])
                 dist.all_reduce(cost)
-                eb = ranges_by_cost(cost.cpu().numpy(), self.world)
-                windows = [node_window(res.ws_edges, eb[r], eb[r + 1]) for r in range(self.world)]
-                plan = halo_plan(self.nbounds, windows)
-                self.halo_bytes += exchange_halo(d["Qs"], self.rank, plan, dist)
-            e0, e1 = eb[self.rank], eb[self.rank + 1]
-            self.edge_lo, self.edge_hi = e0, e1
+                eb = ranges_by_cost(cost.cpu().numpy(), self.world * K)
+                chunks = rank_chunks(eb, self.world, K)
+                windows = [[node_window(res.ws_edges, a, b) for (a, b) in chunks[r]] for r in range(self.world)]
+                self.halo_bytes += exchange_halo(d["Qs"], self.rank, halo_plan(self.nbounds, windows), dist)
+            mine = chunks[self.rank]
+            self.edge_ids = np.concatenate([np.arange(a, b, dtype=np.int64) for (a, b) in mine]) if mine else np.zeros(0, dtype=np.int64)
+            self._local_of = {int(e): k for k, e in enumerate(self.edge_ids.tolist())}
+            ne = int(self.edge_ids.shape[0])
             W = (self.Nq + 31) // 32
-            d["mask"] = torch.zeros((e1 - e0, self.Nq, W), dtype=torch.int32, device=res.torch_device)
-            d["edge_stats"] = torch.zeros((e1 - e0, 2), dtype=torch.int32, device=res.torch_device)
+            d["mask"] = torch.zeros((ne, self.Nq, W), dtype=torch.int32, device=res.torch_device)
+            d["edge_stats"] = torch.zeros((ne, 2), dtype=torch.int32, device=res.torch_device)
             if d["Qs"] is not d["Q"]:
-                wl, wh = windows[self.rank]
-                d["Q"][wl:wh].copy_(d["Qs"][wl:wh])
-            if e1 > e0:
-                res.chain.edges_build(d["wedges"][e0:e1], d["params"], d["Q"], d["count"], self.Nq,
+                for (wl, wh) in windows[self.rank]:
+                    d["Q"][wl:wh].copy_(d["Qs"][wl:wh])
+            if ne:
+                my_wedges = torch.cat([d["wedges"][a:b] for (a, b) in mine if b > a]).contiguous()
+                res.chain.edges_build(my_wedges, d["params"], d["Q"], d["count"], self.Nq,
                                       0.05, d["mask"], d["edge_stats"], d["counters_e"])
         ev[2].record()
         torch.cuda.synchronize(res.torch_device)
@@ -203,10 +237,10 @@ class ShardedResolver(RedundancyResolver):
         return self.stats["t_sample"], self.stats["t_connect"]
 
     def _edge_qlist(self, e):
-        if not (self.edge_lo <= e < self.edge_hi):
+        if e not in self._local_of:
             raise KeyError("workspace edge %d is owned by another rank" % e)
         if e not in self._ecache:
-            m = self._dev["mask"][e - self.edge_lo].cpu().numpy().view(np.uint32)
+            m = self._dev["mask"][self._local_of[e]].cpu().numpy().view(np.uint32)
             bits = np.unpackbits(m.view(np.uint8).reshape(m.shape[0], -1), axis=1, bitorder="little")
             iq, jq = np.nonzero(bits)
             self._ecache[e] = set(zip(iq.tolist(), jq.tolist()))
@@ -233,6 +267,7 @@ class ShardedResolver(RedundancyResolver):
         torch = self.resolution._torch()
         W = (self.Nq + 31) // 32
         full = torch.zeros((self.E, self.Nq, W), dtype=torch.int32, device=self.resolution.torch_device)
-        full[self.edge_lo:self.edge_hi] = self._dev["mask"]
+        if self.edge_ids.shape[0]:
+            full[torch.as_tensor(self.edge_ids, device=full.device)] = self._dev["mask"]
         dist.all_reduce(full)
         return full

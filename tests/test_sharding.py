@@ -34,17 +34,23 @@ def test_partition_properties(world):
     assert sum(per) == load.sum()
     if world > 1:
         assert max(per) <= load.sum() / world + load.max() + 1                          # balanced by pair tests
-    windows = [sharding.node_window(edges, eb[r], eb[r + 1]) for r in range(world)]
-    plan = sharding.halo_plan(nb, windows)
-    for r in range(world):
-        need = np.unique(edges[eb[r]:eb[r + 1]])
-        have = np.zeros(Nw, dtype=bool)
-        have[nb[r]:nb[r + 1]] = True
-        for (p, rr), (a, b) in plan.items():
-            assert p != rr and nb[p] <= a < b <= nb[p + 1]                              # sender owns the slab
-            if rr == r:
-                have[a:b] = True
-        assert have[need].all()
+    for K in (1, 4):
+        ebk = sharding.edge_ranges(edges, count, world * K)
+        chunks = sharding.rank_chunks(ebk, world, K)
+        assert sorted(c for ch in chunks for c in ch) == [(ebk[i], ebk[i + 1]) for i in range(world * K)]
+        windows = [[sharding.node_window(edges, a, b) for (a, b) in chunks[r]] for r in range(world)]
+        plan = sharding.halo_plan(nb, windows)
+        for r in range(world):
+            need = np.unique(np.concatenate([edges[a:b].reshape(-1) for (a, b) in chunks[r]] + [np.zeros(0, dtype=edges.dtype)]))
+            have = np.zeros(Nw, dtype=bool)
+            have[nb[r]:nb[r + 1]] = True
+            for (p, rr), segs in plan.items():
+                assert p != rr
+                for (a, b) in segs:
+                    assert nb[p] <= a < b <= nb[p + 1]                                  # sender owns the slab
+                    if rr == r:
+                        have[a:b] = True
+            assert have[need.astype(np.int64)].all()
     own = sharding.owner_of(np.arange(Nw), nb)
     assert all(nb[o] <= i < nb[o + 1] for i, o in enumerate(own))
     # cost-based re-cut (step 4b): contiguous, covering, balanced within one edge's cost
@@ -75,19 +81,22 @@ def _worker(rank, world, port, ok):
         cnt[lo:hi] = torch.from_numpy(count[lo:hi])
         dist.all_reduce(cnt)
         assert (cnt.numpy() == count).all()
-        eb = sharding.edge_ranges(edges, cnt.numpy(), world)
-        windows = [sharding.node_window(edges, eb[r], eb[r + 1]) for r in range(world)]
+        K = 3
+        eb = sharding.edge_ranges(edges, cnt.numpy(), world * K)
+        chunks = sharding.rank_chunks(eb, world, K)
+        windows = [[sharding.node_window(edges, a, b) for (a, b) in chunks[r]] for r in range(world)]
         plan = sharding.halo_plan(nb, windows)
         nbytes = sharding.exchange_halo(Q, rank, plan, dist)
-        need = np.unique(edges[eb[rank]:eb[rank + 1]])
+        need = np.unique(np.concatenate([edges[a:b].reshape(-1) for (a, b) in chunks[rank]]))
         expect = (torch.from_numpy(need).float()[:, None, None] + 0.001 * torch.arange(n)[None, :, None]
                   + 1e-5 * torch.arange(Nqp)[None, None, :])
         assert torch.equal(Q[need], expect), "rank %d misses halo blocks" % rank
-        expected_bytes = sum((b - a) for (p, r), (a, b) in plan.items() if r == rank) * n * Nqp * 4
+        expected_bytes = sum((b - a) for (p, r), segs in plan.items() if r == rank for (a, b) in segs) * n * Nqp * 4
         assert nbytes == expected_bytes
         # every edge is built exactly once across ranks
         mine = torch.zeros(edges.shape[0], dtype=torch.int32)
-        mine[eb[rank]:eb[rank + 1]] = 1
+        for (a, b) in chunks[rank]:
+            mine[a:b] = 1
         dist.all_reduce(mine)
         assert (mine == 1).all()
         ok[rank] = 1

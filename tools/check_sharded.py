@@ -24,6 +24,6 @@ if rank == 0:
     lo, hi = sr.nbounds[0], sr.nbounds[1]
     assert torch.equal(sr._dev["Qs"][lo:hi], rr._dev["Qs"][lo:hi])
     assert int(pairs.item()) == rr.stats["pairs"], (pairs.item(), rr.stats["pairs"])
-    print("sharded == single GPU: world=%d nodes=%d edges=%d pairs=%d halo_bytes(rank0)=%d" % (world, sr.Nw, sr.E, rr.stats["pairs"], sr.halo_bytes))
+    print("sharded == single GPU: world=%d nodes=%d edges=%d pairs=%d halo_bytes(rank0)=%d chunks=%d" % (world, sr.Nw, sr.E, rr.stats["pairs"], sr.halo_bytes, sr.chunks_per_rank))
 dist.barrier()
 dist.destroy_process_group()
