@@ -205,7 +205,7 @@ static const unsigned kWorkRing = 64;
 // next work counter of the handle's ring (allocated on first use, on the handle's device)
 static unsigned long long *work_slot(grr_handle_s *h) {
   if (!h->d_work) {
-    if (cudaMalloc(&h->d_work, sizeof(unsigned long long) * kWorkRing) != cudaSuccess) {
+    if (cudaMalloc(&h->d_work, sizeof(unsigned long long) * (kWorkRing + 2)) != cudaSuccess) {
       set_error("cudaMalloc(work counters) failed: %s", cudaGetErrorString(cudaGetLastError()));
       return nullptr;
     }
@@ -359,7 +359,10 @@ int grr_edges_build(grr_handle_t h, int dtype, int64_t E, const int32_t *wedges,
   if (!ops) { set_error("bad dtype %d", dtype); return -1; }
   if (E < 0 || Nq < 1 || Nqp < Nq) { set_error("grr_edges_build: bad sizes"); return -1; }
   if (E > 0 && (!wedges || !params || !q_kept || !count || !mask)) { set_error("grr_edges_build: null buffer"); return -1; }
-  return ops->edges_build(h->hc, E, wedges, params, q_kept, count, old_count, Nq, Nqp, epsilon, mask, edge_stats,
+  if (E == 0) return 0;
+  unsigned long long *work = work_slot(h);
+  if (!work) return -3;
+  return ops->edges_build(h->hc, E, wedges, params, q_kept, count, old_count, Nq, Nqp, epsilon, mask, edge_stats, work,
                           (unsigned long long *)counters, (cudaStream_t)stream);
 }
 

@@ -453,6 +453,21 @@ k_edges_build(const __grid_constant__ ChainDev<Real, kMaxJ> c, const int32_t *__
   }
 }
 
+// pair-test load of an edge list: out[0] += pairs that will be tested, out[1] += edges with at least one
+static __global__ void k_edge_load(long long E, const int32_t *__restrict__ wedges, const int32_t *__restrict__ count,
+                            const int32_t *__restrict__ old_count, unsigned long long *out) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned long long p = 0;
+  if (e < E) {
+    const int iw = wedges[2 * e], jw = wedges[2 * e + 1];
+    p = (unsigned long long)count[iw] * (unsigned long long)count[jw];
+    if (old_count) p -= (unsigned long long)old_count[iw] * (unsigned long long)old_count[jw];
+  }
+  unsigned nz = __ballot_sync(0xffffffffu, p != 0);
+  for (int o = 16; o > 0; o >>= 1) p += __shfl_down_sync(0xffffffffu, p, o);
+  if ((threadIdx.x & 31) == 0 && p) { atomicAdd(out, p); atomicAdd(out + 1, (unsigned long long)__popc(nz)); }
+}
+
 // ------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------
@@ -611,7 +626,8 @@ struct Impl {
   }
   static int edges_build(const HostChain &h, long long E, const int32_t *wedges, const void *params, const void *q_kept,
                          const int32_t *count, const int32_t *old_count, int Nq, int Nqp, double epsilon,
-                         uint32_t *mask, uint32_t *edge_stats, unsigned long long *counters, cudaStream_t st) {
+                         uint32_t *mask, uint32_t *edge_stats, unsigned long long *work, unsigned long long *counters,
+                         cudaStream_t st) {
     if (E <= 0) return 0;
     Chain c; fill_chain(h, c);
     const int Wd = (Nq + 31) / 32;
@@ -619,6 +635,21 @@ struct Impl {
     int threads, per_sm;
     lane_geometry(h, fixed, sizeof(Real) == 4 ? 512 : 256, threads, per_sm);
     if (threads < 32) { set_error("edges_build: Nq=%d, n=%d does not fit shared memory", Nq, h.n); return -2; }
+    // CTA size follows the work per workspace edge: a CTA owns one edge, so lanes beyond pairs/~6 would idle
+    // for the whole edge (sparse roadmaps: a few configs per node).  One tiny reduction + an 16-byte readback.
+    {
+      unsigned long long hload[2] = {0, 0};
+      cudaMemsetAsync(work, 0, 2 * sizeof(unsigned long long), st);
+      k_edge_load<<<(unsigned)((E + 255) / 256), 256, 0, st>>>(E, wedges, count, old_count, work);
+      cudaMemcpyAsync(hload, work, sizeof hload, cudaMemcpyDeviceToHost, st);
+      cudaStreamSynchronize(st);
+      if (hload[1] > 0) {
+        const double avg = (double)hload[0] / (double)hload[1];
+        int want = (int)((avg / 6.0 + 31.0) / 32.0) * 32;
+        if (want < 32) want = 32;
+        if (want < threads) threads = want;
+      }
+    }
     const size_t smem = fixed + (size_t)threads * h.n * (4 + mc(h)) * sizeof(Real);
     auto launch = [&](auto kern) -> int {
       if (set_smem(kern, smem, "k_edges_build")) return -2;
