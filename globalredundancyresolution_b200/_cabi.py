@@ -25,7 +25,7 @@ EXPORTS = [
     "grr_last_error", "grr_abi_version", "grr_chain_create", "grr_chain_destroy", "grr_task_set",
     "grr_chain_num_joints", "grr_fk_batch", "grr_ik_solve_batch", "grr_ik_sample", "grr_ik_sample_level", "grr_dedup",
     "grr_edges_build", "grr_edges_cost", "grr_edges_compact", "grr_valid_edge_batch", "grr_gather_node_blocks",
-    "grr_scatter_node_blocks", "grr_fp32_peak",
+    "grr_scatter_node_blocks", "grr_fp32_peak", "grr_fp32x2_peak",
 ]
 
 
@@ -78,6 +78,7 @@ def lib():
     L.grr_gather_node_blocks.argtypes = [C.c_int, i64, vp, i32, i32, vp, vp, vp, vp, vp]
     L.grr_scatter_node_blocks.argtypes = [C.c_int, i64, vp, i32, i32, vp, vp, vp, vp, vp]
     L.grr_fp32_peak.argtypes = [C.c_int, C.POINTER(C.c_double)]
+    L.grr_fp32x2_peak.argtypes = [C.c_int, C.POINTER(C.c_double)]
     for name in EXPORTS:
         if name not in ("grr_last_error",):
             getattr(L, name).restype = C.c_int
@@ -87,7 +88,7 @@ def lib():
 
 def check(rc, what):
     global LAUNCHES
-    if what not in ("grr_chain_create", "grr_task_set", "grr_fp32_peak"):
+    if what not in ("grr_chain_create", "grr_task_set", "grr_fp32_peak", "grr_fp32x2_peak"):
         LAUNCHES += 1
     if rc != 0:
         raise GrrError("%s failed (%d): %s" % (what, rc, lib().grr_last_error().decode()))
@@ -259,4 +260,10 @@ def scatter_node_blocks(idx, packed, packed_count, q, count):
 def fp32_peak(device=0):
     out = C.c_double(0.0)
     check(lib().grr_fp32_peak(int(device), C.byref(out)), "grr_fp32_peak")
+    return out.value
+
+
+def fp32x2_peak(device=0):
+    out = C.c_double(0.0)
+    check(lib().grr_fp32x2_peak(int(device), C.byref(out)), "grr_fp32x2_peak")
     return out.value

@@ -184,6 +184,24 @@ __global__ void __launch_bounds__(256) k_fma_peak(float *out, int iters, float a
   out[blockIdx.x * blockDim.x + threadIdx.x] = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
 }
 
+// packed variant: sm_100 FFMA2 (two FP32 FMAs per instruction per lane)
+__global__ void __launch_bounds__(256) k_fma2_peak(float *out, int iters, float a, float b) {
+  float2 x0 = make_float2(threadIdx.x, threadIdx.x + 1.f), x1 = make_float2(x0.x + 2.f, x0.x + 3.f);
+  float2 x2 = make_float2(x0.x + 4.f, x0.x + 5.f), x3 = make_float2(x0.x + 6.f, x0.x + 7.f);
+  float2 x4 = make_float2(x0.x + 8.f, x0.x + 9.f), x5 = make_float2(x0.x + 10.f, x0.x + 11.f);
+  float2 x6 = make_float2(x0.x + 12.f, x0.x + 13.f), x7 = make_float2(x0.x + 14.f, x0.x + 15.f);
+  const float2 A = make_float2(a, a), B = make_float2(b, b);
+  for (int i = 0; i < iters; i++) {
+#pragma unroll
+    for (int u = 0; u < 16; u++) {
+      x0 = __ffma2_rn(x0, A, B); x1 = __ffma2_rn(x1, A, B); x2 = __ffma2_rn(x2, A, B); x3 = __ffma2_rn(x3, A, B);
+      x4 = __ffma2_rn(x4, A, B); x5 = __ffma2_rn(x5, A, B); x6 = __ffma2_rn(x6, A, B); x7 = __ffma2_rn(x7, A, B);
+    }
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = x0.x + x0.y + x1.x + x1.y + x2.x + x2.y + x3.x + x3.y + x4.x + x4.y + x5.x + x5.y +
+                                               x6.x + x6.y + x7.x + x7.y;
+}
+
 static const Ops *pick_ops(int dtype, int mode) {
   const bool m6 = (mode != GRR_FREE);
   if (dtype == GRR_F32) return m6 ? ops_f32_m6() : ops_f32_m3();
@@ -432,7 +450,12 @@ int grr_scatter_node_blocks(int dtype, int64_t K, const int32_t *idx, int32_t n,
   return launch_ok("k_node_blocks<scatter>");
 }
 
-int grr_fp32_peak(int device, double *tflops_out) {
+static int fp32_peak_impl(int device, double *tflops_out, bool packed);
+int grr_fp32_peak(int device, double *tflops_out) { return fp32_peak_impl(device, tflops_out, false); }
+int grr_fp32x2_peak(int device, double *tflops_out) { return fp32_peak_impl(device, tflops_out, true); }
+}  // extern "C"
+
+static int fp32_peak_impl(int device, double *tflops_out, bool packed) {
   if (!tflops_out) { set_error("null argument"); return -1; }
   cudaError_t e = cudaSetDevice(device);
   if (e != cudaSuccess) { set_error("cudaSetDevice: %s", cudaGetErrorString(e)); return -2; }
@@ -446,12 +469,13 @@ int grr_fp32_peak(int device, double *tflops_out) {
   double best = 0;
   for (int rep = 0; rep < 5; rep++) {
     cudaEventRecord(a);
-    k_fma_peak<<<blocks, threads>>>(buf, iters, 0.999f, 0.001f);
+    if (packed) k_fma2_peak<<<blocks, threads>>>(buf, iters, 0.999f, 0.001f);
+    else k_fma_peak<<<blocks, threads>>>(buf, iters, 0.999f, 0.001f);
     cudaEventRecord(b);
     cudaEventSynchronize(b);
     float ms = 0;
     cudaEventElapsedTime(&ms, a, b);
-    const double flops = 2.0 * 8 * 16 * (double)iters * blocks * threads;
+    const double flops = 2.0 * 8 * 16 * (double)iters * blocks * threads * (packed ? 2.0 : 1.0);
     const double tf = flops / (ms * 1e-3) / 1e12;
     if (rep > 0 && tf > best) best = tf;
   }
@@ -462,4 +486,4 @@ int grr_fp32_peak(int device, double *tflops_out) {
   return rc;
 }
 
-}  // extern "C"
+

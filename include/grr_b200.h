@@ -176,6 +176,8 @@ int grr_scatter_node_blocks(int dtype, int64_t K, const int32_t *idx, int32_t n,
 
 /* -- measurement support: FP32 FMA peak microbenchmark (returns achieved TFLOP/s; synchronous). */
 int grr_fp32_peak(int device, double *tflops_out);
+/* same with the packed sm_100 FFMA2 instruction (two FP32 FMAs per instruction per lane) */
+int grr_fp32x2_peak(int device, double *tflops_out);
 
 #ifdef __cplusplus
 }
