@@ -85,6 +85,14 @@ def make_program(problem, jsonfile="Rfree.json", overrides=None, device=0, dtype
     """redundancy.py:198-252 minus GUI/load: problem -> (pdef, resolution, RedundancyResolver) with the
     workspace graph sampled as the options say."""
     pdef, resolution = load_problem(problem, jsonfile, overrides, device, dtype, ignore_collision, problem_dir)
-    resolution.sampleWorkspace(pdef["Nw"], method=pdef["workspace_graph"])
+    eg = pdef.get("explicit_grid")
+    if eg and pdef.get("orientation") == "variable":
+        # 6-D grids whose size the reference's Nw formula cannot express (SURVEY W3): positions x SO(3) given directly
+        from .workspace import explicit_product_graph
+        params, edges, info = explicit_product_graph(resolution.domain, eg["divs"], eg["rot_N"],
+                                                     staggered=(pdef["workspace_graph"] == "staggered_grid"))
+        resolution.setWorkspaceGraph(params, edges, info)
+    else:
+        resolution.sampleWorkspace(pdef["Nw"], method=pdef["workspace_graph"])
     rr = RedundancyResolver(resolution, cache=pdef.get("cache", 20000), seed=seed)
     return pdef, resolution, rr
