@@ -304,8 +304,18 @@ def run_cuda(args):
     except Exception:
         pass
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    traffic = None
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "edge_traffic.json")))
+        ent = tr.get(workload_name(pdef, res.ws_params.shape[0], res.ws_edges.shape[0]))
+        if ent and world == 1:
+            traffic = ent["dram_bytes_read"] + ent["dram_bytes_write"]
+    except Exception:
+        pass
     roofline = {"bound": "fp32_simt", "kernel": "k_edges_build", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
-                "frac": achieved_tf / peak_tf, "traffic": None,
+                "frac": achieved_tf / peak_tf, "traffic": traffic,
+                "traffic_note": "DRAM bytes read+written per launch from the ncu capture in profiles/ (null for workloads that were not captured); "
+                                "algorithmic bytes per launch = %d (every CTA re-reads both node blocks; the re-reads hit L2)" % int(alg_bytes),
                 "peak_source": "FP32 FMA microbenchmark (grr_fp32_peak) measured in this run; MEASURED_PEAKS.json carries no FP32 SIMT figure",
                 "flops_per_launch": edge_flops, "launch_s": edge_s,
                 "hbm": {"achieved": alg_bytes / edge_s / 1e9, "peak": hbm_peak, "unit": "GB/s", "frac": alg_bytes / edge_s / 1e9 / hbm_peak,
