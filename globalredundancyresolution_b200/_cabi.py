@@ -23,7 +23,7 @@ MAX_JOINTS = 32
 # every symbol include/grr_b200.h declares (checked by tests/test_cabi_symbols.py)
 EXPORTS = [
     "grr_last_error", "grr_abi_version", "grr_chain_create", "grr_chain_destroy", "grr_task_set",
-    "grr_chain_num_joints", "grr_fk_batch", "grr_ik_solve_batch", "grr_ik_sample", "grr_ik_sample_level", "grr_dedup",
+    "grr_chain_num_joints", "grr_fk_batch", "grr_ik_solve_batch", "grr_ik_sample", "grr_ik_sample_level", "grr_dedup", "grr_dedup_sweep",
     "grr_edges_build", "grr_edges_cost", "grr_edges_compact", "grr_valid_edge_batch", "grr_gather_node_blocks",
     "grr_scatter_node_blocks", "grr_fp32_peak", "grr_fp32x2_peak",
 ]
@@ -68,8 +68,9 @@ def lib():
     L.grr_fk_batch.argtypes = [vp, C.c_int, i64, vp, vp, vp, vp]
     L.grr_ik_solve_batch.argtypes = [vp, C.c_int, i64, vp, vp, vp, vp, vp, vp, vp]
     L.grr_ik_sample.argtypes = [vp, C.c_int, i64, i32, i32, vp, vp, u64, i32, vp, vp, vp, vp, vp]
-    L.grr_ik_sample_level.argtypes = [vp, C.c_int, C.c_int, i64, vp, i32, i32, i32, vp, vp, vp, vp, vp, vp, i32, vp, u64, i32, i32,
-                                      vp, vp, vp, vp, vp]
+    L.grr_ik_sample_level.argtypes = [vp, C.c_int, i64, vp, i32, i32, vp, vp, vp, vp, vp, vp, i32, vp, u64, i32, i32, vp, vp, vp,
+                                      vp, vp]
+    L.grr_dedup_sweep.argtypes = [vp, C.c_int, i64, vp, i32, i32, vp, vp, vp, i32, i32, vp, vp, dbl, i32, vp, vp, vp, vp]
     L.grr_dedup.argtypes = [vp, C.c_int, i64, i32, i32, vp, vp, dbl, i32, vp, vp, vp, vp, vp]
     L.grr_edges_build.argtypes = [vp, C.c_int, i64, vp, vp, vp, vp, vp, i32, i32, dbl, vp, vp, vp, vp]
     L.grr_edges_cost.argtypes = [vp, C.c_int, i64, vp, vp, vp, vp, i32, dbl, vp, vp]
@@ -195,16 +196,22 @@ class ChainHandle:
                                   _ptr(status), _ptr(iters), _ptr(counters), _stream(q_raw.device)),
               "grr_ik_sample")
 
-    def ik_sample_level(self, phase, node_list, Nq, col_off, params, node_uid, lower_ptr, lower_idx, degree, q_kept, count,
-                        seed, sample_offset, seed_from_adjacent, q_raw, status, iters=None, counters=None):
+    def ik_sample_level(self, node_list, Nq, params, node_uid, lower_ptr, lower_idx, degree, q_kept, count, seed,
+                        sample_offset, seed_from_adjacent, q_raw, status, nadj, counters=None):
         L = node_list.shape[0]
-        Nqr = q_raw.shape[2]
-        check(lib().grr_ik_sample_level(self._h, dtype_code(q_raw.dtype), int(phase), L, _ptr(node_list), int(Nq), Nqr,
-                                        int(col_off), _ptr(params), _ptr(node_uid), _ptr(lower_ptr), _ptr(lower_idx),
-                                        _ptr(degree), _ptr(q_kept), q_kept.shape[2], _ptr(count),
-                                        C.c_uint64(int(seed) & (2 ** 64 - 1)), int(sample_offset),
-                                        1 if seed_from_adjacent else 0, _ptr(q_raw), _ptr(status), _ptr(iters),
-                                        _ptr(counters), _stream(q_raw.device)), "grr_ik_sample_level")
+        check(lib().grr_ik_sample_level(self._h, dtype_code(q_raw.dtype), L, _ptr(node_list), int(Nq), q_raw.shape[2],
+                                        _ptr(params), _ptr(node_uid), _ptr(lower_ptr), _ptr(lower_idx), _ptr(degree),
+                                        _ptr(q_kept), q_kept.shape[2], _ptr(count), C.c_uint64(int(seed) & (2 ** 64 - 1)),
+                                        int(sample_offset), 1 if seed_from_adjacent else 0, _ptr(q_raw), _ptr(status),
+                                        _ptr(nadj), _ptr(counters), _stream(q_raw.device)), "grr_ik_sample_level")
+
+    def dedup_sweep(self, node_list, Nq, q_seed, status_seed, nadj, seed_from_adjacent, q_rand, status_rand, thresh, q_kept,
+                    count, counters=None):
+        L = node_list.shape[0]
+        check(lib().grr_dedup_sweep(self._h, dtype_code(q_seed.dtype), L, _ptr(node_list), int(Nq), q_seed.shape[2],
+                                    _ptr(q_seed), _ptr(status_seed), _ptr(nadj), 1 if seed_from_adjacent else 0,
+                                    q_rand.shape[2], _ptr(q_rand), _ptr(status_rand), float(thresh), q_kept.shape[2],
+                                    _ptr(q_kept), _ptr(count), _ptr(counters), _stream(q_seed.device)), "grr_dedup_sweep")
 
     def dedup(self, q_raw, status, thresh, q_kept, count, Nq=None, count_in=None, keep_idx=None):
         Nw, n, Nqp = q_raw.shape

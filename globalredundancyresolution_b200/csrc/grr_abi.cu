@@ -31,12 +31,14 @@ static inline int launch_ok(const char *what) {
 template <typename Real>
 __global__ void __launch_bounds__(128)
 k_dedup(int n, int Nq, int Nqp, const Real *__restrict__ q_raw, const uint8_t *__restrict__ status, Real thresh,
-        int Nqp_kept, Real *q_kept, const int32_t *__restrict__ count_in, int32_t *__restrict__ keep_idx,
-        int32_t *__restrict__ count) {
-  const long long node = blockIdx.x;
-  const Real *raw = q_raw + node * n * (long long)Nqp;
+        int Nqp_kept, Real *q_kept, const int32_t *count_in, int32_t *__restrict__ keep_idx,
+        int32_t *count, const int32_t *__restrict__ node_list) {
+  // raw candidates are indexed by block (level-local when node_list is given), kept configs by workspace node
+  const long long blk = blockIdx.x;
+  const long long node = node_list ? node_list[blk] : blk;
+  const Real *raw = q_raw + blk * n * (long long)Nqp;
   Real *out = q_kept + node * n * (long long)Nqp_kept;
-  const uint8_t *st = status + node * Nqp;
+  const uint8_t *st = status + blk * Nqp;
   int kept = count_in ? count_in[node] : 0;
   const int kept0 = kept;
   for (int s = 0; s < Nq; s++) {
@@ -50,14 +52,67 @@ k_dedup(int n, int Nq, int Nqp, const Real *__restrict__ q_raw, const uint8_t *_
     same = __syncthreads_or(same);
     if (!same && kept < Nqp_kept) {
       for (int j = threadIdx.x; j < n; j += blockDim.x) out[j * Nqp_kept + kept] = raw[j * Nqp + s];
-      if (threadIdx.x == 0 && keep_idx) keep_idx[node * Nq + (kept - kept0)] = s;
+      if (threadIdx.x == 0 && keep_idx) keep_idx[blk * Nq + (kept - kept0)] = s;
       kept++;
     }
     __syncthreads();
   }
   if (threadIdx.x == 0) count[node] = kept;
   if (keep_idx)
-    for (int k = (kept - kept0) + threadIdx.x; k < Nq; k += blockDim.x) keep_idx[node * Nq + k] = -1;
+    for (int k = (kept - kept0) + threadIdx.x; k < Nq; k += blockDim.x) keep_idx[blk * Nq + k] = -1;
+}
+
+// ------------------------------------------------------------------------------------------
+// Dedup of one wavefront level of the seeded sweep (solver.py:794-835): candidates in the sweep's order --
+// the node's nadj seeded attempts (level-local), then the first Nq - nadj + numFailed precomputed random-start
+// attempts of the node -- against the node's kept list, in place.  Counts the attempts the sweep ran.
+// ------------------------------------------------------------------------------------------
+template <typename Real>
+__global__ void __launch_bounds__(128)
+k_dedup_sweep(int n, int Nq, const int32_t *__restrict__ node_list, int Nqs, const Real *__restrict__ q_seed,
+              const uint8_t *__restrict__ st_seed, const int32_t *__restrict__ nadj, int use_seeded, int Nqr,
+              const Real *__restrict__ q_rand, const uint8_t *__restrict__ st_rand, Real thresh, int Nqp_kept, Real *q_kept,
+              int32_t *count, unsigned long long *counters) {
+  const long long blk = blockIdx.x;
+  const long long node = node_list[blk];
+  const Real *seedq = q_seed + blk * n * (long long)Nqs;
+  const uint8_t *sts = st_seed + blk * Nqs;
+  const Real *randq = q_rand + node * n * (long long)Nqr;
+  const uint8_t *str = st_rand + node * Nqr;
+  Real *out = q_kept + node * n * (long long)Nqp_kept;
+  const int na = nadj[blk];
+  int nfail = 0;
+  if (use_seeded) for (int s = 0; s < na; s++) nfail += (sts[s] != 0);
+  const int nseed = use_seeded ? na : 0, nrand = Nq - na + nfail;
+  int kept = count[node], nok = 0;
+  for (int cidx = 0; cidx < nseed + nrand; cidx++) {
+    const bool sd = cidx < nseed;
+    const int s = sd ? cidx : cidx - nseed;
+    const uint8_t stv = sd ? sts[s] : str[s];
+    if (stv != 0) continue;
+    nok++;
+    const Real *cand = sd ? seedq + s : randq + s;
+    const int cs = sd ? Nqs : Nqr;
+    int same = 0;
+    for (int k = threadIdx.x; k < kept; k += blockDim.x) {
+      Real d2 = 0;
+      for (int j = 0; j < n; j++) { Real d = cand[(long long)j * cs] - out[j * Nqp_kept + k]; d2 += d * d; }
+      if (sqrt_(d2) < thresh) same = 1;
+    }
+    same = __syncthreads_or(same);
+    if (!same && kept < Nqp_kept) {
+      for (int j = threadIdx.x; j < n; j += blockDim.x) out[j * Nqp_kept + kept] = cand[(long long)j * cs];
+      kept++;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    count[node] = kept;
+    if (counters) {
+      atomicAdd(counters + GRR_CNT_IK_SOLVES, (unsigned long long)(nseed + nrand));
+      atomicAdd(counters + GRR_CNT_IK_OK, (unsigned long long)nok);
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -332,24 +387,24 @@ int grr_ik_sample(grr_handle_t h, int dtype, int64_t Nw, int32_t Nq, int32_t Nqp
                         (unsigned long long *)counters, (cudaStream_t)stream);
 }
 
-int grr_ik_sample_level(grr_handle_t h, int dtype, int phase, int64_t L, const int32_t *node_list, int32_t Nq, int32_t Nqr,
-                        int32_t col_off, const void *params, const int32_t *node_uid, const int32_t *lower_ptr,
-                        const int32_t *lower_idx, const int32_t *degree, const void *q_kept, int32_t Nqp_kept,
-                        const int32_t *count, uint64_t seed, int32_t sample_offset, int32_t seed_from_adjacent, void *q_raw,
-                        uint8_t *status, uint8_t *iters, uint64_t *counters, void *stream) {
+int grr_ik_sample_level(grr_handle_t h, int dtype, int64_t L, const int32_t *node_list, int32_t Nq, int32_t Nqr,
+                        const void *params, const int32_t *node_uid, const int32_t *lower_ptr, const int32_t *lower_idx,
+                        const int32_t *degree, const void *q_kept, int32_t Nqp_kept, const int32_t *count, uint64_t seed,
+                        int32_t sample_offset, int32_t seed_from_adjacent, void *q_raw, uint8_t *status, int32_t *nadj,
+                        uint64_t *counters, void *stream) {
   GRR_CHECK_HANDLE(h);
   const Ops *ops = pick_ops(dtype, h->hc.mode);
   if (!ops) { set_error("bad dtype %d", dtype); return -1; }
   if (L <= 0 || Nq <= 0) return 0;
-  if (phase < 0 || phase > 1 || Nqr < col_off + Nq || col_off < 0) { set_error("grr_ik_sample_level: bad phase / column layout"); return -1; }
-  if (!node_list || !params || !node_uid || !lower_ptr || !lower_idx || !degree || !q_kept || !count || !q_raw || !status) {
+  if (Nqr < Nq) { set_error("grr_ik_sample_level: Nqr < Nq"); return -1; }
+  if (!node_list || !params || !node_uid || !lower_ptr || !lower_idx || !degree || !q_kept || !count || !q_raw || !status || !nadj) {
     set_error("grr_ik_sample_level: null buffer"); return -1;
   }
   unsigned long long *work = work_slot(h);
   if (!work) return -3;
-  return ops->ik_level(phase, h->hc, L, node_list, Nq, Nqr, col_off, params, node_uid, lower_ptr, lower_idx, degree, q_kept,
-                       Nqp_kept, count, seed, sample_offset, seed_from_adjacent, q_raw, status, iters, work,
-                       (unsigned long long *)counters, (cudaStream_t)stream);
+  return ops->ik_level(h->hc, L, node_list, Nq, Nqr, params, node_uid, lower_ptr, lower_idx, degree, q_kept, Nqp_kept, count,
+                       seed, sample_offset, seed_from_adjacent, q_raw, status, nadj, work, (unsigned long long *)counters,
+                       (cudaStream_t)stream);
 }
 
 int grr_dedup(grr_handle_t h, int dtype, int64_t Nw, int32_t Nq, int32_t Nqp, const void *q_raw, const uint8_t *status,
@@ -361,12 +416,34 @@ int grr_dedup(grr_handle_t h, int dtype, int64_t Nw, int32_t Nq, int32_t Nqp, co
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == GRR_F32)
     k_dedup<float><<<(unsigned)Nw, 128, 0, st>>>(h->hc.n, Nq, Nqp, (const float *)q_raw, status, (float)thresh, Nqp_kept,
-                                                 (float *)q_kept, count_in, keep_idx, count);
+                                                 (float *)q_kept, count_in, keep_idx, count, nullptr);
   else if (dtype == GRR_F64)
     k_dedup<double><<<(unsigned)Nw, 128, 0, st>>>(h->hc.n, Nq, Nqp, (const double *)q_raw, status, thresh, Nqp_kept,
-                                                  (double *)q_kept, count_in, keep_idx, count);
+                                                  (double *)q_kept, count_in, keep_idx, count, nullptr);
   else { set_error("bad dtype %d", dtype); return -1; }
   return launch_ok("k_dedup");
+}
+
+int grr_dedup_sweep(grr_handle_t h, int dtype, int64_t L, const int32_t *node_list, int32_t Nq, int32_t Nqs, const void *q_seed,
+                    const uint8_t *status_seed, const int32_t *nadj, int32_t seed_from_adjacent, int32_t Nqr, const void *q_rand,
+                    const uint8_t *status_rand, double thresh, int32_t Nqp_kept, void *q_kept, int32_t *count,
+                    uint64_t *counters, void *stream) {
+  GRR_CHECK_HANDLE(h);
+  if (L <= 0) return 0;
+  if (!node_list || !q_seed || !status_seed || !nadj || !q_rand || !status_rand || !q_kept || !count) {
+    set_error("grr_dedup_sweep: null buffer"); return -1;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == GRR_F32)
+    k_dedup_sweep<float><<<(unsigned)L, 128, 0, st>>>(h->hc.n, Nq, node_list, Nqs, (const float *)q_seed, status_seed, nadj,
+                                                      seed_from_adjacent, Nqr, (const float *)q_rand, status_rand, (float)thresh,
+                                                      Nqp_kept, (float *)q_kept, count, (unsigned long long *)counters);
+  else if (dtype == GRR_F64)
+    k_dedup_sweep<double><<<(unsigned)L, 128, 0, st>>>(h->hc.n, Nq, node_list, Nqs, (const double *)q_seed, status_seed, nadj,
+                                                       seed_from_adjacent, Nqr, (const double *)q_rand, status_rand, thresh,
+                                                       Nqp_kept, (double *)q_kept, count, (unsigned long long *)counters);
+  else { set_error("bad dtype %d", dtype); return -1; }
+  return launch_ok("k_dedup_sweep");
 }
 
 int grr_edges_build(grr_handle_t h, int dtype, int64_t E, const int32_t *wedges, const void *params, const void *q_kept,

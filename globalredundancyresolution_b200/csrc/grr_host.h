@@ -24,11 +24,11 @@ struct Ops {
   int (*ik_sample)(const HostChain &, long long Nw, int Nq, int Nqp, const void *params, const int32_t *uid,
                    unsigned long long seed, int sample_offset, void *q_raw, uint8_t *status, uint8_t *iters,
                    unsigned long long *work, unsigned long long *counters, cudaStream_t st);
-  int (*ik_level)(int phase, const HostChain &, long long Lnodes, const int32_t *node_list, int Nq, int Nqr, int col_off,
-                  const void *params, const int32_t *uid, const int32_t *lower_ptr, const int32_t *lower_idx,
-                  const int32_t *degree, const void *Qk, int Nqk, const int32_t *count, unsigned long long seed,
-                  int sample_offset, int seed_from_adjacent, void *q_raw, uint8_t *status, uint8_t *iters,
-                  unsigned long long *work, unsigned long long *counters, cudaStream_t st);
+  int (*ik_level)(const HostChain &, long long Lnodes, const int32_t *node_list, int Nq, int Nqr, const void *params,
+                  const int32_t *uid, const int32_t *lower_ptr, const int32_t *lower_idx, const int32_t *degree,
+                  const void *Qk, int Nqk, const int32_t *count, unsigned long long seed, int sample_offset,
+                  int seed_from_adjacent, void *q_raw, uint8_t *status, int32_t *nadj, unsigned long long *work,
+                  unsigned long long *counters, cudaStream_t st);
   int (*ik_solve_batch)(const HostChain &, long long P, const void *targets, void *q, uint8_t *status, uint8_t *iters,
                         void *resid, unsigned long long *work, unsigned long long *counters, cudaStream_t st);
   int (*valid_edge_batch)(const HostChain &, long long P, const void *qa, const void *qb, const void *wa, const void *wb,

@@ -6,6 +6,7 @@
 #include "grr_host.h"
 #include "grr_fill.cuh"
 #include <stdlib.h>
+#include <type_traits>
 
 namespace grr {
 
@@ -115,20 +116,21 @@ k_ik_instances(const __grid_constant__ ChainDev<Real, kMaxJ> c, long long total,
 }
 
 // ------------------------------------------------------------------------------------------
-// S1: one wavefront level of sampleConfigurationSpace's sequential sweep (solver.py:757-835).
-// Node i depends on its lower-numbered neighbours only, so all nodes of one level of that DAG are
-// sampled together.  PHASE 0: the numAdjacent attempts seeded from a random config of a random
-// lower neighbour (solver.py:794-815); PHASE 1: the numRandom + numFailed random-start attempts
-// (solver.py:817-835).  Instance (li, s): node = node_list[li]; results go to column s (PHASE 0) or
-// col_off + s (PHASE 1) of the level-local raw buffers, whose status is pre-filled with 255 (skipped).
+// S1: the seeded attempts of one wavefront level of sampleConfigurationSpace's sequential sweep
+// (solver.py:757-815).  Node i depends on its lower-numbered neighbours only, so all nodes of one level of
+// that DAG are processed together.  Instance (l, s), node = node_list[l]: if s < numAdjacent =
+// int(|adj|/deg * Nq), solve from config r1 % count[j] of lower neighbour j = adj[r0 % |adj|] (Philox stream 1).
+// The random-start attempts of the sweep (solver.py:817-835) do not depend on other nodes at all and are
+// computed for the whole graph beforehand by k_ik_instances; k_dedup_sweep then selects the
+// Nq - numAdjacent + numFailed of them the sweep would have run.  nadj[l] is written for that kernel.
 // ------------------------------------------------------------------------------------------
-template <typename Real, int M, int PHASE, bool PL>
+template <typename Real, int M, bool PL>
 __global__ void __launch_bounds__(256)
 k_ik_level(const __grid_constant__ ChainDev<Real, kMaxJ> c, long long total, const int32_t *__restrict__ node_list, int Nq,
-           int Nqr, int col_off, const Real *__restrict__ params, const int32_t *__restrict__ uid,
+           int Nqr, const Real *__restrict__ params, const int32_t *__restrict__ uid,
            const int32_t *__restrict__ lower_ptr, const int32_t *__restrict__ lower_idx, const int32_t *__restrict__ degree,
            const Real *__restrict__ Qk, int Nqk, const int32_t *__restrict__ count, unsigned long long seed, int sample_offset,
-           int seed_from_adjacent, Real *__restrict__ q_raw, uint8_t *__restrict__ status, uint8_t *__restrict__ iters,
+           int seed_from_adjacent, Real *__restrict__ q_raw, uint8_t *__restrict__ status, int32_t *__restrict__ nadj,
            unsigned long long *work, unsigned long long *counters) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int n = c.n, dw = (c.mode == 2 ? 6 : 3);
@@ -155,40 +157,20 @@ k_ik_level(const __grid_constant__ ChainDev<Real, kMaxJ> c, long long total, con
       for (int k = lower_ptr[node]; k < lower_ptr[node + 1]; k++) na += (count[lower_idx[k]] > 0);   // solver.py:776
       const int deg = degree[node];
       const int numAdjacent = deg > 0 ? (int)((double)na / (double)deg * (double)Nq) : 0;              // :777-778
-      Real *xo = mem.xold();
-      if (PHASE == 0) {
-        if (!seed_from_adjacent || s >= numAdjacent) continue;
-        uint32_t r[4];
-        philox4x32_10((uint32_t)uid[node], (uint32_t)(sample_offset + s), 0u, 1u, (uint32_t)seed, (uint32_t)(seed >> 32), r);
-        int pick = (int)(r[0] % (uint32_t)na), jn = -1;
-        for (int k = lower_ptr[node]; k < lower_ptr[node + 1]; k++) {
-          const int cand = lower_idx[k];
-          if (count[cand] > 0) { if (pick == 0) { jn = cand; break; } pick--; }
-        }
-        const int cfg = (int)(r[1] % (uint32_t)count[jn]);
-        const Real *srcq = Qk + ((long long)jn * n) * Nqk + cfg;
-        for (int j = 0; j < n; j++) xo[j * mem.T] = srcq[(long long)j * Nqk];
-        col = s;
-      } else {
-        int numFailed = 0;
-        if (seed_from_adjacent)
-          for (int k = 0; k < numAdjacent; k++) numFailed += (status[l * Nqr + k] != 0);
-        if (s >= Nq - numAdjacent + numFailed) continue;
-        const uint32_t id = (uint32_t)uid[node], smp = (uint32_t)(sample_offset + s);
-        for (int jb = 0; jb * 4 < n; jb++) {
-          uint32_t r[4];
-          philox4x32_10(id, smp, (uint32_t)jb, 0u, (uint32_t)seed, (uint32_t)(seed >> 32), r);
-#pragma unroll
-          for (int k = 0; k < 4; k++) {
-            const int j = jb * 4 + k;
-            if (j < n) {
-              const float u = (float)(r[k] >> 8) * (1.0f / 16777216.0f);
-              xo[j * mem.T] = (Real)fmaf(u, c.srange[j], c.slo[j]);
-            }
-          }
-        }
-        col = col_off + s;
+      if (s == 0) nadj[l] = numAdjacent;
+      if (!seed_from_adjacent || s >= numAdjacent) continue;
+      uint32_t r[4];
+      philox4x32_10((uint32_t)uid[node], (uint32_t)(sample_offset + s), 0u, 1u, (uint32_t)seed, (uint32_t)(seed >> 32), r);
+      int pick = (int)(r[0] % (uint32_t)na), jn = -1;
+      for (int k = lower_ptr[node]; k < lower_ptr[node + 1]; k++) {
+        const int cand = lower_idx[k];
+        if (count[cand] > 0) { if (pick == 0) { jn = cand; break; } pick--; }
       }
+      const int cfg = (int)(r[1] % (uint32_t)count[jn]);
+      const Real *srcq = Qk + ((long long)jn * n) * Nqk + cfg;
+      Real *xo = mem.xold();
+      for (int j = 0; j < n; j++) xo[j * mem.T] = srcq[(long long)j * Nqk];
+      col = s;
       Real w[6];
       for (int k = 0; k < dw; k++) w[k] = params[(long long)node * dw + k];
       target_from_params<Real, M, kMaxJ>(c, w, tg);
@@ -204,8 +186,7 @@ k_ik_level(const __grid_constant__ ChainDev<Real, kMaxJ> c, long long total, con
       Real *dst = q_raw + (li * n) * (long long)Nqr + col;
       for (int j = 0; j < n; j++) dst[(long long)j * Nqr] = L.res[j * mem.T];
       status[li * Nqr + col] = (uint8_t)st;
-      if (iters) iters[li * Nqr + col] = (uint8_t)L.it;
-      cnt.solves++; cnt.iters += L.it; cnt.evals += L.evals; cnt.ok += (st == IK_OK);
+      cnt.iters += L.it; cnt.evals += L.evals;       // attempts / successes are counted by k_dedup_sweep
       li = -1;
       lane_begin_mem(L, mem);
     }
@@ -563,10 +544,10 @@ struct Impl {
     return ik_instances(0, h, Nw * (long long)Nq, Nq, Nqp, params, uid, seed, sample_offset, q_raw, status, iters, nullptr,
                         work, counters, st);
   }
-  static int ik_level(int phase, const HostChain &h, long long Lnodes, const int32_t *node_list, int Nq, int Nqr, int col_off,
+  static int ik_level(const HostChain &h, long long Lnodes, const int32_t *node_list, int Nq, int Nqr,
                       const void *params, const int32_t *uid, const int32_t *lower_ptr, const int32_t *lower_idx,
                       const int32_t *degree, const void *Qk, int Nqk, const int32_t *count, unsigned long long seed,
-                      int sample_offset, int seed_from_adjacent, void *q_raw, uint8_t *status, uint8_t *iters,
+                      int sample_offset, int seed_from_adjacent, void *q_raw, uint8_t *status, int32_t *nadj,
                       unsigned long long *work, unsigned long long *counters, cudaStream_t st) {
     const long long total = Lnodes * (long long)Nq;
     if (total <= 0) return 0;
@@ -574,23 +555,23 @@ struct Impl {
     int threads, per_sm;
     lane_geometry(h, 0, 256, threads, per_sm);
     if (threads < 32) { set_error("ik_level: chain too large for shared memory"); return -2; }
+    // a level is small (tens of nodes): spread it over many small CTAs so that every SM gets lanes
+    if (threads > 64) threads = 64;
     const size_t smem = (size_t)threads * h.n * (4 + mc(h)) * sizeof(Real);
-    long long ctas = (long long)sm_count(h.device) * per_sm;
+    long long ctas = (long long)sm_count(h.device) * 4;
     const long long need = (total + threads - 1) / threads;
     if (ctas > need) ctas = need;
     cudaMemsetAsync(work, 0, sizeof(unsigned long long), st);
     auto launch = [&](auto kern) -> int {
       if (set_smem(kern, smem, "k_ik_level")) return -2;
-      kern<<<(unsigned)ctas, threads, smem, st>>>(c, total, node_list, Nq, Nqr, col_off, (const Real *)params, uid, lower_ptr,
+      kern<<<(unsigned)ctas, threads, smem, st>>>(c, total, node_list, Nq, Nqr, (const Real *)params, uid, lower_ptr,
                                                   lower_idx, degree, (const Real *)Qk, Nqk, count, seed, sample_offset,
-                                                  seed_from_adjacent, (Real *)q_raw, status, iters, work, counters);
+                                                  seed_from_adjacent, (Real *)q_raw, status, nadj, work, counters);
       return 0;
     };
     int rc;
-    if constexpr (kHasPlanar) {
-      if (planar(h)) rc = (phase == 0) ? launch(k_ik_level<Real, M, 0, true>) : launch(k_ik_level<Real, M, 1, true>);
-      else rc = (phase == 0) ? launch(k_ik_level<Real, M, 0, false>) : launch(k_ik_level<Real, M, 1, false>);
-    } else rc = (phase == 0) ? launch(k_ik_level<Real, M, 0, false>) : launch(k_ik_level<Real, M, 1, false>);
+    if constexpr (kHasPlanar) rc = planar(h) ? launch(k_ik_level<Real, M, true>) : launch(k_ik_level<Real, M, false>);
+    else rc = launch(k_ik_level<Real, M, false>);
     if (rc) return rc;
     return check_launch("k_ik_level");
   }

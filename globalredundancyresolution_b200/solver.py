@@ -423,7 +423,10 @@ class RedundancyResolver:
         return self._levels
 
     def _sample_phase_seeded(self, d, N, seed_from_adjacent):
-        """solver.py:757-835 as wavefronts: per level, seeded attempts, random attempts, dedup in attempt order."""
+        """solver.py:757-835 as wavefronts.  The random-start attempts of the sweep depend on no other node, so all
+        Nq of them are solved for the whole graph in one launch first; each level then runs only its seeded
+        attempts and a dedup that takes, in the sweep's order, the seeded results and the first
+        Nq - numAdjacent + numFailed random results."""
         torch = self.resolution._torch()
         res = self.resolution
         lv = self._sweep_levels()
@@ -431,26 +434,27 @@ class RedundancyResolver:
         Nqp = _cabi.round_up4(N)
         bounds = lv["bounds"]
         Lmax = int(np.diff(bounds).max())
-        cap = d["Qs"].shape[2]
-        q_raw = torch.empty((Lmax, n, 2 * Nqp), dtype=sdt, device=dev)
-        status = torch.empty((Lmax, 2 * Nqp), dtype=torch.uint8, device=dev)
-        kept = torch.empty((Lmax, n, cap), dtype=sdt, device=dev)
-        kcount = torch.empty(Lmax, dtype=torch.int32, device=dev)
+        q_rand = torch.empty((self.Nw, n, Nqp), dtype=sdt, device=dev)
+        st_rand = torch.empty((self.Nw, Nqp), dtype=torch.uint8, device=dev)
+        scratch = torch.zeros(_cabi.CNT_SLOTS, dtype=torch.int64, device=dev)
+        res.chain.ik_sample(d["params_s"], d["uid"], self.seed, q_rand, st_rand, None, scratch, Nq=N, sample_offset=self.attempts)
+        d["counters"][_cabi.CNT_IK_ITERS] += scratch[_cabi.CNT_IK_ITERS]       # work done (includes unused attempts)
+        d["counters"][_cabi.CNT_IK_EVALS] += scratch[_cabi.CNT_IK_EVALS]
+        q_seed = torch.empty((Lmax, n, Nqp), dtype=sdt, device=dev)
+        st_seed = torch.empty((Lmax, Nqp), dtype=torch.uint8, device=dev)
+        nadj = torch.zeros(Lmax, dtype=torch.int32, device=dev)
         for l in range(len(bounds) - 1):
             a, b = int(bounds[l]), int(bounds[l + 1])
             L = b - a
             nodes = lv["order"][a:b]
-            status[:L].fill_(255)
-            for phase in (0, 1):
-                if phase == 0 and (not seed_from_adjacent or l == 0):
-                    continue
-                res.chain.ik_sample_level(phase, nodes, N, Nqp, d["params_s"], d["uid"], lv["lower_ptr"], lv["lower_idx"],
-                                          lv["degree"], d["Qs"], d["count"], self.seed, self.attempts, seed_from_adjacent,
-                                          q_raw[:L], status[:L], None, d["counters"])
-            _cabi.gather_node_blocks(nodes, d["Qs"], d["count"], kept[:L], kcount[:L])
-            cin = kcount[:L].clone()
-            res.chain.dedup(q_raw[:L], status[:L], DEDUP_THRESHOLD, kept[:L], kcount[:L], Nq=2 * Nqp, count_in=cin)
-            _cabi.scatter_node_blocks(nodes, kept[:L], kcount[:L], d["Qs"], d["count"])
+            if l > 0:
+                st_seed[:L].fill_(255)
+                res.chain.ik_sample_level(nodes, N, d["params_s"], d["uid"], lv["lower_ptr"], lv["lower_idx"], lv["degree"],
+                                          d["Qs"], d["count"], self.seed, self.attempts, seed_from_adjacent,
+                                          q_seed[:L], st_seed[:L], nadj[:L], d["counters"])
+            res.chain.dedup_sweep(nodes, N, q_seed[:L], st_seed[:L], nadj[:L], seed_from_adjacent and l > 0, q_rand, st_rand,
+                                  DEDUP_THRESHOLD, d["Qs"], d["count"], d["counters"])
+        self._last_raw = (q_rand, st_rand, None)
 
     def sampleConfigurationSpace(self, NConfigsPerPoint=100, connect=True, biased=False, seedFromAdjacent=True,
                                  visibility=False, k=None, order_independent=False):

@@ -104,22 +104,29 @@ int grr_ik_sample(grr_handle_t h, int dtype, int64_t Nw, int32_t Nq, int32_t Nqp
                   const int32_t *node_uid, uint64_t seed, int32_t sample_offset, void *q_raw,
                   uint8_t *status, uint8_t *iters, uint64_t *counters, void *stream);
 
-/* -- S1: one wavefront level of sampleConfigurationSpace's sequential seeded sweep (solver.py:757-835).
- * Node i of the sweep depends only on its lower-numbered neighbours, so the nodes of one level of that
- * DAG are sampled together and the result equals the sequential sweep.  phase 0 = the
- * numAdjacent = int(|adj|/deg * Nq) attempts seeded from config r1 % count[j] of lower neighbour
- * j = adj[r0 % |adj|], (r0,r1) = Philox(key=seed, ctr=(uid, sample_offset+s, 0, 1)) (solver.py:794-815);
- * phase 1 = the (Nq - numAdjacent + numFailed) random-start attempts (solver.py:817-835), which reads
- * phase 0's status.  node_list [dev] i32 [L]; lower_ptr [dev] i32 [Nw+1] / lower_idx [dev] i32: CSR of
- * each node's neighbours with a smaller id in increasing order; degree [dev] i32 [Nw]; q_kept [dev]
- * Real [Nw][n][Nqp_kept] + count: the roadmap so far.  Level-local outputs q_raw [dev] Real [L][n][Nqr],
- * status/iters [dev] u8 [L][Nqr] (status pre-filled with 255 by the caller): phase 0 writes columns
- * [0,Nq), phase 1 columns [col_off, col_off+Nq). */
-int grr_ik_sample_level(grr_handle_t h, int dtype, int phase, int64_t L, const int32_t *node_list, int32_t Nq, int32_t Nqr,
-                        int32_t col_off, const void *params, const int32_t *node_uid, const int32_t *lower_ptr,
-                        const int32_t *lower_idx, const int32_t *degree, const void *q_kept, int32_t Nqp_kept,
-                        const int32_t *count, uint64_t seed, int32_t sample_offset, int32_t seed_from_adjacent, void *q_raw,
-                        uint8_t *status, uint8_t *iters, uint64_t *counters, void *stream);
+/* -- S1: the reference's default sampleConfigurationSpace (solver.py:757-835) is a sequential sweep: node i
+ * makes numAdjacent = int(|adj|/deg * Nq) attempts seeded from configs of its lower-numbered neighbours that
+ * already have configs (adj), then Nq - numAdjacent + numFailed random-start attempts, and dedups in that order.
+ * Node i depends only on lower-numbered neighbours, so the sweep runs as wavefronts over that DAG with an
+ * identical result.  The random-start attempts depend on no other node: the caller computes all Nq of them for
+ * every node first (grr_ik_sample, same Philox stream as S2), then per level:
+ *   grr_ik_sample_level: seeded attempt s < numAdjacent of node node_list[l] starts from config r1 % count[j] of
+ *     lower neighbour j = adj[r0 % |adj|], (r0,r1) = Philox(key=seed, ctr=(uid, sample_offset+s, 0, 1))
+ *     (solver.py:794-799); results to level-local q_raw [dev] Real [L][n][Nqr], status [dev] u8 [L][Nqr] (caller
+ *     pre-fills status with 255), nadj [dev] i32 [L] = numAdjacent.  lower_ptr [dev] i32 [Nw+1] / lower_idx: CSR of
+ *     each node's neighbours with a smaller id in increasing order; degree [dev] i32 [Nw]; q_kept/count: roadmap so far.
+ *   grr_dedup_sweep: greedy 1e-2 filter over the node's seeded results, then its first Nq - nadj + numFailed
+ *     precomputed random results (q_rand [dev] Real [Nw][n][Nqr], status_rand [dev] u8 [Nw][Nqr]), appended to
+ *     q_kept/count in place; adds the attempts the sweep ran / converged to counters. */
+int grr_ik_sample_level(grr_handle_t h, int dtype, int64_t L, const int32_t *node_list, int32_t Nq, int32_t Nqr,
+                        const void *params, const int32_t *node_uid, const int32_t *lower_ptr, const int32_t *lower_idx,
+                        const int32_t *degree, const void *q_kept, int32_t Nqp_kept, const int32_t *count, uint64_t seed,
+                        int32_t sample_offset, int32_t seed_from_adjacent, void *q_raw, uint8_t *status, int32_t *nadj,
+                        uint64_t *counters, void *stream);
+int grr_dedup_sweep(grr_handle_t h, int dtype, int64_t L, const int32_t *node_list, int32_t Nq, int32_t Nqs, const void *q_seed,
+                    const uint8_t *status_seed, const int32_t *nadj, int32_t seed_from_adjacent, int32_t Nqr, const void *q_rand,
+                    const uint8_t *status_rand, double thresh, int32_t Nqp_kept, void *q_kept, int32_t *count,
+                    uint64_t *counters, void *stream);
 
 /* -- S3: greedy first-wins duplicate filter (solver.py:802-813,824-835,886-897).  Keeps sample s
  * iff status==OK and distance to every previously kept config of the node >= thresh.  Existing
