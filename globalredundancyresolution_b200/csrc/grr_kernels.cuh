@@ -319,7 +319,7 @@ k_valid_edge_batch(const __grid_constant__ ChainDev<Real, kMaxJ> c, long long to
 // a shared-memory Nq x Nq bitmask that is written out once.
 // ------------------------------------------------------------------------------------------
 template <typename Real, int M, bool PL>
-__global__ void __launch_bounds__(sizeof(Real) == 4 ? 384 : 256)
+__global__ void __launch_bounds__(sizeof(Real) == 4 ? (M == 3 ? 512 : 384) : 256)
 k_edges_build(const __grid_constant__ ChainDev<Real, kMaxJ> c, const int32_t *__restrict__ wedges,
               const Real *__restrict__ params, const Real *__restrict__ q_kept, const int32_t *__restrict__ count,
               const int32_t *__restrict__ old_count, int Nq, int Nqp, Real epsilon, uint32_t *mask,
@@ -614,7 +614,7 @@ struct Impl {
     const int Wd = (Nq + 31) / 32;
     const size_t fixed = 2 * (size_t)h.n * Nqp * sizeof(Real) + (size_t)((Nq * Wd + 3) & ~3) * sizeof(uint32_t);
     int threads, per_sm;
-    lane_geometry(h, fixed, sizeof(Real) == 4 ? 384 : 256, threads, per_sm);
+    lane_geometry(h, fixed, sizeof(Real) == 4 ? (M == 3 ? 512 : 384) : 256, threads, per_sm);
     if (threads < 32) { set_error("edges_build: Nq=%d, n=%d does not fit shared memory", Nq, h.n); return -2; }
     // CTA size follows the work per workspace edge: a CTA owns one edge, so lanes beyond pairs/~6 would idle
     // for the whole edge (sparse roadmaps: a few configs per node).  One tiny reduction + an 16-byte readback.
