@@ -15,7 +15,7 @@ qlists over OS pipes per task (grr/solver.py:2232-2400).  Here:
                 window; in the node-blocked layout Q[node][dof][Nqp] a node range is ONE contiguous
                 slab, so the exchange is one send/recv per overlapping (owner, user) pair with no
                 pack/unpack kernel (batched isend/irecv -> ncclSend/ncclRecv groups over NVLink);
-  3b. chunks    each rank owns several (default 4) contiguous chunks spread over the grid (chunk c -> rank
+  3b. chunks    each rank owns several (default 8) contiguous chunks spread over the grid (chunk c -> rank
                 c % world) rather than one range, so regional bias of the work estimate averages out;
   4b. rebalance the work of a pair is its Ndivs (interpolated solves), which varies across the workspace
                 (measured: a 50/50 split by pair count was 58/42 by flops).  Each rank computes the exact
@@ -148,7 +148,7 @@ class ShardedResolver(RedundancyResolver):
     0.56 GB in FP32) but fills only its node window, and holds the bitmasks of its own edge range
     chunks (`edge_ids`: global ids of the local mask rows).  `gather_masks()` assembles the full roadmap."""
 
-    def __init__(self, resolution, rank, world, seed=0, sample_dtype="float64", rebalance=True, chunks_per_rank=4):
+    def __init__(self, resolution, rank, world, seed=0, sample_dtype="float64", rebalance=True, chunks_per_rank=8):
         self.rank, self.world = int(rank), int(world)
         self._local_of = {}
         self.rebalance = bool(rebalance)
