@@ -624,6 +624,42 @@ class RedundancyResolver:
                            "edge_ik_evals": int(c[_cabi.CNT_IK_EVALS])})
         return nondeg, self.E, 0, e0.elapsed_time(e1) * 1e-3
 
+    # ---- consumer seam: the CSP of the resolution stage (solver.py:984-1022) ---------------------------
+    def makeCSP(self, visibility=False):
+        """The input of the reference's resolution stage (out of scope here): one variable `q_<n>` per workspace
+        node that has configs, domain range(len(qlist)); one table constraint per non-degenerate workspace edge
+        (a < b) whose allowed tuples are the edge's (iq, jq) set (solver.py:1013-1021).  Returned as plain
+        containers: {'variables': {name: domain}, 'constraints': [((name_a, name_b), set((iq, jq)))]}."""
+        if visibility:
+            raise NotImplementedError("visibility-graph solver is out of scope of the B200 roadmap path")
+        cnt = self.counts()
+        variables = {"q_%d" % n: list(range(int(c))) for n, c in enumerate(cnt) if c > 0}
+        constraints = []
+        if self._dev is not None and self.Nq > 0:
+            offsets, pairs = self.edge_lists()
+            offsets, pairs = offsets.cpu().numpy(), pairs.cpu().numpy()
+            for e, (a, b) in enumerate(self._edges_host):
+                if offsets[e + 1] > offsets[e]:
+                    constraints.append((("q_%d" % a, "q_%d" % b), set(map(tuple, pairs[offsets[e]:offsets[e + 1]].tolist()))))
+        return {"variables": variables, "constraints": constraints}
+
+    def numConflicts(self, assignment):
+        """csp.numConflicts for an assignment {node: iq} (csp.py:79-84 over the tables of makeCSP), evaluated on the
+        device bitmasks: a workspace edge with both endpoints assigned is in conflict iff bit (iq_a, iq_b) is clear."""
+        torch = self.resolution._torch()
+        d = self._dev
+        a = torch.full((self.Nw,), -1, dtype=torch.int64, device=self.resolution.torch_device)
+        if assignment:
+            keys = torch.as_tensor(list(assignment.keys()), dtype=torch.int64, device=a.device)
+            a[keys] = torch.as_tensor(list(assignment.values()), dtype=torch.int64, device=a.device)
+        ia, ib = a[d["wedges"][:, 0].long()], a[d["wedges"][:, 1].long()]
+        both = (ia >= 0) & (ib >= 0)
+        nondeg = d["mask"].view(self.E, -1).ne(0).any(dim=1)
+        e = torch.nonzero(both & nondeg).squeeze(1)
+        words = d["mask"][e, ia[e], ib[e] // 32]
+        ok = (words >> (ib[e] % 32).to(torch.int32)) & 1
+        return int((ok == 0).sum().item())
+
     # ---- sanity (solver.py:365-383) -------------------------------------------------------------------
     def sanityCheck(self):
         cnt = self.counts()

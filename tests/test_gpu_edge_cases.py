@@ -163,3 +163,43 @@ def test_full_size_properties_cfg2(built):
     m1 = rr._dev["mask"].clone()
     rr.connectConfigurationSpace()
     assert torch.equal(m1, rr._dev["mask"])
+
+
+def test_node_block_gather_scatter_and_edge_cost(built):
+    """Halo-exchange helpers (grr_gather/scatter_node_blocks) and the shard work estimate (grr_edges_cost)."""
+    pdef, res, rr = grr.make_program("planar_3R", "baseline_cfg1.json", overrides={"Nw": 100}, seed=3)
+    rr.sampleConfigurationSpace(8, connect=False, order_independent=True)
+    dev = res.torch_device
+    d = rr._dev
+    idx = torch.tensor([5, 17, 2, 63], dtype=torch.int32, device=dev)
+    n, Nqp = d["Q"].shape[1], d["Q"].shape[2]
+    packed = torch.zeros((4, n, Nqp), dtype=d["Q"].dtype, device=dev)
+    pc = torch.zeros(4, dtype=torch.int32, device=dev)
+    _cabi.gather_node_blocks(idx, d["Q"], d["count"], packed, pc)
+    assert torch.equal(packed, d["Q"][idx.long()]) and torch.equal(pc, d["count"][idx.long()])
+    Q2 = torch.zeros_like(d["Q"]); c2 = torch.zeros_like(d["count"])
+    _cabi.scatter_node_blocks(idx, packed, pc, Q2, c2)
+    assert torch.equal(Q2[idx.long()], packed) and torch.equal(c2[idx.long()], pc)
+    mask = torch.ones(Q2.shape[0], dtype=torch.bool, device=dev); mask[idx.long()] = False
+    assert float(Q2[mask].abs().sum()) == 0.0 and int(c2[mask].sum()) == 0
+    # work estimate = sum over pairs of Ndivs + 1, against the oracle's Ndivs
+    cost = torch.zeros(rr.E, dtype=torch.int64, device=dev)
+    res.chain.edges_cost(d["wedges"], d["Q"], d["count"], 0.05, cost)
+    o = oracle_for(res)
+    cnt = rr.counts()
+    Q = np.transpose(d["Q"][:, :, :8].double().cpu().numpy(), (0, 2, 1))
+    e = res.ws_edges
+    want = np.zeros(rr.E, dtype=np.int64)
+    eps = 0.05 * np.sqrt(o.c.nlinks_eps)
+    for k, (i, j) in enumerate(e):
+        if cnt[i] and cnt[j]:
+            dist = np.linalg.norm(Q[i, :cnt[i], None, :] - Q[j, None, :cnt[j], :], axis=2)
+            want[k] = int((np.ceil(dist / eps) + 1).sum())
+    got = cost.cpu().numpy()
+    assert np.abs(got - want).max() <= 2 and int(got.sum()) > 0          # FP32 ceil flips at most
+    # FK batch against the closed form
+    q = d["Q"][5, :, : int(cnt[5])].contiguous() if cnt[5] else d["Q"][17, :, : int(cnt[17])].contiguous()
+    p = torch.empty((q.shape[1], 3), dtype=q.dtype, device=dev)
+    res.chain.fk_batch(q, p)
+    th = np.cumsum(q.double().cpu().numpy(), axis=0)
+    np.testing.assert_allclose(p.cpu().numpy(), np.stack([np.cos(th).sum(0), 0 * th[0], -np.sin(th).sum(0)], axis=1), atol=2e-6)

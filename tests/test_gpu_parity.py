@@ -368,3 +368,26 @@ def test_seeded_sweep_rescues_6d_problems(built):
     print("\n[6-D seeded vs random] configs %d vs %d, C-space edges %d vs %d" % (ns, nr, rr_s.numCSpaceEdges(), rr_r.numCSpaceEdges()))
     assert ns > nr
     rr_s.sanityCheck()
+
+
+def test_make_csp_seam(built):
+    """makeCSP (solver.py:984-1022) hands the roadmap to the resolution stage in the reference's terms."""
+    pdef, res = small_problem("planar_3R", "baseline_cfg1.json", 100, "grid")
+    rr = grr.RedundancyResolver(res, seed=SEED)
+    rr.sampleConfigurationSpace(8, order_independent=True)
+    csp = rr.makeCSP()
+    cnt = rr.counts()
+    assert set(csp["variables"]) == {"q_%d" % n for n in range(rr.Nw) if cnt[n] > 0}
+    assert all(csp["variables"]["q_%d" % n] == list(range(cnt[n])) for n in range(rr.Nw) if cnt[n] > 0)
+    by_edge = {names: allowed for names, allowed in csp["constraints"]}
+    for e, (a, b) in enumerate(rr._edges_host):
+        ql = rr.Gw.edge[a][b]["qlist"]
+        assert by_edge.get(("q_%d" % a, "q_%d" % b), set()) == ql and a < b
+    # numConflicts on the device masks == counting over the tables
+    rng = np.random.default_rng(0)
+    assign = {n: int(rng.integers(0, cnt[n])) for n in range(rr.Nw) if cnt[n] > 0 and rng.random() < 0.8}
+    want = sum(1 for (na, nb), allowed in csp["constraints"]
+               if int(na[2:]) in assign and int(nb[2:]) in assign and (assign[int(na[2:])], assign[int(nb[2:])]) not in allowed)
+    assert rr.numConflicts(assign) == want and want > 0
+    with pytest.raises(NotImplementedError):
+        rr.makeCSP(visibility=True)
