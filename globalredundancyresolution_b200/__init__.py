@@ -7,5 +7,6 @@ from .graph import RedundancyResolutionGraph, IKTask, DEFAULT_EDGE_CHECK_TOLERAN
 from .robot import RobotChain, planar_robot, synthetic_arm, synthetic_arm_links      # noqa: F401
 from .solver import RedundancyResolver                               # noqa: F401
 from .problems import load_problem, make_program                     # noqa: F401
+from .worker import Worker, worker                                   # noqa: F401
 
 __version__ = "0.1.0"

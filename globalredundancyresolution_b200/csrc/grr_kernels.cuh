@@ -501,8 +501,9 @@ struct Impl {
   // persistent lanes: threads per CTA and CTAs so that every SM holds as many lanes as shared memory allows
   static void lane_geometry(const HostChain &h, size_t fixed_bytes, int max_threads, int &threads, int &ctas_per_sm) {
     const size_t per_lane = (size_t)h.n * (4 + mc(h)) * sizeof(Real);
-    ctas_per_sm = 2;
-    size_t per_cta = kSmemBudget / 2 - 1024;
+    static const int force_one = getenv("GRR_ONE_CTA_PER_SM") != nullptr;   // experiment switch
+    ctas_per_sm = force_one ? 1 : 2;
+    size_t per_cta = kSmemBudget / ctas_per_sm - 1024;
     long t = per_cta > fixed_bytes ? (long)((per_cta - fixed_bytes) / per_lane) : 0;
     if (t < 64) { ctas_per_sm = 1; per_cta = kSmemBudget - 1024; t = per_cta > fixed_bytes ? (long)((per_cta - fixed_bytes) / per_lane) : 0; }
     if (t > max_threads) t = max_threads;

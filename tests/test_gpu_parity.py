@@ -391,3 +391,33 @@ def test_make_csp_seam(built):
     assert rr.numConflicts(assign) == want and want > 0
     with pytest.raises(NotImplementedError):
         rr.makeCSP(visibility=True)
+
+
+def test_worker_protocol(built):
+    """The reference's master/worker task tuples (solver.py:2379-2400) answered by the GPU path."""
+    import queue
+    pdef, res = small_problem("planar_3R", "baseline_cfg1.json", 100, "grid")
+    w = grr.Worker(res, seed=SEED)
+    pi, pj = [1.5, 0.0, 0.5], [1.7, 0.0, 0.5]
+    ci, qccs, parents, uid = w.handle(("sample", pi, 16, None, 7))
+    cj = w.handle(("sample", pj, 16, None, 8))[0]
+    assert uid == 7 and len(ci) > 1 and qccs == [[k] for k in range(len(ci))] and parents == [-1] * len(ci)
+    o = oracle_for(res)
+    ref = o.sample_nodes(np.array([pi, pj]), np.array([7, 8]), 16, seed=SEED)
+    np.testing.assert_allclose(res.to_chain(np.asarray(ci)), ref["q_kept"][0, :ref["count"][0]], atol=1e-8)
+    qlist, iw, jw = w.handle(("connect", 3, ci, qccs, pi, 9, cj, [[k] for k in range(len(cj))], pj))
+    assert (iw, jw) == (3, 9)
+    want = {(a, b) for a in range(len(ci)) for b in range(len(cj))
+            if o.valid_edge(res.to_chain(ci[a]), res.to_chain(cj[b]), pi, pj)[0]}
+    assert len(set(qlist) ^ want) <= 1 and len(want) > 0
+    edges = [(0, 0), (1, 0), (0, 1), (1, 1)]
+    multi = w.handle(("test-multi", 3, ci, pi, 9, cj, pj, edges))
+    assert multi == [(3, a, 9, b) for (a, b) in edges if (a, b) in set(qlist)]
+    assert w.handle(("test", 3, 0, ci[0], pi, 9, 0, cj[0], pj)) == ((0, 0) in set(qlist), 3, 0, 9, 0)
+    assert w.handle(("connect", 3, [], [], pi, 9, cj, [], pj)) == ([], 3, 9)
+    tq, rq = queue.Queue(), queue.Queue()
+    tq.put(("test", 3, 0, ci[0], pi, 9, 0, cj[0], pj)); tq.put(("kill",))
+    grr.worker(0, res, tq, rq, seed=SEED)
+    assert rq.get_nowait()[1:] == (3, 0, 9, 0)
+    with pytest.raises(ValueError):
+        w.handle(("bogus",))
