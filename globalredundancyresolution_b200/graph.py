@@ -334,6 +334,34 @@ class RedundancyResolutionGraph:
             return out, info.cpu().numpy()
         return out
 
+    # ---- on-disk format (graph.py:643-670): networkx-1.x gpickle of Gw -------------------------------
+    def save(self, folder):
+        """Writes <folder>/resolution_graph.pickle in the reference's format (nx.write_gpickle of a networkx-1.x
+        Graph, protocol 2), so the reference's loader / GUI can read a roadmap built here."""
+        import os
+        from ._nx1pickle import dumps_graph
+        os.makedirs(folder, exist_ok=True)
+        with open(os.path.join(folder, "resolution_graph.pickle"), "wb") as f:
+            f.write(dumps_graph(self.Gw.node, self.Gw.adj, self.Gw.graph))
+
+    def load(self, folder):
+        """graph.py:648-670: read resolution_graph.pickle (written by the reference or by save()), rebuild the
+        domain from the node params and recount the resolved nodes."""
+        import os
+        from ._nx1pickle import loads_graph
+        with open(os.path.join(folder, "resolution_graph.pickle"), "rb") as f:
+            node, adj, graph = loads_graph(f.read())
+        G = Graph()
+        G.node, G.adj, G.edge, G.graph = node, adj, adj, graph
+        self.Gw = G
+        n = G.number_of_nodes()
+        params = np.asarray([G.node[i]["params"] for i in range(n)], dtype=np.float64)
+        self.domain = ([float(v) for v in params.min(axis=0)], [float(v) for v in params.max(axis=0)])
+        self.resolvedCount = sum(1 for i, d in G.nodes_iter(data=True) if d.get("config", None) is not None)
+        self.ws_params = params
+        self.ws_edges = np.asarray(sorted((min(i, j), max(i, j)) for i, j in G.edges_iter()), dtype=np.int64).reshape(-1, 2)
+        self.ws_info = {}
+
     # ---- resolution bookkeeping (host only; graph.py:852-885) -------------------------------------
     def setConfig(self, i, q):
         assert i < self.Gw.number_of_nodes()

@@ -624,6 +624,42 @@ class RedundancyResolver:
                            "edge_ik_evals": int(c[_cabi.CNT_IK_EVALS])})
         return nondeg, self.E, 0, e0.elapsed_time(e1) * 1e-3
 
+    # ---- checkpoint / resume (solver.py:274-348) ------------------------------------------------------
+    def save(self, folder):
+        """Checkpoint: the reference's resolution_graph.pickle (through resolution.save) plus the device roadmap as
+        roadmap_b200.npz (kept configs in sampling precision, counts, edge bitmasks, attempt counter).  The
+        reference's own Gw_cached.pickle is a shelve-backed CGraph and is not written."""
+        import os
+        self.resolution.save(folder)
+        d = self._dev
+        out = {"Nq": self.Nq, "attempts": self.attempts, "seed": self.seed, "edges": self.resolution.ws_edges,
+               "params": self.resolution.ws_params}
+        if d is not None and self.Nq > 0:
+            out.update({"Qs": d["Qs"].cpu().numpy(), "count": d["count"].cpu().numpy(), "mask": d["mask"].cpu().numpy()})
+        np.savez_compressed(os.path.join(folder, "roadmap_b200.npz"), **out)
+
+    def load(self, folder):
+        """Resume from save(): the roadmap goes back to the device; a following sampleConfigurationSpace call grows
+        it incrementally (only pairs with a new endpoint are tested, solver.py:759,850)."""
+        import os
+        torch = self.resolution._torch()
+        z = np.load(os.path.join(folder, "roadmap_b200.npz"))
+        assert z["edges"].shape == self.resolution.ws_edges.shape and (z["edges"] == self.resolution.ws_edges).all(), \
+            "checkpoint belongs to a different workspace graph"
+        self.initWorkspaceGraph()
+        self.seed, self.attempts = int(z["seed"]), int(z["attempts"])
+        Nq = int(z["Nq"])
+        if Nq > 0:
+            d = self._ensure_device(Nq)
+            dev = self.resolution.torch_device
+            d["Qs"].copy_(torch.as_tensor(z["Qs"], device=dev))
+            d["count"].copy_(torch.as_tensor(z["count"], device=dev))
+            d["mask"].copy_(torch.as_tensor(z["mask"], device=dev))
+            if d["Qs"] is not d["Q"]:
+                d["Q"].copy_(d["Qs"])
+            self.attempts = int(z["attempts"])
+        self.sanityCheck()
+
     # ---- consumer seam: the CSP of the resolution stage (solver.py:984-1022) ---------------------------
     def makeCSP(self, visibility=False):
         """The input of the reference's resolution stage (out of scope here): one variable `q_<n>` per workspace

@@ -421,3 +421,21 @@ def test_worker_protocol(built):
     assert rq.get_nowait()[1:] == (3, 0, 9, 0)
     with pytest.raises(ValueError):
         w.handle(("bogus",))
+
+
+def test_checkpoint_resume_equals_uninterrupted(built, tmp_path):
+    """save() / load() (solver.py:274-348 role): a roadmap checkpointed after the first sampling round and grown
+    after resume equals the roadmap grown without interruption."""
+    pdef, res = small_problem("planar_3R", "baseline_cfg1.json", 100, "grid")
+    a = grr.RedundancyResolver(res, seed=SEED)
+    a.sampleConfigurationSpace(6, order_independent=True)
+    a.save(str(tmp_path))
+    a.sampleConfigurationSpace(6, order_independent=True)
+    pdef2, res2 = small_problem("planar_3R", "baseline_cfg1.json", 100, "grid")
+    b = grr.RedundancyResolver(res2, seed=SEED)
+    b.load(str(tmp_path))
+    assert b.Nq == 6 and b.attempts == 6 and b.numConfigurations() > 0
+    b.sampleConfigurationSpace(6, order_independent=True)
+    assert torch.equal(a._dev["count"], b._dev["count"]) and torch.equal(a._dev["Qs"], b._dev["Qs"])
+    assert torch.equal(a._dev["mask"], b._dev["mask"])
+    assert (tmp_path / "resolution_graph.pickle").exists()

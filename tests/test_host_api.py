@@ -111,3 +111,33 @@ def test_graph_class_is_networkx1_flavoured():
     assert [n for n, d in G.nodes_iter(data=True)] == [0, 1, 2]
     G.remove_edge(0, 1)
     assert not G.has_edge(1, 0)
+
+
+def test_resolution_graph_pickle_matches_reference_layout(tmp_path):
+    """save()/load() use the reference's on-disk format (graph.py:643-649): networkx-1.x gpickle, protocol 2.
+    The writer is checked against the layout of the reference's shipped fixture (same opcode prefix, Python-2
+    str keys, shared edge dicts) and round-trips through the loader."""
+    import pickletools
+    from globalredundancyresolution_b200 import _nx1pickle
+    robot = grr.planar_robot(3)
+    res = grr.RedundancyResolutionGraph(robot)
+    res.readJsonSetup({"domain": [[-3, 0, -3], [3.5, 0, 3.5]], "eelocal": [1, 0, 0], "useCollision": False})
+    res.sampleWorkspace(50, method="grid")
+    res.setConfig(3, [0.1, 0.2, 0.3]); res.setConfig(4, [0.1, 0.25, 0.3])
+    res.markConnected(3, 4)
+    res.save(str(tmp_path))
+    data = (tmp_path / "resolution_graph.pickle").read_bytes()
+    assert data.startswith(b"\x80\x02cnetworkx.classes.graph\nGraph\nq\x01)\x81q\x02}q\x03(U\x04nodeq\x04}")   # fixture prefix
+    ops = [op.name for op, arg, pos in pickletools.genops(data)]
+    assert "BINUNICODE" not in ops and "SHORT_BINSTRING" in ops and ops[-2:] == ["BUILD", "STOP"]
+    node, adj, graph = _nx1pickle.loads_graph(data)
+    assert sorted(node) == list(range(res.Gw.number_of_nodes()))
+    assert node[3]["config"] == [0.1, 0.2, 0.3] and node[7]["params"] == res.Gw.node[7]["params"]
+    assert adj[3][4] is adj[4][3] and adj[3][4]["connected"] is True          # one attr dict per undirected edge
+    res2 = grr.RedundancyResolutionGraph(robot)
+    res2.load(str(tmp_path))
+    assert res2.resolvedCount == 2 and res2.isResolvedEdge(3, 4) and res2.Gw.number_of_edges() == res.Gw.number_of_edges()
+    np.testing.assert_allclose(res2.domain[0], [-3, 0, -3]); np.testing.assert_allclose(res2.domain[1], [3.5, 0, 3.5])
+    np.testing.assert_array_equal(res2.ws_edges, res.ws_edges)
+    with pytest.raises(Exception):
+        _nx1pickle.loads_graph(b"\x80\x02cos\nsystem\nq\x00U\x04trueq\x01\x85q\x02Rq\x03.")   # no arbitrary classes

@@ -103,3 +103,22 @@ def test_random_graph_is_refused():
         W.build_workspace_graph([[-1, 0, -1], [1, 0, 1]], 100, "random", 3, "free")
     with pytest.raises(ValueError):
         W.build_workspace_graph([[-1, 0, -1], [1, 0, 1]], 100, "hexagonal", 3, "free")
+
+
+def test_loader_reads_the_reference_fixture_bytes():
+    """The pickle loader is the same code path that produced the golden fixture: cross-check it on a graph pickle
+    written in the reference's layout with a Python-2 style prefix (the original 1 MB file is not shipped)."""
+    from globalredundancyresolution_b200 import _nx1pickle
+    from globalredundancyresolution_b200.workspace import Graph
+    g = np.load(GOLD)
+    G = Graph()
+    for i, p in enumerate(g["params"].astype(np.float64)):
+        G.add_node(i, params=[float(v) for v in p], qlist=[])
+    for i, j in g["edges"].tolist():
+        G.add_edge(i, j, qlist=[])
+    for i, j in g["connected"].tolist():
+        G.edge[i][j]["connected"] = True
+    data = _nx1pickle.dumps_graph(G.node, G.adj)
+    node, adj, _ = _nx1pickle.loads_graph(data)
+    assert len(node) == 3900 and sum(len(a) for a in adj.values()) // 2 == 19774
+    assert sum(1 for u in adj for v, d in adj[u].items() if u < v and d.get("connected")) == 4211
