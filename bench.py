@@ -106,7 +106,7 @@ def problem_setup(args, world=1):
     if args.nq:
         over["Nq"] = args.nq
     pdef = grr.problems.read_options(name, jf, over)
-    if world > 1:
+    if world > 1 and not args.strong:
         over["Nw"] = pdef["Nw"] * world
         pdef = grr.problems.read_options(name, jf, over)
     return grr, name, jf, over, pdef
@@ -344,7 +344,8 @@ def run_cuda(args):
                "ik_configs_per_s": r["ik_configs_per_s"], "edges_only_per_s": r["edges_only_per_s"]}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong" if args.strong else "weak",
+            "vs_baseline": None,
             "dtype": "f32 (edge phase) / f64 (sampling)", "data": "synthetic",
             "config": {"workload": workload_name(pdef, res.ws_params.shape[0], res.ws_edges.shape[0]), "seed": 0,
                        "l2": "256 MiB flush write between steps, inside the timed region",
@@ -372,6 +373,7 @@ def main():
     ap.add_argument("--nq", type=int, default=0)
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU work per reference step / cpu_baseline sample")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--strong", action="store_true", help="keep the problem size fixed at N > 1 (default: weak scaling, Nw x N)")
     ap.add_argument("--e2e-rebuild", action="store_true", help="rebuild the problem objects inside the e2e region")
     args = ap.parse_args()
     if args.impl == "reference":

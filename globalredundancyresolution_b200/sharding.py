@@ -5,8 +5,10 @@ workspace edges it owns.
 The reference's own data-parallel path is a multiprocessing master/worker pool that pickles whole
 qlists over OS pipes per task (grr/solver.py:2232-2400).  Here:
 
-  1. sampling   rank r samples nodes [n_r, n_{r+1}) -- node-independent work, identical cost per node,
-                RNG keyed by the GLOBAL node id, so the result does not depend on the world size;
+  1. sampling   the node ids are cut into world*8 contiguous chunks, chunk c owned by rank c % world (reachable
+                and unreachable regions -- whose failing solves cost 50 iterations -- are spread over the ranks);
+                node-independent work, RNG keyed by the GLOBAL node id, so the result does not depend on the
+                world size;
   2. counts     one all-reduce of the (zero-padded) count vector: every rank knows every node's count;
   3. edge plan  workspace edges are sorted by (iw, jw); they are cut into `world` contiguous ranges of
                 equal PAIR-TEST load (sum of count[iw]*count[jw], minus both-old pairs) -- a large share
@@ -88,6 +90,23 @@ def node_window(edges, e0, e1):
     return int(sub.min()), int(sub.max()) + 1
 
 
+def node_windows(edges, bounds):
+    """node_window for every chunk [bounds[c], bounds[c+1]) at once.  Edges are sorted by (iw, jw) with iw < jw,
+    so a chunk's lowest node is its first edge's iw and its highest is the maximum jw of the chunk."""
+    bounds = np.asarray(bounds, dtype=np.int64)
+    nchunk = bounds.shape[0] - 1
+    out = [(0, 0)] * nchunk
+    nonempty = np.nonzero(bounds[1:] > bounds[:-1])[0]
+    if nonempty.size == 0:
+        return out
+    starts = bounds[:-1][nonempty]
+    hi = np.maximum.reduceat(edges[:, 1], starts)
+    # reduceat runs to the next start; chunks are contiguous and only empty chunks are skipped, so this is exact
+    for k, c in enumerate(nonempty.tolist()):
+        out[c] = (int(edges[starts[k], 0]), int(hi[k]) + 1)
+    return out
+
+
 def rank_chunks(bounds, world, chunks_per_rank):
     """Chunk c of the world*chunks_per_rank contiguous chunks goes to rank c % world: every rank gets
     `chunks_per_rank` slices spread over the whole grid, so regional errors of the work estimate average out.
@@ -98,32 +117,40 @@ def rank_chunks(bounds, world, chunks_per_rank):
     return out
 
 
-def halo_plan(nbounds, windows):
-    """windows[r] = list of node windows rank r needs.  For every (owner p, user r) pair with p != r, the node
-    slabs [a,b) that p must send to r: the overlaps of r's windows with p's owned range, merged.
-    Returns {(p, r): [(a, b), ...]}."""
+def halo_plan(nbounds, windows, world=None):
+    """windows[r] = list of node windows rank r needs; nbounds = bounds of the contiguous node chunks, chunk c
+    owned by rank c % world (world defaults to the number of chunks: one range per rank).  For every
+    (owner p, user r) pair with p != r, the node slabs [a,b) that p must send to r.  Returns {(p, r): [(a, b), ...]}."""
+    nchunks = len(nbounds) - 1
+    nranks = len(windows)
+    world = nranks if world is None else world
+    nb = np.asarray(nbounds, dtype=np.int64)
     plan = {}
-    world = len(windows)
     for r, wins in enumerate(windows):
         if isinstance(wins, tuple):
             wins = [wins]
-        for p in range(world):
-            if p == r:
+        segs = {}
+        for (lo, hi) in wins:
+            if hi <= lo:
                 continue
-            segs = []
-            for (lo, hi) in wins:
-                a, b = max(lo, nbounds[p]), min(hi, nbounds[p + 1])
+            c0 = int(np.searchsorted(nb, lo, side="right")) - 1
+            c1 = int(np.searchsorted(nb, hi, side="left"))
+            for c in range(max(c0, 0), min(c1, nchunks)):
+                p = c % world
+                if p == r:
+                    continue
+                a, b = max(lo, int(nb[c])), min(hi, int(nb[c + 1]))
                 if b > a:
-                    segs.append((a, b))
-            segs.sort()
+                    segs.setdefault(p, []).append((a, b))
+        for p, lst in segs.items():
+            lst.sort()
             merged = []
-            for a, b in segs:
+            for a, b in lst:
                 if merged and a <= merged[-1][1]:
                     merged[-1] = (merged[-1][0], max(merged[-1][1], b))
                 else:
                     merged.append((a, b))
-            if merged:
-                plan[(p, r)] = merged
+            plan[(p, r)] = merged
     return plan
 
 
@@ -156,13 +183,19 @@ class ShardedResolver(RedundancyResolver):
         self.edge_ids = np.zeros(0, dtype=np.int64)
         self.halo_bytes = 0
         RedundancyResolver.__init__(self, resolution, seed=seed, sample_dtype=sample_dtype)
-        self.nbounds = node_ranges(self.Nw, self.world)
+        self.nbounds = node_ranges(self.Nw, self.world * self.chunks_per_rank)
 
     def initWorkspaceGraph(self, clear=False, drop_device=False):
         RedundancyResolver.initWorkspaceGraph(self, clear, drop_device)
-        self.nbounds = node_ranges(self.Nw, getattr(self, "world", 1))
+        self.nbounds = node_ranges(self.Nw, getattr(self, "world", 1) * getattr(self, "chunks_per_rank", 1))
         self.edge_ids = np.zeros(0, dtype=np.int64)
         self._local_of = {}
+
+    def my_node_ranges(self):
+        """Node chunks owned by this rank: chunk c of the world*chunks_per_rank contiguous chunks -> rank c % world
+        (interleaved so that reachable / unreachable regions of the workspace are spread over the ranks)."""
+        nb = self.nbounds
+        return [(int(nb[c]), int(nb[c + 1])) for c in range(self.rank, len(nb) - 1, self.world) if nb[c + 1] > nb[c]]
 
     def _alloc_mask(self, Nq, W):
         # bitmasks only for the edge range this rank can own at most (allocated lazily per plan)
@@ -186,20 +219,26 @@ class ShardedResolver(RedundancyResolver):
         d = self._ensure_device(N)
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
         d["counters"].zero_(); d["counters_e"].zero_()
-        lo, hi = self.nbounds[self.rank], self.nbounds[self.rank + 1]
+        mine_nodes = self.my_node_ranges()
         ev[0].record()
         d["count"].zero_()
-        self._sample_phase(d, N, lo, hi)
+        if len(mine_nodes) == 1:
+            self._sample_phase(d, N, mine_nodes[0][0], mine_nodes[0][1])
+        else:
+            nodes = torch.cat([torch.arange(lo, hi, dtype=torch.int32, device=res.torch_device) for (lo, hi) in mine_nodes])
+            self._sample_phase_nodes(d, N, nodes)
         dist.all_reduce(d["count"])                       # every rank learns every node's count
         ev[1].record()
         self.attempts += N
         if connect:
             K = self.chunks_per_rank
+            edges = res.ws_edges
             cnt = d["count"].cpu().numpy()
-            eb = edge_ranges(res.ws_edges, cnt, self.world * K)                       # preliminary: by pair count
+            eb = edge_ranges(edges, cnt, self.world * K)                              # preliminary: by pair count
             chunks = rank_chunks(eb, self.world, K)
-            windows = [[node_window(res.ws_edges, a, b) for (a, b) in chunks[r]] for r in range(self.world)]
-            self.halo_bytes = exchange_halo(d["Qs"], self.rank, halo_plan(self.nbounds, windows), dist)
+            wins = node_windows(edges, eb)
+            windows = [wins[r::self.world] for r in range(self.world)]
+            self.halo_bytes = exchange_halo(d["Qs"], self.rank, halo_plan(self.nbounds, windows, self.world), dist)
             if self.rebalance and self.world > 1:
                 # 4b: exact work estimate on the preliminary chunks, then re-cut by cost
                 if d["Qs"] is not d["Q"]:
@@ -210,13 +249,22 @@ class ShardedResolver(RedundancyResolver):
                     if b > a:
                         res.chain.edges_cost(d["wedges"][a:b], d["Q"], d["count"], 0.05, cost[a:b])
                 dist.all_reduce(cost)
-                eb = ranges_by_cost(cost.cpu().numpy(), self.world * K)
+                # cut on the device: only the world*K + 1 boundaries come back to the host
+                cum = torch.cumsum(cost, 0)
+                total = int(cum[-1].item()) if self.E else 0
+                if total > 0:
+                    targets = torch.arange(1, self.world * K, device=cum.device, dtype=torch.float64) * (total / float(self.world * K))
+                    cuts = torch.searchsorted(cum.to(torch.float64), targets, right=False) + 1
+                    eb = [0] + [int(v) for v in torch.clamp(cuts, max=self.E).cpu().tolist()] + [self.E]
+                    for i in range(1, len(eb)):
+                        eb[i] = max(eb[i], eb[i - 1])
                 chunks = rank_chunks(eb, self.world, K)
-                windows = [[node_window(res.ws_edges, a, b) for (a, b) in chunks[r]] for r in range(self.world)]
-                self.halo_bytes += exchange_halo(d["Qs"], self.rank, halo_plan(self.nbounds, windows), dist)
+                wins = node_windows(edges, eb)
+                windows = [wins[r::self.world] for r in range(self.world)]
+                self.halo_bytes += exchange_halo(d["Qs"], self.rank, halo_plan(self.nbounds, windows, self.world), dist)
             mine = chunks[self.rank]
             self.edge_ids = np.concatenate([np.arange(a, b, dtype=np.int64) for (a, b) in mine]) if mine else np.zeros(0, dtype=np.int64)
-            self._local_of = {int(e): k for k, e in enumerate(self.edge_ids.tolist())}
+            self._local_of = None                      # built on demand by _edge_qlist
             ne = int(self.edge_ids.shape[0])
             W = (self.Nq + 31) // 32
             d["mask"] = torch.zeros((ne, self.Nq, W), dtype=torch.int32, device=res.torch_device)
@@ -231,12 +279,14 @@ class ShardedResolver(RedundancyResolver):
         ev[2].record()
         torch.cuda.synchronize(res.torch_device)
         self._invalidate()
-        self._collect_stats(d, ev, N, 0, n_nodes=hi - lo)
+        self._collect_stats(d, ev, N, 0)
         self.stats["halo_bytes"] = self.halo_bytes
-        self.stats["sampled"] = int(d["count"][lo:hi].sum().item())
+        self.stats["sampled"] = int(sum(int(d["count"][lo:hi].sum().item()) for (lo, hi) in mine_nodes))
         return self.stats["t_sample"], self.stats["t_connect"]
 
     def _edge_qlist(self, e):
+        if self._local_of is None:
+            self._local_of = {int(g): k for k, g in enumerate(self.edge_ids.tolist())}
         if e not in self._local_of:
             raise KeyError("workspace edge %d is owned by another rank" % e)
         if e not in self._ecache:
@@ -249,9 +299,11 @@ class ShardedResolver(RedundancyResolver):
     def download(self):
         torch = self.resolution._torch()
         d = self._dev
-        lo, hi = self.nbounds[self.rank], self.nbounds[self.rank + 1]
         out, nbytes = {}, 0
-        for k, t in (("Qs", d["Qs"][lo:hi]), ("count", d["count"][lo:hi]), ("mask", d["mask"])):
+        items = [("mask", d["mask"])]
+        for c, (lo, hi) in enumerate(self.my_node_ranges()):
+            items += [("Qs%d" % c, d["Qs"][lo:hi]), ("count%d" % c, d["count"][lo:hi])]
+        for k, t in items:
             h = self._pinned_like(k, t)
             h.copy_(t, non_blocking=True)
             out[k] = h

@@ -386,6 +386,28 @@ class RedundancyResolver:
         res.chain.dedup(q_raw, status, DEDUP_THRESHOLD, d["Qs"][lo:hi], d["count"][lo:hi], Nq=N, count_in=count_in)
         self._last_raw = (q_raw, status, iters)
 
+    def _sample_phase_nodes(self, d, N, nodes):
+        """Same for an arbitrary node list (device int32 tensor): one launch over the gathered nodes, dedup into a
+        compact buffer, whole node blocks scattered back (used by the interleaved shards of ShardedResolver)."""
+        torch = self.resolution._torch()
+        res = self.resolution
+        sdt = self._sdt()
+        nn = int(nodes.shape[0])
+        if nn == 0:
+            return
+        Nqp_raw = _cabi.round_up4(N)
+        idx = nodes.long()
+        q_raw = torch.empty((nn, res.chain.n, Nqp_raw), dtype=sdt, device=res.torch_device)
+        status = torch.empty((nn, Nqp_raw), dtype=torch.uint8, device=res.torch_device)
+        res.chain.ik_sample(d["params_s"][idx].contiguous(), d["uid"][idx].contiguous(), self.seed, q_raw, status, None,
+                            d["counters"], Nq=N, sample_offset=self.attempts)
+        kept = torch.empty((nn, res.chain.n, d["Qs"].shape[2]), dtype=sdt, device=res.torch_device)
+        kcount = torch.empty(nn, dtype=torch.int32, device=res.torch_device)
+        _cabi.gather_node_blocks(nodes, d["Qs"], d["count"], kept, kcount)
+        cin = kcount.clone()
+        res.chain.dedup(q_raw, status, DEDUP_THRESHOLD, kept, kcount, Nq=N, count_in=cin)
+        _cabi.scatter_node_blocks(nodes, kept, kcount, d["Qs"], d["count"])
+
     def _connect_phase(self, d, old_counts):
         res = self.resolution
         if d["Qs"] is not d["Q"]:

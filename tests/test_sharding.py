@@ -39,18 +39,24 @@ def test_partition_properties(world):
         chunks = sharding.rank_chunks(ebk, world, K)
         assert sorted(c for ch in chunks for c in ch) == [(ebk[i], ebk[i + 1]) for i in range(world * K)]
         windows = [[sharding.node_window(edges, a, b) for (a, b) in chunks[r]] for r in range(world)]
-        plan = sharding.halo_plan(nb, windows)
-        for r in range(world):
-            need = np.unique(np.concatenate([edges[a:b].reshape(-1) for (a, b) in chunks[r]] + [np.zeros(0, dtype=edges.dtype)]))
-            have = np.zeros(Nw, dtype=bool)
-            have[nb[r]:nb[r + 1]] = True
-            for (p, rr), segs in plan.items():
-                assert p != rr
-                for (a, b) in segs:
-                    assert nb[p] <= a < b <= nb[p + 1]                                  # sender owns the slab
-                    if rr == r:
-                        have[a:b] = True
-            assert have[need.astype(np.int64)].all()
+        wins = sharding.node_windows(edges, ebk)
+        assert [wins[r::world] for r in range(world)] == windows                      # vectorised == per chunk
+        for Kn in (1, 3):                                                               # node chunks per rank
+            nbk = sharding.node_ranges(Nw, world * Kn)
+            owner = np.empty(Nw, dtype=np.int64)
+            for c in range(world * Kn):
+                owner[nbk[c]:nbk[c + 1]] = c % world
+            plan = sharding.halo_plan(nbk, windows, world)
+            for r in range(world):
+                need = np.unique(np.concatenate([edges[a:b].reshape(-1) for (a, b) in chunks[r]] + [np.zeros(0, dtype=edges.dtype)]))
+                have = owner == r
+                for (p, rr), segs in plan.items():
+                    assert p != rr
+                    for (a, b) in segs:
+                        assert a < b and (owner[a:b] == p).all()                        # sender owns the slab
+                        if rr == r:
+                            have[a:b] = True
+                assert have[need.astype(np.int64)].all()
     own = sharding.owner_of(np.arange(Nw), nb)
     assert all(nb[o] <= i < nb[o + 1] for i, o in enumerate(own))
     # cost-based re-cut (step 4b): contiguous, covering, balanced within one edge's cost
@@ -71,21 +77,23 @@ def _worker(rank, world, port, ok):
     try:
         params, edges, count = _graph()
         Nw, n, Nqp = params.shape[0], 3, 8
-        nb = sharding.node_ranges(Nw, world)
-        # "sampling": every rank fills only the nodes it owns; counts via all-reduce as in ShardedResolver
+        Kn = 2
+        nb = sharding.node_ranges(Nw, world * Kn)
+        # "sampling": every rank fills only the node chunks it owns (chunk c -> rank c % world); counts via all-reduce
         Q = torch.zeros((Nw, n, Nqp), dtype=torch.float32)
         cnt = torch.zeros(Nw, dtype=torch.int32)
-        lo, hi = nb[rank], nb[rank + 1]
-        ids = torch.arange(lo, hi, dtype=torch.float32)
-        Q[lo:hi] = ids[:, None, None] + 0.001 * torch.arange(n)[None, :, None] + 1e-5 * torch.arange(Nqp)[None, None, :]
-        cnt[lo:hi] = torch.from_numpy(count[lo:hi])
+        for c in range(rank, world * Kn, world):
+            lo, hi = nb[c], nb[c + 1]
+            ids = torch.arange(lo, hi, dtype=torch.float32)
+            Q[lo:hi] = ids[:, None, None] + 0.001 * torch.arange(n)[None, :, None] + 1e-5 * torch.arange(Nqp)[None, None, :]
+            cnt[lo:hi] = torch.from_numpy(count[lo:hi])
         dist.all_reduce(cnt)
         assert (cnt.numpy() == count).all()
         K = 3
         eb = sharding.edge_ranges(edges, cnt.numpy(), world * K)
         chunks = sharding.rank_chunks(eb, world, K)
         windows = [[sharding.node_window(edges, a, b) for (a, b) in chunks[r]] for r in range(world)]
-        plan = sharding.halo_plan(nb, windows)
+        plan = sharding.halo_plan(nb, windows, world)
         nbytes = sharding.exchange_halo(Q, rank, plan, dist)
         need = np.unique(np.concatenate([edges[a:b].reshape(-1) for (a, b) in chunks[rank]]))
         expect = (torch.from_numpy(need).float()[:, None, None] + 0.001 * torch.arange(n)[None, :, None]

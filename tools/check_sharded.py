@@ -21,8 +21,8 @@ if rank == 0:
     rr.sampleConfigurationSpace(Nq, order_independent=True)
     assert torch.equal(cnt, rr._dev["count"]), "counts differ"
     assert torch.equal(full, rr._dev["mask"]), "edge masks differ"
-    lo, hi = sr.nbounds[0], sr.nbounds[1]
-    assert torch.equal(sr._dev["Qs"][lo:hi], rr._dev["Qs"][lo:hi])
+    for (lo, hi) in sr.my_node_ranges():
+        assert torch.equal(sr._dev["Qs"][lo:hi], rr._dev["Qs"][lo:hi])
     assert int(pairs.item()) == rr.stats["pairs"], (pairs.item(), rr.stats["pairs"])
     print("sharded == single GPU: world=%d nodes=%d edges=%d pairs=%d halo_bytes(rank0)=%d chunks=%d" % (world, sr.Nw, sr.E, rr.stats["pairs"], sr.halo_bytes, sr.chunks_per_rank))
 dist.barrier()
