@@ -145,6 +145,31 @@ def cpu_sample_run(res, o, Nq, seed, n_edges, rng):
             "edges_only_per_s": pairs / max(tc, 1e-12)}
 
 
+def python_loop_estimate(grr, o_unused=None, budget_s=2.0):
+    """the oracle called one validEdge at a time from a Python loop on config 1 (planar_3R grid,
+    Nq=10) -- an ESTIMATE of the interpreter-bound regime of the real reference, which crosses the Python/C++
+    boundary several times per interpolated IK point.  Returns validEdge calls per second."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from helpers import oracle_for
+    pdef, res = grr.load_problem("planar_3R", "baseline_cfg1.json")
+    res.sampleWorkspace(pdef["Nw"], method=pdef["workspace_graph"])
+    o = oracle_for(res)
+    mid = res.ws_params.shape[0] // 2
+    nodes = np.arange(mid - 40, mid + 40)
+    out = o.sample_nodes(res.ws_params[nodes], nodes.astype(np.int32), pdef["Nq"], 0, raw=False)
+    e = res.ws_edges
+    sel = e[(e[:, 0] >= nodes[0]) & (e[:, 1] <= nodes[-1])] - nodes[0]
+    calls, t0 = 0, time.perf_counter()
+    for (i, j) in sel.tolist():
+        for a in range(out["count"][i]):
+            for b in range(out["count"][j]):
+                o.valid_edge(out["q_kept"][i, a], out["q_kept"][j, b], res.ws_params[nodes[i]], res.ws_params[nodes[j]])
+                calls += 1
+        if time.perf_counter() - t0 > budget_s:
+            break
+    return calls / max(time.perf_counter() - t0, 1e-9)
+
+
 def cpu_calibrate(res, o, Nq, seconds, rng):
     probe = cpu_sample_run(res, o, Nq, 0, 24, rng)
     per_edge = (probe["t_sample"] + probe["t_connect"]) / probe["edges"]
@@ -341,7 +366,11 @@ def run_cuda(args):
                "sample": "%d workspace edges drawn uniformly at random (+ their %d endpoint nodes) of %d edges / %d nodes, %.1f s of "
                          "wall time; value = whole-job extrapolation pairs*E/e / (t_sample*Nw/n + t_connect*E/e)" % (
                              n_edges, r["nodes"], rr.E, rr.Nw, r["t_sample"] + r["t_connect"]),
-               "ik_configs_per_s": r["ik_configs_per_s"], "edges_only_per_s": r["edges_only_per_s"]}
+               "ik_configs_per_s": r["ik_configs_per_s"], "edges_only_per_s": r["edges_only_per_s"],
+               "python_loop_estimate_cfg1_valid_edge_calls_per_s": python_loop_estimate(grr),
+               "python_loop_note": "ESTIMATE: the oracle called one validEdge at a time from a Python loop on config 1 "
+                                   "(planar_3R, Nq=10), 1 thread -- the real reference is slower still (several "
+                                   "Python<->C++ crossings per interpolated IK point)"}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong" if args.strong else "weak",
