@@ -15,7 +15,7 @@ import numpy as np
 
 from . import _cabi, so3
 from .robot import RobotChain
-from .workspace import Graph, build_workspace_graph, explicit_product_graph
+from .workspace import Graph, build_workspace_graph
 
 DEFAULT_EDGE_CHECK_TOLERANCE = 5e-2          # grr/graph.py:19
 

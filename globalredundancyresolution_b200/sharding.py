@@ -33,7 +33,6 @@ from __future__ import annotations
 
 import numpy as np
 
-from . import _cabi
 from .solver import RedundancyResolver
 
 

@@ -611,7 +611,6 @@ class RedundancyResolver:
         if istart or jstart:
             old = np.zeros(self.Nw, dtype=np.int32)
             old[iw], old[jw] = istart, jstart
-        before = set(self._edge_qlist(e)) if old is not None else set()
         self._connect([e], old)
         after = self._edge_qlist(e)
         if old is None:
