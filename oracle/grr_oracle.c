@@ -321,6 +321,9 @@ static void damped_step(const double *J, const double *F, int m, int n, double l
   }
 }
 
+/* exported for the test that pins the stated equivalence with the SVD damped back-substitution */
+void orc_damped_step(const double *J, const double *F, int m, int n, double lambda, double *p) { damped_step(J, F, m, n, lambda, p); }
+
 /* One IK solve from seed x (in/out).  Returns status. */
 int orc_ik_solve(const orc_chain *c, const double *w, double *x, orc_ikinfo *info) {
   const int n = c->n, m = resid_rows(c);

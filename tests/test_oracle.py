@@ -159,3 +159,25 @@ def test_workspace_interpolate_variable():
     task = grr.IKTask(None, [0, 0, 0], "variable")
     for u in (0.25, 0.5, 0.8):
         np.testing.assert_allclose(o.workspace_interpolate(wa, wb, u), task.interpolate(list(wa), list(wb), u), atol=1e-10)
+
+
+def test_damped_step_equals_svd_back_substitution():
+    """p = -J^T (J J^T + lambda^2 I)^-1 F (Cholesky, what oracle and kernels compute) is the SVD damped
+    back-substitution p = -V diag(w_i / (w_i^2 + lambda^2)) U^T F of SURVEY A.3, including rank-deficient J
+    (planar chains: the y row of the position Jacobian is identically zero)."""
+    L = O.lib()
+    rng = np.random.default_rng(0)
+    dp = C.POINTER(C.c_double)
+    for m, n in ((3, 3), (3, 20), (6, 7), (6, 6)):
+        for trial in range(20):
+            J = rng.normal(size=(m, n))
+            if trial % 3 == 0:
+                J[1, :] = 0.0                                   # rank deficient
+            F = rng.normal(size=m)
+            lam = 0.01
+            p = np.zeros(n)
+            Jc, Fc = np.ascontiguousarray(J), np.ascontiguousarray(F)
+            L.orc_damped_step(Jc.ctypes.data_as(dp), Fc.ctypes.data_as(dp), C.c_int(m), C.c_int(n), C.c_double(lam), p.ctypes.data_as(dp))
+            U, w, Vt = np.linalg.svd(J, full_matrices=False)
+            p_svd = -(Vt.T * (w / (w * w + lam * lam))) @ (U.T @ F)
+            np.testing.assert_allclose(p, p_svd, rtol=1e-7, atol=1e-9)
