@@ -90,7 +90,7 @@ def lib():
 def check(rc, what):
     global LAUNCHES
     if what not in ("grr_chain_create", "grr_task_set", "grr_fp32_peak", "grr_fp32x2_peak"):
-        LAUNCHES += 1
+        LAUNCHES += 2 if what == "grr_edges_build" else 1      # edges_build = k_edge_load + k_edges_build
     if rc != 0:
         raise GrrError("%s failed (%d): %s" % (what, rc, lib().grr_last_error().decode()))
 
