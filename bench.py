@@ -400,7 +400,7 @@ def main():
     ap.add_argument("--problem", default="planar_20R/baseline_cfg2.json")
     ap.add_argument("--nw", type=int, default=0, help="override Nw (profiling runs; reported in config.workload)")
     ap.add_argument("--nq", type=int, default=0)
-    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU work per reference step / cpu_baseline sample")
+    ap.add_argument("--cpu-seconds", type=float, default=30.0, help="CPU work per reference step / cpu_baseline sample")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--strong", action="store_true", help="keep the problem size fixed at N > 1 (default: weak scaling, Nw x N)")
     ap.add_argument("--e2e-rebuild", action="store_true", help="rebuild the problem objects inside the e2e region")
