@@ -40,6 +40,8 @@ __device__ __forceinline__ float abs_(float a) { return fabsf(a); }
 __device__ __forceinline__ double abs_(double a) { return fabs(a); }
 __device__ __forceinline__ float max_(float a, float b) { return fmaxf(a, b); }
 __device__ __forceinline__ double max_(double a, double b) { return fmax(a, b); }
+__device__ __forceinline__ float fma_(float a, float b, float c) { return fmaf(a, b, c); }
+__device__ __forceinline__ double fma_(double a, double b, double c) { return fma(a, b, c); }
 __device__ __forceinline__ float min_(float a, float b) { return fminf(a, b); }
 __device__ __forceinline__ double min_(double a, double b) { return fmin(a, b); }
 __device__ __forceinline__ float ceil_(float a) { return ceilf(a); }

@@ -52,7 +52,7 @@ k_ik_instances(const __grid_constant__ ChainDev<Real, kMaxJ> c, long long total,
   Target<Real, M> tg;
   tg.x[0] = tg.x[1] = tg.x[2] = 0;
   if (M == 6) { for (int k = 0; k < 9; k++) tg.R[k] = (k % 4 == 0) ? Real(1) : Real(0); }
-  for (int j = 0; j < 4 * n; j++) mem.base[j * mem.T] = 0;
+  for (int j = 0; j < lane_reals<col_rows(M, PL)>(n); j++) mem.base[j * mem.T] = 0;
   LaneCounters cnt;
   long long inst = -1;
   bool done = false;
@@ -91,7 +91,7 @@ k_ik_instances(const __grid_constant__ ChainDev<Real, kMaxJ> c, long long total,
     }
     if (__all_sync(0xffffffffu, inst < 0)) break;
     PassOut<Real, M> o;
-    if constexpr (PL) lane_pass_planar<Real, false>(c, tg, L.src, mem, nullptr, 0, o);
+    if constexpr (PL) lane_pass_planar<Real, false>(c, tg, L, mem, nullptr, 0, o);
     else lane_pass<Real, M, false>(c, tg, L.src, mem, nullptr, 0, o);
     const int st = lane_step<Real, M, PL>(c, L, mem, o, inst >= 0);
     if (inst >= 0) {
@@ -141,7 +141,7 @@ k_ik_level(const __grid_constant__ ChainDev<Real, kMaxJ> c, long long total, con
   Target<Real, M> tg;
   tg.x[0] = tg.x[1] = tg.x[2] = 0;
   if (M == 6) { for (int k = 0; k < 9; k++) tg.R[k] = (k % 4 == 0) ? Real(1) : Real(0); }
-  for (int j = 0; j < 4 * n; j++) mem.base[j * mem.T] = 0;
+  for (int j = 0; j < lane_reals<col_rows(M, PL)>(n); j++) mem.base[j * mem.T] = 0;
   LaneCounters cnt;
   long long li = -1;
   int col = 0;
@@ -179,7 +179,7 @@ k_ik_level(const __grid_constant__ ChainDev<Real, kMaxJ> c, long long total, con
     }
     if (__all_sync(0xffffffffu, li < 0)) break;
     PassOut<Real, M> o;
-    if constexpr (PL) lane_pass_planar<Real, false>(c, tg, L.src, mem, nullptr, 0, o);
+    if constexpr (PL) lane_pass_planar<Real, false>(c, tg, L, mem, nullptr, 0, o);
     else lane_pass<Real, M, false>(c, tg, L.src, mem, nullptr, 0, o);
     const int st = lane_step<Real, M, PL>(c, L, mem, o, li >= 0);
     if (li >= 0 && st != IK_RUNNING) {
@@ -257,7 +257,7 @@ k_valid_edge_batch(const __grid_constant__ ChainDev<Real, kMaxJ> c, long long to
   const Real thr2 = thr * thr;
   LaneIK<Real, M> L;
   lane_begin_mem(L, mem);
-  for (int j = 0; j < 4 * n; j++) mem.base[j * mem.T] = 0;
+  for (int j = 0; j < lane_reals<col_rows(M, PL)>(n); j++) mem.base[j * mem.T] = 0;
   PairLane<Real> P;
   WInterp<Real, M> W;
   Target<Real, M> tg;
@@ -286,7 +286,7 @@ k_valid_edge_batch(const __grid_constant__ ChainDev<Real, kMaxJ> c, long long to
     if (__any_sync(0xffffffffu, running)) {
       PassOut<Real, M> o;
       const bool first = running && P.k == 1;
-      if constexpr (PL) lane_pass_planar<Real, true>(c, tg, L.src, mem, first ? P.qa : mem.prev(), first ? P.sa : mem.T, o);
+      if constexpr (PL) lane_pass_planar<Real, true>(c, tg, L, mem, first ? P.qa : mem.prev(), first ? P.sa : mem.T, o);
       else lane_pass<Real, M, true>(c, tg, L.src, mem, first ? P.qa : mem.prev(), first ? P.sa : mem.T, o);
       const int st = lane_step<Real, M, PL>(c, L, mem, o, running);
       if (running && st != IK_RUNNING) {
@@ -354,7 +354,7 @@ k_edges_build(const __grid_constant__ ChainDev<Real, kMaxJ> c, const int32_t *__
   }
   LaneMem<Real, col_rows(M, PL)> mem;
   mem.init(lanes + threadIdx.x, (int)blockDim.x, n);
-  for (int j = 0; j < 4 * n; j++) mem.base[j * mem.T] = 0;
+  for (int j = 0; j < lane_reals<col_rows(M, PL)>(n); j++) mem.base[j * mem.T] = 0;
   __syncthreads();
   LaneCounters cnt;
   if (total) {
@@ -397,7 +397,7 @@ k_edges_build(const __grid_constant__ ChainDev<Real, kMaxJ> c, const int32_t *__
       if (__any_sync(0xffffffffu, running)) {
         PassOut<Real, M> o;
         const bool first = running && P.k == 1;
-        if constexpr (PL) lane_pass_planar<Real, true>(c, tg, L.src, mem, first ? P.qa : mem.prev(), first ? P.sa : mem.T, o);
+        if constexpr (PL) lane_pass_planar<Real, true>(c, tg, L, mem, first ? P.qa : mem.prev(), first ? P.sa : mem.T, o);
         else lane_pass<Real, M, true>(c, tg, L.src, mem, first ? P.qa : mem.prev(), first ? P.sa : mem.T, o);
         const int st = lane_step<Real, M, PL>(c, L, mem, o, running);
         if (running && st != IK_RUNNING) {

@@ -106,13 +106,17 @@ template <typename Real, int M>
 struct LaneIK {
   Real fold, slope, alam, alam2, f2, alamin, stpmax, resid;
   int it, evals, phase;
+  // planar path: the Newton step is folded into the next chain pass.  `first` = that pass derives the
+  // direction p_j = -col_j . y from the Jacobian columns still in memory (ny = -y) and stores it.
+  bool first, check_convx;
+  Real ny[2];
   XSrc<Real> src;
   const Real *res;   // after a final status: the solution, res[j * T]
 };
 
 template <typename Real, int M>
 __device__ __forceinline__ void lane_reset(LaneIK<Real, M> &L) {
-  L.it = 0; L.evals = 0; L.phase = 0;
+  L.it = 0; L.evals = 0; L.phase = 0; L.first = false; L.check_convx = false; L.ny[0] = 0; L.ny[1] = 0;
   L.alam = 0; L.alam2 = 0; L.f2 = 0; L.fold = 0; L.slope = 0; L.alamin = 0; L.stpmax = 0; L.resid = 0;
 }
 // Start an instance whose seed is lerp(qa, qb, u) read from (a, b) with strides (sa, sb).
@@ -159,6 +163,7 @@ struct PassOut {
   Real Fw[M], FL[M], f, fmax, xn2;
   Real s2;                         // |x - xref|^2 when a reference config is given
   Real S[M * (M + 1) / 2];
+  Real pn2, test, testx;           // planar path, first trial of a Newton step: |p|^2, max |p_j|/max(|x_j|,1), max |dx_j|/max(|x_j|,1)
 };
 
 // xref (stride sref): config against which the joint-space distance of the trial point is accumulated
@@ -167,40 +172,51 @@ struct PassOut {
 // goal-link frame equals the last joint frame (the reference's planar_{2,3,5,10,20}R robots).  G stays a
 // rotation about y, kept as (cos, sin); columns have two in-plane components (x, z); the normal matrix is
 // 2x2.  Same algorithm, a third of the arithmetic.
-template <typename Real, bool WITH_REF, typename ChainT>
-__device__ __forceinline__ void lane_pass_planar(const ChainT &c, const Target<Real, 3> &tg, const XSrc<Real> &src,
-                                                 const LaneMem<Real, 2> &mem, const Real *xref, int sref,
-                                                 PassOut<Real, 3> &o) {
+template <typename Real, bool WITH_REF, bool SMALL, typename ChainT>
+__device__ __forceinline__ void lane_pass_planar_(const ChainT &c, const Target<Real, 3> &tg, const LaneIK<Real, 3> &L,
+                                                  const LaneMem<Real, 2> &mem, const Real *xref, int sref,
+                                                  PassOut<Real, 3> &o) {
   const int n = c.n;
+  const XSrc<Real> &src = L.src;
   // in-plane components: I1 = z (index 2), I2 = x (index 0); Rot_y(t): z' = c z - s x, x' = s z + c x
   Real vz = c.ee[2], vx = c.ee[0], vy = c.ee[1];
   Real gc = 1, gs = 0;                       // G = Rot_y(phi): (cos phi, sin phi)
   Real S11 = 0, S12 = 0, S22 = 0, xn2 = 0, s2 = 0;
+  Real pn2 = 0, test = 0, testx = 0;
   const int T = mem.T;
-  const Real *pa = src.a + (n - 1) * src.sa, *pb = src.b + (n - 1) * src.sb;
+  const int sa = src.sa, sb = src.sb;
+  const Real *pa = src.a + (n - 1) * sa;
+  Real *pb = const_cast<Real *>(src.b) + (n - 1) * sb;      // written only by `first` lanes, whose b is mem.p()
   const Real *pr = WITH_REF ? xref + (n - 1) * sref : nullptr;
   Real *pc = mem.cols() + (n - 1) * 2 * T;
   Real *px = mem.xcur() + (n - 1) * T;
-  JointConst<Real> jn = c.jc[n - 1];
-  Real av_n = *pa, bv_n = *pb, rv_n = WITH_REF ? *pr : Real(0);
-  const bool small = c.small_angles != 0;
-#pragma unroll 1
-  for (int j = n - 1; j >= 0; --j) {
-    const JointConst<Real> jc = jn;
-    const Real av = av_n, bv = bv_n, rv = rv_n;
-    if (j > 0) {
-      jn = c.jc[j - 1];
-      pa -= src.sa; pb -= src.sb;
-      av_n = *pa; bv_n = *pb;
-      if (WITH_REF) { pr -= sref; rv_n = *pr; }
+  // dir = b - lk * a: the product is exact for lk in {0, 1}, so this equals (lerp ? b - a : b) bit for bit
+  const Real lk = src.lerp ? Real(1) : Real(0);
+  const Real t = src.t;
+  const bool first = L.first;
+  const Real ny0 = L.ny[0], ny1 = L.ny[1];
+  auto joint = [&](const JointConst<Real> &jc, Real av, Real bv, Real rv, Real *pbw) {
+    // first trial of a Newton step: direction from the columns of the accepted point (still in memory
+    // at this joint: they are overwritten below), stored as p for the later trials of the line search
+    const Real c1o = pc[0], c2o = pc[T], xo = *px;
+    const Real dnew = fma_(c2o, ny1, c1o * ny0);
+    const Real dir = first ? dnew : fma_(-lk, av, bv);
+    if (first) *pbw = dir;
+    pn2 = fma_(dir, dir, pn2);
+    if (SMALL) {                                        // |x_j| <= pi/4: max(|x_j|, 1) == 1
+      test = max_(test, abs_(dir));
+      testx = max_(testx, abs_(av - xo));
+    } else {
+      const Real rinv = rcp_ge1_(max_(abs_(av), Real(1)));
+      test = max_(test, abs_(dir) * rinv);
+      testx = max_(testx, abs_(av - xo) * rinv);
     }
-    const Real dir = src.lerp ? bv - av : bv;
-    const Real xj = min_(max_(av + src.t * dir, jc.bmin), jc.bmax);
+    const Real xj = min_(max_(fma_(t, dir, av), jc.bmin), jc.bmax);
     *px = xj; px -= T;
     xn2 += xj * xj;
     if (WITH_REF) { const Real d = xj - rv; s2 += d * d; }
     Real s, co;
-    if (small) sincos_small(xj, &s, &co); else sincos_joint(xj, &s, &co);
+    if (SMALL) sincos_small(xj, &s, &co); else sincos_joint(xj, &s, &co);
     s *= jc.sgn;
     // column = G^T (axis x v): axis x v = sgn (-v_x e_z + v_z e_x); G^T rotates by -phi
     const Real w1 = -jc.sgn * vx, w2 = jc.sgn * vz;
@@ -211,8 +227,30 @@ __device__ __forceinline__ void lane_pass_planar(const ChainT &c, const Target<R
     vz = nz + jc.tp[2]; vx = nx + jc.tp[0]; vy += jc.tp[1];
     const Real ngc = co * gc - s * gs, ngs = s * gc + co * gs;
     gc = ngc; gs = ngs;
+  };
+  // two joints per trip with two named operand sets: the next joint's constants (an indexed constant-bank
+  // load) and shared-memory operands are in flight while the current joint is computed, and no register
+  // rotation is needed
+  int j = n - 1;
+  JointConst<Real> jcA = c.jc[j], jcB;
+  Real aA = *pa, bA = *pb, rA = WITH_REF ? *pr : Real(0), aB, bB, rB = 0;
+  Real *wA = pb, *wB;
+#pragma unroll 1
+  for (; j >= 1; j -= 2) {
+    jcB = c.jc[j - 1];
+    pa -= sa; pb -= sb; aB = *pa; bB = *pb; wB = pb;
+    if (WITH_REF) { pr -= sref; rB = *pr; }
+    joint(jcA, aA, bA, rA, wA);
+    if (j >= 2) {
+      jcA = c.jc[j - 2];
+      pa -= sa; pb -= sb; aA = *pa; bA = *pb; wA = pb;
+      if (WITH_REF) { pr -= sref; rA = *pr; }
+    }
+    joint(jcB, aB, bB, rB, wB);
   }
+  if (j == 0) joint(jcA, aA, bA, rA, wA);
   o.xn2 = xn2; o.s2 = s2;
+  o.pn2 = pn2; o.test = test; o.testx = testx;
   o.Fw[0] = vx - tg.x[0]; o.Fw[1] = vy - tg.x[1]; o.Fw[2] = vz - tg.x[2];
   o.f = Real(0.5) * (o.Fw[0] * o.Fw[0] + o.Fw[1] * o.Fw[1] + o.Fw[2] * o.Fw[2]);
   // goal-link frame residual, in-plane part: (z, x) rotated by -phi
@@ -221,6 +259,13 @@ __device__ __forceinline__ void lane_pass_planar(const ChainT &c, const Target<R
   o.FL[2] = o.Fw[1];
   o.S[0] = S11; o.S[1] = S12; o.S[2] = S22;
   o.fmax = max_(max_(abs_(o.Fw[0]), abs_(o.Fw[1])), abs_(o.Fw[2]));
+}
+template <typename Real, bool WITH_REF, typename ChainT>
+__device__ __forceinline__ void lane_pass_planar(const ChainT &c, const Target<Real, 3> &tg, const LaneIK<Real, 3> &L,
+                                                 const LaneMem<Real, 2> &mem, const Real *xref, int sref,
+                                                 PassOut<Real, 3> &o) {
+  if (c.small_angles != 0) lane_pass_planar_<Real, WITH_REF, true>(c, tg, L, mem, xref, sref, o);
+  else lane_pass_planar_<Real, WITH_REF, false>(c, tg, L, mem, xref, sref, o);
 }
 
 template <typename Real, int M, bool WITH_REF, typename ChainT>
@@ -348,6 +393,110 @@ __device__ __forceinline__ void chol_solve_fast(Real (&A)[M * (M + 1) / 2], cons
   }
 }
 
+// Numerical Recipes lnsrch backtracking: the next trial step length after a rejected trial
+template <typename Real, int M>
+__device__ __forceinline__ void lane_backtrack(LaneIK<Real, M> &L, Real f) {
+  Real tmplam;
+  if (L.alam == Real(1)) tmplam = -L.slope / (Real(2) * (f - L.fold - L.slope));
+  else {
+    const Real rhs1 = f - L.fold - L.alam * L.slope, rhs2 = L.f2 - L.fold - L.alam2 * L.slope;
+    const Real a = (rhs1 / (L.alam * L.alam) - rhs2 / (L.alam2 * L.alam2)) / (L.alam - L.alam2);
+    const Real b = (-L.alam2 * rhs1 / (L.alam * L.alam) + L.alam * rhs2 / (L.alam2 * L.alam2)) / (L.alam - L.alam2);
+    if (a == Real(0)) tmplam = -L.slope / (Real(2) * b);
+    else {
+      const Real disc = b * b - Real(3) * a * L.slope;
+      if (disc < Real(0)) tmplam = Real(0.5) * L.alam;
+      else if (b <= Real(0)) tmplam = (-b + sqrt_(disc)) / (Real(3) * a);
+      else tmplam = -L.slope / (b + sqrt_(disc));
+    }
+    if (tmplam > Real(0.5) * L.alam) tmplam = Real(0.5) * L.alam;
+  }
+  L.alam2 = L.alam; L.f2 = f;
+  L.alam = max_(tmplam, Real(0.1) * L.alam);
+  L.src.t = L.alam;
+}
+
+// ---- planar transition: no joint loop.  A new Newton iteration only solves the 2x2 normal equations
+// and arms `first`; the next chain pass derives p from the stored columns, writes it, evaluates the first
+// trial point and returns |p|, the step-size tests and the x-convergence test, which are then checked
+// here in the order of the reference algorithm (convergence on x, iteration limit, step clipping,
+// descent test) before that pass is used as the first line-search evaluation.  slope = g.p is taken in
+// closed form: g = J^T F, p = -J^T y  =>  g.p = -F^T (J J^T) y = -FL^T S y.
+template <typename Real, typename ChainT>
+__device__ __forceinline__ int lane_step_planar(const ChainT &c, LaneIK<Real, 3> &L, LaneMem<Real, 2> &mem,
+                                                const PassOut<Real, 3> &o, bool active) {
+  const int n = c.n;
+  const Real tolf = c.tol, tolx = Real(0.01) * c.tol, ALF = Real(1e-4);
+  int st = IK_RUNNING;
+  if (!active) return st;
+  bool search = true, newstep = false, check_convx = false;
+  L.evals++;
+  if (L.first) {
+    L.first = false;
+    if (L.check_convx && o.testx < tolx) st = IK_CONVX;
+    else if (L.check_convx && L.it >= c.max_iters) st = IK_MAXIT;
+    else {
+      Real test = o.test;
+      const Real pn = sqrt_(o.pn2);
+      if (pn > L.stpmax) {
+        // clip the step to stpmax (rare): rescale p in memory and evaluate its first trial again
+        const Real sc = L.stpmax / pn;
+        test = 0;
+        const int T = mem.T;
+        Real *pp = mem.p();
+        const Real *px = mem.xold();
+#pragma unroll 1
+        for (int j = 0; j < n; j++) {
+          const Real pj = pp[j * T] * sc;
+          pp[j * T] = pj;
+          test = max_(test, abs_(pj) / max_(abs_(px[j * T]), Real(1)));
+        }
+        L.slope *= sc;
+        search = false;
+      }
+      if (!(L.slope < Real(0))) { L.it++; st = IK_STALL; }
+      else L.alamin = fdiv_(tolx, test);
+    }
+    if (st != IK_RUNNING || !search) L.evals--;       // that pass was not an evaluation of the algorithm
+    if (st != IK_RUNNING) L.res = mem.xold();
+  }
+  if (st == IK_RUNNING && search) {
+    L.resid = o.fmax;
+    L.res = mem.xcur();
+    if (L.phase == 0) {
+      if (o.fmax < tolf) st = IK_OK;
+      else if (c.max_iters <= 0) st = IK_MAXIT;
+      else { L.stpmax = Real(10) * max_(sqrt_(o.xn2), Real(n)); newstep = true; }
+    } else if (L.alam < L.alamin) {
+      L.it++; L.res = mem.xold(); st = IK_STALL;                        // x <- xold
+    } else if (!(o.f <= L.fold + ALF * L.alam * L.slope)) {
+      lane_backtrack(L, o.f);
+    } else {
+      L.it++;
+      if (o.fmax < tolf) st = IK_OK;
+      else { newstep = true; check_convx = true; }
+    }
+  }
+  if (newstep) {
+    // the accepted point (in xcur) becomes the origin of the next line search: swap roles, no copy
+    { const int t = mem.o_xold; mem.o_xold = mem.o_xcur; mem.o_xcur = t; }
+    // 2x2 in-plane normal equations (the out-of-plane row has no Jacobian)
+    const Real l2 = c.lambda * c.lambda;
+    const Real a11 = o.S[0] + l2, a12 = o.S[1], a22 = o.S[2] + l2;
+    const Real idet = fdiv_(Real(1), a11 * a22 - a12 * a12);
+    const Real y0 = (a22 * o.FL[0] - a12 * o.FL[1]) * idet;
+    const Real y1 = (a11 * o.FL[1] - a12 * o.FL[0]) * idet;
+    L.ny[0] = -y0; L.ny[1] = -y1;
+    L.slope = -(o.FL[0] * (o.S[0] * y0 + o.S[1] * y1) + o.FL[1] * (o.S[1] * y0 + o.S[2] * y1));
+    L.first = true; L.check_convx = check_convx;
+    L.fold = o.f; L.alam = 1; L.alam2 = 0; L.f2 = 0; L.alamin = 0;
+    L.src.a = mem.xold(); L.src.b = mem.p(); L.src.sa = mem.T; L.src.sb = mem.T; L.src.t = 1; L.src.lerp = false;
+    L.res = mem.xold();
+    L.phase = 1;
+  }
+  return st;
+}
+
 // ---- the transition: line search bookkeeping and, if a new iteration starts, the Newton step ----
 // Called by ALL lanes of the warp (`active` = this lane holds a running instance) so that the lanes
 // that start a new iteration execute the step loop together whatever path took them there.
@@ -355,6 +504,7 @@ __device__ __forceinline__ void chol_solve_fast(Real (&A)[M * (M + 1) / 2], cons
 template <typename Real, int M, bool PL, typename ChainT>
 __device__ __forceinline__ int lane_step(const ChainT &c, LaneIK<Real, M> &L, LaneMem<Real, col_rows(M, PL)> &mem,
                                          const PassOut<Real, M> &o, bool active) {
+  if constexpr (PL) return lane_step_planar(c, L, mem, o, active);
   constexpr int MC = col_rows(M, PL);
   const int n = c.n;
   const Real tolf = c.tol, tolx = Real(0.01) * c.tol, ALF = Real(1e-4);
@@ -371,24 +521,7 @@ __device__ __forceinline__ int lane_step(const ChainT &c, LaneIK<Real, M> &L, La
     } else if (L.alam < L.alamin) {
       L.it++; L.res = mem.xold(); st = IK_STALL;                        // x <- xold
     } else if (!(o.f <= L.fold + ALF * L.alam * L.slope)) {
-      Real tmplam;                                                       // backtrack (Numerical Recipes lnsrch)
-      if (L.alam == Real(1)) tmplam = -L.slope / (Real(2) * (o.f - L.fold - L.slope));
-      else {
-        const Real rhs1 = o.f - L.fold - L.alam * L.slope, rhs2 = L.f2 - L.fold - L.alam2 * L.slope;
-        const Real a = (rhs1 / (L.alam * L.alam) - rhs2 / (L.alam2 * L.alam2)) / (L.alam - L.alam2);
-        const Real b = (-L.alam2 * rhs1 / (L.alam * L.alam) + L.alam * rhs2 / (L.alam2 * L.alam2)) / (L.alam - L.alam2);
-        if (a == Real(0)) tmplam = -L.slope / (Real(2) * b);
-        else {
-          const Real disc = b * b - Real(3) * a * L.slope;
-          if (disc < Real(0)) tmplam = Real(0.5) * L.alam;
-          else if (b <= Real(0)) tmplam = (-b + sqrt_(disc)) / (Real(3) * a);
-          else tmplam = -L.slope / (b + sqrt_(disc));
-        }
-        if (tmplam > Real(0.5) * L.alam) tmplam = Real(0.5) * L.alam;
-      }
-      L.alam2 = L.alam; L.f2 = o.f;
-      L.alam = max_(tmplam, Real(0.1) * L.alam);
-      L.src.t = L.alam;
+      lane_backtrack(L, o.f);
     } else {
       L.it++;
       if (o.fmax < tolf) st = IK_OK;
