@@ -92,7 +92,7 @@ k_ik_instances(const __grid_constant__ ChainDev<Real, kMaxJ> c, long long total,
     if (__all_sync(0xffffffffu, inst < 0)) break;
     PassOut<Real, M> o;
     if constexpr (PL) lane_pass_planar<Real, false>(c, tg, L, mem, nullptr, 0, o);
-    else lane_pass<Real, M, false>(c, tg, L.src, mem, nullptr, 0, o);
+    else lane_pass<Real, M, false>(c, tg, L, mem, nullptr, 0, o);
     const int st = lane_step<Real, M, PL>(c, L, mem, o, inst >= 0);
     if (inst >= 0) {
       if (st != IK_RUNNING) {
@@ -180,7 +180,7 @@ k_ik_level(const __grid_constant__ ChainDev<Real, kMaxJ> c, long long total, con
     if (__all_sync(0xffffffffu, li < 0)) break;
     PassOut<Real, M> o;
     if constexpr (PL) lane_pass_planar<Real, false>(c, tg, L, mem, nullptr, 0, o);
-    else lane_pass<Real, M, false>(c, tg, L.src, mem, nullptr, 0, o);
+    else lane_pass<Real, M, false>(c, tg, L, mem, nullptr, 0, o);
     const int st = lane_step<Real, M, PL>(c, L, mem, o, li >= 0);
     if (li >= 0 && st != IK_RUNNING) {
       Real *dst = q_raw + (li * n) * (long long)Nqr + col;
@@ -287,7 +287,7 @@ k_valid_edge_batch(const __grid_constant__ ChainDev<Real, kMaxJ> c, long long to
       PassOut<Real, M> o;
       const bool first = running && P.k == 1;
       if constexpr (PL) lane_pass_planar<Real, true>(c, tg, L, mem, first ? P.qa : mem.prev(), first ? P.sa : mem.T, o);
-      else lane_pass<Real, M, true>(c, tg, L.src, mem, first ? P.qa : mem.prev(), first ? P.sa : mem.T, o);
+      else lane_pass<Real, M, true>(c, tg, L, mem, first ? P.qa : mem.prev(), first ? P.sa : mem.T, o);
       const int st = lane_step<Real, M, PL>(c, L, mem, o, running);
       if (running && st != IK_RUNNING) {
         P.solves++; P.iters += L.it;
@@ -398,7 +398,7 @@ k_edges_build(const __grid_constant__ ChainDev<Real, kMaxJ> c, const int32_t *__
         PassOut<Real, M> o;
         const bool first = running && P.k == 1;
         if constexpr (PL) lane_pass_planar<Real, true>(c, tg, L, mem, first ? P.qa : mem.prev(), first ? P.sa : mem.T, o);
-        else lane_pass<Real, M, true>(c, tg, L.src, mem, first ? P.qa : mem.prev(), first ? P.sa : mem.T, o);
+        else lane_pass<Real, M, true>(c, tg, L, mem, first ? P.qa : mem.prev(), first ? P.sa : mem.T, o);
         const int st = lane_step<Real, M, PL>(c, L, mem, o, running);
         if (running && st != IK_RUNNING) {
           cnt.solves++; cnt.iters += L.it; cnt.evals += L.evals; cnt.ok += (st == IK_OK);

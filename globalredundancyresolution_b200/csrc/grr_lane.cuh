@@ -106,17 +106,19 @@ template <typename Real, int M>
 struct LaneIK {
   Real fold, slope, alam, alam2, f2, alamin, stpmax, resid;
   int it, evals, phase;
-  // planar path: the Newton step is folded into the next chain pass.  `first` = that pass derives the
+  // the Newton step is folded into the next chain pass.  `first` = that pass derives the
   // direction p_j = -col_j . y from the Jacobian columns still in memory (ny = -y) and stores it.
   bool first, check_convx;
-  Real ny[2];
+  Real ny[M];
   XSrc<Real> src;
   const Real *res;   // after a final status: the solution, res[j * T]
 };
 
 template <typename Real, int M>
 __device__ __forceinline__ void lane_reset(LaneIK<Real, M> &L) {
-  L.it = 0; L.evals = 0; L.phase = 0; L.first = false; L.check_convx = false; L.ny[0] = 0; L.ny[1] = 0;
+  L.it = 0; L.evals = 0; L.phase = 0; L.first = false; L.check_convx = false; 
+#pragma unroll
+  for (int r = 0; r < M; r++) L.ny[r] = 0;
   L.alam = 0; L.alam2 = 0; L.f2 = 0; L.fold = 0; L.slope = 0; L.alamin = 0; L.stpmax = 0; L.resid = 0;
 }
 // Start an instance whose seed is lerp(qa, qb, u) read from (a, b) with strides (sa, sb).
@@ -163,7 +165,7 @@ struct PassOut {
   Real Fw[M], FL[M], f, fmax, xn2;
   Real s2;                         // |x - xref|^2 when a reference config is given
   Real S[M * (M + 1) / 2];
-  Real pn2, test, testx;           // planar path, first trial of a Newton step: |p|^2, max |p_j|/max(|x_j|,1), max |dx_j|/max(|x_j|,1)
+  Real pn2, test, testx;           // first trial of a Newton step: |p|^2, max |p_j|/max(|x_j|,1), max |dx_j|/max(|x_j|,1)
 };
 
 // xref (stride sref): config against which the joint-space distance of the trial point is accumulated
@@ -269,43 +271,62 @@ __device__ __forceinline__ void lane_pass_planar(const ChainT &c, const Target<R
 }
 
 template <typename Real, int M, bool WITH_REF, typename ChainT>
-__device__ __forceinline__ void lane_pass(const ChainT &c, const Target<Real, M> &tg, const XSrc<Real> &src,
+__device__ __forceinline__ void lane_pass(const ChainT &c, const Target<Real, M> &tg, const LaneIK<Real, M> &L,
                                           const LaneMem<Real, M> &mem, const Real *xref, int sref, PassOut<Real, M> &o) {
   const int n = c.n;
+  const XSrc<Real> &src = L.src;
   Real v[3] = {c.ee[0], c.ee[1], c.ee[2]};
   Real G[9];
 #pragma unroll
   for (int k = 0; k < 9; k++) G[k] = c.Rtail[k];
 #pragma unroll
   for (int k = 0; k < M * (M + 1) / 2; k++) o.S[k] = 0;
-  Real xn2 = 0, s2 = 0;
+  Real xn2 = 0, s2 = 0, pn2 = 0, test = 0, testx = 0;
   const int T = mem.T;
-  const Real *pa = src.a + (n - 1) * src.sa, *pb = src.b + (n - 1) * src.sb;
+  const int sa = src.sa, sb = src.sb;
+  const Real *pa = src.a + (n - 1) * sa;
+  Real *pb = const_cast<Real *>(src.b) + (n - 1) * sb;      // written only by `first` lanes, whose b is mem.p()
   const Real *pr = WITH_REF ? xref + (n - 1) * sref : nullptr;
   Real *pc = mem.cols() + (n - 1) * M * T;
   Real *px = mem.xcur() + (n - 1) * T;
+  const Real lk = src.lerp ? Real(1) : Real(0);                // dir = b - lk * a (exact product)
+  const Real t = src.t;
+  const bool first = L.first;
   // software pipeline: the next joint's constants (an indexed constant-bank load with ~100+ cycles of
-  // latency) and operands are fetched while the current joint is computed
+  // latency) and operands are fetched while the current joint is computed.  (Two joints per trip with two
+  // named operand sets, as in the planar pass, was measured 7-20 % slower here: the body with its four
+  // joint kinds then needs more than the 128 / 168 registers the launch bounds allow.)
   JointConst<Real> jn = c.jc[n - 1];
   Real av_n = *pa, bv_n = *pb, rv_n = WITH_REF ? *pr : Real(0);
-  const bool small = c.small_angles != 0;
 #pragma unroll 1
   for (int j = n - 1; j >= 0; --j) {
     const JointConst<Real> jc = jn;
     const Real av = av_n, bv = bv_n, rv = rv_n;
+    Real *pbw = pb;
     if (j > 0) {
       jn = c.jc[j - 1];
-      pa -= src.sa; pb -= src.sb;
+      pa -= sa; pb -= sb;
       av_n = *pa; bv_n = *pb;
       if (WITH_REF) { pr -= sref; rv_n = *pr; }
     }
-    const Real dir = src.lerp ? bv - av : bv;
-    const Real xj = min_(max_(av + src.t * dir, jc.bmin), jc.bmax);
+    // first trial of a Newton step: direction from the columns of the accepted point (still in memory
+    // at this joint: they are overwritten below), stored as p for the later trials of the line search
+    Real dnew = 0;
+#pragma unroll
+    for (int r = 0; r < M; r++) dnew = fma_(pc[r * T], L.ny[r], dnew);
+    const Real xo = *px;
+    const Real dir = first ? dnew : fma_(-lk, av, bv);
+    if (first) *pbw = dir;
+    pn2 = fma_(dir, dir, pn2);
+    const Real rinv = rcp_ge1_(max_(abs_(av), Real(1)));
+    test = max_(test, abs_(dir) * rinv);
+    testx = max_(testx, abs_(av - xo) * rinv);
+    const Real xj = min_(max_(fma_(t, dir, av), jc.bmin), jc.bmax);
     *px = xj; px -= T;
     xn2 += xj * xj;
     if (WITH_REF) { const Real d = xj - rv; s2 += d * d; }
     Real s, co;
-    if (small) sincos_small(xj, &s, &co); else sincos_joint(xj, &s, &co);
+    sincos_joint(xj, &s, &co);
     Real col[M];
     if (jc.kind == 0) {
       Real Mj[9];
@@ -343,6 +364,7 @@ __device__ __forceinline__ void lane_pass(const ChainT &c, const Target<Real, M>
     pc -= M * T;
   }
   o.xn2 = xn2; o.s2 = s2;
+  o.pn2 = pn2; o.test = test; o.testx = testx;
   o.Fw[0] = v[0] - tg.x[0]; o.Fw[1] = v[1] - tg.x[1]; o.Fw[2] = v[2] - tg.x[2];
   Real f = o.Fw[0] * o.Fw[0] + o.Fw[1] * o.Fw[1] + o.Fw[2] * o.Fw[2];
   m3_Tvec(G, o.Fw, o.FL);
@@ -416,15 +438,18 @@ __device__ __forceinline__ void lane_backtrack(LaneIK<Real, M> &L, Real f) {
   L.src.t = L.alam;
 }
 
-// ---- planar transition: no joint loop.  A new Newton iteration only solves the 2x2 normal equations
-// and arms `first`; the next chain pass derives p from the stored columns, writes it, evaluates the first
-// trial point and returns |p|, the step-size tests and the x-convergence test, which are then checked
-// here in the order of the reference algorithm (convergence on x, iteration limit, step clipping,
-// descent test) before that pass is used as the first line-search evaluation.  slope = g.p is taken in
-// closed form: g = J^T F, p = -J^T y  =>  g.p = -F^T (J J^T) y = -FL^T S y.
-template <typename Real, typename ChainT>
-__device__ __forceinline__ int lane_step_planar(const ChainT &c, LaneIK<Real, 3> &L, LaneMem<Real, 2> &mem,
-                                                const PassOut<Real, 3> &o, bool active) {
+// ---- the transition: line-search bookkeeping; no joint loop.  A new Newton iteration only solves the
+// damped normal equations for y and arms `first`; the next chain pass derives p_j = -col_j . y from the
+// stored columns, writes it, evaluates the first trial point and returns |p|, the step-size tests and
+// the x-convergence test, which are then checked here in the order of the reference algorithm
+// (convergence on x, iteration limit, step clipping, descent test) before that pass is used as the
+// first line-search evaluation.  slope = g.p is taken in closed form: g = J^T F, p = -J^T y  =>
+// g.p = -F^T (J J^T) y = -FL^T S y.  (v4/v5 ran a separate per-joint step loop here: 27-43 instructions
+// per joint at 73 % lane efficiency, 19 % of all issued instructions.)
+// Returns IK_RUNNING or the final status; after a final status the solution is L.res[j * T].
+template <typename Real, int M, bool PL, typename ChainT>
+__device__ __forceinline__ int lane_step(const ChainT &c, LaneIK<Real, M> &L, LaneMem<Real, col_rows(M, PL)> &mem,
+                                         const PassOut<Real, M> &o, bool active) {
   const int n = c.n;
   const Real tolf = c.tol, tolx = Real(0.01) * c.tol, ALF = Real(1e-4);
   int st = IK_RUNNING;
@@ -480,70 +505,18 @@ __device__ __forceinline__ int lane_step_planar(const ChainT &c, LaneIK<Real, 3>
   if (newstep) {
     // the accepted point (in xcur) becomes the origin of the next line search: swap roles, no copy
     { const int t = mem.o_xold; mem.o_xold = mem.o_xcur; mem.o_xcur = t; }
-    // 2x2 in-plane normal equations (the out-of-plane row has no Jacobian)
     const Real l2 = c.lambda * c.lambda;
-    const Real a11 = o.S[0] + l2, a12 = o.S[1], a22 = o.S[2] + l2;
-    const Real idet = fdiv_(Real(1), a11 * a22 - a12 * a12);
-    const Real y0 = (a22 * o.FL[0] - a12 * o.FL[1]) * idet;
-    const Real y1 = (a11 * o.FL[1] - a12 * o.FL[0]) * idet;
-    L.ny[0] = -y0; L.ny[1] = -y1;
-    L.slope = -(o.FL[0] * (o.S[0] * y0 + o.S[1] * y1) + o.FL[1] * (o.S[1] * y0 + o.S[2] * y1));
-    L.first = true; L.check_convx = check_convx;
-    L.fold = o.f; L.alam = 1; L.alam2 = 0; L.f2 = 0; L.alamin = 0;
-    L.src.a = mem.xold(); L.src.b = mem.p(); L.src.sa = mem.T; L.src.sb = mem.T; L.src.t = 1; L.src.lerp = false;
-    L.res = mem.xold();
-    L.phase = 1;
-  }
-  return st;
-}
-
-// ---- the transition: line search bookkeeping and, if a new iteration starts, the Newton step ----
-// Called by ALL lanes of the warp (`active` = this lane holds a running instance) so that the lanes
-// that start a new iteration execute the step loop together whatever path took them there.
-// Returns IK_RUNNING or the final status; after a final status the solution is L.res[j * T].
-template <typename Real, int M, bool PL, typename ChainT>
-__device__ __forceinline__ int lane_step(const ChainT &c, LaneIK<Real, M> &L, LaneMem<Real, col_rows(M, PL)> &mem,
-                                         const PassOut<Real, M> &o, bool active) {
-  if constexpr (PL) return lane_step_planar(c, L, mem, o, active);
-  constexpr int MC = col_rows(M, PL);
-  const int n = c.n;
-  const Real tolf = c.tol, tolx = Real(0.01) * c.tol, ALF = Real(1e-4);
-  int st = IK_RUNNING;
-  bool newstep = false, check_convx = false;
-  if (active) {
-    L.evals++;
-    L.resid = o.fmax;
-    L.res = mem.xcur();
-    if (L.phase == 0) {
-      if (o.fmax < tolf) st = IK_OK;
-      else if (c.max_iters <= 0) st = IK_MAXIT;
-      else { L.stpmax = Real(10) * max_(sqrt_(o.xn2), Real(n)); newstep = true; }
-    } else if (L.alam < L.alamin) {
-      L.it++; L.res = mem.xold(); st = IK_STALL;                        // x <- xold
-    } else if (!(o.f <= L.fold + ALF * L.alam * L.slope)) {
-      lane_backtrack(L, o.f);
-    } else {
-      L.it++;
-      if (o.fmax < tolf) st = IK_OK;
-      else { newstep = true; check_convx = true; }
-    }
-  }
-  __syncwarp();
-  if (newstep) {
-    // the accepted point (in xcur) becomes the origin of the next line search: swap roles, no copy
-    { const int t = mem.o_xold; mem.o_xold = mem.o_xcur; mem.o_xcur = t; }
-    Real y[M];
-    if (PL) {
+    if constexpr (PL) {
       // 2x2 in-plane normal equations (the out-of-plane row has no Jacobian)
-      const Real l2 = c.lambda * c.lambda;
       const Real a11 = o.S[0] + l2, a12 = o.S[1], a22 = o.S[2] + l2;
       const Real idet = fdiv_(Real(1), a11 * a22 - a12 * a12);
-      y[0] = (a22 * o.FL[0] - a12 * o.FL[1]) * idet;
-      y[1] = (a11 * o.FL[1] - a12 * o.FL[0]) * idet;
-      if (M > 2) y[2] = 0;
+      const Real y0 = (a22 * o.FL[0] - a12 * o.FL[1]) * idet;
+      const Real y1 = (a11 * o.FL[1] - a12 * o.FL[0]) * idet;
+      L.ny[0] = -y0; L.ny[1] = -y1;
+      L.slope = -(o.FL[0] * (o.S[0] * y0 + o.S[1] * y1) + o.FL[1] * (o.S[1] * y0 + o.S[2] * y1));
     } else {
+      Real y[M];
       Real A[M * (M + 1) / 2];
-      const Real l2 = c.lambda * c.lambda;
       if (M == 3) {
 #pragma unroll
         for (int k = 0; k < 6; k++) A[k] = o.S[k];
@@ -551,6 +524,7 @@ __device__ __forceinline__ int lane_step(const ChainT &c, LaneIK<Real, M> &L, La
         for (int r = 0; r < M; r++) A[tri(r, r)] += l2;
         chol_solve_fast<Real, M>(A, o.FL, y);
       } else {
+        // rotation rows: the Jacobian of the log-map residual is Jl^-1(e) times the stored angular rows
         Real D[9], Src[9], Srr[9], DSrc[9], DSrr[9];
         so3_Jl_inv(&o.FL[M - 3], D);
 #pragma unroll
@@ -582,60 +556,24 @@ __device__ __forceinline__ int lane_step(const ChainT &c, LaneIK<Real, M> &L, La
         m3_Tvec(D, &y[M - 3], z);
         y[M - 3] = z[0]; y[M - 2] = z[1]; y[M - 1] = z[2];
       }
-    }
-    Real pn = 0, slope = 0, test = 0, testx = 0;
-    {
-      const int T = mem.T;
-      const Real *px = mem.xold();          // accepted point
-      const Real *po = mem.xcur();          // origin of the search that just ended (phase 1 only)
-      Real *pp = mem.p();
-      const Real *pc = mem.cols();
-#pragma unroll 1
-      for (int j = 0; j < n; j++) {
-        const Real xj = *px, xo = *po;
-        px += T; po += T;
-        const Real rinv = rcp_ge1_(max_(abs_(xj), Real(1)));
-        testx = max_(testx, abs_(xj - xo) * rinv);
-        Real pj = 0, gj = 0;
+      // slope = -FL^T S y with the stored-column normal matrix S (packed lower)
+      Real slope = 0;
 #pragma unroll
-        for (int r = 0; r < MC; r++) { const Real cj = pc[r * T]; pj += cj * y[r]; gj += cj * o.FL[r]; }
-        pc += MC * T;
-        pj = -pj;
-        *pp = pj; pp += T;
-        pn += pj * pj;
-        slope += gj * pj;
-        test = max_(test, abs_(pj) * rinv);
+      for (int r = 0; r < M; r++) {
+        Real sy = 0;
+#pragma unroll
+        for (int q = 0; q < M; q++) sy += ((r >= q) ? o.S[tri(r, q)] : o.S[tri(q, r)]) * y[q];
+        slope += o.FL[r] * sy;
       }
+      L.slope = -slope;
+#pragma unroll
+      for (int r = 0; r < M; r++) L.ny[r] = -y[r];
     }
-    L.alam = 0;
-    L.src.a = mem.xold(); L.src.b = mem.p(); L.src.sa = mem.T; L.src.sb = mem.T; L.src.t = 0; L.src.lerp = false;
+    L.first = true; L.check_convx = check_convx;
+    L.fold = o.f; L.alam = 1; L.alam2 = 0; L.f2 = 0; L.alamin = 0;
+    L.src.a = mem.xold(); L.src.b = mem.p(); L.src.sa = mem.T; L.src.sb = mem.T; L.src.t = 1; L.src.lerp = false;
     L.res = mem.xold();
-    if (check_convx && testx < tolx) st = IK_CONVX;
-    else if (check_convx && L.it >= c.max_iters) st = IK_MAXIT;
-    else {
-      pn = sqrt_(pn);
-      if (pn > L.stpmax) {
-        const Real sc = L.stpmax / pn;
-        test = 0;
-        const int T = mem.T;
-        Real *pp = mem.p();
-        const Real *px = mem.xold();
-#pragma unroll 1
-        for (int j = 0; j < n; j++) {
-          const Real pj = pp[j * T] * sc;
-          pp[j * T] = pj;
-          test = max_(test, abs_(pj) / max_(abs_(px[j * T]), Real(1)));
-        }
-        slope *= sc;
-      }
-      if (!(slope < Real(0))) { L.it++; st = IK_STALL; }
-      else {
-        L.alamin = fdiv_(tolx, test);
-        L.fold = o.f; L.slope = slope; L.alam = 1; L.alam2 = 0; L.f2 = 0;
-        L.src.t = 1;
-        L.phase = 1;
-      }
-    }
+    L.phase = 1;
   }
   return st;
 }
