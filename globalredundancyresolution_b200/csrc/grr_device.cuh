@@ -67,6 +67,7 @@ template <typename Real, int NJ>
 struct ChainDev {
   int n, mode, nlinks_eps, max_iters;
   int small_angles;            // every joint limit inside [-pi/4, pi/4]: sincos needs no range reduction
+  int axes_positive;           // every short-path joint has sgn = +1
   Real tol, lambda;
   // M_j(theta) = Rp_j * Rot(axis_j, theta) = A + sin(theta) * B - cos(theta) * C
   Real A[NJ][9], B[NJ][9], C[NJ][9];

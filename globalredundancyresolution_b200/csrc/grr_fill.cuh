@@ -42,8 +42,11 @@ void fill_chain(const HostChain &h, ChainDev<Real, NJ> &d) {
     for (int k = 0; k < 3; k++) d.jc[j].tp[k] = d.tp[j][k];
   }
   d.small_angles = 1;
-  for (int j = 0; j < h.n && j < NJ; j++)
+  d.axes_positive = 1;
+  for (int j = 0; j < h.n && j < NJ; j++) {
     if (!(h.qmin[j] >= -0.785 && h.qmax[j] <= 0.785)) d.small_angles = 0;
+    if (d.jc[j].kind != 0 && !(d.jc[j].sgn > 0)) d.axes_positive = 0;
+  }
   for (int k = 0; k < 3; k++) d.ee[k] = (Real)h.ee_local[k];
   for (int k = 0; k < 9; k++) { d.Rtail[k] = (Real)h.R_tail[k]; d.Rgoal[k] = (Real)h.R_goal[k]; }
 }

@@ -174,7 +174,7 @@ struct PassOut {
 // goal-link frame equals the last joint frame (the reference's planar_{2,3,5,10,20}R robots).  G stays a
 // rotation about y, kept as (cos, sin); columns have two in-plane components (x, z); the normal matrix is
 // 2x2.  Same algorithm, a third of the arithmetic.
-template <typename Real, bool WITH_REF, bool SMALL, typename ChainT>
+template <typename Real, bool WITH_REF, bool SMALL, bool POS, typename ChainT>
 __device__ __forceinline__ void lane_pass_planar_(const ChainT &c, const Target<Real, 3> &tg, const LaneIK<Real, 3> &L,
                                                   const LaneMem<Real, 2> &mem, const Real *xref, int sref,
                                                   PassOut<Real, 3> &o) {
@@ -219,9 +219,9 @@ __device__ __forceinline__ void lane_pass_planar_(const ChainT &c, const Target<
     if (WITH_REF) { const Real d = xj - rv; s2 += d * d; }
     Real s, co;
     if (SMALL) sincos_small(xj, &s, &co); else sincos_joint(xj, &s, &co);
-    s *= jc.sgn;
+    if (!POS) s *= jc.sgn;
     // column = G^T (axis x v): axis x v = sgn (-v_x e_z + v_z e_x); G^T rotates by -phi
-    const Real w1 = -jc.sgn * vx, w2 = jc.sgn * vz;
+    const Real w1 = POS ? -vx : -jc.sgn * vx, w2 = POS ? vz : jc.sgn * vz;
     const Real c1 = gc * w1 + gs * w2, c2 = gc * w2 - gs * w1;
     pc[0] = c1; pc[T] = c2; pc -= 2 * T;
     S11 += c1 * c1; S12 += c1 * c2; S22 += c2 * c2;
@@ -266,8 +266,9 @@ template <typename Real, bool WITH_REF, typename ChainT>
 __device__ __forceinline__ void lane_pass_planar(const ChainT &c, const Target<Real, 3> &tg, const LaneIK<Real, 3> &L,
                                                  const LaneMem<Real, 2> &mem, const Real *xref, int sref,
                                                  PassOut<Real, 3> &o) {
-  if (c.small_angles != 0) lane_pass_planar_<Real, WITH_REF, true>(c, tg, L, mem, xref, sref, o);
-  else lane_pass_planar_<Real, WITH_REF, false>(c, tg, L, mem, xref, sref, o);
+  // the shipped planar_{10,20}R robots: limits inside +-pi/4 and every axis +e_y
+  if (c.small_angles != 0 && c.axes_positive != 0) lane_pass_planar_<Real, WITH_REF, true, true>(c, tg, L, mem, xref, sref, o);
+  else lane_pass_planar_<Real, WITH_REF, false, false>(c, tg, L, mem, xref, sref, o);
 }
 
 template <typename Real, int M, bool WITH_REF, typename ChainT>
