@@ -25,7 +25,8 @@ EXPORTS = [
     "grr_last_error", "grr_abi_version", "grr_chain_create", "grr_chain_destroy", "grr_task_set",
     "grr_chain_num_joints", "grr_fk_batch", "grr_ik_solve_batch", "grr_ik_sample", "grr_ik_sample_level", "grr_dedup", "grr_dedup_sweep",
     "grr_edges_build", "grr_edges_cost", "grr_edges_compact", "grr_valid_edge_batch", "grr_gather_node_blocks",
-    "grr_scatter_node_blocks", "grr_fp32_peak", "grr_fp32x2_peak",
+    "grr_scatter_node_blocks", "grr_csp_random_assignment", "grr_csp_conflicts", "grr_csp_descent_sweep",
+    "grr_fp32_peak", "grr_fp32x2_peak",
 ]
 
 
@@ -78,6 +79,9 @@ def lib():
     L.grr_valid_edge_batch.argtypes = [vp, C.c_int, i64, vp, vp, vp, vp, dbl, vp, vp, vp, vp]
     L.grr_gather_node_blocks.argtypes = [C.c_int, i64, vp, i32, i32, vp, vp, vp, vp, vp]
     L.grr_scatter_node_blocks.argtypes = [C.c_int, i64, vp, i32, i32, vp, vp, vp, vp, vp]
+    L.grr_csp_random_assignment.argtypes = [i32, i32, vp, u64, i32, vp, vp]
+    L.grr_csp_conflicts.argtypes = [i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    L.grr_csp_descent_sweep.argtypes = [i32, vp, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     L.grr_fp32_peak.argtypes = [C.c_int, C.POINTER(C.c_double)]
     L.grr_fp32x2_peak.argtypes = [C.c_int, C.POINTER(C.c_double)]
     for name in EXPORTS:
@@ -246,6 +250,30 @@ def edges_compact(mask, Nq, offsets, out):
     E = mask.shape[0]
     check(lib().grr_edges_compact(E, int(Nq), _ptr(mask), _ptr(offsets), _ptr(out), _stream(mask.device)),
           "grr_edges_compact")
+
+
+def csp_random_assignment(count, seed, guess_offset, assignment):
+    """assignment i32 [G][Nw] <- random.choice(domain) per variable (csp.py:950-955), -1 where count == 0."""
+    G, Nw = assignment.shape
+    check(lib().grr_csp_random_assignment(Nw, G, _ptr(count), int(seed) & (2 ** 64 - 1), int(guess_offset), _ptr(assignment),
+                                          _stream(count.device)), "grr_csp_random_assignment")
+
+
+def csp_conflicts(Nq, adj_ptr, adj_node, adj_edge, mask, edge_active, assignment, node_conflicts=None, total=None):
+    """numIncompatible per node / numConflicts per guess (csp.py:133-150, :79-84) on the device bitmasks."""
+    G, Nw = assignment.shape
+    check(lib().grr_csp_conflicts(Nw, int(Nq), G, _ptr(adj_ptr), _ptr(adj_node), _ptr(adj_edge), _ptr(mask), _ptr(edge_active),
+                                  _ptr(assignment), _ptr(node_conflicts), _ptr(total), _stream(mask.device)), "grr_csp_conflicts")
+
+
+def csp_descent_sweep(node_list, Nq, adj_ptr, adj_node, adj_edge, mask, edge_active, count, assignment, in_order, active,
+                      changed):
+    """One descent visit (csp.py:996-1030) of the pairwise non-adjacent nodes of node_list, every guess."""
+    G, Nw = assignment.shape
+    check(lib().grr_csp_descent_sweep(node_list.shape[0], _ptr(node_list), Nw, int(Nq), G, _ptr(adj_ptr), _ptr(adj_node),
+                                      _ptr(adj_edge), _ptr(mask), _ptr(edge_active), _ptr(count), _ptr(assignment),
+                                      _ptr(in_order), _ptr(active), _ptr(changed), _stream(mask.device)),
+          "grr_csp_descent_sweep")
 
 
 def gather_node_blocks(idx, q, count, packed, packed_count):

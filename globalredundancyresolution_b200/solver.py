@@ -18,6 +18,8 @@ Visibility-graph / self-motion options are out of scope and raise NotImplemented
 """
 from __future__ import annotations
 
+import time
+
 import numpy as np
 
 from . import _cabi
@@ -716,6 +718,90 @@ class RedundancyResolver:
         words = d["mask"][e, ia[e], ib[e] // 32]
         ok = (words >> (ib[e] % 32).to(torch.int32)) & 1
         return int((ok == 0).sum().item())
+
+    # ---- CSP on the device bitmasks (solver.py:1602-1632, :1713-1737, :2035-2062, :2158-2168) -----
+    def csp(self):
+        """Device-resident makeCSP problem (csp.RoadmapCSP) of the current roadmap."""
+        from .csp import RoadmapCSP
+        return RoadmapCSP(self)
+
+    def encodeCSPAssignment(self):
+        """solver.py:1623-1631: Qsubgraph -> list over the nodes with configs (None where unassigned)."""
+        if len(self.Qsubgraph) == 0:
+            return None
+        return [self.Qsubgraph.get(int(n), None) for n in np.nonzero(self.counts() > 0)[0]]
+
+    def decodeCSPAssignment(self, csp_assignment, visibility=False, **_ignored):
+        """solver.py:1602-1621: assignment -> self.Qsubgraph and the resolution.  Accepts the reference's list over
+        the nodes with configs, or one device row (int32 [Nw], -1 = unassigned) of csp.RoadmapCSP."""
+        if visibility:
+            raise NotImplementedError("visibility-graph solver is out of scope of the B200 roadmap path")
+        nodes = np.nonzero(self.counts() > 0)[0]
+        if hasattr(csp_assignment, "cpu"):
+            row = csp_assignment.reshape(-1).cpu().numpy()
+            self.Qsubgraph = {int(n): int(row[n]) for n in nodes if row[n] >= 0}
+        else:
+            assert len(csp_assignment) == len(nodes)
+            self.Qsubgraph = {int(n): int(v) for n, v in zip(nodes, csp_assignment) if v is not None}
+        self.calculateResolutionFromSubgraph()
+        return None, None, None, None, 0
+
+    def calculateResolutionFromSubgraph(self):
+        """solver.py:2158-2168: resolution.Gw node 'config' = the chosen config, edge 'connected' iff the chosen
+        pair is a C-space edge.  One gather of the chosen configs and one bit test per workspace edge on the device."""
+        res = self.resolution
+        res.clearResolution()
+        if not self.Qsubgraph:
+            return
+        torch = res._torch()
+        d = self._dev
+        nodes = np.fromiter(self.Qsubgraph.keys(), dtype=np.int64)
+        iqs = np.fromiter(self.Qsubgraph.values(), dtype=np.int64)
+        tn, tq = torch.from_numpy(nodes).to(res.torch_device), torch.from_numpy(iqs).to(res.torch_device)
+        q = d["Qs"][tn, :, tq].double().cpu().numpy()
+        for i, row in zip(nodes.tolist(), res.to_full(q)):
+            res.setConfig(i, [float(v) for v in row])
+        a = torch.full((self.Nw,), -1, dtype=torch.int64, device=res.torch_device)
+        a[tn] = tq
+        ia, ib = a[d["wedges"][:, 0].long()], a[d["wedges"][:, 1].long()]
+        e = torch.nonzero((ia >= 0) & (ib >= 0)).squeeze(1)
+        ok = (d["mask"][e, ia[e], ib[e] // 32] >> (ib[e] % 32).to(torch.int32)) & 1
+        for k in e[ok != 0].cpu().tolist():
+            iw, jw = self._edges_host[k]
+            res.markConnected(iw, jw)
+
+    def randomDescentAssignment(self, randomize=True):
+        """solver.py:1713-1737: min-conflicts descent (csp.py:934-1041, perturb=True) from a random assignment, or from
+        the current Qsubgraph if randomize=False; the result becomes Qsubgraph / the resolution."""
+        csp = self.csp()
+        start = None
+        if not randomize and self.Qsubgraph:
+            start = csp.from_reference(self.encodeCSPAssignment())
+        self._csp_guess = getattr(self, "_csp_guess", 0) + 1
+        a = csp.randomDescentAssignment(start, perturb=True, G=1, guess_offset=self._csp_guess)
+        self.decodeCSPAssignment(a[0])
+
+    def solveCSP(self, visibility=False, parallel=False, numRandomDescents=2, numInitialGuesses=10, threads=None, tasks=None,
+                 results=None):
+        """solver.py:2035-2062: best of numInitialGuesses descents.  All guesses are descended at once on the device.
+        Deviation: the reference's first guess comes from CSP.heuristicMaxAssignment (csp.py:739-932, a sequential
+        greedy with arc consistency), which is not built; every guess starts from random values, so the method
+        reported is always 'random'.  Repeating a converged descent (numRandomDescents) changes nothing
+        (perturb=False) and is not executed.  Returns (bestConflicts, bestMethod, solve_time, collapse_time)."""
+        if visibility:
+            raise NotImplementedError("visibility-graph solver is out of scope of the B200 roadmap path")
+        torch = self.resolution._torch()
+        t0 = time.time()
+        csp = self.csp()
+        a = csp.randomDescentAssignment(None, G=max(int(numInitialGuesses), 1))
+        conflicts = csp.numConflicts(a)
+        best = int(torch.argmin(conflicts).item())
+        bestConflicts = int(conflicts[best].item())
+        solve_time = time.time() - t0
+        self.stats["csp"] = {"conflicts": conflicts.cpu().tolist(), "sweeps": csp.sweeps, "guesses": int(a.shape[0]),
+                             "solve_time": solve_time}
+        self.decodeCSPAssignment(a[best])
+        return bestConflicts, "random", solve_time, 0
 
     # ---- sanity (solver.py:365-383) -------------------------------------------------------------------
     def sanityCheck(self):

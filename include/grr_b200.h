@@ -181,6 +181,39 @@ int grr_gather_node_blocks(int dtype, int64_t K, const int32_t *idx, int32_t n, 
 int grr_scatter_node_blocks(int dtype, int64_t K, const int32_t *idx, int32_t n, int32_t Nqp, const void *packed,
                             const int32_t *packed_count, void *q, int32_t *count, void *stream);
 
+/* -- the roadmap's consumer on the bitmasks: the constraint satisfaction problem of
+ * RedundancyResolver.makeCSP (grr/solver.py:984-1022) -- one variable per workspace node with configs, one table
+ * constraint per workspace edge whose C-space edge set is non-empty; the table is the edge's Nq x Nq bitmask --
+ * and CSP.randomDescentAssignment / numIncompatible / numConflicts (grr/utils/csp.py:934-1041, :133-150, :79-84).
+ * G assignments ("guesses", solver.py:2048-2056) are handled at once: assignment [dev] i32 [G][Nw], -1 = no
+ * variable / unassigned.  Adjacency in CSR form over ALL workspace edges: adj_ptr [dev] i32 [Nw+1],
+ * adj_node [dev] i32 [2E], adj_edge [dev] i32 [2E] = e if the node is the first endpoint of workspace edge e
+ * (wedges[e][0], the row index of the bitmask), ~e (bitwise not) if it is the second.
+ * edge_active [dev] u8 [E] = 1 iff the edge's bitmask has a set bit (solver.py:1019).  Nq <= 65535. */
+
+/* random.choice(domain) per variable (csp.py:950-955): Philox4x32-10, key = seed,
+ * counter = (node, guess_offset + g, 0, 2); value = r0 % count[node]. */
+int grr_csp_random_assignment(int32_t Nw, int32_t G, const int32_t *count, uint64_t seed, int32_t guess_offset,
+                              int32_t *assignment, void *stream);
+
+/* node_conflicts [dev] i32 [G][Nw] = numIncompatible(node, assignment[node]) (nullable);
+ * total [dev] i32 [G] = numConflicts(assignment) (nullable; zeroed by the call). */
+int grr_csp_conflicts(int32_t Nw, int32_t Nq, int32_t G, const int32_t *adj_ptr, const int32_t *adj_node,
+                      const int32_t *adj_edge, const uint32_t *mask, const uint8_t *edge_active,
+                      const int32_t *assignment, int32_t *node_conflicts, int32_t *total, void *stream);
+
+/* One descent visit (csp.py:996-1030) of every node of node_list [dev] i32 [n_list] for every guess.  The nodes
+ * of one call must be pairwise non-adjacent (one colour class of the workspace graph); then the call equals the
+ * reference's sequential visits of those nodes in any order.  A node moves to the first value with the fewest
+ * conflicts if that is strictly fewer than it has now.  The reference's `active` set: a node is visited iff
+ * in_order [dev] u8 [G][Nw] (the caller's snapshot of `active` taken when the pass began, csp.py:993-995) is set;
+ * active [dev] u8 [G][Nw] is cleared for every visited node and set for the assigned neighbours of every node
+ * that moved (csp.py:1014-1020, :1027-1028).  changed [dev] i32 [G] += number of nodes that moved. */
+int grr_csp_descent_sweep(int32_t n_list, const int32_t *node_list, int32_t Nw, int32_t Nq, int32_t G,
+                          const int32_t *adj_ptr, const int32_t *adj_node, const int32_t *adj_edge, const uint32_t *mask,
+                          const uint8_t *edge_active, const int32_t *count, int32_t *assignment,
+                          const uint8_t *in_order, uint8_t *active, int32_t *changed, void *stream);
+
 /* -- measurement support: FP32 FMA peak microbenchmark (returns achieved TFLOP/s; synchronous). */
 int grr_fp32_peak(int device, double *tflops_out);
 /* same with the packed sm_100 FFMA2 instruction (two FP32 FMAs per instruction per lane) */

@@ -1,0 +1,186 @@
+"""the roadmap CSP (makeCSP, solver.py:984-1022) and the min-conflicts descent (csp.py:934-1041).
+
+CPU part: the restatement oracle/csp_oracle.py on hand-built problems whose answers follow from the definitions,
+and the host-side graph helpers.  GPU part: the device kernels against that restatement on a real roadmap,
+bit-exact (integer work)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import globalredundancyresolution_b200 as grr            # noqa: E402
+from oracle.csp_oracle import TableCSP                     # noqa: E402
+from helpers import small_problem                          # noqa: E402
+
+
+def path_csp():
+    """a - b - c, two values each; allowed: a==b, b!=c."""
+    c = TableCSP()
+    for name in "abc":
+        c.add_variable([0, 1], name)
+    c.add_constraint({(0, 0), (1, 1)}, ("a", "b"))
+    c.add_constraint({(0, 1), (1, 0)}, ("b", "c"))
+    return c
+
+
+def test_oracle_counts_follow_definitions():
+    c = path_csp()
+    assert c.num_conflicts([0, 0, 1]) == 0
+    assert c.num_conflicts([0, 1, 1]) == 2
+    assert c.num_incompatible(1, 1, [0, 1, 1]) == 2          # b=1 violates both tables
+    assert c.num_incompatible(1, 0, [0, 1, 1]) == 0          # b=0 satisfies both
+    assert c.num_incompatible(0, 1, [None, 1, 1]) == 0       # csp.py:144: only fully assigned scopes count
+    assert c.neighbors == [{1}, {0, 2}, {1}]
+
+
+def test_oracle_descent_is_min_conflicts_first_minimum():
+    c = path_csp()
+    # start [0,1,1]: visiting b first moves it to the first value with fewest conflicts (0) and is done
+    a, passes = c.random_descent([0, 1, 1], order_key=lambda v: (v != 1, v))
+    assert a == [0, 0, 1] and c.num_conflicts(a) == 0
+    # visiting a first: a has 1 conflict, a=1 has 0 -> moves; then b (1 conflict: b,c) -> b=0 has 1 conflict too: stays;
+    # c: c=0 has 0 conflicts -> moves
+    a, passes = c.random_descent([0, 1, 1], order_key=lambda v: v)
+    assert a == [1, 1, 0] and c.num_conflicts(a) == 0
+    # a conflict-free start is returned untouched after one pass
+    a, passes = c.random_descent([0, 0, 1], order_key=lambda v: v)
+    assert a == [0, 0, 1] and passes == 1
+
+
+def test_oracle_descent_never_increases_conflicts():
+    rng = np.random.RandomState(3)
+    c = TableCSP()
+    n, dom = 30, 5
+    for i in range(n):
+        c.add_variable(list(range(dom)), "v%d" % i)
+    for i in range(n):
+        for j in (i + 1, i + 7):
+            if j < n:
+                allowed = {(a, b) for a in range(dom) for b in range(dom) if rng.rand() < 0.4}
+                c.add_constraint(allowed, ("v%d" % i, "v%d" % j))
+    start = [int(rng.randint(dom)) for _ in range(n)]
+    a, passes = c.random_descent(start, order_key=lambda v: v)
+    assert c.num_conflicts(a) <= c.num_conflicts(start)
+    # fixed point: no single variable can strictly improve
+    for v in range(n):
+        cur = c.num_incompatible(v, a[v], a)
+        assert all(c.num_incompatible(v, val, a) >= cur for val in range(dom))
+
+
+def test_colouring_and_adjacency_layout():
+    pdef, res = small_problem("planar_3R", "Rfree.json", 200, "staggered_grid")
+    edges = res.ws_edges
+    Nw = res.ws_params.shape[0]
+    colour = grr.greedy_colouring(Nw, edges.tolist())
+    assert (colour[edges[:, 0]] != colour[edges[:, 1]]).all()
+    assert colour.max() <= 3
+    ptr, nbr, eid = grr.adjacency_csr(Nw, edges)
+    assert ptr[-1] == 2 * len(edges)
+    for i in (0, Nw // 2, Nw - 1):
+        for k in range(ptr[i], ptr[i + 1]):
+            e = eid[k] if eid[k] >= 0 else ~eid[k]
+            a, b = edges[e]
+            assert (a, b) == ((i, nbr[k]) if eid[k] >= 0 else (nbr[k], i))
+        es = [eid[k] if eid[k] >= 0 else ~eid[k] for k in range(ptr[i], ptr[i + 1])]
+        assert es == sorted(es)
+
+
+# ---------------------------------------------------------------------------------------------------------
+def _roadmap(Nw=150, Nq=12, name="planar_3R", jf="Rfree.json"):
+    pdef, res = small_problem(name, jf, Nw, "staggered_grid")
+    rr = grr.RedundancyResolver(res, seed=5)
+    rr.sampleConfigurationSpace(Nq, order_independent=True)
+    return res, rr
+
+
+@pytest.mark.gpu
+def test_device_conflict_counts_match_restatement(built):
+    res, rr = _roadmap()
+    csp = rr.csp()
+    ref = TableCSP.from_container(rr.makeCSP())
+    a = csp.randomAssignment(G=3)
+    tot = csp.numConflicts(a).cpu().tolist()
+    nc = csp.nodeConflicts(a).cpu().numpy()
+    variables = csp.variables()
+    for g in range(3):
+        lst = csp.to_reference(a[g])
+        assert all(v is not None and 0 <= v < len(ref.domains[k]) for k, v in enumerate(lst))
+        assert tot[g] == ref.num_conflicts(lst)
+        assert tot[g] == rr.numConflicts({int(n): v for n, v in zip(variables, lst)})
+        for k, n in enumerate(variables):
+            assert nc[g, n] == ref.num_incompatible(k, lst[k], lst)
+    # different guesses draw different values
+    assert (a[0] != a[1]).any()
+
+
+@pytest.mark.gpu
+def test_device_descent_equals_reference_pass_in_colour_order(built):
+    res, rr = _roadmap()
+    csp = rr.csp()
+    ref = TableCSP.from_container(rr.makeCSP())
+    variables = csp.variables()
+    colour = csp.colour
+    a0 = csp.randomAssignment(G=4, guess_offset=7)
+    a1 = csp.randomDescentAssignment(a0)
+    tot0, tot1 = csp.numConflicts(a0).cpu().tolist(), csp.numConflicts(a1).cpu().tolist()
+    key = lambda k: (int(colour[variables[k]]), int(variables[k]))
+    for g in range(4):
+        want, passes = ref.random_descent(csp.to_reference(a0[g]), order_key=key)
+        assert csp.to_reference(a1[g]) == want, "guess %d" % g
+        assert tot1[g] == ref.num_conflicts(want) <= tot0[g]
+    assert max(tot0) > 0, "test problem has no conflicts to remove"
+
+
+@pytest.mark.gpu
+def test_solve_csp_sets_the_resolution(built):
+    res, rr = _roadmap(Nw=120, Nq=10)
+    conflicts, method, t_solve, t_collapse = rr.solveCSP(numInitialGuesses=6)
+    st = rr.stats["csp"]
+    assert conflicts == min(st["conflicts"]) and method == "random" and st["guesses"] == 6
+    cnt = rr.counts()
+    assert set(rr.Qsubgraph) == set(np.nonzero(cnt > 0)[0].tolist())
+    # resolution: chosen configs solve their node's IK problem; connected edges are C-space edges of the roadmap
+    nres = 0
+    for iw, iq in rr.Qsubgraph.items():
+        q = res.Gw.node[iw]["config"]
+        assert q == rr.Gw.node[iw]["qlist"][iq]
+        assert res.ikError(q, res.Gw.node[iw]["params"]) < 2e-3
+        nres += 1
+    assert res.resolvedCount == nres
+    nconn = nviol = 0
+    for iw, jw in res.Gw.edges_iter():
+        if iw in rr.Qsubgraph and jw in rr.Qsubgraph:
+            has = rr.hasEdge(iw, rr.Qsubgraph[iw], jw, rr.Qsubgraph[jw])
+            assert res.isResolvedEdge(iw, jw) == has
+            nconn += has
+            if not has and len(rr.Gw.edge[min(iw, jw)][max(iw, jw)]["qlist"]) > 0:
+                nviol += 1
+    assert nviol == conflicts and nconn > 0
+    # reference round trip: encode -> decode
+    enc = rr.encodeCSPAssignment()
+    before = dict(rr.Qsubgraph)
+    rr.decodeCSPAssignment(enc)
+    assert rr.Qsubgraph == before
+    # a descent from the current assignment (perturbed) keeps a full assignment
+    rr.randomDescentAssignment(randomize=False)
+    assert set(rr.Qsubgraph) == set(before)
+
+
+@pytest.mark.gpu
+def test_csp_on_a_six_d_task(built):
+    """fixed orientation: sparse roadmap, many nodes without configs and many workspace edges without constraint"""
+    res, rr = _roadmap(Nw=300, Nq=40, name="jaco", jf="Rfixed.json")
+    csp = rr.csp()
+    ref = TableCSP.from_container(rr.makeCSP())
+    variables = csp.variables()
+    if len(variables) == 0:
+        pytest.skip("no configs sampled")
+    a0 = csp.randomAssignment(G=2)
+    a1 = csp.randomDescentAssignment(a0)
+    key = lambda k: (int(csp.colour[variables[k]]), int(variables[k]))
+    for g in range(2):
+        want, _ = ref.random_descent(csp.to_reference(a0[g]), order_key=key)
+        assert csp.to_reference(a1[g]) == want
+    assert (a1[:, rr.counts() == 0] == -1).all()
