@@ -272,6 +272,8 @@ struct grr_handle_s {
   HostChain hc;
   unsigned long long *d_work;   // ring of device work counters for the persistent-lane kernels
   unsigned next_work;
+  unsigned long long *d_scratch;   // grow-only device scratch (pair-queue offsets of grr_edges_build)
+  size_t scratch_words;
 };
 static const unsigned kWorkRing = 64;
 
@@ -284,6 +286,20 @@ static unsigned long long *work_slot(grr_handle_s *h) {
     }
   }
   return h->d_work + (h->next_work++ % kWorkRing);
+}
+
+// device scratch of at least `words` 64-bit words (grow-only; reallocation synchronises the device)
+static unsigned long long *scratch_for(grr_handle_s *h, size_t words) {
+  if (h->scratch_words < words) {
+    if (h->d_scratch) { cudaDeviceSynchronize(); cudaFree(h->d_scratch); h->d_scratch = nullptr; h->scratch_words = 0; }
+    const size_t want = words + words / 4 + 1024;
+    if (cudaMalloc(&h->d_scratch, sizeof(unsigned long long) * want) != cudaSuccess) {
+      set_error("cudaMalloc(scratch, %zu words) failed: %s", want, cudaGetErrorString(cudaGetLastError()));
+      return nullptr;
+    }
+    h->scratch_words = want;
+  }
+  return h->d_scratch;
 }
 
 #define GRR_CHECK_HANDLE(h)                                   \
@@ -328,7 +344,11 @@ int grr_chain_create(const grr_chain_desc *d, int device, grr_handle_t *out) {
 }
 
 int grr_chain_destroy(grr_handle_t h) {
-  if (h && h->d_work) { cudaSetDevice(h->hc.device); cudaFree(h->d_work); }
+  if (h && (h->d_work || h->d_scratch)) {
+    cudaSetDevice(h->hc.device);
+    if (h->d_work) cudaFree(h->d_work);
+    if (h->d_scratch) cudaFree(h->d_scratch);
+  }
   delete h;
   return 0;
 }
@@ -457,7 +477,9 @@ int grr_edges_build(grr_handle_t h, int dtype, int64_t E, const int32_t *wedges,
   if (E == 0) return 0;
   unsigned long long *work = work_slot(h);
   if (!work) return -3;
-  return ops->edges_build(h->hc, E, wedges, params, q_kept, count, old_count, Nq, Nqp, epsilon, mask, edge_stats, work,
+  unsigned long long *scratch = scratch_for(h, (size_t)E + 1);
+  if (!scratch) return -3;
+  return ops->edges_build(h->hc, E, wedges, params, q_kept, count, old_count, Nq, Nqp, epsilon, mask, edge_stats, work, scratch,
                           (unsigned long long *)counters, (cudaStream_t)stream);
 }
 

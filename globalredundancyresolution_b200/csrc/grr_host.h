@@ -36,7 +36,8 @@ struct Ops {
                           unsigned long long *counters, cudaStream_t st);
   int (*edges_build)(const HostChain &, long long E, const int32_t *wedges, const void *params, const void *q_kept,
                      const int32_t *count, const int32_t *old_count, int Nq, int Nqp, double epsilon, uint32_t *mask,
-                     uint32_t *edge_stats, unsigned long long *work, unsigned long long *counters, cudaStream_t st);
+                     uint32_t *edge_stats, unsigned long long *work, unsigned long long *scratch /* E+1 words or null */,
+                     unsigned long long *counters, cudaStream_t st);
 };
 
 const Ops *ops_f32_m3();

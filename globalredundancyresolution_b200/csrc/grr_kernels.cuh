@@ -434,6 +434,181 @@ k_edges_build(const __grid_constant__ ChainDev<Real, kMaxJ> c, const int32_t *__
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// E1/E3 for SPARSE roadmaps (a few configs per node: 6-D tasks, arms with narrow reach -- BASELINE configs
+// 3-5 have 18-200 pair tests per workspace edge).  A CTA per workspace edge then holds 1-3 pairs per lane and
+// most lanes idle while the longest pair finishes.  Here the pairs of ALL workspace edges form one queue:
+// offs[e] = pairs of the edges before e (exclusive scan of count[iw]*count[jw]); persistent lanes run them as
+// independent lane machines.  A warp takes 32 consecutive queue positions at a time, decodes them together
+// (binary search in offs, all lanes at once) into a per-warp shared-memory buffer, and hands them to its lanes
+// as they become free, so the decode costs ~1/32 of a search per pair and no lane waits for another lane's
+// pair.  Endpoint configs are read in place from Q (the few configs of a node stay in L1); verdict bits are
+// OR-ed into the global mask, which k_edges_prepare cleared (keeping both-old bits, solver.py:694).
+// ------------------------------------------------------------------------------------------
+static __global__ void k_edges_prepare(long long E, const int32_t *__restrict__ wedges, const int32_t *__restrict__ count,
+                                       const int32_t *__restrict__ old_count, int Nq, int Wd, uint32_t *mask,
+                                       unsigned long long *offs, uint32_t *edge_stats) {
+  const long long e = blockIdx.x;
+  const int iw = wedges[2 * e], jw = wedges[2 * e + 1];
+  const int ca = count[iw], cb = count[jw];
+  const int oa = old_count ? old_count[iw] : 0, ob = old_count ? old_count[jw] : 0;
+  uint32_t *mrow = mask + e * (long long)Nq * Wd;
+  for (int k = threadIdx.x; k < Nq * Wd; k += blockDim.x) {
+    uint32_t w = 0;
+    if (old_count) {
+      const int a = k / Wd, b0 = (k - a * Wd) * 32;
+      if (a < oa && b0 < ob) { w = mrow[k]; if (ob - b0 < 32) w &= (1u << (ob - b0)) - 1u; }
+    }
+    mrow[k] = w;
+  }
+  if (threadIdx.x == 0) {
+    offs[e + 1] = (unsigned long long)ca * (unsigned long long)cb;     // queue positions (both-old ones are skipped on decode)
+    if (e == 0) offs[0] = 0;
+    if (edge_stats) edge_stats[2 * e] = (uint32_t)((long long)ca * cb - (long long)oa * ob);
+  }
+}
+
+// in-place inclusive scan of a[1..N] (a[0] = 0 stays): one CTA of 1024 threads, a contiguous chunk per thread
+static __global__ void __launch_bounds__(1024) k_scan_u64(long long N, unsigned long long *a) {
+  __shared__ unsigned long long part[1024];
+  const long long chunk = (N + 1023) / 1024;
+  const long long lo = 1 + (long long)threadIdx.x * chunk, hi = min(lo + chunk, N + 1);
+  unsigned long long s = 0;
+  for (long long k = lo; k < hi; k++) s += a[k];
+  part[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 1; o < 1024; o <<= 1) {
+    const unsigned long long v = (threadIdx.x >= (unsigned)o) ? part[threadIdx.x - o] : 0;
+    __syncthreads();
+    part[threadIdx.x] += v;
+    __syncthreads();
+  }
+  unsigned long long run = part[threadIdx.x] - s;
+  for (long long k = lo; k < hi; k++) { run += a[k]; a[k] = run; }
+}
+
+// valid bits now stored per workspace edge -> edge_stats[e][1]
+static __global__ void k_edges_bits(long long E, int words, const uint32_t *__restrict__ mask, uint32_t *edge_stats) {
+  const long long e = blockIdx.x;
+  const uint32_t *mrow = mask + e * (long long)words;
+  unsigned nb = 0;
+  for (int k = threadIdx.x; k < words; k += blockDim.x) nb += __popc(mrow[k]);
+  nb = __reduce_add_sync(0xffffffffu, nb);
+  __shared__ unsigned s_bits;
+  if (threadIdx.x == 0) s_bits = 0;
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0 && nb) atomicAdd(&s_bits, nb);
+  __syncthreads();
+  if (threadIdx.x == 0) edge_stats[2 * e + 1] = s_bits;
+}
+
+template <typename Real, int M, bool PL>
+__global__ void __launch_bounds__(128, (sizeof(Real) == 4 ? (M == 3 ? 4 : 3) : 2))
+k_edges_flat(const __grid_constant__ ChainDev<Real, kMaxJ> c, long long E, const int32_t *__restrict__ wedges,
+             const Real *__restrict__ params, const Real *__restrict__ q_kept, const int32_t *__restrict__ count,
+             const int32_t *__restrict__ old_count, int Nq, int Nqp, Real epsilon, uint32_t *mask,
+             const unsigned long long *__restrict__ offs, unsigned long long *work, unsigned long long *counters) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int n = c.n, dw = (c.mode == 2 ? 6 : 3);
+  const int Wd = (Nq + 31) >> 5;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // per-warp buffer of decoded queue positions: {workspace edge, a << 16 | b}
+  int2 *queue = reinterpret_cast<int2 *>(smem_raw) + warp * 32;
+  Real *lanes = reinterpret_cast<Real *>(reinterpret_cast<int2 *>(smem_raw) + (blockDim.x >> 5) * 32);
+  LaneMem<Real, col_rows(M, PL)> mem;
+  mem.init(lanes + threadIdx.x, (int)blockDim.x, n);
+  for (int j = 0; j < lane_reals<col_rows(M, PL)>(n); j++) mem.base[j * mem.T] = 0;
+  const unsigned long long total = offs[E];
+  const Real eps = epsilon * sqrt_(Real(c.nlinks_eps));
+  const Real thr = eps * Real(c.nlinks_eps);
+  const Real thr2 = thr * thr;
+  LaneIK<Real, M> L;
+  lane_begin_mem(L, mem);
+  PairLane<Real> P;
+  WInterp<Real, M> W;
+  Target<Real, M> tg;
+  tg.x[0] = tg.x[1] = tg.x[2] = 0;
+  if (M == 6) { for (int k = 0; k < 9; k++) tg.R[k] = (k % 4 == 0) ? Real(1) : Real(0); }
+  LaneCounters cnt;
+  long long edge = -1;               // this lane's pair: workspace edge, (a, b)
+  int a = 0, b = 0;
+  int qhead = 0, qtail = 0;          // warp-uniform
+  bool exhausted = false;            // warp-uniform: the global queue has no positions left
+  __syncwarp();
+  for (;;) {
+    int verdict = -1;
+    // ---- hand queue positions to the idle lanes of this warp ----
+    unsigned needm = __ballot_sync(0xffffffffu, edge < 0);
+    while (needm) {
+      if (qhead == qtail) {
+        if (exhausted) break;
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(work, 32ull);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= total) { exhausted = true; break; }
+        const unsigned long long t = base + lane;
+        bool ok = t < total;
+        long long e = 0;
+        int ta = 0, tb = 0;
+        if (ok) {
+          long long lo = 0, hi = E;                              // offs[lo] <= t < offs[hi]
+          while (hi - lo > 1) { const long long mid = (lo + hi) >> 1; if (offs[mid] <= t) lo = mid; else hi = mid; }
+          e = lo;
+          const int iw = wedges[2 * e], jw = wedges[2 * e + 1];
+          const unsigned cb = (unsigned)count[jw];
+          const unsigned off = (unsigned)(t - offs[e]);
+          ta = (int)(off / cb); tb = (int)(off - (unsigned)ta * cb);
+          if (old_count && ta < old_count[iw] && tb < old_count[jw]) ok = false;      // solver.py:694
+        }
+        const unsigned okm = __ballot_sync(0xffffffffu, ok);
+        if (ok) queue[__popc(okm & ((1u << lane) - 1u))] = make_int2((int)e, (int)(((unsigned)ta << 16) | (unsigned)tb));
+        __syncwarp();
+        qhead = 0; qtail = __popc(okm);
+        continue;
+      }
+      const int rank = __popc(needm & ((1u << lane) - 1u)), avail = qtail - qhead;
+      if (edge < 0 && rank < avail) {
+        const int2 ent = queue[qhead + rank];
+        edge = ent.x; a = (int)((unsigned)ent.y >> 16); b = ent.y & 0xffff;
+        const int iw = wedges[2 * edge], jw = wedges[2 * edge + 1];
+        Real a6[6], b6[6];
+        for (int k = 0; k < dw; k++) { a6[k] = params[(long long)iw * dw + k]; b6[k] = params[(long long)jw * dw + k]; }
+        winterp_begin<Real, M, kMaxJ>(c, a6, b6, W);
+        P.qa = q_kept + (long long)iw * n * Nqp + a; P.qb = q_kept + (long long)jw * n * Nqp + b; P.sa = Nqp; P.sb = Nqp;
+        if (!pair_begin<Real, M>(c, eps, P, L)) verdict = 1;
+        else winterp_at<Real, M>(W, Real(1) / Real(P.ndivs + 1), tg);
+      }
+      __syncwarp();
+      qhead += min(__popc(needm), avail);
+      needm = __ballot_sync(0xffffffffu, edge < 0);
+    }
+    if (__all_sync(0xffffffffu, edge < 0)) break;                // nothing running and nothing left to hand out
+    const bool running = (edge >= 0 && verdict < 0);
+    if (__any_sync(0xffffffffu, running)) {
+      PassOut<Real, M> o;
+      const bool first = running && P.k == 1;
+      if constexpr (PL) lane_pass_planar<Real, true>(c, tg, L, mem, first ? P.qa : mem.prev(), first ? P.sa : mem.T, o);
+      else lane_pass<Real, M, true>(c, tg, L, mem, first ? P.qa : mem.prev(), first ? P.sa : mem.T, o);
+      const int st = lane_step<Real, M, PL>(c, L, mem, o, running);
+      if (running && st != IK_RUNNING) {
+        cnt.solves++; cnt.iters += L.it; cnt.evals += L.evals; cnt.ok += (st == IK_OK);
+        if (st != IK_OK) verdict = 0;                             // graph.py:964-966
+        else {
+          verdict = pair_advance(c, mem, o.s2, thr2, P, L);
+          if (verdict < 0) winterp_at<Real, M>(W, Real(P.k) / Real(P.ndivs + 1), tg);
+        }
+      }
+    }
+    if (edge >= 0 && verdict >= 0) {
+      if (verdict) atomicOr(&mask[(edge * Nq + a) * Wd + (b >> 5)], 1u << (b & 31));
+      cnt.pairs++; cnt.valid += verdict;
+      edge = -1;
+      lane_begin_mem(L, mem);   // idle lanes keep walking valid memory
+    }
+  }
+  cnt.flush(counters);
+}
+
 // pair-test load of an edge list: out[0] += pairs that will be tested, out[1] += edges with at least one
 static __global__ void k_edge_load(long long E, const int32_t *__restrict__ wedges, const int32_t *__restrict__ count,
                             const int32_t *__restrict__ old_count, unsigned long long *out) {
@@ -608,30 +783,50 @@ struct Impl {
   }
   static int edges_build(const HostChain &h, long long E, const int32_t *wedges, const void *params, const void *q_kept,
                          const int32_t *count, const int32_t *old_count, int Nq, int Nqp, double epsilon,
-                         uint32_t *mask, uint32_t *edge_stats, unsigned long long *work, unsigned long long *counters,
-                         cudaStream_t st) {
+                         uint32_t *mask, uint32_t *edge_stats, unsigned long long *work, unsigned long long *scratch,
+                         unsigned long long *counters, cudaStream_t st) {
     if (E <= 0) return 0;
     Chain c; fill_chain(h, c);
     const int Wd = (Nq + 31) / 32;
     const size_t fixed = 2 * (size_t)h.n * Nqp * sizeof(Real) + (size_t)((Nq * Wd + 3) & ~3) * sizeof(uint32_t);
     int threads, per_sm;
     lane_geometry(h, fixed, sizeof(Real) == 4 ? (M == 3 ? 512 : 384) : 256, threads, per_sm);
-    if (threads < 32) { set_error("edges_build: Nq=%d, n=%d does not fit shared memory", Nq, h.n); return -2; }
-    // CTA size follows the work per workspace edge: a CTA owns one edge, so lanes beyond pairs/~6 would idle
-    // for the whole edge (sparse roadmaps: a few configs per node).  One tiny reduction + an 16-byte readback.
+    // The work per workspace edge decides the kernel: one tiny reduction + a 16-byte readback.
+    double avg = 0;
     {
       unsigned long long hload[2] = {0, 0};
       cudaMemsetAsync(work, 0, 2 * sizeof(unsigned long long), st);
       k_edge_load<<<(unsigned)((E + 255) / 256), 256, 0, st>>>(E, wedges, count, old_count, work);
       cudaMemcpyAsync(hload, work, sizeof hload, cudaMemcpyDeviceToHost, st);
       cudaStreamSynchronize(st);
-      if (hload[1] > 0) {
-        const double avg = (double)hload[0] / (double)hload[1];
-        int want = (int)((avg / 6.0 + 31.0) / 32.0) * 32;
-        if (want < 32) want = 32;
-        if (want < threads) threads = want;
+      if (hload[1] > 0) avg = (double)hload[0] / (double)hload[1];
+    }
+    // dense: a CTA owns one workspace edge, so lanes beyond pairs/~6 would idle for the whole edge
+    int dense_threads = threads;
+    if (avg > 0 && threads >= 32) {
+      int want = (int)((avg / 6.0 + 31.0) / 32.0) * 32;
+      if (want < 32) want = 32;
+      if (want < dense_threads) dense_threads = want;
+    }
+    // Which kernel: the per-edge CTAs lose the tail of every edge (a lane runs avg/threads pairs whose
+    // durations differ by +-50 %), the global queue loses the staging of the node blocks (configs are read from
+    // L1/L2, which costs more the longer the chain).  Fitted to the five BASELINE configs (profiles/r01_edge_kernel.md):
+    //   dense ~ rounds / (rounds + 1.3),  flat ~ 1 - 0.009 n.
+    bool flat = false;
+    if (scratch) {
+      if (threads < 32) flat = true;                              // node blocks too large to stage
+      else if (avg > 0) {
+        const double rounds = avg / dense_threads;
+        flat = (1.0 - 0.009 * h.n) > rounds / (rounds + 1.3);
       }
     }
+    const char *force = getenv("GRR_EDGES");                      // "flat" / "dense": A/B switch for tests and profiling
+    if (force && scratch && !strcmp(force, "flat")) flat = true;
+    if (force && threads >= 32 && !strcmp(force, "dense")) flat = false;
+    if (flat) return edges_flat(h, c, E, wedges, params, q_kept, count, old_count, Nq, Nqp, epsilon, mask, edge_stats, work,
+                                scratch, counters, st);
+    if (threads < 32) { set_error("edges_build: Nq=%d, n=%d does not fit shared memory", Nq, h.n); return -2; }
+    threads = dense_threads;
     const size_t smem = fixed + (size_t)threads * h.n * (4 + mc(h)) * sizeof(Real);
     auto launch = [&](auto kern) -> int {
       if (set_smem(kern, smem, "k_edges_build")) return -2;
@@ -644,6 +839,41 @@ struct Impl {
     else rc = launch(k_edges_build<Real, M, false>);
     if (rc) return rc;
     return check_launch("k_edges_build");
+  }
+
+  static int edges_flat(const HostChain &h, const Chain &c, long long E, const int32_t *wedges, const void *params,
+                        const void *q_kept, const int32_t *count, const int32_t *old_count, int Nq, int Nqp, double epsilon,
+                        uint32_t *mask, uint32_t *edge_stats, unsigned long long *work, unsigned long long *offs,
+                        unsigned long long *counters, cudaStream_t st) {
+    const int Wd = (Nq + 31) / 32;
+    k_edges_prepare<<<(unsigned)E, 128, 0, st>>>(E, wedges, count, old_count, Nq, Wd, mask, offs, edge_stats);
+    if (int rc = check_launch("k_edges_prepare")) return rc;
+    k_scan_u64<<<1, 1024, 0, st>>>(E, offs);
+    if (int rc = check_launch("k_scan_u64")) return rc;
+    cudaMemsetAsync(work, 0, sizeof(unsigned long long), st);
+    const int threads = 128;
+    const size_t smem = (size_t)(threads / 32) * 32 * sizeof(int2) + (size_t)threads * h.n * (4 + mc(h)) * sizeof(Real);
+    auto launch = [&](auto kern) -> int {
+      if (set_smem(kern, smem, "k_edges_flat")) return -2;
+      int per_sm = 0;
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem) != cudaSuccess || per_sm < 1) {
+        set_error("k_edges_flat: n=%d does not fit shared memory", h.n); return -2;
+      }
+      kern<<<(unsigned)(sm_count(h.device) * per_sm), threads, smem, st>>>(c, E, wedges, (const Real *)params, (const Real *)q_kept,
+                                                                           count, old_count, Nq, Nqp, (Real)epsilon, mask, offs,
+                                                                           work, counters);
+      return 0;
+    };
+    int rc;
+    if constexpr (kHasPlanar) rc = planar(h) ? launch(k_edges_flat<Real, M, true>) : launch(k_edges_flat<Real, M, false>);
+    else rc = launch(k_edges_flat<Real, M, false>);
+    if (rc) return rc;
+    if (int rc2 = check_launch("k_edges_flat")) return rc2;
+    if (edge_stats) {
+      k_edges_bits<<<(unsigned)E, 128, 0, st>>>(E, Nq * Wd, mask, edge_stats);
+      return check_launch("k_edges_bits");
+    }
+    return 0;
   }
 };
 

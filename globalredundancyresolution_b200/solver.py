@@ -660,6 +660,10 @@ class RedundancyResolver:
         if d is not None and self.Nq > 0:
             out.update({"Qs": d["Qs"].cpu().numpy(), "count": d["count"].cpu().numpy(), "mask": d["mask"].cpu().numpy()})
         np.savez_compressed(os.path.join(folder, "roadmap_b200.npz"), **out)
+        if len(self.Qsubgraph) > 0:                              # solver.py:281-285, same text format
+            with open(os.path.join(folder, "Qsubgraph_cached.txt"), "w") as f:
+                for k, v in sorted(self.Qsubgraph.items()):
+                    f.write(str(k) + " " + str(v) + "\n")
 
     def load(self, folder):
         """Resume from save(): the roadmap goes back to the device; a following sampleConfigurationSpace call grows
@@ -681,6 +685,13 @@ class RedundancyResolver:
             if d["Qs"] is not d["Q"]:
                 d["Q"].copy_(d["Qs"])
             self.attempts = int(z["attempts"])
+        self.Qsubgraph = dict()
+        fn = os.path.join(folder, "Qsubgraph_cached.txt")
+        if os.path.exists(fn):                                   # solver.py:305-313
+            with open(fn) as f:
+                for line in f:
+                    k, v = line.split()
+                    self.Qsubgraph[int(k)] = int(v)
         self.sanityCheck()
 
     # ---- consumer seam: the CSP of the resolution stage (solver.py:984-1022) ---------------------------

@@ -163,6 +163,15 @@ def test_solve_csp_sets_the_resolution(built):
     before = dict(rr.Qsubgraph)
     rr.decodeCSPAssignment(enc)
     assert rr.Qsubgraph == before
+    # checkpoint: Qsubgraph_cached.txt in the reference's text format (solver.py:281-285, :305-313)
+    import tempfile
+    with tempfile.TemporaryDirectory() as tmp:
+        rr.save(tmp)
+        lines = open(os.path.join(tmp, "Qsubgraph_cached.txt")).read().split("\n")
+        assert lines[0] == "%d %d" % sorted(before.items())[0]
+        rr2 = grr.RedundancyResolver(res, seed=5)
+        rr2.load(tmp)
+        assert rr2.Qsubgraph == before and (rr2.counts() == rr.counts()).all()
     # a descent from the current assignment (perturbed) keeps a full assignment
     rr.randomDescentAssignment(randomize=False)
     assert set(rr.Qsubgraph) == set(before)

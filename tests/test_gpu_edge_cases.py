@@ -203,3 +203,37 @@ def test_node_block_gather_scatter_and_edge_cost(built):
     res.chain.fk_batch(q, p)
     th = np.cumsum(q.double().cpu().numpy(), axis=0)
     np.testing.assert_allclose(p.cpu().numpy(), np.stack([np.cos(th).sum(0), 0 * th[0], -np.sin(th).sum(0)], axis=1), atol=2e-6)
+
+
+@pytest.mark.parametrize("problem", [("planar_3R", "Rfree.json", 150, 14), ("jaco", "Rfixed.json", 300, 40),
+                                     ("baxter", "Rfree.json", 150, 20)])
+def test_dense_and_flat_edge_kernels_agree(built, problem, monkeypatch):
+    """grr_edges_build picks one of two kernels from the pair load: a CTA per workspace edge (dense roadmaps) or one
+    global queue of pairs (sparse roadmaps).  Same lane machine and the same pairs, also for incremental growth
+    (both-old pairs skipped, old bits kept): pair counts are identical; verdicts and IK work agree up to the
+    FP32 rounding differences between two separately compiled instances of the pass (the compiler contracts
+    a*b+c*d differently; measured: identical masks, 3 of 30,280 solves)."""
+    from helpers import small_problem
+    name, jf, Nw, Nq = problem
+    out = {}
+    for kind in ("dense", "flat"):
+        monkeypatch.setenv("GRR_EDGES", kind)
+        pdef, res = small_problem(name, jf, Nw, "staggered_grid")
+        rr = grr.RedundancyResolver(res, seed=11)
+        rr.sampleConfigurationSpace(Nq // 2, order_independent=True)
+        first = (rr._dev["mask"].cpu().numpy().copy(), rr._dev["edge_stats"].cpu().numpy().copy(), dict(rr.stats))
+        rr.sampleConfigurationSpace(Nq, order_independent=True)            # grows: only pairs with a new endpoint
+        out[kind] = (first, rr._dev["mask"].cpu().numpy().copy(), rr._dev["edge_stats"].cpu().numpy().copy(), dict(rr.stats),
+                     rr.counts().copy())
+    d, f = out["dense"], out["flat"]
+    np.testing.assert_array_equal(d[4], f[4])
+    np.testing.assert_array_equal(d[0][1][:, 0], f[0][1][:, 0])        # pairs tested per workspace edge, first call
+    np.testing.assert_array_equal(d[2][:, 0], f[2][:, 0])              # ... growth call
+    assert d[0][2]["pairs"] == f[0][2]["pairs"] and d[3]["pairs"] == f[3]["pairs"] > 0
+    tol = max(2, int(1e-3 * d[3]["pairs"]))
+    for md, mf in ((d[0][0], f[0][0]), (d[1], f[1])):
+        x = (md ^ mf).view(np.uint8)
+        assert int(np.unpackbits(x).sum()) <= tol
+    for k in ("valid", "ik_solves", "ik_iters", "ik_evals"):
+        assert abs(d[0][2][k] - f[0][2][k]) <= 2e-3 * d[0][2][k] + 2 and abs(d[3][k] - f[3][k]) <= 2e-3 * d[3][k] + 2, k
+    assert abs(int(d[2][:, 1].sum()) - int(f[2][:, 1].sum())) <= tol
