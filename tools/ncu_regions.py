@@ -14,7 +14,7 @@ for a, op, e, t, s in ins:
     m = re.search(r"BRA(?:\.U)?\s+(?:!?U?P\d+,\s*)*(0x[0-9a-f]+)", op)
     if m:
         tgt = int(m.group(1), 16) - base
-        if 0 <= tgt <= a and a - tgt < 0x1000:
+        if 0 <= tgt <= a and a - tgt < 0x3000:
             loops.append((tgt, a))
 covered = set()
 print(f"total warp instructions {tot:.4g}, samples {tots}")
