@@ -388,9 +388,10 @@ class RedundancyResolver:
         res.chain.dedup(q_raw, status, DEDUP_THRESHOLD, d["Qs"][lo:hi], d["count"][lo:hi], Nq=N, count_in=count_in)
         self._last_raw = (q_raw, status, iters)
 
-    def _sample_phase_nodes(self, d, N, nodes):
+    def _sample_phase_nodes(self, d, N, nodes, thresh=DEDUP_THRESHOLD):
         """Same for an arbitrary node list (device int32 tensor): one launch over the gathered nodes, dedup into a
-        compact buffer, whole node blocks scattered back (used by the interleaved shards of ShardedResolver)."""
+        compact buffer, whole node blocks scattered back (used by the interleaved shards of ShardedResolver).
+        thresh=0 keeps every converged attempt (the reference's addNode path, solver.py:2007)."""
         torch = self.resolution._torch()
         res = self.resolution
         sdt = self._sdt()
@@ -407,7 +408,7 @@ class RedundancyResolver:
         kcount = torch.empty(nn, dtype=torch.int32, device=res.torch_device)
         _cabi.gather_node_blocks(nodes, d["Qs"], d["count"], kept, kcount)
         cin = kcount.clone()
-        res.chain.dedup(q_raw, status, DEDUP_THRESHOLD, kept, kcount, Nq=N, count_in=cin)
+        res.chain.dedup(q_raw, status, thresh, kept, kcount, Nq=N, count_in=cin)
         _cabi.scatter_node_blocks(nodes, kept, kcount, d["Qs"], d["count"])
 
     def _connect_phase(self, d, old_counts):
@@ -813,6 +814,40 @@ class RedundancyResolver:
                              "solve_time": solve_time}
         self.decodeCSPAssignment(a[best])
         return bestConflicts, "random", solve_time, 0
+
+    def sampleConflicts(self, NConfigsPerPoint=10):
+        """solver.py:1988-2033: the refinement step between two solveCSP calls.  Conflict nodes = both
+        endpoints of every workspace edge whose endpoints are resolved but which is not connected in the resolution;
+        2 * NConfigsPerPoint more random-start IK solves at each of them (the reference's second loop, "local solving
+        from neighbors", also runs with startRandom=True (solver.py:2012), i.e. its seed is replaced by a random start),
+        every converged attempt appended without dedup (addNode, solver.py:2007, :2020), then every pair with a new
+        endpoint on the workspace edges around those nodes is tested (solver.py:2024-2031).  One sampling launch over
+        the conflict nodes and one incremental edge launch.  Returns (configs added, pairs tested, pairs connected)."""
+        torch = self.resolution._torch()
+        res = self.resolution
+        conflicts = set()
+        for i, j in res.Gw.edges_iter():
+            if res.isResolvedEdge(i, j) or not res.isResolvedNode(i) or not res.isResolvedNode(j):
+                continue
+            conflicts.add(int(i)); conflicts.add(int(j))
+        if not conflicts or self._dev is None or self.Nq == 0:
+            return 0, 0, 0
+        N = 2 * int(NConfigsPerPoint)
+        nodes_h = np.asarray(sorted(conflicts), dtype=np.int32)
+        old = self.counts().astype(np.int32).copy()
+        d = self._ensure_device(max(self.Nq, int(old[nodes_h].max()) + N))
+        d["counters"].zero_(); d["counters_e"].zero_()
+        nodes = torch.from_numpy(nodes_h).to(res.torch_device)
+        self._sample_phase_nodes(d, N, nodes, thresh=0.0)
+        self.attempts += N
+        eids = [e for e, (a, b) in enumerate(self._edges_host) if a in conflicts or b in conflicts]
+        self._connect(eids, old)
+        self._invalidate()
+        ce = d["counters_e"].cpu().numpy()
+        added = int(self.counts().sum() - old.sum())
+        self.stats.update({"conflict_nodes": len(conflicts), "conflict_configs_added": added,
+                           "pairs": int(ce[_cabi.CNT_PAIRS]), "valid": int(ce[_cabi.CNT_VALID])})
+        return added, int(ce[_cabi.CNT_PAIRS]), int(ce[_cabi.CNT_VALID])
 
     # ---- sanity (solver.py:365-383) -------------------------------------------------------------------
     def sanityCheck(self):

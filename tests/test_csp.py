@@ -193,3 +193,50 @@ def test_csp_on_a_six_d_task(built):
         want, _ = ref.random_descent(csp.to_reference(a0[g]), order_key=key)
         assert csp.to_reference(a1[g]) == want
     assert (a1[:, rr.counts() == 0] == -1).all()
+
+
+@pytest.mark.gpu
+def test_sample_conflicts_refines_around_conflict_nodes(built):
+    """solver.py:1988-2033: more configs at the endpoints of unresolved edges, appended without dedup, connected
+    incrementally; everything else untouched; the roadmap invariants hold; a second solveCSP can only start better."""
+    from helpers import oracle_for, unpack_mask
+    res, rr = _roadmap(Nw=150, Nq=8)
+    c0, _, _, _ = rr.solveCSP(numInitialGuesses=4)
+    assert c0 > 0, "test problem resolved without conflicts"
+    conflicts = set()
+    for i, j in res.Gw.edges_iter():
+        if not res.isResolvedEdge(i, j) and res.isResolvedNode(i) and res.isResolvedNode(j):
+            conflicts.update((i, j))
+    cnt0 = rr.counts().copy()
+    mask0 = unpack_mask(rr._dev["mask"].cpu().numpy(), rr.Nq)
+    Nq0 = rr.Nq
+    qsub = dict(rr.Qsubgraph)
+    q_before = {i: rr.Gw.node[i]["qlist"] for i in list(conflicts)[:5]}
+    added, tested, connected = rr.sampleConflicts(3)
+    cnt1 = rr.counts()
+    assert added == int(cnt1.sum() - cnt0.sum()) > 0
+    grown = set(np.nonzero(cnt1 > cnt0)[0].tolist())
+    assert grown <= conflicts and (cnt1 - cnt0).max() <= 6
+    # old configs keep their indices, old verdicts are kept, Qsubgraph stays valid
+    for i, ql in q_before.items():
+        assert rr.Gw.node[i]["qlist"][:len(ql)] == ql
+    mask1 = unpack_mask(rr._dev["mask"].cpu().numpy(), rr.Nq)
+    e = res.ws_edges
+    for k in range(len(e)):
+        a, b = cnt0[e[k, 0]], cnt0[e[k, 1]]
+        assert (mask1[k, :a, :b] == mask0[k, :a, :b]).all()
+    # pairs tested = pairs with a new endpoint on the workspace edges around conflict nodes
+    want = sum(int(cnt1[a]) * int(cnt1[b]) - int(cnt0[a]) * int(cnt0[b]) for a, b in e.tolist() if a in conflicts or b in conflicts)
+    assert tested == want and 0 < connected <= tested
+    # new configs solve their node's IK problem; new verdicts match the oracle
+    o = oracle_for(res)
+    for i in list(grown)[:10]:
+        for q in rr.Gw.node[i]["qlist"][cnt0[i]:]:
+            assert res.ikError(q, res.Gw.node[i]["params"]) < 2e-3
+    Q = np.transpose(rr._dev["Q"][:, :, :rr.Nq].double().cpu().numpy(), (0, 2, 1)).copy()
+    pick = np.asarray([k for k, (a, b) in enumerate(e.tolist()) if a in grown or b in grown][:40])
+    mask_ref, stats = o.connect_edges(e[pick], res.ws_params, Q, cnt1, rr.Nq)
+    assert int((mask1[pick] != mask_ref.astype(bool)).sum()) <= max(1, int(2e-3 * stats[:, 0].sum()))
+    assert rr.Qsubgraph == qsub
+    c1, _, _, _ = rr.solveCSP(numInitialGuesses=4)
+    assert set(rr.Qsubgraph) == set(np.nonzero(cnt1 > 0)[0].tolist())
