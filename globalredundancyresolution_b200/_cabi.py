@@ -12,7 +12,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libgrr_b200.so")
+# GRR_LIB: load another build of the same library, e.g. the one with index checks (`make debug`)
+LIB_PATH = os.environ.get("GRR_LIB") or os.path.join(_HERE, "libgrr_b200.so")
 
 GRR_F32, GRR_F64 = 0, 1
 GRR_FREE, GRR_FIXED, GRR_VARIABLE = 0, 1, 2

@@ -36,6 +36,7 @@ __device__ __forceinline__ int csp_conflict(const uint32_t *__restrict__ mask, c
   const long long e = second ? ~ee : ee;
   if (!edge_active[e] || other < 0) return 0;           // no constraint (solver.py:1019) / unassigned (csp.py:144)
   const int r = second ? other : val, cbit = second ? val : other;
+  GRR_DCHECK(r >= 0 && r < Nq && cbit >= 0 && cbit < Nq);
   const uint32_t w = mask[(e * Nq + r) * W + (cbit >> 5)];
   return ((w >> (cbit & 31)) & 1u) ? 0 : 1;
 }
@@ -97,6 +98,7 @@ k_csp_sweep(int n_list, const int32_t *__restrict__ node_list, int Nw, int Nq, i
   const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (w >= (long long)n_list * G) return;
   const int g = (int)(w / n_list), i = node_list[w - (long long)g * n_list];
+  GRR_DCHECK(i >= 0 && i < Nw && g < G);
   int32_t *a = asg + (long long)g * Nw;
   const int c = count[i];
   const int cur = a[i];

@@ -19,9 +19,19 @@
 // p = -J^T (J J^T + lambda^2 I)^-1 F is invariant under that change of frame.  The Newton
 // iteration itself (a resumable per-lane state machine) is in grr_lane.cuh.
 #pragma once
+#include <stdio.h>
 #include <cuda_runtime.h>
 #include <math_constants.h>
 #include <stdint.h>
+
+// Index checks of our own for the kernels with data-dependent addressing (the global pair queue, the CSP
+// sweeps): compiled in with -DGRR_DEBUG_CHECKS (`make debug` -> libgrr_b200_dbg.so, loaded with GRR_LIB=...);
+// a failed check traps, which surfaces as a launch error of the ABI call.
+#ifdef GRR_DEBUG_CHECKS
+#define GRR_DCHECK(cond) do { if (!(cond)) { printf("GRR_DCHECK failed: %s (%s:%d)\n", #cond, __FILE__, __LINE__); __trap(); } } while (0)
+#else
+#define GRR_DCHECK(cond) do { } while (0)
+#endif
 
 namespace grr {
 

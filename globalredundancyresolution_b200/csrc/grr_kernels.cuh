@@ -558,6 +558,7 @@ k_edges_flat(const __grid_constant__ ChainDev<Real, kMaxJ> c, long long E, const
           const unsigned cb = (unsigned)count[jw];
           const unsigned off = (unsigned)(t - offs[e]);
           ta = (int)(off / cb); tb = (int)(off - (unsigned)ta * cb);
+          GRR_DCHECK(e >= 0 && e < E && offs[e] <= t && t < offs[e + 1] && cb > 0 && ta < count[iw] && tb < (int)cb && ta < Nq && tb < Nq);
           if (old_count && ta < old_count[iw] && tb < old_count[jw]) ok = false;      // solver.py:694
         }
         const unsigned okm = __ballot_sync(0xffffffffu, ok);
@@ -568,6 +569,7 @@ k_edges_flat(const __grid_constant__ ChainDev<Real, kMaxJ> c, long long E, const
       }
       const int rank = __popc(needm & ((1u << lane) - 1u)), avail = qtail - qhead;
       if (edge < 0 && rank < avail) {
+        GRR_DCHECK(qhead + rank < 32 && qtail <= 32);
         const int2 ent = queue[qhead + rank];
         edge = ent.x; a = (int)((unsigned)ent.y >> 16); b = ent.y & 0xffff;
         const int iw = wedges[2 * edge], jw = wedges[2 * edge + 1];
@@ -600,6 +602,7 @@ k_edges_flat(const __grid_constant__ ChainDev<Real, kMaxJ> c, long long E, const
       }
     }
     if (edge >= 0 && verdict >= 0) {
+      GRR_DCHECK(edge < E && a < Nq && b < Nq);
       if (verdict) atomicOr(&mask[(edge * Nq + a) * Wd + (b >> 5)], 1u << (b & 31));
       cnt.pairs++; cnt.valid += verdict;
       edge = -1;
