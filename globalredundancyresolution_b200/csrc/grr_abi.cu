@@ -472,7 +472,7 @@ int grr_edges_build(grr_handle_t h, int dtype, int64_t E, const int32_t *wedges,
   GRR_CHECK_HANDLE(h);
   const Ops *ops = pick_ops(dtype, h->hc.mode);
   if (!ops) { set_error("bad dtype %d", dtype); return -1; }
-  if (E < 0 || Nq < 1 || Nqp < Nq) { set_error("grr_edges_build: bad sizes"); return -1; }
+  if (E < 0 || Nq < 1 || Nq > 65535 || Nqp < Nq) { set_error("grr_edges_build: bad sizes (need 1 <= Nq <= 65535, Nqp >= Nq)"); return -1; }
   if (E > 0 && (!wedges || !params || !q_kept || !count || !mask)) { set_error("grr_edges_build: null buffer"); return -1; }
   if (E == 0) return 0;
   unsigned long long *work = work_slot(h);

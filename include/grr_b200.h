@@ -145,8 +145,11 @@ int grr_dedup(grr_handle_t h, int dtype, int64_t Nw, int32_t Nq, int32_t Nqp, co
  * predicate and sets bit b of mask[e][a][b/32].  mask [dev] u32 [E][Nq][W], W=(Nq+31)/32, is
  * fully overwritten for the edges given (bits of both-old pairs are carried over when old_count is
  * given).  edge_stats [dev] u32 [E][2] = {pairs tested by this call, valid bits now stored for the
- * edge} (nullable); counters nullable.  Synchronises `stream` once (16-byte readback of the pair-test load
- * to size the CTAs) before the main launch. */
+ * edge} (nullable); counters nullable.  Synchronises `stream` once (16-byte readback of the pair-test load)
+ * before the main launch: dense roadmaps run one CTA per workspace edge with both node blocks staged in shared
+ * memory, sparse ones (a few configs per node) one global queue of pairs served by persistent lanes; the handle
+ * keeps E+1 words of device scratch for the queue offsets.  Nq <= 65535.  Env GRR_EDGES=dense|flat overrides the
+ * choice (tests / profiling). */
 int grr_edges_build(grr_handle_t h, int dtype, int64_t E, const int32_t *wedges, const void *params,
                     const void *q_kept, const int32_t *count, const int32_t *old_count, int32_t Nq,
                     int32_t Nqp, double epsilon, uint32_t *mask, uint32_t *edge_stats, uint64_t *counters,
