@@ -749,9 +749,12 @@ struct Impl {
     const size_t per_lane = (size_t)h.n * (4 + mc(h)) * sizeof(Real);
     static const int force_one = getenv("GRR_ONE_CTA_PER_SM") != nullptr;   // experiment switch
     ctas_per_sm = force_one ? 1 : 2;
-    size_t per_cta = kSmemBudget / ctas_per_sm - 1024;
+    // per CTA: 1 KB reserved by the driver + the static shared memory of the kernels (k_edges_build: 4.1 KB of
+    // per-warp pair buffers and counters)
+    constexpr size_t kPerCtaOverhead = 1024 + 4352;
+    size_t per_cta = kSmemBudget / ctas_per_sm - kPerCtaOverhead;
     long t = per_cta > fixed_bytes ? (long)((per_cta - fixed_bytes) / per_lane) : 0;
-    if (t < 64) { ctas_per_sm = 1; per_cta = kSmemBudget - 1024; t = per_cta > fixed_bytes ? (long)((per_cta - fixed_bytes) / per_lane) : 0; }
+    if (t < 64) { ctas_per_sm = 1; per_cta = kSmemBudget - kPerCtaOverhead; t = per_cta > fixed_bytes ? (long)((per_cta - fixed_bytes) / per_lane) : 0; }
     if (t > max_threads) t = max_threads;
     threads = (int)(t / 32) * 32;
   }
