@@ -849,6 +849,125 @@ class RedundancyResolver:
                            "pairs": int(ce[_cabi.CNT_PAIRS]), "valid": int(ce[_cabi.CNT_VALID])})
         return added, int(ce[_cabi.CNT_PAIRS]), int(ce[_cabi.CNT_VALID])
 
+    def fromResolutionToGraph(self, clear=False):
+        """solver.py:2170-2185: every resolved config of the resolution becomes a (new) roadmap config of its node,
+        every connected edge of the resolution a C-space edge between them; Qsubgraph = that map.  Batched: one
+        scatter of the configs, one scatter of the edge bits."""
+        torch = self.resolution._torch()
+        res = self.resolution
+        if clear:
+            self.initWorkspaceGraph()
+        nodes = [i for i, dd in res.Gw.nodes_iter(data=True) if dd.get("config", None) is not None]
+        if not nodes:
+            self.Qsubgraph = dict()
+            return
+        cnt = self.counts().astype(np.int64)
+        nodes_h = np.asarray(nodes, dtype=np.int64)
+        d = self._ensure_device(max(self.Nq, int(cnt[nodes_h].max()) + 1, 1))
+        dev = res.torch_device
+        qc = torch.as_tensor(res.to_chain(np.asarray([res.Gw.node[i]["config"] for i in nodes])), dtype=torch.float64, device=dev)
+        tn, tc = torch.from_numpy(nodes_h).to(dev), torch.from_numpy(cnt[nodes_h]).to(dev)
+        d["Qs"][tn, :, tc] = qc.to(d["Qs"].dtype)
+        d["Q"][tn, :, tc] = qc.to(d["Q"].dtype)
+        d["count"][tn] = (tc + 1).to(torch.int32)
+        iqmap = {int(i): int(c) for i, c in zip(nodes, cnt[nodes_h])}
+        eids, aa, bb = [], [], []
+        for i, j, dd in res.Gw.edges_iter(data=True):
+            if dd.get("connected", False):
+                a, b = (i, j) if i < j else (j, i)
+                eids.append(self.edge_index(a, b)); aa.append(iqmap[a]); bb.append(iqmap[b])
+        if eids:
+            te = torch.as_tensor(eids, dtype=torch.int64, device=dev)
+            ta = torch.as_tensor(aa, dtype=torch.int64, device=dev)
+            tb = torch.as_tensor(bb, dtype=torch.int64, device=dev)
+            bits = torch.bitwise_left_shift(torch.ones_like(tb), tb % 32)
+            bits = torch.where(bits >= 2 ** 31, bits - 2 ** 32, bits).to(torch.int32)
+            d["mask"][te, ta, tb // 32] |= bits          # one bit per (edge, row) at most: the new row of each node
+        self.Qsubgraph = iqmap
+        self._invalidate()
+
+    def optimize(self, numIters=10):
+        """solver.py:1934-1986: coordinate descent on the resolution's joint-space path length.  A
+        resolved node with resolved neighbours tries to move to the IK solution seeded from its neighbours' average
+        config (robot_average, utils.py:118-136), halving the way back to its own config up to 10 times; a move is
+        taken if it does not lengthen the paths to the neighbours and every resolved edge to them stays valid.
+        The reference sweeps the nodes in id order with immediate updates; node i only reads its neighbours, so all
+        nodes of one level of the lower-neighbour DAG (the schedule of the seeded sampling sweep) are processed
+        together with the same result: one batched IK launch and one batched validEdge launch per try and level.
+        Ends with fromResolutionToGraph() like the reference.  Returns the mean path length per resolved edge."""
+        res = self.resolution
+        lv = self._sweep_levels()
+        level = lv["host"][3]
+        nodes = [i for i, dd in res.Gw.nodes_iter(data=True) if dd.get("config", None) is not None]
+        nbrs = {i: [] for i in nodes}
+        nedges = 0
+        for i, j, dd in res.Gw.edges_iter(data=True):
+            if dd.get("connected", False):
+                nbrs[i].append(j); nbrs[j].append(i); nedges += 1
+        for i in nbrs:
+            nbrs[i].sort()
+        active = [i for i in nodes if nbrs[i]]
+        by_level = {}
+        for i in active:
+            by_level.setdefault(int(level[i]), []).append(i)
+        cfg = {i: np.asarray(res.Gw.node[i]["config"], dtype=np.float64) for i in nodes}
+        par = {i: res.Gw.node[i]["params"] for i in nodes}
+        dist = lambda a, b: float(np.sqrt(((a - b) ** 2).sum()))      # robot.distance for 'normal' joints (K1)
+        mean_len = 0.0
+        for _ in range(int(numIters)):
+            total = 0.0
+            for L in sorted(by_level):
+                batch = by_level[L]
+                q0 = {v: cfg[v] for v in batch}
+                d0 = {v: sum(dist(q0[v], cfg[w]) for w in nbrs[v]) for v in batch}
+                qavg = {}
+                for v in batch:                                       # utils.py:123-127
+                    qs = [cfg[w] for w in nbrs[v]]
+                    r = qs[0]
+                    for k in range(1, len(qs)):
+                        r = r + (qs[k] - r) * (1.0 / (k + 1))
+                    qavg[v] = r
+                pending = list(batch)
+                for _try in range(10):                                # solver.py:1956-1978
+                    if not pending:
+                        break
+                    sols = res.solveBatch([qavg[v].tolist() for v in pending], [par[v] for v in pending])
+                    cand = []
+                    for v, q in zip(pending, sols):
+                        if q is None:
+                            continue
+                        q = np.asarray(q, dtype=np.float64)
+                        dsum = sum(dist(q, cfg[w]) for w in nbrs[v])
+                        if dsum <= d0[v]:
+                            cand.append((v, q, dsum))
+                    moved = set()
+                    if cand:
+                        qa, qb, wa, wb, owner = [], [], [], [], []
+                        for k, (v, q, dsum) in enumerate(cand):
+                            for w in nbrs[v]:
+                                qa.append(q.tolist()); qb.append(cfg[w].tolist()); wa.append(par[v]); wb.append(par[w]); owner.append(k)
+                        ok = res.validEdgeBatch(qa, qb, wa, wb)
+                        good = [True] * len(cand)
+                        for k, o in zip(owner, ok):
+                            good[k] = good[k] and o
+                        for k, (v, q, dsum) in enumerate(cand):
+                            if good[k]:
+                                moved.add(v)
+                                d0[v] = dsum
+                                q0[v] = q                             # committed after the level (neighbours are in other levels)
+                    pending = [v for v in pending if v not in moved]
+                    for v in pending:
+                        qavg[v] = q0[v] + (qavg[v] - q0[v]) * 0.5     # robot.interpolate(q0, qavg, 0.5)
+                for v in batch:
+                    cfg[v] = q0[v]
+                    total += d0[v]
+            mean_len = total / max(nedges, 1)
+        for i in nodes:
+            res.Gw.node[i]["config"] = [float(x) for x in cfg[i]]
+        self.stats["optimize_mean_path_length"] = mean_len
+        self.fromResolutionToGraph()
+        return mean_len
+
     # ---- sanity (solver.py:365-383) -------------------------------------------------------------------
     def sanityCheck(self):
         cnt = self.counts()

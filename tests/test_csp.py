@@ -240,3 +240,60 @@ def test_sample_conflicts_refines_around_conflict_nodes(built):
     assert rr.Qsubgraph == qsub
     c1, _, _, _ = rr.solveCSP(numInitialGuesses=4)
     assert set(rr.Qsubgraph) == set(np.nonzero(cnt1 > 0)[0].tolist())
+
+
+def _optimize_sequential(res, numIters):
+    """solver.py:1934-1986 as written: nodes in id order, immediate updates, one solve / validEdge call at a time."""
+    nodes = [i for i, d in res.Gw.nodes_iter(data=True) if d.get("config", None) is not None]
+    nbrs = {i: [] for i in nodes}
+    for i, j, d in res.Gw.edges_iter(data=True):
+        if d.get("connected", False):
+            nbrs[i].append(j); nbrs[j].append(i)
+    cfg = {i: np.asarray(res.Gw.node[i]["config"], dtype=np.float64) for i in nodes}
+    dist = lambda a, b: float(np.sqrt(((a - b) ** 2).sum()))
+    for _ in range(numIters):
+        for v in nodes:
+            ws = sorted(nbrs[v])
+            if not ws:
+                continue
+            x, q0 = res.Gw.node[v]["params"], cfg[v]
+            d0 = sum(dist(q0, cfg[w]) for w in ws)
+            qavg = cfg[ws[0]]
+            for k in range(1, len(ws)):
+                qavg = qavg + (cfg[ws[k]] - qavg) * (1.0 / (k + 1))
+            for _try in range(10):
+                q = res.solve(qavg.tolist(), x)
+                if q is not None:
+                    q = np.asarray(q, dtype=np.float64)
+                    d = sum(dist(q, cfg[w]) for w in ws)
+                    if d <= d0 and all(res.validEdge(q.tolist(), cfg[w].tolist(), x, res.Gw.node[w]["params"]) for w in ws):
+                        cfg[v] = q
+                        break
+                qavg = q0 + (qavg - q0) * 0.5
+    return cfg
+
+
+@pytest.mark.gpu
+def test_optimize_equals_sequential_sweep_and_feeds_the_roadmap(built):
+    res, rr = _roadmap(Nw=90, Nq=8)
+    rr.solveCSP(numInitialGuesses=4)
+    before = {i: list(d["config"]) for i, d in res.Gw.nodes_iter(data=True) if d.get("config", None) is not None}
+    connected = [(i, j) for i, j in res.Gw.edges_iter() if res.isResolvedEdge(i, j)]
+    assert connected
+    length = lambda cfgs: sum(float(np.linalg.norm(np.asarray(cfgs[i]) - np.asarray(cfgs[j]))) for i, j in connected)
+    want = _optimize_sequential(res, 2)
+    cnt0 = rr.counts().copy()
+    rr.optimize(2)
+    after = {i: res.Gw.node[i]["config"] for i in before}
+    for i in before:
+        np.testing.assert_allclose(after[i], want[i], rtol=0, atol=1e-6, err_msg="node %d" % i)
+    assert length(after) <= length(before) + 1e-9
+    assert any(after[i] != before[i] for i in before)
+    assert res.verify()[0] == 0                                  # every connected edge is still a valid edge
+    # fromResolutionToGraph (solver.py:2170-2185): the optimised configs are new roadmap configs, connected to each other
+    cnt1 = rr.counts()
+    for i in before:
+        assert cnt1[i] == cnt0[i] + 1 and rr.Qsubgraph[i] == cnt0[i]
+        assert rr.Gw.node[i]["qlist"][rr.Qsubgraph[i]] == pytest.approx(after[i], abs=1e-12)
+    for i, j in connected:
+        assert rr.hasEdge(i, rr.Qsubgraph[i], j, rr.Qsubgraph[j])
