@@ -18,14 +18,15 @@ LIB_PATH = os.environ.get("GRR_LIB") or os.path.join(_HERE, "libgrr_b200.so")
 GRR_F32, GRR_F64 = 0, 1
 GRR_FREE, GRR_FIXED, GRR_VARIABLE = 0, 1, 2
 IK_OK, IK_STALL, IK_CONVX, IK_MAXIT = 0, 1, 2, 3
-CNT_IK_SOLVES, CNT_IK_ITERS, CNT_IK_EVALS, CNT_PAIRS, CNT_VALID, CNT_IK_OK, CNT_SLOTS = 0, 1, 2, 3, 4, 5, 8
+CNT_IK_SOLVES, CNT_IK_ITERS, CNT_IK_EVALS, CNT_PAIRS, CNT_VALID, CNT_IK_OK = 0, 1, 2, 3, 4, 5
+CNT_FLAGGED, CNT_FLIPPED, CNT_FLAG_DROPPED, CNT_SLOTS = 6, 7, 8, 16
 MAX_JOINTS = 32
 
 # every symbol include/grr_b200.h declares (checked by tests/test_cabi_symbols.py)
 EXPORTS = [
     "grr_last_error", "grr_abi_version", "grr_chain_create", "grr_chain_destroy", "grr_task_set",
     "grr_chain_num_joints", "grr_fk_batch", "grr_ik_solve_batch", "grr_ik_sample", "grr_ik_sample_level", "grr_dedup", "grr_dedup_sweep",
-    "grr_edges_build", "grr_edges_cost", "grr_edges_compact", "grr_valid_edge_batch", "grr_gather_node_blocks",
+    "grr_edges_build", "grr_edges_build_exact", "grr_set_flag_scale", "grr_edges_cost", "grr_edges_compact", "grr_valid_edge_batch", "grr_gather_node_blocks",
     "grr_scatter_node_blocks", "grr_csp_random_assignment", "grr_csp_conflicts", "grr_csp_descent_sweep",
     "grr_fp32_peak", "grr_fp32x2_peak",
 ]
@@ -75,6 +76,8 @@ def lib():
     L.grr_dedup_sweep.argtypes = [vp, C.c_int, i64, vp, i32, i32, vp, vp, vp, i32, i32, vp, vp, dbl, i32, vp, vp, vp, vp]
     L.grr_dedup.argtypes = [vp, C.c_int, i64, i32, i32, vp, vp, dbl, i32, vp, vp, vp, vp, vp]
     L.grr_edges_build.argtypes = [vp, C.c_int, i64, vp, vp, vp, vp, vp, i32, i32, dbl, vp, vp, vp, vp]
+    L.grr_edges_build_exact.argtypes = [vp, i64, vp, vp, vp, vp, vp, vp, vp, i32, i32, dbl, vp, vp, vp, vp]
+    L.grr_set_flag_scale.argtypes = [vp, dbl]
     L.grr_edges_cost.argtypes = [vp, C.c_int, i64, vp, vp, vp, vp, i32, dbl, vp, vp]
     L.grr_edges_compact.argtypes = [i64, i32, vp, vp, vp, vp]
     L.grr_valid_edge_batch.argtypes = [vp, C.c_int, i64, vp, vp, vp, vp, dbl, vp, vp, vp, vp]
@@ -94,8 +97,9 @@ def lib():
 
 def check(rc, what):
     global LAUNCHES
-    if what not in ("grr_chain_create", "grr_task_set", "grr_fp32_peak", "grr_fp32x2_peak"):
-        LAUNCHES += 2 if what == "grr_edges_build" else 1      # edges_build = k_edge_load + k_edges_build
+    if what not in ("grr_chain_create", "grr_task_set", "grr_fp32_peak", "grr_fp32x2_peak", "grr_set_flag_scale"):
+        # edges_build = k_edge_load + k_edges_build (+ k_edges_recheck in the exact build)
+        LAUNCHES += {"grr_edges_build": 2, "grr_edges_build_exact": 3}.get(what, 1)
     if rc != 0:
         raise GrrError("%s failed (%d): %s" % (what, rc, lib().grr_last_error().decode()))
 
@@ -233,6 +237,20 @@ class ChainHandle:
                                     _ptr(q_kept), _ptr(count), _ptr(old_count), int(Nq), Nqp, float(epsilon),
                                     _ptr(mask), _ptr(edge_stats), _ptr(counters), _stream(q_kept.device)),
               "grr_edges_build")
+
+    def edges_build_exact(self, wedges, params32, params64, q32, q64, count, Nq, epsilon, mask, edge_stats=None, counters=None,
+                          old_count=None):
+        """Edge sets of double-precision arithmetic at single-precision speed (near-tie flags + recheck)."""
+        import torch
+        assert q32.dtype == torch.float32 and q64.dtype == torch.float64 and q32.shape == q64.shape
+        assert params32.dtype == torch.float32 and params64.dtype == torch.float64
+        E = wedges.shape[0]
+        check(lib().grr_edges_build_exact(self._h, E, _ptr(wedges), _ptr(params32), _ptr(params64), _ptr(q32), _ptr(q64),
+                                          _ptr(count), _ptr(old_count), int(Nq), q32.shape[2], float(epsilon), _ptr(mask),
+                                          _ptr(edge_stats), _ptr(counters), _stream(q32.device)), "grr_edges_build_exact")
+
+    def set_flag_scale(self, scale):
+        check(lib().grr_set_flag_scale(self._h, float(scale)), "grr_set_flag_scale")
 
     def edges_cost(self, wedges, q_kept, count, epsilon, cost, old_count=None):
         E = wedges.shape[0]

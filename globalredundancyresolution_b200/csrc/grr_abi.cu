@@ -3,6 +3,7 @@
 // compaction, FK, node-block gather/scatter for the halo exchange, FP32 peak microbenchmark.
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <new>
 #include "grr_device.cuh"
 #include "grr_host.h"
@@ -280,12 +281,13 @@ static const unsigned kWorkRing = 64;
 // next work counter of the handle's ring (allocated on first use, on the handle's device)
 static unsigned long long *work_slot(grr_handle_s *h) {
   if (!h->d_work) {
-    if (cudaMalloc(&h->d_work, sizeof(unsigned long long) * (kWorkRing + 2)) != cudaSuccess) {
+    if (cudaMalloc(&h->d_work, sizeof(unsigned long long) * 2 * kWorkRing) != cudaSuccess) {
       set_error("cudaMalloc(work counters) failed: %s", cudaGetErrorString(cudaGetLastError()));
       return nullptr;
     }
   }
-  return h->d_work + (h->next_work++ % kWorkRing);
+  // two words per slot (grr_edges_build's load reduction uses both); one handle serves one stream at a time
+  return h->d_work + 2 * (h->next_work++ % kWorkRing);
 }
 
 // device scratch of at least `words` 64-bit words (grow-only; reallocation synchronises the device)
@@ -301,6 +303,8 @@ static unsigned long long *scratch_for(grr_handle_s *h, size_t words) {
   }
   return h->d_scratch;
 }
+
+static unsigned long long *scratch_cb(void *ctx, size_t words) { return scratch_for((grr_handle_s *)ctx, words); }
 
 #define GRR_CHECK_HANDLE(h)                                   \
   if (!(h)) { set_error("null handle"); return -1; }          \
@@ -339,7 +343,20 @@ int grr_chain_create(const grr_chain_desc *d, int device, grr_handle_t *out) {
     if (!(nn > 0.999 && nn < 1.001)) { set_error("grr_chain_create: axis %d is not unit", j); delete h; return -1; }
     if (!(c.qmin[j] <= c.qmax[j])) { set_error("grr_chain_create: qmin>qmax at joint %d", j); delete h; return -1; }
   }
+  {
+    // near-tie margins of grr_edges_build_exact: safety factor 8 over the measured single-precision differences
+    // (DESIGN.md 3.4); GRR_FLAG_SCALE overrides it for experiments
+    const char *fs = getenv("GRR_FLAG_SCALE");
+    flag_margins(c, fs ? atof(fs) : 8.0);
+  }
   *out = h;
+  return 0;
+}
+
+int grr_set_flag_scale(grr_handle_t h, double scale) {
+  if (!h) { set_error("null handle"); return -1; }
+  if (!(scale > 0)) { set_error("grr_set_flag_scale: scale must be positive"); return -1; }
+  flag_margins(h->hc, scale);
   return 0;
 }
 
@@ -477,10 +494,26 @@ int grr_edges_build(grr_handle_t h, int dtype, int64_t E, const int32_t *wedges,
   if (E == 0) return 0;
   unsigned long long *work = work_slot(h);
   if (!work) return -3;
-  unsigned long long *scratch = scratch_for(h, (size_t)E + 1);
-  if (!scratch) return -3;
-  return ops->edges_build(h->hc, E, wedges, params, q_kept, count, old_count, Nq, Nqp, epsilon, mask, edge_stats, work, scratch,
-                          (unsigned long long *)counters, (cudaStream_t)stream);
+  const ScratchReq sreq = {h, scratch_cb};
+  return ops->edges_build(h->hc, E, wedges, params, q_kept, count, old_count, Nq, Nqp, epsilon, mask, edge_stats, work, &sreq,
+                          (unsigned long long *)counters, (cudaStream_t)stream, nullptr);
+}
+
+int grr_edges_build_exact(grr_handle_t h, int64_t E, const int32_t *wedges, const float *params32, const double *params64,
+                          const float *q_kept32, const double *q_kept64, const int32_t *count, const int32_t *old_count,
+                          int32_t Nq, int32_t Nqp, double epsilon, uint32_t *mask, uint32_t *edge_stats, uint64_t *counters,
+                          void *stream) {
+  GRR_CHECK_HANDLE(h);
+  const Ops *ops = pick_ops(GRR_F32, h->hc.mode);
+  if (E < 0 || Nq < 1 || Nq > 65535 || Nqp < Nq) { set_error("grr_edges_build_exact: bad sizes (need 1 <= Nq <= 65535, Nqp >= Nq)"); return -1; }
+  if (E > 0 && (!wedges || !params32 || !params64 || !q_kept32 || !q_kept64 || !count || !mask)) { set_error("grr_edges_build_exact: null buffer"); return -1; }
+  if (E == 0) return 0;
+  unsigned long long *work = work_slot(h);
+  if (!work) return -3;
+  const ScratchReq sreq = {h, scratch_cb};
+  const ExactArgs ex = {params64, q_kept64};
+  return ops->edges_build(h->hc, E, wedges, params32, q_kept32, count, old_count, Nq, Nqp, epsilon, mask, edge_stats, work, &sreq,
+                          (unsigned long long *)counters, (cudaStream_t)stream, &ex);
 }
 
 int grr_edges_cost(grr_handle_t h, int dtype, int64_t E, const int32_t *wedges, const void *q_kept, const int32_t *count,

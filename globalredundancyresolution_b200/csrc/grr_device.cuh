@@ -33,6 +33,10 @@
 #define GRR_DCHECK(cond) do { } while (0)
 #endif
 
+// Lane-machine building blocks are __host__ __device__: the product runs them in the kernels only; the host
+// instantiation exists for the near-tie study / CPU checks of the same source (tools/lane_host.cu, tests).
+#define GRR_DEV __host__ __device__ __forceinline__
+
 namespace grr {
 
 constexpr int kMaxJ = 32;
@@ -40,25 +44,22 @@ constexpr int kMaxJ = 32;
 // ------------------------------------------------------------------------------------------
 // scalar helpers, overloaded on precision
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ void sincos_(float a, float *s, float *c) { sincosf(a, s, c); }
-__device__ __forceinline__ void sincos_(double a, double *s, double *c) { sincos(a, s, c); }
-__device__ __forceinline__ float sqrt_(float a) { return sqrtf(a); }
-__device__ __forceinline__ double sqrt_(double a) { return sqrt(a); }
-__device__ __forceinline__ float atan2_(float a, float b) { return atan2f(a, b); }
-__device__ __forceinline__ double atan2_(double a, double b) { return atan2(a, b); }
-__device__ __forceinline__ float abs_(float a) { return fabsf(a); }
-__device__ __forceinline__ double abs_(double a) { return fabs(a); }
-__device__ __forceinline__ float max_(float a, float b) { return fmaxf(a, b); }
-__device__ __forceinline__ double max_(double a, double b) { return fmax(a, b); }
-__device__ __forceinline__ float fma_(float a, float b, float c) { return fmaf(a, b, c); }
-__device__ __forceinline__ double fma_(double a, double b, double c) { return fma(a, b, c); }
-__device__ __forceinline__ float min_(float a, float b) { return fminf(a, b); }
-__device__ __forceinline__ double min_(double a, double b) { return fmin(a, b); }
-__device__ __forceinline__ float ceil_(float a) { return ceilf(a); }
-__device__ __forceinline__ double ceil_(double a) { return ceil(a); }
-template <typename Real> __device__ __forceinline__ Real inf_();
-template <> __device__ __forceinline__ float inf_<float>() { return CUDART_INF_F; }
-template <> __device__ __forceinline__ double inf_<double>() { return CUDART_INF; }
+GRR_DEV void sincos_(float a, float *s, float *c) { sincosf(a, s, c); }
+GRR_DEV void sincos_(double a, double *s, double *c) { sincos(a, s, c); }
+GRR_DEV float sqrt_(float a) { return sqrtf(a); }
+GRR_DEV double sqrt_(double a) { return sqrt(a); }
+GRR_DEV float atan2_(float a, float b) { return atan2f(a, b); }
+GRR_DEV double atan2_(double a, double b) { return atan2(a, b); }
+GRR_DEV float abs_(float a) { return fabsf(a); }
+GRR_DEV double abs_(double a) { return fabs(a); }
+GRR_DEV float max_(float a, float b) { return fmaxf(a, b); }
+GRR_DEV double max_(double a, double b) { return fmax(a, b); }
+GRR_DEV float fma_(float a, float b, float c) { return fmaf(a, b, c); }
+GRR_DEV double fma_(double a, double b, double c) { return fma(a, b, c); }
+GRR_DEV float min_(float a, float b) { return fminf(a, b); }
+GRR_DEV double min_(double a, double b) { return fmin(a, b); }
+GRR_DEV float ceil_(float a) { return ceilf(a); }
+GRR_DEV double ceil_(double a) { return ceil(a); }
 
 // ------------------------------------------------------------------------------------------
 // chain constants (kernel parameter, __grid_constant__: lives in the constant bank)
@@ -79,6 +80,9 @@ struct ChainDev {
   int small_angles;            // every joint limit inside [-pi/4, pi/4]: sincos needs no range reduction
   int axes_positive;           // every short-path joint has sgn = +1
   Real tol, lambda;
+  // near-tie margins of the single-precision edge phase (FLAG builds of lane_step / pair_advance; all 0 otherwise)
+  Real fl_f, fl_f2, fl_x, fl_alam, fl_rel, fl_leaf, fl_nd, fl_dd, fl_curv;
+  int fl_maxit;                // solves longer than this many Newton iterations are not trusted in single precision
   // M_j(theta) = Rp_j * Rot(axis_j, theta) = A + sin(theta) * B - cos(theta) * C
   Real A[NJ][9], B[NJ][9], C[NJ][9];
   Real tp[NJ][3];
@@ -101,33 +105,33 @@ struct Target {
 // 3x3 helpers (row-major)
 // ------------------------------------------------------------------------------------------
 template <typename Real>
-__device__ __forceinline__ void m3_mul(const Real *A, const Real *B, Real *C) {  // C = A B (no alias)
+GRR_DEV void m3_mul(const Real *A, const Real *B, Real *C) {  // C = A B (no alias)
 #pragma unroll
   for (int i = 0; i < 3; i++)
 #pragma unroll
     for (int j = 0; j < 3; j++) C[3 * i + j] = A[3 * i] * B[j] + A[3 * i + 1] * B[3 + j] + A[3 * i + 2] * B[6 + j];
 }
 template <typename Real>
-__device__ __forceinline__ void m3_Tmul(const Real *A, const Real *B, Real *C) {  // C = A^T B
+GRR_DEV void m3_Tmul(const Real *A, const Real *B, Real *C) {  // C = A^T B
 #pragma unroll
   for (int i = 0; i < 3; i++)
 #pragma unroll
     for (int j = 0; j < 3; j++) C[3 * i + j] = A[i] * B[j] + A[3 + i] * B[3 + j] + A[6 + i] * B[6 + j];
 }
 template <typename Real>
-__device__ __forceinline__ void m3_vec(const Real *A, const Real *v, Real *r) {  // r = A v (no alias)
+GRR_DEV void m3_vec(const Real *A, const Real *v, Real *r) {  // r = A v (no alias)
 #pragma unroll
   for (int i = 0; i < 3; i++) r[i] = A[3 * i] * v[0] + A[3 * i + 1] * v[1] + A[3 * i + 2] * v[2];
 }
 template <typename Real>
-__device__ __forceinline__ void m3_Tvec(const Real *A, const Real *v, Real *r) {  // r = A^T v
+GRR_DEV void m3_Tvec(const Real *A, const Real *v, Real *r) {  // r = A^T v
 #pragma unroll
   for (int i = 0; i < 3; i++) r[i] = A[i] * v[0] + A[3 + i] * v[1] + A[6 + i] * v[2];
 }
 
 // klampt.math.so3.from_moment: exp map (graph.py:96,152)
 template <typename Real>
-__device__ void so3_exp(const Real *w, Real *R) {
+__host__ __device__ void so3_exp(const Real *w, Real *R) {
   Real t2 = w[0] * w[0] + w[1] * w[1] + w[2] * w[2];
   Real th = sqrt_(t2);
   if (th < Real(1e-12)) {
@@ -146,7 +150,7 @@ __device__ void so3_exp(const Real *w, Real *R) {
 
 // klampt.math.so3.moment: log map with theta = atan2(|skew|, (tr-1)/2) (graph.py:118,154)
 template <typename Real>
-__device__ void so3_log(const Real *R, Real *w) {
+__host__ __device__ void so3_log(const Real *R, Real *w) {
   Real v0 = Real(0.5) * (R[7] - R[5]), v1 = Real(0.5) * (R[2] - R[6]), v2 = Real(0.5) * (R[3] - R[1]);
   Real s = sqrt_(v0 * v0 + v1 * v1 + v2 * v2);
   Real c = Real(0.5) * (R[0] + R[4] + R[8] - Real(1));
@@ -181,7 +185,7 @@ __device__ void so3_log(const Real *R, Real *w) {
 
 // inverse left Jacobian of SO(3) at e: D = I - 0.5 [e]x + g [e]x^2
 template <typename Real>
-__device__ void so3_Jl_inv(const Real *e, Real *D) {
+__host__ __device__ void so3_Jl_inv(const Real *e, Real *D) {
   Real t2 = e[0] * e[0] + e[1] * e[1] + e[2] * e[2];
   Real g;
   if (t2 < Real(1e-8)) g = Real(1.0 / 12.0);
@@ -198,12 +202,13 @@ __device__ void so3_Jl_inv(const Real *e, Real *D) {
 // ------------------------------------------------------------------------------------------
 // Philox4x32-10 (counter-based RNG shared by specification with the CPU oracle)
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+GRR_DEV void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
                                               uint32_t k1, uint32_t *out) {
 #pragma unroll
   for (int r = 0; r < 10; r++) {
-    uint32_t h0 = __umulhi(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
-    uint32_t h1 = __umulhi(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
+    const uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
+    uint32_t h0 = (uint32_t)(p0 >> 32), l0 = (uint32_t)p0;
+    uint32_t h1 = (uint32_t)(p1 >> 32), l1 = (uint32_t)p1;
     uint32_t n0 = h1 ^ c1 ^ k0, n2 = h0 ^ c3 ^ k1;
     c0 = n0; c1 = l1; c2 = n2; c3 = l0;
     k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
@@ -215,7 +220,7 @@ __host__ __device__ constexpr int tri(int r, int c) { return r * (r + 1) / 2 + c
 
 // forward-facing FK for the API (EE point + goal-link rotation), same backward walk
 template <typename Real, int NJ>
-__device__ void chain_fk(const ChainDev<Real, NJ> &c, const Real *x, Real *p, Real *Rl) {
+__host__ __device__ void chain_fk(const ChainDev<Real, NJ> &c, const Real *x, Real *p, Real *Rl) {
   Real v[3] = {c.ee[0], c.ee[1], c.ee[2]}, G[9];
   for (int k = 0; k < 9; k++) G[k] = c.Rtail[k];
   for (int j = c.n - 1; j >= 0; j--) {
@@ -235,7 +240,7 @@ __device__ void chain_fk(const ChainDev<Real, NJ> &c, const Real *x, Real *p, Re
 // damped step: y = (J J^T + lambda^2 I)^-1 F_L  via Cholesky; p_j = -(cp_j . y_p + cr_j . z)
 // ------------------------------------------------------------------------------------------
 template <typename Real, int M>
-__device__ __forceinline__ void chol_solve(Real (&A)[M * (M + 1) / 2], const Real *b, Real *y) {
+GRR_DEV void chol_solve(Real (&A)[M * (M + 1) / 2], const Real *b, Real *y) {
 #pragma unroll
   for (int r = 0; r < M; r++) {
 #pragma unroll
@@ -269,7 +274,7 @@ enum : int { IK_RUNNING = -1, IK_OK = 0, IK_STALL = 1, IK_CONVX = 2, IK_MAXIT = 
 // workspace targets: setIKProblem (graph.py:737-745) and workspaceInterpolate (graph.py:768-777)
 // ------------------------------------------------------------------------------------------
 template <typename Real, int M, int NJ>
-__device__ __forceinline__ void target_from_params(const ChainDev<Real, NJ> &c, const Real *w, Target<Real, M> &tg) {
+GRR_DEV void target_from_params(const ChainDev<Real, NJ> &c, const Real *w, Target<Real, M> &tg) {
   tg.x[0] = w[0]; tg.x[1] = w[1]; tg.x[2] = w[2];
   if (M == 6) {
     if (c.mode == 2) so3_exp(w + 3, tg.R);
@@ -289,7 +294,7 @@ struct WInterp {
   bool rot;                   // variable orientation
 };
 template <typename Real, int M, int NJ>
-__device__ __forceinline__ void winterp_begin(const ChainDev<Real, NJ> &c, const Real *wa, const Real *wb, WInterp<Real, M> &W) {
+GRR_DEV void winterp_begin(const ChainDev<Real, NJ> &c, const Real *wa, const Real *wb, WInterp<Real, M> &W) {
 #pragma unroll
   for (int k = 0; k < 3; k++) { W.xa[k] = wa[k]; W.dx[k] = wb[k] - wa[k]; }
   W.rot = false;
@@ -307,7 +312,7 @@ __device__ __forceinline__ void winterp_begin(const ChainDev<Real, NJ> &c, const
   }
 }
 template <typename Real, int M>
-__device__ __forceinline__ void winterp_at(const WInterp<Real, M> &W, Real u, Target<Real, M> &tg) {
+GRR_DEV void winterp_at(const WInterp<Real, M> &W, Real u, Target<Real, M> &tg) {
 #pragma unroll
   for (int k = 0; k < 3; k++) tg.x[k] = W.xa[k] + u * W.dx[k];
   if (M == 6) {

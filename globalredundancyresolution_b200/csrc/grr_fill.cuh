@@ -6,9 +6,43 @@
 
 namespace grr {
 
+// Margins within which a decision of the single-precision edge phase counts as a near-tie.  u = 2^-24 * scale;
+// the multipliers are the measured sizes of the single- vs double-precision differences of each quantity
+// (tools/flag_study.py runs the same lane machine in both precisions on the host), `scale` is the safety factor.
+//   FL_F     max|F| against tol, absolute: position rows carry ~u * reach * sqrt(n) of round-off, rotation rows ~u * pi * sqrt(n)
+//   FL_X     convergence-on-x test value against tolx, absolute
+//   FL_ALAM  step length against alamin, relative
+//   FL_REL   other comparisons (|p| vs stpmax, descent test, discriminant), relative
+//   FL_LEAF  consecutive-config distance against the discontinuity threshold, relative
+//   FL_ND    dist / eps against the next integer (Ndivs = ceil), absolute
+//   FL_DD    relative error allowed for the directional derivative that resolves Armijo near-ties (lane_step)
+//   FL_CURV  bound of |sum_r F_r d2 F_r| / |F| per unit |p|^2 (reach * n) for the second-order term of that model
+//   FL_MAXIT solves with more Newton iterations than this are re-tested (the iterates of a long solve drift apart)
+inline void flag_margins(HostChain &h, double scale) {
+  double reach = 0;
+  for (int j = 0; j < h.n; j++) reach += sqrt(h.tp[3 * j] * h.tp[3 * j] + h.tp[3 * j + 1] * h.tp[3 * j + 1] + h.tp[3 * j + 2] * h.tp[3 * j + 2]);
+  reach += sqrt(h.ee_local[0] * h.ee_local[0] + h.ee_local[1] * h.ee_local[1] + h.ee_local[2] * h.ee_local[2]);
+  if (h.mode != GRR_FREE && reach < 3.15) reach = 3.15;
+  if (reach < 1.0) reach = 1.0;
+  const double u = scale * 5.9604644775390625e-08;
+  h.fl[FL_F] = u * reach * sqrt((double)h.n);
+  h.fl[FL_X] = u * 4.0;
+  h.fl[FL_ALAM] = u * 2048.0;
+  h.fl[FL_REL] = u * 256.0;
+  h.fl[FL_LEAF] = u * 8.0;
+  h.fl[FL_ND] = u * 64.0;
+  h.fl[FL_MAXIT] = 1e9;
+  h.fl[FL_DD] = u * 2048.0;
+  h.fl[FL_CURV] = reach * h.n;
+}
+
 template <typename Real, int NJ>
 void fill_chain(const HostChain &h, ChainDev<Real, NJ> &d) {
   memset(&d, 0, sizeof(d));
+  d.fl_f = (Real)h.fl[FL_F]; d.fl_f2 = (Real)(4.0 * h.fl[FL_F] * h.fl[FL_F]); d.fl_x = (Real)h.fl[FL_X];
+  d.fl_alam = (Real)h.fl[FL_ALAM]; d.fl_rel = (Real)h.fl[FL_REL]; d.fl_leaf = (Real)h.fl[FL_LEAF]; d.fl_nd = (Real)h.fl[FL_ND];
+  d.fl_dd = (Real)h.fl[FL_DD]; d.fl_curv = (Real)h.fl[FL_CURV];
+  d.fl_maxit = h.fl[FL_MAXIT] > 1e6 ? 1 << 20 : (int)h.fl[FL_MAXIT];
   d.n = h.n; d.mode = h.mode; d.nlinks_eps = h.nlinks_eps; d.max_iters = h.max_iters;
   d.tol = (Real)h.tol; d.lambda = (Real)h.lambda;
   for (int j = 0; j < h.n && j < NJ; j++) {

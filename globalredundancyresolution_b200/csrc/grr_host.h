@@ -14,9 +14,18 @@ struct HostChain {
   double Rp[GRR_MAX_JOINTS * 9], tp[GRR_MAX_JOINTS * 3], axis[GRR_MAX_JOINTS * 3];
   double qmin[GRR_MAX_JOINTS], qmax[GRR_MAX_JOINTS];
   double ee_local[3], R_tail[9], R_goal[9];
+  // near-tie margins of the exact edge build (grr_edges_build_exact), see flag_margins() in grr_fill.cuh
+  double fl[10];
 };
 
+enum { FL_F = 0, FL_X = 1, FL_ALAM = 2, FL_REL = 3, FL_LEAF = 4, FL_ND = 5, FL_MAXIT = 6, FL_DD = 7, FL_CURV = 8 };
+
 void set_error(const char *fmt, ...);
+
+// grow-only device scratch of the handle (reallocation synchronises the device)
+struct ScratchReq { void *ctx; unsigned long long *(*get)(void *ctx, size_t words); };
+// double-precision inputs of the exact edge build's second pass
+struct ExactArgs { const void *params64, *q64; };
 
 // One table of launchers per (precision, residual rows).  `work` is a zero-initialised-by-the-launcher
 // device counter from which persistent lanes pull their next instance.
@@ -36,8 +45,8 @@ struct Ops {
                           unsigned long long *counters, cudaStream_t st);
   int (*edges_build)(const HostChain &, long long E, const int32_t *wedges, const void *params, const void *q_kept,
                      const int32_t *count, const int32_t *old_count, int Nq, int Nqp, double epsilon, uint32_t *mask,
-                     uint32_t *edge_stats, unsigned long long *work, unsigned long long *scratch /* E+1 words or null */,
-                     unsigned long long *counters, cudaStream_t st);
+                     uint32_t *edge_stats, unsigned long long *work, const ScratchReq *scratch /* nullable */,
+                     unsigned long long *counters, cudaStream_t st, const ExactArgs *exact /* nullable */);
 };
 
 const Ops *ops_f32_m3();

@@ -207,20 +207,32 @@ struct PairLane {
   int sa, sb;
   int k, ndivs;       // current interpolation index, graph.py:946
   int solves, iters;  // diagnostics
+  // FLAG builds (single-precision edge phase with near-tie bookkeeping, see lane_step): flag != 0 <=> some decision
+  // of this pair fell within the single-precision error of its threshold and the pair is re-tested in double
+  // precision; amb_prev = ambiguity radius (LaneIK::amb) of the previous interpolated solution.
+  int flag;
+  int k0;             // FLAG builds: first interpolation index with a near-tie (0: Ndivs itself); recheck kernel: restart index
+  Real amb_prev;
 };
 
-// Ndivs = ceil(robot.distance(qa, qb) / eps) (graph.py:944-946)
-template <typename Real>
-__device__ __forceinline__ int pair_ndivs(int n, Real eps, const Real *qa, int sa, const Real *qb, int sb) {
+// Ndivs = ceil(robot.distance(qa, qb) / eps) (graph.py:944-946).  FLAG: bit 30 of the result is set when dist / eps
+// lies within fl_nd of an integer (the rounding may go the other way in double precision).
+constexpr int kNdFlag = 1 << 30;
+template <typename Real, bool FLAG = false>
+GRR_DEV int pair_ndivs(int n, Real eps, const Real *qa, int sa, const Real *qb, int sb, Real fl_nd = Real(0)) {
   Real d2 = 0;
   for (int j = 0; j < n; j++) { const Real d = qa[j * sa] - qb[j * sb]; d2 += d * d; }
-  return (int)ceil_(sqrt_(d2) / eps);
+  const Real r = sqrt_(d2) / eps, cr = ceil_(r);
+  int nd = (int)cr;
+  if (FLAG && (cr - r < fl_nd || r - (cr - Real(1)) < fl_nd)) nd |= kNdFlag;
+  return nd;
 }
 
 // Arm the seed of k=1 for a pair whose Ndivs is known.  Returns false if the pair is decided already.
 template <typename Real, int M>
-__device__ __forceinline__ bool pair_arm(int ndivs, PairLane<Real> &P, LaneIK<Real, M> &L) {
-  P.ndivs = ndivs;
+GRR_DEV bool pair_arm(int ndivs, PairLane<Real> &P, LaneIK<Real, M> &L) {
+  P.flag = (ndivs & kNdFlag) ? PH_R_NDIVS : 0; P.k0 = 0; P.amb_prev = 0;
+  P.ndivs = ndivs & ~kNdFlag;
   P.k = 1; P.solves = 0; P.iters = 0;
   if (P.ndivs <= 0) return false;                                // dist == 0: single leaf of length 0 -> valid
   lane_begin_lerp<Real, M>(L, P.qa, P.sa, P.qb, P.sb, Real(1) / Real(P.ndivs + 1));   // graph.py:961-962
@@ -228,28 +240,60 @@ __device__ __forceinline__ bool pair_arm(int ndivs, PairLane<Real> &P, LaneIK<Re
 }
 
 // Begin pair: distance -> Ndivs, arm the seed of k=1.  Returns false if the pair is decided already.
-template <typename Real, int M, typename ChainT>
-__device__ __forceinline__ bool pair_begin(const ChainT &c, Real eps, PairLane<Real> &P, LaneIK<Real, M> &L) {
-  return pair_arm<Real, M>(pair_ndivs<Real>(c.n, eps, P.qa, P.sa, P.qb, P.sb), P, L);
+template <typename Real, int M, bool FLAG = false, typename ChainT>
+GRR_DEV bool pair_begin(const ChainT &c, Real eps, PairLane<Real> &P, LaneIK<Real, M> &L) {
+  return pair_arm<Real, M>(pair_ndivs<Real, FLAG>(c.n, eps, P.qa, P.sa, P.qb, P.sb, c.fl_nd), P, L);
 }
 
 // One interpolated solve finished with IK_OK; s2 = |q_k - q_{k-1}|^2 was accumulated by the final
 // pass.  Leaf test, then either the closing leaf (q_Ndivs, qb) or the next k: the solution buffer
 // becomes `prev` by swapping roles.  Returns +1 valid, 0 invalid, -1 continue (seed armed).
-template <typename Real, int M, int MC, typename ChainT>
-__device__ __forceinline__ int pair_advance(const ChainT &c, LaneMem<Real, MC> &mem, Real s2, Real thr2, PairLane<Real> &P,
-                                            LaneIK<Real, M> &L) {
-  if (s2 > thr2) return 0;                                       // graph.py:954-959 (leaf)
+// FLAG: a leaf distance within its margin of the threshold (round-off fl_leaf plus the ambiguity radii of the two
+// solutions it joins) flags the pair.
+// FLAG bookkeeping at the end of every interpolated solve (converged or not): collect the solve's near-tie reasons.
+template <typename Real, int M>
+GRR_DEV void pair_note_solve(PairLane<Real> &P, const LaneIK<Real, M> &L) {
+  const int r = L.phase & PH_R_ALL;
+  if (r && !P.flag) P.k0 = P.k;
+  P.flag |= r;
+}
+
+// skip_first_leaf: the recheck kernel restarts a pair at solve kstart > 1, whose predecessor has not been computed:
+// the leaf (kstart - 1, kstart) was settled by the single-precision pass.
+template <bool FLAG = false, typename Real, int M, int MC, typename ChainT>
+GRR_DEV int pair_advance(const ChainT &c, LaneMem<Real, MC> &mem, Real s2, Real thr2, PairLane<Real> &P,
+                         LaneIK<Real, M> &L, bool skip_first_leaf = false) {
+  Real thr = 0;
+  if (FLAG) {
+    thr = sqrt_(thr2);
+    const Real amb = L.amb + P.amb_prev;
+    if (abs_(s2 - thr2) < thr2 * (Real(2) * c.fl_leaf) + amb * (Real(2) * thr + amb)) { if (!P.flag) P.k0 = P.k; P.flag |= PH_R_LEAF; }
+    P.amb_prev = L.amb;
+  }
+  if (!skip_first_leaf && s2 > thr2) return 0;                   // graph.py:954-959 (leaf)
   if (P.k == P.ndivs) {
     const int n = c.n, T = mem.T;
     Real e2 = 0;
     for (int j = 0; j < n; j++) { const Real e = P.qb[j * P.sb] - L.res[j * T]; e2 += e * e; }
+    if (FLAG && abs_(e2 - thr2) < thr2 * (Real(2) * c.fl_leaf) + L.amb * (Real(2) * thr + L.amb)) { if (!P.flag) P.k0 = P.k; P.flag |= PH_R_LEAF; }
     return (e2 > thr2) ? 0 : 1;
   }
   { const int t = mem.o_prev; mem.o_prev = mem.o_xcur; mem.o_xcur = t; }   // IK_OK leaves the solution in xcur
   P.k++;
   lane_begin_lerp<Real, M>(L, P.qa, P.sa, P.qb, P.sb, Real(P.k) / Real(P.ndivs + 1));
   return -1;
+}
+
+// Near-tie list of the exact edge build: word 0 = entries appended (may exceed the capacity: the excess is dropped and
+// reported), entries from word 2 on, two words each: {workspace edge << 32 | a << 16 | b, reasons << 32 | k0}.
+GRR_DEV void flag_push(unsigned long long *flist, unsigned long long fcap, long long e, int a, int b, int k0, int reasons) {
+#ifdef __CUDA_ARCH__
+  const unsigned long long pos = atomicAdd(flist, 1ull);
+  if (pos < fcap) {
+    flist[2 + 2 * pos] = ((unsigned long long)e << 32) | ((unsigned long long)(unsigned)a << 16) | (unsigned long long)(unsigned)b;
+    flist[3 + 2 * pos] = ((unsigned long long)(unsigned)reasons << 32) | (unsigned long long)(unsigned)k0;
+  }
+#endif
 }
 
 // explicit pairs, SoA qa[n][P], qb[n][P]  (validEdge, graph.py:1051-1053), work-fetching lanes
@@ -329,12 +373,13 @@ k_valid_edge_batch(const __grid_constant__ ChainDev<Real, kMaxJ> c, long long to
 // shared-memory counter and run their pairs as independent lane machines; verdict bits are OR-ed into
 // a shared-memory Nq x Nq bitmask that is written out once.
 // ------------------------------------------------------------------------------------------
-template <typename Real, int M, bool PL>
+template <typename Real, int M, bool PL, bool FLAG>
 __global__ void __launch_bounds__(sizeof(Real) == 4 ? (M == 3 ? 512 : 384) : 256)
 k_edges_build(const __grid_constant__ ChainDev<Real, kMaxJ> c, const int32_t *__restrict__ wedges,
               const Real *__restrict__ params, const Real *__restrict__ q_kept, const int32_t *__restrict__ count,
               const int32_t *__restrict__ old_count, int Nq, int Nqp, Real epsilon, uint32_t *mask,
-              uint32_t *__restrict__ edge_stats, unsigned long long *counters) {
+              uint32_t *__restrict__ edge_stats, unsigned long long *counters, unsigned long long *flist,
+              unsigned long long fcap) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int n = c.n, dw = (c.mode == 2 ? 6 : 3);
   const int Wd = (Nq + 31) >> 5;
@@ -427,11 +472,14 @@ k_edges_build(const __grid_constant__ ChainDev<Real, kMaxJ> c, const int32_t *__
             if (ta < oa && tb < ob) ok = false;                   // solver.py:694
           }
           if (ok) {
-            nd = pair_ndivs<Real>(n, eps, sa + ta, Nqp, sb + tb, Nqp);
-            if (nd <= 0) {                                        // dist == 0 -> valid, no solves
-              if (!second) { atomicOr(&smask[ta * Wd + (tb >> 5)], 1u << (tb & 31)); cnt.pairs++; cnt.valid++; }
+            nd = pair_ndivs<Real, FLAG>(n, eps, sa + ta, Nqp, sb + tb, Nqp, c.fl_nd);
+            if ((nd & ~kNdFlag) <= 0) {                           // dist == 0 -> valid, no solves
+              if (!second) {
+                atomicOr(&smask[ta * Wd + (tb >> 5)], 1u << (tb & 31)); cnt.pairs++; cnt.valid++;
+                if (FLAG && (nd & kNdFlag)) flag_push(flist, fcap, e, ta, tb, 0, PH_R_NDIVS);
+              }
               ok = false;
-            } else if ((nd >= nd_cut) == second) ok = false;      // not this sweep's
+            } else if (((nd & ~kNdFlag) >= nd_cut) == second) ok = false;      // not this sweep's
           }
           const unsigned okm = __ballot_sync(0xffffffffu, ok);
           if (ok) queue[__popc(okm & ((1u << lane) - 1u))] = make_uint2(((unsigned)ta << 16) | (unsigned)tb, (unsigned)nd);
@@ -458,18 +506,20 @@ k_edges_build(const __grid_constant__ ChainDev<Real, kMaxJ> c, const int32_t *__
         const bool first = running && P.k == 1;
         if constexpr (PL) lane_pass_planar<Real, true>(c, tg, L, mem, first ? P.qa : mem.prev(), first ? P.sa : mem.T, o);
         else lane_pass<Real, M, true>(c, tg, L, mem, first ? P.qa : mem.prev(), first ? P.sa : mem.T, o);
-        const int st = lane_step<Real, M, PL>(c, L, mem, o, running);
+        const int st = lane_step<Real, M, PL, FLAG>(c, L, mem, o, running);
         if (running && st != IK_RUNNING) {
           cnt.solves++; cnt.iters += L.it; cnt.evals += L.evals; cnt.ok += (st == IK_OK);
+          if (FLAG) pair_note_solve(P, L);
           if (st != IK_OK) verdict = 0;                         // graph.py:964-966
           else {
-            verdict = pair_advance(c, mem, o.s2, thr2, P, L);
+            verdict = pair_advance<FLAG>(c, mem, o.s2, thr2, P, L);
             if (verdict < 0) winterp_at<Real, M>(W, Real(P.k) / Real(P.ndivs + 1), tg);
           }
         }
       }
       if (a >= 0 && verdict >= 0) {
         if (verdict) atomicOr(&smask[a * Wd + (b >> 5)], 1u << (b & 31));
+        if (FLAG && P.flag) flag_push(flist, fcap, e, a, b, P.k0, P.flag);
         cnt.pairs++; cnt.valid += verdict;
         a = -1;
         lane_begin_mem(L, mem);   // idle lanes keep walking valid memory
@@ -561,12 +611,13 @@ static __global__ void k_edges_bits(long long E, int words, const uint32_t *__re
   if (threadIdx.x == 0) edge_stats[2 * e + 1] = s_bits;
 }
 
-template <typename Real, int M, bool PL>
+template <typename Real, int M, bool PL, bool FLAG>
 __global__ void __launch_bounds__(128, (sizeof(Real) == 4 ? (M == 3 ? 4 : 3) : 2))
 k_edges_flat(const __grid_constant__ ChainDev<Real, kMaxJ> c, long long E, const int32_t *__restrict__ wedges,
              const Real *__restrict__ params, const Real *__restrict__ q_kept, const int32_t *__restrict__ count,
              const int32_t *__restrict__ old_count, int Nq, int Nqp, Real epsilon, uint32_t *mask,
-             const unsigned long long *__restrict__ offs, unsigned long long *work, unsigned long long *counters) {
+             const unsigned long long *__restrict__ offs, unsigned long long *work, unsigned long long *counters,
+             unsigned long long *flist, unsigned long long fcap) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int n = c.n, dw = (c.mode == 2 ? 6 : 3);
   const int Wd = (Nq + 31) >> 5;
@@ -621,10 +672,11 @@ k_edges_flat(const __grid_constant__ ChainDev<Real, kMaxJ> c, long long E, const
           if (old_count && ta < old_count[iw] && tb < old_count[jw]) ok = false;      // solver.py:694
           if (ok) {
             // all lanes measure their pair together (a lane doing this alone ran with 1.5 of 32 lanes active)
-            nd = pair_ndivs<Real>(n, eps, q_kept + (long long)iw * n * Nqp + ta, Nqp, q_kept + (long long)jw * n * Nqp + tb, Nqp);
-            if (nd <= 0) {                                        // dist == 0 -> valid, no solves
+            nd = pair_ndivs<Real, FLAG>(n, eps, q_kept + (long long)iw * n * Nqp + ta, Nqp, q_kept + (long long)jw * n * Nqp + tb, Nqp, c.fl_nd);
+            if ((nd & ~kNdFlag) <= 0) {                           // dist == 0 -> valid, no solves
               atomicOr(&mask[(e * Nq + ta) * Wd + (tb >> 5)], 1u << (tb & 31));
               cnt.pairs++; cnt.valid++;
+              if (FLAG && (nd & kNdFlag)) flag_push(flist, fcap, e, ta, tb, 0, PH_R_NDIVS);
               ok = false;
             }
           }
@@ -659,12 +711,13 @@ k_edges_flat(const __grid_constant__ ChainDev<Real, kMaxJ> c, long long E, const
       const bool first = running && P.k == 1;
       if constexpr (PL) lane_pass_planar<Real, true>(c, tg, L, mem, first ? P.qa : mem.prev(), first ? P.sa : mem.T, o);
       else lane_pass<Real, M, true>(c, tg, L, mem, first ? P.qa : mem.prev(), first ? P.sa : mem.T, o);
-      const int st = lane_step<Real, M, PL>(c, L, mem, o, running);
+      const int st = lane_step<Real, M, PL, FLAG>(c, L, mem, o, running);
       if (running && st != IK_RUNNING) {
         cnt.solves++; cnt.iters += L.it; cnt.evals += L.evals; cnt.ok += (st == IK_OK);
+        if (FLAG) pair_note_solve(P, L);
         if (st != IK_OK) verdict = 0;                             // graph.py:964-966
         else {
-          verdict = pair_advance(c, mem, o.s2, thr2, P, L);
+          verdict = pair_advance<FLAG>(c, mem, o.s2, thr2, P, L);
           if (verdict < 0) winterp_at<Real, M>(W, Real(P.k) / Real(P.ndivs + 1), tg);
         }
       }
@@ -672,12 +725,114 @@ k_edges_flat(const __grid_constant__ ChainDev<Real, kMaxJ> c, long long E, const
     if (edge >= 0 && verdict >= 0) {
       GRR_DCHECK(edge < E && a < Nq && b < Nq);
       if (verdict) atomicOr(&mask[(edge * Nq + a) * Wd + (b >> 5)], 1u << (b & 31));
+      if (FLAG && P.flag) flag_push(flist, fcap, edge, a, b, P.k0, P.flag);
       cnt.pairs++; cnt.valid += verdict;
       edge = -1;
       lane_begin_mem(L, mem);   // idle lanes keep walking valid memory
     }
   }
   cnt.flush(counters);
+}
+
+// ------------------------------------------------------------------------------------------
+// Second pass of the exact edge build (grr_edges_build_exact): the pairs the single-precision pass listed as
+// near-ties are decided again in the arithmetic of the reference (IEEE double, on the double-precision configs)
+// and their mask bits overwritten.  Solves 1 .. k0 - 1 of a listed pair ran clear of every margin, so the
+// double-precision run restarts at solve max(k0 - 1, 1) (k0 - 1 supplies the predecessor of the leaf (k0 - 1, k0);
+// the leaf before it was settled by the first pass) and runs the pair to its end.  k0 = 0 (Ndivs rounding): whole pair.
+// Persistent lanes pull list entries from a global counter.
+// ------------------------------------------------------------------------------------------
+template <typename Real, int M, bool PL>
+__global__ void __launch_bounds__(128)
+k_edges_recheck(const __grid_constant__ ChainDev<Real, kMaxJ> c, const int32_t *__restrict__ wedges,
+                const Real *__restrict__ params, const Real *__restrict__ q_kept, int Nq, int Nqp, Real epsilon, uint32_t *mask,
+                uint32_t *edge_stats, const unsigned long long *__restrict__ flist, unsigned long long fcap,
+                unsigned long long *work, unsigned long long *counters) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int n = c.n, dw = (c.mode == 2 ? 6 : 3);
+  const int Wd = (Nq + 31) >> 5;
+  LaneMem<Real, col_rows(M, PL)> mem;
+  mem.init(reinterpret_cast<Real *>(smem_raw) + threadIdx.x, (int)blockDim.x, n);
+  for (int j = 0; j < lane_reals<col_rows(M, PL)>(n); j++) mem.base[j * mem.T] = 0;
+  const unsigned long long listed = flist[0];
+  const unsigned long long total = listed < fcap ? listed : fcap;
+  const Real eps = epsilon * sqrt_(Real(c.nlinks_eps));
+  const Real thr = eps * Real(c.nlinks_eps);
+  const Real thr2 = thr * thr;
+  LaneIK<Real, M> L;
+  lane_begin_mem(L, mem);
+  PairLane<Real> P;
+  WInterp<Real, M> W;
+  Target<Real, M> tg;
+  tg.x[0] = tg.x[1] = tg.x[2] = 0;
+  if (M == 6) { for (int k = 0; k < 9; k++) tg.R[k] = (k % 4 == 0) ? Real(1) : Real(0); }
+  long long edge = -1;
+  int a = 0, b = 0, kstart = 1;
+  unsigned flagged = 0, flipped = 0;
+  long long dvalid = 0;
+  bool done = false;
+  for (;;) {
+    int verdict = -1;
+    if (edge < 0 && !done) {
+      const unsigned long long t = atomicAdd(work, 1ull);
+      if (t >= total) done = true;
+      else {
+        const unsigned long long w0 = flist[2 + 2 * t], w1 = flist[3 + 2 * t];
+        edge = (long long)(w0 >> 32); a = (int)((w0 >> 16) & 0xffffu); b = (int)(w0 & 0xffffu);
+        const int k0 = (int)(w1 & 0xffffffffu);
+        const int iw = wedges[2 * edge], jw = wedges[2 * edge + 1];
+        Real a6[6], b6[6];
+        for (int k = 0; k < dw; k++) { a6[k] = params[(long long)iw * dw + k]; b6[k] = params[(long long)jw * dw + k]; }
+        winterp_begin<Real, M, kMaxJ>(c, a6, b6, W);
+        P.qa = q_kept + (long long)iw * n * Nqp + a; P.qb = q_kept + (long long)jw * n * Nqp + b; P.sa = Nqp; P.sb = Nqp;
+        flagged++;
+        if (!pair_begin<Real, M>(c, eps, P, L)) verdict = 1;
+        else {
+          kstart = (k0 >= 2 && k0 <= P.ndivs) ? k0 - 1 : 1;
+          P.k = kstart;
+          const Real u = Real(P.k) / Real(P.ndivs + 1);
+          lane_begin_lerp<Real, M>(L, P.qa, P.sa, P.qb, P.sb, u);
+          winterp_at<Real, M>(W, u, tg);
+        }
+      }
+    }
+    if (__all_sync(0xffffffffu, edge < 0)) break;
+    const bool running = (edge >= 0 && verdict < 0);
+    if (__any_sync(0xffffffffu, running)) {
+      PassOut<Real, M> o;
+      const bool first = running && P.k == 1;
+      if constexpr (PL) lane_pass_planar<Real, true>(c, tg, L, mem, first ? P.qa : mem.prev(), first ? P.sa : mem.T, o);
+      else lane_pass<Real, M, true>(c, tg, L, mem, first ? P.qa : mem.prev(), first ? P.sa : mem.T, o);
+      const int st = lane_step<Real, M, PL>(c, L, mem, o, running);
+      if (running && st != IK_RUNNING) {
+        if (st != IK_OK) verdict = 0;
+        else {
+          verdict = pair_advance(c, mem, o.s2, thr2, P, L, P.k == kstart && kstart > 1);
+          if (verdict < 0) winterp_at<Real, M>(W, Real(P.k) / Real(P.ndivs + 1), tg);
+        }
+      }
+    }
+    if (edge >= 0 && verdict >= 0) {
+      uint32_t *word = &mask[(edge * Nq + a) * Wd + (b >> 5)];
+      const uint32_t bit = 1u << (b & 31);
+      const uint32_t old = verdict ? atomicOr(word, bit) : atomicAnd(word, ~bit);
+      const int was = (old & bit) ? 1 : 0;
+      if (was != verdict) {
+        flipped++; dvalid += verdict - was;
+        if (edge_stats) atomicAdd(&edge_stats[2 * edge + 1], (uint32_t)(verdict - was));
+      }
+      edge = -1;
+      lane_begin_mem(L, mem);
+    }
+  }
+  if (counters) {
+    warp_add(counters, GRR_CNT_FLAGGED, flagged);
+    warp_add(counters, GRR_CNT_FLIPPED, flipped);
+    // valid-pair count of the first pass corrected by the verdicts that changed (two's complement add)
+    for (int o = 16; o > 0; o >>= 1) dvalid += __shfl_down_sync(0xffffffffu, dvalid, o);
+    if ((threadIdx.x & 31) == 0 && dvalid) atomicAdd(counters + GRR_CNT_VALID, (unsigned long long)dvalid);
+    if (blockIdx.x == 0 && threadIdx.x == 0 && listed > fcap) atomicAdd(counters + GRR_CNT_FLAG_DROPPED, listed - fcap);
+  }
 }
 
 // pair-test load of an edge list: out[0] += pairs that will be tested, out[1] += edges with at least one
@@ -855,11 +1010,14 @@ struct Impl {
     if (rc) return rc;
     return check_launch("k_valid_edge_batch");
   }
+  // ex != nullptr: exact build -- single-precision pass with near-tie flags, then the listed pairs again in double
   static int edges_build(const HostChain &h, long long E, const int32_t *wedges, const void *params, const void *q_kept,
                          const int32_t *count, const int32_t *old_count, int Nq, int Nqp, double epsilon,
-                         uint32_t *mask, uint32_t *edge_stats, unsigned long long *work, unsigned long long *scratch,
-                         unsigned long long *counters, cudaStream_t st) {
+                         uint32_t *mask, uint32_t *edge_stats, unsigned long long *work, const ScratchReq *sreq,
+                         unsigned long long *counters, cudaStream_t st, const ExactArgs *ex) {
     if (E <= 0) return 0;
+    if (ex && sizeof(Real) != 4) { set_error("edges_build: the exact build is a single-precision pass + double-precision recheck"); return -1; }
+    if (ex && !sreq) { set_error("edges_build: the exact build needs the handle's scratch"); return -1; }
     Chain c; fill_chain(h, c);
     const int Wd = (Nq + 31) / 32;
     const size_t fixed = 2 * (size_t)h.n * Nqp * sizeof(Real) + (size_t)((Nq * Wd + 3) & ~3) * sizeof(uint32_t);
@@ -867,13 +1025,25 @@ struct Impl {
     lane_geometry(h, fixed, sizeof(Real) == 4 ? (M == 3 ? 512 : 384) : 256, threads, per_sm);
     // The work per workspace edge decides the kernel: one tiny reduction + a 16-byte readback.
     double avg = 0;
+    unsigned long long pairs = 0;
     {
       unsigned long long hload[2] = {0, 0};
       cudaMemsetAsync(work, 0, 2 * sizeof(unsigned long long), st);
       k_edge_load<<<(unsigned)((E + 255) / 256), 256, 0, st>>>(E, wedges, count, old_count, work);
       cudaMemcpyAsync(hload, work, sizeof hload, cudaMemcpyDeviceToHost, st);
       cudaStreamSynchronize(st);
+      pairs = hload[0];
       if (hload[1] > 0) avg = (double)hload[0] / (double)hload[1];
+    }
+    // device scratch: E + 1 queue offsets (global-queue kernel), then the near-tie list (count word + pad + entries)
+    unsigned long long *offs = nullptr, *flist = nullptr;
+    unsigned long long fcap = 0;
+    if (sreq) {
+      size_t words = (size_t)E + 2;
+      if (ex) { fcap = pairs / 4 + 65536; words += 2 + 2 * (size_t)fcap; }
+      offs = sreq->get(sreq->ctx, words);
+      if (!offs) return -3;
+      if (ex) { flist = offs + ((E + 2) & ~1ll); cudaMemsetAsync(flist, 0, 2 * sizeof(unsigned long long), st); }
     }
     // dense: a CTA owns one workspace edge, so lanes beyond pairs/~6 would idle for the whole edge
     int dense_threads = threads;
@@ -887,7 +1057,7 @@ struct Impl {
     // L1/L2, which costs more the longer the chain).  Fitted to the five BASELINE configs (profiles/r01_edge_kernel.md):
     //   dense ~ rounds / (rounds + 1.3),  flat ~ 1 - 0.009 n.
     bool flat = false;
-    if (scratch) {
+    if (offs) {
       if (threads < 32) flat = true;                              // node blocks too large to stage
       else if (avg > 0) {
         const double rounds = avg / dense_threads;
@@ -895,30 +1065,68 @@ struct Impl {
       }
     }
     const char *force = getenv("GRR_EDGES");                      // "flat" / "dense": A/B switch for tests and profiling
-    if (force && scratch && !strcmp(force, "flat")) flat = true;
+    if (force && offs && !strcmp(force, "flat")) flat = true;
     if (force && threads >= 32 && !strcmp(force, "dense")) flat = false;
-    if (flat) return edges_flat(h, c, E, wedges, params, q_kept, count, old_count, Nq, Nqp, epsilon, mask, edge_stats, work,
-                                scratch, counters, st);
-    if (threads < 32) { set_error("edges_build: Nq=%d, n=%d does not fit shared memory", Nq, h.n); return -2; }
-    threads = dense_threads;
-    const size_t smem = fixed + (size_t)threads * h.n * (4 + mc(h)) * sizeof(Real);
+    int rc = 0;
+    if (flat) rc = edges_flat(h, c, E, wedges, params, q_kept, count, old_count, Nq, Nqp, epsilon, mask, edge_stats, work,
+                              offs, counters, st, flist, fcap);
+    else {
+      if (threads < 32) { set_error("edges_build: Nq=%d, n=%d does not fit shared memory", Nq, h.n); return -2; }
+      threads = dense_threads;
+      const size_t smem = fixed + (size_t)threads * h.n * (4 + mc(h)) * sizeof(Real);
+      auto launch = [&](auto kern) -> int {
+        if (set_smem(kern, smem, "k_edges_build")) return -2;
+        kern<<<(unsigned)E, threads, smem, st>>>(c, wedges, (const Real *)params, (const Real *)q_kept, count, old_count, Nq, Nqp,
+                                                 (Real)epsilon, mask, edge_stats, counters, flist, fcap);
+        return 0;
+      };
+      const bool pl = planar(h);
+      if constexpr (kHasPlanar && sizeof(Real) == 4) {
+        if (pl) rc = flist ? launch(k_edges_build<Real, M, true, true>) : launch(k_edges_build<Real, M, true, false>);
+        else rc = flist ? launch(k_edges_build<Real, M, false, true>) : launch(k_edges_build<Real, M, false, false>);
+      } else if constexpr (kHasPlanar) {
+        rc = pl ? launch(k_edges_build<Real, M, true, false>) : launch(k_edges_build<Real, M, false, false>);
+      } else if constexpr (sizeof(Real) == 4) {
+        rc = flist ? launch(k_edges_build<Real, M, false, true>) : launch(k_edges_build<Real, M, false, false>);
+      } else rc = launch(k_edges_build<Real, M, false, false>);
+      if (rc) return rc;
+      rc = check_launch("k_edges_build");
+    }
+    if (rc || !ex) return rc;
+    return Impl<double, M>::edges_recheck(h, wedges, ex->params64, ex->q64, Nq, Nqp, epsilon, mask, edge_stats, flist, fcap,
+                                          work, counters, st);
+  }
+
+  // second pass of the exact build: the listed near-tie pairs in this Impl's arithmetic (instantiated for double)
+  static int edges_recheck(const HostChain &h, const int32_t *wedges, const void *params, const void *q_kept, int Nq, int Nqp,
+                           double epsilon, uint32_t *mask, uint32_t *edge_stats, const unsigned long long *flist,
+                           unsigned long long fcap, unsigned long long *work, unsigned long long *counters, cudaStream_t st) {
+    Chain c; fill_chain(h, c);
+    const int threads = 128;
+    const size_t smem = (size_t)threads * h.n * (4 + mc(h)) * sizeof(Real);
+    cudaMemsetAsync(work, 0, sizeof(unsigned long long), st);
     auto launch = [&](auto kern) -> int {
-      if (set_smem(kern, smem, "k_edges_build")) return -2;
-      kern<<<(unsigned)E, threads, smem, st>>>(c, wedges, (const Real *)params, (const Real *)q_kept, count, old_count, Nq, Nqp,
-                                               (Real)epsilon, mask, edge_stats, counters);
+      if (set_smem(kern, smem, "k_edges_recheck")) return -2;
+      int per_sm = 0;
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem) != cudaSuccess || per_sm < 1) {
+        set_error("k_edges_recheck: n=%d does not fit shared memory", h.n); return -2;
+      }
+      kern<<<(unsigned)(sm_count(h.device) * per_sm), threads, smem, st>>>(c, wedges, (const Real *)params, (const Real *)q_kept, Nq,
+                                                                           Nqp, (Real)epsilon, mask, edge_stats, flist, fcap, work,
+                                                                           counters);
       return 0;
     };
     int rc;
-    if constexpr (kHasPlanar) rc = planar(h) ? launch(k_edges_build<Real, M, true>) : launch(k_edges_build<Real, M, false>);
-    else rc = launch(k_edges_build<Real, M, false>);
+    if constexpr (kHasPlanar) rc = planar(h) ? launch(k_edges_recheck<Real, M, true>) : launch(k_edges_recheck<Real, M, false>);
+    else rc = launch(k_edges_recheck<Real, M, false>);
     if (rc) return rc;
-    return check_launch("k_edges_build");
+    return check_launch("k_edges_recheck");
   }
 
   static int edges_flat(const HostChain &h, const Chain &c, long long E, const int32_t *wedges, const void *params,
                         const void *q_kept, const int32_t *count, const int32_t *old_count, int Nq, int Nqp, double epsilon,
                         uint32_t *mask, uint32_t *edge_stats, unsigned long long *work, unsigned long long *offs,
-                        unsigned long long *counters, cudaStream_t st) {
+                        unsigned long long *counters, cudaStream_t st, unsigned long long *flist, unsigned long long fcap) {
     const int Wd = (Nq + 31) / 32;
     k_edges_prepare<<<(unsigned)E, 128, 0, st>>>(E, wedges, count, old_count, Nq, Wd, mask, offs, edge_stats);
     if (int rc = check_launch("k_edges_prepare")) return rc;
@@ -935,12 +1143,19 @@ struct Impl {
       }
       kern<<<(unsigned)(sm_count(h.device) * per_sm), threads, smem, st>>>(c, E, wedges, (const Real *)params, (const Real *)q_kept,
                                                                            count, old_count, Nq, Nqp, (Real)epsilon, mask, offs,
-                                                                           work, counters);
+                                                                           work, counters, flist, fcap);
       return 0;
     };
     int rc;
-    if constexpr (kHasPlanar) rc = planar(h) ? launch(k_edges_flat<Real, M, true>) : launch(k_edges_flat<Real, M, false>);
-    else rc = launch(k_edges_flat<Real, M, false>);
+    const bool pl = planar(h);
+    if constexpr (kHasPlanar && sizeof(Real) == 4) {
+      if (pl) rc = flist ? launch(k_edges_flat<Real, M, true, true>) : launch(k_edges_flat<Real, M, true, false>);
+      else rc = flist ? launch(k_edges_flat<Real, M, false, true>) : launch(k_edges_flat<Real, M, false, false>);
+    } else if constexpr (kHasPlanar) {
+      rc = pl ? launch(k_edges_flat<Real, M, true, false>) : launch(k_edges_flat<Real, M, false, false>);
+    } else if constexpr (sizeof(Real) == 4) {
+      rc = flist ? launch(k_edges_flat<Real, M, false, true>) : launch(k_edges_flat<Real, M, false, false>);
+    } else rc = launch(k_edges_flat<Real, M, false, false>);
     if (rc) return rc;
     if (int rc2 = check_launch("k_edges_flat")) return rc2;
     if (edge_stats) {

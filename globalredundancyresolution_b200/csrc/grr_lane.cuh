@@ -26,20 +26,31 @@
 #include "grr_device.cuh"
 
 namespace grr {
+#if defined(GRR_STUDY) && !defined(__CUDA_ARCH__)
+void study_tie(double alam, double Dc, double curv, double tgt, double slope, bool same, double slack, double fold, double pn2, int it);
+#endif
 
 // ---- fast scalar helpers (float: MUFU based; double: exact) ---------------------------------
-__device__ __forceinline__ float fdiv_(float a, float b) { return __fdividef(a, b); }
-__device__ __forceinline__ double fdiv_(double a, double b) { return a / b; }
-__device__ __forceinline__ float rcp_ge1_(float a) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a)); return r; }  // a >= 1
-__device__ __forceinline__ double rcp_ge1_(double a) { return 1.0 / a; }
-__device__ __forceinline__ float rsqrt_(float a) { return rsqrtf(a); }
-__device__ __forceinline__ double rsqrt_(double a) { return 1.0 / sqrt(a); }
+#ifdef __CUDA_ARCH__
+GRR_DEV float fdiv_(float a, float b) { return __fdividef(a, b); }
+GRR_DEV float rcp_ge1_(float a) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a)); return r; }  // a >= 1
+GRR_DEV float rsqrt_(float a) { return rsqrtf(a); }
+GRR_DEV int float_bits_(float t) { return __float_as_int(t); }
+#else
+GRR_DEV float fdiv_(float a, float b) { return a / b; }
+GRR_DEV float rcp_ge1_(float a) { return 1.0f / a; }
+GRR_DEV float rsqrt_(float a) { return 1.0f / sqrtf(a); }
+GRR_DEV int float_bits_(float t) { int q; memcpy(&q, &t, 4); return q; }
+#endif
+GRR_DEV double fdiv_(double a, double b) { return a / b; }
+GRR_DEV double rcp_ge1_(double a) { return 1.0 / a; }
+GRR_DEV double rsqrt_(double a) { return 1.0 / sqrt(a); }
 
 // sin/cos for joint angles (|x| << 2^22): Cody-Waite reduction to [-pi/4, pi/4] with the
 // round-to-nearest magic constant (no F2I / I2F), cephes minimax polynomials, quadrant fix-up.
-__device__ __forceinline__ void sincos_joint(float x, float *s, float *c) {
+GRR_DEV void sincos_joint(float x, float *s, float *c) {
   const float t = fmaf(x, 0.636619772367581343f, 12582912.0f);
-  const int q = __float_as_int(t);
+  const int q = float_bits_(t);
   const float k = t - 12582912.0f;
   float r = fmaf(k, -1.5707962512969970703f, x);
   r = fmaf(k, -7.5497894158615963534e-08f, r);
@@ -56,9 +67,9 @@ __device__ __forceinline__ void sincos_joint(float x, float *s, float *c) {
   *s = (q & 2) ? -ss : ss;
   *c = ((q + 1) & 2) ? -cc : cc;
 }
-__device__ __forceinline__ void sincos_joint(double x, double *s, double *c) { sincos(x, s, c); }
+GRR_DEV void sincos_joint(double x, double *s, double *c) { sincos(x, s, c); }
 // every joint limit of the chain lies inside [-pi/4, pi/4] (planar 10R / 20R): no reduction, no fix-up
-__device__ __forceinline__ void sincos_small(float r, float *s, float *c) {
+GRR_DEV void sincos_small(float r, float *s, float *c) {
   const float r2 = r * r;
   float sp = fmaf(r2, -1.9515295891e-4f, 8.3321608736e-3f);
   sp = fmaf(sp, r2, -1.6666654611e-1f);
@@ -67,7 +78,7 @@ __device__ __forceinline__ void sincos_small(float r, float *s, float *c) {
   cp = fmaf(cp, r2, 4.166664568298827e-2f);
   *c = fmaf(cp * r2, r2, fmaf(r2, -0.5f, 1.0f));
 }
-__device__ __forceinline__ void sincos_small(double x, double *s, double *c) { sincos(x, s, c); }
+GRR_DEV void sincos_small(double x, double *s, double *c) { sincos(x, s, c); }
 
 // Reals of shared memory one lane needs: three rotating config buffers (line-search origin xold,
 // trial point xcur, previous interpolated solution prev), the direction p and the Jacobian columns.
@@ -83,14 +94,14 @@ struct LaneMem {
   int T;        // lanes per CTA (stride)
   int n;
   int o_xold, o_xcur, o_prev;   // element offsets of the three config buffers
-  __device__ __forceinline__ void init(Real *b, int T_, int n_) {
+  GRR_DEV void init(Real *b, int T_, int n_) {
     base = b; T = T_; n = n_; o_xold = 0; o_xcur = n_ * T_; o_prev = 2 * n_ * T_;
   }
-  __device__ __forceinline__ Real *xold() const { return base + o_xold; }
-  __device__ __forceinline__ Real *xcur() const { return base + o_xcur; }
-  __device__ __forceinline__ Real *prev() const { return base + o_prev; }
-  __device__ __forceinline__ Real *p() const { return base + 3 * n * T; }
-  __device__ __forceinline__ Real *cols() const { return base + 4 * n * T; }   // [j][r], r < MC
+  GRR_DEV Real *xold() const { return base + o_xold; }
+  GRR_DEV Real *xcur() const { return base + o_xcur; }
+  GRR_DEV Real *prev() const { return base + o_prev; }
+  GRR_DEV Real *p() const { return base + 3 * n * T; }
+  GRR_DEV Real *cols() const { return base + 4 * n * T; }   // [j][r], r < MC
 };
 
 // Where the current trial point comes from: x_j = clamp(a[j*sa] + t * (lerp ? b[j*sb] - a[j*sa] : b[j*sb])).
@@ -102,9 +113,22 @@ struct XSrc {
   bool lerp;
 };
 
+// bits of LaneIK::phase.  PH_SEARCH: a line search is running (else: the seed point is being evaluated).
+// The other three belong to the near-tie bookkeeping of the FP32 edge phase (FLAG builds of lane_step, see there):
+// PH_SOFT: a convergence test fell within the FP32 error of tol and was taken as "not converged"; PH_HARD: a
+// decision whose two outcomes cannot both be followed fell within its margin (the pair must be re-tested in
+// double precision); PH_INFL: the step length of this solve came out of an interior backtrack (its error is a
+// multiple of the plain round-off, margins are widened).
+enum : int { PH_SEARCH = 1, PH_SOFT = 2, PH_HARD = 4, PH_INFL = 8,
+             // which decision raised PH_HARD (diagnostics; they ride along in the same word at no cost)
+             PH_R_CONVX = 1 << 4, PH_R_STPMAX = 1 << 5, PH_R_SLOPE = 1 << 6, PH_R_ALAM = 1 << 7, PH_R_ARMIJO = 1 << 8,
+             PH_R_DISC = 1 << 9, PH_R_SOFT2 = 1 << 10, PH_R_SOFTFAIL = 1 << 11, PH_R_MAXIT = 1 << 12, PH_R_LEAF = 1 << 13,
+             PH_R_NDIVS = 1 << 14, PH_R_ALL = 0x7ff0 };
+
 template <typename Real, int M>
 struct LaneIK {
   Real fold, slope, alam, alam2, f2, alamin, stpmax, resid;
+  Real amb;      // FLAG builds: after IK_OK, radius within which the double-precision solution may lie (0 = round-off only)
   int it, evals, phase;
   // the Newton step is folded into the next chain pass.  `first` = that pass derives the
   // direction p_j = -col_j . y from the Jacobian columns still in memory (ny = -y) and stores it.
@@ -115,21 +139,21 @@ struct LaneIK {
 };
 
 template <typename Real, int M>
-__device__ __forceinline__ void lane_reset(LaneIK<Real, M> &L) {
+GRR_DEV void lane_reset(LaneIK<Real, M> &L) {
   L.it = 0; L.evals = 0; L.phase = 0; L.first = false; L.check_convx = false; 
 #pragma unroll
   for (int r = 0; r < M; r++) L.ny[r] = 0;
-  L.alam = 0; L.alam2 = 0; L.f2 = 0; L.fold = 0; L.slope = 0; L.alamin = 0; L.stpmax = 0; L.resid = 0;
+  L.alam = 0; L.alam2 = 0; L.f2 = 0; L.fold = 0; L.slope = 0; L.alamin = 0; L.stpmax = 0; L.resid = 0; L.amb = 0;
 }
 // Start an instance whose seed is lerp(qa, qb, u) read from (a, b) with strides (sa, sb).
 template <typename Real, int M>
-__device__ __forceinline__ void lane_begin_lerp(LaneIK<Real, M> &L, const Real *a, int sa, const Real *b, int sb, Real u) {
+GRR_DEV void lane_begin_lerp(LaneIK<Real, M> &L, const Real *a, int sa, const Real *b, int sb, Real u) {
   lane_reset(L);
   L.src.a = a; L.src.b = b; L.src.sa = sa; L.src.sb = sb; L.src.t = u; L.src.lerp = true;
 }
 // Start an instance whose seed has been written to mem.xold() (t = 0: the direction is ignored).
 template <typename Real, int M, int MC>
-__device__ __forceinline__ void lane_begin_mem(LaneIK<Real, M> &L, const LaneMem<Real, MC> &mem) {
+GRR_DEV void lane_begin_mem(LaneIK<Real, M> &L, const LaneMem<Real, MC> &mem) {
   lane_reset(L);
   L.src.a = mem.xold(); L.src.b = mem.p(); L.src.sa = mem.T; L.src.sb = mem.T; L.src.t = 0; L.src.lerp = false;
   L.res = mem.xold();
@@ -138,7 +162,7 @@ __device__ __forceinline__ void lane_begin_mem(LaneIK<Real, M> &L, const LaneMem
 // short joint: identity preceding rotation, axis = sgn * e_K.  (I1, I2) are the two components the
 // rotation mixes: new_I1 = c a_I1 - s a_I2, new_I2 = s a_I1 + c a_I2.
 template <typename Real, int M, int K>
-__device__ __forceinline__ void joint_axis(Real s, Real co, Real sgn, Real *v, Real *G, Real *col) {
+GRR_DEV void joint_axis(Real s, Real co, Real sgn, Real *v, Real *G, Real *col) {
   constexpr int I1 = (K + 1) % 3, I2 = (K + 2) % 3;
   // column: G^T (axis x v), axis x v has components I1: -sgn v_I2, I2: +sgn v_I1
   const Real w1 = -sgn * v[I2], w2 = sgn * v[I1];
@@ -175,7 +199,7 @@ struct PassOut {
 // rotation about y, kept as (cos, sin); columns have two in-plane components (x, z); the normal matrix is
 // 2x2.  Same algorithm, a third of the arithmetic.
 template <typename Real, bool WITH_REF, bool SMALL, bool POS, typename ChainT>
-__device__ __forceinline__ void lane_pass_planar_(const ChainT &c, const Target<Real, 3> &tg, const LaneIK<Real, 3> &L,
+GRR_DEV void lane_pass_planar_(const ChainT &c, const Target<Real, 3> &tg, const LaneIK<Real, 3> &L,
                                                   const LaneMem<Real, 2> &mem, const Real *xref, int sref,
                                                   PassOut<Real, 3> &o) {
   const int n = c.n;
@@ -263,7 +287,7 @@ __device__ __forceinline__ void lane_pass_planar_(const ChainT &c, const Target<
   o.fmax = max_(max_(abs_(o.Fw[0]), abs_(o.Fw[1])), abs_(o.Fw[2]));
 }
 template <typename Real, bool WITH_REF, typename ChainT>
-__device__ __forceinline__ void lane_pass_planar(const ChainT &c, const Target<Real, 3> &tg, const LaneIK<Real, 3> &L,
+GRR_DEV void lane_pass_planar(const ChainT &c, const Target<Real, 3> &tg, const LaneIK<Real, 3> &L,
                                                  const LaneMem<Real, 2> &mem, const Real *xref, int sref,
                                                  PassOut<Real, 3> &o) {
   // the shipped planar_{10,20}R robots: limits inside +-pi/4 and every axis +e_y
@@ -272,7 +296,7 @@ __device__ __forceinline__ void lane_pass_planar(const ChainT &c, const Target<R
 }
 
 template <typename Real, int M, bool WITH_REF, typename ChainT>
-__device__ __forceinline__ void lane_pass(const ChainT &c, const Target<Real, M> &tg, const LaneIK<Real, M> &L,
+GRR_DEV void lane_pass(const ChainT &c, const Target<Real, M> &tg, const LaneIK<Real, M> &L,
                                           const LaneMem<Real, M> &mem, const Real *xref, int sref, PassOut<Real, M> &o) {
   const int n = c.n;
   const XSrc<Real> &src = L.src;
@@ -387,7 +411,7 @@ __device__ __forceinline__ void lane_pass(const ChainT &c, const Target<Real, M>
 
 // Cholesky solve of the packed SPD matrix A (lower) with reciprocal square roots.
 template <typename Real, int M>
-__device__ __forceinline__ void chol_solve_fast(Real (&A)[M * (M + 1) / 2], const Real *b, Real *y) {
+GRR_DEV void chol_solve_fast(Real (&A)[M * (M + 1) / 2], const Real *b, Real *y) {
   Real inv[M];
 #pragma unroll
   for (int r = 0; r < M; r++) {
@@ -417,8 +441,8 @@ __device__ __forceinline__ void chol_solve_fast(Real (&A)[M * (M + 1) / 2], cons
 }
 
 // Numerical Recipes lnsrch backtracking: the next trial step length after a rejected trial
-template <typename Real, int M>
-__device__ __forceinline__ void lane_backtrack(LaneIK<Real, M> &L, Real f) {
+template <bool FLAG, typename Real, int M>
+GRR_DEV void lane_backtrack(LaneIK<Real, M> &L, Real f, Real fl_rel) {
   Real tmplam;
   if (L.alam == Real(1)) tmplam = -L.slope / (Real(2) * (f - L.fold - L.slope));
   else {
@@ -428,15 +452,57 @@ __device__ __forceinline__ void lane_backtrack(LaneIK<Real, M> &L, Real f) {
     if (a == Real(0)) tmplam = -L.slope / (Real(2) * b);
     else {
       const Real disc = b * b - Real(3) * a * L.slope;
+      if (FLAG && abs_(disc) < fl_rel * b * b) L.phase |= PH_HARD | PH_R_DISC;       // the two branches are not continuous at disc = 0
       if (disc < Real(0)) tmplam = Real(0.5) * L.alam;
       else if (b <= Real(0)) tmplam = (-b + sqrt_(disc)) / (Real(3) * a);
       else tmplam = -L.slope / (b + sqrt_(disc));
     }
     if (tmplam > Real(0.5) * L.alam) tmplam = Real(0.5) * L.alam;
   }
+  // min / max clamps are continuous; an interior value carries the cancellation error of f - fold - slope
+  if (FLAG && tmplam > Real(0.1) * L.alam && tmplam < Real(0.5) * L.alam) L.phase |= PH_INFL;
   L.alam2 = L.alam; L.f2 = f;
   L.alam = max_(tmplam, Real(0.1) * L.alam);
   L.src.t = L.alam;
+}
+
+// Directional derivative of f = |F|^2 / 2 at the current trial point along the line-search direction with the joints
+// that sit on a limit and are pushed outwards taken out (the clamped direction p_c): Dc = g . p_c, g = J^T F from the
+// columns and residual of the pass that has just run.  `same_set` = the joints clamped at the trial point are exactly
+// those clamped at the line-search origin for every step length (origin on the limit, p pointing outwards), i.e. the
+// clamped path origin -> trial point is a straight segment along p_c.  Runs in the transition (few lanes active); it
+// is only called when an Armijo test is a near-tie in single precision.
+template <typename Real, int M, bool PL, typename ChainT>
+GRR_DEV void lane_dirderiv(const ChainT &c, const LaneMem<Real, col_rows(M, PL)> &mem, const PassOut<Real, M> &o, Real &Dc,
+                           bool &same_set) {
+  constexpr int MC = col_rows(M, PL);
+  Real z[MC];
+#pragma unroll
+  for (int r = 0; r < (MC < 3 ? MC : 3); r++) z[r] = o.FL[r];
+  if constexpr (M == 6) {
+    Real D[9];
+    so3_Jl_inv(&o.FL[3], D);
+    m3_Tvec(D, &o.FL[3], &z[3]);
+  }
+  const int n = c.n, T = mem.T;
+  const Real *pp = mem.p(), *xo = mem.xold(), *xt = mem.xcur(), *pc = mem.cols();
+  Real acc = 0;
+  bool same = true;
+#pragma unroll 1
+  for (int j = 0; j < n; j++) {
+    const Real pj = pp[j * T], a = xo[j * T], b = xt[j * T];
+    const Real lo = c.jc[j].bmin, hi = c.jc[j].bmax;
+    const bool out_old = (a >= hi && pj > Real(0)) || (a <= lo && pj < Real(0));
+    const bool out_new = (b >= hi && pj > Real(0)) || (b <= lo && pj < Real(0));
+    if (out_new != out_old) same = false;
+    if (!out_old) {
+      Real g = 0;
+#pragma unroll
+      for (int r = 0; r < MC; r++) g = fma_(pc[(j * MC + r) * T], z[r], g);
+      acc = fma_(g, pj, acc);
+    }
+  }
+  Dc = acc; same_set = same;
 }
 
 // ---- the transition: line-search bookkeeping; no joint loop.  A new Newton iteration only solves the
@@ -448,8 +514,23 @@ __device__ __forceinline__ void lane_backtrack(LaneIK<Real, M> &L, Real f) {
 // g.p = -F^T (J J^T) y = -FL^T S y.  (v4/v5 ran a separate per-joint step loop here: 27-43 instructions
 // per joint at 73 % lane efficiency, 19 % of all issued instructions.)
 // Returns IK_RUNNING or the final status; after a final status the solution is L.res[j * T].
-template <typename Real, int M, bool PL, typename ChainT>
-__device__ __forceinline__ int lane_step(const ChainT &c, LaneIK<Real, M> &L, LaneMem<Real, col_rows(M, PL)> &mem,
+//
+// FLAG (single-precision edge phase): near-tie bookkeeping for bit-identical edge sets.  The reference
+// arithmetic is IEEE double; a single-precision run can only end with another verdict if one of its discrete
+// decisions is taken within the single-precision error of its threshold (measured: 2e-6 .. 3.4e-5 of the pair
+// tests, profiles/r01_parity_report.md).  Every decision is therefore checked against a margin (c.fl_*, filled
+// by fill_chain from the handle's flag scale):
+//   * convergence tests max|F| < tol within the margin are SOFT: the solve goes on as "not converged" and must
+//     converge clearly at the very next test; both outcomes of the tie then lead to "solve succeeded" and the
+//     two candidate solutions differ by at most that last step, which widens the margin of the adjacent leaf
+//     distance tests (L.amb).  (Ties here are frequent -- every solve crosses tol once -- and almost always
+//     harmless, so they are resolved in place: one extra Newton iteration.)
+//   * every other decision (Armijo accept, stall alam < alamin, convergence on x, descent test, step clipping,
+//     the discriminant branch of the cubic backtrack, a second soft tie or a failure after one) within its
+//     margin is HARD: PH_HARD is set, the caller lists the pair and it is re-tested in double precision
+//     (k_edges_flat<double, ..., LIST>).
+template <typename Real, int M, bool PL, bool FLAG = false, typename ChainT>
+GRR_DEV int lane_step(const ChainT &c, LaneIK<Real, M> &L, LaneMem<Real, col_rows(M, PL)> &mem,
                                          const PassOut<Real, M> &o, bool active) {
   const int n = c.n;
   const Real tolf = c.tol, tolx = Real(0.01) * c.tol, ALF = Real(1e-4);
@@ -459,11 +540,13 @@ __device__ __forceinline__ int lane_step(const ChainT &c, LaneIK<Real, M> &L, La
   L.evals++;
   if (L.first) {
     L.first = false;
+    if (FLAG && L.check_convx && abs_(o.testx - tolx) < c.fl_x) L.phase |= PH_HARD | PH_R_CONVX;
     if (L.check_convx && o.testx < tolx) st = IK_CONVX;
     else if (L.check_convx && L.it >= c.max_iters) st = IK_MAXIT;
     else {
       Real test = o.test;
       const Real pn = sqrt_(o.pn2);
+      if (FLAG && abs_(pn - L.stpmax) < c.fl_rel * L.stpmax) L.phase |= PH_HARD | PH_R_STPMAX;
       if (pn > L.stpmax) {
         // clip the step to stpmax (rare): rescale p in memory and evaluate its first trial again
         const Real sc = L.stpmax / pn;
@@ -480,6 +563,7 @@ __device__ __forceinline__ int lane_step(const ChainT &c, LaneIK<Real, M> &L, La
         L.slope *= sc;
         search = false;
       }
+      if (FLAG && !(L.slope < -c.fl_rel * L.fold)) L.phase |= PH_HARD | PH_R_SLOPE;
       if (!(L.slope < Real(0))) { L.it++; st = IK_STALL; }
       else L.alamin = fdiv_(tolx, test);
     }
@@ -489,20 +573,71 @@ __device__ __forceinline__ int lane_step(const ChainT &c, LaneIK<Real, M> &L, La
   if (st == IK_RUNNING && search) {
     L.resid = o.fmax;
     L.res = mem.xcur();
-    if (L.phase == 0) {
-      if (o.fmax < tolf) st = IK_OK;
+    // convergence test with the soft-tie rule (see above); `conv` is the decision that is followed
+    bool conv = o.fmax < tolf;
+    auto conv_test = [&]() {
+      if (FLAG) {
+        const bool near = abs_(o.fmax - tolf) < ((L.phase & PH_INFL) ? Real(8) * c.fl_f : c.fl_f);
+        if (L.phase & PH_SOFT) { if (near || !conv) L.phase |= PH_HARD | PH_R_SOFT2; }
+        else if (near) { L.phase |= PH_SOFT; conv = false; }
+      }
+    };
+    if (!(L.phase & PH_SEARCH)) {
+      conv_test();
+      if (conv) st = IK_OK;
       else if (c.max_iters <= 0) st = IK_MAXIT;
       else { L.stpmax = Real(10) * max_(sqrt_(o.xn2), Real(n)); newstep = true; }
-    } else if (L.alam < L.alamin) {
-      L.it++; L.res = mem.xold(); st = IK_STALL;                        // x <- xold
-    } else if (!(o.f <= L.fold + ALF * L.alam * L.slope)) {
-      lane_backtrack(L, o.f);
     } else {
-      L.it++;
-      if (o.fmax < tolf) st = IK_OK;
-      else { newstep = true; check_convx = true; }
+      if (FLAG && abs_(L.alam - L.alamin) < c.fl_alam * L.alamin) L.phase |= PH_HARD | PH_R_ALAM;
+      if (L.alam < L.alamin) {
+        L.it++; L.res = mem.xold(); st = IK_STALL;                        // x <- xold
+      } else {
+        const Real rhs = L.fold + ALF * L.alam * L.slope;
+        bool accept = o.f <= rhs;
+        if (FLAG) {
+          // |f - rhs| against the error of f and fold: |F| dF ~ sqrt(fold) fl_f, compared in squares
+          const Real df = o.f - rhs, w = (L.phase & PH_INFL) ? Real(64) * c.fl_f2 : c.fl_f2;
+          if (df * df < w * L.fold) {
+            // Near-tie: f - fold is below the single-precision noise (typically a small step length late in a
+            // backtracking sequence, or a step that barely moves).  Decide by the first-order model instead, which
+            // single precision resolves: on the clamped segment origin -> trial point, f(a) - fold lies between
+            // a (Dc -+ alam C |p|^2), C >= |p_c^T H p_c| / |p|^2, so if that interval clears ALF slope for every
+            // a <= alam the exact test rejects at this and every shorter step (-> the search ends below alamin:
+            // stalled), and if it lies below, the exact test accepts here.  Otherwise the pair is re-tested.
+            Real Dc; bool same;
+            lane_dirderiv<Real, M, PL>(c, mem, o, Dc, same);
+            Real trS = 0;
+            if constexpr (PL) trS = o.S[0] + o.S[2];
+            else {
+#pragma unroll
+              for (int r = 0; r < M; r++) trS += o.S[tri(r, r)];
+            }
+            const Real curv = L.alam * o.pn2 * (trS + sqrt_(Real(2) * L.fold) * c.fl_curv);
+            const Real tgt = ALF * L.slope, slack = c.fl_dd * (abs_(Dc) + abs_(L.slope));
+            if (same && Dc - curv - tgt > slack) { L.it++; L.res = mem.xold(); st = IK_STALL; }
+            else if (same && Dc + curv - tgt < -slack) accept = true;
+            else L.phase |= PH_HARD | PH_R_ARMIJO;
+#if defined(GRR_STUDY) && !defined(__CUDA_ARCH__)
+            study_tie((double)L.alam, (double)Dc, (double)curv, (double)tgt, (double)L.slope, same, (double)slack, (double)L.fold, (double)o.pn2, L.it);
+#endif
+          }
+        }
+        if (st != IK_RUNNING) { }
+        else if (!accept) lane_backtrack<FLAG>(L, o.f, c.fl_rel);
+        else {
+          L.it++;
+          conv_test();
+          if (conv) {
+            st = IK_OK;
+            // a soft tie one test earlier: the double-precision run may have stopped one step before this point
+            if (FLAG) L.amb = (L.phase & PH_SOFT) ? L.alam * sqrt_(o.pn2) : Real(0);
+          } else { newstep = true; check_convx = true; }
+        }
+      }
     }
   }
+  if (FLAG && st > IK_OK && (L.phase & PH_SOFT)) L.phase |= PH_HARD | PH_R_SOFTFAIL;     // the other outcome of the tie was "succeeded"
+  if (FLAG && L.it > c.fl_maxit) L.phase |= PH_HARD | PH_R_MAXIT;
   if (newstep) {
     // the accepted point (in xcur) becomes the origin of the next line search: swap roles, no copy
     { const int t = mem.o_xold; mem.o_xold = mem.o_xcur; mem.o_xcur = t; }
@@ -574,7 +709,7 @@ __device__ __forceinline__ int lane_step(const ChainT &c, LaneIK<Real, M> &L, La
     L.fold = o.f; L.alam = 1; L.alam2 = 0; L.f2 = 0; L.alamin = 0;
     L.src.a = mem.xold(); L.src.b = mem.p(); L.src.sa = mem.T; L.src.sb = mem.T; L.src.t = 1; L.src.lerp = false;
     L.res = mem.xold();
-    L.phase = 1;
+    L.phase |= PH_SEARCH;
   }
   return st;
 }

@@ -132,16 +132,23 @@ class RoadmapView:
 
 
 class RedundancyResolver:
-    def __init__(self, resolution, cache=20000, cacheloc=None, seed=0, sample_dtype="float64"):
+    def __init__(self, resolution, cache=20000, cacheloc=None, seed=0, sample_dtype="float64", exact_edges=True):
         """`cache` / `cacheloc` are accepted for signature compatibility (solver.py:239); the disk-backed
         CGraph they configure is replaced by device tensors.
 
         Precision: the Nw*Nq random-start sampling solves (<1 % of the work, long Newton runs whose
         round-off is amplified by up to 50 iterations) run in `sample_dtype` (default float64, so the kept
         joint values agree with the FP64 reference arithmetic to ~1e-12); the O(D Nw Nq^2) edge phase runs
-        in the resolution's dtype (default float32, the FP32 SIMT product path)."""
+        in the resolution's dtype (default float32, the FP32 SIMT product path).
+
+        exact_edges (float32 resolutions only): grr_edges_build_exact -- the single-precision pass lists every pair in
+        which a discrete decision of validEdgeLinear fell within the single-precision error of its threshold, and
+        those pairs (a few per cent) are decided again in double precision, so the edge sets equal those of the
+        reference's double-precision arithmetic (stats: 'flagged', 'flipped').  False = plain single precision
+        (2e-6 .. 3.4e-5 of the verdicts differ, profiles/r01_parity_report.md)."""
         self.resolution = resolution
         self.sample_dtype = sample_dtype
+        self.exact_edges = bool(exact_edges)
         self.robot = resolution.robot
         self.cachesize = cache
         self.cacheloc = cacheloc
@@ -411,12 +418,30 @@ class RedundancyResolver:
         res.chain.dedup(q_raw, status, thresh, kept, kcount, Nq=N, count_in=cin)
         _cabi.scatter_node_blocks(nodes, kept, kcount, d["Qs"], d["count"])
 
-    def _connect_phase(self, d, old_counts):
+    def _edges_launch(self, d, wedges, mask, stats, old_counts):
+        """One edge-construction call on the given workspace edges: the exact build (single-precision pass + double-
+        precision recheck of the near-ties) for float32 resolutions unless exact_edges=False, else the plain kernels."""
+        torch = self.resolution._torch()
         res = self.resolution
         if d["Qs"] is not d["Q"]:
             d["Q"].copy_(d["Qs"])            # edge phase reads the kept configs in its own precision
-        res.chain.edges_build(d["wedges"], d["params"], d["Q"], d["count"], self.Nq, DEFAULT_EDGE_CHECK_TOLERANCE,
-                              d["mask"], d["edge_stats"], d["counters_e"], old_count=old_counts)
+        if self.exact_edges and res.torch_dtype == torch.float32:
+            q64 = d["Qs"] if d["Qs"].dtype == torch.float64 else d["Q"].double()
+            p64 = d["params_s"] if d["params_s"].dtype == torch.float64 else d["params"].double()
+            res.chain.edges_build_exact(wedges, d["params"], p64, d["Q"], q64, d["count"], self.Nq, DEFAULT_EDGE_CHECK_TOLERANCE,
+                                        mask, stats, d["counters_e"], old_count=old_counts)
+        else:
+            res.chain.edges_build(wedges, d["params"], d["Q"], d["count"], self.Nq, DEFAULT_EDGE_CHECK_TOLERANCE,
+                                  mask, stats, d["counters_e"], old_count=old_counts)
+
+    def _check_exact(self, ce):
+        """The near-tie list of the exact build must not have overflowed (it never does below 25 % flagged pairs)."""
+        if int(ce[_cabi.CNT_FLAG_DROPPED]) != 0:
+            raise _cabi.GrrError("grr_edges_build_exact: %d near-tie pairs did not fit the recheck list; the edge sets are not "
+                                 "exact (lower the flag scale or use dtype='float64')" % int(ce[_cabi.CNT_FLAG_DROPPED]))
+
+    def _connect_phase(self, d, old_counts):
+        self._edges_launch(d, d["wedges"], d["mask"], d["edge_stats"], old_counts)
 
     def _sweep_levels(self):
         """Wavefront schedule of the sequential sweep of solver.py:773: node i needs the final qlists of its
@@ -527,6 +552,7 @@ class RedundancyResolver:
         t_connect = ev[1].elapsed_time(ev[2]) * 1e-3
         c = d["counters"].cpu().numpy()
         ce = d["counters_e"].cpu().numpy()
+        self._check_exact(ce)
         self.stats = {"sample_ik_solves": int(c[_cabi.CNT_IK_SOLVES]), "sample_ik_iters": int(c[_cabi.CNT_IK_ITERS]),
                       "sample_ik_evals": int(c[_cabi.CNT_IK_EVALS]), "sample_ik_ok": int(c[_cabi.CNT_IK_OK]),
                       "edge_ik_solves": int(ce[_cabi.CNT_IK_SOLVES]), "edge_ik_iters": int(ce[_cabi.CNT_IK_ITERS]),
@@ -535,6 +561,7 @@ class RedundancyResolver:
                       "ik_iters": int(c[_cabi.CNT_IK_ITERS] + ce[_cabi.CNT_IK_ITERS]),
                       "ik_evals": int(c[_cabi.CNT_IK_EVALS] + ce[_cabi.CNT_IK_EVALS]),
                       "pairs": int(ce[_cabi.CNT_PAIRS]), "valid": int(ce[_cabi.CNT_VALID]),
+                      "flagged": int(ce[_cabi.CNT_FLAGGED]), "flipped": int(ce[_cabi.CNT_FLIPPED]),
                       "sampled": int(d["count"].sum().item()) - start_total,
                       "attempts": int(c[_cabi.CNT_IK_SOLVES]), "t_sample": t_sample, "t_connect": t_connect}
 
@@ -596,10 +623,7 @@ class RedundancyResolver:
         oc = None
         if old_counts is not None:
             oc = torch.as_tensor(np.asarray(old_counts, dtype=np.int32), device=res.torch_device)
-        if d["Qs"] is not d["Q"]:
-            d["Q"].copy_(d["Qs"])
-        res.chain.edges_build(wedges, d["params"], d["Q"], d["count"], self.Nq, DEFAULT_EDGE_CHECK_TOLERANCE,
-                              sub_mask, stats, d["counters_e"], old_count=oc)
+        self._edges_launch(d, wedges, sub_mask, stats, oc)
         d["mask"][eid] = sub_mask
         for e in edge_ids:
             self._ecache.pop(int(e), None)
@@ -643,7 +667,9 @@ class RedundancyResolver:
         m8 = d["mask"].view(torch.uint8).reshape(self.E, -1)
         nondeg = int((m8 != 0).any(dim=1).sum().item())
         c = d["counters_e"].cpu().numpy()
+        self._check_exact(c)
         self.stats.update({"pairs": int(c[_cabi.CNT_PAIRS]), "valid": int(c[_cabi.CNT_VALID]), "t_connect": e0.elapsed_time(e1) * 1e-3,
+                           "flagged": int(c[_cabi.CNT_FLAGGED]), "flipped": int(c[_cabi.CNT_FLIPPED]),
                            "edge_ik_solves": int(c[_cabi.CNT_IK_SOLVES]), "edge_ik_iters": int(c[_cabi.CNT_IK_ITERS]),
                            "edge_ik_evals": int(c[_cabi.CNT_IK_EVALS])})
         return nondeg, self.E, 0, e0.elapsed_time(e1) * 1e-3

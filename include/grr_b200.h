@@ -70,7 +70,10 @@ enum {
   GRR_CNT_PAIRS = 3,       /* validEdge calls (pair tests)                      */
   GRR_CNT_VALID = 4,       /* pair tests that returned True                     */
   GRR_CNT_IK_OK = 5,       /* IK instances that converged                       */
-  GRR_CNT_SLOTS = 8        /* length of a counters array (uint64)               */
+  GRR_CNT_FLAGGED = 6,     /* grr_edges_build_exact: pairs re-tested in double precision              */
+  GRR_CNT_FLIPPED = 7,     /* ... of which the double-precision verdict differed from the first pass  */
+  GRR_CNT_FLAG_DROPPED = 8,/* ... near-tie pairs that did not fit the list (must be 0; the call fails)*/
+  GRR_CNT_SLOTS = 16       /* length of a counters array (uint64)               */
 };
 
 const char *grr_last_error(void);
@@ -154,6 +157,23 @@ int grr_edges_build(grr_handle_t h, int dtype, int64_t E, const int32_t *wedges,
                     const void *q_kept, const int32_t *count, const int32_t *old_count, int32_t Nq,
                     int32_t Nqp, double epsilon, uint32_t *mask, uint32_t *edge_stats, uint64_t *counters,
                     void *stream);
+
+/* The same with edge sets equal to those of IEEE double arithmetic (the reference's: Klamp't / KrisLibrary compute in
+ * double) at single-precision speed.  First pass: grr_edges_build's single-precision kernels, which additionally check
+ * every discrete decision of validEdgeLinear's interpolated solves (max|F| < tol, the line search's sufficient-decrease
+ * / minimum-step / convergence-on-x tests, step clipping, the rounding of Ndivs, the leaf distance threshold;
+ * graph.py:938-1006 + SURVEY A.3) against the single-precision error of the compared quantities and list the pairs in
+ * which one of them is a near-tie.  Second pass: the listed pairs (a few per cent) are decided again in double
+ * precision on the double-precision configs and their bits overwritten.  q_kept32 must be q_kept64 rounded to float
+ * (same layout), params32 likewise.  counters additionally receive GRR_CNT_FLAGGED / FLIPPED / FLAG_DROPPED
+ * (FLAG_DROPPED != 0: the handle's near-tie list overflowed -- more than a quarter of the pairs -- and the result is
+ * NOT exact).  The margins are `scale` times the measured single/double differences (default 8;
+ * grr_set_flag_scale). */
+int grr_edges_build_exact(grr_handle_t h, int64_t E, const int32_t *wedges, const float *params32, const double *params64,
+                          const float *q_kept32, const double *q_kept64, const int32_t *count, const int32_t *old_count,
+                          int32_t Nq, int32_t Nqp, double epsilon, uint32_t *mask, uint32_t *edge_stats, uint64_t *counters,
+                          void *stream);
+int grr_set_flag_scale(grr_handle_t h, double scale);
 
 /* Work estimate of grr_edges_build per workspace edge: sum over the pairs it will test of
  * Ndivs + 1 = ceil(robot.distance(qa,qb) / eps) + 1 (graph.py:944-946), i.e. interpolated IK solves +

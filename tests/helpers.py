@@ -30,3 +30,14 @@ def unpack_mask(mask_i32, Nq):
     m = np.ascontiguousarray(mask_i32).view(np.uint32)
     bits = np.unpackbits(m.view(np.uint8).reshape(m.shape[0], m.shape[1], -1), axis=2, bitorder="little")
     return bits[:, :, :Nq].astype(bool)
+
+
+def reference_configs(rr, cap=None):
+    """Kept configs the oracle must be run on to reproduce the device's edge sets, as [Nw][cap][n] float64: the
+    sampling-precision configs (Qs) -- the exact edge build and the float64 build decide every pair in double
+    precision on those; a plain single-precision build (exact_edges=False) reads their float32 roundings (Q)."""
+    import torch
+    cap = rr.Nq if cap is None else cap
+    exact = rr.exact_edges or rr.resolution.torch_dtype == torch.float64
+    key = "Qs" if exact else "Q"
+    return np.ascontiguousarray(np.transpose(rr._dev[key][:, :, :cap].double().cpu().numpy(), (0, 2, 1)))

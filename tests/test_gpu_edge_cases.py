@@ -4,7 +4,7 @@ import pytest
 
 import globalredundancyresolution_b200 as grr
 from globalredundancyresolution_b200 import _cabi
-from helpers import oracle_for, unpack_mask
+from helpers import oracle_for, reference_configs, unpack_mask
 from oracle import oracle as O
 
 torch = pytest.importorskip("torch")
@@ -54,10 +54,10 @@ def test_word_boundaries_and_ragged_counts(built, Nq):
     cnt = rr.counts()
     np.testing.assert_array_equal(cnt, ref["count"])
     assert cnt[4] == 0
-    Q = np.transpose(rr._dev["Q"][:, :, :Nq].double().cpu().numpy(), (0, 2, 1))
+    Q = reference_configs(rr, Nq)
     mask_ref, stats = o.connect_edges(edges, params, Q.copy(), cnt, Nq)
     mask_dev = unpack_mask(rr._dev["mask"].cpu().numpy(), Nq)
-    assert int((mask_dev != mask_ref.astype(bool)).sum()) <= max(1, int(2e-3 * stats[:, 0].sum()))
+    assert int((mask_dev != mask_ref.astype(bool)).sum()) == 0
     # bits outside count[iw] x count[jw] are never set
     for e, (i, j) in enumerate(edges):
         assert not mask_dev[e, cnt[i]:, :].any() and not mask_dev[e, :, cnt[j]:].any()
@@ -109,14 +109,14 @@ def test_large_nq_six_rows_fits_shared_memory(built):
     rr.sanityCheck()
     cnt = rr.counts()
     o = oracle_for(res)
-    Q = np.transpose(rr._dev["Q"][:, :, :200].double().cpu().numpy(), (0, 2, 1))
+    Q = reference_configs(rr, 200)
     e = res.ws_edges
     busy = np.argsort(-(cnt[e[:, 0]] * cnt[e[:, 1]]))[:12]
     mask_ref, stats = o.connect_edges(e[busy], res.ws_params, Q.copy(), cnt, 200)
     mask_dev = unpack_mask(rr._dev["mask"][torch.as_tensor(busy, device=res.torch_device)].cpu().numpy(), 200)
     tested = int(stats[:, 0].sum())
     assert tested > 0
-    assert int((mask_dev != mask_ref.astype(bool)).sum()) <= max(1, int(2e-3 * tested))
+    assert int((mask_dev != mask_ref.astype(bool)).sum()) == 0
 
 
 def test_full_size_properties_cfg2(built):
@@ -230,10 +230,10 @@ def test_dense_and_flat_edge_kernels_agree(built, problem, monkeypatch):
     np.testing.assert_array_equal(d[0][1][:, 0], f[0][1][:, 0])        # pairs tested per workspace edge, first call
     np.testing.assert_array_equal(d[2][:, 0], f[2][:, 0])              # ... growth call
     assert d[0][2]["pairs"] == f[0][2]["pairs"] and d[3]["pairs"] == f[3]["pairs"] > 0
-    tol = max(2, int(1e-3 * d[3]["pairs"]))
+    # the exact build decides every near-tie in double precision: both kernels give the same edge sets bit for bit
     for md, mf in ((d[0][0], f[0][0]), (d[1], f[1])):
-        x = (md ^ mf).view(np.uint8)
-        assert int(np.unpackbits(x).sum()) <= tol
-    for k in ("valid", "ik_solves", "ik_iters", "ik_evals"):
+        np.testing.assert_array_equal(md, mf)
+    assert d[0][2]["valid"] == f[0][2]["valid"] and d[3]["valid"] == f[3]["valid"]
+    for k in ("ik_solves", "ik_iters", "ik_evals"):        # single-precision work counters: the kernels round differently
         assert abs(d[0][2][k] - f[0][2][k]) <= 2e-3 * d[0][2][k] + 2 and abs(d[3][k] - f[3][k]) <= 2e-3 * d[3][k] + 2, k
-    assert abs(int(d[2][:, 1].sum()) - int(f[2][:, 1].sum())) <= tol
+    np.testing.assert_array_equal(d[2][:, 1], f[2][:, 1])

@@ -16,7 +16,7 @@ import pytest
 
 import globalredundancyresolution_b200 as grr
 from globalredundancyresolution_b200 import _cabi
-from helpers import oracle_for, small_problem, unpack_mask
+from helpers import reference_configs, oracle_for, small_problem, unpack_mask
 
 torch = pytest.importorskip("torch")
 pytestmark = pytest.mark.gpu
@@ -110,11 +110,15 @@ def _classify_mismatches(o, res, q_dev, cnt, mask_dev, mask_ref):
 
 
 @pytest.mark.parametrize("case", list(CASES))
-@pytest.mark.parametrize("dtype", ["float64", "float32"])
+@pytest.mark.parametrize("dtype", ["float64", "float32", "float32-plain"])
 def test_roadmap_build_matches_oracle(built, case, dtype):
-    """End to end through RedundancyResolver: sampling (FP64) + dedup + all-pairs edge construction."""
-    pdef, res = small_problem(*CASES[case], dtype=dtype)
-    rr = grr.RedundancyResolver(res, seed=SEED)
+    """End to end through RedundancyResolver: sampling (FP64) + dedup + all-pairs edge construction.
+    float32 = the product path (single-precision pass + double-precision recheck of the near-ties) and float64 = the
+    double-precision build must give the oracle's edge sets bit for bit; float32-plain (exact_edges=False) is the
+    single-precision pass alone, whose differing verdicts are classified and bounded by the measured rate."""
+    exact = dtype != "float32-plain"
+    pdef, res = small_problem(*CASES[case], dtype=dtype.split("-")[0])
+    rr = grr.RedundancyResolver(res, seed=SEED, exact_edges=exact)
     rr.sampleConfigurationSpace(NQ, order_independent=True)
     o = oracle_for(res)
     ref = o.sample_nodes(res.ws_params, rr.node_uid, NQ, seed=SEED)
@@ -127,7 +131,8 @@ def test_roadmap_build_matches_oracle(built, case, dtype):
         if c:
             assert np.abs(Qs[i, :c] - ref["q_kept"][i, :c]).max() < 1e-8
             assert np.abs(Q[i, :c] - ref["q_kept"][i, :c]).max() < 1e-5           # north_star tolerance
-    # edges: oracle on the device's own (rounded) configs, so only the edge arithmetic is compared
+    # edges: oracle on the configs the device decides on (helpers.reference_configs), so only the edge arithmetic is compared
+    Q = reference_configs(rr, NQ)
     mask_ref, stats = o.connect_edges(res.ws_edges, res.ws_params, Q.copy(), cnt, NQ)
     mask_ref = mask_ref.astype(bool)
     mask_dev = unpack_mask(rr._dev["mask"].cpu().numpy(), NQ)
@@ -137,8 +142,17 @@ def test_roadmap_build_matches_oracle(built, case, dtype):
     band, ikflip = _classify_mismatches(o, res, Q, cnt, mask_dev, mask_ref)
     print("\n[%s %s] pairs=%d valid=%d mismatches=%d (threshold-band=%d, ik-path=%d)"
           % (case, dtype, tested, int(mask_ref.sum()), mism, band, ikflip))
-    budget = 1e-3 if dtype == "float64" else 2e-3
-    assert mism <= max(1, int(budget * tested)), "%d of %d pair verdicts differ" % (mism, tested)
+    if exact:
+        assert mism == 0, "%d of %d pair verdicts differ from the double-precision oracle" % (mism, tested)
+        if dtype == "float32":
+            print("   near-tie pairs re-tested in double: %d (%.2f %%), verdicts changed by the recheck: %d"
+                  % (rr.stats["flagged"], 100.0 * rr.stats["flagged"] / max(tested, 1), rr.stats["flipped"]))
+            assert rr.stats["flagged"] <= 0.25 * tested + 16
+    else:
+        # measured: <= 1 differing verdict in 4,687 pairs on planar_3R, 0 on the other test problems; every one is a
+        # near-tie of an interpolated solve ("ik-path") or lies in the threshold band
+        assert mism <= max(1, int(5e-4 * tested)), "%d of %d pair verdicts differ" % (mism, tested)
+        assert band + ikflip == mism
     # orientation + range invariants of the stored edge sets (solver.py:450-452,486-487)
     rr.sanityCheck()
     es = rr._dev["edge_stats"].cpu().numpy()
@@ -173,13 +187,14 @@ def test_variable_orientation_roadmap(built):
     Q = np.transpose(rr._dev["Q"][:, :, :NQv].double().cpu().numpy(), (0, 2, 1))
     for i in range(rr.Nw):
         assert np.abs(Q[i, :cnt[i]] - ref["q_kept"][i, :cnt[i]]).max() < 1e-5
+    Q = reference_configs(rr, NQv)
     mask_ref, stats = o.connect_edges(res.ws_edges, res.ws_params, Q.copy(), cnt, NQv)
     mask_dev = unpack_mask(rr._dev["mask"].cpu().numpy(), NQv)
     tested = int(stats[:, 0].sum())
     mism = int((mask_dev != mask_ref.astype(bool)).sum())
     print("\n[variable] nodes=%d configs=%d pairs=%d valid=%d mismatches=%d" % (rr.Nw, cnt.sum(), tested, mask_ref.sum(), mism))
     assert tested > 100 and 0 < mask_ref.sum() < tested
-    assert mism <= max(1, int(2e-3 * tested))
+    assert mism == 0
 
 
 def test_valid_edge_and_solve_api(built):
@@ -235,9 +250,9 @@ def test_incremental_growth_matches_single_shot_rules(built):
     assert (m3 == m2).all() and nE == rr.E and nondeg == int(m3.reshape(rr.E, -1).any(axis=1).sum())
     # oracle on the final roadmap
     o = oracle_for(res)
-    Q = np.transpose(rr._dev["Q"][:, :, :rr.Nq].double().cpu().numpy(), (0, 2, 1))
+    Q = reference_configs(rr)
     mask_ref, stats = o.connect_edges(e, res.ws_params, Q.copy(), c2, rr.Nq)
-    assert int((m3 != mask_ref.astype(bool)).sum()) <= max(1, int(2e-3 * stats[:, 0].sum()))
+    assert int((m3 != mask_ref.astype(bool)).sum()) == 0
 
 
 def test_container_api_and_views(built):
