@@ -81,7 +81,7 @@ struct ChainDev {
   int axes_positive;           // every short-path joint has sgn = +1
   Real tol, lambda;
   // near-tie margins of the single-precision edge phase (FLAG builds of lane_step / pair_advance; all 0 otherwise)
-  Real fl_f, fl_f2, fl_x, fl_alam, fl_rel, fl_leaf, fl_nd, fl_dd, fl_curv;
+  Real fl_f, fl_f2, fl_x, fl_alam, fl_rel, fl_leaf, fl_nd, fl_dd, fl_curv, fl_curv1, fl_jac;
   int fl_maxit;                // solves longer than this many Newton iterations are not trusted in single precision
   // M_j(theta) = Rp_j * Rot(axis_j, theta) = A + sin(theta) * B - cos(theta) * C
   Real A[NJ][9], B[NJ][9], C[NJ][9];

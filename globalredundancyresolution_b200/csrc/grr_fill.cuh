@@ -41,7 +41,7 @@ void fill_chain(const HostChain &h, ChainDev<Real, NJ> &d) {
   memset(&d, 0, sizeof(d));
   d.fl_f = (Real)h.fl[FL_F]; d.fl_f2 = (Real)(4.0 * h.fl[FL_F] * h.fl[FL_F]); d.fl_x = (Real)h.fl[FL_X];
   d.fl_alam = (Real)h.fl[FL_ALAM]; d.fl_rel = (Real)h.fl[FL_REL]; d.fl_leaf = (Real)h.fl[FL_LEAF]; d.fl_nd = (Real)h.fl[FL_ND];
-  d.fl_dd = (Real)h.fl[FL_DD]; d.fl_curv = (Real)h.fl[FL_CURV];
+  d.fl_dd = (Real)h.fl[FL_DD]; d.fl_curv = (Real)h.fl[FL_CURV]; d.fl_curv1 = (Real)(h.fl[FL_CURV] / h.n); d.fl_jac = (Real)(h.fl[FL_CURV] / h.n);   // |d max|F| / dx| <= reach (rotation rows: 1)
   d.fl_maxit = h.fl[FL_MAXIT] > 1e6 ? 1 << 20 : (int)h.fl[FL_MAXIT];
   d.n = h.n; d.mode = h.mode; d.nlinks_eps = h.nlinks_eps; d.max_iters = h.max_iters;
   d.tol = (Real)h.tol; d.lambda = (Real)h.lambda;

@@ -252,8 +252,10 @@ GRR_DEV bool pair_begin(const ChainT &c, Real eps, PairLane<Real> &P, LaneIK<Rea
 // solutions it joins) flags the pair.
 // FLAG bookkeeping at the end of every interpolated solve (converged or not): collect the solve's near-tie reasons.
 template <typename Real, int M>
-GRR_DEV void pair_note_solve(PairLane<Real> &P, const LaneIK<Real, M> &L) {
-  const int r = L.phase & PH_R_ALL;
+GRR_DEV void pair_note_solve(PairLane<Real> &P, const LaneIK<Real, M> &L, int st) {
+  int r = L.phase & PH_R_ALL;
+  if (st > IK_OK && (L.phase & PH_SOFT)) r |= PH_R_SOFTFAIL;     // the other outcome of the soft tie was "solve succeeded"
+  if (L.phase & PH_PEND) r |= PH_R_ARMIJO;                       // a near-tie that never got its second sample
   if (r && !P.flag) P.k0 = P.k;
   P.flag |= r;
 }
@@ -265,8 +267,11 @@ GRR_DEV int pair_advance(const ChainT &c, LaneMem<Real, MC> &mem, Real s2, Real 
                          LaneIK<Real, M> &L, bool skip_first_leaf = false) {
   Real thr = 0;
   if (FLAG) {
-    thr = sqrt_(thr2);
-    const Real amb = L.amb + P.amb_prev;
+    // margin of the leaf tests: round-off plus the ambiguity radii of the two solutions, the latter capped at half the
+    // threshold (the drift estimate of a sensitive solve is astronomically large: such a solve then flags its leaves
+    // only when their length lies within 0.5 .. 1.5 thr)
+    thr = thr2 * rsqrt_est_(thr2);
+    const Real amb = min_(L.amb + P.amb_prev, Real(0.5) * thr);
     if (abs_(s2 - thr2) < thr2 * (Real(2) * c.fl_leaf) + amb * (Real(2) * thr + amb)) { if (!P.flag) P.k0 = P.k; P.flag |= PH_R_LEAF; }
     P.amb_prev = L.amb;
   }
@@ -275,7 +280,10 @@ GRR_DEV int pair_advance(const ChainT &c, LaneMem<Real, MC> &mem, Real s2, Real 
     const int n = c.n, T = mem.T;
     Real e2 = 0;
     for (int j = 0; j < n; j++) { const Real e = P.qb[j * P.sb] - L.res[j * T]; e2 += e * e; }
-    if (FLAG && abs_(e2 - thr2) < thr2 * (Real(2) * c.fl_leaf) + L.amb * (Real(2) * thr + L.amb)) { if (!P.flag) P.k0 = P.k; P.flag |= PH_R_LEAF; }
+    if (FLAG) {
+      const Real amb = min_(L.amb, Real(0.5) * thr);
+      if (abs_(e2 - thr2) < thr2 * (Real(2) * c.fl_leaf) + amb * (Real(2) * thr + amb)) { if (!P.flag) P.k0 = P.k; P.flag |= PH_R_LEAF; }
+    }
     return (e2 > thr2) ? 0 : 1;
   }
   { const int t = mem.o_prev; mem.o_prev = mem.o_xcur; mem.o_xcur = t; }   // IK_OK leaves the solution in xcur
@@ -509,7 +517,7 @@ k_edges_build(const __grid_constant__ ChainDev<Real, kMaxJ> c, const int32_t *__
         const int st = lane_step<Real, M, PL, FLAG>(c, L, mem, o, running);
         if (running && st != IK_RUNNING) {
           cnt.solves++; cnt.iters += L.it; cnt.evals += L.evals; cnt.ok += (st == IK_OK);
-          if (FLAG) pair_note_solve(P, L);
+          if (FLAG) pair_note_solve(P, L, st);
           if (st != IK_OK) verdict = 0;                         // graph.py:964-966
           else {
             verdict = pair_advance<FLAG>(c, mem, o.s2, thr2, P, L);
@@ -714,7 +722,7 @@ k_edges_flat(const __grid_constant__ ChainDev<Real, kMaxJ> c, long long E, const
       const int st = lane_step<Real, M, PL, FLAG>(c, L, mem, o, running);
       if (running && st != IK_RUNNING) {
         cnt.solves++; cnt.iters += L.it; cnt.evals += L.evals; cnt.ok += (st == IK_OK);
-        if (FLAG) pair_note_solve(P, L);
+        if (FLAG) pair_note_solve(P, L, st);
         if (st != IK_OK) verdict = 0;                             // graph.py:964-966
         else {
           verdict = pair_advance<FLAG>(c, mem, o.s2, thr2, P, L);
@@ -743,7 +751,7 @@ k_edges_flat(const __grid_constant__ ChainDev<Real, kMaxJ> c, long long E, const
 // Persistent lanes pull list entries from a global counter.
 // ------------------------------------------------------------------------------------------
 template <typename Real, int M, bool PL>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(256)
 k_edges_recheck(const __grid_constant__ ChainDev<Real, kMaxJ> c, const int32_t *__restrict__ wedges,
                 const Real *__restrict__ params, const Real *__restrict__ q_kept, int Nq, int Nqp, Real epsilon, uint32_t *mask,
                 uint32_t *edge_stats, const unsigned long long *__restrict__ flist, unsigned long long fcap,
@@ -1093,6 +1101,7 @@ struct Impl {
       rc = check_launch("k_edges_build");
     }
     if (rc || !ex) return rc;
+    if (getenv("GRR_NO_RECHECK")) return rc;                      // timing experiments only: first pass without the second
     return Impl<double, M>::edges_recheck(h, wedges, ex->params64, ex->q64, Nq, Nqp, epsilon, mask, edge_stats, flist, fcap,
                                           work, counters, st);
   }
@@ -1102,7 +1111,10 @@ struct Impl {
                            double epsilon, uint32_t *mask, uint32_t *edge_stats, const unsigned long long *flist,
                            unsigned long long fcap, unsigned long long *work, unsigned long long *counters, cudaStream_t st) {
     Chain c; fill_chain(h, c);
-    const int threads = 128;
+    // as many lanes per SM as shared memory allows, in one or two CTAs
+    int threads, per_sm_want;
+    lane_geometry(h, 0, 256, threads, per_sm_want);
+    if (threads < 32) { set_error("k_edges_recheck: n=%d does not fit shared memory", h.n); return -2; }
     const size_t smem = (size_t)threads * h.n * (4 + mc(h)) * sizeof(Real);
     cudaMemsetAsync(work, 0, sizeof(unsigned long long), st);
     auto launch = [&](auto kern) -> int {

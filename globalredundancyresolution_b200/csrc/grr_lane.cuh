@@ -26,25 +26,25 @@
 #include "grr_device.cuh"
 
 namespace grr {
-#if defined(GRR_STUDY) && !defined(__CUDA_ARCH__)
-void study_tie(double alam, double Dc, double curv, double tgt, double slope, bool same, double slack, double fold, double pn2, int it);
-#endif
 
 // ---- fast scalar helpers (float: MUFU based; double: exact) ---------------------------------
 #ifdef __CUDA_ARCH__
 GRR_DEV float fdiv_(float a, float b) { return __fdividef(a, b); }
 GRR_DEV float rcp_ge1_(float a) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a)); return r; }  // a >= 1
 GRR_DEV float rsqrt_(float a) { return rsqrtf(a); }
+GRR_DEV float rsqrt_est_(float a) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a)); return r; }  // estimates only
 GRR_DEV int float_bits_(float t) { return __float_as_int(t); }
 #else
 GRR_DEV float fdiv_(float a, float b) { return a / b; }
 GRR_DEV float rcp_ge1_(float a) { return 1.0f / a; }
 GRR_DEV float rsqrt_(float a) { return 1.0f / sqrtf(a); }
+GRR_DEV float rsqrt_est_(float a) { return 1.0f / sqrtf(a); }
 GRR_DEV int float_bits_(float t) { int q; memcpy(&q, &t, 4); return q; }
 #endif
 GRR_DEV double fdiv_(double a, double b) { return a / b; }
 GRR_DEV double rcp_ge1_(double a) { return 1.0 / a; }
 GRR_DEV double rsqrt_(double a) { return 1.0 / sqrt(a); }
+GRR_DEV double rsqrt_est_(double a) { return 1.0 / sqrt(a); }
 
 // sin/cos for joint angles (|x| << 2^22): Cody-Waite reduction to [-pi/4, pi/4] with the
 // round-to-nearest magic constant (no F2I / I2F), cephes minimax polynomials, quadrant fix-up.
@@ -123,12 +123,16 @@ enum : int { PH_SEARCH = 1, PH_SOFT = 2, PH_HARD = 4, PH_INFL = 8,
              // which decision raised PH_HARD (diagnostics; they ride along in the same word at no cost)
              PH_R_CONVX = 1 << 4, PH_R_STPMAX = 1 << 5, PH_R_SLOPE = 1 << 6, PH_R_ALAM = 1 << 7, PH_R_ARMIJO = 1 << 8,
              PH_R_DISC = 1 << 9, PH_R_SOFT2 = 1 << 10, PH_R_SOFTFAIL = 1 << 11, PH_R_MAXIT = 1 << 12, PH_R_LEAF = 1 << 13,
-             PH_R_NDIVS = 1 << 14, PH_R_ALL = 0x7ff0 };
+             PH_R_NDIVS = 1 << 14, PH_R_ALL = 0x7ff0,
+             PH_PEND = 1 << 15 };   // an Armijo near-tie awaits its second derivative sample (see lane_step)
 
 template <typename Real, int M>
 struct LaneIK {
   Real fold, slope, alam, alam2, f2, alamin, stpmax, resid;
   Real amb;      // FLAG builds: after IK_OK, radius within which the double-precision solution may lie (0 = round-off only)
+  Real t_a, t_D, t_ar;   // FLAG builds: first derivative sample of a pending Armijo near-tie (step length, g.p_c, last clear rejection)
+  Real aerr;     // FLAG builds: relative error of the current (interpolated) step length
+  Real rad;      // FLAG builds: running estimate of |x(single) - x(double)| over the iterations of this solve (see lane_step)
   int it, evals, phase;
   // the Newton step is folded into the next chain pass.  `first` = that pass derives the
   // direction p_j = -col_j . y from the Jacobian columns still in memory (ny = -y) and stores it.
@@ -143,7 +147,7 @@ GRR_DEV void lane_reset(LaneIK<Real, M> &L) {
   L.it = 0; L.evals = 0; L.phase = 0; L.first = false; L.check_convx = false; 
 #pragma unroll
   for (int r = 0; r < M; r++) L.ny[r] = 0;
-  L.alam = 0; L.alam2 = 0; L.f2 = 0; L.fold = 0; L.slope = 0; L.alamin = 0; L.stpmax = 0; L.resid = 0; L.amb = 0;
+  L.alam = 0; L.alam2 = 0; L.f2 = 0; L.fold = 0; L.slope = 0; L.alamin = 0; L.stpmax = 0; L.resid = 0; L.amb = 0; L.rad = 0; L.aerr = 0; L.t_a = 0; L.t_D = 0; L.t_ar = 0;
 }
 // Start an instance whose seed is lerp(qa, qb, u) read from (a, b) with strides (sa, sb).
 template <typename Real, int M>
@@ -411,7 +415,7 @@ GRR_DEV void lane_pass(const ChainT &c, const Target<Real, M> &tg, const LaneIK<
 
 // Cholesky solve of the packed SPD matrix A (lower) with reciprocal square roots.
 template <typename Real, int M>
-GRR_DEV void chol_solve_fast(Real (&A)[M * (M + 1) / 2], const Real *b, Real *y) {
+GRR_DEV void chol_solve_fast(Real (&A)[M * (M + 1) / 2], const Real *b, Real *y, Real *inv2sum = nullptr) {
   Real inv[M];
 #pragma unroll
   for (int r = 0; r < M; r++) {
@@ -438,11 +442,17 @@ GRR_DEV void chol_solve_fast(Real (&A)[M * (M + 1) / 2], const Real *b, Real *y)
     for (int k = r + 1; k < M; k++) acc -= A[tri(k, r)] * y[k];
     y[r] = acc * inv[r];
   }
+  if (inv2sum) {          // sum of the squared diagonal of L^-1: a (lower) estimate of trace(A^-1) ~ 1 / lambda_min
+    Real t = 0;
+#pragma unroll
+    for (int r = 0; r < M; r++) t += inv[r] * inv[r];
+    *inv2sum = t;
+  }
 }
 
 // Numerical Recipes lnsrch backtracking: the next trial step length after a rejected trial
 template <bool FLAG, typename Real, int M>
-GRR_DEV void lane_backtrack(LaneIK<Real, M> &L, Real f, Real fl_rel) {
+GRR_DEV void lane_backtrack(LaneIK<Real, M> &L, Real f, Real fl_rel, Real fl_f0 = Real(0)) {
   Real tmplam;
   if (L.alam == Real(1)) tmplam = -L.slope / (Real(2) * (f - L.fold - L.slope));
   else {
@@ -460,33 +470,61 @@ GRR_DEV void lane_backtrack(LaneIK<Real, M> &L, Real f, Real fl_rel) {
     if (tmplam > Real(0.5) * L.alam) tmplam = Real(0.5) * L.alam;
   }
   // min / max clamps are continuous; an interior value carries the cancellation error of f - fold - slope
-  if (FLAG && tmplam > Real(0.1) * L.alam && tmplam < Real(0.5) * L.alam) L.phase |= PH_INFL;
+  if (FLAG) {
+    L.aerr = 0;
+    if (tmplam > Real(0.1) * L.alam && tmplam < Real(0.5) * L.alam) {
+      L.phase |= PH_INFL;
+      // f - fold is known to ~2 |F| fl_f; the step length inherits that relative to the differences it is built from
+      const Real ef = Real(2) * fl_f0;
+      const Real d1 = abs_(f - L.fold - L.alam * L.slope);
+      const Real d2 = (L.alam == Real(1)) ? d1 : abs_(L.f2 - L.fold - L.alam2 * L.slope);
+      L.aerr = ef / max_(min_(d1, d2), Real(1e-30));
+    }
+  }
   L.alam2 = L.alam; L.f2 = f;
   L.alam = max_(tmplam, Real(0.1) * L.alam);
   L.src.t = L.alam;
 }
 
-// Directional derivative of f = |F|^2 / 2 at the current trial point along the line-search direction with the joints
-// that sit on a limit and are pushed outwards taken out (the clamped direction p_c): Dc = g . p_c, g = J^T F from the
-// columns and residual of the pass that has just run.  `same_set` = the joints clamped at the trial point are exactly
-// those clamped at the line-search origin for every step length (origin on the limit, p pointing outwards), i.e. the
-// clamped path origin -> trial point is a straight segment along p_c.  Runs in the transition (few lanes active); it
-// is only called when an Armijo test is a near-tie in single precision.
-template <typename Real, int M, bool PL, typename ChainT>
-GRR_DEV void lane_dirderiv(const ChainT &c, const LaneMem<Real, col_rows(M, PL)> &mem, const PassOut<Real, M> &o, Real &Dc,
-                           bool &same_set) {
-  constexpr int MC = col_rows(M, PL);
-  Real z[MC];
-#pragma unroll
-  for (int r = 0; r < (MC < 3 ? MC : 3); r++) z[r] = o.FL[r];
-  if constexpr (M == 6) {
-    Real D[9];
-    so3_Jl_inv(&o.FL[3], D);
-    m3_Tvec(D, &o.FL[3], &z[3]);
-  }
-  const int n = c.n, T = mem.T;
-  const Real *pp = mem.p(), *xo = mem.xold(), *xt = mem.xcur(), *pc = mem.cols();
-  Real acc = 0;
+// ---- near-ties of the sufficient-decrease test (FLAG builds) -------------------------------------------
+// When f - rhs is below the single-precision noise (late in a backtracking sequence, or a step that barely moves)
+// the test is decided by the first-order model instead, which single precision resolves.  On the clamped segment
+// origin -> trial point, phi(a) = f(clamp(xold + a p)) has phi'(a) = D(a) = g(x(a)) . p_c with p_c = p minus the joints
+// that sit on a limit and are pushed outwards, and the exact test at step a reads b(a) = (phi(a) - fold) / a -
+// ALF slope <= 0.
+//   one sample Dc = D(alam), worst-case curvature bound C |p|^2:  b(a) within D - tgt -+ alam C |p|^2 for every
+//     a <= alam, so a clear sign settles this and every shorter step (rejected for good -> the search ends below
+//     alamin: stalled; or accepted here);
+//   two samples (this trial and the next, shorter one): D is linear in a up to the third-order term, so
+//     b(a) = D0 - tgt + a kappa / 2 is settled on (0, amax] by its two ends; amax covers every step length the
+//     double-precision search can try after its last clear rejection.
+// Anything else flags the pair.  Runs out of line (rare: ~0.3 ties per pair on the headline config) so that the
+// lane machine's loop stays within the instruction cache.
+template <typename Real>
+struct TieIn {
+  Real FLz[6];           // residual in the goal-link frame, rotation rows already multiplied by Jl^-T (see lane_tie)
+  Real trS, pn2, fold, slope, alam, alam2, t_a, t_D, t_ar;
+  int pending;           // a first sample is waiting (PH_PEND)
+  int final_sample;      // the search ends at this trial (alam < alamin): no third chance
+};
+template <typename Real>
+struct TieOut {
+  int code;              // 0 flag the pair, 1 certified: stalled, 2 certified: accept here, 3 first sample stored: treat as rejected
+  Real t_a, t_D, t_ar;
+};
+enum : int { TIE_FLAG = 0, TIE_STALL = 1, TIE_ACCEPT = 2, TIE_PENDING = 3 };
+
+template <typename Real, int MC, typename ChainT>
+#ifdef __CUDA_ARCH__
+__device__ __noinline__
+#else
+inline
+#endif
+TieOut<Real> lane_tie(const ChainT *cp, const Real *base, int T, int o_xold, int o_xcur, TieIn<Real> in) {
+  const ChainT &c = *cp;
+  const int n = c.n;
+  const Real *pp = base + 3 * n * T, *xo = base + o_xold, *xt = base + o_xcur, *pc = base + 4 * n * T;
+  Real Dc = 0;
   bool same = true;
 #pragma unroll 1
   for (int j = 0; j < n; j++) {
@@ -498,11 +536,64 @@ GRR_DEV void lane_dirderiv(const ChainT &c, const LaneMem<Real, col_rows(M, PL)>
     if (!out_old) {
       Real g = 0;
 #pragma unroll
-      for (int r = 0; r < MC; r++) g = fma_(pc[(j * MC + r) * T], z[r], g);
-      acc = fma_(g, pj, acc);
+      for (int r = 0; r < MC; r++) g = fma_(pc[(j * MC + r) * T], in.FLz[r], g);
+      Dc = fma_(g, pj, Dc);
     }
   }
-  Dc = acc; same_set = same;
+  TieOut<Real> out;
+  out.code = TIE_FLAG; out.t_a = in.t_a; out.t_D = in.t_D; out.t_ar = in.t_ar;
+  if (!same) return out;
+  const Real ALF = Real(1e-4);
+  const Real F0 = sqrt_(Real(2) * in.fold), tgt = ALF * in.slope;
+  if (!in.pending) {
+    const Real curv = in.alam * in.pn2 * (in.trS + F0 * c.fl_curv);
+    const Real slack = c.fl_dd * (abs_(Dc) + abs_(in.slope));
+    if (Dc - curv - tgt > slack) out.code = TIE_STALL;
+    else if (Dc + curv - tgt < -slack) out.code = TIE_ACCEPT;
+    else if (!in.final_sample && Dc - tgt > slack) {       // (D <= tgt here: a shorter step cannot be certified as rejected either)
+      out.code = TIE_PENDING; out.t_a = in.alam; out.t_D = Dc; out.t_ar = (in.alam2 > Real(0)) ? in.alam2 : in.alam;
+    }
+    return out;
+  }
+  const Real kappa = (in.t_D - Dc) / (in.t_a - in.alam), D0 = Dc - in.alam * kappa;
+  const Real amax = max_(in.t_a, Real(0.5) * in.t_ar);
+  const Real pn = sqrt_(in.pn2);
+  const Real tau = c.fl_curv * in.pn2 * pn * (Real(3) * sqrt_(in.trS) + F0 * sqrt_(Real(n)) * pn);
+  const Real s3 = c.fl_dd * (abs_(Dc) + abs_(in.t_D) + abs_(in.slope) + abs_(kappa) * amax) + amax * amax * tau;
+  const Real b0 = D0 - tgt, bm = D0 - tgt + Real(0.5) * amax * kappa;
+  if (amax * pn < Real(0.05) && b0 > s3 && bm > s3) out.code = TIE_STALL;
+  return out;
+}
+
+// gathers the operands of lane_tie from the lane's state
+template <typename Real, int M, bool PL, typename ChainT>
+GRR_DEV int lane_tie_call(const ChainT &c, LaneIK<Real, M> &L, const LaneMem<Real, col_rows(M, PL)> &mem, const PassOut<Real, M> &o,
+                          bool final_sample) {
+  constexpr int MC = col_rows(M, PL);
+  TieIn<Real> in;
+#pragma unroll
+  for (int r = 0; r < 6; r++) in.FLz[r] = 0;
+#pragma unroll
+  for (int r = 0; r < (MC < 3 ? MC : 3); r++) in.FLz[r] = o.FL[r];
+  if constexpr (M == 6) {
+    Real D[9];
+    so3_Jl_inv(&o.FL[3], D);
+    m3_Tvec(D, &o.FL[3], &in.FLz[3]);
+  }
+  Real trS = 0;
+  if constexpr (PL) trS = o.S[0] + o.S[2];
+  else {
+#pragma unroll
+    for (int r = 0; r < M; r++) trS += o.S[tri(r, r)];
+  }
+  in.trS = trS; in.pn2 = o.pn2; in.fold = L.fold; in.slope = L.slope; in.alam = L.alam; in.alam2 = L.alam2;
+  in.t_a = L.t_a; in.t_D = L.t_D; in.t_ar = L.t_ar;
+  in.pending = (L.phase & PH_PEND) ? 1 : 0; in.final_sample = final_sample ? 1 : 0;
+  const TieOut<Real> out = lane_tie<Real, MC>(&c, mem.base, mem.T, mem.o_xold, mem.o_xcur, in);
+  L.t_a = out.t_a; L.t_D = out.t_D; L.t_ar = out.t_ar;
+  L.phase &= ~PH_PEND;
+  if (out.code == TIE_PENDING) L.phase |= PH_PEND;
+  return out.code;
 }
 
 // ---- the transition: line-search bookkeeping; no joint loop.  A new Newton iteration only solves the
@@ -577,9 +668,14 @@ GRR_DEV int lane_step(const ChainT &c, LaneIK<Real, M> &L, LaneMem<Real, col_row
     bool conv = o.fmax < tolf;
     auto conv_test = [&]() {
       if (FLAG) {
-        const bool near = abs_(o.fmax - tolf) < ((L.phase & PH_INFL) ? Real(8) * c.fl_f : c.fl_f);
-        if (L.phase & PH_SOFT) { if (near || !conv) L.phase |= PH_HARD | PH_R_SOFT2; }
-        else if (near) { L.phase |= PH_SOFT; conv = false; }
+        // common case first: far from tol and no soft tie pending -> a few instructions.  The margin grows with the
+        // iteration count: the iterates of a long (creeping) solve drift apart by more than one evaluation's round-off.
+        const Real m1 = c.fl_f * fma_(Real(0.125), Real(L.it), Real(1));
+        if (abs_(o.fmax - tolf) < Real(8) * m1 || (L.phase & PH_SOFT)) {
+          const bool near = abs_(o.fmax - tolf) < ((L.phase & PH_INFL) ? Real(8) * m1 : m1);
+          if (L.phase & PH_SOFT) { if (near || !conv) L.phase |= PH_HARD | PH_R_SOFT2; }
+          else if (near) { L.phase |= PH_SOFT; conv = false; }
+        }
       }
     };
     if (!(L.phase & PH_SEARCH)) {
@@ -590,6 +686,10 @@ GRR_DEV int lane_step(const ChainT &c, LaneIK<Real, M> &L, LaneMem<Real, col_row
     } else {
       if (FLAG && abs_(L.alam - L.alamin) < c.fl_alam * L.alamin) L.phase |= PH_HARD | PH_R_ALAM;
       if (L.alam < L.alamin) {
+        // the search ends here; a pending near-tie gets its second derivative sample from this trial point
+        if (FLAG && (L.phase & PH_PEND)) {
+          if (lane_tie_call<Real, M, PL>(c, L, mem, o, true) != TIE_STALL) L.phase |= PH_HARD | PH_R_ARMIJO;
+        }
         L.it++; L.res = mem.xold(); st = IK_STALL;                        // x <- xold
       } else {
         const Real rhs = L.fold + ALF * L.alam * L.slope;
@@ -598,46 +698,47 @@ GRR_DEV int lane_step(const ChainT &c, LaneIK<Real, M> &L, LaneMem<Real, col_row
           // |f - rhs| against the error of f and fold: |F| dF ~ sqrt(fold) fl_f, compared in squares
           const Real df = o.f - rhs, w = (L.phase & PH_INFL) ? Real(64) * c.fl_f2 : c.fl_f2;
           if (df * df < w * L.fold) {
-            // Near-tie: f - fold is below the single-precision noise (typically a small step length late in a
-            // backtracking sequence, or a step that barely moves).  Decide by the first-order model instead, which
-            // single precision resolves: on the clamped segment origin -> trial point, f(a) - fold lies between
-            // a (Dc -+ alam C |p|^2), C >= |p_c^T H p_c| / |p|^2, so if that interval clears ALF slope for every
-            // a <= alam the exact test rejects at this and every shorter step (-> the search ends below alamin:
-            // stalled), and if it lies below, the exact test accepts here.  Otherwise the pair is re-tested.
-            Real Dc; bool same;
-            lane_dirderiv<Real, M, PL>(c, mem, o, Dc, same);
-            Real trS = 0;
-            if constexpr (PL) trS = o.S[0] + o.S[2];
-            else {
-#pragma unroll
-              for (int r = 0; r < M; r++) trS += o.S[tri(r, r)];
-            }
-            const Real curv = L.alam * o.pn2 * (trS + sqrt_(Real(2) * L.fold) * c.fl_curv);
-            const Real tgt = ALF * L.slope, slack = c.fl_dd * (abs_(Dc) + abs_(L.slope));
-            if (same && Dc - curv - tgt > slack) { L.it++; L.res = mem.xold(); st = IK_STALL; }
-            else if (same && Dc + curv - tgt < -slack) accept = true;
+            const int code = lane_tie_call<Real, M, PL>(c, L, mem, o, false);
+            if (code == TIE_STALL) { L.it++; L.res = mem.xold(); st = IK_STALL; }
+            else if (code == TIE_ACCEPT) accept = true;
+            else if (code == TIE_PENDING) accept = false;
             else L.phase |= PH_HARD | PH_R_ARMIJO;
-#if defined(GRR_STUDY) && !defined(__CUDA_ARCH__)
-            study_tie((double)L.alam, (double)Dc, (double)curv, (double)tgt, (double)L.slope, same, (double)slack, (double)L.fold, (double)o.pn2, L.it);
-#endif
           }
         }
         if (st != IK_RUNNING) { }
-        else if (!accept) lane_backtrack<FLAG>(L, o.f, c.fl_rel);
+        else if (!accept) lane_backtrack<FLAG>(L, o.f, c.fl_rel, FLAG ? sqrt_(Real(2) * L.fold) * c.fl_f : Real(0));
         else {
           L.it++;
+          if (FLAG) {
+            // accepted clear of the margin while an earlier near-tie of this search is still open: that tie stays undecided
+            if (L.phase & PH_PEND) { L.phase &= ~PH_PEND; L.phase |= PH_HARD | PH_R_ARMIJO; }
+            // Drift r of the single-precision iterate from the double-precision one over one accepted step (estimate).
+            // A step of amplification A = |step| / |F| (>> 1 near a singular configuration, up to 1 / (2 lambda)) turns
+            // the residual round-off fl_f into A fl_f of joint error, carries an existing difference on with the factor
+            // 1 + A^2 |F| |dJ| (the step depends on where it is taken), and an interpolated step length adds its own
+            // relative error aerr times the step.  (A worst-case bound through |J^+| and |(J J^T + lambda^2)^-1 F| was
+            // tried: it holds in all but ~1e-5 of the solves but is astronomically large for 10-30 % of the solves of
+            // the 6-/7-joint arms; this estimate is exceeded by the measured drift in ~1e-3 of the solves, by <= 30x.)
+            const Real f2x = max_(Real(2) * L.fold, Real(1e-30)), ri = rsqrt_est_(f2x);
+            const Real pn = o.pn2 * rsqrt_est_(max_(o.pn2, Real(1e-30)));
+            const Real A = L.alam * pn * ri;                              // |step| / |F|
+            L.rad = fma_(L.rad, fma_(A * A * (f2x * ri), c.fl_curv1, Real(1)), fma_(L.alam * pn, L.aerr, A * c.fl_f));
+          }
           conv_test();
           if (conv) {
             st = IK_OK;
             // a soft tie one test earlier: the double-precision run may have stopped one step before this point
-            if (FLAG) L.amb = (L.phase & PH_SOFT) ? L.alam * sqrt_(o.pn2) : Real(0);
+            if (FLAG) {
+              L.amb = Real(4) * L.rad;
+              if (L.phase & PH_SOFT) L.amb += L.alam * o.pn2 * rsqrt_est_(max_(o.pn2, Real(1e-30)));
+            }
           } else { newstep = true; check_convx = true; }
         }
       }
     }
   }
-  if (FLAG && st > IK_OK && (L.phase & PH_SOFT)) L.phase |= PH_HARD | PH_R_SOFTFAIL;     // the other outcome of the tie was "succeeded"
-  if (FLAG && L.it > c.fl_maxit) L.phase |= PH_HARD | PH_R_MAXIT;
+  // (a failure after a soft tie -- the other outcome of the tie was "succeeded" -- and a near-tie still pending at the
+  // end of the solve are turned into flags by the caller: pair_note_solve)
   if (newstep) {
     // the accepted point (in xcur) becomes the origin of the next line search: swap roles, no copy
     { const int t = mem.o_xold; mem.o_xold = mem.o_xcur; mem.o_xcur = t; }
@@ -707,6 +808,7 @@ GRR_DEV int lane_step(const ChainT &c, LaneIK<Real, M> &L, LaneMem<Real, col_row
     }
     L.first = true; L.check_convx = check_convx;
     L.fold = o.f; L.alam = 1; L.alam2 = 0; L.f2 = 0; L.alamin = 0;
+    if (FLAG) L.aerr = 0;
     L.src.a = mem.xold(); L.src.b = mem.p(); L.src.sa = mem.T; L.src.sb = mem.T; L.src.t = 1; L.src.lerp = false;
     L.res = mem.xold();
     L.phase |= PH_SEARCH;

@@ -1,0 +1,6 @@
+mkdir -p gpurun_out/r2e
+for cfg in "planar_20R baseline_cfg2.json" "jaco baseline_cfg3.json" "baxter baseline_cfg4.json" "robonaut2 baseline_cfg5.json Nw=30000"; do
+  tag=$(echo $cfg | cut -d' ' -f1)
+  python tools/exact_report.py $cfg scales=8 > gpurun_out/r2e/exact_$tag.jsonl 2> gpurun_out/r2e/exact_$tag.err
+done
+cut -c1-800 gpurun_out/r2e/*.jsonl

@@ -43,16 +43,34 @@ assert (rrp.counts() == c64).all()
 base.update({"t_connect_plain_f32": tcp, "plain_f32_differing": popcount(mp ^ m64)})
 del rrp
 for sc in scales:
+    os.environ["GRR_NO_RECHECK"] = "1"
+    rr, ts, tc_first = run("float32", True, sc)
+    del rr, os.environ["GRR_NO_RECHECK"]
     rr, ts, tc = run("float32", True, sc)
     m = rr._dev["mask"].cpu().numpy()
     x = m ^ m64
     out = dict(base)
-    out.update({"scale": sc, "t_connect_exact": tc, "overhead_vs_plain": tc / tcp - 1.0, "flagged": rr.stats["flagged"],
+    out.update({"scale": sc, "t_connect_exact": tc, "overhead_vs_plain": tc / tcp - 1.0, "t_first_pass": tc_first, "t_recheck": tc - tc_first, "flagged": rr.stats["flagged"],
                 "flagged_frac": rr.stats["flagged"] / max(rr.stats["pairs"], 1), "flipped": rr.stats["flipped"],
                 "differing_vs_f64": popcount(x), "valid_exact": rr.stats["valid"],
                 "edge_stats_ok": bool((rr._dev["edge_stats"][:, 1].cpu().numpy().astype(np.int64).sum()) == popcount(m))})
     if out["differing_vs_f64"]:
         e, a, w = np.nonzero(x)
         out["differing_examples"] = [[int(e[k]), int(a[k]), int(w[k]), int(x[e[k], a[k], w[k]])] for k in range(min(len(e), 8))]
+        # dump the differing pairs (double-precision configs + workspace parameters) for the host trace (tools/flag_study.py)
+        res = rr.resolution
+        Qs = rr._dev["Qs"]
+        qa, qb, wa, wb, ids = [], [], [], [], []
+        for k in range(min(len(e), 64)):
+            word = int(x[e[k], a[k], w[k]]) & 0xffffffff
+            for bit in range(32):
+                if (word >> bit) & 1:
+                    b = int(w[k]) * 32 + bit
+                    iw, jw = res.ws_edges[e[k]]
+                    qa.append(Qs[iw, :, a[k]].double().cpu().numpy()); qb.append(Qs[jw, :, b].double().cpu().numpy())
+                    wa.append(res.ws_params[iw]); wb.append(res.ws_params[jw]); ids.append((int(e[k]), int(a[k]), b, int((m[e[k], a[k], w[k]] >> bit) & 1)))
+        os.makedirs(os.path.join(ROOT, "gpurun_out", "differing"), exist_ok=True)
+        np.savez(os.path.join(ROOT, "gpurun_out", "differing", "%s_%s_scale%g.npz" % (name, jf.replace(".json", ""), sc)),
+                 qa=np.asarray(qa), qb=np.asarray(qb), wa=np.asarray(wa), wb=np.asarray(wb), ids=np.asarray(ids))
     print(json.dumps(out), flush=True)
     del rr

@@ -58,6 +58,17 @@ def run_pairs(L, desc, qa, qb, wa, wb, precision, scale=8.0, fl=None, eps=5e-2):
     return valid.astype(bool), info
 
 
+def trace_pair(L, desc, qa, qb, wa, wb, precision, scale=8.0, cap=128, eps=5e-2):
+    tr = np.zeros((cap, 42)); info = np.zeros(8, dtype=np.int32)
+    dp = C.POINTER(C.c_double)
+    f = lambda x: np.ascontiguousarray(x, dtype=np.float64)
+    qa, qb, wa, wb = f(qa), f(qb), f(wa), f(wb)
+    v = L.lane_host_trace(C.byref(desc), C.c_double(scale), qa.ctypes.data_as(dp), qb.ctypes.data_as(dp), wa.ctypes.data_as(dp),
+                          wb.ctypes.data_as(dp), C.c_double(eps), C.c_int(precision), tr.ctypes.data_as(dp), C.c_int(cap),
+                          info.ctypes.data_as(C.c_void_p))
+    return v, info, tr[:info[2]]
+
+
 def patch_pairs(res, o, Nq, seed, n_edges, rng):
     """Random workspace edges -> their endpoint nodes sampled by the oracle -> all config pairs."""
     E = res.ws_edges.shape[0]
@@ -82,7 +93,7 @@ def main():
     import globalredundancyresolution_b200 as grr
     from helpers import oracle_for
     name, jf = sys.argv[1], sys.argv[2]
-    pos = [a for a in sys.argv[3:] if "=" not in a or a.split("=")[0] in ("n_edges", "scale", "seed", "check_oracle")]
+    pos = [a for a in sys.argv[3:] if "=" not in a or a.split("=")[0] in ("n_edges", "scale", "seed", "check_oracle", "dump")]
     kv = dict(a.split("=") for a in pos if "=" in a)
     n_edges = int(kv.get("n_edges", 300)); scale = float(kv.get("scale", 8)); seed = int(kv.get("seed", 0))
     over = grr.problems.parse_overrides([a for a in sys.argv[3:] if a not in pos])
@@ -132,6 +143,9 @@ def main():
     out["mismatch_examples"] = [{"v32": bool(v32[t]), "info32": i32[t].tolist(), "info64": i64[t].tolist()} for t in np.nonzero(mism)[0][:40]]
     bad = np.nonzero(mism & ~flagged)[0][:10]
     out["unflagged_examples"] = [{"i": int(t), "v32": bool(v32[t]), "info32": i32[t].tolist(), "info64": i64[t].tolist()} for t in bad]
+    if "dump" in kv:
+        t = np.nonzero(mism & ~flagged)[0]
+        np.savez(kv["dump"], qa=qa[t], qb=qb[t], wa=wa[t], wb=wb[t], v32=v32[t], v64=v64[t])
     print(json.dumps(out))
 
 

@@ -7,30 +7,14 @@
 // the flag rates measured here are estimates of the device's, confirmed on the GPU by tests/test_gpu_exact.py.
 //
 // build: nvcc -O2 -std=c++17 --expt-relaxed-constexpr -Xcompiler -fPIC,-fopenmp -shared -o tools/_build/liblane_host.so tools/lane_host.cu
-#define GRR_STUDY 1
 #include "../globalredundancyresolution_b200/csrc/grr_kernels.cuh"
 #include <omp.h>
 
-#include <atomic>
 namespace grr {
 void set_error(const char *, ...) {}
-// near-tie statistics of the Armijo certificate (host study build only)
-static std::atomic<long long> g_tie[16];
-static FILE *g_tie_log = nullptr;
-void study_tie(double alam, double Dc, double curv, double tgt, double slope, bool same, double slack, double fold, double pn2, int it) {
-  g_tie[0]++;
-  if (!same) g_tie[1]++;
-  else if (Dc - curv - tgt > slack) g_tie[2]++;
-  else if (Dc + curv - tgt < -slack) g_tie[3]++;
-  else if (Dc - tgt > slack || Dc - tgt < -slack) g_tie[4]++;   // the curvature bound is what blocks it
-  else g_tie[5]++;                                              // first-order model undecided
-  if (g_tie_log && (g_tie[0] % 97) == 0)
-    fprintf(g_tie_log, "%d %d %.3e %.3e %.3e %.3e %.3e %.3e %.3e %.3e\n", (int)same, it, alam, Dc, curv, tgt, slope, slack, fold, pn2);
-}
-
 template <typename Real, int M, bool PL, bool FLAG>
 static void run_pair(const ChainDev<Real, kMaxJ> &c, const Real *qa, const Real *qb, const Real *wa, const Real *wb,
-                     Real epsilon, uint8_t *valid, int32_t *info) {
+                     Real epsilon, uint8_t *valid, int32_t *info, double *trace = nullptr, int trace_cap = 0) {
   constexpr int MC = col_rows(M, PL);
   Real buf[lane_reals<MC>(kMaxJ)];
   const int n = c.n;
@@ -64,7 +48,14 @@ static void run_pair(const ChainDev<Real, kMaxJ> &c, const Real *qa, const Real 
     if (st != IK_RUNNING) {
       P.solves++; P.iters += L.it;
       if (L.it > maxit) maxit = L.it;
-      if (FLAG) pair_note_solve(P, L);
+      if (trace && P.solves <= trace_cap) {
+        // per solve: k, status, iterations, evals, residual, phase bits, leaf s2, target (3), solution (n)
+        double *tr = trace + (size_t)(P.solves - 1) * (10 + kMaxJ);
+        tr[0] = P.k; tr[1] = st; tr[2] = L.it; tr[3] = (double)L.amb; tr[4] = (double)L.resid; tr[5] = L.phase; tr[6] = (double)o.s2;
+        tr[7] = (double)tg.x[0]; tr[8] = (double)tg.x[1]; tr[9] = (double)tg.x[2];
+        for (int j = 0; j < n; j++) tr[10 + j] = (double)L.res[j];
+      }
+      if (FLAG) pair_note_solve(P, L, st);
       if (st != IK_OK) { verdict = 0; fail = 1; fstat = st; fit = L.it; fres = (double)L.resid; }
       else {
         verdict = pair_advance<FLAG>(c, mem, o.s2, thr2, P, L);
@@ -127,10 +118,37 @@ extern "C" int lane_host_pairs(const grr_chain_desc *d, const double *fl, double
   return 0;
 }
 
-extern "C" void lane_host_tie_stats(long long *out, const char *logfile) {
-  for (int k = 0; k < 16; k++) { out[k] = g_tie[k]; g_tie[k] = 0; }
-  if (g_tie_log) { fclose(g_tie_log); g_tie_log = nullptr; }
-  if (logfile) g_tie_log = fopen(logfile, "w");
+// one pair with a per-solve trace [cap][10 + 32] (see run_pair); precision as in lane_host_pairs
+extern "C" int lane_host_trace(const grr_chain_desc *d, double scale, const double *qa, const double *qb, const double *wa,
+                               const double *wb, double epsilon, int precision, double *trace, int cap, int32_t *info) {
+  HostChain h;
+  memset(&h, 0, sizeof h);
+  h.n = d->n; h.mode = d->mode; h.nlinks_eps = d->nlinks_eps; h.max_iters = d->max_iters; h.device = 0;
+  h.tol = d->tol; h.lambda = d->lambda;
+  memcpy(h.Rp, d->Rp, sizeof(double) * 9 * d->n); memcpy(h.tp, d->tp, sizeof(double) * 3 * d->n);
+  memcpy(h.axis, d->axis, sizeof(double) * 3 * d->n); memcpy(h.qmin, d->qmin, sizeof(double) * d->n);
+  memcpy(h.qmax, d->qmax, sizeof(double) * d->n); memcpy(h.ee_local, d->ee_local, sizeof h.ee_local);
+  memcpy(h.R_tail, d->R_tail, sizeof h.R_tail); memcpy(h.R_goal, d->R_goal, sizeof h.R_goal);
+  flag_margins(h, scale);
+  const bool m6 = h.mode != GRR_FREE, pl = !m6 && is_planar_y(h);
+  const int n = h.n, dw = (h.mode == 2 ? 6 : 3);
+  uint8_t v = 0;
+  auto go = [&](auto real, auto Mtag, auto PLtag, auto FLtag) {
+    using Real = decltype(real);
+    constexpr int M = decltype(Mtag)::value; constexpr bool PL = decltype(PLtag)::value; constexpr bool FL = decltype(FLtag)::value;
+    ChainDev<Real, kMaxJ> *c = new ChainDev<Real, kMaxJ>;
+    fill_chain(h, *c);
+    Real a[kMaxJ], b[kMaxJ], w0[6], w1[6];
+    for (int j = 0; j < n; j++) { a[j] = (Real)qa[j]; b[j] = (Real)qb[j]; }
+    for (int k = 0; k < dw; k++) { w0[k] = (Real)wa[k]; w1[k] = (Real)wb[k]; }
+    run_pair<Real, M, PL, FL>(*c, a, b, w0, w1, (Real)epsilon, &v, info, trace, cap);
+    delete c;
+  };
+  using T = std::true_type; using F = std::false_type;
+  using I3 = std::integral_constant<int, 3>; using I6 = std::integral_constant<int, 6>;
+  if (precision == 0) { if (m6) go(0.f, I6{}, F{}, T{}); else if (pl) go(0.f, I3{}, T{}, T{}); else go(0.f, I3{}, F{}, T{}); }
+  else { if (m6) go(0.0, I6{}, F{}, F{}); else if (pl) go(0.0, I3{}, T{}, F{}); else go(0.0, I3{}, F{}, F{}); }
+  return v;
 }
 
 extern "C" void lane_host_margins(const grr_chain_desc *d, double scale, double *fl_out) {
