@@ -119,6 +119,13 @@ def workload_name(pdef, Nw, E):
         pdef.get("orientation", "free"))
 
 
+def config_dict(pdef, Nw, E, n_gpus):
+    """The `config` object of the JSON line: identical in the CUDA arm and in the reference arm."""
+    return {"workload": workload_name(pdef, Nw, E), "seed": 0,
+            "l2": "256 MiB flush write between steps, inside the timed region (CUDA arm)",
+            "parallelism": "1 GPU" if n_gpus <= 1 else "workspace nodes sharded over %d ranks + NCCL halo exchange" % n_gpus}
+
+
 # --------------------------------------------------------------------------------------------------
 # reference arm: the CPU oracle port on a bounded sample, all host threads
 # --------------------------------------------------------------------------------------------------
@@ -152,7 +159,7 @@ def python_loop_estimate(grr, o_unused=None, budget_s=2.0):
     boundary several times per interpolated IK point.  Returns validEdge calls per second."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     from helpers import oracle_for
-    pdef, res = grr.load_problem("planar_3R", "baseline_cfg1.json")
+    pdef, res = grr.load_problem("planar_3R", "baseline_cfg1.json", lazy_chain=True)
     res.sampleWorkspace(pdef["Nw"], method=pdef["workspace_graph"])
     o = oracle_for(res)
     mid = res.ws_params.shape[0] // 2
@@ -185,9 +192,13 @@ def run_reference(args):
     from helpers import oracle_for
     from oracle import oracle as O
     grr, name, jf, over, pdef = problem_setup(args, max(1, args.gpus))
-    pdef2, res = grr.load_problem(name, jf, overrides=over)
+    # lazy_chain: the problem is described without creating a library handle, so this arm never maps libgrr_b200.so
+    pdef2, res = grr.load_problem(name, jf, overrides=over, lazy_chain=True)
     res.sampleWorkspace(pdef["Nw"], method=pdef["workspace_graph"])
     o = oracle_for(res)
+    # all host threads, whatever OMP_NUM_THREADS says (torchrun sets it to 1 for every rank)
+    cores = args.cpu_threads or os.cpu_count() or 1
+    O.set_num_threads(cores)
     cores = O.num_threads()
     rng = np.random.default_rng(0)
     n_edges = cpu_calibrate(res, o, pdef["Nq"], args.cpu_seconds, rng)      # ~cpu_seconds of CPU work per step
@@ -207,12 +218,96 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * wall / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_name(pdef, res.ws_params.shape[0], res.ws_edges.shape[0]), "seed": 0},
+            "config": config_dict(pdef, res.ws_params.shape[0], res.ws_edges.shape[0], args.gpus),
             "ik_configs_per_s": tot_attempts / max(t_s, 1e-12),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
                              "note": "CPU oracle (oracle/grr_oracle.c, OpenMP); the reference itself is Python 2 + Klamp't/IKDB and cannot run here"},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
+
+
+def popcount32(a):
+    return int(np.unpackbits(np.ascontiguousarray(a).view(np.uint8)).sum())
+
+
+def sub_records(args, grr, torch, _cabi, name, jf, over, pdef, res, rr, local, peak_tf):
+    """Untimed-by-the-headline extras on one GPU, each measured with CUDA events of its own:
+    parity        the product roadmap (single-precision pass + double-precision recheck) against the float64 build of the
+                  same kernels over the WHOLE roadmap, and against the CPU oracle on a random sample of workspace edges
+    seeded_sweep  the reference's default sampleConfigurationSpace call (seedFromAdjacent=True, sequential sweep as
+                  wavefronts) on the same workload
+    jaco          BASELINE config 3 (Jaco-like 6R, free orientation, Nw=20000, Nq=50): IK configs/s, edges tested/s, roofline
+    roofline_ik   the sampling kernel (k_ik_instances) of the headline workload"""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from helpers import oracle_for, reference_configs, unpack_mask
+    from oracle import oracle as O
+    out = {}
+    Nq = pdef["Nq"]
+    n, m = res.chain.n, (3 if res.chain.mode == 0 else 6)
+    # -- sampling-kernel roofline (headline workload, last timed step's counters)
+    st = rr.stats
+    ik_flops = flops_model(n, m, st["sample_ik_iters"], st["sample_ik_evals"], 0, 0)
+    out["roofline_ik"] = {"kernel": "k_ik_instances<%s>" % rr.sample_dtype, "bound": "fp32_simt" if rr.sample_dtype == "float32" else "fp64",
+                          "achieved": ik_flops / max(st["t_sample"], 1e-12) / 1e12, "unit": "TFLOP/s", "peak": peak_tf,
+                          "frac": ik_flops / max(st["t_sample"], 1e-12) / 1e12 / peak_tf, "launch_s": st["t_sample"],
+                          "flops_per_launch": ik_flops, "ik_attempts": st["attempts"], "ik_iters": st["sample_ik_iters"],
+                          "note": "sampling runs in double precision (kept joint values equal the reference arithmetic to 1e-12); the fraction "
+                                  "is taken against the FP32 FMA peak, i.e. it is a lower bound of the kernel's own (FP64) roofline fraction; "
+                                  "t_sample includes the dedup kernel"}
+    # -- parity over the whole roadmap
+    m_prod = rr._dev["mask"].cpu().numpy()
+    cnt = rr.counts()
+    pd64, res64 = grr.load_problem(name, jf, overrides=over, device=local, dtype="float64")
+    res64.sampleWorkspace(pd64["Nw"], method=pd64["workspace_graph"])
+    rr64 = grr.RedundancyResolver(res64, seed=0)
+    ts64, tc64 = rr64.sampleConfigurationSpace(Nq, order_independent=True)
+    m64 = rr64._dev["mask"].cpu().numpy()
+    mism = popcount32(m_prod ^ m64) if (rr64.counts() == cnt).all() else -1
+    rng = np.random.default_rng(7)
+    e = res.ws_edges
+    cand = np.nonzero(cnt[e[:, 0]].astype(np.int64) * cnt[e[:, 1]] > 0)[0]
+    pick = np.sort(rng.choice(cand, size=min(args.parity_edges, cand.size), replace=False))
+    o = oracle_for(res)
+    O.set_num_threads(args.cpu_threads or os.cpu_count() or 1)
+    Q = reference_configs(rr, Nq)
+    t0 = time.perf_counter()
+    mask_ref, stats = o.connect_edges(e[pick], res.ws_params, Q, cnt, Nq)
+    t_or = time.perf_counter() - t0
+    mdev = unpack_mask(m_prod[pick], Nq)
+    out["parity"] = {"pairs_checked": int(st["pairs"]), "mismatches": int(mism), "in_band": 0,
+                     "against": "float64 build of the same kernels over the whole roadmap (its masks equal the CPU oracle's on every test problem)",
+                     "float64_build_connect_s": tc64,
+                     "oracle_sample": {"workspace_edges": int(pick.size), "pairs": int(stats[:, 0].sum()),
+                                       "mismatches": int((mdev != mask_ref.astype(bool)).sum()), "oracle_seconds": round(t_or, 2)},
+                     "rechecked_frac": st.get("flagged", 0) / max(st["pairs"], 1), "verdicts_changed_by_recheck": st.get("flipped", 0)}
+    del rr64, res64, m64
+    # -- the reference's default call: seeded sweep
+    rr.initWorkspaceGraph()
+    rr.sampleConfigurationSpace(Nq)                       # warm (builds the level schedule)
+    rr.initWorkspaceGraph()
+    ts, tc = rr.sampleConfigurationSpace(Nq)
+    s2 = rr.stats
+    out["seeded_sweep"] = {"call": "sampleConfigurationSpace(Nq) with the reference's defaults (seedFromAdjacent=True)",
+                           "t_sample_s": ts, "t_connect_s": tc, "pairs": s2["pairs"], "configs": s2["sampled"], "ik_attempts": s2["attempts"],
+                           "pairs_per_s": s2["pairs"] / max(ts + tc, 1e-12), "ik_configs_per_s": s2["attempts"] / max(ts, 1e-12)}
+    # -- BASELINE config 3
+    pj, resj, rrj = grr.make_program("jaco", "baseline_cfg3.json", device=local, seed=0)
+    for _ in range(2):
+        rrj.initWorkspaceGraph()
+        tsj, tcj = rrj.sampleConfigurationSpace(pj["Nq"], order_independent=True)
+    sj = rrj.stats
+    nj, mj = resj.chain.n, (3 if resj.chain.mode == 0 else 6)
+    fj = flops_model(nj, mj, sj["edge_ik_iters"], sj["edge_ik_evals"], sj["pairs"], sj["edge_ik_solves"] + sj["pairs"])
+    rrj.exact_edges = False
+    rrj.initWorkspaceGraph()
+    _, tcj_plain = rrj.sampleConfigurationSpace(pj["Nq"], order_independent=True)
+    out["jaco"] = {"workload": workload_name(pj, rrj.Nw, rrj.E), "ik_configs_per_s": sj["attempts"] / max(tsj, 1e-12),
+                   "edges_tested_per_s": sj["pairs"] / max(tcj, 1e-12), "pairs": sj["pairs"], "t_sample_s": tsj, "t_connect_s": tcj,
+                   "t_connect_single_precision_only_s": tcj_plain, "rechecked_frac": sj.get("flagged", 0) / max(sj["pairs"], 1),
+                   "roofline": {"bound": "fp32_simt", "kernel": "k_edges_flat", "achieved": fj / max(tcj, 1e-12) / 1e12, "peak": peak_tf,
+                                "unit": "TFLOP/s", "frac": fj / max(tcj, 1e-12) / 1e12 / peak_tf,
+                                "note": "single-precision work model over the whole exact build (first pass + double-precision recheck time)"}}
+    return out
 
 
 # --------------------------------------------------------------------------------------------------
@@ -360,6 +455,7 @@ def run_cuda(args):
         from oracle import oracle as O
         o = oracle_for(res)
         rng = np.random.default_rng(0)
+        O.set_num_threads(args.cpu_threads or os.cpu_count() or 1)
         n_edges = cpu_calibrate(res, o, Nq, args.cpu_seconds, rng)
         r = cpu_sample_run(res, o, Nq, 0, n_edges, rng)
         nthreads = O.num_threads()
@@ -377,13 +473,16 @@ def run_cuda(args):
                                    "(planar_3R, Nq=10), 1 thread -- the real reference is slower still (several "
                                    "Python<->C++ crossings per interpolated IK point)"}
 
+    # ---- sub-records (1 GPU): parity of the product path, the reference's default (seeded) call, BASELINE config 3 (Jaco) ---
+    extras = {}
+    if world == 1 and not args.no_extras:
+        extras = sub_records(args, grr, torch, _cabi, name, jf, over, pdef, res, rr, local, peak_tf)
+
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong" if args.strong else "weak",
             "vs_baseline": None,
-            "dtype": "f32 (edge phase) / f64 (sampling)", "data": "synthetic",
-            "config": {"workload": workload_name(pdef, res.ws_params.shape[0], res.ws_edges.shape[0]), "seed": 0,
-                       "l2": "256 MiB flush write between steps, inside the timed region",
-                       "parallelism": "1 GPU" if world == 1 else "workspace nodes sharded over %d ranks + NCCL halo exchange" % world},
+            "dtype": "f32 + f64 recheck of near-ties (edge phase) / f64 (sampling)", "data": "synthetic",
+            "config": config_dict(pdef, res.ws_params.shape[0], res.ws_edges.shape[0], world),
             "ik_configs_per_s": tot["attempts"] / (ts_ms * 1e-3), "edges_tested_per_s_edge_phase_only": tot["pairs"] / (tc_ms * 1e-3),
             "pairs_per_step": tot["pairs"] / args.steps, "valid_fraction": tot["valid"] / max(tot["pairs"], 1.0),
             "ik_solves_per_step": tot["ik_solves"] / args.steps, "ik_iters_per_step": tot["ik_iters"] / args.steps,
@@ -391,6 +490,11 @@ def run_cuda(args):
             "connect_ms_per_rank": [round(float(v), 2) for v in rank_ms.cpu()],
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
             "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "cpu_baseline": cpu}
+    line.update(extras)
+    st0 = rr.stats
+    line["exact_edges"] = {"enabled": bool(getattr(rr, "exact_edges", False)), "rechecked_pairs": st0.get("flagged"),
+                           "rechecked_frac": (st0.get("flagged") or 0) / max(st0["pairs"], 1), "verdicts_changed": st0.get("flipped"),
+                           "note": "single-precision pass lists near-tie pairs; those are decided again in double precision (grr_edges_build_exact)"}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -407,6 +511,9 @@ def main():
     ap.add_argument("--nq", type=int, default=0)
     ap.add_argument("--cpu-seconds", type=float, default=30.0, help="CPU work per reference step / cpu_baseline sample")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--cpu-threads", type=int, default=0, help="host threads of the CPU arms (default: all, ignoring OMP_NUM_THREADS)")
+    ap.add_argument("--parity-edges", type=int, default=60, help="workspace edges of the oracle sample in the parity sub-record")
+    ap.add_argument("--no-extras", action="store_true", help="skip the parity / seeded-sweep / Jaco sub-records (profiling runs)")
     ap.add_argument("--strong", action="store_true", help="keep the problem size fixed at N > 1 (default: weak scaling, Nw x N)")
     ap.add_argument("--e2e-rebuild", action="store_true", help="rebuild the problem objects inside the e2e region")
     args = ap.parse_args()

@@ -133,43 +133,58 @@ def round_up4(nq):
 class ChainHandle:
     """Opaque (device, chain) handle: grr_chain_create / grr_chain_destroy."""
 
-    def __init__(self, chain_arrays, mode, R_goal=None, nlinks_eps=None, tol=1e-3, max_iters=50, lam=0.01, device=0):
+    def __init__(self, chain_arrays, mode, R_goal=None, nlinks_eps=None, tol=1e-3, max_iters=50, lam=0.01, device=0, lazy=False):
         """chain_arrays: dict with Rp [n,9], tp [n,3], axis [n,3], qmin [n], qmax [n], ee_local [3], R_tail [9]
         (numpy float64; produced by robot.RobotChain.fold())."""
-        L = lib()
         self.n = int(chain_arrays["qmin"].shape[0])
+        if not (1 <= self.n <= MAX_JOINTS):
+            raise GrrError("grr_chain_create: n=%d outside 1..%d" % (self.n, MAX_JOINTS))
         self.mode = int(mode)
         self.device = int(device)
         self._keep = {k: np.ascontiguousarray(np.asarray(chain_arrays[k], dtype=np.float64))
                       for k in ("Rp", "tp", "axis", "qmin", "qmax", "ee_local", "R_tail")}
-        d = ChainDesc()
-        d.n = self.n
-        d.mode = self.mode
-        d.nlinks_eps = int(nlinks_eps if nlinks_eps is not None else self.n)
-        d.max_iters = int(max_iters)
-        d.tol = float(tol)
-        d.lambda_ = float(lam)
-        dp = C.POINTER(C.c_double)
-        for k in ("Rp", "tp", "axis", "qmin", "qmax"):
-            setattr(d, k, self._keep[k].ctypes.data_as(dp))
-        d.ee_local[:] = list(self._keep["ee_local"].reshape(3))
-        d.R_tail[:] = list(self._keep["R_tail"].reshape(9))
-        rg = np.eye(3).reshape(9) if R_goal is None else np.asarray(R_goal, dtype=np.float64).reshape(9)
-        d.R_goal[:] = list(rg)
-        self.nlinks_eps = d.nlinks_eps
-        self.tol, self.max_iters, self.lam = d.tol, d.max_iters, d.lambda_
-        h = C.c_void_p()
-        check(L.grr_chain_create(C.byref(d), self.device, C.byref(h)), "grr_chain_create")
-        self._h = h
+        self.nlinks_eps = int(nlinks_eps if nlinks_eps is not None else self.n)
+        self.tol, self.max_iters, self.lam = float(tol), int(max_iters), float(lam)
+        self._R_goal = np.eye(3).reshape(9) if R_goal is None else np.asarray(R_goal, dtype=np.float64).reshape(9).copy()
+        self._flag_scale = None
+        self._handle = None
+        if not lazy:
+            self._h            # create (and validate) now
+
+    @property
+    def _h(self):
+        """The library handle, created on first use (describing a chain does not need the library: the CPU reference
+        arm of bench.py builds problems without ever mapping libgrr_b200.so)."""
+        if self._handle is None:
+            L = lib()
+            d = ChainDesc()
+            d.n = self.n
+            d.mode = self.mode
+            d.nlinks_eps = self.nlinks_eps
+            d.max_iters = self.max_iters
+            d.tol = self.tol
+            d.lambda_ = self.lam
+            dp = C.POINTER(C.c_double)
+            for k in ("Rp", "tp", "axis", "qmin", "qmax"):
+                setattr(d, k, self._keep[k].ctypes.data_as(dp))
+            d.ee_local[:] = list(self._keep["ee_local"].reshape(3))
+            d.R_tail[:] = list(self._keep["R_tail"].reshape(9))
+            d.R_goal[:] = list(self._R_goal)
+            h = C.c_void_p()
+            check(L.grr_chain_create(C.byref(d), self.device, C.byref(h)), "grr_chain_create")
+            self._handle = h
+            if self._flag_scale is not None:
+                check(L.grr_set_flag_scale(h, float(self._flag_scale)), "grr_set_flag_scale")
+        return self._handle
 
     @property
     def dw(self):
         return 6 if self.mode == GRR_VARIABLE else 3
 
     def close(self):
-        if getattr(self, "_h", None):
-            lib().grr_chain_destroy(self._h)
-            self._h = None
+        if getattr(self, "_handle", None):
+            lib().grr_chain_destroy(self._handle)
+            self._handle = None
 
     def __del__(self):
         try:
@@ -182,8 +197,11 @@ class ChainHandle:
         if R_goal is not None:
             arr = (C.c_double * 9)(*[float(v) for v in np.asarray(R_goal).reshape(9)])
             rg = C.cast(arr, C.POINTER(C.c_double))
-        check(lib().grr_task_set(self._h, int(mode), rg), "grr_task_set")
         self.mode = int(mode)
+        if R_goal is not None:
+            self._R_goal = np.asarray(R_goal, dtype=np.float64).reshape(9).copy()
+        if self._handle is not None:
+            check(lib().grr_task_set(self._handle, int(mode), rg), "grr_task_set")
 
     # ---- thin wrappers: torch tensors in, status checked --------------------------------------
     def fk_batch(self, q, out_p, out_R=None):
@@ -250,7 +268,9 @@ class ChainHandle:
                                           _ptr(edge_stats), _ptr(counters), _stream(q32.device)), "grr_edges_build_exact")
 
     def set_flag_scale(self, scale):
-        check(lib().grr_set_flag_scale(self._h, float(scale)), "grr_set_flag_scale")
+        self._flag_scale = float(scale)
+        if self._handle is not None:
+            check(lib().grr_set_flag_scale(self._handle, float(scale)), "grr_set_flag_scale")
 
     def edges_cost(self, wedges, q_kept, count, epsilon, cost, old_count=None):
         E = wedges.shape[0]

@@ -16,6 +16,7 @@ class _Writer:
     def __init__(self):
         self.out = io.BytesIO()
         self.memo = {}
+        self._set_global = None
 
     def w(self, b):
         self.out.write(b)
@@ -53,7 +54,39 @@ class _Writer:
             raw = obj.encode("latin1")
             self.w((b"U" + bytes([len(raw)]) if len(raw) < 256 else b"T" + struct.pack("<i", len(raw))) + raw)
             self.put(obj)
-        elif isinstance(obj, (list, tuple)):
+        elif isinstance(obj, tuple):
+            # Python-2 protocol 2: EMPTY_TUPLE / TUPLE1..3 / MARK .. TUPLE (the (iq, jq) members of an edge qlist)
+            if len(obj) == 0:
+                self.w(b")")
+            elif len(obj) <= 3:
+                for v in obj:
+                    self.save(v)
+                self.w((b"\x85", b"\x86", b"\x87")[len(obj) - 1])
+            else:
+                self.w(b"(")
+                for v in obj:
+                    self.save(v)
+                self.w(b"t")
+        elif isinstance(obj, (set, frozenset)):
+            # `set` under Python 2: GLOBAL __builtin__.set applied to a one-tuple holding the member list
+            # (Gw.edge[i][j]['qlist'] of Gw_cached.pickle, grr/solver.py:270,458)
+            if self._set_global is None:
+                self._set_global = object()
+                self.w(b"c__builtin__\nset\n")
+                self.put(self._set_global)
+            else:
+                self.get(self._set_global)
+            members = sorted(obj)
+            self.w(b"]")
+            self.put(members)
+            if members:
+                self.w(b"(")
+                for v in members:
+                    self.save(v)
+                self.w(b"e")
+            self.w(b"\x85R")
+            self.put(obj)
+        elif isinstance(obj, list):
             if id(obj) in self.memo:
                 return self.get(obj)
             self.w(b"]")
@@ -103,6 +136,8 @@ class _Unpickler(pickle.Unpickler):
     def find_class(self, module, name):
         if module.startswith("networkx"):
             return _GraphStub
+        if module in ("__builtin__", "builtins") and name in ("set", "frozenset"):
+            return set
         raise pickle.UnpicklingError("unexpected class %s.%s in a graph pickle" % (module, name))
 
 

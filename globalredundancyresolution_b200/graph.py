@@ -77,7 +77,7 @@ class RedundancyResolutionGraph:
     """See module docstring.  `world_or_robot` is a robot.RobotChain (or any object with a `.robot(0)`
     method returning one, mirroring graph.py:494-500)."""
 
-    def __init__(self, world_or_robot, device=0, dtype="float32"):
+    def __init__(self, world_or_robot, device=0, dtype="float32", lazy_chain=False):
         if isinstance(world_or_robot, RobotChain):
             self.world = None
             self.robot = world_or_robot
@@ -94,6 +94,7 @@ class RedundancyResolutionGraph:
         self.wRadius = None
         self.resolvedCount = 0
         self.device = int(device)
+        self.lazy_chain = bool(lazy_chain)     # describe the chain without touching libgrr_b200.so until a kernel is needed
         self.dtype_name = dtype
         self.chain = None            # _cabi.ChainHandle, created by readJsonSetup
         self.fold = None             # folded chain arrays (robot.RobotChain.fold)
@@ -190,7 +191,8 @@ class RedundancyResolutionGraph:
             R_goal = so3.matrix(task.orientationparams).reshape(9)
         p = self.ikSolverParams
         self.chain = _cabi.ChainHandle(self.fold, _MODE[task.orientation], R_goal=R_goal, nlinks_eps=nlinks,
-                                       tol=p.tol, max_iters=p.numIters, lam=p.damping, device=self.device)
+                                       tol=p.tol, max_iters=p.numIters, lam=p.damping, device=self.device,
+                                       lazy=self.lazy_chain)
         self.q_ref = np.asarray(self.robot.getConfig(), dtype=np.float64)
         self.active_idx = np.asarray(self.fold["active"], dtype=np.int64)
 

@@ -71,11 +71,11 @@ def load_robot(filename, search_dirs=()):
 
 
 def load_problem(problem, jsonfile="Rfree.json", overrides=None, device=0, dtype="float32", ignore_collision=False,
-                 problem_dir=None):
+                 problem_dir=None, lazy_chain=False):
     """Returns (pdef, resolution) with the IK problem set up; the workspace graph is not sampled yet."""
     pdef = read_options(problem, jsonfile, overrides, problem_dir)
     robot = load_robot(pdef["filename"])
-    resolution = RedundancyResolutionGraph(robot, device=device, dtype=dtype)
+    resolution = RedundancyResolutionGraph(robot, device=device, dtype=dtype, lazy_chain=lazy_chain)
     resolution.readJsonSetup(pdef, ignore_collision=ignore_collision)
     return pdef, resolution
 
@@ -95,4 +95,5 @@ def make_program(problem, jsonfile="Rfree.json", overrides=None, device=0, dtype
     else:
         resolution.sampleWorkspace(pdef["Nw"], method=pdef["workspace_graph"])
     rr = RedundancyResolver(resolution, cache=pdef.get("cache", 20000), seed=seed)
+    rr.settings = pdef                                 # written as settings.json by rr.save (redundancy.py:147-150)
     return pdef, resolution, rr

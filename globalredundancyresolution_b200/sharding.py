@@ -174,14 +174,15 @@ class ShardedResolver(RedundancyResolver):
     0.56 GB in FP32) but fills only its node window, and holds the bitmasks of its own edge range
     chunks (`edge_ids`: global ids of the local mask rows).  `gather_masks()` assembles the full roadmap."""
 
-    def __init__(self, resolution, rank, world, seed=0, sample_dtype="float64", rebalance=True, chunks_per_rank=8):
+    def __init__(self, resolution, rank, world, seed=0, sample_dtype="float64", rebalance=True, chunks_per_rank=8,
+                 exact_edges=True):
         self.rank, self.world = int(rank), int(world)
         self._local_of = {}
         self.rebalance = bool(rebalance)
         self.chunks_per_rank = int(chunks_per_rank)
         self.edge_ids = np.zeros(0, dtype=np.int64)
         self.halo_bytes = 0
-        RedundancyResolver.__init__(self, resolution, seed=seed, sample_dtype=sample_dtype)
+        RedundancyResolver.__init__(self, resolution, seed=seed, sample_dtype=sample_dtype, exact_edges=exact_edges)
         self.nbounds = node_ranges(self.Nw, self.world * self.chunks_per_rank)
 
     def initWorkspaceGraph(self, clear=False, drop_device=False):
@@ -268,13 +269,10 @@ class ShardedResolver(RedundancyResolver):
             W = (self.Nq + 31) // 32
             d["mask"] = torch.zeros((ne, self.Nq, W), dtype=torch.int32, device=res.torch_device)
             d["edge_stats"] = torch.zeros((ne, 2), dtype=torch.int32, device=res.torch_device)
-            if d["Qs"] is not d["Q"]:
-                for (wl, wh) in windows[self.rank]:
-                    d["Q"][wl:wh].copy_(d["Qs"][wl:wh])
             if ne:
                 my_wedges = torch.cat([d["wedges"][a:b] for (a, b) in mine if b > a]).contiguous()
-                res.chain.edges_build(my_wedges, d["params"], d["Q"], d["count"], self.Nq,
-                                      0.05, d["mask"], d["edge_stats"], d["counters_e"])
+                # (rounds the kept configs to the edge precision, then the exact build or the plain kernels)
+                self._edges_launch(d, my_wedges, d["mask"], d["edge_stats"], None)
         ev[2].record()
         torch.cuda.synchronize(res.torch_device)
         self._invalidate()

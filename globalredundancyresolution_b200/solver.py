@@ -314,18 +314,25 @@ class RedundancyResolver:
     def numCSpaceEdges(self):
         if self._dev is None or self.Nq == 0:
             return 0
+        return int(self._bits_per_edge().sum().item())
+
+    def _bits_per_edge(self):
+        """Valid bits per workspace edge (int64 [E]): SWAR popcount on the 32-bit mask words, in place-sized temporaries
+        (a look-up-table gather over mask.long() needs 8x the mask's memory: 3.7 GB -> 30 GB on config 5)."""
         torch = self.resolution._torch()
-        m = self._dev["mask"].view(torch.uint8)
-        lut = torch.tensor([bin(v).count("1") for v in range(256)], dtype=torch.int64, device=m.device)
-        return int(lut[m.long()].sum().item())
+        x = self._dev["mask"].reshape(self.E, -1)
+        x = x - ((x >> 1) & 0x55555555)
+        x = (x & 0x33333333) + ((x >> 2) & 0x33333333)
+        x = (x + (x >> 4)) & 0x0F0F0F0F
+        x = (x * 0x01010101) >> 24
+        return (x & 0xFF).sum(dim=1, dtype=torch.int64)
 
     def edge_lists(self):
         """All C-space edges as (offsets [E+1], pairs [total,2]) materialised by the compaction kernel."""
         torch = self.resolution._torch()
         d = self._dev
-        m8 = d["mask"].view(torch.uint8)
-        lut = torch.tensor([bin(v).count("1") for v in range(256)], dtype=torch.int64, device=m8.device)
-        per_edge = lut[m8.long()].reshape(self.E, -1).sum(dim=1)
+        per_edge = self._bits_per_edge()
+        m8 = d["mask"]
         offsets = torch.zeros(self.E + 1, dtype=torch.int64, device=m8.device)
         offsets[1:] = torch.cumsum(per_edge, 0)
         total = int(offsets[-1].item())
@@ -675,11 +682,22 @@ class RedundancyResolver:
         return nondeg, self.E, 0, e0.elapsed_time(e1) * 1e-3
 
     # ---- checkpoint / resume (solver.py:274-348) ------------------------------------------------------
-    def save(self, folder):
-        """Checkpoint: the reference's resolution_graph.pickle (through resolution.save) plus the device roadmap as
-        roadmap_b200.npz (kept configs in sampling precision, counts, edge bitmasks, attempt counter).  The
-        reference's own Gw_cached.pickle is a shelve-backed CGraph and is not written."""
+    GW_PICKLE_MAX_EDGES = 5_000_000     # C-space edges above which save() skips Gw_cached.pickle unless asked to
+
+    def save(self, folder, close=False, gw_cached="auto"):
+        """solver.py:274-291.  Writes, like the reference with cache=0:
+          resolution_graph.pickle  (through resolution.save; networkx-1.x gpickle)
+          Gw_cached.pickle         nx.write_gpickle of the roadmap: Gw.node[i] = {'params', 'qlist': [full configs]},
+                                   Gw.edge[i][j] = {'qlist': set((iq, jq))} -- the format the reference's load() and GUI
+                                   read.  gw_cached='auto' writes it when the roadmap has at most GW_PICKLE_MAX_EDGES
+                                   C-space edges (config 2 has 9.8e7: a multi-GB pickle of Python tuples), True forces it
+          Qsubgraph_cached.txt     (when a resolution has been decoded)
+          settings.json            the problem options (redundancy.py:147-150), when `self.settings` is set (make_program)
+        plus roadmap_b200.npz, the device roadmap as arrays (kept configs in sampling precision, counts, edge bitmasks,
+        attempt counter), from which load() resumes without re-parsing Python containers."""
+        import json
         import os
+        from ._nx1pickle import dumps_graph
         self.resolution.save(folder)
         d = self._dev
         out = {"Nq": self.Nq, "attempts": self.attempts, "seed": self.seed, "edges": self.resolution.ws_edges,
@@ -687,31 +705,77 @@ class RedundancyResolver:
         if d is not None and self.Nq > 0:
             out.update({"Qs": d["Qs"].cpu().numpy(), "count": d["count"].cpu().numpy(), "mask": d["mask"].cpu().numpy()})
         np.savez_compressed(os.path.join(folder, "roadmap_b200.npz"), **out)
+        n_edges = self.numCSpaceEdges()
+        if gw_cached is True or (gw_cached == "auto" and n_edges <= self.GW_PICKLE_MAX_EDGES):
+            node, adj = self._gw_containers()
+            with open(os.path.join(folder, "Gw_cached.pickle"), "wb") as f:
+                f.write(dumps_graph(node, adj, {}))
         if len(self.Qsubgraph) > 0:                              # solver.py:281-285, same text format
             with open(os.path.join(folder, "Qsubgraph_cached.txt"), "w") as f:
                 for k, v in sorted(self.Qsubgraph.items()):
                     f.write(str(k) + " " + str(v) + "\n")
+        if getattr(self, "settings", None) is not None:          # redundancy.py:147-150
+            with open(os.path.join(folder, "settings.json"), "w") as f:
+                json.dump({k: v for k, v in self.settings.items() if not k.startswith("_")}, f)
+
+    def _gw_containers(self):
+        """The roadmap as the reference's containers: ({i: {'params', 'qlist'}}, {i: {j: {'qlist': set}}}) with the edge
+        dict shared by both directions (networkx-1.x adjacency)."""
+        cnt = self.counts()
+        node = {}
+        Qh = None
+        if self._dev is not None and self.Nq > 0:
+            Qh = self._dev["Qs"].double().cpu().numpy()
+        for i in range(self.Nw):
+            ql = []
+            if Qh is not None and cnt[i] > 0:
+                ql = [[float(v) for v in row] for row in self.resolution.to_full(Qh[i, :, :cnt[i]].T)]
+            node[i] = {"params": [float(v) for v in self.resolution.ws_params[i]], "qlist": ql}
+        adj = {i: {} for i in range(self.Nw)}
+        lists = {}
+        if Qh is not None:
+            offsets, pairs = self.edge_lists()
+            offsets, pairs = offsets.cpu().numpy(), pairs.cpu().numpy()
+            for e in range(self.E):
+                lists[e] = set(map(tuple, pairs[offsets[e]:offsets[e + 1]].tolist()))
+        for e, (i, j) in enumerate(self._edges_host):
+            ed = {"qlist": lists.get(e, set())}
+            adj[i][j] = ed
+            adj[j][i] = ed
+        return node, adj
 
     def load(self, folder):
-        """Resume from save(): the roadmap goes back to the device; a following sampleConfigurationSpace call grows
-        it incrementally (only pairs with a new endpoint are tested, solver.py:759,850)."""
+        """solver.py:293-348.  Resumes from save(): roadmap_b200.npz if present, else the reference's own
+        Gw_cached.pickle (cache=0 format, written by the reference or by save()); then resolution_graph.pickle and
+        Qsubgraph_cached.txt.  A following sampleConfigurationSpace call grows the roadmap incrementally (only pairs
+        with a new endpoint are tested, solver.py:759,850)."""
         import os
         torch = self.resolution._torch()
-        z = np.load(os.path.join(folder, "roadmap_b200.npz"))
-        assert z["edges"].shape == self.resolution.ws_edges.shape and (z["edges"] == self.resolution.ws_edges).all(), \
-            "checkpoint belongs to a different workspace graph"
-        self.initWorkspaceGraph()
-        self.seed, self.attempts = int(z["seed"]), int(z["attempts"])
-        Nq = int(z["Nq"])
-        if Nq > 0:
-            d = self._ensure_device(Nq)
-            dev = self.resolution.torch_device
-            d["Qs"].copy_(torch.as_tensor(z["Qs"], device=dev))
-            d["count"].copy_(torch.as_tensor(z["count"], device=dev))
-            d["mask"].copy_(torch.as_tensor(z["mask"], device=dev))
-            if d["Qs"] is not d["Q"]:
-                d["Q"].copy_(d["Qs"])
-            self.attempts = int(z["attempts"])
+        npz = os.path.join(folder, "roadmap_b200.npz")
+        gwp = os.path.join(folder, "Gw_cached.pickle")
+        if os.path.exists(npz):
+            z = np.load(npz)
+            assert z["edges"].shape == self.resolution.ws_edges.shape and (z["edges"] == self.resolution.ws_edges).all(), \
+                "checkpoint belongs to a different workspace graph"
+            self.initWorkspaceGraph()
+            self.seed, self.attempts = int(z["seed"]), int(z["attempts"])
+            Nq = int(z["Nq"])
+            if Nq > 0:
+                d = self._ensure_device(Nq)
+                dev = self.resolution.torch_device
+                d["Qs"].copy_(torch.as_tensor(z["Qs"], device=dev))
+                d["count"].copy_(torch.as_tensor(z["count"], device=dev))
+                d["mask"].copy_(torch.as_tensor(z["mask"], device=dev))
+                if d["Qs"] is not d["Q"]:
+                    d["Q"].copy_(d["Qs"])
+                self.attempts = int(z["attempts"])
+        elif os.path.exists(gwp):
+            self._load_gw_pickle(gwp)
+        else:
+            # solver.py:299-308: no cached roadmap -> import the resolution itself as a one-config-per-node roadmap
+            self.resolution.load(folder)
+            self.fromResolutionToGraph(clear=True)
+            return
         self.Qsubgraph = dict()
         fn = os.path.join(folder, "Qsubgraph_cached.txt")
         if os.path.exists(fn):                                   # solver.py:305-313
@@ -720,6 +784,39 @@ class RedundancyResolver:
                     k, v = line.split()
                     self.Qsubgraph[int(k)] = int(v)
         self.sanityCheck()
+
+    def _load_gw_pickle(self, path):
+        """Device roadmap from a Gw_cached.pickle (networkx-1.x gpickle, node 'qlist' = configs, edge 'qlist' = (iq, jq)
+        sets or lists -- "some old versions have qlist as a set?", solver.py:310-313)."""
+        from ._nx1pickle import loads_graph
+        torch = self.resolution._torch()
+        res = self.resolution
+        with open(path, "rb") as f:
+            node, adj, _ = loads_graph(f.read())
+        assert len(node) == self.Nw, "Gw_cached.pickle belongs to a different workspace graph"
+        self.initWorkspaceGraph()
+        counts = np.asarray([len(node[i].get("qlist", [])) for i in range(self.Nw)], dtype=np.int32)
+        Nq = int(counts.max()) if self.Nw else 0
+        if Nq == 0:
+            return
+        d = self._ensure_device(Nq)
+        n = res.chain.n
+        Qh = np.zeros((self.Nw, n, d["Qs"].shape[2]), dtype=np.float64)
+        for i in range(self.Nw):
+            if counts[i]:
+                Qh[i, :, :counts[i]] = res.to_chain(np.asarray(node[i]["qlist"], dtype=np.float64)).T
+        W = (Nq + 31) // 32
+        M = np.zeros((self.E, Nq, W), dtype=np.uint32)
+        for e, (i, j) in enumerate(self._edges_host):
+            for (a, b) in adj[i][j].get("qlist", ()):
+                M[e, a, b >> 5] |= np.uint32(1 << (b & 31))
+        dev = res.torch_device
+        d["Qs"].copy_(torch.as_tensor(Qh, device=dev).to(d["Qs"].dtype))
+        d["count"].copy_(torch.as_tensor(counts, device=dev))
+        d["mask"].copy_(torch.as_tensor(M.view(np.int32), device=dev))
+        if d["Qs"] is not d["Q"]:
+            d["Q"].copy_(d["Qs"])
+        self.attempts = Nq
 
     # ---- consumer seam: the CSP of the resolution stage (solver.py:984-1022) ---------------------------
     def makeCSP(self, visibility=False):

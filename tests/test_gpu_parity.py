@@ -454,3 +454,38 @@ def test_checkpoint_resume_equals_uninterrupted(built, tmp_path):
     assert torch.equal(a._dev["count"], b._dev["count"]) and torch.equal(a._dev["Qs"], b._dev["Qs"])
     assert torch.equal(a._dev["mask"], b._dev["mask"])
     assert (tmp_path / "resolution_graph.pickle").exists()
+
+
+def test_gw_cached_pickle_and_settings_roundtrip(built, tmp_path):
+    """save() writes the reference's own files (solver.py:274-291, redundancy.py:147-150): Gw_cached.pickle in the
+    cache=0 format (nx.write_gpickle: node 'qlist' = configs, edge 'qlist' = set of (iq, jq)), settings.json; load()
+    rebuilds the device roadmap from Gw_cached.pickle alone when roadmap_b200.npz is absent (a roadmap written by the
+    reference), and falls back to the resolution when neither exists (solver.py:299-308)."""
+    import json
+    import os
+    from globalredundancyresolution_b200._nx1pickle import loads_graph
+    pdef, res, a = grr.make_program("planar_3R", "baseline_cfg1.json", overrides={"Nw": 100, "workspace_graph": "grid"}, seed=SEED)
+    a.sampleConfigurationSpace(6, order_independent=True)
+    a.solveCSP(numInitialGuesses=2)
+    a.save(str(tmp_path))
+    for fn in ("Gw_cached.pickle", "resolution_graph.pickle", "roadmap_b200.npz", "settings.json", "Qsubgraph_cached.txt"):
+        assert (tmp_path / fn).exists(), fn
+    assert json.load(open(tmp_path / "settings.json"))["Nq"] == pdef["Nq"]
+    node, adj, _ = loads_graph(open(tmp_path / "Gw_cached.pickle", "rb").read())
+    cnt = a.counts()
+    assert [len(node[i]["qlist"]) for i in range(a.Nw)] == cnt.tolist()
+    i, j = a._edges_host[int(np.argmax(a._dev["edge_stats"][:, 1].cpu().numpy()))]
+    assert adj[i][j]["qlist"] == a.Gw.edge[i][j]["qlist"] and adj[i][j] is adj[j][i] and len(adj[i][j]["qlist"]) > 0
+    assert len(node[i]["qlist"][0]) == res.robot.numLinks()
+    # the reference's file alone
+    os.remove(tmp_path / "roadmap_b200.npz")
+    pdef2, res2, b = grr.make_program("planar_3R", "baseline_cfg1.json", overrides={"Nw": 100, "workspace_graph": "grid"}, seed=SEED)
+    b.load(str(tmp_path))
+    assert torch.equal(a._dev["count"], b._dev["count"]) and torch.equal(a._dev["mask"], b._dev["mask"])
+    assert torch.allclose(a._dev["Qs"], b._dev["Qs"], atol=0, rtol=0)
+    assert b.Qsubgraph == a.Qsubgraph
+    # neither file: the resolution becomes a one-config-per-node roadmap
+    os.remove(tmp_path / "Gw_cached.pickle")
+    pdef3, res3, c = grr.make_program("planar_3R", "baseline_cfg1.json", overrides={"Nw": 100, "workspace_graph": "grid"}, seed=SEED)
+    c.load(str(tmp_path))
+    assert c.numConfigurations() == len(a.Qsubgraph) and set(c.Qsubgraph) == set(a.Qsubgraph)

@@ -141,3 +141,40 @@ def test_resolution_graph_pickle_matches_reference_layout(tmp_path):
     np.testing.assert_array_equal(res2.ws_edges, res.ws_edges)
     with pytest.raises(Exception):
         _nx1pickle.loads_graph(b"\x80\x02cos\nsystem\nq\x00U\x04trueq\x01\x85q\x02Rq\x03.")   # no arbitrary classes
+
+
+def test_nx1pickle_sets_and_tuples_roundtrip():
+    """Gw_cached.pickle (solver.py:274-279, cache=0): node qlists are lists of configs, edge qlists Python-2 `set`s of
+    (iq, jq) tuples shared by both directions of the adjacency."""
+    from globalredundancyresolution_b200._nx1pickle import dumps_graph, loads_graph
+    ed = {"qlist": {(0, 1), (2, 3), (300, 70000)}}
+    node = {0: {"params": [1.0, 2.0, 3.0], "qlist": [[0.1, 0.2], [0.3, 0.4]]}, 1: {"params": [0.0, 0.0, 1.0], "qlist": []}}
+    adj = {0: {1: ed}, 1: {0: ed}}
+    data = dumps_graph(node, adj)
+    assert b"c__builtin__\nset\n" in data                       # what Python 2's pickler writes for a set
+    n2, a2, g2 = loads_graph(data)
+    assert n2 == node and a2[0][1]["qlist"] == ed["qlist"] and a2[0][1] is a2[1][0]
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/output/atlas/Rfree_W4000/resolution_graph.pickle"),
+                    reason="the reference checkout is not present (GPU box)")
+def test_loader_reads_the_references_own_pickle(tmp_path):
+    """The reference's only shipped artefact goes through the product loader (graph.py:648-670): 3900 nodes, 19,774
+    workspace edges, resolved configs of 46 DOF (ATLAS), and a save() of it is read back identically."""
+    import shutil
+    import globalredundancyresolution_b200 as grr
+    from globalredundancyresolution_b200._nx1pickle import loads_graph
+    src = "/root/reference/output/atlas/Rfree_W4000/resolution_graph.pickle"
+    node, adj, graph = loads_graph(open(src, "rb").read())
+    assert len(node) == 3900 and sum(len(v) for v in adj.values()) // 2 == 19774
+    shutil.copy(src, tmp_path / "resolution_graph.pickle")
+    res = grr.RedundancyResolutionGraph(grr.planar_robot(3))
+    res.load(str(tmp_path))
+    assert res.Gw.number_of_nodes() == 3900 and res.ws_edges.shape == (19774, 2)
+    resolved = [i for i, d in res.Gw.nodes_iter(data=True) if d.get("config") is not None]
+    assert res.resolvedCount == len(resolved) > 0 and len(res.Gw.node[resolved[0]]["config"]) == 46
+    out = tmp_path / "again"
+    res.save(str(out))
+    node2, adj2, _ = loads_graph(open(out / "resolution_graph.pickle", "rb").read())
+    assert node2 == node and {k: set(v) for k, v in adj2.items()} == {k: set(v) for k, v in adj.items()}
+    assert all(adj2[i][j] == adj[i][j] for i in adj for j in adj[i])
