@@ -226,6 +226,50 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def strong_cfg5(grr, torch, dist, sharding, rank, world, local, dev, steps=2):
+    """BASELINE config 5 (Robonaut2-like arm, fixed orientation, Nw=100000 -> 99,536 nodes / 533,113 workspace edges,
+    Nq=200) at its specified size on `world` GPUs: the strong-scaling point of north_star ("sharded over 8 x B200 with
+    halo exchange").  One warm-up build, then `steps` timed builds (barrier + synchronize on both sides, max over
+    ranks).  The 1-GPU run of the same record is the denominator of the speed-up."""
+    pd, res5 = grr.load_problem("robonaut2", "baseline_cfg5.json", device=local)
+    res5.sampleWorkspace(pd["Nw"], method=pd["workspace_graph"])
+    rr5 = sharding.ShardedResolver(res5, rank, world, seed=0) if world > 1 else grr.RedundancyResolver(res5, seed=0)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    rr5.sampleConfigurationSpace(pd["Nq"], order_independent=True)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    pairs = tc = ts = 0.0
+    e0.record()
+    for _ in range(steps):
+        rr5.initWorkspaceGraph()
+        a, b = rr5.sampleConfigurationSpace(pd["Nq"], order_independent=True)
+        ts += a; tc += b
+        pairs += rr5.stats["pairs"]
+    e1.record()
+    barrier()
+    v = torch.tensor([e0.elapsed_time(e1), tc * 1e3, ts * 1e3], dtype=torch.float64, device=dev)
+    vmin = v.clone()
+    p = torch.tensor([pairs, float(rr5.stats.get("flagged", 0) or 0)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(v, op=dist.ReduceOp.MAX)
+        dist.all_reduce(vmin, op=dist.ReduceOp.MIN)
+        dist.all_reduce(p)
+    ms, tcm, tsm = [float(x) / steps for x in v.cpu()]
+    out = {"workload": workload_name(pd, rr5.Nw, rr5.E), "scaling": "strong", "n_gpus": world, "steps": steps, "ms_per_step": ms,
+           "pairs_per_step": float(p[0].item()) / steps, "pairs_per_s": float(p[0].item()) / steps / (ms * 1e-3),
+           "connect_ms_max_rank": tcm, "connect_ms_min_rank": float(vmin[1].item()) / steps, "sample_ms_max_rank": tsm,
+           "exchange": getattr(rr5, "exchange", None), "bytes_received_rank0": int(getattr(rr5, "halo_bytes", 0)),
+           "rechecked_frac_last_step": float(p[1].item()) / max(float(p[0].item()) / steps, 1.0)}
+    del rr5, res5
+    torch.cuda.empty_cache()
+    return out
+
+
 def popcount32(a):
     return int(np.unpackbits(np.ascontiguousarray(a).view(np.uint8)).sum())
 
@@ -409,6 +453,11 @@ def run_cuda(args):
         dist.all_reduce(e2e_p, op=dist.ReduceOp.SUM)
     e2e_value = float(e2e_p.item()) / float(e2e_s.item())
 
+    # ---- BASELINE config 5 as specified (fixed problem size at every N: strong scaling), all ranks --------------
+    strong5 = None
+    if not args.no_extras and not args.strong and args.problem == "planar_20R/baseline_cfg2.json":
+        strong5 = strong_cfg5(grr, torch, dist, sharding, rank, world, local, dev)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -491,6 +540,8 @@ def run_cuda(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
             "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "cpu_baseline": cpu}
     line.update(extras)
+    if strong5 is not None:
+        line["strong_cfg5"] = strong5
     st0 = rr.stats
     line["exact_edges"] = {"enabled": bool(getattr(rr, "exact_edges", False)), "rechecked_pairs": st0.get("flagged"),
                            "rechecked_frac": (st0.get("flagged") or 0) / max(st0["pairs"], 1), "verdicts_changed": st0.get("flipped"),

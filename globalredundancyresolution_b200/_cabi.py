@@ -27,7 +27,7 @@ EXPORTS = [
     "grr_last_error", "grr_abi_version", "grr_chain_create", "grr_chain_destroy", "grr_task_set",
     "grr_chain_num_joints", "grr_fk_batch", "grr_ik_solve_batch", "grr_ik_sample", "grr_ik_sample_level", "grr_dedup", "grr_dedup_sweep",
     "grr_edges_build", "grr_edges_build_exact", "grr_set_flag_scale", "grr_edges_cost", "grr_edges_compact", "grr_valid_edge_batch", "grr_gather_node_blocks",
-    "grr_scatter_node_blocks", "grr_csp_random_assignment", "grr_csp_conflicts", "grr_csp_descent_sweep",
+    "grr_scatter_node_blocks", "grr_halo_exchange", "grr_csp_random_assignment", "grr_csp_conflicts", "grr_csp_descent_sweep",
     "grr_fp32_peak", "grr_fp32x2_peak",
 ]
 
@@ -83,6 +83,7 @@ def lib():
     L.grr_valid_edge_batch.argtypes = [vp, C.c_int, i64, vp, vp, vp, vp, dbl, vp, vp, vp, vp]
     L.grr_gather_node_blocks.argtypes = [C.c_int, i64, vp, i32, i32, vp, vp, vp, vp, vp]
     L.grr_scatter_node_blocks.argtypes = [C.c_int, i64, vp, i32, i32, vp, vp, vp, vp, vp]
+    L.grr_halo_exchange.argtypes = [vp, vp, C.c_int, i32, i32, vp, vp, vp, vp, vp, vp, vp]
     L.grr_csp_random_assignment.argtypes = [i32, i32, vp, u64, i32, vp, vp]
     L.grr_csp_conflicts.argtypes = [i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     L.grr_csp_descent_sweep.argtypes = [i32, vp, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
@@ -271,6 +272,19 @@ class ChainHandle:
         self._flag_scale = float(scale)
         if self._handle is not None:
             check(lib().grr_set_flag_scale(self._handle, float(scale)), "grr_set_flag_scale")
+
+    def halo_exchange(self, nccl_comm, slabs, q, count=None):
+        """grr_halo_exchange: slabs = [(peer, is_send, node_lo, node_hi), ...]; nccl_comm = the caller's ncclComm_t as an
+        integer / c_void_p (hosts without PyTorch; the torch path of sharding.exchange_halo does the same through
+        torch.distributed)."""
+        k = len(slabs)
+        peer = (C.c_int32 * k)(*[int(s[0]) for s in slabs])
+        snd = (C.c_int32 * k)(*[1 if s[1] else 0 for s in slabs])
+        lo = (C.c_int64 * k)(*[int(s[2]) for s in slabs])
+        hi = (C.c_int64 * k)(*[int(s[3]) for s in slabs])
+        check(lib().grr_halo_exchange(self._h, C.c_void_p(int(nccl_comm) if not isinstance(nccl_comm, C.c_void_p) else nccl_comm.value),
+                                      dtype_code(q.dtype), q.shape[2], k, peer, snd, lo, hi, _ptr(q), _ptr(count), _stream(q.device)),
+              "grr_halo_exchange")
 
     def edges_cost(self, wedges, q_kept, count, epsilon, cost, old_count=None):
         E = wedges.shape[0]

@@ -4,6 +4,8 @@
 #include <stdarg.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <dlfcn.h>
+#include <nccl.h>
 #include <new>
 #include "grr_device.cuh"
 #include "grr_host.h"
@@ -580,6 +582,71 @@ int grr_scatter_node_blocks(int dtype, int64_t K, const int32_t *idx, int32_t n,
     k_node_blocks<double, false><<<(unsigned)K, 128, 0, st>>>(K, idx, n * Nqp, (double *)q, count, (double *)packed, (int32_t *)packed_count);
   else { set_error("bad dtype %d", dtype); return -1; }
   return launch_ok("k_node_blocks<scatter>");
+}
+
+// ------------------------------------------------------------------------------------------
+// halo exchange over NCCL for hosts without PyTorch: the library resolves
+// ncclGroupStart / ncclSend / ncclRecv / ncclGroupEnd from the libnccl.so.2 the process already
+// uses (dlopen by soname), so it has no link-time dependency on NCCL.
+// ------------------------------------------------------------------------------------------
+namespace {
+struct NcclApi {
+  ncclResult_t (*GroupStart)();
+  ncclResult_t (*GroupEnd)();
+  ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
+  ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
+  const char *(*GetErrorString)(ncclResult_t);
+  bool ok;
+};
+const NcclApi *nccl_api() {
+  static NcclApi api = {nullptr, nullptr, nullptr, nullptr, nullptr, false};
+  static bool tried = false;
+  if (tried) return api.ok ? &api : nullptr;
+  tried = true;
+  const char *path = getenv("GRR_NCCL_LIB");
+  void *lib = dlopen(path ? path : "libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!lib) { set_error("grr_halo_exchange: cannot load %s: %s", path ? path : "libnccl.so.2", dlerror()); return nullptr; }
+  api.GroupStart = (ncclResult_t(*)())dlsym(lib, "ncclGroupStart");
+  api.GroupEnd = (ncclResult_t(*)())dlsym(lib, "ncclGroupEnd");
+  api.Send = (ncclResult_t(*)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t))dlsym(lib, "ncclSend");
+  api.Recv = (ncclResult_t(*)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t))dlsym(lib, "ncclRecv");
+  api.GetErrorString = (const char *(*)(ncclResult_t))dlsym(lib, "ncclGetErrorString");
+  api.ok = api.GroupStart && api.GroupEnd && api.Send && api.Recv;
+  if (!api.ok) { set_error("grr_halo_exchange: libnccl lacks ncclSend / ncclRecv (NCCL >= 2.7 needed)"); return nullptr; }
+  return &api;
+}
+}  // namespace
+
+extern "C" int grr_halo_exchange(grr_handle_t h, void *nccl_comm, int dtype, int32_t Nqp, int32_t n_slabs, const int32_t *peer,
+                                 const int32_t *is_send, const int64_t *node_lo, const int64_t *node_hi, void *q, int32_t *count,
+                                 void *stream) {
+  GRR_CHECK_HANDLE(h);
+  if (n_slabs < 0 || Nqp < 1) { set_error("grr_halo_exchange: bad sizes"); return -1; }
+  if (n_slabs == 0) return 0;
+  if (!nccl_comm || !peer || !is_send || !node_lo || !node_hi || !q) { set_error("grr_halo_exchange: null argument"); return -1; }
+  if (dtype != GRR_F32 && dtype != GRR_F64) { set_error("bad dtype %d", dtype); return -1; }
+  for (int k = 0; k < n_slabs; k++)
+    if (node_lo[k] < 0 || node_hi[k] < node_lo[k] || peer[k] < 0) { set_error("grr_halo_exchange: bad slab %d", k); return -1; }
+  const NcclApi *api = nccl_api();
+  if (!api) return -4;
+  const size_t blk = (size_t)h->hc.n * (size_t)Nqp, esz = dtype == GRR_F64 ? 8 : 4;
+  const ncclDataType_t ty = dtype == GRR_F64 ? ncclFloat64 : ncclFloat32;
+  ncclComm_t comm = (ncclComm_t)nccl_comm;
+  cudaStream_t st = (cudaStream_t)stream;
+  ncclResult_t rc = api->GroupStart();
+  for (int k = 0; k < n_slabs && rc == ncclSuccess; k++) {
+    const size_t nn = (size_t)(node_hi[k] - node_lo[k]);
+    if (nn == 0) continue;
+    char *qp = (char *)q + (size_t)node_lo[k] * blk * esz;
+    rc = is_send[k] ? api->Send(qp, nn * blk, ty, peer[k], comm, st) : api->Recv(qp, nn * blk, ty, peer[k], comm, st);
+    if (rc == ncclSuccess && count)
+      rc = is_send[k] ? api->Send(count + node_lo[k], nn, ncclInt32, peer[k], comm, st)
+                      : api->Recv(count + node_lo[k], nn, ncclInt32, peer[k], comm, st);
+  }
+  const ncclResult_t rc2 = api->GroupEnd();
+  if (rc == ncclSuccess) rc = rc2;
+  if (rc != ncclSuccess) { set_error("grr_halo_exchange: NCCL error %d (%s)", (int)rc, api->GetErrorString ? api->GetErrorString(rc) : "?"); return -4; }
+  return 0;
 }
 
 static int fp32_peak_impl(int device, double *tflops_out, bool packed);

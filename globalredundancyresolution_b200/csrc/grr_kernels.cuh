@@ -292,6 +292,38 @@ GRR_DEV int pair_advance(const ChainT &c, LaneMem<Real, MC> &mem, Real s2, Real 
   return -1;
 }
 
+// Serves the near-tie requests of a warp's lanes (lane_tie_operands): for each requesting lane the whole warp computes
+// the directional derivative Dc = sum over the free joints of (col_j . z) p_j and the `same` test, one joint per lane,
+// reading the requester's shared-memory column.  All 32 lanes must call.
+template <typename Real, int M, bool PL, typename ChainT>
+__device__ __forceinline__ void warp_tie_service(const ChainT &c, LaneIK<Real, M> &L, const LaneMem<Real, col_rows(M, PL)> &mem,
+                                                 bool running) {
+#ifdef __CUDA_ARCH__
+  constexpr int MC = col_rows(M, PL);
+  unsigned tq = __ballot_sync(0xffffffffu, running && (L.phase & PH_TIEQ));
+  const int lane = threadIdx.x & 31;
+  while (tq) {
+    const int src = __ffs(tq) - 1;
+    tq &= tq - 1;
+    Real z[MC];
+#pragma unroll
+    for (int r = 0; r < MC; r++) z[r] = __shfl_sync(0xffffffffu, L.ny[r], src);
+    const int oxo = __shfl_sync(0xffffffffu, mem.o_xold, src), oxc = __shfl_sync(0xffffffffu, mem.o_xcur, src);
+    const Real *base = mem.base + (src - lane);            // lanes of a warp are adjacent columns of the [element][lane] layout
+    Real part = 0;
+    bool same = true;
+    for (int j = lane; j < c.n; j += 32) tie_joint<Real, MC>(c, base, mem.T, oxo, oxc, z, j, part, same);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    const bool all_same = __all_sync(0xffffffffu, same);
+    if (lane == src) {
+      L.t_Dc = part;
+      L.phase = (L.phase & ~(PH_TIEQ | PH_TSAME)) | PH_TIER | (all_same ? PH_TSAME : 0);
+    }
+  }
+#endif
+}
+
 // Near-tie list of the exact edge build: word 0 = entries appended (may exceed the capacity: the excess is dropped and
 // reported), entries from word 2 on, two words each: {workspace edge << 32 | a << 16 | b, reasons << 32 | k0}.
 GRR_DEV void flag_push(unsigned long long *flist, unsigned long long fcap, long long e, int a, int b, int k0, int reasons) {
@@ -515,6 +547,7 @@ k_edges_build(const __grid_constant__ ChainDev<Real, kMaxJ> c, const int32_t *__
         if constexpr (PL) lane_pass_planar<Real, true>(c, tg, L, mem, first ? P.qa : mem.prev(), first ? P.sa : mem.T, o);
         else lane_pass<Real, M, true>(c, tg, L, mem, first ? P.qa : mem.prev(), first ? P.sa : mem.T, o);
         const int st = lane_step<Real, M, PL, FLAG>(c, L, mem, o, running);
+        if constexpr (FLAG) warp_tie_service<Real, M, PL>(c, L, mem, running);
         if (running && st != IK_RUNNING) {
           cnt.solves++; cnt.iters += L.it; cnt.evals += L.evals; cnt.ok += (st == IK_OK);
           if (FLAG) pair_note_solve(P, L, st);
@@ -720,6 +753,7 @@ k_edges_flat(const __grid_constant__ ChainDev<Real, kMaxJ> c, long long E, const
       if constexpr (PL) lane_pass_planar<Real, true>(c, tg, L, mem, first ? P.qa : mem.prev(), first ? P.sa : mem.T, o);
       else lane_pass<Real, M, true>(c, tg, L, mem, first ? P.qa : mem.prev(), first ? P.sa : mem.T, o);
       const int st = lane_step<Real, M, PL, FLAG>(c, L, mem, o, running);
+      if constexpr (FLAG) warp_tie_service<Real, M, PL>(c, L, mem, running);
       if (running && st != IK_RUNNING) {
         cnt.solves++; cnt.iters += L.it; cnt.evals += L.evals; cnt.ok += (st == IK_OK);
         if (FLAG) pair_note_solve(P, L, st);

@@ -67,7 +67,40 @@ GRR_DEV void sincos_joint(float x, float *s, float *c) {
   *s = (q & 2) ? -ss : ss;
   *c = ((q + 1) & 2) ? -cc : cc;
 }
-GRR_DEV void sincos_joint(double x, double *s, double *c) { sincos(x, s, c); }
+// Double precision (float64 build, recheck pass of the exact edge build): the same structure with fdlibm's kernels
+// (__kernel_sin / __kernel_cos on [-pi/4, pi/4], < 1 ulp) instead of the library sincos, whose general-purpose code is
+// ~170 instructions per call with its 64-bit immediates and slow-path tests -- half of the double-precision chain pass.
+GRR_DEV void sincos_kernel_(double r, double *s, double *c) {
+  const double z = r * r;
+  double ps = fma(z, 1.58969099521155010221e-10, -2.50507602534068634195e-08);
+  ps = fma(ps, z, 2.75573137070700676789e-06);
+  ps = fma(ps, z, -1.98412698298579493134e-04);
+  ps = fma(ps, z, 8.33333333332248946124e-03);
+  *s = fma(z * r, fma(z, ps, -1.66666666666666324348e-01), r);
+  double pc = fma(z, -1.13596475577881948265e-11, 2.08757232129817482790e-09);
+  pc = fma(pc, z, -2.75573143513906633035e-07);
+  pc = fma(pc, z, 2.48015872894767294178e-05);
+  pc = fma(pc, z, -1.38888888888741095749e-03);
+  pc = fma(pc, z, 4.16666666666666019037e-02);
+  // cos = (1 - qx) - ((z/2 - qx) - z^2 pc) with qx ~ |r|/4 rounded to 24 bits, so that 1 - qx is exact (fdlibm's trick)
+  const double qx = (double)(float)(0.25 * fabs(r));
+  *c = (1.0 - qx) - ((0.5 * z - qx) - z * (z * pc));
+}
+GRR_DEV void sincos_joint(double x, double *s, double *c) {
+  const double k = rint(x * 6.36619772367581382433e-01);
+  // pi/2 in three parts, the first two with 33 significant bits: k * part is exact for |k| < 2^20, i.e. |x| < 1.6e6 rad.
+  // (Joint angles live in their limits; only the iterate of a diverging solve of an unbounded joint can leave that
+  // range, and such a solve fails in either arithmetic.)
+  double r = fma(k, -1.57079632673412561417e+00, x);
+  r = fma(k, -6.07710050630396597660e-11, r);
+  r = fma(k, -2.02226624879595063154e-21, r);
+  double sk, ck;
+  sincos_kernel_(r, &sk, &ck);
+  const int q = (int)k;
+  const double ss = (q & 1) ? ck : sk, cc = (q & 1) ? sk : ck;
+  *s = (q & 2) ? -ss : ss;
+  *c = ((q + 1) & 2) ? -cc : cc;
+}
 // every joint limit of the chain lies inside [-pi/4, pi/4] (planar 10R / 20R): no reduction, no fix-up
 GRR_DEV void sincos_small(float r, float *s, float *c) {
   const float r2 = r * r;
@@ -78,7 +111,7 @@ GRR_DEV void sincos_small(float r, float *s, float *c) {
   cp = fmaf(cp, r2, 4.166664568298827e-2f);
   *c = fmaf(cp * r2, r2, fmaf(r2, -0.5f, 1.0f));
 }
-GRR_DEV void sincos_small(double x, double *s, double *c) { sincos(x, s, c); }
+GRR_DEV void sincos_small(double x, double *s, double *c) { sincos_kernel_(x, s, c); }
 
 // Reals of shared memory one lane needs: three rotating config buffers (line-search origin xold,
 // trial point xcur, previous interpolated solution prev), the direction p and the Jacobian columns.
@@ -124,12 +157,14 @@ enum : int { PH_SEARCH = 1, PH_SOFT = 2, PH_HARD = 4, PH_INFL = 8,
              PH_R_CONVX = 1 << 4, PH_R_STPMAX = 1 << 5, PH_R_SLOPE = 1 << 6, PH_R_ALAM = 1 << 7, PH_R_ARMIJO = 1 << 8,
              PH_R_DISC = 1 << 9, PH_R_SOFT2 = 1 << 10, PH_R_SOFTFAIL = 1 << 11, PH_R_MAXIT = 1 << 12, PH_R_LEAF = 1 << 13,
              PH_R_NDIVS = 1 << 14, PH_R_ALL = 0x7ff0,
-             PH_PEND = 1 << 15 };   // an Armijo near-tie awaits its second derivative sample (see lane_step)
+             PH_PEND = 1 << 15,     // an Armijo near-tie awaits its second derivative sample (see lane_step)
+             PH_TIEQ = 1 << 16, PH_TIER = 1 << 17, PH_TSAME = 1 << 18 };   // near-tie request posted / answered / answer's `same` bit
 
 template <typename Real, int M>
 struct LaneIK {
   Real fold, slope, alam, alam2, f2, alamin, stpmax, resid;
   Real amb;      // FLAG builds: after IK_OK, radius within which the double-precision solution may lie (0 = round-off only)
+  Real t_Dc;             // FLAG builds: answer to a posted near-tie request (directional derivative at the trial point)
   Real t_a, t_D, t_ar;   // FLAG builds: first derivative sample of a pending Armijo near-tie (step length, g.p_c, last clear rejection)
   Real aerr;     // FLAG builds: relative error of the current (interpolated) step length
   Real rad;      // FLAG builds: running estimate of |x(single) - x(double)| over the iterations of this solve (see lane_step)
@@ -147,7 +182,7 @@ GRR_DEV void lane_reset(LaneIK<Real, M> &L) {
   L.it = 0; L.evals = 0; L.phase = 0; L.first = false; L.check_convx = false; 
 #pragma unroll
   for (int r = 0; r < M; r++) L.ny[r] = 0;
-  L.alam = 0; L.alam2 = 0; L.f2 = 0; L.fold = 0; L.slope = 0; L.alamin = 0; L.stpmax = 0; L.resid = 0; L.amb = 0; L.rad = 0; L.aerr = 0; L.t_a = 0; L.t_D = 0; L.t_ar = 0;
+  L.alam = 0; L.alam2 = 0; L.f2 = 0; L.fold = 0; L.slope = 0; L.alamin = 0; L.stpmax = 0; L.resid = 0; L.amb = 0; L.rad = 0; L.aerr = 0; L.t_a = 0; L.t_D = 0; L.t_ar = 0; L.t_Dc = 0;
 }
 // Start an instance whose seed is lerp(qa, qb, u) read from (a, b) with strides (sa, sb).
 template <typename Real, int M>
@@ -498,102 +533,106 @@ GRR_DEV void lane_backtrack(LaneIK<Real, M> &L, Real f, Real fl_rel, Real fl_f0 
 //   two samples (this trial and the next, shorter one): D is linear in a up to the third-order term, so
 //     b(a) = D0 - tgt + a kappa / 2 is settled on (0, amax] by its two ends; amax covers every step length the
 //     double-precision search can try after its last clear rejection.
-// Anything else flags the pair.  Runs out of line (rare: ~0.3 ties per pair on the headline config) so that the
-// lane machine's loop stays within the instruction cache.
-template <typename Real>
-struct TieIn {
-  Real FLz[6];           // residual in the goal-link frame, rotation rows already multiplied by Jl^-T (see lane_tie)
-  Real trS, pn2, fold, slope, alam, alam2, t_a, t_D, t_ar;
-  int pending;           // a first sample is waiting (PH_PEND)
-  int final_sample;      // the search ends at this trial (alam < alamin): no third chance
-};
-template <typename Real>
-struct TieOut {
-  int code;              // 0 flag the pair, 1 certified: stalled, 2 certified: accept here, 3 first sample stored: treat as rejected
-  Real t_a, t_D, t_ar;
-};
+// Anything else flags the pair.
 enum : int { TIE_FLAG = 0, TIE_STALL = 1, TIE_ACCEPT = 2, TIE_PENDING = 3 };
 
-template <typename Real, int MC, typename ChainT>
-#ifdef __CUDA_ARCH__
-__device__ __noinline__
-#else
-inline
-#endif
-TieOut<Real> lane_tie(const ChainT *cp, const Real *base, int T, int o_xold, int o_xcur, TieIn<Real> in) {
-  const ChainT &c = *cp;
-  const int n = c.n;
-  const Real *pp = base + 3 * n * T, *xo = base + o_xold, *xt = base + o_xcur, *pc = base + 4 * n * T;
-  Real Dc = 0;
-  bool same = true;
-#pragma unroll 1
-  for (int j = 0; j < n; j++) {
-    const Real pj = pp[j * T], a = xo[j * T], b = xt[j * T];
-    const Real lo = c.jc[j].bmin, hi = c.jc[j].bmax;
-    const bool out_old = (a >= hi && pj > Real(0)) || (a <= lo && pj < Real(0));
-    const bool out_new = (b >= hi && pj > Real(0)) || (b <= lo && pj < Real(0));
-    if (out_new != out_old) same = false;
-    if (!out_old) {
-      Real g = 0;
-#pragma unroll
-      for (int r = 0; r < MC; r++) g = fma_(pc[(j * MC + r) * T], in.FLz[r], g);
-      Dc = fma_(g, pj, Dc);
-    }
-  }
-  TieOut<Real> out;
-  out.code = TIE_FLAG; out.t_a = in.t_a; out.t_D = in.t_D; out.t_ar = in.t_ar;
-  if (!same) return out;
-  const Real ALF = Real(1e-4);
-  const Real F0 = sqrt_(Real(2) * in.fold), tgt = ALF * in.slope;
-  if (!in.pending) {
-    const Real curv = in.alam * in.pn2 * (in.trS + F0 * c.fl_curv);
-    const Real slack = c.fl_dd * (abs_(Dc) + abs_(in.slope));
-    if (Dc - curv - tgt > slack) out.code = TIE_STALL;
-    else if (Dc + curv - tgt < -slack) out.code = TIE_ACCEPT;
-    else if (!in.final_sample && Dc - tgt > slack) {       // (D <= tgt here: a shorter step cannot be certified as rejected either)
-      out.code = TIE_PENDING; out.t_a = in.alam; out.t_D = Dc; out.t_ar = (in.alam2 > Real(0)) ? in.alam2 : in.alam;
-    }
-    return out;
-  }
-  const Real kappa = (in.t_D - Dc) / (in.t_a - in.alam), D0 = Dc - in.alam * kappa;
-  const Real amax = max_(in.t_a, Real(0.5) * in.t_ar);
-  const Real pn = sqrt_(in.pn2);
-  const Real tau = c.fl_curv * in.pn2 * pn * (Real(3) * sqrt_(in.trS) + F0 * sqrt_(Real(n)) * pn);
-  const Real s3 = c.fl_dd * (abs_(Dc) + abs_(in.t_D) + abs_(in.slope) + abs_(kappa) * amax) + amax * amax * tau;
-  const Real b0 = D0 - tgt, bm = D0 - tgt + Real(0.5) * amax * kappa;
-  if (amax * pn < Real(0.05) && b0 > s3 && bm > s3) out.code = TIE_STALL;
-  return out;
-}
-
-// gathers the operands of lane_tie from the lane's state
-template <typename Real, int M, bool PL, typename ChainT>
-GRR_DEV int lane_tie_call(const ChainT &c, LaneIK<Real, M> &L, const LaneMem<Real, col_rows(M, PL)> &mem, const PassOut<Real, M> &o,
-                          bool final_sample) {
+// z with g_j = col_j . z: the residual in the goal-link frame, rotation rows multiplied by Jl^-T (the Jacobian of the
+// log-map residual is Jl^-1 times the stored angular columns, see lane_step)
+template <typename Real, int M, bool PL>
+GRR_DEV void tie_weights(const PassOut<Real, M> &o, Real *z) {
   constexpr int MC = col_rows(M, PL);
-  TieIn<Real> in;
 #pragma unroll
-  for (int r = 0; r < 6; r++) in.FLz[r] = 0;
-#pragma unroll
-  for (int r = 0; r < (MC < 3 ? MC : 3); r++) in.FLz[r] = o.FL[r];
+  for (int r = 0; r < (MC < 3 ? MC : 3); r++) z[r] = o.FL[r];
   if constexpr (M == 6) {
     Real D[9];
     so3_Jl_inv(&o.FL[3], D);
-    m3_Tvec(D, &o.FL[3], &in.FLz[3]);
+    m3_Tvec(D, &o.FL[3], &z[3]);
   }
+}
+
+// one joint's share of Dc = g . p_c and of the `same` test (see above); base = the lane's shared-memory column
+template <typename Real, int MC, typename ChainT>
+GRR_DEV void tie_joint(const ChainT &c, const Real *base, int T, int o_xold, int o_xcur, const Real *z, int j, Real &Dc, bool &same) {
+  const int n = c.n;
+  const Real pj = base[(3 * n + j) * T], a = base[o_xold + j * T], b = base[o_xcur + j * T];
+  const Real lo = c.jc[j].bmin, hi = c.jc[j].bmax;
+  const bool out_old = (a >= hi && pj > Real(0)) || (a <= lo && pj < Real(0));
+  const bool out_new = (b >= hi && pj > Real(0)) || (b <= lo && pj < Real(0));
+  if (out_new != out_old) same = false;
+  if (!out_old) {
+    const Real *pc = base + (4 * n + j * MC) * T;
+    Real g = 0;
+#pragma unroll
+    for (int r = 0; r < MC; r++) g = fma_(pc[r * T], z[r], g);
+    Dc = fma_(g, pj, Dc);
+  }
+}
+
+// The decision once Dc and `same` are known.  Updates the pending first sample (L.t_*, PH_PEND).
+template <typename Real, int M, bool PL, typename ChainT>
+GRR_DEV int lane_tie_decide(const ChainT &c, LaneIK<Real, M> &L, const PassOut<Real, M> &o, Real Dc, bool same, bool final_sample) {
+  const bool pending = (L.phase & PH_PEND) != 0;
+  L.phase &= ~PH_PEND;
+  if (!same) return TIE_FLAG;
   Real trS = 0;
   if constexpr (PL) trS = o.S[0] + o.S[2];
   else {
 #pragma unroll
     for (int r = 0; r < M; r++) trS += o.S[tri(r, r)];
   }
-  in.trS = trS; in.pn2 = o.pn2; in.fold = L.fold; in.slope = L.slope; in.alam = L.alam; in.alam2 = L.alam2;
-  in.t_a = L.t_a; in.t_D = L.t_D; in.t_ar = L.t_ar;
-  in.pending = (L.phase & PH_PEND) ? 1 : 0; in.final_sample = final_sample ? 1 : 0;
-  const TieOut<Real> out = lane_tie<Real, MC>(&c, mem.base, mem.T, mem.o_xold, mem.o_xcur, in);
-  L.t_a = out.t_a; L.t_D = out.t_D; L.t_ar = out.t_ar;
-  L.phase &= ~PH_PEND;
-  if (out.code == TIE_PENDING) L.phase |= PH_PEND;
-  return out.code;
+  const Real ALF = Real(1e-4);
+  const Real F0 = sqrt_(Real(2) * L.fold), tgt = ALF * L.slope;
+  if (!pending) {
+    const Real curv = L.alam * o.pn2 * (trS + F0 * c.fl_curv);
+    const Real slack = c.fl_dd * (abs_(Dc) + abs_(L.slope));
+    if (Dc - curv - tgt > slack) return TIE_STALL;
+    if (Dc + curv - tgt < -slack) return TIE_ACCEPT;
+    if (!final_sample && Dc - tgt > slack) {               // (D <= tgt: a shorter step cannot be certified as rejected either)
+      L.phase |= PH_PEND;
+      L.t_a = L.alam; L.t_D = Dc; L.t_ar = (L.alam2 > Real(0)) ? L.alam2 : L.alam;
+      return TIE_PENDING;
+    }
+    return TIE_FLAG;
+  }
+  const Real kappa = (L.t_D - Dc) / (L.t_a - L.alam), D0 = Dc - L.alam * kappa;
+  const Real amax = max_(L.t_a, Real(0.5) * L.t_ar);
+  const Real pn = sqrt_(o.pn2);
+  const Real tau = c.fl_curv * o.pn2 * pn * (Real(3) * sqrt_(trS) + F0 * sqrt_(Real(c.n)) * pn);
+  const Real s3 = c.fl_dd * (abs_(Dc) + abs_(L.t_D) + abs_(L.slope) + abs_(kappa) * amax) + amax * amax * tau;
+  const Real b0 = D0 - tgt, bm = D0 - tgt + Real(0.5) * amax * kappa;
+  return (amax * pn < Real(0.05) && b0 > s3 && bm > s3) ? TIE_STALL : TIE_FLAG;
+}
+
+// Near-tie met in lane_step.  Device: the directional derivative is a loop over the joints that would run with one
+// lane of the warp active (measured: 5.7 % of all issued instructions); instead the lane posts a request (PH_TIEQ, its
+// weights z in L.ny, which is free during a line search), leaves its state untouched and returns; the kernel then
+// lets the whole warp compute Dc for it, one joint per lane (warp_tie_service in grr_kernels.cuh), and the lane meets
+// the same tie again one trip later -- it re-evaluates the same trial point -- with the answer in L.t_Dc (PH_TIER).
+// Host build (one lane): computed on the spot.  Returns false if the request was posted (caller returns IK_RUNNING).
+template <typename Real, int M, bool PL, typename ChainT>
+GRR_DEV bool lane_tie_operands(const ChainT &c, LaneIK<Real, M> &L, const LaneMem<Real, col_rows(M, PL)> &mem,
+                               const PassOut<Real, M> &o, Real &Dc, bool &same) {
+  constexpr int MC = col_rows(M, PL);
+  if (L.phase & PH_TIER) {
+    L.phase &= ~PH_TIER;
+    Dc = L.t_Dc; same = (L.phase & PH_TSAME) != 0;
+    L.phase &= ~PH_TSAME;
+    return true;
+  }
+#ifdef __CUDA_ARCH__
+  Real z[MC];
+  tie_weights<Real, M, PL>(o, z);
+#pragma unroll
+  for (int r = 0; r < MC; r++) L.ny[r] = z[r];
+  L.phase |= PH_TIEQ;
+  return false;
+#else
+  Real z[MC];
+  tie_weights<Real, M, PL>(o, z);
+  Dc = 0; same = true;
+  for (int j = 0; j < c.n; j++) tie_joint<Real, MC>(c, mem.base, mem.T, mem.o_xold, mem.o_xcur, z, j, Dc, same);
+  return true;
+#endif
 }
 
 // ---- the transition: line-search bookkeeping; no joint loop.  A new Newton iteration only solves the
@@ -688,7 +727,9 @@ GRR_DEV int lane_step(const ChainT &c, LaneIK<Real, M> &L, LaneMem<Real, col_row
       if (L.alam < L.alamin) {
         // the search ends here; a pending near-tie gets its second derivative sample from this trial point
         if (FLAG && (L.phase & PH_PEND)) {
-          if (lane_tie_call<Real, M, PL>(c, L, mem, o, true) != TIE_STALL) L.phase |= PH_HARD | PH_R_ARMIJO;
+          Real Dc; bool same;
+          if (!lane_tie_operands<Real, M, PL>(c, L, mem, o, Dc, same)) { L.evals--; return IK_RUNNING; }
+          if (lane_tie_decide<Real, M, PL>(c, L, o, Dc, same, true) != TIE_STALL) L.phase |= PH_HARD | PH_R_ARMIJO;
         }
         L.it++; L.res = mem.xold(); st = IK_STALL;                        // x <- xold
       } else {
@@ -698,7 +739,9 @@ GRR_DEV int lane_step(const ChainT &c, LaneIK<Real, M> &L, LaneMem<Real, col_row
           // |f - rhs| against the error of f and fold: |F| dF ~ sqrt(fold) fl_f, compared in squares
           const Real df = o.f - rhs, w = (L.phase & PH_INFL) ? Real(64) * c.fl_f2 : c.fl_f2;
           if (df * df < w * L.fold) {
-            const int code = lane_tie_call<Real, M, PL>(c, L, mem, o, false);
+            Real Dc; bool same;
+            if (!lane_tie_operands<Real, M, PL>(c, L, mem, o, Dc, same)) { L.evals--; return IK_RUNNING; }
+            const int code = lane_tie_decide<Real, M, PL>(c, L, o, Dc, same, false);
             if (code == TIE_STALL) { L.it++; L.res = mem.xold(); st = IK_STALL; }
             else if (code == TIE_ACCEPT) accept = true;
             else if (code == TIE_PENDING) accept = false;

@@ -36,6 +36,10 @@ import numpy as np
 from .solver import RedundancyResolver
 
 
+def _round_up(v, m):
+    return (int(v) + m - 1) // m * m
+
+
 def node_ranges(Nw, world):
     """Contiguous, near-equal node ranges: rank r owns [b[r], b[r+1])."""
     b = [(Nw * r) // world for r in range(world + 1)]
@@ -175,8 +179,20 @@ class ShardedResolver(RedundancyResolver):
     chunks (`edge_ids`: global ids of the local mask rows).  `gather_masks()` assembles the full roadmap."""
 
     def __init__(self, resolution, rank, world, seed=0, sample_dtype="float64", rebalance=True, chunks_per_rank=8,
-                 exact_edges=True):
+                 exact_edges=True, exchange="auto", edge_chunks_per_rank=64):
+        """exchange: how the sampled configs reach the ranks that test edges on them.
+             'halo'       node windows of each rank's edge chunks, one slab per (owner, user) pair (+ the cost-based
+                          re-cut of step 4b and its second, small exchange);
+             'allgather'  every rank receives every node's kept configs (one in-place all-reduce of the zero-padded
+                          [Nw][n][max count] block: 25 MB of payload on config 5, 0.33 GB on the wire), and the edge list
+                          is cut into world*edge_chunks_per_rank chunks of equal pair count dealt round-robin -- with
+                          many small chunks per rank the regional differences of the work per pair average out, so no
+                          cost estimate, no cost all-reduce and no second exchange are needed, and the host-side plan
+                          shrinks to one cumulative sum;
+             'auto'       'allgather' while the block fits 4 GB, else 'halo'."""
         self.rank, self.world = int(rank), int(world)
+        self.exchange = exchange
+        self.edge_chunks_per_rank = int(edge_chunks_per_rank)
         self._local_of = {}
         self.rebalance = bool(rebalance)
         self.chunks_per_rank = int(chunks_per_rank)
@@ -231,43 +247,70 @@ class ShardedResolver(RedundancyResolver):
         ev[1].record()
         self.attempts += N
         if connect:
-            K = self.chunks_per_rank
             edges = res.ws_edges
-            cnt = d["count"].cpu().numpy()
-            eb = edge_ranges(edges, cnt, self.world * K)                              # preliminary: by pair count
-            chunks = rank_chunks(eb, self.world, K)
-            wins = node_windows(edges, eb)
-            windows = [wins[r::self.world] for r in range(self.world)]
-            self.halo_bytes = exchange_halo(d["Qs"], self.rank, halo_plan(self.nbounds, windows, self.world), dist)
-            if self.rebalance and self.world > 1:
-                # 4b: exact work estimate on the preliminary chunks, then re-cut by cost
-                if d["Qs"] is not d["Q"]:
-                    for (wl, wh) in windows[self.rank]:
-                        d["Q"][wl:wh].copy_(d["Qs"][wl:wh])
-                cost = torch.zeros(self.E, dtype=torch.int64, device=res.torch_device)
-                for (a, b) in chunks[self.rank]:
-                    if b > a:
-                        res.chain.edges_cost(d["wedges"][a:b], d["Q"], d["count"], 0.05, cost[a:b])
-                dist.all_reduce(cost)
-                # cut on the device: only the world*K + 1 boundaries come back to the host
-                cum = torch.cumsum(cost, 0)
-                total = int(cum[-1].item()) if self.E else 0
-                if total > 0:
-                    targets = torch.arange(1, self.world * K, device=cum.device, dtype=torch.float64) * (total / float(self.world * K))
-                    cuts = torch.searchsorted(cum.to(torch.float64), targets, right=False) + 1
-                    eb = [0] + [int(v) for v in torch.clamp(cuts, max=self.E).cpu().tolist()] + [self.E]
-                    for i in range(1, len(eb)):
-                        eb[i] = max(eb[i], eb[i - 1])
+            mode = self.exchange
+            if mode == "auto":
+                mode = "allgather" if d["Qs"].numel() * d["Qs"].element_size() <= 4 * 2 ** 30 else "halo"
+            if mode == "allgather":
+                K = self.edge_chunks_per_rank
+                cnt_dev = d["count"]
+                cmax = int(cnt_dev.max().item()) if self.Nw else 0          # (sync: the plan below needs the counts anyway)
+                cnt = cnt_dev.cpu().numpy()
+                if cmax > 0 and self.world > 1:
+                    # kept configs of every node to every rank: blocks of nodes this rank did not sample are zero
+                    own = torch.zeros(self.Nw, dtype=torch.bool, device=res.torch_device)
+                    for (lo, hi) in mine_nodes:
+                        own[lo:hi] = True
+                    cpad = min(_round_up(cmax, 4), d["Qs"].shape[2])
+                    blk = d["Qs"][:, :, :cpad] * own[:, None, None].to(d["Qs"].dtype)
+                    blk = blk.contiguous()
+                    dist.all_reduce(blk)
+                    d["Qs"][:, :, :cpad] = blk
+                    self.halo_bytes = int(blk.numel() * blk.element_size())
+                eb = edge_ranges(edges, cnt, self.world * K)
+                chunks = rank_chunks(eb, self.world, K)
+            else:
+                K = self.chunks_per_rank
+                cnt = d["count"].cpu().numpy()
+                eb = edge_ranges(edges, cnt, self.world * K)                              # preliminary: by pair count
                 chunks = rank_chunks(eb, self.world, K)
                 wins = node_windows(edges, eb)
                 windows = [wins[r::self.world] for r in range(self.world)]
-                self.halo_bytes += exchange_halo(d["Qs"], self.rank, halo_plan(self.nbounds, windows, self.world), dist)
+                self.halo_bytes = exchange_halo(d["Qs"], self.rank, halo_plan(self.nbounds, windows, self.world), dist)
+                if self.rebalance and self.world > 1:
+                    # 4b: exact work estimate on the preliminary chunks, then re-cut by cost
+                    if d["Qs"] is not d["Q"]:
+                        for (wl, wh) in windows[self.rank]:
+                            d["Q"][wl:wh].copy_(d["Qs"][wl:wh])
+                    cost = torch.zeros(self.E, dtype=torch.int64, device=res.torch_device)
+                    for (a, b) in chunks[self.rank]:
+                        if b > a:
+                            res.chain.edges_cost(d["wedges"][a:b], d["Q"], d["count"], 0.05, cost[a:b])
+                    dist.all_reduce(cost)
+                    # cut on the device: only the world*K + 1 boundaries come back to the host
+                    cum = torch.cumsum(cost, 0)
+                    total = int(cum[-1].item()) if self.E else 0
+                    if total > 0:
+                        targets = torch.arange(1, self.world * K, device=cum.device, dtype=torch.float64) * (total / float(self.world * K))
+                        cuts = torch.searchsorted(cum.to(torch.float64), targets, right=False) + 1
+                        eb = [0] + [int(v) for v in torch.clamp(cuts, max=self.E).cpu().tolist()] + [self.E]
+                        for i in range(1, len(eb)):
+                            eb[i] = max(eb[i], eb[i - 1])
+                    chunks = rank_chunks(eb, self.world, K)
+                    wins = node_windows(edges, eb)
+                    windows = [wins[r::self.world] for r in range(self.world)]
+                    self.halo_bytes += exchange_halo(d["Qs"], self.rank, halo_plan(self.nbounds, windows, self.world), dist)
             mine = chunks[self.rank]
             self.edge_ids = np.concatenate([np.arange(a, b, dtype=np.int64) for (a, b) in mine]) if mine else np.zeros(0, dtype=np.int64)
             self._local_of = None                      # built on demand by _edge_qlist
             ne = int(self.edge_ids.shape[0])
             W = (self.Nq + 31) // 32
-            d["mask"] = torch.zeros((ne, self.Nq, W), dtype=torch.int32, device=res.torch_device)
+            # the bitmask buffer is kept across builds (the kernels overwrite every row they are given)
+            buf = self.__dict__.get("_mask_buf")
+            if buf is None or buf.shape[0] < ne or buf.shape[1:] != (self.Nq, W):
+                buf = torch.zeros((ne + ne // 16 + 1, self.Nq, W), dtype=torch.int32, device=res.torch_device)
+                self._mask_buf = buf
+            d["mask"] = buf[:ne]
             d["edge_stats"] = torch.zeros((ne, 2), dtype=torch.int32, device=res.torch_device)
             if ne:
                 my_wedges = torch.cat([d["wedges"][a:b] for (a, b) in mine if b > a]).contiguous()

@@ -204,6 +204,17 @@ int grr_gather_node_blocks(int dtype, int64_t K, const int32_t *idx, int32_t n, 
 int grr_scatter_node_blocks(int dtype, int64_t K, const int32_t *idx, int32_t n, int32_t Nqp, const void *packed,
                             const int32_t *packed_count, void *q, int32_t *count, void *stream);
 
+/* The exchange itself for hosts that do not use PyTorch (replaces the pickled qlists the reference's
+ * master/worker pool sends over OS pipes, grr/solver.py:2298-2337,2367-2400).  In the node-blocked layout a node range
+ * [node_lo, node_hi) of q [dev] Real [Nw][n][Nqp] is one contiguous slab, so a halo is a list of slabs, each sent to or
+ * received from one peer rank in place: ncclGroupStart; ncclSend / ncclRecv per slab (and of count[node_lo..node_hi)
+ * [dev] i32 when count != NULL); ncclGroupEnd, all on `stream`.  nccl_comm is the caller's ncclComm_t; the library
+ * resolves the NCCL entry points from the libnccl.so.2 already loaded in the process (env GRR_NCCL_LIB overrides the
+ * name), so it carries no link-time dependency on NCCL.  Returns -4 on an NCCL error. */
+int grr_halo_exchange(grr_handle_t h, void *nccl_comm, int dtype, int32_t Nqp, int32_t n_slabs, const int32_t *peer,
+                      const int32_t *is_send, const int64_t *node_lo, const int64_t *node_hi, void *q, int32_t *count,
+                      void *stream);
+
 /* -- the roadmap's consumer on the bitmasks: the constraint satisfaction problem of
  * RedundancyResolver.makeCSP (grr/solver.py:984-1022) -- one variable per workspace node with configs, one table
  * constraint per workspace edge whose C-space edge set is non-empty; the table is the edge's Nq x Nq bitmask --

@@ -67,3 +67,11 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".inc")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in txt and "from oracle" not in txt and "grr_oracle" not in txt, f
+
+
+def test_halo_exchange_validates_arguments_without_a_gpu():
+    """grr_halo_exchange is exported and refuses a null communicator before touching NCCL or the device."""
+    import ctypes as C
+    L = _cabi.lib()
+    assert L.grr_halo_exchange(None, None, 0, 4, 1, None, None, None, None, None, None, None) == -1
+    assert b"null handle" in L.grr_last_error()

@@ -1,4 +1,6 @@
-"""torchrun -n N tools/check_sharded.py: sharded roadmap == single-GPU roadmap (same seeds, global node ids)."""
+"""torchrun -n N tools/check_sharded.py: the sharded roadmap equals the single-GPU roadmap (same seeds, global node ids)
+for both exchange modes (halo windows / all-gather of the kept configs) and for the exact and the plain edge build.
+Run by tests/test_gpu_sharded.py when at least two GPUs are visible."""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -8,22 +10,32 @@ from globalredundancyresolution_b200 import sharding
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-name, jf, Nw, Nq = "planar_20R", "baseline_cfg2.json", 600, 24
-pdef, res = grr.load_problem(name, jf, overrides={"Nw": Nw}, device=local)
-res.sampleWorkspace(Nw, method=pdef["workspace_graph"])
-sr = sharding.ShardedResolver(res, rank, world, seed=3)
-ts, tc = sr.sampleConfigurationSpace(Nq, order_independent=True)
-full = sr.gather_masks()
-cnt = sr._dev["count"].clone()
-pairs = torch.tensor([float(sr.stats["pairs"])], device="cuda"); dist.all_reduce(pairs)
-if rank == 0:
-    rr = grr.RedundancyResolver(res, seed=3)
-    rr.sampleConfigurationSpace(Nq, order_independent=True)
-    assert torch.equal(cnt, rr._dev["count"]), "counts differ"
-    assert torch.equal(full, rr._dev["mask"]), "edge masks differ"
-    for (lo, hi) in sr.my_node_ranges():
-        assert torch.equal(sr._dev["Qs"][lo:hi], rr._dev["Qs"][lo:hi])
-    assert int(pairs.item()) == rr.stats["pairs"], (pairs.item(), rr.stats["pairs"])
-    print("sharded == single GPU: world=%d nodes=%d edges=%d pairs=%d halo_bytes(rank0)=%d chunks=%d" % (world, sr.Nw, sr.E, rr.stats["pairs"], sr.halo_bytes, sr.chunks_per_rank))
-dist.barrier()
+cases = [("planar_20R", "baseline_cfg2.json", 600, 24), ("robonaut2", "baseline_cfg5.json", 1500, 120)]
+for (name, jf, Nw, Nq) in cases:
+    pdef, res = grr.load_problem(name, jf, overrides={"Nw": Nw}, device=local)
+    res.sampleWorkspace(Nw, method=pdef["workspace_graph"])
+    ref = {}
+    for exact in (True, False):
+        if rank == 0:
+            rr = grr.RedundancyResolver(res, seed=3, exact_edges=exact)
+            rr.sampleConfigurationSpace(Nq, order_independent=True)
+            ref[exact] = (rr._dev["count"].clone(), rr._dev["mask"].clone(), rr._dev["Qs"].clone(), rr.stats["pairs"], rr.stats["valid"])
+        for exchange in ("halo", "allgather"):
+            sr = sharding.ShardedResolver(res, rank, world, seed=3, exact_edges=exact, exchange=exchange)
+            for rep in range(2):                      # twice: buffers are re-used across builds
+                sr.initWorkspaceGraph()
+                ts, tc = sr.sampleConfigurationSpace(Nq, order_independent=True)
+            full = sr.gather_masks()
+            cnt = sr._dev["count"].clone()
+            tot = torch.tensor([float(sr.stats["pairs"]), float(sr.stats["valid"])], device="cuda"); dist.all_reduce(tot)
+            if rank == 0:
+                c0, m0, q0, p0, v0 = ref[exact]
+                assert torch.equal(cnt, c0), "counts differ"
+                assert torch.equal(full, m0), "edge masks differ (%s, exact=%s, %s)" % (name, exact, exchange)
+                for (lo, hi) in sr.my_node_ranges():
+                    assert torch.equal(sr._dev["Qs"][lo:hi], q0[lo:hi])
+                assert int(tot[0].item()) == p0 and int(tot[1].item()) == v0, (tot.tolist(), p0, v0)
+                print("sharded == single GPU: %s world=%d nodes=%d edges=%d pairs=%d exact=%s exchange=%s bytes received(rank0)=%d"
+                      % (name, world, sr.Nw, sr.E, p0, exact, exchange, sr.halo_bytes), flush=True)
+            dist.barrier()
 dist.destroy_process_group()
