@@ -50,6 +50,115 @@ def adjacency_csr(Nw, edges):
     return ptr.astype(np.int32), other[order].astype(np.int32), eid[order].astype(np.int32)
 
 
+def heuristic_max_assignment(count, edges, mask, choose=None):
+    """CSP.heuristicMaxAssignment (grr/utils/csp.py:739-932) on the roadmap's bitmasks, host side (the reference runs it
+    once per solveCSP call as the first guess, solver.py:2042; it is a sequential greedy).
+
+    count [Nw] configs per node, edges [E][2] workspace edges (iw < jw), mask uint32 [E][Nq][W] edge bitmasks.
+    Variables = nodes with configs, constraints = workspace edges with a non-empty mask (solver.py:1013-1021).
+    The algorithm: repeatedly take the unassigned variable with the fewest remaining values (ties: most unassigned
+    neighbours; ties: `choose(candidates)`, the reference's random.choice -- default: the smallest node id), give it
+    the value with the best (min over unassigned neighbours of #values still compatible, #neighbours with any
+    compatible value) -- first best in domain order --, and forward-check its neighbours' domains.  A variable whose
+    domain ran empty gets the value of its original domain with the fewest conflicts against the assigned neighbours.
+    The reference's arc-consistency passes (csp.py:756-806, :915) call isCompatible2 (csp.py:152-165), every path of
+    which returns True, so they never remove a value; they are therefore not executed here (oracle/csp_oracle.py keeps
+    them literally and gives the same result).  Returns (assignment int32 [Nw], -1 = no variable; list of failures)."""
+    count = np.asarray(count, dtype=np.int64)
+    edges = np.asarray(edges, dtype=np.int64).reshape(-1, 2)
+    mask = np.ascontiguousarray(mask).view(np.uint32)
+    Nw, E = count.shape[0], edges.shape[0]
+    Nq = mask.shape[1] if E else int(count.max() if Nw else 0)
+    active = mask.reshape(E, -1).any(axis=1) if E else np.zeros(0, dtype=bool)
+    inc = [[] for _ in range(Nw)]                       # (other node, edge, this node is the first endpoint)
+    for e in np.nonzero(active)[0].tolist():
+        a, b = int(edges[e, 0]), int(edges[e, 1])
+        if count[a] > 0 and count[b] > 0:
+            inc[a].append((b, e, True))
+            inc[b].append((a, e, False))
+    bits_cache = {}
+
+    def bits(e):                                        # bool [Nq][Nq], (value of first endpoint, value of second)
+        m = bits_cache.get(e)
+        if m is None:
+            m = np.unpackbits(mask[e].view(np.uint8).reshape(mask.shape[1], -1), axis=1, bitorder="little")[:, :Nq].astype(bool)
+            bits_cache[e] = m
+        return m
+
+    dom = np.zeros((Nw, max(Nq, 1)), dtype=bool)
+    for i in np.nonzero(count > 0)[0]:
+        dom[i, :count[i]] = True
+    res = np.full(Nw, -1, dtype=np.int32)
+    unassigned = count > 0
+    size = count.copy()
+    degree = np.asarray([len(inc[i]) for i in range(Nw)], dtype=np.int64)
+    BIG = np.int64(1 << 20)
+    NEG = np.iinfo(np.int64).min
+    failures = []
+    # values assigned through the empty-domain branch are not forward-checked at once (csp.py:853-858 `continue`); the
+    # reference meets their constraints later, whenever it filters or scans a neighbour's domain against the whole
+    # partial assignment (compatible / isCompatible, csp.py:195-223,116-131): kept here as pending row masks per node
+    pending = [[] for _ in range(Nw)]
+
+    def effective(n):
+        d = dom[n]
+        for (e, first_n, val_other) in pending[n]:
+            B = bits(e)
+            d = d & (B[:, val_other] if first_n else B[val_other])
+        return d
+
+    remaining = int(unassigned.sum())
+    while remaining > 0:
+        key = np.where(unassigned, -size * BIG + degree, NEG)          # lexicographic (-len(domain), degree)
+        cand = np.nonzero(key == key.max())[0]
+        best = int(cand[0] if choose is None else choose([int(c) for c in cand]))
+        if size[best] == 0:
+            # csp.py:838-858: minimum-conflict value of the ORIGINAL domain against the assigned neighbours
+            ninc = np.zeros(count[best], dtype=np.int64)
+            for (n, e, first) in inc[best]:
+                if res[n] >= 0:
+                    B = bits(e)
+                    ok = B[:count[best], res[n]] if first else B[res[n], :count[best]]
+                    ninc += ~ok
+            value = int(np.argmin(ninc))
+            failures.append(best)
+        else:
+            values = np.nonzero(dom[best])[0]
+            mincompat = np.full(values.shape[0], 100000, dtype=np.int64)
+            numcompat = np.zeros(values.shape[0], dtype=np.int64)
+            for (n, e, first) in inc[best]:
+                if not unassigned[n]:
+                    continue
+                B = bits(e)
+                # values of n still in its domain that stay compatible when best = value, for every candidate value
+                dn = effective(n)
+                nc = B[values][:, dn].sum(axis=1) if first else B[dn][:, values].sum(axis=0)
+                numcompat += nc != 0
+                mincompat = np.minimum(mincompat, nc)
+            score = mincompat * BIG + numcompat                        # lexicographic; first best wins (strict >)
+            value = int(values[int(np.argmax(score))])
+        res[best] = value
+        unassigned[best] = False
+        remaining -= 1
+        if size[best] == 0:
+            # csp.py:853-858: the reference `continue`s here -- no forward checking from a variable whose domain ran
+            # empty, and its neighbours keep their (now stale) degree until one of their other neighbours is assigned
+            for (n, e, first) in inc[best]:
+                if unassigned[n]:
+                    pending[n].append((e, not first, value))
+            bits_cache.clear()
+            continue
+        for (n, e, first) in inc[best]:
+            if unassigned[n]:
+                B = bits(e)
+                dom[n] = effective(n) & (B[value] if first else B[:, value])     # forward checking (csp.py:906-913)
+                pending[n] = []
+                size[n] = int(dom[n].sum())
+                degree[n] = sum(1 for (m, _, _) in inc[n] if unassigned[m])      # getdegree(n), csp.py:925
+        bits_cache.clear()
+    return res, failures
+
+
 class RoadmapCSP:
     """Device-resident view of makeCSP's problem for one RedundancyResolver (its current counts and bitmasks).
 
@@ -94,6 +203,12 @@ class RoadmapCSP:
         for i, v in zip(self.variables(), values):
             row[i] = -1 if v is None else int(v)
         return self.torch.from_numpy(row).to(self.device).view(1, -1)
+
+    def heuristicMaxAssignment(self, choose=None):
+        """csp.py:739-932 on this roadmap (host-side greedy on the downloaded bitmasks, see heuristic_max_assignment);
+        returns one assignment row [1][Nw] on the device and the list of variables whose domain ran empty."""
+        res, failures = heuristic_max_assignment(self.count.cpu().numpy(), self.rr.resolution.ws_edges, self.mask.cpu().numpy(), choose)
+        return self.torch.from_numpy(res).to(self.device).view(1, -1), failures
 
     # ---- primitives ---------------------------------------------------------------------------------------
     def randomAssignment(self, G=1, seed=None, guess_offset=0):

@@ -917,26 +917,40 @@ class RedundancyResolver:
         self.decodeCSPAssignment(a[0])
 
     def solveCSP(self, visibility=False, parallel=False, numRandomDescents=2, numInitialGuesses=10, threads=None, tasks=None,
-                 results=None):
-        """solver.py:2035-2062: best of numInitialGuesses descents.  All guesses are descended at once on the device.
-        Deviation: the reference's first guess comes from CSP.heuristicMaxAssignment (csp.py:739-932, a sequential
-        greedy with arc consistency), which is not built; every guess starts from random values, so the method
-        reported is always 'random'.  Repeating a converged descent (numRandomDescents) changes nothing
-        (perturb=False) and is not executed.  Returns (bestConflicts, bestMethod, solve_time, collapse_time)."""
+                 results=None, heuristic=True):
+        """solver.py:2035-2062: the first guess is CSP.heuristicMaxAssignment (csp.py:739-932; host-side greedy on the
+        bitmasks, csp.heuristic_max_assignment) followed by descents, the other numInitialGuesses - 1 guesses start from
+        random values and are descended all at once on the device; the best one wins, the heuristic guess on ties
+        (`conflicts < bestConflicts`, solver.py:2054).  Repeating a converged descent (numRandomDescents) changes nothing
+        (perturb=False) and is not executed.  The reference breaks ties among equally constrained variables with
+        random.choice; here the smallest node id is taken.  heuristic=False skips the first guess (every guess random).
+        Returns (bestConflicts, bestMethod, solve_time, collapse_time)."""
         if visibility:
             raise NotImplementedError("visibility-graph solver is out of scope of the B200 roadmap path")
         torch = self.resolution._torch()
         t0 = time.time()
         csp = self.csp()
-        a = csp.randomDescentAssignment(None, G=max(int(numInitialGuesses), 1))
-        conflicts = csp.numConflicts(a)
-        best = int(torch.argmin(conflicts).item())
-        bestConflicts = int(conflicts[best].item())
+        G = max(int(numInitialGuesses), 1)
+        best_row, bestConflicts, bestMethod, all_conf, failures = None, None, None, [], []
+        if heuristic:
+            a0, failures = csp.heuristicMaxAssignment()
+            a0 = csp.randomDescentAssignment(a0)
+            bestConflicts = int(csp.numConflicts(a0)[0].item())
+            best_row, bestMethod = a0[0], "heuristic max"
+            all_conf.append(bestConflicts)
+            G -= 1
+        if G > 0:
+            a = csp.randomDescentAssignment(None, G=G)
+            conflicts = csp.numConflicts(a)
+            k = int(torch.argmin(conflicts).item())
+            all_conf += conflicts.cpu().tolist()
+            if bestConflicts is None or int(conflicts[k].item()) < bestConflicts:
+                best_row, bestConflicts, bestMethod = a[k], int(conflicts[k].item()), "random"
         solve_time = time.time() - t0
-        self.stats["csp"] = {"conflicts": conflicts.cpu().tolist(), "sweeps": csp.sweeps, "guesses": int(a.shape[0]),
-                             "solve_time": solve_time}
-        self.decodeCSPAssignment(a[best])
-        return bestConflicts, "random", solve_time, 0
+        self.stats["csp"] = {"conflicts": all_conf, "sweeps": csp.sweeps, "guesses": len(all_conf), "solve_time": solve_time,
+                             "heuristic_failures": len(failures)}
+        self.decodeCSPAssignment(best_row)
+        return bestConflicts, bestMethod, solve_time, 0
 
     def sampleConflicts(self, NConfigsPerPoint=10):
         """solver.py:1988-2033: the refinement step between two solveCSP calls.  Conflict nodes = both

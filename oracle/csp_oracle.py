@@ -97,3 +97,130 @@ class TableCSP:
                 active.discard(i)                                                                       # :1027-1028
             if not changed:                                                                             # :1039-1040
                 return assignment, passes
+
+    # ---- csp.py:739-932 ----------------------------------------------------------------------------------------
+    def is_compatible2(self, v1, val1, v2, val2):
+        """csp.py:152-165 isCompatible2, literally -- INCLUDING its defect: every path of the reference function ends in
+        `return True` (a satisfied constraint returns True early, and the fall-through is `return True` as well), so
+        no pair of values is ever reported incompatible and the arc-consistency passes of heuristicMaxAssignment
+        (csp.py:756-806) remove nothing.  A drop-in must give the reference's results, so this is kept."""
+        for k in self.incident[v1]:
+            scope = self.scopes[k]
+            if v2 in scope and v1 in scope:
+                vals = tuple(val1 if v == v1 else val2 for v in scope)
+                if vals in self.tables[k]:
+                    return True
+        return True
+
+    def is_compatible(self, var, value, assignment):
+        """csp.py isCompatible: var=value violates no constraint whose other variables are assigned."""
+        return self.num_incompatible(var, value, assignment) == 0
+
+    def heuristic_max_assignment(self, choose):
+        """csp.py:739-932 (heuristicMaxAssignment), literally: arc consistency on every pair of neighbouring unassigned
+        variables, then repeatedly the unassigned variable with the fewest remaining values (ties: most unassigned
+        neighbours; ties: `choose(list)` where the reference calls random.choice), given the value that leaves its
+        neighbours the most freedom (score (min over unassigned neighbours of #compatible values, #neighbours with any
+        compatible value, -assignmentCost = 0), first best in domain order), forward checking + arc consistency around
+        it.  A variable whose domain ran empty gets the value of its ORIGINAL domain with the fewest conflicts."""
+        nv = len(self.names)
+        res = [None] * nv
+        unassigned = set(range(nv))
+        domains = [list(d) for d in self.domains]
+
+        def ac3(v1, v2):
+            d1, d2 = list(domains[v1]), list(domains[v2])
+            numchanged, changed = 0, True
+            while changed:
+                changed = False
+                newd1, newd2 = [], []
+                for val1 in d1:
+                    if any(self.is_compatible2(v1, val1, v2, val2) for val2 in d2):
+                        newd1.append(val1)
+                    else:
+                        changed = True; numchanged += 1
+                for val2 in d2:
+                    if any(self.is_compatible2(v1, val1, v2, val2) for val1 in newd1):
+                        newd2.append(val2)
+                    else:
+                        changed = True; numchanged += 1
+                if changed:
+                    d1, d2 = newd1, newd2
+            if numchanged == 0:
+                return domains[v1], domains[v2]
+            return d1, d2
+
+        def run_ac3(v1=None, v2=None):
+            if v1 is None:
+                for a in sorted(unassigned):
+                    run_ac3(a)
+            elif v2 is None:
+                for b in sorted(self.neighbors[v1]):
+                    if b in unassigned:
+                        run_ac3(v1, b)
+            else:
+                d1, d2 = ac3(v1, v2)
+                if len(d1) == 0 or len(d2) == 0:
+                    return
+                domains[v1], domains[v2] = d1, d2
+
+        run_ac3()
+        getdegree = lambda n: len([m for m in self.neighbors[n] if m in unassigned])
+        degrees = {n: getdegree(n) for n in unassigned}
+        getscore = lambda var: (-len(domains[var]), degrees[var])
+        scores = {v: getscore(v) for v in unassigned}
+        failures = []
+        while unassigned:
+            bestlist, bestscore = [], (-float("inf"), 0)
+            for var in sorted(scores):
+                sc = scores[var]
+                if sc > bestscore:
+                    bestscore, bestlist = sc, [var]
+                elif sc == bestscore:
+                    bestlist.append(var)
+            best = choose(bestlist)
+            domain = domains[best]
+            if len(domain) == 0:
+                mininc, bestval = 10000000, None
+                for val in self.domains[best]:
+                    ninc = self.num_incompatible(best, val, res)
+                    if ninc < mininc:
+                        bestval, mininc = val, ninc
+                res[best] = bestval
+                del scores[best]; del degrees[best]
+                unassigned.remove(best)
+                failures.append(best)
+                continue
+            bestvalue, bestsc = None, (-1, 0, 0)
+            for value in domain:
+                mincompatible, numcompatible = 100000, 0
+                res[best] = value
+                for n in sorted(self.neighbors[best]):
+                    if n not in unassigned:
+                        continue
+                    ncompatible = 0
+                    for nval in domains[n]:
+                        if self.is_compatible(n, nval, res):
+                            ncompatible += 1
+                            if ncompatible >= mincompatible:
+                                break
+                    if ncompatible != 0:
+                        numcompatible += 1
+                    mincompatible = min(ncompatible, mincompatible)
+                sc = (mincompatible, numcompatible, 0)
+                if sc > bestsc:
+                    bestsc, bestvalue = sc, value
+            res[best] = bestvalue
+            for n in sorted(self.neighbors[best]):
+                if n in unassigned:
+                    domains[n] = [v for v in domains[n] if self.is_compatible(n, v, res)]
+            for n in sorted(self.neighbors[best]):
+                if n in unassigned:
+                    run_ac3(n)
+            unassigned.remove(best)
+            del scores[best]; del degrees[best]
+            for n in self.neighbors[best]:
+                if n in unassigned:
+                    degrees[n] = getdegree(n)
+                    scores[n] = getscore(n)
+        return res, failures

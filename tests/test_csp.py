@@ -138,7 +138,17 @@ def test_solve_csp_sets_the_resolution(built):
     res, rr = _roadmap(Nw=120, Nq=10)
     conflicts, method, t_solve, t_collapse = rr.solveCSP(numInitialGuesses=6)
     st = rr.stats["csp"]
-    assert conflicts == min(st["conflicts"]) and method == "random" and st["guesses"] == 6
+    assert conflicts == min(st["conflicts"]) and st["guesses"] == 6
+    # the first guess is heuristicMaxAssignment + descent (solver.py:2042-2046); it keeps the title on ties (:2054)
+    assert method == ("heuristic max" if st["conflicts"][0] == conflicts else "random")
+    # and it is what the literal restatement computes on the reference's own container (makeCSP), then descended
+    ref = TableCSP.from_container(rr.makeCSP())
+    want, fails = ref.heuristic_max_assignment(min)
+    csp = rr.csp()
+    a0, fails_dev = csp.heuristicMaxAssignment()
+    assert csp.to_reference(a0[0]) == want and len(fails) == len(fails_dev)
+    c2, m2, _, _ = rr.solveCSP(numInitialGuesses=6, heuristic=False)
+    assert m2 == "random" and rr.stats["csp"]["guesses"] == 6
     cnt = rr.counts()
     assert set(rr.Qsubgraph) == set(np.nonzero(cnt > 0)[0].tolist())
     # resolution: chosen configs solve their node's IK problem; connected edges are C-space edges of the roadmap

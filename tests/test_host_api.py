@@ -178,3 +178,39 @@ def test_loader_reads_the_references_own_pickle(tmp_path):
     node2, adj2, _ = loads_graph(open(out / "resolution_graph.pickle", "rb").read())
     assert node2 == node and {k: set(v) for k, v in adj2.items()} == {k: set(v) for k, v in adj.items()}
     assert all(adj2[i][j] == adj[i][j] for i in adj for j in adj[i])
+
+
+def test_heuristic_max_assignment_equals_literal_restatement():
+    """csp.heuristic_max_assignment (the product's host-side greedy on the edge bitmasks) against the literal
+    restatement of CSP.heuristicMaxAssignment (grr/utils/csp.py:739-932, oracle/csp_oracle.py) on random CSPs in the
+    roadmap's format: same assignment, same list of variables whose domain ran empty, for two tie-break rules."""
+    from globalredundancyresolution_b200.csp import heuristic_max_assignment
+    from oracle.csp_oracle import TableCSP
+    rng = np.random.default_rng(0)
+    failures_seen = 0
+    for trial in range(120):
+        Nw = int(rng.integers(4, 16)); Nq = int(rng.integers(2, 40))
+        count = rng.integers(0, Nq + 1, size=Nw)
+        edges = np.asarray(sorted({(min(a, b), max(a, b)) for a, b in rng.integers(0, Nw, size=(3 * Nw, 2)) if a != b}))
+        W = (Nq + 31) // 32
+        B = rng.random((len(edges), Nq, Nq)) < rng.choice([0.0, 0.05, 0.3, 0.8])
+        for e, (a, b) in enumerate(edges):
+            B[e, count[a]:, :] = False; B[e, :, count[b]:] = False
+        pad = np.zeros((len(edges), Nq, W * 32), dtype=np.uint8); pad[:, :, :Nq] = B
+        mask = np.packbits(pad, axis=2, bitorder="little").view(np.uint32).reshape(len(edges), Nq, W)
+        csp = TableCSP()
+        for i in range(Nw):
+            if count[i] > 0:
+                csp.add_variable(list(range(count[i])), "q_%d" % i)
+        for e, (a, b) in enumerate(edges):
+            if B[e].any():
+                csp.add_constraint(set(zip(*np.nonzero(B[e]))), ("q_%d" % a, "q_%d" % b))
+        pick = min if trial % 2 == 0 else (lambda lst: lst[(7 * len(lst)) // 11])
+        ref, fails_ref = csp.heuristic_max_assignment(pick)
+        got, fails = heuristic_max_assignment(count, edges, mask, pick)
+        var_nodes = np.nonzero(count > 0)[0]
+        assert [int(got[i]) for i in var_nodes] == [int(v) for v in ref]
+        assert [int(np.nonzero(var_nodes == f)[0][0]) for f in fails] == fails_ref
+        assert (got[count == 0] == -1).all()
+        failures_seen += len(fails)
+    assert failures_seen > 50            # the empty-domain branch (csp.py:838-858) is exercised
