@@ -26,7 +26,7 @@ MAX_JOINTS = 32
 EXPORTS = [
     "grr_last_error", "grr_abi_version", "grr_chain_create", "grr_chain_destroy", "grr_task_set",
     "grr_chain_num_joints", "grr_fk_batch", "grr_ik_solve_batch", "grr_ik_sample", "grr_ik_sample_level", "grr_dedup", "grr_dedup_sweep",
-    "grr_edges_build", "grr_edges_build_exact", "grr_set_flag_scale", "grr_edges_cost", "grr_edges_compact", "grr_valid_edge_batch", "grr_gather_node_blocks",
+    "grr_edges_build", "grr_edges_build_exact", "grr_set_flag_scale", "grr_edges_exact_mode", "grr_edges_cost", "grr_edges_compact", "grr_valid_edge_batch", "grr_gather_node_blocks",
     "grr_scatter_node_blocks", "grr_halo_exchange", "grr_csp_random_assignment", "grr_csp_conflicts", "grr_csp_descent_sweep",
     "grr_fp32_peak", "grr_fp32x2_peak",
 ]
@@ -78,6 +78,7 @@ def lib():
     L.grr_edges_build.argtypes = [vp, C.c_int, i64, vp, vp, vp, vp, vp, i32, i32, dbl, vp, vp, vp, vp]
     L.grr_edges_build_exact.argtypes = [vp, i64, vp, vp, vp, vp, vp, vp, vp, i32, i32, dbl, vp, vp, vp, vp]
     L.grr_set_flag_scale.argtypes = [vp, dbl]
+    L.grr_edges_exact_mode.argtypes = [vp]
     L.grr_edges_cost.argtypes = [vp, C.c_int, i64, vp, vp, vp, vp, i32, dbl, vp, vp]
     L.grr_edges_compact.argtypes = [i64, i32, vp, vp, vp, vp]
     L.grr_valid_edge_batch.argtypes = [vp, C.c_int, i64, vp, vp, vp, vp, dbl, vp, vp, vp, vp]
@@ -98,7 +99,7 @@ def lib():
 
 def check(rc, what):
     global LAUNCHES
-    if what not in ("grr_chain_create", "grr_task_set", "grr_fp32_peak", "grr_fp32x2_peak", "grr_set_flag_scale"):
+    if what not in ("grr_chain_create", "grr_task_set", "grr_fp32_peak", "grr_fp32x2_peak", "grr_set_flag_scale", "grr_edges_exact_mode"):
         # edges_build = k_edge_load + k_edges_build (+ k_edges_recheck in the exact build)
         LAUNCHES += {"grr_edges_build": 2, "grr_edges_build_exact": 3}.get(what, 1)
     if rc != 0:
@@ -267,6 +268,14 @@ class ChainHandle:
         check(lib().grr_edges_build_exact(self._h, E, _ptr(wedges), _ptr(params32), _ptr(params64), _ptr(q32), _ptr(q64),
                                           _ptr(count), _ptr(old_count), int(Nq), q32.shape[2], float(epsilon), _ptr(mask),
                                           _ptr(edge_stats), _ptr(counters), _stream(q32.device)), "grr_edges_build_exact")
+
+    def exact_mode(self):
+        """'recheck' (single-precision pass + double-precision recheck) or 'double' (double-precision kernels): what
+        grr_edges_build_exact does for this chain."""
+        rc = lib().grr_edges_exact_mode(self._h)
+        if rc < 0:
+            check(rc, "grr_edges_exact_mode")
+        return {1: "recheck", 2: "double"}[rc]
 
     def set_flag_scale(self, scale):
         self._flag_scale = float(scale)

@@ -501,6 +501,14 @@ int grr_edges_build(grr_handle_t h, int dtype, int64_t E, const int32_t *wedges,
                           (unsigned long long *)counters, (cudaStream_t)stream, nullptr);
 }
 
+int grr_edges_exact_mode(grr_handle_t h) {
+  if (!h) { set_error("null handle"); return -1; }
+  const char *force = getenv("GRR_EXACT_MODE");                   // "recheck" / "double": experiments
+  if (force && !strcmp(force, "recheck")) return 1;
+  if (force && !strcmp(force, "double")) return 2;
+  return (h->hc.mode == GRR_FREE && is_planar_y_chain(h->hc)) ? 1 : 2;
+}
+
 int grr_edges_build_exact(grr_handle_t h, int64_t E, const int32_t *wedges, const float *params32, const double *params64,
                           const float *q_kept32, const double *q_kept64, const int32_t *count, const int32_t *old_count,
                           int32_t Nq, int32_t Nqp, double epsilon, uint32_t *mask, uint32_t *edge_stats, uint64_t *counters,
@@ -513,6 +521,12 @@ int grr_edges_build_exact(grr_handle_t h, int64_t E, const int32_t *wedges, cons
   unsigned long long *work = work_slot(h);
   if (!work) return -3;
   const ScratchReq sreq = {h, scratch_cb};
+  if (grr_edges_exact_mode(h) == 2) {
+    // general chains: the double-precision kernels on the double-precision configs (see grr_edges_exact_mode)
+    const Ops *ops64 = pick_ops(GRR_F64, h->hc.mode);
+    return ops64->edges_build(h->hc, E, wedges, params64, q_kept64, count, old_count, Nq, Nqp, epsilon, mask, edge_stats, work, &sreq,
+                              (unsigned long long *)counters, (cudaStream_t)stream, nullptr);
+  }
   const ExactArgs ex = {params64, q_kept64};
   return ops->edges_build(h->hc, E, wedges, params32, q_kept32, count, old_count, Nq, Nqp, epsilon, mask, edge_stats, work, &sreq,
                           (unsigned long long *)counters, (cudaStream_t)stream, &ex);

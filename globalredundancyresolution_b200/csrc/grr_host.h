@@ -4,6 +4,7 @@
 #include <stdint.h>
 #include <string.h>
 #include <limits>
+#include <math.h>
 #include "../../include/grr_b200.h"
 
 namespace grr {
@@ -21,6 +22,20 @@ struct HostChain {
 enum { FL_F = 0, FL_X = 1, FL_ALAM = 2, FL_REL = 3, FL_LEAF = 4, FL_ND = 5, FL_MAXIT = 6, FL_DD = 7, FL_CURV = 8 };
 
 void set_error(const char *fmt, ...);
+
+// planar-y chain: every joint has identity preceding rotation and axis +-e_y, goal-link frame = last joint frame, free
+// orientation (the reference's planar_{2,3,5,10,20}R robots): the chains with the two-dimensional specialisation of the
+// lane pass, and the ones whose exact edge build is the single-precision pass + recheck
+inline bool is_planar_y_chain(const HostChain &h) {
+  if (h.mode != GRR_FREE) return false;
+  for (int k = 0; k < 9; k++) if (fabs(h.R_tail[k] - ((k % 4 == 0) ? 1.0 : 0.0)) > 1e-14) return false;
+  for (int j = 0; j < h.n; j++) {
+    const double *R = h.Rp + 9 * j, *a = h.axis + 3 * j;
+    for (int k = 0; k < 9; k++) if (fabs(R[k] - ((k % 4 == 0) ? 1.0 : 0.0)) > 1e-14) return false;
+    if (fabs(fabs(a[1]) - 1.0) > 1e-14 || fabs(a[0]) > 1e-14 || fabs(a[2]) > 1e-14) return false;
+  }
+  return true;
+}
 
 // grow-only device scratch of the handle (reallocation synchronises the device)
 struct ScratchReq { void *ctx; unsigned long long *(*get)(void *ctx, size_t words); };

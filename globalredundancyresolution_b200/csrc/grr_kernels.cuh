@@ -919,17 +919,7 @@ inline int set_smem(Kern kern, size_t smem, const char *what) {
   return 0;
 }
 
-// planar-y chain: every joint of the short kind about +-e_y, goal-link frame = last joint frame, free orientation
-inline bool is_planar_y(const HostChain &h) {
-  if (h.mode != GRR_FREE) return false;
-  for (int k = 0; k < 9; k++) if (fabs(h.R_tail[k] - ((k % 4 == 0) ? 1.0 : 0.0)) > 1e-14) return false;
-  for (int j = 0; j < h.n; j++) {
-    const double *R = h.Rp + 9 * j, *a = h.axis + 3 * j;
-    for (int k = 0; k < 9; k++) if (fabs(R[k] - ((k % 4 == 0) ? 1.0 : 0.0)) > 1e-14) return false;
-    if (fabs(fabs(a[1]) - 1.0) > 1e-14 || fabs(a[0]) > 1e-14 || fabs(a[2]) > 1e-14) return false;
-  }
-  return true;
-}
+inline bool is_planar_y(const HostChain &h) { return is_planar_y_chain(h); }
 
 template <typename Real, int M>
 struct Impl {

@@ -441,6 +441,15 @@ class RedundancyResolver:
             res.chain.edges_build(wedges, d["params"], d["Q"], d["count"], self.Nq, DEFAULT_EDGE_CHECK_TOLERANCE,
                                   mask, stats, d["counters_e"], old_count=old_counts)
 
+    def edge_arithmetic(self):
+        """'f32+f64 recheck' / 'f64' (exact build, by chain: grr_edges_exact_mode) / 'f32' (exact_edges=False) / 'f64' (float64 resolution)."""
+        torch = self.resolution._torch()
+        if self.resolution.torch_dtype == torch.float64:
+            return "f64"
+        if not self.exact_edges:
+            return "f32"
+        return "f32+f64 recheck" if self.resolution.chain.exact_mode() == "recheck" else "f64"
+
     def _check_exact(self, ce):
         """The near-tie list of the exact build must not have overflowed (it never does below 25 % flagged pairs)."""
         if int(ce[_cabi.CNT_FLAG_DROPPED]) != 0:
@@ -569,6 +578,7 @@ class RedundancyResolver:
                       "ik_evals": int(c[_cabi.CNT_IK_EVALS] + ce[_cabi.CNT_IK_EVALS]),
                       "pairs": int(ce[_cabi.CNT_PAIRS]), "valid": int(ce[_cabi.CNT_VALID]),
                       "flagged": int(ce[_cabi.CNT_FLAGGED]), "flipped": int(ce[_cabi.CNT_FLIPPED]),
+                      "edge_arithmetic": self.edge_arithmetic(),
                       "sampled": int(d["count"].sum().item()) - start_total,
                       "attempts": int(c[_cabi.CNT_IK_SOLVES]), "t_sample": t_sample, "t_connect": t_connect}
 

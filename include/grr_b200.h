@@ -174,6 +174,13 @@ int grr_edges_build_exact(grr_handle_t h, int64_t E, const int32_t *wedges, cons
                           int32_t Nq, int32_t Nqp, double epsilon, uint32_t *mask, uint32_t *edge_stats, uint64_t *counters,
                           void *stream);
 int grr_set_flag_scale(grr_handle_t h, double scale);
+/* How grr_edges_build_exact decides a chain's pairs: 1 = single-precision pass + double-precision recheck of the listed
+ * near-ties (planar chains: every joint about +-e_y; measured 0 differing verdicts of 1.05e8 on BASELINE config 2, 2-4 % of
+ * the pairs re-tested), 2 = the double-precision kernels throughout (every other chain: the interpolated solves of 6-/7-joint
+ * arms pass near singular configurations where single- and double-precision iterates drift apart without any decision being
+ * close, a quarter to a third of their pairs would have to be re-tested and the two-pass build costs what double precision
+ * costs).  Env GRR_EXACT_MODE=recheck|double overrides (experiments). */
+int grr_edges_exact_mode(grr_handle_t h);
 
 /* Work estimate of grr_edges_build per workspace edge: sum over the pairs it will test of
  * Ndivs + 1 = ceil(robot.distance(qa,qb) / eps) + 1 (graph.py:944-946), i.e. interpolated IK solves +
