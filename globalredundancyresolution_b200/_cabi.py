@@ -29,6 +29,8 @@ EXPORTS = [
     "grr_edges_build", "grr_edges_build_exact", "grr_set_flag_scale", "grr_edges_exact_mode", "grr_edges_cost", "grr_edges_compact", "grr_valid_edge_batch", "grr_gather_node_blocks",
     "grr_scatter_node_blocks", "grr_halo_exchange", "grr_csp_random_assignment", "grr_csp_conflicts", "grr_csp_descent_sweep",
     "grr_fp32_peak", "grr_fp32x2_peak",
+    "grr_edges_test_listed", "grr_manifold_knn_list", "grr_manifold_components", "grr_qcc_candidates", "grr_qcc_wave",
+    "grr_qcc_connect", "grr_pair_hash",
 ]
 
 
@@ -79,6 +81,14 @@ def lib():
     L.grr_edges_build_exact.argtypes = [vp, i64, vp, vp, vp, vp, vp, vp, vp, i32, i32, dbl, vp, vp, vp, vp]
     L.grr_set_flag_scale.argtypes = [vp, dbl]
     L.grr_edges_exact_mode.argtypes = [vp]
+    L.grr_edges_test_listed.argtypes = [vp, C.c_int, vp, vp, vp, i32, i32, dbl, vp, vp, vp, u64, vp, vp]
+    L.grr_manifold_knn_list.argtypes = [C.c_int, i64, vp, i32, i32, i32, vp, vp, i32, vp, u64, vp]
+    L.grr_manifold_components.argtypes = [C.c_int, i64, vp, i32, i32, i32, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, vp]
+    L.grr_qcc_candidates.argtypes = [C.c_int, i64, vp, i32, i32, i32, vp, vp, vp, vp, vp, vp, i32, u64, i32, vp, vp]
+    L.grr_qcc_wave.argtypes = [i64, vp, vp, vp, i32, vp, i32, vp, i32, i32, i32, vp, u64, vp]
+    L.grr_qcc_connect.argtypes = [i64, vp, vp, vp, i32, vp, i32, vp, i32, i32, vp, vp, vp, vp, vp]
+    L.grr_pair_hash.argtypes = [u64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]
+    L.grr_pair_hash.restype = C.c_uint32
     L.grr_edges_cost.argtypes = [vp, C.c_int, i64, vp, vp, vp, vp, i32, dbl, vp, vp]
     L.grr_edges_compact.argtypes = [i64, i32, vp, vp, vp, vp]
     L.grr_valid_edge_batch.argtypes = [vp, C.c_int, i64, vp, vp, vp, vp, dbl, vp, vp, vp, vp]
@@ -91,7 +101,7 @@ def lib():
     L.grr_fp32_peak.argtypes = [C.c_int, C.POINTER(C.c_double)]
     L.grr_fp32x2_peak.argtypes = [C.c_int, C.POINTER(C.c_double)]
     for name in EXPORTS:
-        if name not in ("grr_last_error",):
+        if name not in ("grr_last_error", "grr_pair_hash"):
             getattr(L, name).restype = C.c_int
     _lib = L
     return L
@@ -99,7 +109,7 @@ def lib():
 
 def check(rc, what):
     global LAUNCHES
-    if what not in ("grr_chain_create", "grr_task_set", "grr_fp32_peak", "grr_fp32x2_peak", "grr_set_flag_scale", "grr_edges_exact_mode"):
+    if what not in ("grr_chain_create", "grr_task_set", "grr_fp32_peak", "grr_fp32x2_peak", "grr_set_flag_scale", "grr_edges_exact_mode", "grr_pair_hash"):
         # edges_build = k_edge_load + k_edges_build (+ k_edges_recheck in the exact build)
         LAUNCHES += {"grr_edges_build": 2, "grr_edges_build_exact": 3}.get(what, 1)
     if rc != 0:
@@ -301,6 +311,13 @@ class ChainHandle:
                                    _ptr(old_count), q_kept.shape[2], float(epsilon), _ptr(cost), _stream(q_kept.device)),
               "grr_edges_cost")
 
+    def edges_test_listed(self, wedges, params, q_kept, Nq, epsilon, mask, plist, counters=None, edge_stats=None):
+        """Test the listed pairs (plist: int64 device tensor {count, pad, entries...}) and set / clear their mask bits."""
+        cap = (plist.shape[0] - 2) // 2
+        check(lib().grr_edges_test_listed(self._h, dtype_code(q_kept.dtype), _ptr(wedges), _ptr(params), _ptr(q_kept), int(Nq),
+                                          q_kept.shape[2], float(epsilon), _ptr(mask), _ptr(edge_stats), _ptr(plist), cap,
+                                          _ptr(counters), _stream(q_kept.device)), "grr_edges_test_listed")
+
     def valid_edge_batch(self, qa, qb, wa, wb, epsilon, valid, info=None, counters=None):
         P = qa.shape[1]
         check(lib().grr_valid_edge_batch(self._h, dtype_code(qa.dtype), P, _ptr(qa), _ptr(qb), _ptr(wa), _ptr(wb),
@@ -336,6 +353,45 @@ def csp_descent_sweep(node_list, Nq, adj_ptr, adj_node, adj_edge, mask, edge_act
                                       _ptr(adj_edge), _ptr(mask), _ptr(edge_active), _ptr(count), _ptr(assignment),
                                       _ptr(in_order), _ptr(active), _ptr(changed), _stream(mask.device)),
           "grr_csp_descent_sweep")
+
+
+def manifold_knn_list(q, count, Nq, knn, plist, node_list=None):
+    """Pairs the k-nearest branch of constructSelfMotionManifold may test (solver.py:635-643) -> plist."""
+    Nn = q.shape[0] if node_list is None else node_list.shape[0]
+    cap = (plist.shape[0] - 2) // 2
+    check(lib().grr_manifold_knn_list(dtype_code(q.dtype), Nn, _ptr(node_list), q.shape[1], int(Nq), q.shape[2], _ptr(q), _ptr(count),
+                                      int(knn), _ptr(plist), cap, _stream(q.device)), "grr_manifold_knn_list")
+
+
+def manifold_components(q, count, Nq, self_mask, knn, label, ncc, parents, members, cc_start, ntests=None, node_list=None):
+    """constructSelfMotionManifold (solver.py:623-669) replayed on the self mask's verdict bits."""
+    Nn = q.shape[0] if node_list is None else node_list.shape[0]
+    check(lib().grr_manifold_components(dtype_code(q.dtype), Nn, _ptr(node_list), q.shape[1], int(Nq), q.shape[2], _ptr(q), _ptr(count),
+                                        _ptr(self_mask), int(knn), _ptr(label), _ptr(ncc), _ptr(parents), _ptr(members),
+                                        _ptr(cc_start), _ptr(ntests), _stream(q.device)), "grr_manifold_components")
+
+
+def qcc_candidates(wedges, q, Nq, uid, ncc, members, cc_start, cc_off, max_tests, seed, swap, cand):
+    check(lib().grr_qcc_candidates(dtype_code(q.dtype), wedges.shape[0], _ptr(wedges), q.shape[1], int(Nq), q.shape[2], _ptr(q),
+                                   _ptr(uid), _ptr(ncc), _ptr(members), _ptr(cc_start), _ptr(cc_off), int(max_tests),
+                                   int(seed) & (2 ** 64 - 1), int(swap), _ptr(cand), _stream(q.device)), "grr_qcc_candidates")
+
+
+def qcc_wave(wedges, ncc, cc_off, max_tests, cand, Nq, tested_mask, slot0, slot1, swap, plist):
+    cap = (plist.shape[0] - 2) // 2
+    check(lib().grr_qcc_wave(wedges.shape[0], _ptr(wedges), _ptr(ncc), _ptr(cc_off), int(max_tests), _ptr(cand), int(Nq),
+                             _ptr(tested_mask), int(slot0), int(slot1), int(swap), _ptr(plist), cap, _stream(wedges.device)), "grr_qcc_wave")
+
+
+def qcc_connect(wedges, ncc, cc_off, max_tests, cand, Nq, tested_mask, mode, swap, mask, conn, nconn, ntests=None):
+    check(lib().grr_qcc_connect(wedges.shape[0], _ptr(wedges), _ptr(ncc), _ptr(cc_off), int(max_tests), _ptr(cand), int(Nq),
+                                _ptr(tested_mask), int(mode), int(swap), _ptr(mask), _ptr(conn), _ptr(nconn), _ptr(ntests),
+                                _stream(wedges.device)), "grr_qcc_connect")
+
+
+def pair_hash(seed, iw, jw, a, b):
+    """The keyed hash that orders the sampled candidates of a CC pair (host function of the library)."""
+    return int(lib().grr_pair_hash(int(seed) & (2 ** 64 - 1), int(iw), int(jw), int(a), int(b)))
 
 
 def gather_node_blocks(idx, q, count, packed, packed_count):

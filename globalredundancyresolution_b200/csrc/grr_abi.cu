@@ -501,6 +501,20 @@ int grr_edges_build(grr_handle_t h, int dtype, int64_t E, const int32_t *wedges,
                           (unsigned long long *)counters, (cudaStream_t)stream, nullptr);
 }
 
+int grr_edges_test_listed(grr_handle_t h, int dtype, const int32_t *wedges, const void *params, const void *q_kept, int32_t Nq,
+                          int32_t Nqp, double epsilon, uint32_t *mask, uint32_t *edge_stats, const uint64_t *list, uint64_t cap,
+                          uint64_t *counters, void *stream) {
+  GRR_CHECK_HANDLE(h);
+  const Ops *ops = pick_ops(dtype, h->hc.mode);
+  if (!ops) { set_error("bad dtype %d", dtype); return -1; }
+  if (!wedges || !params || !q_kept || !mask || !list || Nq < 1 || Nqp < Nq || Nq > 65535) { set_error("grr_edges_test_listed: bad argument"); return -1; }
+  if (cap == 0) return 0;
+  unsigned long long *work = work_slot(h);
+  if (!work) return -3;
+  return ops->edges_listed(h->hc, wedges, params, q_kept, Nq, Nqp, epsilon, mask, edge_stats, (const unsigned long long *)list, cap, work,
+                           (unsigned long long *)counters, (cudaStream_t)stream);
+}
+
 int grr_edges_exact_mode(grr_handle_t h) {
   if (!h) { set_error("null handle"); return -1; }
   const char *force = getenv("GRR_EXACT_MODE");                   // "recheck" / "double": experiments

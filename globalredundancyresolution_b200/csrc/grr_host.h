@@ -62,6 +62,9 @@ struct Ops {
                      const int32_t *count, const int32_t *old_count, int Nq, int Nqp, double epsilon, uint32_t *mask,
                      uint32_t *edge_stats, unsigned long long *work, const ScratchReq *scratch /* nullable */,
                      unsigned long long *counters, cudaStream_t st, const ExactArgs *exact /* nullable */);
+  int (*edges_listed)(const HostChain &, const int32_t *wedges, const void *params, const void *q_kept, int Nq, int Nqp,
+                      double epsilon, uint32_t *mask, uint32_t *edge_stats, const unsigned long long *list,
+                      unsigned long long cap, unsigned long long *work, unsigned long long *counters, cudaStream_t st);
 };
 
 const Ops *ops_f32_m3();

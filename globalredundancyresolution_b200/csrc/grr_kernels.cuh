@@ -510,6 +510,7 @@ k_edges_build(const __grid_constant__ ChainDev<Real, kMaxJ> c, const int32_t *__
           if (ok) {
             ta = (int)(t / (unsigned)cb); tb = (int)(t - (unsigned)ta * (unsigned)cb);
             if (ta < oa && tb < ob) ok = false;                   // solver.py:694
+            if (iw == jw && ta <= tb) ok = false;                 // self-motion pairs: validEdge(q_i, q_j, x, x), i > j (solver.py:648-653)
           }
           if (ok) {
             nd = pair_ndivs<Real, FLAG>(n, eps, sa + ta, Nqp, sb + tb, Nqp, c.fl_nd);
@@ -614,7 +615,8 @@ static __global__ void k_edges_prepare(long long E, const int32_t *__restrict__ 
   if (threadIdx.x == 0) {
     offs[e + 1] = (unsigned long long)ca * (unsigned long long)cb;     // queue positions (both-old ones are skipped on decode)
     if (e == 0) offs[0] = 0;
-    if (edge_stats) edge_stats[2 * e] = (uint32_t)((long long)ca * cb - (long long)oa * ob);
+    if (edge_stats) edge_stats[2 * e] = (iw == jw) ? (uint32_t)(((long long)ca * (ca - 1) - (long long)oa * (oa - 1)) / 2)
+                                                   : (uint32_t)((long long)ca * cb - (long long)oa * ob);
   }
 }
 
@@ -711,6 +713,7 @@ k_edges_flat(const __grid_constant__ ChainDev<Real, kMaxJ> c, long long E, const
           ta = (int)(off / cb); tb = (int)(off - (unsigned)ta * cb);
           GRR_DCHECK(e >= 0 && e < E && offs[e] <= t && t < offs[e + 1] && cb > 0 && ta < count[iw] && tb < (int)cb && ta < Nq && tb < Nq);
           if (old_count && ta < old_count[iw] && tb < old_count[jw]) ok = false;      // solver.py:694
+          if (iw == jw && ta <= tb) ok = false;                                       // self-motion pairs i > j (solver.py:648-653)
           if (ok) {
             // all lanes measure their pair together (a lane doing this alone ran with 1.5 of 32 lanes active)
             nd = pair_ndivs<Real, FLAG>(n, eps, q_kept + (long long)iw * n * Nqp + ta, Nqp, q_kept + (long long)jw * n * Nqp + tb, Nqp, c.fl_nd);
@@ -789,13 +792,14 @@ __global__ void __launch_bounds__(256)
 k_edges_recheck(const __grid_constant__ ChainDev<Real, kMaxJ> c, const int32_t *__restrict__ wedges,
                 const Real *__restrict__ params, const Real *__restrict__ q_kept, int Nq, int Nqp, Real epsilon, uint32_t *mask,
                 uint32_t *edge_stats, const unsigned long long *__restrict__ flist, unsigned long long fcap,
-                unsigned long long *work, unsigned long long *counters) {
+                unsigned long long *work, unsigned long long *counters, int listed_mode) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int n = c.n, dw = (c.mode == 2 ? 6 : 3);
   const int Wd = (Nq + 31) >> 5;
   LaneMem<Real, col_rows(M, PL)> mem;
   mem.init(reinterpret_cast<Real *>(smem_raw) + threadIdx.x, (int)blockDim.x, n);
   for (int j = 0; j < lane_reals<col_rows(M, PL)>(n); j++) mem.base[j * mem.T] = 0;
+  LaneCounters cnt;
   const unsigned long long listed = flist[0];
   const unsigned long long total = listed < fcap ? listed : fcap;
   const Real eps = epsilon * sqrt_(Real(c.nlinks_eps));
@@ -847,6 +851,7 @@ k_edges_recheck(const __grid_constant__ ChainDev<Real, kMaxJ> c, const int32_t *
       else lane_pass<Real, M, true>(c, tg, L, mem, first ? P.qa : mem.prev(), first ? P.sa : mem.T, o);
       const int st = lane_step<Real, M, PL>(c, L, mem, o, running);
       if (running && st != IK_RUNNING) {
+        cnt.solves++; cnt.iters += L.it; cnt.evals += L.evals; cnt.ok += (st == IK_OK);
         if (st != IK_OK) verdict = 0;
         else {
           verdict = pair_advance(c, mem, o.s2, thr2, P, L, P.k == kstart && kstart > 1);
@@ -863,11 +868,16 @@ k_edges_recheck(const __grid_constant__ ChainDev<Real, kMaxJ> c, const int32_t *
         flipped++; dvalid += verdict - was;
         if (edge_stats) atomicAdd(&edge_stats[2 * edge + 1], (uint32_t)(verdict - was));
       }
+      cnt.pairs++; cnt.valid += verdict;
       edge = -1;
       lane_begin_mem(L, mem);
     }
   }
-  if (counters) {
+  if (listed_mode) {
+    // explicit pair list (grr_edges_test_listed): these are first tests, counted like the edge kernels count theirs
+    cnt.flush(counters);
+    if (counters && blockIdx.x == 0 && threadIdx.x == 0 && listed > fcap) atomicAdd(counters + GRR_CNT_FLAG_DROPPED, listed - fcap);
+  } else if (counters) {
     warp_add(counters, GRR_CNT_FLAGGED, flagged);
     warp_add(counters, GRR_CNT_FLIPPED, flipped);
     // valid-pair count of the first pass corrected by the verdicts that changed (two's complement add)
@@ -1133,7 +1143,8 @@ struct Impl {
   // second pass of the exact build: the listed near-tie pairs in this Impl's arithmetic (instantiated for double)
   static int edges_recheck(const HostChain &h, const int32_t *wedges, const void *params, const void *q_kept, int Nq, int Nqp,
                            double epsilon, uint32_t *mask, uint32_t *edge_stats, const unsigned long long *flist,
-                           unsigned long long fcap, unsigned long long *work, unsigned long long *counters, cudaStream_t st) {
+                           unsigned long long fcap, unsigned long long *work, unsigned long long *counters, cudaStream_t st,
+                           int listed_mode = 0) {
     Chain c; fill_chain(h, c);
     // as many lanes per SM as shared memory allows, in one or two CTAs
     int threads, per_sm_want;
@@ -1149,7 +1160,7 @@ struct Impl {
       }
       kern<<<(unsigned)(sm_count(h.device) * per_sm), threads, smem, st>>>(c, wedges, (const Real *)params, (const Real *)q_kept, Nq,
                                                                            Nqp, (Real)epsilon, mask, edge_stats, flist, fcap, work,
-                                                                           counters);
+                                                                           counters, listed_mode);
       return 0;
     };
     int rc;
@@ -1157,6 +1168,14 @@ struct Impl {
     else rc = launch(k_edges_recheck<Real, M, false>);
     if (rc) return rc;
     return check_launch("k_edges_recheck");
+  }
+
+  // explicit pair list {edge << 32 | a << 16 | b, 0}: each listed pair is tested and its mask bit set or cleared
+  // (the tests of the visibility-graph variant: knn pairs of constructSelfMotionManifold, testAndConnectQccs candidates)
+  static int edges_listed(const HostChain &h, const int32_t *wedges, const void *params, const void *q_kept, int Nq, int Nqp,
+                          double epsilon, uint32_t *mask, uint32_t *edge_stats, const unsigned long long *list,
+                          unsigned long long cap, unsigned long long *work, unsigned long long *counters, cudaStream_t st) {
+    return edges_recheck(h, wedges, params, q_kept, Nq, Nqp, epsilon, mask, edge_stats, list, cap, work, counters, st, 1);
   }
 
   static int edges_flat(const HostChain &h, const Chain &c, long long E, const int32_t *wedges, const void *params,

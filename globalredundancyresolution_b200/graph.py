@@ -265,6 +265,12 @@ class RedundancyResolutionGraph:
         torch = self._torch()
         return torch.as_tensor(np.ascontiguousarray(arr), dtype=dtype or self.torch_dtype, device=self.torch_device)
 
+    def _api_dtype(self):
+        """Precision of the per-call entry points that take Python lists (solve, validEdge, ikError, getIKParameters and
+        their batch forms): double, the reference's arithmetic -- these calls are bound by host conversions, not by the
+        kernels, and their answers (joint values, edge verdicts) then equal the reference's without a recheck."""
+        return self._torch().float64
+
     def solve(self, qinit, x, testfeasibility=True):
         """graph.py:779-790: IK at workspace params x seeded from qinit; returns the full config or None."""
         res = self.solveBatch([qinit], [x])
@@ -275,8 +281,8 @@ class RedundancyResolutionGraph:
         torch = self._torch()
         self.setIKProblem(xs[0])
         P = len(qinits)
-        q = self._dev(self.to_chain(np.asarray(qinits)).T)                     # [n][P]
-        tg = self._dev(np.asarray(xs, dtype=np.float64))
+        q = self._dev(self.to_chain(np.asarray(qinits)).T, self._api_dtype())  # [n][P]
+        tg = self._dev(np.asarray(xs, dtype=np.float64), self._api_dtype())
         status = torch.empty(P, dtype=torch.uint8, device=self.torch_device)
         self.chain.ik_solve_batch(tg, q, status)
         st = status.cpu().numpy()
@@ -287,9 +293,9 @@ class RedundancyResolutionGraph:
         """graph.py:887-893: 2-norm of the IK residual at q for workspace params x."""
         torch = self._torch()
         self.setIKProblem(x)
-        qd = self._dev(self.to_chain(np.asarray([q])).T)
-        p = torch.empty((1, 3), dtype=self.torch_dtype, device=self.torch_device)
-        R = torch.empty((1, 9), dtype=self.torch_dtype, device=self.torch_device)
+        qd = self._dev(self.to_chain(np.asarray([q])).T, self._api_dtype())
+        p = torch.empty((1, 3), dtype=self._api_dtype(), device=self.torch_device)
+        R = torch.empty((1, 9), dtype=self._api_dtype(), device=self.torch_device)
         self.chain.fk_batch(qd, p, R)
         p = p.double().cpu().numpy()[0]
         err = p - np.asarray(x[:3], dtype=np.float64)
@@ -304,9 +310,9 @@ class RedundancyResolutionGraph:
     def getIKParameters(self, q):
         """graph.py:747-756"""
         torch = self._torch()
-        qd = self._dev(self.to_chain(np.asarray([q])).T)
-        p = torch.empty((1, 3), dtype=self.torch_dtype, device=self.torch_device)
-        R = torch.empty((1, 9), dtype=self.torch_dtype, device=self.torch_device)
+        qd = self._dev(self.to_chain(np.asarray([q])).T, self._api_dtype())
+        p = torch.empty((1, 3), dtype=self._api_dtype(), device=self.torch_device)
+        R = torch.empty((1, 9), dtype=self._api_dtype(), device=self.torch_device)
         self.chain.fk_batch(qd, p, R)
         x = [float(v) for v in p.double().cpu().numpy()[0]]
         if self.ikTaskSpace[0].orientation == "variable":
@@ -324,10 +330,10 @@ class RedundancyResolutionGraph:
     def validEdgeBatch(self, qas, qbs, was, wbs, epsilon=DEFAULT_EDGE_CHECK_TOLERANCE, return_info=False):
         torch = self._torch()
         P = len(qas)
-        qa = self._dev(self.to_chain(np.asarray(qas)).T)
-        qb = self._dev(self.to_chain(np.asarray(qbs)).T)
-        wa = self._dev(np.asarray(was, dtype=np.float64))
-        wb = self._dev(np.asarray(wbs, dtype=np.float64))
+        qa = self._dev(self.to_chain(np.asarray(qas)).T, self._api_dtype())
+        qb = self._dev(self.to_chain(np.asarray(qbs)).T, self._api_dtype())
+        wa = self._dev(np.asarray(was, dtype=np.float64), self._api_dtype())
+        wb = self._dev(np.asarray(wbs, dtype=np.float64), self._api_dtype())
         valid = torch.empty(P, dtype=torch.uint8, device=self.torch_device)
         info = torch.empty((P, 4), dtype=torch.int32, device=self.torch_device) if return_info else None
         self.chain.valid_edge_batch(qa, qb, wa, wb, epsilon, valid, info)

@@ -14,7 +14,7 @@ from lower-numbered neighbours in a sequential Gauss-Seidel sweep driven by Pyth
 `random` (solver.py:773-815).  The device path draws every start from a counter-based Philox stream
 keyed by (node, sample) -- the semantics of the reference's own order-independent
 parallelQSamplingAtP (solver.py:875-897) -- so that CPU oracle and GPU see identical seeds.
-Visibility-graph / self-motion options are out of scope and raise NotImplementedError.
+The visibility-graph variant (visibility=True / selfmotion=True) lives in visibility.py.
 """
 from __future__ import annotations
 
@@ -24,6 +24,7 @@ import numpy as np
 
 from . import _cabi
 from .graph import DEFAULT_EDGE_CHECK_TOLERANCE
+from .visibility import VisibilityMixin
 
 DEDUP_THRESHOLD = 1e-2      # solver.py:805,827,889
 
@@ -36,18 +37,23 @@ class _NodeView(dict):
         self._rr, self._i = rr, i
         dict.__setitem__(self, "params", rr.resolution.Gw.node[i]["params"])
 
-    def __getitem__(self, k):
+    def _lazy(self, k):
         if k == "qlist":
-            return self._rr._node_qlist(self._i)
-        return dict.__getitem__(self, k)
+            return True, self._rr._node_qlist(self._i)
+        if k in ("qccs", "qcc_parents") and getattr(self._rr, "_vis", None) is not None:      # solver.py:223-228
+            return True, (self._rr._node_qccs(self._i) if k == "qccs" else self._rr._node_qcc_parents(self._i))
+        return False, None
+
+    def __getitem__(self, k):
+        hit, v = self._lazy(k)
+        return v if hit else dict.__getitem__(self, k)
 
     def get(self, k, default=None):
-        if k == "qlist":
-            return self._rr._node_qlist(self._i)
-        return dict.get(self, k, default)
+        hit, v = self._lazy(k)
+        return v if hit else dict.get(self, k, default)
 
     def __contains__(self, k):
-        return k == "qlist" or dict.__contains__(self, k)
+        return k == "qlist" or (k in ("qccs", "qcc_parents") and getattr(self._rr, "_vis", None) is not None) or dict.__contains__(self, k)
 
 
 class _EdgeView(dict):
@@ -131,7 +137,7 @@ class RoadmapView:
         return list(self.edges_iter(data))
 
 
-class RedundancyResolver:
+class RedundancyResolver(VisibilityMixin):
     def __init__(self, resolution, cache=20000, cacheloc=None, seed=0, sample_dtype="float64", exact_edges=True):
         """`cache` / `cacheloc` are accepted for signature compatibility (solver.py:239); the disk-backed
         CGraph they configure is replaced by device tensors.
@@ -184,6 +190,8 @@ class RedundancyResolver:
             self._static = None
             self.h2d_bytes = 0
         self._dev = None
+        self._vis = None             # self-motion manifolds (visibility.py)
+        self._vis_host = None
         self._qcache = {}
         self._ecache = {}
         self.Gw = RoadmapView(self)
@@ -242,6 +250,7 @@ class RedundancyResolver:
             d["Q"], d["Qs"], d["mask"] = Q, Qs, mask
             d["edge_stats"] = torch.zeros((mask.shape[0], 2), dtype=torch.int32, device=dev)
             self.Nq = Nq
+            self._vis = self._vis_host = None       # manifolds are per capacity
         return d
 
     def _alloc_mask(self, Nq, W):
@@ -441,6 +450,18 @@ class RedundancyResolver:
             res.chain.edges_build(wedges, d["params"], d["Q"], d["count"], self.Nq, DEFAULT_EDGE_CHECK_TOLERANCE,
                                   mask, stats, d["counters_e"], old_count=old_counts)
 
+    def _edges_launch_raw(self, wedges, params, Q, count, Nq, mask, stats, counters, old_counts):
+        """The same on explicit tensors (params [Nn][dw], Q [Nn][n][Nqp] in one precision) that are not the roadmap's."""
+        torch = self.resolution._torch()
+        res = self.resolution
+        if self.exact_edges and res.torch_dtype == torch.float32:
+            q64, p64 = Q.double(), params.double()
+            res.chain.edges_build_exact(wedges, params.float(), p64, Q.float(), q64, count, Nq, DEFAULT_EDGE_CHECK_TOLERANCE, mask, stats,
+                                        counters, old_count=old_counts)
+        else:
+            res.chain.edges_build(wedges, params.to(res.torch_dtype), Q.to(res.torch_dtype), count, Nq, DEFAULT_EDGE_CHECK_TOLERANCE, mask,
+                                  stats, counters, old_count=old_counts)
+
     def edge_arithmetic(self):
         """'f32+f64 recheck' / 'f64' (exact build, by chain: grr_edges_exact_mode) / 'f32' (exact_edges=False) / 'f64' (float64 resolution)."""
         torch = self.resolution._torch()
@@ -533,11 +554,12 @@ class RedundancyResolver:
         DAG with results equal to the sequential sweep.  order_independent=True selects the semantics of the
         reference's own data-parallel path parallelQSamplingAtP (solver.py:875-897): every attempt is a random
         start, nodes are independent (one launch; this is what shards across GPUs)."""
-        if visibility:
-            raise NotImplementedError("visibility-graph solver is out of scope of the B200 roadmap path")
         torch = self.resolution._torch()
         old_counts = self._dev["count"].clone() if self._dev is not None and self.Nq > 0 else None
         start_total = int(old_counts.sum().item()) if old_counts is not None else 0
+        if visibility and start_total != 0:
+            raise NotImplementedError("visibility=True grows an empty roadmap only (the reference's incremental visibility "
+                                      "path re-runs testAndConnectQccs over existing C-space edges, solver.py:842-848)")
         if biased and start_total != 0:
             raise NotImplementedError("biased re-sampling (solver.py:780-785) is not implemented on the device path")
         N = int(NConfigsPerPoint)
@@ -553,15 +575,32 @@ class RedundancyResolver:
             self._sample_phase(d, N, 0, self.Nw)
         else:
             self._sample_phase_seeded(d, N, bool(seedFromAdjacent))
+        if visibility:
+            # solver.py:836-837: the manifold of each node right after its samples (counted in t_sample, :853);
+            # :842-848: testAndConnectQccs(i, j) for the lower-numbered neighbours j of i -- outer loop over i's components
+            self.constructSelfMotionManifolds(k)
         ev[1].record()
         self.attempts += N
         if connect:
-            self._connect_phase(d, old_counts)
+            if visibility:
+                self._connect_visibility(None, 10, swap=1)
+            else:
+                self._connect_phase(d, old_counts)
         ev[2].record()
         torch.cuda.synchronize(res.torch_device)
         self._invalidate()
         self._collect_stats(d, ev, N, start_total)
+        if visibility:
+            self._visibility_stats()
         return self.stats["t_sample"], self.stats["t_connect"]
+
+    def _visibility_stats(self):
+        v = self._vis
+        self.stats.update(v["stats"])
+        lc = v.get("last_connect")
+        if lc is not None:
+            self.stats.update({"cc_pairs": int(lc["conn"].shape[0]), "cc_pairs_connected": int(lc["nconn"].sum().item()),
+                               "reference_edge_tests": int(lc["ntests"].sum().item())})
 
     def _collect_stats(self, d, ev, N, start_total, n_nodes=None):
         t_sample = ev[0].elapsed_time(ev[1]) * 1e-3
@@ -583,11 +622,9 @@ class RedundancyResolver:
                       "attempts": int(c[_cabi.CNT_IK_SOLVES]), "t_sample": t_sample, "t_connect": t_connect}
 
     def parallelQSamplingAtP(self, params, NConfigs=100, selfmotion=True, k=None, uid=None):
-        """solver.py:875-947 for one workspace point: returns (configs, qccs, qcc_parents).  Self-motion
-        manifolds (selfmotion=True) belong to the visibility solver and are out of scope; with
+        """solver.py:875-947 for one workspace point: returns (configs, qccs, qcc_parents).  selfmotion=True builds the
+        point's self-motion manifold (k=None: all-pairs visibility PRM, else k-nearest; visibility.py); with
         selfmotion=False every config is its own component (qccs singletons, parents -1)."""
-        if selfmotion:
-            raise NotImplementedError("self-motion manifold construction is out of scope; pass selfmotion=False")
         torch = self.resolution._torch()
         res = self.resolution
         N = int(NConfigs)
@@ -604,6 +641,9 @@ class RedundancyResolver:
         res.chain.dedup(q_raw, status, DEDUP_THRESHOLD, q_kept, count, Nq=N)
         c = int(count.item())
         configs = [[float(v) for v in row] for row in res.to_full(q_kept[0, :, :c].T.double().cpu().numpy())] if c else []
+        if selfmotion and c > 0:
+            qccs, parents = self._manifold_at_point(q_kept, count, p, k)
+            return configs, qccs, parents
         return configs, [[i] for i in range(c)], [-1] * c
 
     # ---- connection (solver.py:484-501, 689-755) ---------------------------------------------------
@@ -664,8 +704,6 @@ class RedundancyResolver:
     def connectConfigurationSpace(self, visibility=False, k=None, counts=None):
         """solver.py:700-755 batch variant over every workspace edge.  Returns
         (numNondegenerateEdges, numWorkspaceEdges, self_motion_time, inter_wnode_time)."""
-        if visibility:
-            raise NotImplementedError("visibility-graph solver is out of scope of the B200 roadmap path")
         torch = self.resolution._torch()
         res = self.resolution
         d = self._dev
@@ -673,11 +711,16 @@ class RedundancyResolver:
             return 0, self.E, 0, 0.0
         oc = None
         if counts is not None:
+            assert not visibility, "Can't have counts (incremental construction) plus visibility graph construction"   # solver.py:713
             oc = torch.as_tensor(np.asarray(counts, dtype=np.int32), device=res.torch_device)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         d["counters_e"].zero_()
+        self_motion_time = self.constructSelfMotionManifolds(k) if visibility else 0           # solver.py:701
         e0.record()
-        self._connect_phase(d, oc)
+        if visibility:
+            self._connect_visibility(None, 10, swap=0)                                       # solver.py:725-726
+        else:
+            self._connect_phase(d, oc)
         e1.record()
         torch.cuda.synchronize(res.torch_device)
         self._ecache.clear()
@@ -689,7 +732,9 @@ class RedundancyResolver:
                            "flagged": int(c[_cabi.CNT_FLAGGED]), "flipped": int(c[_cabi.CNT_FLIPPED]),
                            "edge_ik_solves": int(c[_cabi.CNT_IK_SOLVES]), "edge_ik_iters": int(c[_cabi.CNT_IK_ITERS]),
                            "edge_ik_evals": int(c[_cabi.CNT_IK_EVALS])})
-        return nondeg, self.E, 0, e0.elapsed_time(e1) * 1e-3
+        if visibility:
+            self._visibility_stats()
+        return nondeg, self.E, self_motion_time, e0.elapsed_time(e1) * 1e-3
 
     # ---- checkpoint / resume (solver.py:274-348) ------------------------------------------------------
     GW_PICKLE_MAX_EDGES = 5_000_000     # C-space edges above which save() skips Gw_cached.pickle unless asked to
@@ -835,7 +880,7 @@ class RedundancyResolver:
         (a < b) whose allowed tuples are the edge's (iq, jq) set (solver.py:1013-1021).  Returned as plain
         containers: {'variables': {name: domain}, 'constraints': [((name_a, name_b), set((iq, jq)))]}."""
         if visibility:
-            raise NotImplementedError("visibility-graph solver is out of scope of the B200 roadmap path")
+            return self._make_csp_visibility()
         cnt = self.counts()
         variables = {"q_%d" % n: list(range(int(c))) for n, c in enumerate(cnt) if c > 0}
         constraints = []
@@ -880,7 +925,9 @@ class RedundancyResolver:
         """solver.py:1602-1621: assignment -> self.Qsubgraph and the resolution.  Accepts the reference's list over
         the nodes with configs, or one device row (int32 [Nw], -1 = unassigned) of csp.RoadmapCSP."""
         if visibility:
-            raise NotImplementedError("visibility-graph solver is out of scope of the B200 roadmap path")
+            raise NotImplementedError("collapsing a component-level assignment into configurations (collapseQccSubgraph, "
+                                      "solver.py:1024-1600) belongs to the resolution stage and is out of scope; the "
+                                      "visibility roadmap itself and makeCSP(visibility=True) are built (visibility.py)")
         nodes = np.nonzero(self.counts() > 0)[0]
         if hasattr(csp_assignment, "cpu"):
             row = csp_assignment.reshape(-1).cpu().numpy()
@@ -936,7 +983,9 @@ class RedundancyResolver:
         random.choice; here the smallest node id is taken.  heuristic=False skips the first guess (every guess random).
         Returns (bestConflicts, bestMethod, solve_time, collapse_time)."""
         if visibility:
-            raise NotImplementedError("visibility-graph solver is out of scope of the B200 roadmap path")
+            raise NotImplementedError("collapsing a component-level assignment into configurations (collapseQccSubgraph, "
+                                      "solver.py:1024-1600) belongs to the resolution stage and is out of scope; the "
+                                      "visibility roadmap itself and makeCSP(visibility=True) are built (visibility.py)")
         torch = self.resolution._torch()
         t0 = time.time()
         csp = self.csp()

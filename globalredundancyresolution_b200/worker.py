@@ -10,9 +10,10 @@ processes; `Worker.handle(task)` answers the same tuples with the same result tu
   ('test-multi', iw, qlist_i, params_i, jw, qlist_j, params_j, edges) -> [(iw, iq, jw, jq), ...]
   ('kill',)                                                        -> None
 
-Self-motion manifolds belong to the visibility solver (out of scope): 'sample' returns singleton
-components, with which the reference's parallelEdgeConnection (solver.py:949-982) degenerates to testing
-every (a, b) pair once -- which is what 'connect' does here in one launch.
+'sample' builds the point's self-motion manifold like the reference's worker does (parallelQSamplingAtP's default
+selfmotion=True, solver.py:875-947); Worker(selfmotion=False) returns singleton components instead, with which
+parallelEdgeConnection (solver.py:949-982) tests every (a, b) pair once -- the basic solver's all-pairs rule.
+'connect' is parallelEdgeConnection on the given components.
 """
 from __future__ import annotations
 
@@ -20,8 +21,9 @@ from .solver import RedundancyResolver
 
 
 class Worker:
-    def __init__(self, resolution, seed=0):
+    def __init__(self, resolution, seed=0, selfmotion=True):
         self.resolution = resolution
+        self.selfmotion = bool(selfmotion)
         self.rr = RedundancyResolver(resolution, cache=0, seed=seed)
 
     def handle(self, task):
@@ -29,15 +31,11 @@ class Worker:
         res = self.resolution
         if kind == "sample":
             params, Nq, k, uid = task[1], task[2], task[3], task[4]
-            configs, qccs, parents = self.rr.parallelQSamplingAtP(params, NConfigs=Nq, selfmotion=False, k=k, uid=uid)
+            configs, qccs, parents = self.rr.parallelQSamplingAtP(params, NConfigs=Nq, selfmotion=self.selfmotion, k=k, uid=uid)
             return (configs, qccs, parents, uid)
         if kind == "connect":
-            iw, qi, pi, jw, qj, pj = task[1], task[2], task[4], task[5], task[6], task[8]
-            if not qi or not qj:
-                return ([], iw, jw)
-            pairs = [(a, b) for a in range(len(qi)) for b in range(len(qj))]
-            ok = res.validEdgeBatch([qi[a] for a, b in pairs], [qj[b] for a, b in pairs], [pi] * len(pairs), [pj] * len(pairs))
-            return ([p for p, v in zip(pairs, ok) if v], iw, jw)
+            qlist = self.rr.parallelEdgeConnection(task[2], task[3], task[4], task[6], task[7], task[8])
+            return (qlist, task[1], task[5])
         if kind == "test":
             validity = res.validEdge(task[3], task[7], task[4], task[8])
             return (validity, task[1], task[2], task[5], task[6])
@@ -55,9 +53,9 @@ class Worker:
         raise ValueError("unknown task %r" % (kind,))
 
 
-def worker(index, resolution, tasks, results, seed=0):
+def worker(index, resolution, tasks, results, seed=0, selfmotion=True):
     """Queue loop with the reference's signature shape (solver.py:2367): get a task, put its result."""
-    w = Worker(resolution, seed=seed)
+    w = Worker(resolution, seed=seed, selfmotion=selfmotion)
     while True:
         task = tasks.get()
         if task[0] == "kill":

@@ -255,6 +255,66 @@ int grr_csp_descent_sweep(int32_t n_list, const int32_t *node_list, int32_t Nw, 
                           const uint8_t *edge_active, const int32_t *count, int32_t *assignment,
                           const uint8_t *in_order, uint8_t *active, int32_t *changed, void *stream);
 
+/* -- visibility-graph variant.  The reference interleaves the choice of the pairs to test (distance sorts,
+ * union-find, early exits) with validEdge; validEdge is a pure function of the pair, so the predicate runs in batches on the
+ * edge kernels and the calls below replay the reference's sequential choice logic on the verdict bits.
+ *
+ * Same-node pairs: a workspace "edge" (i, i) in the wedges of grr_edges_build / _exact denotes the pairs a > b of node i,
+ * tested as validEdge(q_a, q_b, x_i, x_i) (constructSelfMotionManifold's all-pairs branch, grr/solver.py:645-655); bit
+ * (a, b), a > b, of that edge's mask. */
+
+/* Explicit pair list: list [dev] u64 = {number of entries, pad, then per entry {edge << 32 | a << 16 | b, 0}} with `edge`
+ * an index into wedges; every listed pair is tested with validEdge (graph.py:938-1006) in `dtype` and bit (a, b) of
+ * mask[edge] set or cleared (entries beyond `cap` are ignored and counted in GRR_CNT_FLAG_DROPPED).  Backs the k-nearest
+ * branch of constructSelfMotionManifold (:635-643) and the CC-pair tests of testAndConnectQccs / parallelEdgeConnection. */
+int grr_edges_test_listed(grr_handle_t h, int dtype, const int32_t *wedges, const void *params, const void *q_kept, int32_t Nq,
+                          int32_t Nqp, double epsilon, uint32_t *mask, uint32_t *edge_stats, const uint64_t *list, uint64_t cap,
+                          uint64_t *counters, void *stream);
+
+/* constructSelfMotionManifold (grr/solver.py:623-669) for the Nn nodes of node_list [dev] i32 (NULL: nodes 0..Nn-1), one
+ * warp per node, on self_mask [dev] u32 [Nw][Nq][W] (bit (i, j) = validEdge(q_i, q_j, x, x)).  knn = 0: all-pairs branch
+ * (for i ascending the j < i of other components by increasing (distance, j)); knn > 0: the k nearest configs of the
+ * node by (distance, j), i itself included (KDTree.knearest, grr/utils/kdtree.py:333-339).  Outputs, indexed by node:
+ * label [Nw][Nq] = index of the config's component in `qccs` (components ordered by smallest member; -1 beyond count),
+ * ncc [Nw], parents [Nw][Nq] = `qcc_parents` (depth-first predecessors in the merge forest, roots in index order,
+ * neighbours in merge order, :661-668), members [Nw][Nq] = configs sorted by (component, id), cc_start [Nw][Nq+1] =
+ * first position of each component in members, ntests [Nw] = validEdge calls the reference's loop makes (nullable).
+ * grr_manifold_knn_list emits the pairs the knn branch may test ({node << 32 | i << 16 | j, 0}, list[0] += entries) for
+ * grr_edges_test_listed on wedges[node] = (node, node).  Distances in IEEE double without contraction.  Nq <= 512. */
+int grr_manifold_knn_list(int dtype, int64_t Nn, const int32_t *node_list, int32_t n, int32_t Nq, int32_t Nqp, const void *q_kept,
+                          const int32_t *count, int32_t knn, uint64_t *list, uint64_t cap, void *stream);
+int grr_manifold_components(int dtype, int64_t Nn, const int32_t *node_list, int32_t n, int32_t Nq, int32_t Nqp, const void *q_kept,
+                            const int32_t *count, const uint32_t *self_mask, int32_t knn, int32_t *label, int32_t *ncc,
+                            int32_t *parents, int32_t *members, int32_t *cc_start, int32_t *ntests, void *stream);
+
+/* testAndConnectQccs (grr/solver.py:517-561) / parallelEdgeConnection (:949-982) on E workspace edges.
+ * grr_qcc_candidates: for every CC pair (ci, cj) of every edge, cand [dev] i32 [(cc_off[e] + ci*ncc[jw] + cj) * 2T + slot]:
+ * slots [0, T) = the pairs a << 16 | b with the T = max_tests smallest (robot.distance, a, b) (:534-546), slots [T, 2T) =
+ * of the remaining pairs the T with the smallest (grr_pair_hash, a, b) -- a keyed hash stands in for random.sample (:551);
+ * -1 = no such pair.  cc_off [dev] i64 [E+1] = exclusive scan of ncc[iw]*ncc[jw] (caller computes); node_uid as in
+ * grr_ik_sample (nullable: node index).
+ * grr_qcc_wave: appends to `list` (format of grr_edges_test_listed) slots [slot0, slot1) of every CC pair none of whose
+ * earlier slots has its bit set in tested_mask [dev] u32 [E][Nq][W] (the mask grr_edges_test_listed writes).
+ * grr_qcc_connect: the reference's loops on the verdict bits; mode 0 = testAndConnectQccs (a component of node i stops at
+ * the first component of node j it connects to, :548-550), mode 1 = parallelEdgeConnection (every CC pair).  Sets bit
+ * (a, b) of mask [dev] u32 [E][Nq][W] for every connection; conn [dev] i32 [cc_off[E]] = a << 16 | b, -1 (none) or -2 (not
+ * reached); nconn [dev] i32 [E] = numConnected; ntests [dev] i32 [E] = validEdge calls of the reference's loops (nullable).
+ * swap = 0: the outer loop runs over the components of wedges[e][0] (connectConfigurationSpace calls testAndConnectQccs(iw, jw)
+ * with iw < jw, :725-726); swap = 1: over those of wedges[e][1] (sampleConfigurationSpace calls it with the node being
+ * sampled first and its lower-numbered neighbour second, :842-848).  Candidates and conn then hold (outer config) << 16 |
+ * (inner config); list entries, tested_mask and mask stay in the orientation of wedges. */
+int grr_qcc_candidates(int dtype, int64_t E, const int32_t *wedges, int32_t n, int32_t Nq, int32_t Nqp, const void *q_kept,
+                       const int32_t *node_uid, const int32_t *ncc, const int32_t *members, const int32_t *cc_start,
+                       const int64_t *cc_off, int32_t max_tests, uint64_t seed, int32_t swap, int32_t *cand, void *stream);
+int grr_qcc_wave(int64_t E, const int32_t *wedges, const int32_t *ncc, const int64_t *cc_off, int32_t max_tests, const int32_t *cand,
+                 int32_t Nq, const uint32_t *tested_mask, int32_t slot0, int32_t slot1, int32_t swap, uint64_t *list, uint64_t cap,
+                 void *stream);
+int grr_qcc_connect(int64_t E, const int32_t *wedges, const int32_t *ncc, const int64_t *cc_off, int32_t max_tests, const int32_t *cand,
+                    int32_t Nq, const uint32_t *tested_mask, int32_t mode, int32_t swap, uint32_t *mask, int32_t *conn,
+                    int32_t *nconn, int32_t *ntests, void *stream);
+/* the hash of grr_qcc_candidates (host function; lets a caller or a test reproduce the sampled candidates) */
+uint32_t grr_pair_hash(uint64_t seed, uint32_t iw, uint32_t jw, uint32_t a, uint32_t b);
+
 /* -- measurement support: FP32 FMA peak microbenchmark (returns achieved TFLOP/s; synchronous). */
 int grr_fp32_peak(int device, double *tflops_out);
 /* same with the packed sm_100 FFMA2 instruction (two FP32 FMAs per instruction per lane) */

@@ -65,7 +65,33 @@ def construct_self_motion_manifold(n, dist, valid):
                     ccs.merge(i, j)
                     adj[i].append(j)
                     adj[j].append(i)
-    parents = [-1] * n                                                    # :661-666
+    return ccs.components(), _dfs_parents(n, adj), tests
+
+
+def construct_self_motion_manifold_knn(n, dist, valid, k):
+    """solver.py:635-643 (k given): for every config the k nearest of the node's configs -- KDTree.knearest
+    (grr/utils/kdtree.py:333-339, results sorted by distance; the query point itself is in the tree and comes back first)
+    -- each tested when it lies in another component.  valid(i, j) is called with i the query config."""
+    ccs = DisjointSet()
+    adj = {i: [] for i in range(n)}
+    for i in range(n):
+        ccs.add(i)
+    tests = []
+    for i in range(n):
+        knn = sorted((dist(i, j), j) for j in range(n))[:k]
+        for d, j in knn:
+            if not ccs.same(i, j):
+                tests.append((i, j))
+                if valid(i, j):
+                    ccs.merge(i, j)
+                    adj[i].append(j)
+                    adj[j].append(i)
+    return ccs.components(), _dfs_parents(n, adj), tests
+
+
+def _dfs_parents(n, adj):
+    """nx.dfs_edges(Gccs) -> parentList (solver.py:661-666): roots in index order, neighbours in insertion order."""
+    parents = [-1] * n
     seen = set()
     for root in range(n):
         if root in seen:
@@ -82,38 +108,42 @@ def construct_self_motion_manifold(n, dist, valid):
                     break
             else:
                 stack.pop()
-    return ccs.components(), parents, tests
+    return parents
 
 
 def _cc_pair(qicc, qjcc, dist, valid, max_tests, sample):
     """The body shared by :529-558 and :954-980: candidates of one CC pair in increasing distance, at most max_tests of
-    them, then up to max_tests more drawn by `sample` from the rest.  Returns the connecting (a, b) or None."""
+    them, then up to max_tests more drawn by `sample` from the rest.  Returns (the connecting (a, b) or None, the phase
+    that found it: 1 = nearest candidates, 2 = sampled ones)."""
     distances = sorted((dist(a, b), a, b) for a in qicc for b in qjcc)
     cnt = 0
     for d, a, b in distances:
         cnt += 1
         if valid(a, b):
-            return (a, b)
+            return (a, b), 1
         if cnt >= max_tests:
             break
     if len(distances) > max_tests:
         rest = distances[max_tests:]
         for (d, a, b) in sample(rest, min(max_tests, len(rest))):
             if valid(a, b):
-                return (a, b)
-    return None
+                return (a, b), 2
+    return None, 0
 
 
 def test_and_connect_qccs(iqccs, jqccs, dist, valid, sample, max_tests=10):
-    """solver.py:517-561: for every CC of node i, the CCs of node j in order until one connects (`break`, :548-550).
-    Returns the list of added C-space edges (a, b); its length is the reference's return value numConnected."""
+    """solver.py:517-561: for every CC of node i, the CCs of node j in order; a connection by one of the nearest
+    candidates ends the loop over node j's CCs (`break`, :548-550), a connection by a sampled candidate does not (:551-558
+    has no break).  Returns the list of added C-space edges (a, b); its length is the reference's return value
+    numConnected."""
     added = []
     for qicc in iqccs:
         for qjcc in jqccs:
-            hit = _cc_pair(qicc, qjcc, dist, valid, max_tests, sample)
+            hit, phase = _cc_pair(qicc, qjcc, dist, valid, max_tests, sample)
             if hit is not None:
                 added.append(hit)
-                break
+                if phase == 1:
+                    break
     return added
 
 
@@ -122,7 +152,7 @@ def parallel_edge_connection(iqccs, jqccs, dist, valid, sample, max_tests=20):
     qlist = []
     for qicc in iqccs:
         for qjcc in jqccs:
-            hit = _cc_pair(qicc, qjcc, dist, valid, max_tests, sample)
+            hit, phase = _cc_pair(qicc, qjcc, dist, valid, max_tests, sample)
             if hit is not None:
                 qlist.append(hit)
     return qlist

@@ -96,10 +96,12 @@ def test_make_program_builds_reference_sized_graphs():
     assert rr.Gw.node[5]["params"] == res.Gw.node[5]["params"]
     with pytest.raises(KeyError):
         rr.Gw.edge[0][500]
-    with pytest.raises(NotImplementedError):
+    # no CUDA device here: every compute entry point fails loudly instead of falling back to the CPU
+    with pytest.raises(grr._cabi.GrrError):
         rr.sampleConfigurationSpace(4, visibility=True)
     with pytest.raises(NotImplementedError):
-        rr.parallelQSamplingAtP([1, 0, 1], 4)          # selfmotion=True default -> out of scope
+        rr.decodeCSPAssignment([0], visibility=True)   # collapse of component-level assignments: resolution stage
+    assert rr.getSelfMotionCcsStats()["configuredW"] == 0
 
 
 def test_graph_class_is_networkx1_flavoured():
