@@ -30,7 +30,7 @@ EXPORTS = [
     "grr_scatter_node_blocks", "grr_halo_exchange", "grr_csp_random_assignment", "grr_csp_conflicts", "grr_csp_descent_sweep",
     "grr_fp32_peak", "grr_fp32x2_peak",
     "grr_edges_test_listed", "grr_manifold_knn_list", "grr_manifold_components", "grr_qcc_candidates", "grr_qcc_wave",
-    "grr_qcc_connect", "grr_pair_hash",
+    "grr_qcc_connect", "grr_pair_hash", "grr_ik_sample_sweep",
 ]
 
 
@@ -81,6 +81,8 @@ def lib():
     L.grr_edges_build_exact.argtypes = [vp, i64, vp, vp, vp, vp, vp, vp, vp, i32, i32, dbl, vp, vp, vp, vp]
     L.grr_set_flag_scale.argtypes = [vp, dbl]
     L.grr_edges_exact_mode.argtypes = [vp]
+    L.grr_ik_sample_sweep.argtypes = [vp, C.c_int, i64, vp, i32, i32, vp, vp, vp, vp, vp, vp, i32, vp, u64, i32, i32, vp, vp, dbl, vp,
+                                      vp, vp]
     L.grr_edges_test_listed.argtypes = [vp, C.c_int, vp, vp, vp, i32, i32, dbl, vp, vp, vp, u64, vp, vp]
     L.grr_manifold_knn_list.argtypes = [C.c_int, i64, vp, i32, i32, i32, vp, vp, i32, vp, u64, vp]
     L.grr_manifold_components.argtypes = [C.c_int, i64, vp, i32, i32, i32, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, vp]
@@ -243,6 +245,21 @@ class ChainHandle:
                                         _ptr(q_kept), q_kept.shape[2], _ptr(count), C.c_uint64(int(seed) & (2 ** 64 - 1)),
                                         int(sample_offset), 1 if seed_from_adjacent else 0, _ptr(q_raw), _ptr(status),
                                         _ptr(nadj), _ptr(counters), _stream(q_raw.device)), "grr_ik_sample_level")
+
+    def ik_sample_sweep(self, order, Nq, params, node_uid, lower_ptr, lower_idx, degree, q_kept, count, seed, sample_offset,
+                        seed_from_adjacent, q_rand, status_rand, thresh, ready, counters=None):
+        """The seeded sweep as one dataflow launch.  Returns False when a node's working set does not fit shared memory
+        (the caller then runs the level-by-level launches)."""
+        global LAUNCHES
+        rc = lib().grr_ik_sample_sweep(self._h, dtype_code(q_rand.dtype), order.shape[0], _ptr(order), int(Nq), q_rand.shape[2],
+                                       _ptr(params), _ptr(node_uid), _ptr(lower_ptr), _ptr(lower_idx), _ptr(degree), _ptr(q_kept),
+                                       q_kept.shape[2], _ptr(count), C.c_uint64(int(seed) & (2 ** 64 - 1)), int(sample_offset),
+                                       1 if seed_from_adjacent else 0, _ptr(q_rand), _ptr(status_rand), float(thresh), _ptr(ready),
+                                       _ptr(counters), _stream(q_rand.device))
+        if rc == -5:
+            return False
+        check(rc, "grr_ik_sample_sweep")
+        return True
 
     def dedup_sweep(self, node_list, Nq, q_seed, status_seed, nadj, seed_from_adjacent, q_rand, status_rand, thresh, q_kept,
                     count, counters=None):

@@ -195,6 +195,222 @@ k_ik_level(const __grid_constant__ ChainDev<Real, kMaxJ> c, long long total, con
 }
 
 // ------------------------------------------------------------------------------------------
+// S1 as ONE launch: the whole sequential sweep of sampleConfigurationSpace (solver.py:773-835) as a dataflow over the
+// dependency DAG.  Node i needs the final qlists of its lower-numbered neighbours only; persistent CTAs claim nodes in
+// level order (order[] = nodes sorted by level(i) = 1 + max level of the lower neighbours, so everything a claimed node
+// waits for was claimed earlier by a CTA that is resident and running), wait on the neighbours' ready flags
+// (acquire), run the node's numAdjacent seeded attempts as lane machines, filter seeded + random-start results
+// against the node's kept list in the sweep's order, publish the list and release the node's flag.  The random-start
+// attempts do not depend on other nodes and are precomputed for the whole graph (k_ik_instances), as in the
+// level-by-level version this replaces (280 levels x 2 launches on BASELINE config 2).
+// The duplicate filter of a node is done in two steps so that its serial part is short: all candidate-candidate and
+// candidate-kept distances at once (bit matrix `close`), then one warp walks the candidates in order.
+// Reads of other nodes' count / configs go through L2 (__ldcg): they were written by other SMs during this launch.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ int ld_acquire_(const int32_t *p) {
+  int v;
+#ifdef __CUDA_ARCH__
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+#else
+  v = *p;
+#endif
+  return v;
+}
+__device__ __forceinline__ void st_release_(int32_t *p, int v) {
+#ifdef __CUDA_ARCH__
+  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+#else
+  *p = v;
+#endif
+}
+
+template <typename Real, int M, bool PL>
+__global__ void __launch_bounds__(128)
+k_sweep_dataflow(const __grid_constant__ ChainDev<Real, kMaxJ> c, long long Nn, const int32_t *__restrict__ order, int Nq,
+                 int Nqr, const Real *__restrict__ params, const int32_t *__restrict__ uid,
+                 const int32_t *__restrict__ lower_ptr, const int32_t *__restrict__ lower_idx,
+                 const int32_t *__restrict__ degree, Real *Qk, int Nqk, int32_t *count, unsigned long long seed,
+                 int sample_offset, int seed_from_adjacent, const Real *__restrict__ q_rand,
+                 const uint8_t *__restrict__ st_rand, Real thresh, int32_t *ready, unsigned long long *work,
+                 unsigned long long *counters) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int n = c.n, dw = (c.mode == 2 ? 6 : 3);
+  const int T = blockDim.x, tid = threadIdx.x, lane = tid & 31;
+  const int NqS = (Nq + 3) & ~3, Cmax = 2 * Nq, Wc = (Cmax + 31) >> 5;
+  Real *lanes = reinterpret_cast<Real *>(smem_raw);
+  Real *cseed = lanes + (size_t)T * lane_reals<col_rows(M, PL)>(n);           // [n][NqS] seeded results
+  uint32_t *close = reinterpret_cast<uint32_t *>(cseed + (size_t)n * NqS);     // [Cmax][Wc] candidate s close to candidate t < s
+  int32_t *clist = reinterpret_cast<int32_t *>(close + (size_t)Cmax * Wc);     // [Cmax] ok candidates in sweep order: s (seeded) / Nq + s (random)
+  int32_t *slot = clist + Cmax;                                                // [Cmax] position in the kept list or -1
+  uint8_t *sst = reinterpret_cast<uint8_t *>(slot + Cmax);                     // [NqS] status of the seeded attempts
+  uint8_t *cold = sst + NqS;                                                   // [Cmax] candidate close to an already kept config
+  __shared__ long long s_pos;
+  __shared__ int s_nok, s_kept;
+  LaneMem<Real, col_rows(M, PL)> mem;
+  mem.init(lanes + tid, T, n);
+  for (int j = 0; j < lane_reals<col_rows(M, PL)>(n); j++) mem.base[j * mem.T] = 0;
+  LaneIK<Real, M> L;
+  lane_begin_mem(L, mem);
+  Target<Real, M> tg;
+  tg.x[0] = tg.x[1] = tg.x[2] = 0;
+  if (M == 6) { for (int k = 0; k < 9; k++) tg.R[k] = (k % 4 == 0) ? Real(1) : Real(0); }
+  LaneCounters cnt;
+  for (;;) {
+    __syncthreads();
+    if (tid == 0) s_pos = (long long)atomicAdd(work, 1ull);
+    __syncthreads();
+    const long long pos = s_pos;
+    if (pos >= Nn) break;
+    const int node = order[pos];
+    const int lp0 = lower_ptr[node], nlow = lower_ptr[node + 1] - lp0;
+    // wait for the lower-numbered neighbours (solver.py:773: the sweep visits nodes in increasing order)
+    for (int k = tid; k < nlow; k += T) {
+      const int32_t *f = ready + lower_idx[lp0 + k];
+      while (ld_acquire_(f) == 0) __nanosleep(64);
+    }
+    __syncthreads();
+    int na = 0;
+    for (int k = 0; k < nlow; k++) na += (__ldcg(count + lower_idx[lp0 + k]) > 0);                          // solver.py:776
+    const int deg = degree[node];
+    const int numAdjRef = deg > 0 ? (int)((double)na / (double)deg * (double)Nq) : 0;                      // :777-778
+    const int numAdjacent = seed_from_adjacent ? numAdjRef : 0;                                             // :790 (seeded attempts run)
+    Real w[6];
+    for (int k = 0; k < dw; k++) w[k] = params[(long long)node * dw + k];
+    target_from_params<Real, M, kMaxJ>(c, w, tg);
+    // ---- seeded attempts (solver.py:786-815): lane machines, attempt s on lane s % T ----
+    int s_mine = tid;                 // next attempt of this lane
+    int s_run = -1;                   // attempt in flight
+    for (;;) {
+      if (s_run < 0 && s_mine < numAdjacent) {
+        s_run = s_mine; s_mine += T;
+        uint32_t r[4];
+        philox4x32_10((uint32_t)uid[node], (uint32_t)(sample_offset + s_run), 0u, 1u, (uint32_t)seed, (uint32_t)(seed >> 32), r);
+        int pick = (int)(r[0] % (uint32_t)na), jn = -1;
+        for (int k = 0; k < nlow; k++) {
+          const int cand = lower_idx[lp0 + k];
+          if (__ldcg(count + cand) > 0) { if (pick == 0) { jn = cand; break; } pick--; }
+        }
+        const int cfg = (int)(r[1] % (uint32_t)__ldcg(count + jn));
+        const Real *srcq = Qk + ((long long)jn * n) * Nqk + cfg;
+        Real *xo = mem.xold();
+        for (int j = 0; j < n; j++) xo[j * mem.T] = __ldcg(srcq + (long long)j * Nqk);
+        lane_begin_mem(L, mem);
+      }
+      if (__all_sync(0xffffffffu, s_run < 0)) break;
+      PassOut<Real, M> o;
+      if constexpr (PL) lane_pass_planar<Real, false>(c, tg, L, mem, nullptr, 0, o);
+      else lane_pass<Real, M, false>(c, tg, L, mem, nullptr, 0, o);
+      const int st = lane_step<Real, M, PL>(c, L, mem, o, s_run >= 0);
+      if (s_run >= 0 && st != IK_RUNNING) {
+        for (int j = 0; j < n; j++) cseed[j * NqS + s_run] = L.res[j * mem.T];
+        sst[s_run] = (uint8_t)st;
+        cnt.iters += L.it; cnt.evals += L.evals;
+        s_run = -1;
+        lane_begin_mem(L, mem);
+      }
+    }
+    __syncthreads();
+    // ---- candidates in the sweep's order: seeded, then the first Nq - numAdjacent + numFailed random-start results ----
+    if (tid < 32) {
+      int nfail = 0;
+      for (int s = lane; s < numAdjacent; s += 32) nfail += (sst[s] != 0);
+      nfail = __reduce_add_sync(0xffffffffu, nfail);
+      const int nseed = numAdjacent;
+      // solver.py:779,817: numRandomSamples = NConfigsPerPoint - numAdjacentSamples (also when seeding is off) + numFailed
+      const int nrand = Nq - numAdjRef + nfail;
+      const uint8_t *str = st_rand + (long long)node * Nqr;
+      int nok = 0;
+      for (int base = 0; base < nseed + nrand; base += 32) {
+        const int ci = base + lane;
+        bool ok = false;
+        if (ci < nseed) ok = (sst[ci] == 0);
+        else if (ci < nseed + nrand) ok = (str[ci - nseed] == 0);
+        const unsigned m = __ballot_sync(0xffffffffu, ok);
+        if (ok) clist[nok + __popc(m & ((1u << lane) - 1u))] = (ci < nseed) ? ci : Nq + (ci - nseed);
+        nok += __popc(m);
+      }
+      if (lane == 0) {
+        s_nok = nok;
+        if (counters) {
+          atomicAdd(counters + GRR_CNT_IK_SOLVES, (unsigned long long)(nseed + nrand));
+          atomicAdd(counters + GRR_CNT_IK_OK, (unsigned long long)nok);
+        }
+      }
+    }
+    for (int k = tid; k < Cmax * Wc; k += T) close[k] = 0;
+    for (int k = tid; k < Cmax; k += T) cold[k] = 0;
+    __syncthreads();
+    const int C = s_nok;
+    const int kept0 = count[node];                // this node's own list: written by this CTA only (or before the launch)
+    Real *out = Qk + (long long)node * n * Nqk;
+    const Real *randq = q_rand + (long long)node * n * Nqr;
+    auto cand_ptr = [&](int ci, int &stride) -> const Real * {
+      const int id = clist[ci];
+      if (id < Nq) { stride = NqS; return cseed + id; }
+      stride = Nqr; return randq + (id - Nq);
+    };
+    // all distances at once: (candidate s, candidate t < s) and (candidate s, already kept k)
+    const int npair = C * (C - 1) / 2;
+    for (int pidx = tid; pidx < npair + C * kept0; pidx += T) {
+      int sidx, tidx;
+      bool vs_old = pidx >= npair;
+      if (!vs_old) {
+        // row s has s entries: s = floor((1 + sqrt(1 + 8 p)) / 2)
+        sidx = (int)((1.0f + sqrtf(1.0f + 8.0f * (float)pidx)) * 0.5f);
+        while (sidx * (sidx - 1) / 2 > pidx) sidx--;
+        while ((sidx + 1) * sidx / 2 <= pidx) sidx++;
+        tidx = pidx - sidx * (sidx - 1) / 2;
+      } else { sidx = (pidx - npair) / kept0; tidx = (pidx - npair) - sidx * kept0; }
+      int ss, ts;
+      const Real *a = cand_ptr(sidx, ss);
+      Real d2 = 0;
+      if (!vs_old) {
+        const Real *b = cand_ptr(tidx, ts);
+        for (int j = 0; j < n; j++) { Real d = a[(long long)j * ss] - b[(long long)j * ts]; d2 += d * d; }
+        if (sqrt_(d2) < thresh) atomicOr(&close[sidx * Wc + (tidx >> 5)], 1u << (tidx & 31));
+      } else {
+        for (int j = 0; j < n; j++) { Real d = a[(long long)j * ss] - out[j * Nqk + tidx]; d2 += d * d; }
+        if (sqrt_(d2) < thresh) cold[sidx] = 1;
+      }
+    }
+    __syncthreads();
+    // one warp walks the candidates in order (first wins, solver.py:802-813,824-835)
+    if (tid < 32) {
+      uint32_t keepw[4] = {0, 0, 0, 0};        // lane owns words lane, lane + 32, ... of the keep mask (Wc <= 128)
+      int kept = kept0;
+      for (int sidx = 0; sidx < C; sidx++) {
+        bool hit = false;
+#pragma unroll
+        for (int q = 0; q < 4; q++) { const int wd = lane + 32 * q; if (wd < Wc) hit |= (close[sidx * Wc + wd] & keepw[q]) != 0; }
+        hit = __any_sync(0xffffffffu, hit) || cold[sidx];
+        const bool take = !hit && kept < Nqk;
+        if (take) {
+          const int wd = sidx >> 5;
+#pragma unroll
+          for (int q = 0; q < 4; q++) if (wd == lane + 32 * q) keepw[q] |= 1u << (sidx & 31);
+        }
+        if (lane == 0) slot[sidx] = take ? kept : -1;
+        kept += take;
+      }
+      if (lane == 0) s_kept = kept;
+    }
+    __syncthreads();
+    for (int k = tid; k < C * n; k += T) {
+      const int sidx = k / n, j = k - sidx * n;
+      const int sl = slot[sidx];
+      if (sl >= 0) { int ss; const Real *a = cand_ptr(sidx, ss); out[j * Nqk + sl] = a[(long long)j * ss]; }
+    }
+    __syncthreads();
+    if (tid == 0) {
+      count[node] = s_kept;
+      __threadfence();
+      st_release_(ready + node, 1);
+    }
+  }
+  cnt.flush(counters);
+}
+
+// ------------------------------------------------------------------------------------------
 // V1 state of one pair held by one lane: validEdgeLinear (graph.py:938-1006) in closed form:
 // valid <=> every interpolated IK k=1..Ndivs (seed lerp(qa,qb,u_k), target winterp(wa,wb,u_k))
 // converges and every consecutive distance (qa, q_1, ..., q_Ndivs, qb) is <= thr.  The BFS order of
@@ -1021,6 +1237,42 @@ struct Impl {
     else rc = launch(k_ik_level<Real, M, false>);
     if (rc) return rc;
     return check_launch("k_ik_level");
+  }
+  // the whole seeded sweep as one dataflow launch (see k_sweep_dataflow); returns -5 if a node's working set does not
+  // fit shared memory (the caller falls back to the level-by-level launches)
+  static int ik_sweep(const HostChain &h, long long Nn, const int32_t *order, int Nq, int Nqr, const void *params,
+                      const int32_t *uid, const int32_t *lower_ptr, const int32_t *lower_idx, const int32_t *degree, void *Qk,
+                      int Nqk, int32_t *count, unsigned long long seed, int sample_offset, int seed_from_adjacent,
+                      const void *q_rand, const uint8_t *st_rand, double thresh, int32_t *ready, unsigned long long *work,
+                      unsigned long long *counters, cudaStream_t st) {
+    if (Nn <= 0) return 0;
+    Chain c; fill_chain(h, c);
+    const int NqS = (Nq + 3) & ~3, Cmax = 2 * Nq, Wc = (Cmax + 31) / 32;
+    if (Wc > 128) return -5;
+    const size_t fixed = (size_t)h.n * NqS * sizeof(Real) + (size_t)Cmax * Wc * 4 + (size_t)Cmax * 8 + NqS + Cmax + 64;
+    int threads = Nq > 128 ? 128 : 64;
+    const size_t per_lane = (size_t)h.n * (4 + mc(h)) * sizeof(Real);
+    while (threads > 32 && fixed + threads * per_lane > 110 * 1024) threads -= 32;
+    const size_t smem = fixed + threads * per_lane;
+    if (smem > kSmemBudget - 2048) return -5;
+    cudaMemsetAsync(work, 0, sizeof(unsigned long long), st);
+    cudaMemsetAsync(ready, 0, sizeof(int32_t) * (size_t)Nn, st);
+    auto launch = [&](auto kern) -> int {
+      if (set_smem(kern, smem, "k_sweep_dataflow")) return -2;
+      int per_sm = 0;
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem) != cudaSuccess || per_sm < 1) return -5;
+      long long ctas = (long long)sm_count(h.device) * per_sm;          // persistent: every CTA must be resident (it may wait)
+      if (ctas > Nn) ctas = Nn;
+      kern<<<(unsigned)ctas, threads, smem, st>>>(c, Nn, order, Nq, Nqr, (const Real *)params, uid, lower_ptr, lower_idx, degree,
+                                                  (Real *)Qk, Nqk, count, seed, sample_offset, seed_from_adjacent,
+                                                  (const Real *)q_rand, st_rand, (Real)thresh, ready, work, counters);
+      return 0;
+    };
+    int rc;
+    if constexpr (kHasPlanar) rc = planar(h) ? launch(k_sweep_dataflow<Real, M, true>) : launch(k_sweep_dataflow<Real, M, false>);
+    else rc = launch(k_sweep_dataflow<Real, M, false>);
+    if (rc) return rc;
+    return check_launch("k_sweep_dataflow");
   }
   static int ik_solve_batch(const HostChain &h, long long P, const void *targets, void *q, uint8_t *status,
                             uint8_t *iters, void *resid, unsigned long long *work, unsigned long long *counters,

@@ -155,6 +155,7 @@ class RedundancyResolver(VisibilityMixin):
         self.resolution = resolution
         self.sample_dtype = sample_dtype
         self.exact_edges = bool(exact_edges)
+        self.sweep_mode = "auto"     # seeded sweep: "auto" (one dataflow launch, level launches if it does not fit) / "dataflow" / "levels"
         self.robot = resolution.robot
         self.cachesize = cache
         self.cacheloc = cacheloc
@@ -527,6 +528,15 @@ class RedundancyResolver(VisibilityMixin):
         res.chain.ik_sample(d["params_s"], d["uid"], self.seed, q_rand, st_rand, None, scratch, Nq=N, sample_offset=self.attempts)
         d["counters"][_cabi.CNT_IK_ITERS] += scratch[_cabi.CNT_IK_ITERS]       # work done (includes unused attempts)
         d["counters"][_cabi.CNT_IK_EVALS] += scratch[_cabi.CNT_IK_EVALS]
+        self._last_raw = (q_rand, st_rand, None)
+        if self.sweep_mode != "levels":
+            # one dataflow launch over the dependency DAG (k_sweep_dataflow)
+            ready = torch.empty(self.Nw, dtype=torch.int32, device=dev)
+            if res.chain.ik_sample_sweep(lv["order"], N, d["params_s"], d["uid"], lv["lower_ptr"], lv["lower_idx"], lv["degree"],
+                                         d["Qs"], d["count"], self.seed, self.attempts, seed_from_adjacent, q_rand, st_rand,
+                                         DEDUP_THRESHOLD, ready, d["counters"]):
+                return
+            assert self.sweep_mode != "dataflow", "the dataflow sweep does not fit shared memory for this Nq"
         q_seed = torch.empty((Lmax, n, Nqp), dtype=sdt, device=dev)
         st_seed = torch.empty((Lmax, Nqp), dtype=torch.uint8, device=dev)
         nadj = torch.zeros(Lmax, dtype=torch.int32, device=dev)

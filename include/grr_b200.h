@@ -121,6 +121,17 @@ int grr_ik_sample(grr_handle_t h, int dtype, int64_t Nw, int32_t Nq, int32_t Nqp
  *   grr_dedup_sweep: greedy 1e-2 filter over the node's seeded results, then its first Nq - nadj + numFailed
  *     precomputed random results (q_rand [dev] Real [Nw][n][Nqr], status_rand [dev] u8 [Nw][Nqr]), appended to
  *     q_kept/count in place; adds the attempts the sweep ran / converged to counters. */
+/* The whole sweep as ONE launch (a dataflow over the same DAG): persistent CTAs claim nodes in the order `order` [dev] i32
+ * [Nw] (nodes sorted by level, level(i) = 1 + max level of the lower-numbered neighbours), wait on the neighbours' flags in
+ * ready [dev] i32 [Nw] (zeroed by the call), run the node's seeded attempts, filter seeded + precomputed random-start
+ * results (q_rand / status_rand as for grr_dedup_sweep) in the sweep's order into q_kept / count and release the node's
+ * flag.  Result identical to the level-by-level calls below, which it replaces when a node's working set (its
+ * candidates' distance bit matrix) fits shared memory; returns -5 otherwise. */
+int grr_ik_sample_sweep(grr_handle_t h, int dtype, int64_t Nw, const int32_t *order, int32_t Nq, int32_t Nqr, const void *params,
+                        const int32_t *node_uid, const int32_t *lower_ptr, const int32_t *lower_idx, const int32_t *degree,
+                        void *q_kept, int32_t Nqp_kept, int32_t *count, uint64_t seed, int32_t sample_offset,
+                        int32_t seed_from_adjacent, const void *q_rand, const uint8_t *status_rand, double thresh, int32_t *ready,
+                        uint64_t *counters, void *stream);
 int grr_ik_sample_level(grr_handle_t h, int dtype, int64_t L, const int32_t *node_list, int32_t Nq, int32_t Nqr,
                         const void *params, const int32_t *node_uid, const int32_t *lower_ptr, const int32_t *lower_idx,
                         const int32_t *degree, const void *q_kept, int32_t Nqp_kept, const int32_t *count, uint64_t seed,
