@@ -3,6 +3,7 @@
 #pragma once
 #include "grr_device.cuh"
 #include "grr_lane.cuh"
+#include "grr_lane2.cuh"
 #include "grr_host.h"
 #include "grr_fill.cuh"
 #include <stdlib.h>
@@ -511,7 +512,8 @@ GRR_DEV int pair_advance(const ChainT &c, LaneMem<Real, MC> &mem, Real s2, Real 
 // Serves the near-tie requests of a warp's lanes (lane_tie_operands): for each requesting lane the whole warp computes
 // the directional derivative Dc = sum over the free joints of (col_j . z) p_j and the `same` test, one joint per lane,
 // reading the requester's shared-memory column.  All 32 lanes must call.
-template <typename Real, int M, bool PL, typename ChainT>
+// LS = shared-memory columns per thread (1; 2 in the two-slot kernel, where a slot's columns of neighbouring threads are 2 apart)
+template <typename Real, int M, bool PL, int LS = 1, typename ChainT>
 __device__ __forceinline__ void warp_tie_service(const ChainT &c, LaneIK<Real, M> &L, const LaneMem<Real, col_rows(M, PL)> &mem,
                                                  bool running) {
 #ifdef __CUDA_ARCH__
@@ -525,7 +527,7 @@ __device__ __forceinline__ void warp_tie_service(const ChainT &c, LaneIK<Real, M
 #pragma unroll
     for (int r = 0; r < MC; r++) z[r] = __shfl_sync(0xffffffffu, L.ny[r], src);
     const int oxo = __shfl_sync(0xffffffffu, mem.o_xold, src), oxc = __shfl_sync(0xffffffffu, mem.o_xcur, src);
-    const Real *base = mem.base + (src - lane);            // lanes of a warp are adjacent columns of the [element][lane] layout
+    const Real *base = mem.base + LS * (src - lane);       // lanes of a warp are adjacent columns of the [element][lane] layout
     Real part = 0;
     bool same = true;
     for (int j = lane; j < c.n; j += 32) tie_joint<Real, MC>(c, base, mem.T, oxo, oxc, z, j, part, same);
@@ -794,6 +796,190 @@ k_edges_build(const __grid_constant__ ChainDev<Real, kMaxJ> c, const int32_t *__
   for (int k = threadIdx.x; k < Nq * Wd; k += blockDim.x) { const uint32_t w = smask[k]; mrow[k] = w; nbits += __popc(w); }
   if (edge_stats) {
     // {pairs tested in this call, valid bits now stored for the edge}
+    const unsigned wbits = __reduce_add_sync(0xffffffffu, nbits);
+    if ((threadIdx.x & 31) == 0 && wbits) atomicAdd(&s_bits, wbits);
+    __syncthreads();
+    if (threadIdx.x == 0) { edge_stats[2 * e] = s_tested; edge_stats[2 * e + 1] = s_bits; }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// E1/E3, dense roadmaps of the planar small-angle chains (BASELINE config 2): k_edges_build with TWO lane machines
+// (slots) per thread on the packed FP32 instructions (grr_lane2.cuh).  Same claiming, queueing, verdict and near-tie
+// logic per slot; the chain pass serves both slots at once.
+// ------------------------------------------------------------------------------------------
+template <bool FLAG>
+__global__ void __launch_bounds__(256)
+k_edges_build2(const __grid_constant__ ChainDev<float, kMaxJ> c, const int32_t *__restrict__ wedges,
+               const float *__restrict__ params, const float *__restrict__ q_kept, const int32_t *__restrict__ count,
+               const int32_t *__restrict__ old_count, int Nq, int Nqp, float epsilon, uint32_t *mask,
+               uint32_t *__restrict__ edge_stats, unsigned long long *counters, unsigned long long *flist,
+               unsigned long long fcap) {
+  using Real = float;
+  constexpr int M = 3;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int n = c.n;
+  const int Wd = (Nq + 31) >> 5;
+  Real *sa = reinterpret_cast<Real *>(smem_raw);
+  Real *sb = sa + n * Nqp;
+  uint32_t *smask = reinterpret_cast<uint32_t *>(sb + n * Nqp);
+  Real *lanes = reinterpret_cast<Real *>(smask + ((Nq * Wd + 3) & ~3));
+  __shared__ unsigned s_next, s_tested, s_valid, s_bits, s_ndsum, s_ndcnt;
+  __shared__ uint2 s_queue[8 * 32];           // per-warp buffers of claimed pairs (<= 256 threads per CTA)
+  const long long e = blockIdx.x;
+  const int iw = wedges[2 * e], jw = wedges[2 * e + 1];
+  const int ca = count[iw], cb = count[jw];
+  const int oa = old_count ? old_count[iw] : 0, ob = old_count ? old_count[jw] : 0;
+  uint32_t *mrow = mask + e * (long long)Nq * Wd;
+  const unsigned total = (unsigned)ca * (unsigned)cb;
+  if (threadIdx.x == 0) { s_next = 0; s_tested = 0; s_valid = 0; s_bits = 0; s_ndsum = 0; s_ndcnt = 0; }
+  for (int k = threadIdx.x; k < Nq * Wd; k += blockDim.x) {
+    uint32_t w = 0;
+    if (old_count) {
+      const int a = k / Wd, b0 = (k - a * Wd) * 32;
+      if (a < oa && b0 < ob) { w = mrow[k]; if (ob - b0 < 32) w &= (1u << (ob - b0)) - 1u; }
+    }
+    smask[k] = w;
+  }
+  if (total) {
+    const Real *ga = q_kept + (long long)iw * n * Nqp, *gb = q_kept + (long long)jw * n * Nqp;
+    for (int k = threadIdx.x; k < n * Nqp; k += blockDim.x) { sa[k] = ga[k]; sb[k] = gb[k]; }
+  }
+  LaneMem<Real, 2> mem[2];
+#pragma unroll
+  for (int s = 0; s < 2; s++) {
+    mem[s].init(lanes + 2 * threadIdx.x + s, 2 * (int)blockDim.x, n);
+    for (int j = 0; j < lane_reals<2>(n); j++) mem[s].base[j * mem[s].T] = 0;
+  }
+  __syncthreads();
+  LaneCounters cnt;
+  if (total) {
+    const Real eps = epsilon * sqrt_(Real(c.nlinks_eps));
+    const Real thr = eps * Real(c.nlinks_eps);
+    const Real thr2 = thr * thr;
+    WInterp<Real, M> W;
+    {
+      Real a6[6], b6[6];
+      for (int k = 0; k < 3; k++) { a6[k] = params[(long long)iw * 3 + k]; b6[k] = params[(long long)jw * 3 + k]; }
+      winterp_begin<Real, M, kMaxJ>(c, a6, b6, W);
+    }
+    LaneIK<Real, M> L[2];
+    PairLane<Real> P[2];
+    Target<Real, M> tg[2];
+    int a[2] = {-1, -1}, b[2] = {0, 0};
+#pragma unroll
+    for (int s = 0; s < 2; s++) { lane_begin_mem(L[s], mem[s]); tg[s].x[0] = tg[s].x[1] = tg[s].x[2] = 0; P[s].qa = sa; P[s].qb = sb; P[s].sa = Nqp; P[s].sb = Nqp; P[s].k = 2; }
+    {
+      const unsigned ts = (unsigned)(((unsigned long long)threadIdx.x * total) / blockDim.x);
+      const int ta = (int)(ts / (unsigned)cb), tb = (int)(ts - (unsigned)ta * (unsigned)cb);
+      const int nd = pair_ndivs<Real>(n, eps, sa + ta, Nqp, sb + tb, Nqp);
+      const unsigned sum = __reduce_add_sync(0xffffffffu, (unsigned)max(nd, 0));
+      if ((threadIdx.x & 31) == 0) { atomicAdd(&s_ndsum, sum); atomicAdd(&s_ndcnt, 32u); }
+    }
+    __syncthreads();
+    const int nd_cut = (int)((s_ndsum + s_ndcnt / 2) / s_ndcnt);
+    const unsigned total2 = 2u * total;
+    const int lane = threadIdx.x & 31;
+    uint2 *queue = reinterpret_cast<uint2 *>(s_queue) + (threadIdx.x >> 5) * 32;
+    int qhead = 0, qtail = 0;          // warp-uniform
+    bool exhausted = false;            // warp-uniform
+    for (;;) {
+      int verdict[2] = {-1, -1};
+#pragma unroll
+      for (int s = 0; s < 2; s++) {
+        unsigned needm = __ballot_sync(0xffffffffu, a[s] < 0);
+        while (needm) {
+          if (qhead == qtail) {
+            if (exhausted) break;
+            unsigned base = 0;
+            if (lane == 0) base = atomicAdd(&s_next, 32u);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (base >= total2) { exhausted = true; break; }
+            const unsigned t2 = base + lane;
+            const bool second = t2 >= total;
+            const unsigned t = second ? t2 - total : t2;
+            bool ok = t2 < total2;
+            int ta = 0, tb = 0, nd = 0;
+            if (ok) {
+              ta = (int)(t / (unsigned)cb); tb = (int)(t - (unsigned)ta * (unsigned)cb);
+              if (ta < oa && tb < ob) ok = false;                   // solver.py:694
+              if (iw == jw && ta <= tb) ok = false;                 // self-motion pairs i > j (solver.py:648-653)
+            }
+            if (ok) {
+              nd = pair_ndivs<Real, FLAG>(n, eps, sa + ta, Nqp, sb + tb, Nqp, c.fl_nd);
+              if ((nd & ~kNdFlag) <= 0) {
+                if (!second) {
+                  atomicOr(&smask[ta * Wd + (tb >> 5)], 1u << (tb & 31)); cnt.pairs++; cnt.valid++;
+                  if (FLAG && (nd & kNdFlag)) flag_push(flist, fcap, e, ta, tb, 0, PH_R_NDIVS);
+                }
+                ok = false;
+              } else if (((nd & ~kNdFlag) >= nd_cut) == second) ok = false;
+            }
+            const unsigned okm = __ballot_sync(0xffffffffu, ok);
+            if (ok) queue[__popc(okm & ((1u << lane) - 1u))] = make_uint2(((unsigned)ta << 16) | (unsigned)tb, (unsigned)nd);
+            __syncwarp();
+            qhead = 0; qtail = __popc(okm);
+            continue;
+          }
+          const int rank = __popc(needm & ((1u << lane) - 1u)), avail = qtail - qhead;
+          if (a[s] < 0 && rank < avail) {
+            const uint2 ent = queue[qhead + rank];
+            a[s] = (int)(ent.x >> 16); b[s] = (int)(ent.x & 0xffffu);
+            P[s].qa = sa + a[s]; P[s].qb = sb + b[s]; P[s].sa = Nqp; P[s].sb = Nqp;
+            pair_arm<Real, M>((int)ent.y, P[s], L[s]);
+            winterp_at<Real, M>(W, Real(1) / Real(P[s].ndivs + 1), tg[s]);
+          }
+          __syncwarp();
+          qhead += min(__popc(needm), avail);
+          needm = __ballot_sync(0xffffffffu, a[s] < 0);
+        }
+      }
+      if (__all_sync(0xffffffffu, a[0] < 0 && a[1] < 0)) break;
+      const bool run0 = a[0] >= 0, run1 = a[1] >= 0;
+      {
+        PassOut<Real, M> o[2];
+        const bool f0 = run0 && P[0].k == 1, f1 = run1 && P[1].k == 1;
+        const float *const xref[2] = {f0 ? P[0].qa : mem[0].prev(), f1 ? P[1].qa : mem[1].prev()};
+        const int sref[2] = {f0 ? P[0].sa : mem[0].T, f1 ? P[1].sa : mem[1].T};
+        lane_pass_planar2(c, tg, L, mem, xref, sref, o);
+#pragma unroll
+        for (int s = 0; s < 2; s++) {
+          const bool running = (s == 0 ? run0 : run1);
+          const int st = lane_step<Real, M, true, FLAG>(c, L[s], mem[s], o[s], running);
+          if constexpr (FLAG) warp_tie_service<Real, M, true, 2>(c, L[s], mem[s], running);
+          if (running && st != IK_RUNNING) {
+            cnt.solves++; cnt.iters += L[s].it; cnt.evals += L[s].evals; cnt.ok += (st == IK_OK);
+            if (FLAG) pair_note_solve(P[s], L[s], st);
+            if (st != IK_OK) verdict[s] = 0;                       // graph.py:964-966
+            else {
+              verdict[s] = pair_advance<FLAG>(c, mem[s], o[s].s2, thr2, P[s], L[s]);
+              if (verdict[s] < 0) winterp_at<Real, M>(W, Real(P[s].k) / Real(P[s].ndivs + 1), tg[s]);
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int s = 0; s < 2; s++) {
+        if (a[s] >= 0 && verdict[s] >= 0) {
+          if (verdict[s]) atomicOr(&smask[a[s] * Wd + (b[s] >> 5)], 1u << (b[s] & 31));
+          if (FLAG && P[s].flag) flag_push(flist, fcap, e, a[s], b[s], P[s].k0, P[s].flag);
+          cnt.pairs++; cnt.valid += verdict[s];
+          a[s] = -1;
+          lane_begin_mem(L[s], mem[s]);   // idle slots keep walking valid memory
+          P[s].k = 2;                     // (their reference config is the slot's own prev buffer)
+        }
+      }
+    }
+  }
+  {
+    const unsigned tp = __reduce_add_sync(0xffffffffu, cnt.pairs), tv = __reduce_add_sync(0xffffffffu, cnt.valid);
+    if ((threadIdx.x & 31) == 0 && tp) { atomicAdd(&s_tested, tp); atomicAdd(&s_valid, tv); }
+  }
+  cnt.flush(counters);
+  __syncthreads();
+  unsigned nbits = 0;
+  for (int k = threadIdx.x; k < Nq * Wd; k += blockDim.x) { const uint32_t w = smask[k]; mrow[k] = w; nbits += __popc(w); }
+  if (edge_stats) {
     const unsigned wbits = __reduce_add_sync(0xffffffffu, nbits);
     if ((threadIdx.x & 31) == 0 && wbits) atomicAdd(&s_bits, wbits);
     __syncthreads();
@@ -1376,6 +1562,19 @@ struct Impl {
       };
       const bool pl = planar(h);
       if constexpr (kHasPlanar && sizeof(Real) == 4) {
+        // two lane machines per thread on the packed FP32 instructions (k_edges_build2): planar small-angle chains
+        static const bool no_dual = getenv("GRR_DUAL") == nullptr;      // opt-in until validated on the GPU
+        if (pl && c.small_angles != 0 && c.axes_positive != 0 && !no_dual && threads >= 64) {
+          const int threads2 = (threads / 2) / 32 * 32;
+          const size_t smem2 = fixed + (size_t)threads2 * 2 * h.n * (4 + mc(h)) * sizeof(Real);
+          auto launch2 = [&](auto kern) -> int {
+            if (set_smem(kern, smem2, "k_edges_build2")) return -2;
+            kern<<<(unsigned)E, threads2, smem2, st>>>(c, wedges, (const Real *)params, (const Real *)q_kept, count, old_count, Nq, Nqp,
+                                                       (Real)epsilon, mask, edge_stats, counters, flist, fcap);
+            return 0;
+          };
+          rc = flist ? launch2(k_edges_build2<true>) : launch2(k_edges_build2<false>);
+        } else
         if (pl) rc = flist ? launch(k_edges_build<Real, M, true, true>) : launch(k_edges_build<Real, M, true, false>);
         else rc = flist ? launch(k_edges_build<Real, M, false, true>) : launch(k_edges_build<Real, M, false, false>);
       } else if constexpr (kHasPlanar) {

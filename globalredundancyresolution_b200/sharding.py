@@ -62,9 +62,11 @@ def edge_ranges(edges, count, world, old_count=None):
     total = cum[-1]
     if total == 0:
         return [(edges.shape[0] * r) // world for r in range(world + 1)]
-    targets = [total * r / float(world) for r in range(1, world)]
-    cuts = [int(np.searchsorted(cum, t, side="left")) for t in targets]
-    b = [0] + cuts + [edges.shape[0]]
+    # one vectorised search (a Python loop of searchsorted calls with float targets converts the whole integer array
+    # per call: 66 ms of host time for 512 cuts of 533k edges, the largest serial section of the 8-GPU build)
+    targets = np.asarray([total * r / float(world) for r in range(1, world)], dtype=np.float64)
+    cuts = np.searchsorted(cum.astype(np.float64), targets, side="left").tolist()
+    b = [0] + [int(v) for v in cuts] + [edges.shape[0]]
     for i in range(1, len(b)):
         b[i] = max(b[i], b[i - 1])
     return b
@@ -78,8 +80,8 @@ def ranges_by_cost(cost, world):
     E = cost.shape[0]
     if total <= 0:
         return [(E * r) // world for r in range(world + 1)]
-    cuts = [int(np.searchsorted(cum, total * r / float(world), side="left")) for r in range(1, world)]
-    b = [0] + cuts + [E]
+    cuts = np.searchsorted(cum, np.asarray([total * r / float(world) for r in range(1, world)]), side="left").tolist()
+    b = [0] + [int(v) for v in cuts] + [E]
     for i in range(1, len(b)):
         b[i] = max(b[i], b[i - 1])
     return b
@@ -178,7 +180,7 @@ class ShardedResolver(RedundancyResolver):
     0.56 GB in FP32) but fills only its node window, and holds the bitmasks of its own edge range
     chunks (`edge_ids`: global ids of the local mask rows).  `gather_masks()` assembles the full roadmap."""
 
-    def __init__(self, resolution, rank, world, seed=0, sample_dtype="float64", rebalance=True, chunks_per_rank=8,
+    def __init__(self, resolution, rank, world, seed=0, sample_dtype="float64", rebalance=True, chunks_per_rank=64,
                  exact_edges=True, exchange="auto", edge_chunks_per_rank=64):
         """exchange: how the sampled configs reach the ranks that test edges on them.
              'halo'       node windows of each rank's edge chunks, one slab per (owner, user) pair (+ the cost-based
@@ -236,6 +238,15 @@ class ShardedResolver(RedundancyResolver):
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
         d["counters"].zero_(); d["counters_e"].zero_()
         mine_nodes = self.my_node_ranges()
+        import os, time
+        prof = os.environ.get("GRR_SHARD_PROFILE") is not None      # section wall times with device syncs (measurement runs only)
+        marks = []
+
+        def mark(name):
+            if prof:
+                torch.cuda.synchronize(res.torch_device)
+                marks.append((name, time.perf_counter()))
+        mark("start")
         ev[0].record()
         d["count"].zero_()
         if len(mine_nodes) == 1:
@@ -243,7 +254,9 @@ class ShardedResolver(RedundancyResolver):
         else:
             nodes = torch.cat([torch.arange(lo, hi, dtype=torch.int32, device=res.torch_device) for (lo, hi) in mine_nodes])
             self._sample_phase_nodes(d, N, nodes)
+        mark("sample_kernels")
         dist.all_reduce(d["count"])                       # every rank learns every node's count
+        mark("allreduce_count")
         ev[1].record()
         self.attempts += N
         if connect:
@@ -267,8 +280,10 @@ class ShardedResolver(RedundancyResolver):
                     dist.all_reduce(blk)
                     d["Qs"][:, :, :cpad] = blk
                     self.halo_bytes = int(blk.numel() * blk.element_size())
+                mark("exchange_configs")
                 eb = edge_ranges(edges, cnt, self.world * K)
                 chunks = rank_chunks(eb, self.world, K)
+                mark("plan")
             else:
                 K = self.chunks_per_rank
                 cnt = d["count"].cpu().numpy()
@@ -315,12 +330,16 @@ class ShardedResolver(RedundancyResolver):
             if ne:
                 my_wedges = torch.cat([d["wedges"][a:b] for (a, b) in mine if b > a]).contiguous()
                 # (rounds the kept configs to the edge precision, then the exact build or the plain kernels)
+                mark("prepare_launch")
                 self._edges_launch(d, my_wedges, d["mask"], d["edge_stats"], None)
+                mark("edge_kernels")
         ev[2].record()
         torch.cuda.synchronize(res.torch_device)
         self._invalidate()
         self._collect_stats(d, ev, N, 0)
         self.stats["halo_bytes"] = self.halo_bytes
+        if prof:
+            self.stats["sections_ms"] = {marks[i][0]: round((marks[i][1] - marks[i - 1][1]) * 1e3, 2) for i in range(1, len(marks))}
         self.stats["sampled"] = int(sum(int(d["count"][lo:hi].sum().item()) for (lo, hi) in mine_nodes))
         return self.stats["t_sample"], self.stats["t_connect"]
 
