@@ -426,14 +426,19 @@ class RedundancyResolver(VisibilityMixin):
         idx = nodes.long()
         q_raw = torch.empty((nn, res.chain.n, Nqp_raw), dtype=sdt, device=res.torch_device)
         status = torch.empty((nn, Nqp_raw), dtype=torch.uint8, device=res.torch_device)
+        mark = getattr(self, "_mark", None) or (lambda name: None)
         res.chain.ik_sample(d["params_s"][idx].contiguous(), d["uid"][idx].contiguous(), self.seed, q_raw, status, None,
                             d["counters"], Nq=N, sample_offset=self.attempts)
+        mark("ik_sample")
         kept = torch.empty((nn, res.chain.n, d["Qs"].shape[2]), dtype=sdt, device=res.torch_device)
         kcount = torch.empty(nn, dtype=torch.int32, device=res.torch_device)
         _cabi.gather_node_blocks(nodes, d["Qs"], d["count"], kept, kcount)
         cin = kcount.clone()
+        mark("gather")
         res.chain.dedup(q_raw, status, thresh, kept, kcount, Nq=N, count_in=cin)
+        mark("dedup")
         _cabi.scatter_node_blocks(nodes, kept, kcount, d["Qs"], d["count"])
+        mark("scatter")
 
     def _edges_launch(self, d, wedges, mask, stats, old_counts):
         """One edge-construction call on the given workspace edges: the exact build (single-precision pass + double-
