@@ -28,7 +28,7 @@ EXPORTS = [
     "grr_chain_num_joints", "grr_fk_batch", "grr_ik_solve_batch", "grr_ik_sample", "grr_ik_sample_level", "grr_dedup", "grr_dedup_sweep",
     "grr_edges_build", "grr_edges_build_exact", "grr_set_flag_scale", "grr_edges_exact_mode", "grr_edges_cost", "grr_edges_compact", "grr_valid_edge_batch", "grr_gather_node_blocks",
     "grr_scatter_node_blocks", "grr_halo_exchange", "grr_csp_random_assignment", "grr_csp_conflicts", "grr_csp_descent_sweep",
-    "grr_fp32_peak", "grr_fp32x2_peak",
+    "grr_fp32_peak", "grr_fp32x2_peak", "grr_fp64_peak",
     "grr_edges_test_listed", "grr_manifold_knn_list", "grr_manifold_components", "grr_qcc_candidates", "grr_qcc_wave",
     "grr_qcc_connect", "grr_pair_hash", "grr_ik_sample_sweep",
 ]
@@ -102,6 +102,7 @@ def lib():
     L.grr_csp_descent_sweep.argtypes = [i32, vp, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     L.grr_fp32_peak.argtypes = [C.c_int, C.POINTER(C.c_double)]
     L.grr_fp32x2_peak.argtypes = [C.c_int, C.POINTER(C.c_double)]
+    L.grr_fp64_peak.argtypes = [C.c_int, C.POINTER(C.c_double)]
     for name in EXPORTS:
         if name not in ("grr_last_error", "grr_pair_hash"):
             getattr(L, name).restype = C.c_int
@@ -111,7 +112,7 @@ def lib():
 
 def check(rc, what):
     global LAUNCHES
-    if what not in ("grr_chain_create", "grr_task_set", "grr_fp32_peak", "grr_fp32x2_peak", "grr_set_flag_scale", "grr_edges_exact_mode", "grr_pair_hash"):
+    if what not in ("grr_chain_create", "grr_task_set", "grr_fp32_peak", "grr_fp32x2_peak", "grr_fp64_peak", "grr_set_flag_scale", "grr_edges_exact_mode", "grr_pair_hash"):
         # edges_build = k_edge_load + k_edges_build (+ k_edges_recheck in the exact build)
         LAUNCHES += {"grr_edges_build": 2, "grr_edges_build_exact": 3}.get(what, 1)
     if rc != 0:
@@ -430,6 +431,12 @@ def scatter_node_blocks(idx, packed, packed_count, q, count):
 def fp32_peak(device=0):
     out = C.c_double(0.0)
     check(lib().grr_fp32_peak(int(device), C.byref(out)), "grr_fp32_peak")
+    return out.value
+
+
+def fp64_peak(device=0):
+    out = C.c_double(0.0)
+    check(lib().grr_fp64_peak(int(device), C.byref(out)), "grr_fp64_peak")
     return out.value
 
 

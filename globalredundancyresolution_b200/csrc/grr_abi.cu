@@ -242,6 +242,19 @@ __global__ void __launch_bounds__(256) k_fma_peak(float *out, int iters, float a
   out[blockIdx.x * blockDim.x + threadIdx.x] = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
 }
 
+// double precision FMA peak (roofline denominator of the double-precision kernels: sampling, general-chain edge phase)
+__global__ void __launch_bounds__(256) k_dfma_peak(double *out, int iters, double a, double b) {
+  double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+  for (int i = 0; i < iters; i++) {
+#pragma unroll
+    for (int u = 0; u < 16; u++) {
+      x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+      x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+    }
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+}
+
 // packed variant: sm_100 FFMA2 (two FP32 FMAs per instruction per lane)
 __global__ void __launch_bounds__(256) k_fma2_peak(float *out, int iters, float a, float b) {
   float2 x0 = make_float2(threadIdx.x, threadIdx.x + 1.f), x1 = make_float2(x0.x + 2.f, x0.x + 3.f);
@@ -700,6 +713,34 @@ extern "C" int grr_halo_exchange(grr_handle_t h, void *nccl_comm, int dtype, int
 }
 
 static int fp32_peak_impl(int device, double *tflops_out, bool packed);
+int grr_fp64_peak(int device, double *tflops_out) {
+  if (!tflops_out) { set_error("null argument"); return -1; }
+  cudaError_t e = cudaSetDevice(device);
+  if (e != cudaSuccess) { set_error("cudaSetDevice: %s", cudaGetErrorString(e)); return -2; }
+  int sms = 0;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+  const int blocks = sms * 8, threads = 256, iters = 1024;
+  double *buf = nullptr;
+  if (cudaMalloc(&buf, sizeof(double) * blocks * threads) != cudaSuccess) { set_error("cudaMalloc failed"); return -3; }
+  cudaEvent_t a, b;
+  cudaEventCreate(&a); cudaEventCreate(&b);
+  double best = 0;
+  for (int rep = 0; rep < 5; rep++) {
+    cudaEventRecord(a);
+    k_dfma_peak<<<blocks, threads>>>(buf, iters, 0.999, 0.001);
+    cudaEventRecord(b);
+    cudaEventSynchronize(b);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, a, b);
+    const double tf = 2.0 * 8 * 16 * (double)iters * blocks * threads / (ms * 1e-3) / 1e12;
+    if (rep > 0 && tf > best) best = tf;
+  }
+  cudaEventDestroy(a); cudaEventDestroy(b);
+  cudaFree(buf);
+  if (cudaGetLastError() != cudaSuccess) { set_error("k_dfma_peak failed"); return -2; }
+  *tflops_out = best;
+  return 0;
+}
 int grr_fp32_peak(int device, double *tflops_out) { return fp32_peak_impl(device, tflops_out, false); }
 int grr_fp32x2_peak(int device, double *tflops_out) { return fp32_peak_impl(device, tflops_out, true); }
 }  // extern "C"

@@ -39,7 +39,7 @@ struct LaneCounters {
 //   MODE 1: explicit (target, seed) instances, SoA q[n][P]  (RedundancyResolutionGraph.solve, graph.py:779-790)
 // ------------------------------------------------------------------------------------------
 template <typename Real, int M, int MODE, bool PL>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, (sizeof(Real) == 8 && M == 3) ? 2 : 1)
 k_ik_instances(const __grid_constant__ ChainDev<Real, kMaxJ> c, long long total, int Nq, int Nqp,
                const Real *__restrict__ params, const int32_t *__restrict__ uid, unsigned long long seed, int sample_offset,
                Real *__restrict__ q, uint8_t *__restrict__ status, uint8_t *__restrict__ iters, Real *__restrict__ resid,
@@ -1056,8 +1056,17 @@ static __global__ void k_edges_bits(long long E, int words, const uint32_t *__re
   if (threadIdx.x == 0) edge_stats[2 * e + 1] = s_bits;
 }
 
+// double precision: 3 CTAs per SM for 3 residual rows (168 registers, 36 bytes of spills: 12 instead of 8 warps per SM hide
+// the FP64 latencies -- the kernel sat at 52 % issue utilisation with `stalled_wait` 1.6 per issue), 2 for 6 rows
+// (capping that build at 168 registers spills 1.6 KB per thread)
 template <typename Real, int M, bool PL, bool FLAG>
-__global__ void __launch_bounds__(128, (sizeof(Real) == 4 ? (M == 3 ? 4 : 3) : 2))
+#ifndef GRR_F64M3_BLOCKS
+#define GRR_F64M3_BLOCKS 3
+#endif
+#ifndef GRR_F64M6_BLOCKS
+#define GRR_F64M6_BLOCKS 2
+#endif
+__global__ void __launch_bounds__(128, (sizeof(Real) == 4 ? (M == 3 ? 4 : 3) : (M == 3 ? GRR_F64M3_BLOCKS : GRR_F64M6_BLOCKS)))
 k_edges_flat(const __grid_constant__ ChainDev<Real, kMaxJ> c, long long E, const int32_t *__restrict__ wedges,
              const Real *__restrict__ params, const Real *__restrict__ q_kept, const int32_t *__restrict__ count,
              const int32_t *__restrict__ old_count, int Nq, int Nqp, Real epsilon, uint32_t *mask,

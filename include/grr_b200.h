@@ -328,6 +328,8 @@ uint32_t grr_pair_hash(uint64_t seed, uint32_t iw, uint32_t jw, uint32_t a, uint
 
 /* -- measurement support: FP32 FMA peak microbenchmark (returns achieved TFLOP/s; synchronous). */
 int grr_fp32_peak(int device, double *tflops_out);
+/* double-precision FMA peak: denominator for the double-precision kernels (sampling; edge phase of general chains) */
+int grr_fp64_peak(int device, double *tflops_out);
 /* same with the packed sm_100 FFMA2 instruction (two FP32 FMAs per instruction per lane) */
 int grr_fp32x2_peak(int device, double *tflops_out);
 

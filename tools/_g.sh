@@ -1,6 +1,6 @@
-mkdir -p gpurun_out/r2k
-export GRR_DUAL=1
-CMD="python bench.py --steps 1 --warmup 1 --nw 1500 --no-cpu --no-extras"
-$CMD > gpurun_out/r2k/plain.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:k_edges_build2 -s 1 -c 1 -o gpurun_out/r2k/dual_nw1500 $CMD > gpurun_out/r2k/ncu_full.log 2>&1
-tail -2 gpurun_out/r2k/ncu_full.log
+export GRR_LIB=$PWD/globalredundancyresolution_b200/libgrr_var1.so
+for cfg in "jaco baseline_cfg3.json" "baxter baseline_cfg4.json" "robonaut2 baseline_cfg5.json Nw=20000"; do
+  timeout 300 python tools/time_cfg.py $cfg 2>&1 | tail -1 | cut -c1-260
+done
+unset GRR_LIB
+timeout 300 python tools/time_cfg.py robonaut2 baseline_cfg5.json Nw=20000 2>&1 | tail -1 | cut -c1-260
