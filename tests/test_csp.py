@@ -252,8 +252,19 @@ def test_sample_conflicts_refines_around_conflict_nodes(built):
     assert set(rr.Qsubgraph) == set(np.nonzero(cnt1 > 0)[0].tolist())
 
 
-def _optimize_sequential(res, numIters):
-    """solver.py:1934-1986 as written: nodes in id order, immediate updates, one solve / validEdge call at a time."""
+def _optimize_sequential(res, numIters, o=None):
+    """solver.py:1934-1986 as written: nodes in id order, immediate updates, one solve / validEdge call at a time --
+    with the CPU ORACLE's IK solve and validEdge when `o` is given (arithmetic parity), else through the product's own
+    per-call API (schedule equivalence only)."""
+    if o is not None:
+        def solve(qinit, x):
+            q, status, _, _, _ = o.ik_solve(np.asarray(x, dtype=np.float64), res.to_chain(np.asarray(qinit, dtype=np.float64)))
+            return None if status != 0 else res.to_full(q[None])[0].tolist()
+
+        def valid_edge(qa, qb, xa, xb):
+            return o.valid_edge(res.to_chain(np.asarray(qa)), res.to_chain(np.asarray(qb)), xa, xb)[0]
+    else:
+        solve, valid_edge = res.solve, res.validEdge
     nodes = [i for i, d in res.Gw.nodes_iter(data=True) if d.get("config", None) is not None]
     nbrs = {i: [] for i in nodes}
     for i, j, d in res.Gw.edges_iter(data=True):
@@ -272,11 +283,11 @@ def _optimize_sequential(res, numIters):
             for k in range(1, len(ws)):
                 qavg = qavg + (cfg[ws[k]] - qavg) * (1.0 / (k + 1))
             for _try in range(10):
-                q = res.solve(qavg.tolist(), x)
+                q = solve(qavg.tolist(), x)
                 if q is not None:
                     q = np.asarray(q, dtype=np.float64)
                     d = sum(dist(q, cfg[w]) for w in ws)
-                    if d <= d0 and all(res.validEdge(q.tolist(), cfg[w].tolist(), x, res.Gw.node[w]["params"]) for w in ws):
+                    if d <= d0 and all(valid_edge(q.tolist(), cfg[w].tolist(), x, res.Gw.node[w]["params"]) for w in ws):
                         cfg[v] = q
                         break
                 qavg = q0 + (qavg - q0) * 0.5
@@ -291,12 +302,13 @@ def test_optimize_equals_sequential_sweep_and_feeds_the_roadmap(built):
     connected = [(i, j) for i, j in res.Gw.edges_iter() if res.isResolvedEdge(i, j)]
     assert connected
     length = lambda cfgs: sum(float(np.linalg.norm(np.asarray(cfgs[i]) - np.asarray(cfgs[j]))) for i, j in connected)
-    want = _optimize_sequential(res, 2)
+    from helpers import oracle_for
+    want = _optimize_sequential(res, 2, o=oracle_for(res))        # the reference's loop on the CPU oracle's solve / validEdge
     cnt0 = rr.counts().copy()
     rr.optimize(2)
     after = {i: res.Gw.node[i]["config"] for i in before}
     for i in before:
-        np.testing.assert_allclose(after[i], want[i], rtol=0, atol=1e-6, err_msg="node %d" % i)
+        np.testing.assert_allclose(after[i], want[i], rtol=0, atol=1e-8, err_msg="node %d" % i)
     assert length(after) <= length(before) + 1e-9
     assert any(after[i] != before[i] for i in before)
     assert res.verify()[0] == 0                                  # every connected edge is still a valid edge

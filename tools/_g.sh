@@ -1,6 +1,5 @@
-export GRR_LIB=$PWD/globalredundancyresolution_b200/libgrr_var1.so
-for cfg in "jaco baseline_cfg3.json" "baxter baseline_cfg4.json" "robonaut2 baseline_cfg5.json Nw=20000"; do
-  timeout 300 python tools/time_cfg.py $cfg 2>&1 | tail -1 | cut -c1-260
-done
-unset GRR_LIB
-timeout 300 python tools/time_cfg.py robonaut2 baseline_cfg5.json Nw=20000 2>&1 | tail -1 | cut -c1-260
+mkdir -p gpurun_out/r2m
+timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/r2m/pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/r2m/pytest.log
+tail -8 gpurun_out/r2m/pytest.log
+timeout 900 python bench.py > gpurun_out/r2m/bench.json 2> gpurun_out/r2m/bench.err; tail -c 300 gpurun_out/r2m/bench.json; tail -3 gpurun_out/r2m/bench.err
+python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r2m/smoke.log 2>&1; tail -3 gpurun_out/r2m/smoke.log
