@@ -219,12 +219,17 @@ class ShardedResolver(RedundancyResolver):
     def _alloc_mask(self, Nq, W):
         # bitmasks only for the edge range this rank can own at most (allocated lazily per plan)
         torch = self.resolution._torch()
-        return torch.zeros((0, Nq, W), dtype=torch.int32, device=self.resolution.torch_device)
+        rows = 0
+        if self._dev is not None and "mask" in self._dev:
+            rows = int(self._dev["mask"].shape[0])      # incremental growth: this rank's rows are kept (and widened)
+        return torch.zeros((rows, Nq, W), dtype=torch.int32, device=self.resolution.torch_device)
 
     def sampleConfigurationSpace(self, NConfigsPerPoint=100, connect=True, biased=False, seedFromAdjacent=False,
                                  visibility=False, k=None, order_independent=True):
         """Sharded build: order-independent sampling only (parallelQSamplingAtP semantics, solver.py:875-897);
-        the seeded Gauss-Seidel sweep does not shard."""
+        the seeded Gauss-Seidel sweep does not shard.  A second call grows the roadmap incrementally
+        (solver.py:759,850: only pairs with a new endpoint are tested) in all-gather mode with round-robin edges, where
+        a rank's workspace edges -- and so its mask rows -- are the same in every call."""
         if visibility:
             raise NotImplementedError("visibility-graph solver is out of scope of the B200 roadmap path")
         if not order_independent:
@@ -232,10 +237,20 @@ class ShardedResolver(RedundancyResolver):
         import torch.distributed as dist
         torch = self.resolution._torch()
         res = self.resolution
-        if self.Nq > 0:
-            raise NotImplementedError("incremental growth is single-GPU only in this round")
         N = int(NConfigsPerPoint)
-        d = self._ensure_device(N)
+        incremental = self.Nq > 0
+        old_counts = None
+        if incremental:
+            mode0 = self.exchange
+            if mode0 == "auto":
+                mode0 = "allgather" if self._dev["Qs"].numel() * self._dev["Qs"].element_size() <= 4 * 2 ** 30 else "halo"
+            if mode0 != "allgather" or self.edge_chunks_per_rank != 0:
+                raise NotImplementedError("sharded incremental growth needs exchange='allgather' with round-robin edges "
+                                          "(edge_chunks_per_rank=0): the halo plan re-cuts the edge list per call")
+            old_counts = self._dev["count"].clone()
+        d = self._ensure_device(self.Nq + N)
+        if incremental:
+            self._mask_buf = d["mask"]                  # widened copy of this rank's rows (old bits kept)
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
         d["counters"].zero_(); d["counters_e"].zero_()
         mine_nodes = self.my_node_ranges()
@@ -250,7 +265,13 @@ class ShardedResolver(RedundancyResolver):
         self._mark = mark if prof else None
         mark("start")
         ev[0].record()
-        d["count"].zero_()
+        if incremental:
+            own0 = torch.zeros(self.Nw, dtype=torch.bool, device=res.torch_device)
+            for (lo, hi) in mine_nodes:
+                own0[lo:hi] = True
+            d["count"].mul_(own0.to(d["count"].dtype))     # other ranks' counts come back with the all-reduce
+        else:
+            d["count"].zero_()
         if len(mine_nodes) == 1:
             self._sample_phase(d, N, mine_nodes[0][0], mine_nodes[0][1])
         else:
@@ -343,7 +364,7 @@ class ShardedResolver(RedundancyResolver):
                     my_wedges = torch.cat([d["wedges"][a:b] for (a, b) in mine if b > a]).contiguous()
                 # (rounds the kept configs to the edge precision, then the exact build or the plain kernels)
                 mark("prepare_launch")
-                self._edges_launch(d, my_wedges, d["mask"], d["edge_stats"], None)
+                self._edges_launch(d, my_wedges, d["mask"], d["edge_stats"], old_counts)
                 mark("edge_kernels")
         ev[2].record()
         torch.cuda.synchronize(res.torch_device)

@@ -38,4 +38,22 @@ for (name, jf, Nw, Nq) in cases:
                 print("sharded == single GPU: %s world=%d nodes=%d edges=%d pairs=%d exact=%s exchange=%s bytes received(rank0)=%d"
                       % (name, world, sr.Nw, sr.E, p0, exact, exchange, sr.halo_bytes), flush=True)
             dist.barrier()
+    # incremental growth (a second sampleConfigurationSpace call, solver.py:759,850): all-gather mode, round-robin edges
+    if rank == 0:
+        rr = grr.RedundancyResolver(res, seed=3)
+        rr.sampleConfigurationSpace(Nq // 2, order_independent=True)
+        rr.sampleConfigurationSpace(Nq - Nq // 2, order_independent=True)
+        ref2 = (rr._dev["count"].clone(), rr._dev["mask"].clone(), rr._dev["Qs"].clone(), rr.stats["pairs"])
+    sr = sharding.ShardedResolver(res, rank, world, seed=3, exchange="allgather")
+    sr.sampleConfigurationSpace(Nq // 2, order_independent=True)
+    sr.sampleConfigurationSpace(Nq - Nq // 2, order_independent=True)
+    full = sr.gather_masks()
+    tot = torch.tensor([float(sr.stats["pairs"])], device="cuda"); dist.all_reduce(tot)
+    if rank == 0:
+        assert torch.equal(sr._dev["count"], ref2[0]), "counts differ after incremental growth"
+        assert torch.equal(full, ref2[1]), "edge masks differ after incremental growth (%s)" % name
+        assert torch.equal(sr._dev["Qs"], ref2[2]), "configs differ after incremental growth"
+        assert int(tot[0].item()) == ref2[3], (tot.tolist(), ref2[3])
+        print("sharded incremental == single GPU incremental: %s world=%d pairs of the second call=%d" % (name, world, ref2[3]), flush=True)
+    dist.barrier()
 dist.destroy_process_group()
