@@ -695,7 +695,12 @@ class RedundancyResolver(VisibilityMixin):
         oc = None
         if old_counts is not None:
             oc = torch.as_tensor(np.asarray(old_counts, dtype=np.int32), device=res.torch_device)
+        prev = sub_mask.clone() if oc is None else None
         self._edges_launch(d, wedges, sub_mask, stats, oc)
+        if prev is not None:
+            # solver.py:494-495: testAndConnect answers True for a pair that is already an edge and never removes one --
+            # edges put there by addEdge / fromResolutionToGraph survive a re-test of the workspace edge
+            sub_mask |= prev
         d["mask"][eid] = sub_mask
         for e in edge_ids:
             self._ecache.pop(int(e), None)
@@ -735,7 +740,12 @@ class RedundancyResolver(VisibilityMixin):
         if visibility:
             self._connect_visibility(None, 10, swap=0)                                       # solver.py:725-726
         else:
+            # counts=None re-tests every pair: existing edges stay edges whatever the re-test says (solver.py:494-495)
+            prev = d["mask"].clone() if (oc is None and bool(d["mask"].ne(0).any().item())) else None
             self._connect_phase(d, oc)
+            if prev is not None:
+                d["mask"] |= prev
+                del prev
         e1.record()
         torch.cuda.synchronize(res.torch_device)
         self._ecache.clear()

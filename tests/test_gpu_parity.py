@@ -285,6 +285,17 @@ def test_container_api_and_views(built):
         assert not rr.hasEdge(iw, a, jw, b)
         rr.addEdge(jw, b, iw, a)
         assert rr.hasEdge(iw, a, jw, b)
+    # an edge put there by hand survives a re-test of its workspace edge, valid or not: the reference's testAndConnect
+    # answers True for a pair that is already in the qlist and nothing removes it (solver.py:494-495)
+    bad = next(((a, b) for a in range(cnt[iw]) for b in range(cnt[jw]) if (a, b) not in qs), None)
+    if bad is not None:
+        rr.addEdge(iw, bad[0], jw, bad[1])
+        rr.connectConfigurationSpaceOnEdge(iw, jw)
+        assert rr.hasEdge(iw, bad[0], jw, bad[1])
+        rr.connectConfigurationSpace()
+        assert rr.hasEdge(iw, bad[0], jw, bad[1])
+        rr.removeEdge(iw, bad[0], jw, bad[1])
+        assert rr.Gw.edge[iw][jw]["qlist"] == qs
     k = rr.addNode(iw, ql[0])
     assert k == cnt[iw] and rr.counts()[iw] == cnt[iw] + 1
     np.testing.assert_allclose(rr.Gw.node[iw]["qlist"][k], ql[0], atol=1e-12)
