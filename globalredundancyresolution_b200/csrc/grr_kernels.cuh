@@ -291,7 +291,9 @@ k_sweep_dataflow(const __grid_constant__ ChainDev<Real, kMaxJ> c, long long Nn, 
           const int cand = lower_idx[lp0 + k];
           if (__ldcg(count + cand) > 0) { if (pick == 0) { jn = cand; break; } pick--; }
         }
+        GRR_DCHECK(jn >= 0 && jn < node && na > 0);
         const int cfg = (int)(r[1] % (uint32_t)__ldcg(count + jn));
+        GRR_DCHECK(cfg < Nqk);
         const Real *srcq = Qk + ((long long)jn * n) * Nqk + cfg;
         Real *xo = mem.xold();
         for (int j = 0; j < n; j++) xo[j * mem.T] = __ldcg(srcq + (long long)j * Nqk);
@@ -327,6 +329,7 @@ k_sweep_dataflow(const __grid_constant__ ChainDev<Real, kMaxJ> c, long long Nn, 
         if (ci < nseed) ok = (sst[ci] == 0);
         else if (ci < nseed + nrand) ok = (str[ci - nseed] == 0);
         const unsigned m = __ballot_sync(0xffffffffu, ok);
+        GRR_DCHECK(nok + __popc(m) <= Cmax && nseed + nrand <= Cmax && nrand <= Nqr);
         if (ok) clist[nok + __popc(m & ((1u << lane) - 1u))] = (ci < nseed) ? ci : Nq + (ci - nseed);
         nok += __popc(m);
       }
@@ -399,6 +402,7 @@ k_sweep_dataflow(const __grid_constant__ ChainDev<Real, kMaxJ> c, long long Nn, 
     for (int k = tid; k < C * n; k += T) {
       const int sidx = k / n, j = k - sidx * n;
       const int sl = slot[sidx];
+      GRR_DCHECK(sl < Nqk);
       if (sl >= 0) { int ss; const Real *a = cand_ptr(sidx, ss); out[j * Nqk + sl] = a[(long long)j * ss]; }
     }
     __syncthreads();
@@ -1236,6 +1240,7 @@ k_edges_recheck(const __grid_constant__ ChainDev<Real, kMaxJ> c, const int32_t *
       else {
         const unsigned long long w0 = flist[2 + 2 * t], w1 = flist[3 + 2 * t];
         edge = (long long)(w0 >> 32); a = (int)((w0 >> 16) & 0xffffu); b = (int)(w0 & 0xffffu);
+        GRR_DCHECK(a < Nq && b < Nq && edge >= 0);
         const int k0 = (int)(w1 & 0xffffffffu);
         const int iw = wedges[2 * edge], jw = wedges[2 * edge + 1];
         Real a6[6], b6[6];

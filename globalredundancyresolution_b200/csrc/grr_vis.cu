@@ -15,6 +15,7 @@
 #include <stdint.h>
 #include <float.h>
 #include <cuda_runtime.h>
+#include "grr_device.cuh"
 #include "grr_host.h"
 
 namespace grr {
@@ -128,6 +129,7 @@ k_manifold(int n, int Nq, int Nqp, const Real *__restrict__ Q, const int32_t *__
         }
         continue;
       }
+      GRR_DCHECK((int)bj < c && i < c);
       const int lj = label[bj];
       if (lj == li) continue;                                                      // :639 (knn mode)
       tests++;
@@ -136,6 +138,7 @@ k_manifold(int n, int Nq, int Nqp, const Real *__restrict__ Q, const int32_t *__
         const int keep = min(li, lj), drop = max(li, lj);
         __syncwarp();
         for (int x = lane; x < c; x += 32) if (label[x] == drop) label[x] = keep;
+        GRR_DCHECK(nm < Nq - 1 || Nq == 1);
         if (lane == 0) medge[nm] = (i << 16) | (int)bj;
         nm++;
         __syncwarp();
@@ -242,6 +245,7 @@ k_qcc_candidates(long long E, const int32_t *__restrict__ wedges, int n, int Nq,
         if (bk == kNone || key_less(d, key, bd, bk)) { bd = d; bk = key; }
       }
       warp_key_min(bd, bk);
+      GRR_DCHECK(bk != kNone && (int)(bk >> 16) < Nq && (int)(bk & 0xffffu) < Nq);
       if (lane == 0) out[got] = (int32_t)bk;
       last_d = bd; last_k = bk; have_last = true;
     }
@@ -280,6 +284,7 @@ __device__ __forceinline__ int32_t canon(int32_t ab, int swap) { return swap ? (
 
 __device__ __forceinline__ bool vbit(const uint32_t *vm, long long e, int Nq, int Wd, int32_t ab) {
   const int a = ab >> 16, b = ab & 0xffff;
+  GRR_DCHECK(a >= 0 && a < Nq && b < Nq);
   return (vm[(e * Nq + a) * Wd + (b >> 5)] >> (b & 31)) & 1u;
 }
 
