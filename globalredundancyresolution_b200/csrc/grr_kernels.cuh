@@ -434,6 +434,13 @@ struct PairLane {
   int flag;
   int k0;             // FLAG builds: first interpolation index with a near-tie (0: Ndivs itself); recheck kernel: restart index
   Real amb_prev;
+  Real inv;           // single precision: 1 / (Ndivs + 1), so that u_k = k * inv costs no division per solve
+  // u_k = k / (Ndivs + 1) (graph.py:961): the exact quotient in double precision (the reference's value), k * inv in
+  // single precision (within one ulp of it; the IEEE division at every solve boundary was 3 % of the stall samples)
+  GRR_DEV Real u_at(int kk) const {
+    if constexpr (sizeof(Real) == 4) return Real(kk) * inv;
+    else return Real(kk) / Real(ndivs + 1);
+  }
 };
 
 // Ndivs = ceil(robot.distance(qa, qb) / eps) (graph.py:944-946).  FLAG: bit 30 of the result is set when dist / eps
@@ -456,7 +463,8 @@ GRR_DEV bool pair_arm(int ndivs, PairLane<Real> &P, LaneIK<Real, M> &L) {
   P.ndivs = ndivs & ~kNdFlag;
   P.k = 1; P.solves = 0; P.iters = 0;
   if (P.ndivs <= 0) return false;                                // dist == 0: single leaf of length 0 -> valid
-  lane_begin_lerp<Real, M>(L, P.qa, P.sa, P.qb, P.sb, Real(1) / Real(P.ndivs + 1));   // graph.py:961-962
+  P.inv = Real(1) / Real(P.ndivs + 1);
+  lane_begin_lerp<Real, M>(L, P.qa, P.sa, P.qb, P.sb, P.u_at(1));                     // graph.py:961-962
   return true;
 }
 
@@ -509,7 +517,7 @@ GRR_DEV int pair_advance(const ChainT &c, LaneMem<Real, MC> &mem, Real s2, Real 
   }
   { const int t = mem.o_prev; mem.o_prev = mem.o_xcur; mem.o_xcur = t; }   // IK_OK leaves the solution in xcur
   P.k++;
-  lane_begin_lerp<Real, M>(L, P.qa, P.sa, P.qb, P.sb, Real(P.k) / Real(P.ndivs + 1));
+  lane_begin_lerp<Real, M>(L, P.qa, P.sa, P.qb, P.sb, P.u_at(P.k));
   return -1;
 }
 
@@ -595,7 +603,7 @@ k_valid_edge_batch(const __grid_constant__ ChainDev<Real, kMaxJ> c, long long to
         winterp_begin<Real, M, kMaxJ>(c, a6, b6, W);
         P.qa = qa + t; P.qb = qb + t; P.sa = (int)total; P.sb = (int)total;
         if (!pair_begin<Real, M>(c, eps, P, L)) verdict = 1;
-        else winterp_at<Real, M>(W, Real(1) / Real(P.ndivs + 1), tg);
+        else winterp_at<Real, M>(W, P.u_at(1), tg);
       }
     }
     const bool running = (t >= 0 && verdict < 0);
@@ -613,7 +621,7 @@ k_valid_edge_batch(const __grid_constant__ ChainDev<Real, kMaxJ> c, long long to
         else {
           verdict = pair_advance(c, mem, o.s2, thr2, P, L);
           if (verdict == 0) fail = 2;
-          if (verdict < 0) winterp_at<Real, M>(W, Real(P.k) / Real(P.ndivs + 1), tg);
+          if (verdict < 0) winterp_at<Real, M>(W, P.u_at(P.k), tg);
         }
       }
     }
@@ -756,7 +764,7 @@ k_edges_build(const __grid_constant__ ChainDev<Real, kMaxJ> c, const int32_t *__
           a = (int)(ent.x >> 16); b = (int)(ent.x & 0xffffu);
           P.qa = sa + a; P.qb = sb + b; P.sa = Nqp; P.sb = Nqp;
           pair_arm<Real, M>((int)ent.y, P, L);
-          winterp_at<Real, M>(W, Real(1) / Real(P.ndivs + 1), tg);
+          winterp_at<Real, M>(W, P.u_at(1), tg);
         }
         __syncwarp();
         qhead += min(__popc(needm), avail);
@@ -777,7 +785,7 @@ k_edges_build(const __grid_constant__ ChainDev<Real, kMaxJ> c, const int32_t *__
           if (st != IK_OK) verdict = 0;                         // graph.py:964-966
           else {
             verdict = pair_advance<FLAG>(c, mem, o.s2, thr2, P, L);
-            if (verdict < 0) winterp_at<Real, M>(W, Real(P.k) / Real(P.ndivs + 1), tg);
+            if (verdict < 0) winterp_at<Real, M>(W, P.u_at(P.k), tg);
           }
         }
       }
@@ -931,7 +939,7 @@ k_edges_build2(const __grid_constant__ ChainDev<float, kMaxJ> c, const int32_t *
             a[s] = (int)(ent.x >> 16); b[s] = (int)(ent.x & 0xffffu);
             P[s].qa = sa + a[s]; P[s].qb = sb + b[s]; P[s].sa = Nqp; P[s].sb = Nqp;
             pair_arm<Real, M>((int)ent.y, P[s], L[s]);
-            winterp_at<Real, M>(W, Real(1) / Real(P[s].ndivs + 1), tg[s]);
+            winterp_at<Real, M>(W, P[s].u_at(1), tg[s]);
           }
           __syncwarp();
           qhead += min(__popc(needm), avail);
@@ -957,7 +965,7 @@ k_edges_build2(const __grid_constant__ ChainDev<float, kMaxJ> c, const int32_t *
             if (st != IK_OK) verdict[s] = 0;                       // graph.py:964-966
             else {
               verdict[s] = pair_advance<FLAG>(c, mem[s], o[s].s2, thr2, P[s], L[s]);
-              if (verdict[s] < 0) winterp_at<Real, M>(W, Real(P[s].k) / Real(P[s].ndivs + 1), tg[s]);
+              if (verdict[s] < 0) winterp_at<Real, M>(W, P[s].u_at(P[s].k), tg[s]);
             }
           }
         }
@@ -1157,7 +1165,7 @@ k_edges_flat(const __grid_constant__ ChainDev<Real, kMaxJ> c, long long E, const
         winterp_begin<Real, M, kMaxJ>(c, a6, b6, W);
         P.qa = q_kept + (long long)iw * n * Nqp + a; P.qb = q_kept + (long long)jw * n * Nqp + b; P.sa = Nqp; P.sb = Nqp;
         pair_arm<Real, M>(ent.z, P, L);
-        winterp_at<Real, M>(W, Real(1) / Real(P.ndivs + 1), tg);
+        winterp_at<Real, M>(W, P.u_at(1), tg);
       }
       __syncwarp();
       qhead += min(__popc(needm), avail);
@@ -1178,7 +1186,7 @@ k_edges_flat(const __grid_constant__ ChainDev<Real, kMaxJ> c, long long E, const
         if (st != IK_OK) verdict = 0;                             // graph.py:964-966
         else {
           verdict = pair_advance<FLAG>(c, mem, o.s2, thr2, P, L);
-          if (verdict < 0) winterp_at<Real, M>(W, Real(P.k) / Real(P.ndivs + 1), tg);
+          if (verdict < 0) winterp_at<Real, M>(W, P.u_at(P.k), tg);
         }
       }
     }
@@ -1252,7 +1260,7 @@ k_edges_recheck(const __grid_constant__ ChainDev<Real, kMaxJ> c, const int32_t *
         else {
           kstart = (k0 >= 2 && k0 <= P.ndivs) ? k0 - 1 : 1;
           P.k = kstart;
-          const Real u = Real(P.k) / Real(P.ndivs + 1);
+          const Real u = P.u_at(P.k);
           lane_begin_lerp<Real, M>(L, P.qa, P.sa, P.qb, P.sb, u);
           winterp_at<Real, M>(W, u, tg);
         }
@@ -1271,7 +1279,7 @@ k_edges_recheck(const __grid_constant__ ChainDev<Real, kMaxJ> c, const int32_t *
         if (st != IK_OK) verdict = 0;
         else {
           verdict = pair_advance(c, mem, o.s2, thr2, P, L, P.k == kstart && kstart > 1);
-          if (verdict < 0) winterp_at<Real, M>(W, Real(P.k) / Real(P.ndivs + 1), tg);
+          if (verdict < 0) winterp_at<Real, M>(W, P.u_at(P.k), tg);
         }
       }
     }

@@ -675,11 +675,14 @@ GRR_DEV int lane_step(const ChainT &c, LaneIK<Real, M> &L, LaneMem<Real, col_row
     else if (L.check_convx && L.it >= c.max_iters) st = IK_MAXIT;
     else {
       Real test = o.test;
-      const Real pn = sqrt_(o.pn2);
-      if (FLAG && abs_(pn - L.stpmax) < c.fl_rel * L.stpmax) L.phase |= PH_HARD | PH_R_STPMAX;
-      if (pn > L.stpmax) {
+      // |p| > stpmax is tested in squares (L.stpmax holds max(|x|^2, n^2), stpmax = 10 sqrt of it): no square root on the
+      // common path; the roots are taken only when the step is clipped
+      const Real stp2 = Real(100) * L.stpmax;
+      if (FLAG && abs_(o.pn2 - stp2) < Real(2) * c.fl_rel * stp2) L.phase |= PH_HARD | PH_R_STPMAX;
+      if (o.pn2 > stp2) {
         // clip the step to stpmax (rare): rescale p in memory and evaluate its first trial again
-        const Real sc = L.stpmax / pn;
+        const Real pn = sqrt_(o.pn2);
+        const Real sc = (Real(10) * sqrt_(L.stpmax)) / pn;
         test = 0;
         const int T = mem.T;
         Real *pp = mem.p();
@@ -721,7 +724,7 @@ GRR_DEV int lane_step(const ChainT &c, LaneIK<Real, M> &L, LaneMem<Real, col_row
       conv_test();
       if (conv) st = IK_OK;
       else if (c.max_iters <= 0) st = IK_MAXIT;
-      else { L.stpmax = Real(10) * max_(sqrt_(o.xn2), Real(n)); newstep = true; }
+      else { L.stpmax = max_(o.xn2, Real(n) * Real(n)); newstep = true; }       // stpmax = 10 max(|x|, n), kept squared / 100
     } else {
       if (FLAG && abs_(L.alam - L.alamin) < c.fl_alam * L.alamin) L.phase |= PH_HARD | PH_R_ALAM;
       if (L.alam < L.alamin) {

@@ -38,7 +38,7 @@ static void run_pair(const ChainDev<Real, kMaxJ> &c, const Real *qa, const Real 
   P.qa = qa; P.qb = qb; P.sa = 1; P.sb = 1;
   int verdict = -1, fail = 0, maxit = 0, fstat = 0, fit = 0; double fres = 0;
   if (!pair_begin<Real, M, FLAG>(c, eps, P, L)) verdict = 1;
-  else winterp_at<Real, M>(W, Real(1) / Real(P.ndivs + 1), tg);
+  else winterp_at<Real, M>(W, P.u_at(1), tg);
   while (verdict < 0) {
     PassOut<Real, M> o;
     const bool first = P.k == 1;
@@ -60,7 +60,7 @@ static void run_pair(const ChainDev<Real, kMaxJ> &c, const Real *qa, const Real 
       else {
         verdict = pair_advance<FLAG>(c, mem, o.s2, thr2, P, L);
         if (verdict == 0) fail = 2;
-        if (verdict < 0) winterp_at<Real, M>(W, Real(P.k) / Real(P.ndivs + 1), tg);
+        if (verdict < 0) winterp_at<Real, M>(W, P.u_at(P.k), tg);
       }
     }
   }
