@@ -82,7 +82,7 @@ def lib():
     L.grr_set_flag_scale.argtypes = [vp, dbl]
     L.grr_edges_exact_mode.argtypes = [vp]
     L.grr_ik_sample_sweep.argtypes = [vp, C.c_int, i64, vp, i32, i32, vp, vp, vp, vp, vp, vp, i32, vp, u64, i32, i32, vp, vp, dbl, vp,
-                                      vp, vp]
+                                      vp, vp, i32, i64, i32, vp]
     L.grr_edges_test_listed.argtypes = [vp, C.c_int, vp, vp, vp, i32, i32, dbl, vp, vp, vp, u64, vp, vp]
     L.grr_manifold_knn_list.argtypes = [C.c_int, i64, vp, i32, i32, i32, vp, vp, i32, vp, u64, vp]
     L.grr_manifold_components.argtypes = [C.c_int, i64, vp, i32, i32, i32, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, vp]
@@ -248,15 +248,18 @@ class ChainHandle:
                                         _ptr(nadj), _ptr(counters), _stream(q_raw.device)), "grr_ik_sample_level")
 
     def ik_sample_sweep(self, order, Nq, params, node_uid, lower_ptr, lower_idx, degree, q_kept, count, seed, sample_offset,
-                        seed_from_adjacent, q_rand, status_rand, thresh, ready, counters=None):
+                        seed_from_adjacent, q_rand, status_rand, thresh, ready, counters=None, biased=None):
         """The seeded sweep as one dataflow launch.  Returns False when a node's working set does not fit shared memory
-        (the caller then runs the level-by-level launches)."""
+        (the caller then runs the level-by-level launches).  biased = (start_total, nodes_with_configs, total_after int64
+        [Nw] device tensor): the `biased=True` re-sampling of solver.py:780-785 (q_rand / status_rand are None)."""
         global LAUNCHES
-        rc = lib().grr_ik_sample_sweep(self._h, dtype_code(q_rand.dtype), order.shape[0], _ptr(order), int(Nq), q_rand.shape[2],
+        b = biased or (0, 0, None)
+        rc = lib().grr_ik_sample_sweep(self._h, dtype_code(q_kept.dtype), order.shape[0], _ptr(order), int(Nq),
+                                       q_rand.shape[2] if q_rand is not None else round_up4(Nq),
                                        _ptr(params), _ptr(node_uid), _ptr(lower_ptr), _ptr(lower_idx), _ptr(degree), _ptr(q_kept),
                                        q_kept.shape[2], _ptr(count), C.c_uint64(int(seed) & (2 ** 64 - 1)), int(sample_offset),
                                        1 if seed_from_adjacent else 0, _ptr(q_rand), _ptr(status_rand), float(thresh), _ptr(ready),
-                                       _ptr(counters), _stream(q_rand.device))
+                                       _ptr(counters), _stream(q_kept.device), 1 if biased else 0, int(b[0]), int(b[1]), _ptr(b[2]))
         if rc == -5:
             return False
         check(rc, "grr_ik_sample_sweep")

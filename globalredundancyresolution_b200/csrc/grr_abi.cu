@@ -463,20 +463,23 @@ int grr_ik_sample_sweep(grr_handle_t h, int dtype, int64_t Nw, const int32_t *or
                         const int32_t *node_uid, const int32_t *lower_ptr, const int32_t *lower_idx, const int32_t *degree,
                         void *q_kept, int32_t Nqp_kept, int32_t *count, uint64_t seed, int32_t sample_offset,
                         int32_t seed_from_adjacent, const void *q_rand, const uint8_t *status_rand, double thresh, int32_t *ready,
-                        uint64_t *counters, void *stream) {
+                        uint64_t *counters, void *stream, int32_t biased, int64_t start_total, int32_t nodes_with_configs,
+                        int64_t *total_after) {
   GRR_CHECK_HANDLE(h);
   const Ops *ops = pick_ops(dtype, h->hc.mode);
   if (!ops) { set_error("bad dtype %d", dtype); return -1; }
   if (Nw <= 0 || Nq <= 0) return 0;
   if (Nqr < Nq) { set_error("grr_ik_sample_sweep: Nqr < Nq"); return -1; }
-  if (!order || !params || !node_uid || !lower_ptr || !lower_idx || !degree || !q_kept || !count || !q_rand || !status_rand || !ready) {
+  if (!order || !params || !node_uid || !lower_ptr || !lower_idx || !degree || !q_kept || !count || !ready ||
+      (!biased && (!q_rand || !status_rand)) || (biased && !total_after)) {
     set_error("grr_ik_sample_sweep: null buffer"); return -1;
   }
   unsigned long long *work = work_slot(h);
   if (!work) return -3;
   const int rc = ops->ik_sweep(h->hc, Nw, order, Nq, Nqr, params, node_uid, lower_ptr, lower_idx, degree, q_kept, Nqp_kept, count, seed,
                                sample_offset, seed_from_adjacent, q_rand, status_rand, thresh, ready, work,
-                               (unsigned long long *)counters, (cudaStream_t)stream);
+                               (unsigned long long *)counters, (cudaStream_t)stream, biased ? 1 : 0, (long long)start_total,
+                               nodes_with_configs, (long long *)total_after);
   if (rc == -5) set_error("grr_ik_sample_sweep: Nq=%d, n=%d: a node's working set does not fit shared memory (use the level launches)", Nq, h->hc.n);
   return rc;
 }

@@ -65,7 +65,8 @@ struct Ops {
   int (*ik_sweep)(const HostChain &, long long Nn, const int32_t *order, int Nq, int Nqr, const void *params, const int32_t *uid,
                   const int32_t *lower_ptr, const int32_t *lower_idx, const int32_t *degree, void *Qk, int Nqk, int32_t *count,
                   unsigned long long seed, int sample_offset, int seed_from_adjacent, const void *q_rand, const uint8_t *st_rand,
-                  double thresh, int32_t *ready, unsigned long long *work, unsigned long long *counters, cudaStream_t st);
+                  double thresh, int32_t *ready, unsigned long long *work, unsigned long long *counters, cudaStream_t st,
+                  int biased, long long start_total, int nodes_with_configs, long long *total_after);
   int (*edges_listed)(const HostChain &, const int32_t *wedges, const void *params, const void *q_kept, int Nq, int Nqp,
                       double epsilon, uint32_t *mask, uint32_t *edge_stats, const unsigned long long *list,
                       unsigned long long cap, unsigned long long *work, unsigned long long *counters, cudaStream_t st);

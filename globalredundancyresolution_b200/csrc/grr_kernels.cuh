@@ -225,7 +225,12 @@ __device__ __forceinline__ void st_release_(int32_t *p, int v) {
 #endif
 }
 
-template <typename Real, int M, bool PL>
+// BIASED (solver.py:780-785, `biased=True` on a roadmap that already has configs): a node's number of random-start
+// attempts is NConfigsPerPoint * configuration_count / (nodes_with_configs * len(qlist)) with configuration_count the
+// RUNNING total of the sweep, so node i also waits for node i - 1 (order[] is then the identity), reads the total node
+// i - 1 published and runs its random-start attempts itself, T at a time (they cannot be precomputed: their number is
+// known only now), each round filtered into the kept list before the next.
+template <typename Real, int M, bool PL, bool BIASED>
 __global__ void __launch_bounds__(128)
 k_sweep_dataflow(const __grid_constant__ ChainDev<Real, kMaxJ> c, long long Nn, const int32_t *__restrict__ order, int Nq,
                  int Nqr, const Real *__restrict__ params, const int32_t *__restrict__ uid,
@@ -233,19 +238,21 @@ k_sweep_dataflow(const __grid_constant__ ChainDev<Real, kMaxJ> c, long long Nn, 
                  const int32_t *__restrict__ degree, Real *Qk, int Nqk, int32_t *count, unsigned long long seed,
                  int sample_offset, int seed_from_adjacent, const Real *__restrict__ q_rand,
                  const uint8_t *__restrict__ st_rand, Real thresh, int32_t *ready, unsigned long long *work,
-                 unsigned long long *counters) {
+                 unsigned long long *counters, long long start_total, int nodes_with_configs, long long *total_after) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int n = c.n, dw = (c.mode == 2 ? 6 : 3);
   const int T = blockDim.x, tid = threadIdx.x, lane = tid & 31;
-  const int NqS = (Nq + 3) & ~3, Cmax = 2 * Nq, Wc = (Cmax + 31) >> 5;
+  // candidates of one filter batch: seeded + random (<= 2 Nq); BIASED: seeded (<= Nq), then rounds of T random ones
+  const int NqS = (Nq + 3) & ~3, Cmax = (BIASED && 2 * Nq < 128) ? 128 : 2 * Nq, Wc = (Cmax + 31) >> 5;
   Real *lanes = reinterpret_cast<Real *>(smem_raw);
   Real *cseed = lanes + (size_t)T * lane_reals<col_rows(M, PL)>(n);           // [n][NqS] seeded results
-  uint32_t *close = reinterpret_cast<uint32_t *>(cseed + (size_t)n * NqS);     // [Cmax][Wc] candidate s close to candidate t < s
+  Real *crand = cseed + (size_t)n * NqS;                                       // BIASED: [n][T] random-start results of one round
+  uint32_t *close = reinterpret_cast<uint32_t *>(crand + (BIASED ? (size_t)n * T : 0));   // [Cmax][Wc] candidate s close to candidate t < s
   int32_t *clist = reinterpret_cast<int32_t *>(close + (size_t)Cmax * Wc);     // [Cmax] ok candidates in sweep order: s (seeded) / Nq + s (random)
   int32_t *slot = clist + Cmax;                                                // [Cmax] position in the kept list or -1
-  uint8_t *sst = reinterpret_cast<uint8_t *>(slot + Cmax);                     // [NqS] status of the seeded attempts
-  uint8_t *cold = sst + NqS;                                                   // [Cmax] candidate close to an already kept config
-  __shared__ long long s_pos;
+  uint8_t *sst = reinterpret_cast<uint8_t *>(slot + Cmax);                     // [max(NqS, T)] status of the attempts of the current batch
+  uint8_t *cold = sst + (NqS > T ? NqS : T);                                   // [Cmax] candidate close to an already kept config
+  __shared__ long long s_pos, s_total;
   __shared__ int s_nok, s_kept;
   LaneMem<Real, col_rows(M, PL)> mem;
   mem.init(lanes + tid, T, n);
@@ -278,134 +285,213 @@ k_sweep_dataflow(const __grid_constant__ ChainDev<Real, kMaxJ> c, long long Nn, 
     Real w[6];
     for (int k = 0; k < dw; k++) w[k] = params[(long long)node * dw + k];
     target_from_params<Real, M, kMaxJ>(c, w, tg);
-    // ---- seeded attempts (solver.py:786-815): lane machines, attempt s on lane s % T ----
-    int s_mine = tid;                 // next attempt of this lane
-    int s_run = -1;                   // attempt in flight
-    for (;;) {
-      if (s_run < 0 && s_mine < numAdjacent) {
-        s_run = s_mine; s_mine += T;
-        uint32_t r[4];
-        philox4x32_10((uint32_t)uid[node], (uint32_t)(sample_offset + s_run), 0u, 1u, (uint32_t)seed, (uint32_t)(seed >> 32), r);
-        int pick = (int)(r[0] % (uint32_t)na), jn = -1;
-        for (int k = 0; k < nlow; k++) {
-          const int cand = lower_idx[lp0 + k];
-          if (__ldcg(count + cand) > 0) { if (pick == 0) { jn = cand; break; } pick--; }
-        }
-        GRR_DCHECK(jn >= 0 && jn < node && na > 0);
-        const int cfg = (int)(r[1] % (uint32_t)__ldcg(count + jn));
-        GRR_DCHECK(cfg < Nqk);
-        const Real *srcq = Qk + ((long long)jn * n) * Nqk + cfg;
-        Real *xo = mem.xold();
-        for (int j = 0; j < n; j++) xo[j * mem.T] = __ldcg(srcq + (long long)j * Nqk);
-        lane_begin_mem(L, mem);
-      }
-      if (__all_sync(0xffffffffu, s_run < 0)) break;
-      PassOut<Real, M> o;
-      if constexpr (PL) lane_pass_planar<Real, false>(c, tg, L, mem, nullptr, 0, o);
-      else lane_pass<Real, M, false>(c, tg, L, mem, nullptr, 0, o);
-      const int st = lane_step<Real, M, PL>(c, L, mem, o, s_run >= 0);
-      if (s_run >= 0 && st != IK_RUNNING) {
-        for (int j = 0; j < n; j++) cseed[j * NqS + s_run] = L.res[j * mem.T];
-        sst[s_run] = (uint8_t)st;
-        cnt.iters += L.it; cnt.evals += L.evals;
-        s_run = -1;
-        lane_begin_mem(L, mem);
-      }
-    }
-    __syncthreads();
-    // ---- candidates in the sweep's order: seeded, then the first Nq - numAdjacent + numFailed random-start results ----
-    if (tid < 32) {
-      int nfail = 0;
-      for (int s = lane; s < numAdjacent; s += 32) nfail += (sst[s] != 0);
-      nfail = __reduce_add_sync(0xffffffffu, nfail);
-      const int nseed = numAdjacent;
-      // solver.py:779,817: numRandomSamples = NConfigsPerPoint - numAdjacentSamples (also when seeding is off) + numFailed
-      const int nrand = Nq - numAdjRef + nfail;
-      const uint8_t *str = st_rand + (long long)node * Nqr;
-      int nok = 0;
-      for (int base = 0; base < nseed + nrand; base += 32) {
-        const int ci = base + lane;
-        bool ok = false;
-        if (ci < nseed) ok = (sst[ci] == 0);
-        else if (ci < nseed + nrand) ok = (str[ci - nseed] == 0);
-        const unsigned m = __ballot_sync(0xffffffffu, ok);
-        GRR_DCHECK(nok + __popc(m) <= Cmax && nseed + nrand <= Cmax && nrand <= Nqr);
-        if (ok) clist[nok + __popc(m & ((1u << lane) - 1u))] = (ci < nseed) ? ci : Nq + (ci - nseed);
-        nok += __popc(m);
-      }
-      if (lane == 0) {
-        s_nok = nok;
-        if (counters) {
-          atomicAdd(counters + GRR_CNT_IK_SOLVES, (unsigned long long)(nseed + nrand));
-          atomicAdd(counters + GRR_CNT_IK_OK, (unsigned long long)nok);
-        }
-      }
-    }
-    for (int k = tid; k < Cmax * Wc; k += T) close[k] = 0;
-    for (int k = tid; k < Cmax; k += T) cold[k] = 0;
-    __syncthreads();
-    const int C = s_nok;
-    const int kept0 = count[node];                // this node's own list: written by this CTA only (or before the launch)
+    const int kept_start = count[node];           // this node's own list: written by this CTA only (or before the launch)
     Real *out = Qk + (long long)node * n * Nqk;
     const Real *randq = q_rand + (long long)node * n * Nqr;
     auto cand_ptr = [&](int ci, int &stride) -> const Real * {
       const int id = clist[ci];
       if (id < Nq) { stride = NqS; return cseed + id; }
+      if (BIASED) { stride = T; return crand + (id - Nq); }
       stride = Nqr; return randq + (id - Nq);
     };
-    // all distances at once: (candidate s, candidate t < s) and (candidate s, already kept k)
-    const int npair = C * (C - 1) / 2;
-    for (int pidx = tid; pidx < npair + C * kept0; pidx += T) {
-      int sidx, tidx;
-      bool vs_old = pidx >= npair;
-      if (!vs_old) {
-        // row s has s entries: s = floor((1 + sqrt(1 + 8 p)) / 2)
-        sidx = (int)((1.0f + sqrtf(1.0f + 8.0f * (float)pidx)) * 0.5f);
-        while (sidx * (sidx - 1) / 2 > pidx) sidx--;
-        while ((sidx + 1) * sidx / 2 <= pidx) sidx++;
-        tidx = pidx - sidx * (sidx - 1) / 2;
-      } else { sidx = (pidx - npair) / kept0; tidx = (pidx - npair) - sidx * kept0; }
-      int ss, ts;
-      const Real *a = cand_ptr(sidx, ss);
-      Real d2 = 0;
-      if (!vs_old) {
-        const Real *b = cand_ptr(tidx, ts);
-        for (int j = 0; j < n; j++) { Real d = a[(long long)j * ss] - b[(long long)j * ts]; d2 += d * d; }
-        if (sqrt_(d2) < thresh) atomicOr(&close[sidx * Wc + (tidx >> 5)], 1u << (tidx & 31));
-      } else {
-        for (int j = 0; j < n; j++) { Real d = a[(long long)j * ss] - out[j * Nqk + tidx]; d2 += d * d; }
-        if (sqrt_(d2) < thresh) cold[sidx] = 1;
-      }
-    }
-    __syncthreads();
-    // one warp walks the candidates in order (first wins, solver.py:802-813,824-835)
-    if (tid < 32) {
-      uint32_t keepw[4] = {0, 0, 0, 0};        // lane owns words lane, lane + 32, ... of the keep mask (Wc <= 128)
-      int kept = kept0;
-      for (int sidx = 0; sidx < C; sidx++) {
-        bool hit = false;
+    // attempts [0, count) of one batch as lane machines, attempt s on lane s % T; kind 0: seeded from a lower neighbour's
+    // config (solver.py:794-799) -> cseed, kind 1 (BIASED): random start number s0 + s (the S2 stream) -> crand
+    auto run_attempts = [&](int kind, int nattempt, int s0) {
+      int s_mine = tid, s_run = -1;
+      for (;;) {
+        if (s_run < 0 && s_mine < nattempt) {
+          s_run = s_mine; s_mine += T;
+          Real *xo = mem.xold();
+          if (kind == 0) {
+            uint32_t r[4];
+            philox4x32_10((uint32_t)uid[node], (uint32_t)(sample_offset + s_run), 0u, 1u, (uint32_t)seed, (uint32_t)(seed >> 32), r);
+            int pick = (int)(r[0] % (uint32_t)na), jn = -1;
+            for (int k = 0; k < nlow; k++) {
+              const int cand = lower_idx[lp0 + k];
+              if (__ldcg(count + cand) > 0) { if (pick == 0) { jn = cand; break; } pick--; }
+            }
+            GRR_DCHECK(jn >= 0 && jn < node && na > 0);
+            const int cfg = (int)(r[1] % (uint32_t)__ldcg(count + jn));
+            GRR_DCHECK(cfg < Nqk);
+            const Real *srcq = Qk + ((long long)jn * n) * Nqk + cfg;
+            for (int j = 0; j < n; j++) xo[j * mem.T] = __ldcg(srcq + (long long)j * Nqk);
+          } else {
+            const uint32_t id = (uint32_t)uid[node], smp = (uint32_t)(s0 + s_run + sample_offset);
+            for (int jb = 0; jb * 4 < n; jb++) {
+              uint32_t r[4];
+              philox4x32_10(id, smp, (uint32_t)jb, 0u, (uint32_t)seed, (uint32_t)(seed >> 32), r);
 #pragma unroll
-        for (int q = 0; q < 4; q++) { const int wd = lane + 32 * q; if (wd < Wc) hit |= (close[sidx * Wc + wd] & keepw[q]) != 0; }
-        hit = __any_sync(0xffffffffu, hit) || cold[sidx];
-        const bool take = !hit && kept < Nqk;
-        if (take) {
-          const int wd = sidx >> 5;
-#pragma unroll
-          for (int q = 0; q < 4; q++) if (wd == lane + 32 * q) keepw[q] |= 1u << (sidx & 31);
+              for (int k = 0; k < 4; k++) {
+                const int j = jb * 4 + k;
+                if (j < n) xo[j * mem.T] = (Real)fmaf((float)(r[k] >> 8) * (1.0f / 16777216.0f), c.srange[j], c.slo[j]);
+              }
+            }
+          }
+          lane_begin_mem(L, mem);
         }
-        if (lane == 0) slot[sidx] = take ? kept : -1;
-        kept += take;
+        if (__all_sync(0xffffffffu, s_run < 0)) break;
+        PassOut<Real, M> o;
+        if constexpr (PL) lane_pass_planar<Real, false>(c, tg, L, mem, nullptr, 0, o);
+        else lane_pass<Real, M, false>(c, tg, L, mem, nullptr, 0, o);
+        const int st = lane_step<Real, M, PL>(c, L, mem, o, s_run >= 0);
+        if (s_run >= 0 && st != IK_RUNNING) {
+          Real *dst = (kind == 0) ? cseed + s_run : crand + s_run;
+          const int ds = (kind == 0) ? NqS : T;
+          for (int j = 0; j < n; j++) dst[j * ds] = L.res[j * mem.T];
+          sst[s_run] = (uint8_t)st;
+          cnt.iters += L.it; cnt.evals += L.evals;
+          s_run = -1;
+          lane_begin_mem(L, mem);
+        }
       }
-      if (lane == 0) s_kept = kept;
-    }
+    };
+    // filter the candidates clist[0, C) (in order) against the kept list out[0, kept_in) and against each other, append
+    // the survivors (first wins, solver.py:802-813,824-835); s_kept = new length.  All distances at once into a bit
+    // matrix, then one warp walks the candidates in order.
+    auto filter_batch = [&](int C, int kept_in) {
+      for (int k = tid; k < C * Wc; k += T) close[k] = 0;
+      for (int k = tid; k < C; k += T) cold[k] = 0;
+      __syncthreads();
+      const int npair = C * (C - 1) / 2;
+      for (int pidx = tid; pidx < npair + C * kept_in; pidx += T) {
+        int sidx, tidx;
+        const bool vs_old = pidx >= npair;
+        if (!vs_old) {
+          // row s has s entries: s = floor((1 + sqrt(1 + 8 p)) / 2)
+          sidx = (int)((1.0f + sqrtf(1.0f + 8.0f * (float)pidx)) * 0.5f);
+          while (sidx * (sidx - 1) / 2 > pidx) sidx--;
+          while ((sidx + 1) * sidx / 2 <= pidx) sidx++;
+          tidx = pidx - sidx * (sidx - 1) / 2;
+        } else { sidx = (pidx - npair) / kept_in; tidx = (pidx - npair) - sidx * kept_in; }
+        int ss, ts;
+        const Real *a = cand_ptr(sidx, ss);
+        Real d2 = 0;
+        if (!vs_old) {
+          const Real *b = cand_ptr(tidx, ts);
+          for (int j = 0; j < n; j++) { Real d = a[(long long)j * ss] - b[(long long)j * ts]; d2 += d * d; }
+          if (sqrt_(d2) < thresh) atomicOr(&close[sidx * Wc + (tidx >> 5)], 1u << (tidx & 31));
+        } else {
+          for (int j = 0; j < n; j++) { Real d = a[(long long)j * ss] - out[j * Nqk + tidx]; d2 += d * d; }
+          if (sqrt_(d2) < thresh) cold[sidx] = 1;
+        }
+      }
+      __syncthreads();
+      if (tid < 32) {
+        uint32_t keepw[4] = {0, 0, 0, 0};        // lane owns words lane, lane + 32, ... of the keep mask (Wc <= 128)
+        int kept = kept_in;
+        for (int sidx = 0; sidx < C; sidx++) {
+          bool hit = false;
+#pragma unroll
+          for (int q = 0; q < 4; q++) { const int wd = lane + 32 * q; if (wd < Wc) hit |= (close[sidx * Wc + wd] & keepw[q]) != 0; }
+          hit = __any_sync(0xffffffffu, hit) || cold[sidx];
+          const bool take = !hit && kept < Nqk;
+          if (take) {
+            const int wd = sidx >> 5;
+#pragma unroll
+            for (int q = 0; q < 4; q++) if (wd == lane + 32 * q) keepw[q] |= 1u << (sidx & 31);
+          }
+          if (lane == 0) slot[sidx] = take ? kept : -1;
+          kept += take;
+        }
+        if (lane == 0) s_kept = kept;
+      }
+      __syncthreads();
+      for (int k = tid; k < C * n; k += T) {
+        const int sidx = k / n, j = k - sidx * n;
+        const int sl = slot[sidx];
+        GRR_DCHECK(sl < Nqk);
+        if (sl >= 0) { int ss; const Real *a = cand_ptr(sidx, ss); out[j * Nqk + sl] = a[(long long)j * ss]; }
+      }
+      __syncthreads();
+    };
+    // ---- seeded attempts (solver.py:786-815) ----
+    run_attempts(0, numAdjacent, 0);
     __syncthreads();
-    for (int k = tid; k < C * n; k += T) {
-      const int sidx = k / n, j = k - sidx * n;
-      const int sl = slot[sidx];
-      GRR_DCHECK(sl < Nqk);
-      if (sl >= 0) { int ss; const Real *a = cand_ptr(sidx, ss); out[j * Nqk + sl] = a[(long long)j * ss]; }
+    int nfail = 0;
+    for (int s = 0; s < numAdjacent; s++) nfail += (sst[s] != 0);          // (every thread; numAdjacent <= Nq)
+    if constexpr (!BIASED) {
+      // candidates in the sweep's order: seeded, then the first Nq - numAdjacent + numFailed precomputed random-start results
+      const int nseed = numAdjacent;
+      const int nrand = Nq - numAdjRef + nfail;                            // solver.py:779,817
+      if (tid < 32) {
+        const uint8_t *str = st_rand + (long long)node * Nqr;
+        int nok = 0;
+        for (int base = 0; base < nseed + nrand; base += 32) {
+          const int ci = base + lane;
+          bool ok = false;
+          if (ci < nseed) ok = (sst[ci] == 0);
+          else if (ci < nseed + nrand) ok = (str[ci - nseed] == 0);
+          const unsigned m = __ballot_sync(0xffffffffu, ok);
+          GRR_DCHECK(nok + __popc(m) <= Cmax && nseed + nrand <= Cmax && nrand <= Nqr);
+          if (ok) clist[nok + __popc(m & ((1u << lane) - 1u))] = (ci < nseed) ? ci : Nq + (ci - nseed);
+          nok += __popc(m);
+        }
+        if (lane == 0) {
+          s_nok = nok;
+          if (counters) {
+            atomicAdd(counters + GRR_CNT_IK_SOLVES, (unsigned long long)(nseed + nrand));
+            atomicAdd(counters + GRR_CNT_IK_OK, (unsigned long long)nok);
+          }
+        }
+      }
+      __syncthreads();
+      filter_batch(s_nok, kept_start);
+    } else {
+      // seeded results first
+      if (tid < 32) {
+        int nok = 0;
+        for (int base = 0; base < numAdjacent; base += 32) {
+          const int ci = base + lane;
+          const bool ok = ci < numAdjacent && sst[ci] == 0;
+          const unsigned m = __ballot_sync(0xffffffffu, ok);
+          if (ok) clist[nok + __popc(m & ((1u << lane) - 1u))] = ci;
+          nok += __popc(m);
+        }
+        if (lane == 0) s_nok = nok;
+      }
+      __syncthreads();
+      unsigned long long n_ok = (unsigned long long)s_nok;
+      filter_batch(s_nok, kept_start);
+      // the running total of the sweep: published by node - 1 (solver.py:763,784,812,833)
+      if (tid == 0) {
+        long long tot = start_total;
+        if (node > 0) { while (ld_acquire_(ready + node - 1) == 0) __nanosleep(64); tot = *((volatile long long *)total_after + (node - 1)); }
+        s_total = tot;
+      }
+      __syncthreads();
+      // numRandomSamples = 0 for a node without configs, else NConfigsPerPoint * configuration_count / (nodes_with_configs * len(qlist))
+      // (Python 2 integer division) with the total and the node's length as they were when its turn began
+      const long long conf = s_total;            // (:779-785 come before this node's own attempts)
+      long long nrand_ll = (kept_start == 0 || nodes_with_configs == 0) ? 0
+                         : ((long long)Nq * conf) / ((long long)nodes_with_configs * (long long)kept_start);
+      const long long nrand = nrand_ll + nfail;
+      for (long long s0 = 0; s0 < nrand; s0 += T) {
+        const int nb = (int)((nrand - s0 < T) ? (nrand - s0) : T);
+        run_attempts(1, nb, (int)s0);
+        __syncthreads();
+        if (tid < 32) {
+          int nok = 0;
+          for (int base = 0; base < nb; base += 32) {
+            const int ci = base + lane;
+            const bool ok = ci < nb && sst[ci] == 0;
+            const unsigned m = __ballot_sync(0xffffffffu, ok);
+            if (ok) clist[nok + __popc(m & ((1u << lane) - 1u))] = Nq + ci;
+            nok += __popc(m);
+          }
+          if (lane == 0) s_nok = nok;
+        }
+        __syncthreads();
+        n_ok += (unsigned long long)s_nok;
+        filter_batch(s_nok, s_kept);
+      }
+      if (tid == 0) {
+        total_after[node] = s_total + (long long)(s_kept - kept_start);
+        if (counters) {
+          atomicAdd(counters + GRR_CNT_IK_SOLVES, (unsigned long long)numAdjacent + (unsigned long long)nrand);
+          atomicAdd(counters + GRR_CNT_IK_OK, n_ok);
+        }
+      }
     }
-    __syncthreads();
     if (tid == 0) {
       count[node] = s_kept;
       __threadfence();
@@ -1452,14 +1538,16 @@ struct Impl {
                       const int32_t *uid, const int32_t *lower_ptr, const int32_t *lower_idx, const int32_t *degree, void *Qk,
                       int Nqk, int32_t *count, unsigned long long seed, int sample_offset, int seed_from_adjacent,
                       const void *q_rand, const uint8_t *st_rand, double thresh, int32_t *ready, unsigned long long *work,
-                      unsigned long long *counters, cudaStream_t st) {
+                      unsigned long long *counters, cudaStream_t st, int biased, long long start_total, int nodes_with_configs,
+                      long long *total_after) {
     if (Nn <= 0) return 0;
     Chain c; fill_chain(h, c);
-    const int NqS = (Nq + 3) & ~3, Cmax = 2 * Nq, Wc = (Cmax + 31) / 32;
+    const int NqS = (Nq + 3) & ~3, Cmax = (biased && 2 * Nq < 128) ? 128 : 2 * Nq, Wc = (Cmax + 31) / 32;
     if (Wc > 128) return -5;
-    const size_t fixed = (size_t)h.n * NqS * sizeof(Real) + (size_t)Cmax * Wc * 4 + (size_t)Cmax * 8 + NqS + Cmax + 64;
     int threads = Nq > 128 ? 128 : 64;
-    const size_t per_lane = (size_t)h.n * (4 + mc(h)) * sizeof(Real);
+    // per lane: the lane machine's joint vectors (+ one result column of the random-start rounds of the biased sweep)
+    const size_t per_lane = (size_t)h.n * (4 + mc(h)) * sizeof(Real) + (biased ? (size_t)h.n * sizeof(Real) + 1 : 0);
+    const size_t fixed = (size_t)h.n * NqS * sizeof(Real) + (size_t)Cmax * Wc * 4 + (size_t)Cmax * 8 + NqS + Cmax + 64;
     while (threads > 32 && fixed + threads * per_lane > 110 * 1024) threads -= 32;
     const size_t smem = fixed + threads * per_lane;
     if (smem > kSmemBudget - 2048) return -5;
@@ -1473,12 +1561,15 @@ struct Impl {
       if (ctas > Nn) ctas = Nn;
       kern<<<(unsigned)ctas, threads, smem, st>>>(c, Nn, order, Nq, Nqr, (const Real *)params, uid, lower_ptr, lower_idx, degree,
                                                   (Real *)Qk, Nqk, count, seed, sample_offset, seed_from_adjacent,
-                                                  (const Real *)q_rand, st_rand, (Real)thresh, ready, work, counters);
+                                                  (const Real *)q_rand, st_rand, (Real)thresh, ready, work, counters, start_total,
+                                                  nodes_with_configs, total_after);
       return 0;
     };
     int rc;
-    if constexpr (kHasPlanar) rc = planar(h) ? launch(k_sweep_dataflow<Real, M, true>) : launch(k_sweep_dataflow<Real, M, false>);
-    else rc = launch(k_sweep_dataflow<Real, M, false>);
+    if constexpr (kHasPlanar) {
+      if (planar(h)) rc = biased ? launch(k_sweep_dataflow<Real, M, true, true>) : launch(k_sweep_dataflow<Real, M, true, false>);
+      else rc = biased ? launch(k_sweep_dataflow<Real, M, false, true>) : launch(k_sweep_dataflow<Real, M, false, false>);
+    } else rc = biased ? launch(k_sweep_dataflow<Real, M, false, true>) : launch(k_sweep_dataflow<Real, M, false, false>);
     if (rc) return rc;
     return check_launch("k_sweep_dataflow");
   }

@@ -515,6 +515,23 @@ class RedundancyResolver(VisibilityMixin):
         }
         return self._levels
 
+    def _sample_phase_biased(self, d, N, seed_from_adjacent, start_total, nodes_with):
+        """solver.py:780-785 (`biased=True` on a roadmap that has configs): one dataflow launch in node order; every node
+        waits for its predecessor's running total and runs its own random-start attempts (k_sweep_dataflow<BIASED>)."""
+        torch = self.resolution._torch()
+        res = self.resolution
+        lv = self._sweep_levels()
+        dev = res.torch_device
+        order = torch.arange(self.Nw, dtype=torch.int32, device=dev)
+        ready = torch.empty(self.Nw, dtype=torch.int32, device=dev)
+        total_after = torch.zeros(self.Nw, dtype=torch.int64, device=dev)
+        ok = res.chain.ik_sample_sweep(order, N, d["params_s"], d["uid"], lv["lower_ptr"], lv["lower_idx"], lv["degree"], d["Qs"],
+                                       d["count"], self.seed, self.attempts, seed_from_adjacent, None, None, DEDUP_THRESHOLD, ready,
+                                       d["counters"], biased=(start_total, nodes_with, total_after))
+        if not ok:
+            raise NotImplementedError("biased re-sampling: NConfigsPerPoint=%d does not fit the sweep kernel's shared memory" % N)
+        self._last_raw = None
+
     def _sample_phase_seeded(self, d, N, seed_from_adjacent):
         """solver.py:757-835 as wavefronts.  The random-start attempts of the sweep depend on no other node, so all
         Nq of them are solved for the whole graph in one launch first; each level then runs only its seeded
@@ -575,10 +592,20 @@ class RedundancyResolver(VisibilityMixin):
         if visibility and start_total != 0:
             raise NotImplementedError("visibility=True grows an empty roadmap only (the reference's incremental visibility "
                                       "path re-runs testAndConnectQccs over existing C-space edges, solver.py:842-848)")
-        if biased and start_total != 0:
-            raise NotImplementedError("biased re-sampling (solver.py:780-785) is not implemented on the device path")
         N = int(NConfigsPerPoint)
-        d = self._ensure_device(self.Nq + N)
+        biased = bool(biased) and start_total != 0           # solver.py:780: no effect on an empty roadmap
+        grow = N
+        if biased:
+            if order_independent:
+                raise NotImplementedError("biased re-sampling is defined by the sequential sweep (solver.py:780-785); "
+                                          "call sampleConfigurationSpace without order_independent=True")
+            # room for the extra attempts of sparse nodes: N * total / (nodes_with * len) each, with the total allowed to
+            # grow by half during the sweep; configs beyond the capacity are dropped (the oracle is given the same cap)
+            cnt = old_counts.cpu().numpy().astype(np.int64)
+            nodes_with = int((cnt > 0).sum())
+            est = np.where(cnt > 0, N + (N * (3 * start_total // 2)) // (nodes_with * np.maximum(cnt, 1)) + 1, N)
+            grow = int(min(max(N, int(est.max())), 1024))
+        d = self._ensure_device(self.Nq + grow)
         res = self.resolution
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
         d["counters"].zero_()
@@ -588,6 +615,8 @@ class RedundancyResolver(VisibilityMixin):
         ev[0].record()
         if order_independent:
             self._sample_phase(d, N, 0, self.Nw)
+        elif biased:
+            self._sample_phase_biased(d, N, bool(seedFromAdjacent), start_total, nodes_with)
         else:
             self._sample_phase_seeded(d, N, bool(seedFromAdjacent))
         if visibility:
@@ -595,7 +624,8 @@ class RedundancyResolver(VisibilityMixin):
             # :842-848: testAndConnectQccs(i, j) for the lower-numbered neighbours j of i -- outer loop over i's components
             self.constructSelfMotionManifolds(k)
         ev[1].record()
-        self.attempts += N
+        # Philox sample indices used so far per node (the biased sweep may use more than N random starts on a node)
+        self.attempts += (1 << 16) if biased else N
         if connect:
             if visibility:
                 self._connect_visibility(None, 10, swap=1)

@@ -126,12 +126,18 @@ int grr_ik_sample(grr_handle_t h, int dtype, int64_t Nw, int32_t Nq, int32_t Nqp
  * ready [dev] i32 [Nw] (zeroed by the call), run the node's seeded attempts, filter seeded + precomputed random-start
  * results (q_rand / status_rand as for grr_dedup_sweep) in the sweep's order into q_kept / count and release the node's
  * flag.  Result identical to the level-by-level calls below, which it replaces when a node's working set (its
- * candidates' distance bit matrix) fits shared memory; returns -5 otherwise. */
+ * candidates' distance bit matrix) fits shared memory; returns -5 otherwise.
+ * biased != 0 (solver.py:780-785, `biased=True` on a roadmap that already holds start_total configs in nodes_with_configs
+ * nodes): node i makes Nq * configuration_count / (nodes_with_configs * count_i) random-start attempts (none if it has
+ * no configs), configuration_count being the running total of the sweep -- so `order` must be 0..Nw-1, node i also waits
+ * for node i - 1, whose total it reads from total_after [dev] i64 [Nw], and runs its random-start attempts itself
+ * (q_rand / status_rand are not read, Nqr = Nq); configs beyond the capacity Nqp_kept are dropped. */
 int grr_ik_sample_sweep(grr_handle_t h, int dtype, int64_t Nw, const int32_t *order, int32_t Nq, int32_t Nqr, const void *params,
                         const int32_t *node_uid, const int32_t *lower_ptr, const int32_t *lower_idx, const int32_t *degree,
                         void *q_kept, int32_t Nqp_kept, int32_t *count, uint64_t seed, int32_t sample_offset,
                         int32_t seed_from_adjacent, const void *q_rand, const uint8_t *status_rand, double thresh, int32_t *ready,
-                        uint64_t *counters, void *stream);
+                        uint64_t *counters, void *stream, int32_t biased, int64_t start_total, int32_t nodes_with_configs,
+                        int64_t *total_after);
 int grr_ik_sample_level(grr_handle_t h, int dtype, int64_t L, const int32_t *node_list, int32_t Nq, int32_t Nqr,
                         const void *params, const int32_t *node_uid, const int32_t *lower_ptr, const int32_t *lower_idx,
                         const int32_t *degree, const void *q_kept, int32_t Nqp_kept, const int32_t *count, uint64_t seed,

@@ -517,19 +517,28 @@ void orc_sample_nodes(const orc_chain *c, int64_t Nw, const double *params, cons
 /* order; degree[i] = len(Gw.neighbors(i)).  q_kept/count are in-out (incremental growth:  */
 /* existing configs take part in the dedup; solver.py:759).  cap = slots per node.          */
 /* ------------------------------------------------------------------------------------- */
-void orc_sample_seeded(const orc_chain *c, int64_t Nw, const double *params, const int32_t *node_uid,
-                       const int32_t *lower_ptr, const int32_t *lower_idx, const int32_t *degree, int32_t Nq,
-                       uint64_t seed, int32_t sample_offset, int32_t seed_from_adjacent, double dedup_thresh,
-                       int32_t cap, double *q_kept, int32_t *count, int64_t *stats /* [4]: adj tries, adj ok, rnd tries, rnd ok */) {
+/* biased != 0: solver.py:780-785 -- on a roadmap that already has configs, numRandomSamples of a node is 0 if it has     */
+/* no configs, else NConfigsPerPoint * configuration_count / (number_of_nodes_with_configurations * len(qlist)) in     */
+/* Python 2 integer arithmetic, configuration_count being the running total of the sweep (incremented by every addNode). */
+void orc_sample_seeded_b(const orc_chain *c, int64_t Nw, const double *params, const int32_t *node_uid,
+                         const int32_t *lower_ptr, const int32_t *lower_idx, const int32_t *degree, int32_t Nq,
+                         uint64_t seed, int32_t sample_offset, int32_t seed_from_adjacent, double dedup_thresh,
+                         int32_t cap, double *q_kept, int32_t *count, int64_t *stats /* [4]: adj tries, adj ok, rnd tries, rnd ok */,
+                         int32_t biased) {
   const int n = c->n, dw = wdim(c);
   int64_t st_adj = 0, st_adj_ok = 0, st_rnd = 0, st_rnd_ok = 0;
+  int64_t configuration_count = 0, nodes_with = 0;                                 /* :759-764 */
+  for (int64_t i = 0; i < Nw; i++) { configuration_count += count[i]; nodes_with += (count[i] > 0); }
+  const int64_t start_node_count = configuration_count;
   for (int64_t i = 0; i < Nw; i++) {
     int adj[64], na = 0;
     for (int k = lower_ptr[i]; k < lower_ptr[i + 1]; k++)
       if (count[lower_idx[k]] > 0 && na < 64) adj[na++] = lower_idx[k];            /* solver.py:776 */
     const double frac = degree[i] > 0 ? (double)na / (double)degree[i] : 0.0;      /* :777 */
     const int numAdjacent = (int)(frac * Nq);                                      /* :778 */
-    const int numRandom = Nq - numAdjacent;                                        /* :779 */
+    int64_t numRandom = Nq - numAdjacent;                                          /* :779 */
+    if (biased && start_node_count != 0)                                           /* :780-785 */
+      numRandom = count[i] == 0 ? 0 : ((int64_t)Nq * configuration_count) / (nodes_with * (int64_t)count[i]);
     int numFailed = 0, kept = count[i];
     if (seed_from_adjacent) {
       for (int s = 0; s < numAdjacent; s++) {                                      /* :794-815 */
@@ -546,10 +555,10 @@ void orc_sample_seeded(const orc_chain *c, int64_t Nw, const double *params, con
         int same = 0;
         for (int k = 0; k < kept; k++)
           if (orc_distance(c, x, q_kept + (i * cap + k) * n) < dedup_thresh) { same = 1; break; }
-        if (!same && kept < cap) { memcpy(q_kept + (i * cap + kept) * n, x, sizeof(double) * n); kept++; }
+        if (!same && kept < cap) { memcpy(q_kept + (i * cap + kept) * n, x, sizeof(double) * n); kept++; configuration_count++; }
       }
     }
-    for (int s = 0; s < numRandom + numFailed; s++) {                              /* :817-835 */
+    for (int64_t s = 0; s < numRandom + numFailed; s++) {                          /* :817-835 */
       double x[ORC_MAXJ]; orc_ikinfo info;
       orc_random_seed(c, seed, (uint32_t)node_uid[i], (uint32_t)(sample_offset + s), x);
       orc_ik_solve(c, params + i * dw, x, &info);
@@ -559,11 +568,18 @@ void orc_sample_seeded(const orc_chain *c, int64_t Nw, const double *params, con
       int same = 0;
       for (int k = 0; k < kept; k++)
         if (orc_distance(c, x, q_kept + (i * cap + k) * n) < dedup_thresh) { same = 1; break; }
-      if (!same && kept < cap) { memcpy(q_kept + (i * cap + kept) * n, x, sizeof(double) * n); kept++; }
+      if (!same && kept < cap) { memcpy(q_kept + (i * cap + kept) * n, x, sizeof(double) * n); kept++; configuration_count++; }
     }
     count[i] = kept;
   }
   if (stats) { stats[0] = st_adj; stats[1] = st_adj_ok; stats[2] = st_rnd; stats[3] = st_rnd_ok; }
+}
+void orc_sample_seeded(const orc_chain *c, int64_t Nw, const double *params, const int32_t *node_uid,
+                       const int32_t *lower_ptr, const int32_t *lower_idx, const int32_t *degree, int32_t Nq,
+                       uint64_t seed, int32_t sample_offset, int32_t seed_from_adjacent, double dedup_thresh,
+                       int32_t cap, double *q_kept, int32_t *count, int64_t *stats) {
+  orc_sample_seeded_b(c, Nw, params, node_uid, lower_ptr, lower_idx, degree, Nq, seed, sample_offset, seed_from_adjacent,
+                      dedup_thresh, cap, q_kept, count, stats, 0);
 }
 
 /* ------------------------------------------------------------------------------------- */

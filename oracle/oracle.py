@@ -158,7 +158,7 @@ class Oracle:
                 "count": count}
 
     def sample_seeded(self, params, node_uid, lower_ptr, lower_idx, degree, Nq, seed, cap=None, sample_offset=0,
-                      seed_from_adjacent=True, dedup=1e-2, q_kept=None, count=None):
+                      seed_from_adjacent=True, dedup=1e-2, q_kept=None, count=None, biased=False):
         """solver.py:757-835 sequential sweep.  Returns dict(q_kept [Nw][cap][n], count [Nw], stats [4])."""
         params, node_uid = f64(params), i32(node_uid)
         Nw = params.shape[0]
@@ -167,10 +167,11 @@ class Oracle:
         count = np.zeros(Nw, dtype=np.int32) if count is None else i32(count).copy()
         stats = np.zeros(4, dtype=np.int64)
         lp, li, dg = i32(lower_ptr), i32(lower_idx), i32(degree)
-        self.L.orc_sample_seeded(self.ref, C.c_int64(Nw), _p(params), _p(node_uid, C.c_int32), _p(lp, C.c_int32),
-                                 _p(li, C.c_int32), _p(dg, C.c_int32), C.c_int32(Nq), C.c_uint64(seed),
-                                 C.c_int32(sample_offset), C.c_int32(1 if seed_from_adjacent else 0), C.c_double(dedup),
-                                 C.c_int32(cap), _p(q_kept), _p(count, C.c_int32), _p(stats, C.c_int64))
+        self.L.orc_sample_seeded_b(self.ref, C.c_int64(Nw), _p(params), _p(node_uid, C.c_int32), _p(lp, C.c_int32),
+                                   _p(li, C.c_int32), _p(dg, C.c_int32), C.c_int32(Nq), C.c_uint64(seed),
+                                   C.c_int32(sample_offset), C.c_int32(1 if seed_from_adjacent else 0), C.c_double(dedup),
+                                   C.c_int32(cap), _p(q_kept), _p(count, C.c_int32), _p(stats, C.c_int64),
+                                   C.c_int32(1 if biased else 0))
         return {"q_kept": q_kept, "count": count, "stats": stats}
 
     def workspace_interpolate(self, wa, wb, u):

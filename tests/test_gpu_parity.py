@@ -382,6 +382,44 @@ def test_seeded_sweep_equals_sequential_oracle(built, case, seed_adj):
     np.testing.assert_array_equal(rr.counts(), ref2["count"])
 
 
+@pytest.mark.parametrize("case", ["planar_3R_free", "planar_20R_free", "jaco_free"])
+def test_biased_resampling_equals_sequential_oracle(built, case):
+    """sampleConfigurationSpace(N, biased=True) on a roadmap that has configs (solver.py:780-785): a node's number of
+    random-start attempts is N * configuration_count / (nodes_with_configs * len(qlist)) with configuration_count the
+    running total of the sweep -- sparse nodes get more attempts, empty ones none.  The device runs it as a dataflow in
+    node order (every node waits for its predecessor's total); same counts, configs and attempt statistics as the
+    oracle's sequential loop."""
+    pdef, res = small_problem(*CASES[case], dtype="float32")
+    rr = grr.RedundancyResolver(res, seed=SEED)
+    rr.sampleConfigurationSpace(NQ, connect=False)
+    o = oracle_for(res)
+    lp, li, dg = _lower_csr(res)
+    ref = o.sample_seeded(res.ws_params, rr.node_uid, lp, li, dg, NQ, seed=SEED)
+    np.testing.assert_array_equal(rr.counts(), ref["count"])
+    off = rr.attempts
+    N2 = 6
+    rr.sampleConfigurationSpace(N2, connect=False, biased=True)
+    cap = rr.Nq
+    assert cap > NQ + N2, "sparse nodes must have been given room for more than N attempts"
+    q0 = np.zeros((rr.Nw, cap, res.chain.n)); q0[:, :NQ] = ref["q_kept"]
+    ref2 = o.sample_seeded(res.ws_params, rr.node_uid, lp, li, dg, N2, seed=SEED, cap=cap, sample_offset=off, q_kept=q0,
+                           count=ref["count"], biased=True)
+    cnt = rr.counts()
+    np.testing.assert_array_equal(cnt, ref2["count"])
+    Qs = np.transpose(rr._dev["Qs"][:, :, :cap].double().cpu().numpy(), (0, 2, 1))
+    worst = max((np.abs(Qs[i, :cnt[i]] - ref2["q_kept"][i, :cnt[i]]).max() for i in range(rr.Nw) if cnt[i]), default=0.0)
+    assert worst < 1e-8
+    st = ref2["stats"]
+    assert rr.stats["sample_ik_solves"] == st[0] + st[2] and rr.stats["sample_ik_ok"] == st[1] + st[3]
+    added = cnt.astype(np.int64) - ref["count"]
+    assert (added[ref["count"] == 0] <= N2).all()                  # nodes without configs: seeded attempts only
+    assert st[2] > N2 * int((ref["count"] > 0).sum()) * 0.5          # the random-start budget follows the formula, not N per node
+    print("\n[%s biased] configs %d -> %d, random-start attempts %d (N * nodes = %d), capacity %d"
+          % (case, int(ref["count"].sum()), int(cnt.sum()), int(st[2]), N2 * rr.Nw, cap))
+    with pytest.raises(NotImplementedError):
+        rr.sampleConfigurationSpace(N2, connect=False, biased=True, order_independent=True)
+
+
 def test_seeded_sweep_rescues_6d_problems(built):
     """Random starts converge on ~1 % of attempts for a 7-DOF arm with a 6-D task; seeding from neighbours is
     what makes such roadmaps non-empty in the reference.  Fixed-orientation Baxter-like arm, small grid."""
