@@ -234,6 +234,8 @@ class ShardedResolver(RedundancyResolver):
             raise NotImplementedError("visibility-graph solver is out of scope of the B200 roadmap path")
         if not order_independent:
             raise NotImplementedError("the seeded sweep is single-GPU; shard with order_independent=True")
+        if biased:
+            raise NotImplementedError("biased re-sampling is defined by the sequential sweep (single-GPU)")
         import torch.distributed as dist
         torch = self.resolution._torch()
         res = self.resolution
