@@ -38,8 +38,11 @@ struct LaneCounters {
 //           (parallelQSamplingAtP solver.py:875-885; random phase of sampleConfigurationSpace :817-821)
 //   MODE 1: explicit (target, seed) instances, SoA q[n][P]  (RedundancyResolutionGraph.solve, graph.py:779-790)
 // ------------------------------------------------------------------------------------------
+// double precision, 3 residual rows: CTAs of at most 192 lanes, two per SM (<= 170 registers: 141-160 used, no spills;
+// 256 lanes x 2 would cap the build at 128 registers, which the general pass does not fit without spilling).  Steady
+// state on one B200: config 3 sampling 12.6 ms (1 CTA of 256 per SM: 21.9 ms), config 2 sampling 8.0 ms.
 template <typename Real, int M, int MODE, bool PL>
-__global__ void __launch_bounds__(256, (sizeof(Real) == 8 && M == 3) ? 2 : 1)
+__global__ void __launch_bounds__((sizeof(Real) == 8 && M == 3) ? 192 : 256, (sizeof(Real) == 8 && M == 3) ? 2 : 1)
 k_ik_instances(const __grid_constant__ ChainDev<Real, kMaxJ> c, long long total, int Nq, int Nqp,
                const Real *__restrict__ params, const int32_t *__restrict__ uid, unsigned long long seed, int sample_offset,
                Real *__restrict__ q, uint8_t *__restrict__ status, uint8_t *__restrict__ iters, Real *__restrict__ resid,
@@ -1473,7 +1476,7 @@ struct Impl {
     if (total <= 0) return 0;
     Chain c; fill_chain(h, c);
     int threads, per_sm;
-    lane_geometry(h, 0, 256, threads, per_sm);
+    lane_geometry(h, 0, (sizeof(Real) == 8 && M == 3) ? 192 : 256, threads, per_sm);
     if (threads < 32) { set_error("ik: chain too large for shared memory"); return -2; }
     const size_t smem = (size_t)threads * h.n * (4 + mc(h)) * sizeof(Real);
     long long ctas = (long long)sm_count(h.device) * per_sm;

@@ -43,8 +43,27 @@ GRR_DEV int float_bits_(float t) { int q; memcpy(&q, &t, 4); return q; }
 #endif
 GRR_DEV double fdiv_(double a, double b) { return a / b; }
 GRR_DEV double rcp_ge1_(double a) { return 1.0 / a; }
+#ifdef __CUDA_ARCH__
+GRR_DEV double rsqrt_(double a) { return rsqrt(a); }      // (1 / sqrt as an IEEE square root + IEEE division was 5.7 % of the double-precision edge kernel's samples)
+#else
 GRR_DEV double rsqrt_(double a) { return 1.0 / sqrt(a); }
+#endif
 GRR_DEV double rsqrt_est_(double a) { return 1.0 / sqrt(a); }
+
+// Running maximum of the step-size tests, max_j |d_j| / max(|x_j|, 1) (NewtonRoot's `test`).  Single precision:
+// the value, with a MUFU reciprocal per joint.  Double precision: the maximising fraction (num, den), compared by
+// cross-multiplication -- an IEEE double division per joint and test was 3 % of the kernel -- and divided once per pass.
+template <typename Real> struct RatioMax;
+template <> struct RatioMax<float> {
+  float v = 0;
+  GRR_DEV void add(float num, float rinv, float) { v = fmaxf(v, num * rinv); }
+  GRR_DEV float get() const { return v; }
+};
+template <> struct RatioMax<double> {
+  double n = 0, d = 1;
+  GRR_DEV void add(double num, double, double den) { if (num * d > n * den) { n = num; d = den; } }
+  GRR_DEV double get() const { return n / d; }
+};
 
 // sin/cos for joint angles (|x| << 2^22): Cody-Waite reduction to [-pi/4, pi/4] with the
 // round-to-nearest magic constant (no F2I / I2F), cephes minimax polynomials, quadrant fix-up.
@@ -248,6 +267,7 @@ GRR_DEV void lane_pass_planar_(const ChainT &c, const Target<Real, 3> &tg, const
   Real gc = 1, gs = 0;                       // G = Rot_y(phi): (cos phi, sin phi)
   Real S11 = 0, S12 = 0, S22 = 0, xn2 = 0, s2 = 0;
   Real pn2 = 0, test = 0, testx = 0;
+  RatioMax<Real> rtest, rtestx;           // (chains with joint ranges beyond +-pi/4)
   const int T = mem.T;
   const int sa = src.sa, sb = src.sb;
   const Real *pa = src.a + (n - 1) * sa;
@@ -272,9 +292,10 @@ GRR_DEV void lane_pass_planar_(const ChainT &c, const Target<Real, 3> &tg, const
       test = max_(test, abs_(dir));
       testx = max_(testx, abs_(av - xo));
     } else {
-      const Real rinv = rcp_ge1_(max_(abs_(av), Real(1)));
-      test = max_(test, abs_(dir) * rinv);
-      testx = max_(testx, abs_(av - xo) * rinv);
+      const Real den = (abs_(av) > Real(1)) ? abs_(av) : Real(1);
+      const Real rinv = sizeof(Real) == 4 ? rcp_ge1_(den) : Real(0);
+      rtest.add(abs_(dir), rinv, den);
+      rtestx.add(abs_(av - xo), rinv, den);
     }
     const Real xj = min_(max_(fma_(t, dir, av), jc.bmin), jc.bmax);
     *px = xj; px -= T;
@@ -315,6 +336,7 @@ GRR_DEV void lane_pass_planar_(const ChainT &c, const Target<Real, 3> &tg, const
   }
   if (j == 0) joint(jcA, aA, bA, rA, wA);
   o.xn2 = xn2; o.s2 = s2;
+  if (!SMALL) { test = rtest.get(); testx = rtestx.get(); }
   o.pn2 = pn2; o.test = test; o.testx = testx;
   o.Fw[0] = vx - tg.x[0]; o.Fw[1] = vy - tg.x[1]; o.Fw[2] = vz - tg.x[2];
   o.f = Real(0.5) * (o.Fw[0] * o.Fw[0] + o.Fw[1] * o.Fw[1] + o.Fw[2] * o.Fw[2]);
@@ -345,7 +367,8 @@ GRR_DEV void lane_pass(const ChainT &c, const Target<Real, M> &tg, const LaneIK<
   for (int k = 0; k < 9; k++) G[k] = c.Rtail[k];
 #pragma unroll
   for (int k = 0; k < M * (M + 1) / 2; k++) o.S[k] = 0;
-  Real xn2 = 0, s2 = 0, pn2 = 0, test = 0, testx = 0;
+  Real xn2 = 0, s2 = 0, pn2 = 0;
+  RatioMax<Real> rtest, rtestx;
   const int T = mem.T;
   const int sa = src.sa, sb = src.sb;
   const Real *pa = src.a + (n - 1) * sa;
@@ -382,9 +405,10 @@ GRR_DEV void lane_pass(const ChainT &c, const Target<Real, M> &tg, const LaneIK<
     const Real dir = first ? dnew : fma_(-lk, av, bv);
     if (first) *pbw = dir;
     pn2 = fma_(dir, dir, pn2);
-    const Real rinv = rcp_ge1_(max_(abs_(av), Real(1)));
-    test = max_(test, abs_(dir) * rinv);
-    testx = max_(testx, abs_(av - xo) * rinv);
+    const Real den = (abs_(av) > Real(1)) ? abs_(av) : Real(1);
+    const Real rinv = sizeof(Real) == 4 ? rcp_ge1_(den) : Real(0);
+    rtest.add(abs_(dir), rinv, den);
+    rtestx.add(abs_(av - xo), rinv, den);
     const Real xj = min_(max_(fma_(t, dir, av), jc.bmin), jc.bmax);
     *px = xj; px -= T;
     xn2 += xj * xj;
@@ -428,7 +452,7 @@ GRR_DEV void lane_pass(const ChainT &c, const Target<Real, M> &tg, const LaneIK<
     pc -= M * T;
   }
   o.xn2 = xn2; o.s2 = s2;
-  o.pn2 = pn2; o.test = test; o.testx = testx;
+  o.pn2 = pn2; o.test = rtest.get(); o.testx = rtestx.get();
   o.Fw[0] = v[0] - tg.x[0]; o.Fw[1] = v[1] - tg.x[1]; o.Fw[2] = v[2] - tg.x[2];
   Real f = o.Fw[0] * o.Fw[0] + o.Fw[1] * o.Fw[1] + o.Fw[2] * o.Fw[2];
   m3_Tvec(G, o.Fw, o.FL);

@@ -9,7 +9,7 @@ exact = not any(a == "exact=0" for a in sys.argv[3:])
 over = grr.problems.parse_overrides([a for a in sys.argv[3:] if a != "exact=0"])
 pdef, res, rr = grr.make_program(name, jf, overrides=over)
 rr.exact_edges = exact
-for rep in range(2):
+for rep in range(int(os.environ.get("REPS", "2"))):
     rr.initWorkspaceGraph()
     t0 = time.time()
     ts, tc = rr.sampleConfigurationSpace(pdef["Nq"], order_independent=True)
