@@ -340,7 +340,7 @@ def sub_records(args, grr, torch, _cabi, name, jf, over, pdef, res, rr, local, p
                            "pairs_per_s": s2["pairs"] / max(ts + tc, 1e-12), "ik_configs_per_s": s2["attempts"] / max(ts, 1e-12)}
     # -- BASELINE config 3
     pj, resj, rrj = grr.make_program("jaco", "baseline_cfg3.json", device=local, seed=0)
-    for _ in range(2):
+    for _ in range(4):                                    # the last of four builds (buffers allocated, kernels warm)
         rrj.initWorkspaceGraph()
         tsj, tcj = rrj.sampleConfigurationSpace(pj["Nq"], order_independent=True)
     sj = rrj.stats
