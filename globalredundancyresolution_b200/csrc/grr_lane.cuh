@@ -559,6 +559,13 @@ GRR_DEV void lane_backtrack(LaneIK<Real, M> &L, Real f, Real fl_rel, Real fl_f0 
 //     double-precision search can try after its last clear rejection.
 // Anything else flags the pair.
 enum : int { TIE_FLAG = 0, TIE_STALL = 1, TIE_ACCEPT = 2, TIE_PENDING = 3 };
+// host study only (tools/lane_host.cu defines GRR_TIE_STATS): which branch of the tie logic decided, how often
+#if defined(GRR_TIE_STATS) && !defined(__CUDA_ARCH__)
+extern long long g_tie_hist[16];
+#define GRR_TIE_STAT(i) do { _Pragma("omp atomic") g_tie_hist[i]++; } while (0)
+#else
+#define GRR_TIE_STAT(i) do { } while (0)
+#endif
 
 // z with g_j = col_j . z: the residual in the goal-link frame, rotation rows multiplied by Jl^-T (the Jacobian of the
 // log-map residual is Jl^-1 times the stored angular columns, see lane_step)
@@ -597,7 +604,7 @@ template <typename Real, int M, bool PL, typename ChainT>
 GRR_DEV int lane_tie_decide(const ChainT &c, LaneIK<Real, M> &L, const PassOut<Real, M> &o, Real Dc, bool same, bool final_sample) {
   const bool pending = (L.phase & PH_PEND) != 0;
   L.phase &= ~PH_PEND;
-  if (!same) return TIE_FLAG;
+  if (!same) { GRR_TIE_STAT(0); return TIE_FLAG; }
   Real trS = 0;
   if constexpr (PL) trS = o.S[0] + o.S[2];
   else {
@@ -609,13 +616,15 @@ GRR_DEV int lane_tie_decide(const ChainT &c, LaneIK<Real, M> &L, const PassOut<R
   if (!pending) {
     const Real curv = L.alam * o.pn2 * (trS + F0 * c.fl_curv);
     const Real slack = c.fl_dd * (abs_(Dc) + abs_(L.slope));
-    if (Dc - curv - tgt > slack) return TIE_STALL;
-    if (Dc + curv - tgt < -slack) return TIE_ACCEPT;
+    if (Dc - curv - tgt > slack) { GRR_TIE_STAT(6); return TIE_STALL; }
+    if (Dc + curv - tgt < -slack) { GRR_TIE_STAT(7); return TIE_ACCEPT; }
     if (!final_sample && Dc - tgt > slack) {               // (D <= tgt: a shorter step cannot be certified as rejected either)
       L.phase |= PH_PEND;
       L.t_a = L.alam; L.t_D = Dc; L.t_ar = (L.alam2 > Real(0)) ? L.alam2 : L.alam;
+      GRR_TIE_STAT(8);
       return TIE_PENDING;
     }
+    GRR_TIE_STAT(final_sample ? 1 : 2);
     return TIE_FLAG;
   }
   const Real kappa = (L.t_D - Dc) / (L.t_a - L.alam), D0 = Dc - L.alam * kappa;
@@ -624,7 +633,9 @@ GRR_DEV int lane_tie_decide(const ChainT &c, LaneIK<Real, M> &L, const PassOut<R
   const Real tau = c.fl_curv * o.pn2 * pn * (Real(3) * sqrt_(trS) + F0 * sqrt_(Real(c.n)) * pn);
   const Real s3 = c.fl_dd * (abs_(Dc) + abs_(L.t_D) + abs_(L.slope) + abs_(kappa) * amax) + amax * amax * tau;
   const Real b0 = D0 - tgt, bm = D0 - tgt + Real(0.5) * amax * kappa;
-  return (amax * pn < Real(0.05) && b0 > s3 && bm > s3) ? TIE_STALL : TIE_FLAG;
+  if (amax * pn < Real(0.05) && b0 > s3 && bm > s3) { GRR_TIE_STAT(9); return TIE_STALL; }
+  GRR_TIE_STAT(!(amax * pn < Real(0.05)) ? 3 : (!(b0 > s3) ? 4 : 5));
+  return TIE_FLAG;
 }
 
 // Near-tie met in lane_step.  Device: the directional derivative is a loop over the joints that would run with one
@@ -781,7 +792,7 @@ GRR_DEV int lane_step(const ChainT &c, LaneIK<Real, M> &L, LaneMem<Real, col_row
           L.it++;
           if (FLAG) {
             // accepted clear of the margin while an earlier near-tie of this search is still open: that tie stays undecided
-            if (L.phase & PH_PEND) { L.phase &= ~PH_PEND; L.phase |= PH_HARD | PH_R_ARMIJO; }
+            if (L.phase & PH_PEND) { L.phase &= ~PH_PEND; L.phase |= PH_HARD | PH_R_ARMIJO; GRR_TIE_STAT(10); }
             // Drift r of the single-precision iterate from the double-precision one over one accepted step (estimate).
             // A step of amplification A = |step| / |F| (>> 1 near a singular configuration, up to 1 / (2 lambda)) turns
             // the residual round-off fl_f into A fl_f of joint error, carries an existing difference on with the factor

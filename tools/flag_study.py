@@ -118,10 +118,17 @@ def main():
     P = qa.shape[0]
     v64, i64 = run_pairs(L, desc, qa, qb, wa, wb, 1)
     t2 = time.time()
+    hist = (C.c_longlong * 16)()
+    L.lane_host_tie_hist(hist, 1)
     v32, i32 = run_pairs(L, desc, qa, qb, wa, wb, 0, scale=scale)
     t3 = time.time()
+    L.lane_host_tie_hist(hist, 1)
+    tie_names = ["flag:limit status changed", "flag:1 sample, final", "flag:1 sample, D<=tgt", "flag:2 samples, step too long",
+                 "flag:2 samples, b0", "flag:2 samples, bm", "stall:1 sample", "accept:1 sample", "pending", "stall:2 samples",
+                 "flag:accepted while pending"]
     out = {"problem": name + "/" + jf, "pairs": int(P), "scale": scale, "valid64": int(v64.sum()), "valid32": int(v32.sum()),
            "t_sample": round(t1 - t0, 1), "t64": round(t2 - t1, 1), "t32": round(t3 - t2, 1)}
+    out["tie_decisions"] = {nm: int(hist[k]) for k, nm in enumerate(tie_names)}
     if int(kv.get("check_oracle", 0)):
         k = min(P, int(kv["check_oracle"]))
         vo, _ = o.valid_edge_batch(qa[:k], qb[:k], wa[:k], wb[:k])
@@ -140,7 +147,7 @@ def main():
     out["flagged_valid32"] = {r: int((((i32[:, 0] >> (4 + k)) & 1).astype(bool) & v32).sum()) for k, r in enumerate(REASONS)}
     out["flagged_pairs_valid32"] = int((flagged & v32).sum()); out["flagged_pairs_invalid32"] = int((flagged & ~v32).sum())
     out["invalid32"] = int((~v32).sum())
-    out["mismatch_examples"] = [{"v32": bool(v32[t]), "info32": i32[t].tolist(), "info64": i64[t].tolist()} for t in np.nonzero(mism)[0][:40]]
+    out["mismatch_examples"] = [{"v32": bool(v32[t]), "info32": i32[t].tolist(), "info64": i64[t].tolist()} for t in np.nonzero(mism)[0][:4]]
     bad = np.nonzero(mism & ~flagged)[0][:10]
     out["unflagged_examples"] = [{"i": int(t), "v32": bool(v32[t]), "info32": i32[t].tolist(), "info64": i64[t].tolist()} for t in bad]
     if "dump" in kv:

@@ -7,10 +7,12 @@
 // the flag rates measured here are estimates of the device's, confirmed on the GPU by tests/test_gpu_exact.py.
 //
 // build: nvcc -O2 -std=c++17 --expt-relaxed-constexpr -Xcompiler -fPIC,-fopenmp -shared -o tools/_build/liblane_host.so tools/lane_host.cu
+#define GRR_TIE_STATS
 #include "../globalredundancyresolution_b200/csrc/grr_kernels.cuh"
 #include <omp.h>
 
 namespace grr {
+long long g_tie_hist[16] = {0};
 void set_error(const char *, ...) {}
 template <typename Real, int M, bool PL, bool FLAG>
 static void run_pair(const ChainDev<Real, kMaxJ> &c, const Real *qa, const Real *qb, const Real *wa, const Real *wb,
@@ -159,4 +161,8 @@ extern "C" void lane_host_margins(const grr_chain_desc *d, double scale, double 
   memcpy(h.ee_local, d->ee_local, sizeof h.ee_local);
   flag_margins(h, scale);
   memcpy(fl_out, h.fl, sizeof h.fl);
+}
+
+extern "C" void lane_host_tie_hist(long long *out, int reset) {
+  for (int k = 0; k < 16; k++) { out[k] = grr::g_tie_hist[k]; if (reset) grr::g_tie_hist[k] = 0; }
 }
