@@ -8,6 +8,7 @@ from .robot import RobotChain, planar_robot, synthetic_arm, synthetic_arm_links 
 from .solver import RedundancyResolver                               # noqa: F401
 from .problems import load_problem, make_program                     # noqa: F401
 from .worker import Worker, worker                                   # noqa: F401
+from .resolvers import StatCollector, SequentialResolver, ParallelResolver            # noqa: F401
 from .csp import RoadmapCSP, greedy_colouring, adjacency_csr          # noqa: F401
 
 __version__ = "0.1.0"

@@ -709,6 +709,57 @@ class RedundancyResolver(VisibilityMixin):
             return True
         return False
 
+    def testAndAddEdge(self, iw, iq, jw, q):
+        """solver.py:503-515: connect the existing config (iw, iq) to a new config q of node jw; if the edge is feasible the
+        config is added and connected, and its index returned, else None.  (The reference reads qlist[iw] where it means
+        qlist[iq], :509 -- the intended index is used here.)"""
+        cnt = self.counts()
+        assert 0 <= iq < cnt[iw]
+        assert jw < self.Nw
+        a = self._node_qlist(iw)[iq]
+        res = self.resolution
+        if res.validEdge(a, q, res.Gw.node[iw]["params"], res.Gw.node[jw]["params"]):
+            jq = self.addNode(jw, q)
+            self.addEdge(iw, iq, jw, jq)
+            return jq
+        return None
+
+    def edgeInResolution(self, iw, jw):
+        """solver.py:370-373."""
+        if iw > jw:
+            return self.edgeInResolution(jw, iw)
+        return iw in self.Qsubgraph and jw in self.Qsubgraph and self.hasEdge(iw, self.Qsubgraph[iw], jw, self.Qsubgraph[jw])
+
+    def printStats(self):
+        """solver.py:375-420, from the device counters (returns the numbers it prints)."""
+        res = self.resolution
+        cnt = self.counts()
+        e = res.ws_edges
+        both = (cnt[e[:, 0]] > 0) & (cnt[e[:, 1]] > 0)
+        per_edge = self._bits_per_edge().cpu().numpy() if (self._dev is not None and self.Nq > 0) else np.zeros(self.E, dtype=np.int64)
+        resolved = [(i, j) for (i, j) in self._edges_host if cnt[i] > 0 and cnt[j] > 0 and res.isResolvedEdge(i, j)]
+        sumd = sum(float(np.linalg.norm(np.asarray(res.Gw.node[i]["config"]) - np.asarray(res.Gw.node[j]["config"]))) for i, j in resolved)
+        sumw = sum(res.workspaceDistance(res.Gw.node[i]["params"], res.Gw.node[j]["params"]) for i, j in resolved)
+        out = {"workspace_nodes": self.Nw, "workspace_edges": self.E, "configs": int(cnt.sum()), "cspace_edges": int(per_edge.sum()),
+               "nodes_with_configs": int((cnt > 0).sum()), "potential_edges": int(both.sum()),
+               "edges_with_configs": int(((per_edge > 0) & both).sum()), "edges_in_resolution": len(resolved),
+               "avg_cspace_distance": (sumd / len(resolved)) if resolved else None,
+               "avg_cspace_over_workspace_distance": (sumd / sumw) if resolved and sumw > 0 else None}
+        print("**** REDUNDANCY RESOLUTION STATS *****")
+        print("Roadmap has", out["workspace_nodes"], "workspace nodes and", out["workspace_edges"], "edges")
+        print("  and", out["configs"], "configuration space nodes and", out["cspace_edges"], "edges")
+        print("  of %d nodes, %d have no configuration, and %d / %d are not in redundancy resolution"
+              % (self.Nw, self.Nw - out["nodes_with_configs"], out["nodes_with_configs"] - res.resolvedCount, out["nodes_with_configs"]))
+        print("  of %d edges, %d  are missing a configuration space edge, and %d / %d are not in redundancy resolution"
+              % (out["potential_edges"], out["potential_edges"] - out["edges_with_configs"],
+                 out["potential_edges"] - out["edges_in_resolution"], out["potential_edges"]))
+        if not res.hasResolution():
+            print("  Resolution is empty.")
+        elif resolved:
+            print("  Average configuration space distance:", out["avg_cspace_distance"])
+            print("  Average configuration space distance / workspace distance:", out["avg_cspace_over_workspace_distance"])
+        return out
+
     def testAndConnectAll(self, iw, jw):
         return self.connectConfigurationSpaceOnEdge(iw, jw) > 0
 

@@ -178,9 +178,26 @@ class VisibilityMixin:
         self._last_qcc = {"cand": cand, "tested_mask": vmask}                       # kept for inspection (tests, tools)
         return cc_off, conn[:total], nconn, ntests
 
-    def _connect_visibility(self, edge_ids=None, max_tests=10, swap=0):
-        """testAndConnectQccs on every workspace edge (or the listed ones); sets the bits of the connecting pairs in the
-        roadmap's edge masks.  Returns nconn (device int32 per edge)."""
+    def connectParallel(self, maxTestsPerCC=20):
+        """The edge phase of the reference's ParallelResolver (superviseEdgeTests, solver.py:2298-2337): parallelEdgeConnection
+        on every workspace edge, whose result REPLACES the edge's qlist.  Returns the number of non-degenerate edges."""
+        torch = self.resolution._torch()
+        self._dev["mask"].zero_()
+        self._dev["counters_e"].zero_()
+        nconn = self._connect_visibility(None, maxTestsPerCC, swap=0, mode=1)
+        torch.cuda.synchronize(self.resolution.torch_device)
+        self._visibility_stats()
+        return int((nconn > 0).sum().item())
+
+    def numNondegenerateEdges(self):
+        """Workspace edges with at least one C-space edge."""
+        if self._dev is None or self.Nq == 0:
+            return 0
+        return int(self._dev["mask"].view(self.E, -1).ne(0).any(dim=1).sum().item())
+
+    def _connect_visibility(self, edge_ids=None, max_tests=10, swap=0, mode=0):
+        """testAndConnectQccs (mode 0) / parallelEdgeConnection (mode 1) on every workspace edge (or the listed ones); sets
+        the bits of the connecting pairs in the roadmap's edge masks.  Returns nconn (device int32 per edge)."""
         torch = self.resolution._torch()
         d = self._dev
         v = self._vis_state()
@@ -191,7 +208,7 @@ class VisibilityMixin:
             eid = torch.as_tensor(np.asarray(edge_ids, dtype=np.int64), device=self.resolution.torch_device)
             wedges, mask = d["wedges"][eid].contiguous(), d["mask"][eid].contiguous()
         cc_off, conn, nconn, ntests = self._qcc_connect(wedges, p, Q, d["uid"], v["ncc"], v["members"], v["cc_start"], self.Nq, mask,
-                                                        max_tests, 0, swap, d["counters_e"])
+                                                        max_tests, mode, swap, d["counters_e"])
         if edge_ids is not None:
             d["mask"][eid] = mask
         v["last_connect"] = {"cc_off": cc_off, "conn": conn, "nconn": nconn, "ntests": ntests, "swap": swap}

@@ -193,3 +193,54 @@ def test_worker_tasks_build_manifolds(built):
     qlist, iw, jw = w.handle(("connect", 3, ci, qi, pi, 9, cj, qj, pj))
     assert (iw, jw) == (3, 9) and qlist == rr.parallelEdgeConnection(ci, qi, pi, cj, qj, pj)
     assert 0 < len(qlist) <= len(qi) * len(qj)
+
+
+def test_resolver_drivers(built, tmp_path):
+    """SequentialResolver / ParallelResolver (solver.py:2186-2365), the callers redundancy.py builds: the parallel driver's
+    edge phase is parallelEdgeConnection on every workspace edge (qlists replaced), its statistics come from the manifolds;
+    the sequential driver is sampleConfigurationSpace + solveCSP + the CSV report."""
+    prob = PROBLEMS[0]
+    name, jf, over, Nq, seed = prob
+    pdef, res, rr = grr.make_program(name, jf, overrides=over, seed=seed)
+    pr = grr.ParallelResolver(rr, makeParams={"problem": "planar_3R", "Nw": pdef["Nw"], "workspace_graph": pdef["workspace_graph"]}, threads=8)
+    pr.stats.folder = str(tmp_path)
+    pr.spawnWorkers()
+    pr.superviseQSampling(Nq, None)
+    pr.superviseEdgeTests()
+    o = oracle_for(res)
+    ref = _oracle_edges(o, res, rr, 0, 20, parallel=True)
+    got = unpack_mask(rr._dev["mask"].cpu().numpy(), rr.Nq)
+    for e in range(rr.E):
+        a, b = np.nonzero(got[e])
+        assert sorted(zip(a.tolist(), b.tolist())) == sorted(set(ref[e])), "workspace edge %d" % e
+    rep = pr.getStats().getReport()
+    st = rr.getSelfMotionCcsStats()
+    assert rep["configuredW"] == st["configuredW"] and rep["avgNumQccs"] == pytest.approx(st["avgNumQccs"])
+    assert rep["nondegenerate_workspace_edges"] == sum(1 for e in ref if ref[e]) == rr.numNondegenerateEdges()
+    assert rep["threads"] == 8 and rep["sampling_time"] > 0 and rep["edge_time"] > 0
+    out = pr.writeReport()
+    assert open(out).read().count("\n") == 1
+    with pytest.raises(NotImplementedError):
+        pr.solveCSP()
+    # sequential driver, basic solver
+    pdef, res2, rr2 = grr.make_program(name, jf, overrides=over, seed=seed)
+    sr = grr.SequentialResolver("planar_3R", rr2, pdef["Nw"], pdef["workspace_graph"], False)
+    sr.stats.folder = str(tmp_path)
+    out2 = sr.run(8, None, str(tmp_path / "run"), solveCSP=True)
+    rep2 = sr.stats.getReport()
+    assert out2 == out and open(out).read().count("\n") == 2
+    assert rep2["min_conflicts"] >= 0 and rep2["csp_method"] in ("heuristic max", "random") and rep2["edge_time"] > 0
+    assert rep2["nondegenerate_workspace_edges"] == rr2.numNondegenerateEdges() > 0
+    stats = rr2.printStats()
+    assert stats["configs"] == rr2.numConfigurations() and stats["cspace_edges"] == rr2.numCSpaceEdges()
+    assert stats["edges_in_resolution"] == sum(1 for i, j in res2.Gw.edges_iter() if res2.isResolvedEdge(i, j)) > 0
+    i, j = next((i, j) for i, j in res2.Gw.edges_iter() if res2.isResolvedEdge(i, j))
+    assert rr2.edgeInResolution(i, j) and rr2.edgeInResolution(j, i)
+    # testAndAddEdge (solver.py:503-515): a valid new config is added and connected, an invalid one is not
+    cnt = rr2.counts()
+    iq = rr2.Qsubgraph[i]
+    qnew = res2.Gw.node[j]["config"]
+    jq = rr2.testAndAddEdge(i, iq, j, qnew)
+    assert jq == cnt[j] and rr2.hasEdge(i, iq, j, jq) and rr2.counts()[j] == cnt[j] + 1
+    far = [v + 2.5 for v in qnew]
+    assert rr2.testAndAddEdge(i, iq, j, far) is None and rr2.counts()[j] == cnt[j] + 1

@@ -216,3 +216,26 @@ def test_heuristic_max_assignment_equals_literal_restatement():
         assert (got[count == 0] == -1).all()
         failures_seen += len(fails)
     assert failures_seen > 50            # the empty-domain branch (csp.py:838-858) is exercised
+
+
+def test_stat_collector_report_matches_reference_columns(tmp_path):
+    """StatCollector (solver.py:67-207): component statistics and the CSV row of experiments/<problem>_k_experiments.csv."""
+    st = grr.StatCollector(problem="planar_3R", folder=str(tmp_path))
+    st.setNw(1000); st.setNq(10); st.setMethod("grid"); st.setThreads(4); st.setVisK(None)
+    for qccs in ([[0, 1, 2], [3]], [[0]], []):
+        st.add(qccs)
+    st.inc(); st.inc(2)
+    st.setTotalWorkspaceEdges(7); st.setSamplingTime(0.5); st.setEdgeTime(1.5)
+    r = st.getReport()
+    assert (r["configuredW"], r["avgNumConfigs"], r["avgNumQccs"], r["avgMaxSize"], r["avgAvgSize"], r["avgMinSize"]) == (2, 2.5, 1.5, 2.0, 1.5, 1.0)
+    assert r["nondegenerate_workspace_edges"] == 3
+    out = st.writeReport()
+    st.writeReport()
+    lines = open(out).read().split("\n")
+    assert out.endswith("planar_3R_k_experiments.csv") and len(lines) == 3
+    assert lines[0].startswith("num_w,num_q_per_w,threads,cache_size,k,workspace_sampling_method") and lines[0].count(",") == 20
+    assert lines[1] == "1000,10,4,0,None,grid,2,3,7,2.5,1.5,2.0,1.5,1.0,0.5,1.5,-1,None,-1,-1"
+    empty = grr.StatCollector()
+    assert empty.getReport()["avgNumQccs"] == float("inf")
+    with pytest.raises(AssertionError):
+        empty.writeReport()
