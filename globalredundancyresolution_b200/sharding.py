@@ -227,13 +227,18 @@ class ShardedResolver(RedundancyResolver):
     def sampleConfigurationSpace(self, NConfigsPerPoint=100, connect=True, biased=False, seedFromAdjacent=False,
                                  visibility=False, k=None, order_independent=True):
         """Sharded build: order-independent sampling only (parallelQSamplingAtP semantics, solver.py:875-897);
-        the seeded Gauss-Seidel sweep does not shard.  A second call grows the roadmap incrementally
+        with order_independent=False every rank runs the reference's seeded sweep in full and only the edge phase is
+        sharded.  A second call grows the roadmap incrementally
         (solver.py:759,850: only pairs with a new endpoint are tested) in all-gather mode with round-robin edges, where
         a rank's workspace edges -- and so its mask rows -- are the same in every call."""
         if visibility:
             raise NotImplementedError("visibility-graph solver is out of scope of the B200 roadmap path")
-        if not order_independent:
-            raise NotImplementedError("the seeded sweep is single-GPU; shard with order_independent=True")
+        # The reference's default (seeded) sweep is a chain over the whole grid and only a few per cent of the work: every
+        # rank runs it in full (same Philox streams, same result on every rank, no exchange at all) and the edge phase is
+        # sharded -- workspace edge e on rank e % world.
+        replicated = not order_independent
+        if replicated and self.edge_chunks_per_rank != 0:
+            raise NotImplementedError("the seeded sweep on several GPUs uses round-robin edges (edge_chunks_per_rank=0)")
         if biased:
             raise NotImplementedError("biased re-sampling is defined by the sequential sweep (single-GPU)")
         import torch.distributed as dist
@@ -242,13 +247,14 @@ class ShardedResolver(RedundancyResolver):
         N = int(NConfigsPerPoint)
         incremental = self.Nq > 0
         old_counts = None
-        if incremental:
+        if incremental and not replicated:
             mode0 = self.exchange
             if mode0 == "auto":
                 mode0 = "allgather" if self._dev["Qs"].numel() * self._dev["Qs"].element_size() <= 4 * 2 ** 30 else "halo"
             if mode0 != "allgather" or self.edge_chunks_per_rank != 0:
                 raise NotImplementedError("sharded incremental growth needs exchange='allgather' with round-robin edges "
                                           "(edge_chunks_per_rank=0): the halo plan re-cuts the edge list per call")
+        if incremental:
             old_counts = self._dev["count"].clone()
         d = self._ensure_device(self.Nq + N)
         if incremental:
@@ -265,22 +271,29 @@ class ShardedResolver(RedundancyResolver):
                 torch.cuda.synchronize(res.torch_device)
                 marks.append((name, time.perf_counter()))
         self._mark = mark if prof else None
+        if replicated:
+            self._sweep_levels()
         mark("start")
         ev[0].record()
-        if incremental:
+        if replicated:
+            self._sample_phase_seeded(d, N, bool(seedFromAdjacent))
+        elif incremental:
             own0 = torch.zeros(self.Nw, dtype=torch.bool, device=res.torch_device)
             for (lo, hi) in mine_nodes:
                 own0[lo:hi] = True
             d["count"].mul_(own0.to(d["count"].dtype))     # other ranks' counts come back with the all-reduce
         else:
             d["count"].zero_()
-        if len(mine_nodes) == 1:
+        if replicated:
+            pass
+        elif len(mine_nodes) == 1:
             self._sample_phase(d, N, mine_nodes[0][0], mine_nodes[0][1])
         else:
             nodes = torch.cat([torch.arange(lo, hi, dtype=torch.int32, device=res.torch_device) for (lo, hi) in mine_nodes])
             self._sample_phase_nodes(d, N, nodes)
         mark("sample_kernels")
-        dist.all_reduce(d["count"])                       # every rank learns every node's count
+        if not replicated:
+            dist.all_reduce(d["count"])                   # every rank learns every node's count
         mark("allreduce_count")
         ev[1].record()
         self.attempts += N
@@ -289,12 +302,14 @@ class ShardedResolver(RedundancyResolver):
             mode = self.exchange
             if mode == "auto":
                 mode = "allgather" if d["Qs"].numel() * d["Qs"].element_size() <= 4 * 2 ** 30 else "halo"
+            if replicated:
+                mode = "allgather"                        # (nothing to gather: every rank holds every node's configs)
             if mode == "allgather":
                 K = self.edge_chunks_per_rank
                 cnt_dev = d["count"]
                 cmax = int(cnt_dev.max().item()) if self.Nw else 0          # (sync: the plan below needs the counts anyway)
                 cnt = cnt_dev.cpu().numpy()
-                if cmax > 0 and self.world > 1:
+                if cmax > 0 and self.world > 1 and not replicated:
                     # kept configs of every node to every rank: blocks of nodes this rank did not sample are zero
                     own = torch.zeros(self.Nw, dtype=torch.bool, device=res.torch_device)
                     for (lo, hi) in mine_nodes:

@@ -27,6 +27,7 @@ def test_sharded_roadmap_equals_single_gpu(built):
     assert out.returncode == 0, out.stderr[-3000:]
     assert out.stdout.count("sharded == single GPU") == 8
     assert out.stdout.count("sharded incremental == single GPU incremental") == 2
+    assert out.stdout.count("sharded seeded == single GPU seeded") == 2
 
 
 def test_halo_exchange_c_abi(built):

@@ -56,4 +56,19 @@ for (name, jf, Nw, Nq) in cases:
         assert int(tot[0].item()) == ref2[3], (tot.tolist(), ref2[3])
         print("sharded incremental == single GPU incremental: %s world=%d pairs of the second call=%d" % (name, world, ref2[3]), flush=True)
     dist.barrier()
+    # the reference's default (seeded) sweep: replicated on every rank, edge phase sharded
+    if rank == 0:
+        rr = grr.RedundancyResolver(res, seed=3)
+        rr.sampleConfigurationSpace(Nq)
+        ref3 = (rr._dev["count"].clone(), rr._dev["mask"].clone(), rr._dev["Qs"].clone(), rr.stats["pairs"])
+    sr = sharding.ShardedResolver(res, rank, world, seed=3)
+    sr.sampleConfigurationSpace(Nq, order_independent=False, seedFromAdjacent=True)
+    full = sr.gather_masks()
+    tot = torch.tensor([float(sr.stats["pairs"])], device="cuda"); dist.all_reduce(tot)
+    if rank == 0:
+        assert torch.equal(sr._dev["count"], ref3[0]) and torch.equal(sr._dev["Qs"], ref3[2]), "seeded sweep differs"
+        assert torch.equal(full, ref3[1]), "edge masks differ after the seeded sweep (%s)" % name
+        assert int(tot[0].item()) == ref3[3]
+        print("sharded seeded == single GPU seeded: %s world=%d pairs=%d" % (name, world, ref3[3]), flush=True)
+    dist.barrier()
 dist.destroy_process_group()
