@@ -580,7 +580,22 @@ GRR_DEV void pair_note_solve(PairLane<Real> &P, const LaneIK<Real, M> &L, int st
 
 // skip_first_leaf: the recheck kernel restarts a pair at solve kstart > 1, whose predecessor has not been computed:
 // the leaf (kstart - 1, kstart) was settled by the single-precision pass.
-template <bool FLAG = false, typename Real, int M, int MC, typename ChainT>
+// Closing leaf (q_Ndivs, qb) of a pair once its squared length e2 is known.
+template <bool FLAG, typename Real, int M, typename ChainT>
+GRR_DEV int pair_close(const ChainT &c, Real e2, Real thr2, PairLane<Real> &P, const LaneIK<Real, M> &L) {
+  if (FLAG) {
+    const Real thr = thr2 * rsqrt_est_(thr2);
+    const Real amb = min_(L.amb, Real(0.5) * thr);
+    if (abs_(e2 - thr2) < thr2 * (Real(2) * c.fl_leaf) + amb * (Real(2) * thr + amb)) { if (!P.flag) P.k0 = P.k; P.flag |= PH_R_LEAF; }
+  }
+  return (e2 > thr2) ? 0 : 1;
+}
+constexpr int kNeedClose = -2;     // pair_advance<.., COOP>: the closing leaf is left to the warp (warp_close_service)
+
+// COOP: instead of summing the closing leaf's squared length joint by joint on this lane alone (a loop that ran with
+// 1.5 of 32 lanes active: 2.6 % of the dense kernel's issue slots), return kNeedClose; the kernel lets the whole warp
+// compute it, one joint per lane.
+template <bool FLAG = false, bool COOP = false, typename Real, int M, int MC, typename ChainT>
 GRR_DEV int pair_advance(const ChainT &c, LaneMem<Real, MC> &mem, Real s2, Real thr2, PairLane<Real> &P,
                          LaneIK<Real, M> &L, bool skip_first_leaf = false) {
   Real thr = 0;
@@ -595,14 +610,11 @@ GRR_DEV int pair_advance(const ChainT &c, LaneMem<Real, MC> &mem, Real s2, Real 
   }
   if (!skip_first_leaf && s2 > thr2) return 0;                   // graph.py:954-959 (leaf)
   if (P.k == P.ndivs) {
+    if (COOP) return kNeedClose;
     const int n = c.n, T = mem.T;
     Real e2 = 0;
     for (int j = 0; j < n; j++) { const Real e = P.qb[j * P.sb] - L.res[j * T]; e2 += e * e; }
-    if (FLAG) {
-      const Real amb = min_(L.amb, Real(0.5) * thr);
-      if (abs_(e2 - thr2) < thr2 * (Real(2) * c.fl_leaf) + amb * (Real(2) * thr + amb)) { if (!P.flag) P.k0 = P.k; P.flag |= PH_R_LEAF; }
-    }
-    return (e2 > thr2) ? 0 : 1;
+    return pair_close<FLAG>(c, e2, thr2, P, L);
   }
   { const int t = mem.o_prev; mem.o_prev = mem.o_xcur; mem.o_xcur = t; }   // IK_OK leaves the solution in xcur
   P.k++;
@@ -641,6 +653,31 @@ __device__ __forceinline__ void warp_tie_service(const ChainT &c, LaneIK<Real, M
     }
   }
 #endif
+}
+
+// Serves the closing-leaf requests of a warp's lanes (pair_advance<.., COOP>): for each requesting lane the whole warp sums
+// |qb - q_Ndivs|^2, one joint per lane (n <= 32), reading the requester's staged endpoint config and its solution in
+// shared memory.  Returns this lane's e2 (meaningful on requesting lanes).  All 32 lanes must call.
+template <typename Real, int M>
+__device__ __forceinline__ Real warp_close_service(int n, int T, const PairLane<Real> &P, const LaneIK<Real, M> &L, bool request) {
+  Real mine = 0;
+#ifdef __CUDA_ARCH__
+  unsigned rq = __ballot_sync(0xffffffffu, request);
+  const int lane = threadIdx.x & 31;
+  while (rq) {
+    const int src = __ffs(rq) - 1;
+    rq &= rq - 1;
+    const Real *qb = reinterpret_cast<const Real *>(__shfl_sync(0xffffffffu, (unsigned long long)P.qb, src));
+    const Real *rs = reinterpret_cast<const Real *>(__shfl_sync(0xffffffffu, (unsigned long long)L.res, src));
+    const int sb = __shfl_sync(0xffffffffu, P.sb, src);
+    Real e = 0;
+    if (lane < n) { e = qb[lane * sb] - rs[lane * T]; e *= e; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) e += __shfl_xor_sync(0xffffffffu, e, o);
+    if (lane == src) mine = e;
+  }
+#endif
+  return mine;
 }
 
 // Near-tie list of the exact edge build: word 0 = entries appended (may exceed the capacity: the excess is dropped and
@@ -868,14 +905,19 @@ k_edges_build(const __grid_constant__ ChainDev<Real, kMaxJ> c, const int32_t *__
         else lane_pass<Real, M, true>(c, tg, L, mem, first ? P.qa : mem.prev(), first ? P.sa : mem.T, o);
         const int st = lane_step<Real, M, PL, FLAG>(c, L, mem, o, running);
         if constexpr (FLAG) warp_tie_service<Real, M, PL>(c, L, mem, running);
+        constexpr bool COOP = sizeof(Real) == 4;                // (double precision keeps the sequential sum of the oracle)
         if (running && st != IK_RUNNING) {
           cnt.solves++; cnt.iters += L.it; cnt.evals += L.evals; cnt.ok += (st == IK_OK);
           if (FLAG) pair_note_solve(P, L, st);
           if (st != IK_OK) verdict = 0;                         // graph.py:964-966
           else {
-            verdict = pair_advance<FLAG>(c, mem, o.s2, thr2, P, L);
-            if (verdict < 0) winterp_at<Real, M>(W, P.u_at(P.k), tg);
+            verdict = pair_advance<FLAG, COOP>(c, mem, o.s2, thr2, P, L);
+            if (verdict == -1) winterp_at<Real, M>(W, P.u_at(P.k), tg);
           }
+        }
+        if constexpr (COOP) {
+          const Real e2 = warp_close_service<Real, M>(n, mem.T, P, L, running && verdict == kNeedClose);
+          if (running && verdict == kNeedClose) verdict = pair_close<FLAG>(c, e2, thr2, P, L);
         }
       }
       if (a >= 0 && verdict >= 0) {
