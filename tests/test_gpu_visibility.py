@@ -244,3 +244,31 @@ def test_resolver_drivers(built, tmp_path):
     assert jq == cnt[j] and rr2.hasEdge(i, iq, j, jq) and rr2.counts()[j] == cnt[j] + 1
     far = [v + 2.5 for v in qnew]
     assert rr2.testAndAddEdge(i, iq, j, far) is None and rr2.counts()[j] == cnt[j] + 1
+
+
+@pytest.mark.parametrize("Nq", [1, 2, 33])
+@pytest.mark.parametrize("k", [None, 3, 64])
+def test_visibility_edge_cases(built, Nq, k):
+    """Empty and single-config nodes, a node count around the 32-bit mask word, k larger than any node's config count:
+    manifolds and the visibility roadmap still equal the restatement."""
+    res = grr.RedundancyResolutionGraph(grr.planar_robot(3))
+    res.readJsonSetup({"orientation": "free", "domain": [[-3, 0, -3], [3.5, 0, 3.5]], "eelocal": [1, 0, 0], "useCollision": False})
+    params = np.array([[1.5, 0, 0.5], [1.7, 0, 0.5], [1.5, 0, 0.7], [2.95, 0, 0.0], [9, 0, 0], [1.6, 0, 0.6]])
+    edges = np.array([[0, 1], [0, 2], [0, 5], [1, 2], [1, 3], [1, 5], [2, 5], [3, 4]])
+    res.setWorkspaceGraph(params, edges)
+    rr = grr.RedundancyResolver(res, seed=4)
+    rr.sampleConfigurationSpace(Nq, order_independent=True, visibility=True, k=k)
+    o = oracle_for(res)
+    cnt = rr.counts()
+    assert cnt[4] == 0 and rr.Gw.node[4]["qccs"] == [] and rr.Gw.node[4]["qcc_parents"] == []
+    ref = _oracle_manifolds(o, res, rr, k)
+    for i in range(rr.Nw):
+        assert rr.Gw.node[i]["qccs"] == ref[i][0] and rr.Gw.node[i]["qcc_parents"] == ref[i][1], "node %d" % i
+    want = _oracle_edges(o, res, rr, 1, 10)
+    got = unpack_mask(rr._dev["mask"].cpu().numpy(), rr.Nq)
+    for e in range(rr.E):
+        a, b = np.nonzero(got[e])
+        assert sorted(zip(a.tolist(), b.tolist())) == want[e], "workspace edge %d" % e
+    assert rr.Gw.edge[3][4]["qlist"] == set()
+    st = rr.getSelfMotionCcsStats()
+    assert st["configuredW"] == int((cnt > 0).sum()) and st["sumConfigs"] == int(cnt.sum())
