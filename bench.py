@@ -280,6 +280,7 @@ def sub_records(args, grr, torch, _cabi, name, jf, over, pdef, res, rr, local, p
                   same kernels over the WHOLE roadmap, and against the CPU oracle on a random sample of workspace edges
     seeded_sweep  the reference's default sampleConfigurationSpace call (seedFromAdjacent=True, sequential sweep as
                   wavefronts) on the same workload
+    visibility    the visibility-graph variant (self-motion manifolds + CC-pair connection) on the same workload
     jaco          BASELINE config 3 (Jaco-like 6R, free orientation, Nw=20000, Nq=50): IK configs/s, edges tested/s, roofline
     roofline_ik   the sampling kernel (k_ik_instances) of the headline workload"""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -338,6 +339,16 @@ def sub_records(args, grr, torch, _cabi, name, jf, over, pdef, res, rr, local, p
     out["seeded_sweep"] = {"call": "sampleConfigurationSpace(Nq) with the reference's defaults (seedFromAdjacent=True)",
                            "t_sample_s": ts, "t_connect_s": tc, "pairs": s2["pairs"], "configs": s2["sampled"], "ik_attempts": s2["attempts"],
                            "pairs_per_s": s2["pairs"] / max(ts + tc, 1e-12), "ik_configs_per_s": s2["attempts"] / max(ts, 1e-12)}
+    # -- the visibility-graph variant on the same workload (the reference's recommended solver, README.md:110-131)
+    for _ in range(3):
+        rr.initWorkspaceGraph()
+        tsv, tcv = rr.sampleConfigurationSpace(Nq, order_independent=True, visibility=True, k=None)
+    sv = rr.stats
+    out["visibility"] = {"call": "sampleConfigurationSpace(Nq, visibility=True, k=None) on random-start samples",
+                         "t_sample_incl_manifolds_s": tsv, "t_connect_s": tcv, "same_node_pairs_tested": sv["self_pairs_tested"],
+                         "reference_manifold_tests": sv["reference_tests"], "components": sv["components"],
+                         "cc_pairs": sv["cc_pairs"], "cc_pairs_connected": sv["cc_pairs_connected"],
+                         "reference_edge_tests": sv["reference_edge_tests"]}
     # -- BASELINE config 3
     pj, resj, rrj = grr.make_program("jaco", "baseline_cfg3.json", device=local, seed=0)
     for _ in range(4):                                    # the last of four builds (buffers allocated, kernels warm)
@@ -554,6 +565,7 @@ def run_cuda(args):
                                    "Python<->C++ crossings per interpolated IK point)"}
 
     # ---- sub-records (1 GPU): parity of the product path, the reference's default (seeded) call, BASELINE config 3 (Jaco) ---
+    st_main = dict(rr.stats)             # the headline workload's last build (the sub-records below re-use rr)
     extras = {}
     if world == 1 and not args.no_extras:
         extras = sub_records(args, grr, torch, _cabi, name, jf, over, pdef, res, rr, local, peak_tf)
@@ -573,7 +585,7 @@ def run_cuda(args):
     line.update(extras)
     if strong5 is not None:
         line["strong_cfg5"] = strong5
-    st0 = rr.stats
+    st0 = st_main
     line["exact_edges"] = {"enabled": bool(getattr(rr, "exact_edges", False)), "rechecked_pairs": st0.get("flagged"),
                            "rechecked_frac": (st0.get("flagged") or 0) / max(st0["pairs"], 1), "verdicts_changed": st0.get("flipped"),
                            "note": "single-precision pass lists near-tie pairs; those are decided again in double precision (grr_edges_build_exact)"}
