@@ -1758,6 +1758,15 @@ struct Impl {
     // as many lanes per SM as shared memory allows, in one or two CTAs
     int threads, per_sm_want;
     lane_geometry(h, 0, 256, threads, per_sm_want);
+    {
+      // this kernel has no static shared memory and no staged node blocks: one CTA per SM can hold more lanes than two
+      // (planar 20R in double precision: 224 against 2 x 96; the kernel is latency-bound at 6 warps per SM)
+      const size_t per_lane = (size_t)h.n * (4 + mc(h)) * sizeof(Real);
+      long t1 = (long)((kSmemBudget - 1024) / per_lane) / 32 * 32;
+      if (t1 > 256) t1 = 256;
+      static const bool off = getenv("GRR_RECHECK_TWO_CTAS") != nullptr;      // A/B switch
+      if (!off && t1 > (long)threads * per_sm_want) threads = (int)t1;
+    }
     if (threads < 32) { set_error("k_edges_recheck: n=%d does not fit shared memory", h.n); return -2; }
     const size_t smem = (size_t)threads * h.n * (4 + mc(h)) * sizeof(Real);
     cudaMemsetAsync(work, 0, sizeof(unsigned long long), st);
