@@ -207,13 +207,15 @@ class RedundancyResolutionGraph:
         return out
 
     # ---- workspace graph -----------------------------------------------------------------------
-    def sampleWorkspace(self, N, k="auto", method="random"):
-        """graph.py:1057-1168 (grid / staggered_grid; 'random' is broken upstream and refused here)."""
+    def sampleWorkspace(self, N, k="auto", method="random", seed=0):
+        """graph.py:1057-1168: grid / staggered_grid, and 'random' (N uniform samples joined to their k nearest
+        neighbours, k = int((1 + 1/dims) e ln N) for 'auto') as the reference intends it -- as shipped that branch
+        raises NameError (graph.py:168,1079).  `seed` keys the random samples (the reference's are unseeded)."""
         assert self.domain is not None, "Need to set domain before calling sampleWorkspace"
-        if method in ("grid", "staggered_grid") and len(self.ikTaskSpace) != 1:
+        if len(self.ikTaskSpace) != 1:
             raise NotImplementedError("TODO: multiple task spaces")
         task = self.ikTaskSpace[0]
-        params, edges, info = build_workspace_graph(self.domain, N, method, task.numConstraints, task.orientation)
+        params, edges, info = build_workspace_graph(self.domain, N, method, task.numConstraints, task.orientation, k=k, seed=seed)
         self._set_workspace(params, edges, info)
 
     def setWorkspaceGraph(self, params, edges, info=None):

@@ -500,11 +500,26 @@ class RedundancyResolver(VisibilityMixin):
         cnt_lower = np.bincount(e[:, 1], minlength=Nw)
         lower_ptr = np.concatenate([[0], np.cumsum(cnt_lower)]).astype(np.int32)
         degree = (np.bincount(e[:, 0], minlength=Nw) + cnt_lower).astype(np.int32)
+        # longest-path levels by peeling the DAG front by front (one vectorised round per level, O(E) in total)
         level = np.zeros(Nw, dtype=np.int64)
-        for i in range(Nw):
-            a, b = lower_ptr[i], lower_ptr[i + 1]
-            if b > a:
-                level[i] = level[lower_idx[a:b]].max() + 1
+        upper_order = np.argsort(e[:, 0], kind="stable")
+        upper_idx = e[upper_order, 1]
+        upper_ptr = np.concatenate([[0], np.cumsum(np.bincount(e[:, 0], minlength=Nw))])
+        pending = cnt_lower.copy()
+        front = np.flatnonzero(pending == 0)
+        l = 0
+        while front.size:
+            level[front] = l
+            a, b = upper_ptr[front], upper_ptr[front + 1]
+            tot = int((b - a).sum())
+            if tot == 0:
+                break
+            pos = np.repeat(a - np.concatenate([[0], np.cumsum(b - a)[:-1]]), b - a) + np.arange(tot)
+            ups = upper_idx[pos]
+            np.subtract.at(pending, ups, 1)
+            cand = np.unique(ups)
+            front = cand[pending[cand] == 0]
+            l += 1
         by_level = np.argsort(level, kind="stable").astype(np.int32)
         bounds = np.concatenate([[0], np.cumsum(np.bincount(level))]).astype(np.int64)
         dev = self.resolution.torch_device

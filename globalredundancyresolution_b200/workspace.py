@@ -5,7 +5,8 @@ Host-side setup code (one-off, negligible next to the IK / edge kernels; SURVEY 
 integer index arithmetic over numpy arrays instead of the reference's dict-of-tuples graphs, but it
 produces the same node numbering (insertion order of the reference's loops), parameters and edge set
 as grr/graph.py:184-303 (IKTask.grid / staggered_grid), :1090-1166 (sampleWorkspace sizing and
-renumbering) and grr/utils/so3_grid.py:5-160.  tests/test_workspace_graphs.py pins this against the
+renumbering), :1077-1089 + :808-841 (the `random` k-nearest-neighbour graph) and grr/utils/so3_grid.py:5-160.
+tests/test_workspace_graphs.py pins this against the
 reference's shipped fixture and against the literal restatement in oracle/graphs.py.
 """
 from __future__ import annotations
@@ -286,7 +287,7 @@ def _moments(R):
 # ---------------------------------------------------------------------------------------------
 # sampleWorkspace sizing (graph.py:1090-1166)
 # ---------------------------------------------------------------------------------------------
-def build_workspace_graph(domain, N, method, num_constraints, orientation):
+def build_workspace_graph(domain, N, method, num_constraints, orientation, k="auto", seed=0):
     """Returns (params [Nw,dw] float64, edges [E,2] int64 i<j sorted, info dict)."""
     bmin, bmax = [float(v) for v in domain[0]], [float(v) for v in domain[1]]
     dims = len([1 for a, b in zip(bmin, bmax) if a != b])                      # graph.py:1076
@@ -326,9 +327,84 @@ def build_workspace_graph(domain, N, method, num_constraints, orientation):
             pp, pe = cartesian_product(pp, pe, _moments(R), re)
         return pp, pe, info
     if method == "random":
-        raise NotImplementedError(
-            "workspace_graph='random' raises NameError in the reference (graph.py:168,1079) and is out of scope")
+        params = random_workspace_points(domain, N, orientation, seed)
+        if k == "auto":
+            k = int((1 + 1.0 / dims) * math.e * math.log(N))                   # graph.py:1082
+        edges = knn_workspace_edges(params, int(k) + 1)                        # graph.py:1088: k + 1 (the node itself is one of them)
+        return params, edges, {"k": int(k), "seed": seed}
     raise ValueError("Unknown method " + str(method))                         # graph.py:1168
+
+
+# ---------------------------------------------------------------------------------------------
+# workspace_graph = "random" (graph.py:1077-1089, 166-182, 808-841)
+# ---------------------------------------------------------------------------------------------
+def random_workspace_points(domain, N, orientation, seed=0):
+    """N workspace parameter vectors drawn as IKTask.sample intends (graph.py:166-182): positions uniform in
+    [bmin, bmax] (a degenerate axis keeps its value), plus the moment of a uniformly drawn rotation for
+    orientation='variable'.  As shipped the reference raises NameError here (`task.sample(domain)` at :1079 and
+    `bmin, bmax` at :168 are undefined names): this is the evident intent -- `(bmin, bmax) = domain`.  The reference
+    draws from Python's unseeded global `random`; here the draws are a seeded Philox stream."""
+    bmin = np.asarray(domain[0], dtype=np.float64)
+    bmax = np.asarray(domain[1], dtype=np.float64)
+    rng = np.random.Generator(np.random.Philox(key=int(seed)))
+    x = bmin + rng.random((N, bmin.shape[0])) * (bmax - bmin)
+    if orientation == "variable":
+        assert bmin.shape[0] in (3, 6)                                          # graph.py:172-177
+        qu = rng.standard_normal((N, 4))
+        qu /= np.linalg.norm(qu, axis=1, keepdims=True)
+        mom = np.asarray([_so3.moment(_so3.from_quaternion(q)) for q in qu])
+        x = np.concatenate([x[:, :3], mom], axis=1)
+    elif orientation == "axis":
+        raise NotImplementedError("orientation='axis' is out of scope")
+    return x
+
+
+def _rotations_from_moments(w):
+    """Rodrigues' formula on [N,3] rotation vectors -> [N,3,3] (so3.from_moment, vectorised)."""
+    th = np.linalg.norm(w, axis=1)
+    safe = np.where(th < 1e-12, 1.0, th)
+    a = w / safe[:, None]
+    K = np.zeros((w.shape[0], 3, 3))
+    K[:, 0, 1], K[:, 0, 2], K[:, 1, 0] = -a[:, 2], a[:, 1], a[:, 2]
+    K[:, 1, 2], K[:, 2, 0], K[:, 2, 1] = -a[:, 0], -a[:, 1], a[:, 0]
+    s, c = np.sin(th)[:, None, None], np.cos(th)[:, None, None]
+    return np.eye(3)[None] + s * K + (1.0 - c) * (K @ K)
+
+
+def knn_workspace_edges(params, kq):
+    """connectWorkspaceNeighbors(i, k=kq) for every node i (graph.py:808-841, 1086-1088): node i is joined to its kq
+    nearest nodes in the L2 metric on the parameter vectors (one of which is i itself).  Parameters with a rotation part
+    (len > 3) are also looked up at the antipodal moment rx - 2 pi rx/|rx| (:826-833), and the kq candidates kept are the
+    closest by workspace distance |dp| + angle(Ra^T Rb)/pi (:835-837; a node found by both look-ups takes two of the kq
+    places, as in the reference).  k-d tree look-ups instead of the reference's Python kd-tree; same neighbours."""
+    from scipy.spatial import cKDTree
+    params = np.asarray(params, dtype=np.float64)
+    N, dw = params.shape
+    kq = min(int(kq), N)
+    tree = cKDTree(params)
+    _, idx = tree.query(params, k=kq)
+    idx = idx.reshape(N, kq)
+    if dw > 3:
+        rx = params[:, 3:]
+        nr = np.linalg.norm(rx, axis=1)
+        far = nr > 0.01
+        xnew = params.copy()
+        xnew[far, 3:] = rx[far] - 2 * math.pi * rx[far] / nr[far, None]
+        _, idx2 = tree.query(xnew, k=kq)
+        cand = np.concatenate([idx, idx2.reshape(N, kq)], axis=1)               # [N, 2 kq]
+        R = _rotations_from_moments(rx)
+        dp = np.linalg.norm(params[cand, :3] - params[:, None, :3], axis=2)
+        rel = np.einsum("nji,ncjk->ncik", R, R[cand])                           # Ra^T Rb per candidate
+        v = 0.5 * np.stack([rel[..., 2, 1] - rel[..., 1, 2], rel[..., 0, 2] - rel[..., 2, 0], rel[..., 1, 0] - rel[..., 0, 1]], axis=-1)
+        ang = np.arctan2(np.linalg.norm(v, axis=-1), 0.5 * (np.trace(rel, axis1=-2, axis2=-1) - 1.0))
+        d = dp + ang / math.pi
+        d[~far, kq:] = np.inf                                                   # no antipodal look-up for these nodes
+        order = np.lexsort((cand, d), axis=1)[:, :kq]
+        idx = np.take_along_axis(cand, order, axis=1)
+    src = np.repeat(np.arange(N), idx.shape[1])
+    dst = idx.reshape(-1)
+    keep = src != dst
+    return _canon_edges(np.stack([src[keep], dst[keep]], axis=1))
 
 
 def explicit_product_graph(domain, divs, rot_N, staggered=True):

@@ -240,3 +240,37 @@ def sample_workspace(domain, N, method, num_constraints, orientation):
         if a != b:
             out_edges.add((min(a, b), max(a, b)))
     return out_params, out_edges, divs
+
+
+def connect_workspace_neighbors(params, k, workspace_distance):
+    """The k-nearest-neighbour loop of sampleWorkspace(method='random') (graph.py:1086-1088) with
+    connectWorkspaceNeighbors (graph.py:823-841) written out: for every node, the k nearest stored points in the L2
+    metric on the parameter lists (the node itself is one of them), for parameters with a rotation part also the k
+    nearest of the antipodal moment, the union sorted by (workspace distance, point, node) and cut to k; every
+    neighbour other than the node itself becomes an edge.  Brute force instead of the reference's kd-tree (same
+    neighbours).  Returns the set of (i<j)."""
+    pts = [list(map(float, p)) for p in params]
+    N = len(pts)
+
+    def knearest(x, k):
+        d = sorted((math.sqrt(sum((a - b) ** 2 for a, b in zip(x, pt))), n) for n, pt in enumerate(pts))
+        return [(pts[n], n) for (_, n) in d[:k]]
+
+    edges = set()
+    for iw in range(N):
+        x = pts[iw]
+        knn = knearest(x, k)
+        if len(x) > 3:
+            rx = x[3:]
+            nrm = math.sqrt(sum(v * v for v in rx))
+            if nrm > 0.01:
+                rxnew = [v + (v / nrm) * (-2 * math.pi) for v in rx]
+                knn += knearest(x[:3] + rxnew, k)
+            sortlist = [(workspace_distance(pt, x), pt, n) for pt, n in knn]
+            knn = [(pt, n) for (d, pt, n) in sorted(sortlist)]
+            knn = knn[:k]
+        for pt, n in knn:
+            if n == iw:
+                continue
+            edges.add((min(iw, n), max(iw, n)))
+    return edges

@@ -30,6 +30,9 @@ CASES = {
     "baxter_fixed": ("baxter", "Rdown.json", 150, "staggered_grid"),
     "robonaut2_fixed": ("robonaut2", "baseline_cfg5.json", 150, "staggered_grid"),
     "atlas_free_generic_n": ("atlas", "Rfree.json", 150, "staggered_grid"),
+    # workspace_graph="random": uniform samples joined to their k nearest neighbours (irregular degrees, long edges)
+    "planar_20R_random": ("planar_20R", "baseline_cfg2.json", 60, "random"),
+    "jaco_random": ("jaco", "baseline_cfg3.json", 60, "random"),
 }
 NQ = 12
 SEED = 5

@@ -98,9 +98,7 @@ def test_variable_orientation_6d_quirk():
     assert (p.shape[0], e.shape[0]) == (40248, 429408)
 
 
-def test_random_graph_is_refused():
-    with pytest.raises(NotImplementedError):
-        W.build_workspace_graph([[-1, 0, -1], [1, 0, 1]], 100, "random", 3, "free")
+def test_unknown_method_is_refused():
     with pytest.raises(ValueError):
         W.build_workspace_graph([[-1, 0, -1], [1, 0, 1]], 100, "hexagonal", 3, "free")
 
@@ -122,3 +120,44 @@ def test_loader_reads_the_reference_fixture_bytes():
     node, adj, _ = _nx1pickle.loads_graph(data)
     assert len(node) == 3900 and sum(len(a) for a in adj.values()) // 2 == 19774
     assert sum(1 for u in adj for v, d in adj[u].items() if u < v and d.get("connected")) == 4211
+
+
+# ---- workspace_graph = "random" (graph.py:1077-1089; raises NameError upstream, built here as intended) ----------
+def _ws_distance(a, b):
+    from globalredundancyresolution_b200 import so3
+    dt = math.sqrt(sum((p - q) ** 2 for p, q in zip(a[:3], b[:3])))
+    if len(a) <= 3:
+        return dt
+    return dt + so3.distance(so3.from_moment(a[3:]), so3.from_moment(b[3:])) / math.pi
+
+
+@pytest.mark.parametrize("orientation,nc,domain,N", [
+    ("free", 3, [[-2, 0, -2], [2.15, 0, 2.15]], 300),
+    ("fixed", 6, [[-0.3, -0.8, 0.4], [1.4, 1.0, 2.0]], 250),
+    ("variable", 6, [[-1, -0.8, -0.7, -math.pi, -math.pi, -math.pi], [1.5, 1.7, 1.8, -math.pi, -math.pi, -math.pi]], 160),
+])
+def test_random_workspace_graph_equals_literal_knn(orientation, nc, domain, N):
+    params, edges, info = W.build_workspace_graph(domain, N, "random", nc, orientation, seed=3)
+    dims = len([1 for a, b in zip(domain[0], domain[1]) if a != b])
+    assert info["k"] == int((1 + 1.0 / dims) * math.e * math.log(N))
+    assert params.shape == (N, 6 if orientation == "variable" else 3)
+    lo, hi = np.asarray(domain[0][:3]), np.asarray(domain[1][:3])
+    assert (params[:, :3] >= lo).all() and (params[:, :3] <= hi).all()
+    if orientation == "variable":
+        assert (np.linalg.norm(params[:, 3:], axis=1) <= math.pi + 1e-12).all()
+    e_o = OG.connect_workspace_neighbors(params, info["k"] + 1, _ws_distance)
+    assert {tuple(e) for e in edges.tolist()} == e_o
+    deg = np.bincount(edges.reshape(-1), minlength=N)
+    assert deg.min() >= (info["k"] if orientation != "variable" else 1)        # every node keeps its own k neighbours
+    # same seed -> same graph; another seed -> another graph
+    p2, e2, _ = W.build_workspace_graph(domain, N, "random", nc, orientation, seed=3)
+    assert np.array_equal(p2, params) and np.array_equal(e2, edges)
+    p3, _, _ = W.build_workspace_graph(domain, N, "random", nc, orientation, seed=4)
+    assert not np.array_equal(p3, params)
+
+
+def test_random_workspace_graph_explicit_k():
+    params, edges, info = W.build_workspace_graph([[-1, -1, 0], [1, 1, 0]], 100, "random", 3, "free", k=4)
+    assert info["k"] == 4
+    deg = np.bincount(edges.reshape(-1), minlength=100)
+    assert deg.min() >= 4
