@@ -25,7 +25,7 @@ MAX_JOINTS = 32
 # every symbol include/grr_b200.h declares (checked by tests/test_cabi_symbols.py)
 EXPORTS = [
     "grr_last_error", "grr_abi_version", "grr_chain_create", "grr_chain_destroy", "grr_task_set",
-    "grr_chain_num_joints", "grr_fk_batch", "grr_ik_solve_batch", "grr_ik_sample", "grr_ik_sample_level", "grr_dedup", "grr_dedup_sweep",
+    "grr_chain_num_joints", "grr_chain_set_spin_joints", "grr_fk_batch", "grr_ik_solve_batch", "grr_ik_sample", "grr_ik_sample_level", "grr_dedup", "grr_dedup_sweep",
     "grr_edges_build", "grr_edges_build_exact", "grr_set_flag_scale", "grr_edges_exact_mode", "grr_edges_cost", "grr_edges_compact", "grr_valid_edge_batch", "grr_gather_node_blocks",
     "grr_scatter_node_blocks", "grr_halo_exchange", "grr_csp_random_assignment", "grr_csp_conflicts", "grr_csp_descent_sweep",
     "grr_fp32_peak", "grr_fp32x2_peak", "grr_fp64_peak",
@@ -70,6 +70,7 @@ def lib():
     L.grr_chain_destroy.argtypes = [vp]
     L.grr_task_set.argtypes = [vp, C.c_int, C.POINTER(C.c_double)]
     L.grr_chain_num_joints.argtypes = [vp]
+    L.grr_chain_set_spin_joints.argtypes = [vp, C.POINTER(C.c_int32)]
     L.grr_fk_batch.argtypes = [vp, C.c_int, i64, vp, vp, vp, vp]
     L.grr_ik_solve_batch.argtypes = [vp, C.c_int, i64, vp, vp, vp, vp, vp, vp, vp]
     L.grr_ik_sample.argtypes = [vp, C.c_int, i64, i32, i32, vp, vp, u64, i32, vp, vp, vp, vp, vp]
@@ -112,7 +113,7 @@ def lib():
 
 def check(rc, what):
     global LAUNCHES
-    if what not in ("grr_chain_create", "grr_task_set", "grr_fp32_peak", "grr_fp32x2_peak", "grr_fp64_peak", "grr_set_flag_scale", "grr_edges_exact_mode", "grr_pair_hash"):
+    if what not in ("grr_chain_create", "grr_task_set", "grr_fp32_peak", "grr_fp32x2_peak", "grr_fp64_peak", "grr_set_flag_scale", "grr_edges_exact_mode", "grr_pair_hash", "grr_chain_set_spin_joints"):
         # edges_build = k_edge_load + k_edges_build (+ k_edges_recheck in the exact build)
         LAUNCHES += {"grr_edges_build": 2, "grr_edges_build_exact": 3}.get(what, 1)
     if rc != 0:
@@ -158,6 +159,8 @@ class ChainHandle:
         self.device = int(device)
         self._keep = {k: np.ascontiguousarray(np.asarray(chain_arrays[k], dtype=np.float64))
                       for k in ("Rp", "tp", "axis", "qmin", "qmax", "ee_local", "R_tail")}
+        sp = chain_arrays.get("spin") if hasattr(chain_arrays, "get") else None
+        self.spin = np.zeros(self.n, dtype=np.int32) if sp is None else np.ascontiguousarray(np.asarray(sp, dtype=np.int32))
         self.nlinks_eps = int(nlinks_eps if nlinks_eps is not None else self.n)
         self.tol, self.max_iters, self.lam = float(tol), int(max_iters), float(lam)
         self._R_goal = np.eye(3).reshape(9) if R_goal is None else np.asarray(R_goal, dtype=np.float64).reshape(9).copy()
@@ -188,6 +191,8 @@ class ChainHandle:
             h = C.c_void_p()
             check(L.grr_chain_create(C.byref(d), self.device, C.byref(h)), "grr_chain_create")
             self._handle = h
+            if self.spin.any():
+                check(L.grr_chain_set_spin_joints(h, self.spin.ctypes.data_as(C.POINTER(C.c_int32))), "grr_chain_set_spin_joints")
             if self._flag_scale is not None:
                 check(L.grr_set_flag_scale(h, float(self._flag_scale)), "grr_set_flag_scale")
         return self._handle

@@ -33,7 +33,7 @@ static inline int launch_ok(const char *what) {
 // ------------------------------------------------------------------------------------------
 template <typename Real>
 __global__ void __launch_bounds__(128)
-k_dedup(int n, int Nq, int Nqp, const Real *__restrict__ q_raw, const uint8_t *__restrict__ status, Real thresh,
+k_dedup(int n, unsigned spin, int Nq, int Nqp, const Real *__restrict__ q_raw, const uint8_t *__restrict__ status, Real thresh,
         int Nqp_kept, Real *q_kept, const int32_t *count_in, int32_t *__restrict__ keep_idx,
         int32_t *count, const int32_t *__restrict__ node_list) {
   // raw candidates are indexed by block (level-local when node_list is given), kept configs by workspace node
@@ -49,7 +49,7 @@ k_dedup(int n, int Nq, int Nqp, const Real *__restrict__ q_raw, const uint8_t *_
     int same = 0;
     for (int k = threadIdx.x; k < kept; k += blockDim.x) {
       Real d2 = 0;
-      for (int j = 0; j < n; j++) { Real d = raw[j * Nqp + s] - out[j * Nqp_kept + k]; d2 += d * d; }
+      for (int j = 0; j < n; j++) { Real d = joint_diff(spin, j, raw[j * Nqp + s], out[j * Nqp_kept + k]); d2 += d * d; }
       if (sqrt_(d2) < thresh) same = 1;
     }
     same = __syncthreads_or(same);
@@ -72,7 +72,7 @@ k_dedup(int n, int Nq, int Nqp, const Real *__restrict__ q_raw, const uint8_t *_
 // ------------------------------------------------------------------------------------------
 template <typename Real>
 __global__ void __launch_bounds__(128)
-k_dedup_sweep(int n, int Nq, const int32_t *__restrict__ node_list, int Nqs, const Real *__restrict__ q_seed,
+k_dedup_sweep(int n, unsigned spin, int Nq, const int32_t *__restrict__ node_list, int Nqs, const Real *__restrict__ q_seed,
               const uint8_t *__restrict__ st_seed, const int32_t *__restrict__ nadj, int use_seeded, int Nqr,
               const Real *__restrict__ q_rand, const uint8_t *__restrict__ st_rand, Real thresh, int Nqp_kept, Real *q_kept,
               int32_t *count, unsigned long long *counters) {
@@ -99,7 +99,7 @@ k_dedup_sweep(int n, int Nq, const int32_t *__restrict__ node_list, int Nqs, con
     int same = 0;
     for (int k = threadIdx.x; k < kept; k += blockDim.x) {
       Real d2 = 0;
-      for (int j = 0; j < n; j++) { Real d = cand[(long long)j * cs] - out[j * Nqp_kept + k]; d2 += d * d; }
+      for (int j = 0; j < n; j++) { Real d = joint_diff(spin, j, cand[(long long)j * cs], out[j * Nqp_kept + k]); d2 += d * d; }
       if (sqrt_(d2) < thresh) same = 1;
     }
     same = __syncthreads_or(same);
@@ -167,7 +167,7 @@ k_edges_compact(int Nq, const uint32_t *__restrict__ mask, const long long *__re
 // ------------------------------------------------------------------------------------------
 template <typename Real>
 __global__ void __launch_bounds__(256)
-k_edges_cost(int n, int nlinks_eps, const int32_t *__restrict__ wedges, const Real *__restrict__ q_kept,
+k_edges_cost(int n, unsigned spin, int nlinks_eps, const int32_t *__restrict__ wedges, const Real *__restrict__ q_kept,
              const int32_t *__restrict__ count, const int32_t *__restrict__ old_count, int Nqp, Real epsilon,
              unsigned long long *__restrict__ cost) {
   extern __shared__ __align__(16) unsigned char smem_cost[];
@@ -190,7 +190,7 @@ k_edges_cost(int n, int nlinks_eps, const int32_t *__restrict__ wedges, const Re
     const int a = (int)(t / (unsigned)cb), b = (int)(t - (unsigned)a * (unsigned)cb);
     if (a < oa && b < ob) continue;
     Real d2 = 0;
-    for (int j = 0; j < n; j++) { const Real d = sa[j * Nqp + a] - sb[j * Nqp + b]; d2 += d * d; }
+    for (int j = 0; j < n; j++) { const Real d = joint_diff(spin, j, sa[j * Nqp + a], sb[j * Nqp + b]); d2 += d * d; }
     acc += (unsigned long long)ceil_(sqrt_(d2) / eps) + 1ull;
   }
   for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
@@ -368,6 +368,12 @@ int grr_chain_create(const grr_chain_desc *d, int device, grr_handle_t *out) {
   return 0;
 }
 
+int grr_chain_set_spin_joints(grr_handle_t h, const int32_t *flags) {
+  if (!h) { set_error("null handle"); return -1; }
+  for (int j = 0; j < h->hc.n; j++) h->hc.spin[j] = (flags && flags[j]) ? 1 : 0;
+  return 0;
+}
+
 int grr_set_flag_scale(grr_handle_t h, double scale) {
   if (!h) { set_error("null handle"); return -1; }
   if (!(scale > 0)) { set_error("grr_set_flag_scale: scale must be positive"); return -1; }
@@ -492,10 +498,10 @@ int grr_dedup(grr_handle_t h, int dtype, int64_t Nw, int32_t Nq, int32_t Nqp, co
   if (!q_raw || !status || !q_kept || !count) { set_error("grr_dedup: null buffer"); return -1; }
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == GRR_F32)
-    k_dedup<float><<<(unsigned)Nw, 128, 0, st>>>(h->hc.n, Nq, Nqp, (const float *)q_raw, status, (float)thresh, Nqp_kept,
+    k_dedup<float><<<(unsigned)Nw, 128, 0, st>>>(h->hc.n, spin_mask_of(h->hc), Nq, Nqp, (const float *)q_raw, status, (float)thresh, Nqp_kept,
                                                  (float *)q_kept, count_in, keep_idx, count, nullptr);
   else if (dtype == GRR_F64)
-    k_dedup<double><<<(unsigned)Nw, 128, 0, st>>>(h->hc.n, Nq, Nqp, (const double *)q_raw, status, thresh, Nqp_kept,
+    k_dedup<double><<<(unsigned)Nw, 128, 0, st>>>(h->hc.n, spin_mask_of(h->hc), Nq, Nqp, (const double *)q_raw, status, thresh, Nqp_kept,
                                                   (double *)q_kept, count_in, keep_idx, count, nullptr);
   else { set_error("bad dtype %d", dtype); return -1; }
   return launch_ok("k_dedup");
@@ -512,11 +518,11 @@ int grr_dedup_sweep(grr_handle_t h, int dtype, int64_t L, const int32_t *node_li
   }
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == GRR_F32)
-    k_dedup_sweep<float><<<(unsigned)L, 128, 0, st>>>(h->hc.n, Nq, node_list, Nqs, (const float *)q_seed, status_seed, nadj,
+    k_dedup_sweep<float><<<(unsigned)L, 128, 0, st>>>(h->hc.n, spin_mask_of(h->hc), Nq, node_list, Nqs, (const float *)q_seed, status_seed, nadj,
                                                       seed_from_adjacent, Nqr, (const float *)q_rand, status_rand, (float)thresh,
                                                       Nqp_kept, (float *)q_kept, count, (unsigned long long *)counters);
   else if (dtype == GRR_F64)
-    k_dedup_sweep<double><<<(unsigned)L, 128, 0, st>>>(h->hc.n, Nq, node_list, Nqs, (const double *)q_seed, status_seed, nadj,
+    k_dedup_sweep<double><<<(unsigned)L, 128, 0, st>>>(h->hc.n, spin_mask_of(h->hc), Nq, node_list, Nqs, (const double *)q_seed, status_seed, nadj,
                                                        seed_from_adjacent, Nqr, (const double *)q_rand, status_rand, thresh,
                                                        Nqp_kept, (double *)q_kept, count, (unsigned long long *)counters);
   else { set_error("bad dtype %d", dtype); return -1; }
@@ -595,12 +601,12 @@ int grr_edges_cost(grr_handle_t h, int dtype, int64_t E, const int32_t *wedges, 
   if (dtype == GRR_F32) {
     auto kern = k_edges_cost<float>;
     if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    kern<<<(unsigned)E, 256, smem, st>>>(n, h->hc.nlinks_eps, wedges, (const float *)q_kept, count, old_count, Nqp, (float)epsilon,
+    kern<<<(unsigned)E, 256, smem, st>>>(n, spin_mask_of(h->hc), h->hc.nlinks_eps, wedges, (const float *)q_kept, count, old_count, Nqp, (float)epsilon,
                                          (unsigned long long *)cost);
   } else if (dtype == GRR_F64) {
     auto kern = k_edges_cost<double>;
     if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    kern<<<(unsigned)E, 256, smem, st>>>(n, h->hc.nlinks_eps, wedges, (const double *)q_kept, count, old_count, Nqp, epsilon,
+    kern<<<(unsigned)E, 256, smem, st>>>(n, spin_mask_of(h->hc), h->hc.nlinks_eps, wedges, (const double *)q_kept, count, old_count, Nqp, epsilon,
                                          (unsigned long long *)cost);
   } else { set_error("bad dtype %d", dtype); return -1; }
   return launch_ok("k_edges_cost");

@@ -60,6 +60,30 @@ GRR_DEV float min_(float a, float b) { return fminf(a, b); }
 GRR_DEV double min_(double a, double b) { return fmin(a, b); }
 GRR_DEV float ceil_(float a) { return ceilf(a); }
 GRR_DEV double ceil_(double a) { return ceil(a); }
+GRR_DEV float fmod_(float a, float b) { return fmodf(a, b); }
+GRR_DEV double fmod_(double a, double b) { return fmod(a, b); }
+
+// ---- 'spin' joints (continuous rotation; Klamp't joint type 'spin', reference flag graph.py:556-561) ----------------
+// robot.distance takes the wrapped angular difference of such a joint and robot.interpolate its shorter arc (SURVEY K1/K2,
+// A.1: [recalled] KrisLibrary AngleNormalize / AngleDiff / AngleInterp); the oracle restates the same three functions.
+// spin_mask bit j of the chain constants marks active joint j; every use is behind `if (spin_mask ...)`, so chains of
+// 'normal' joints (every shipped problem) run the code they ran before.
+template <typename Real> GRR_DEV Real angle_normalize(Real a) {           // into [0, 2 pi)
+  const Real an = fmod_(a, Real(6.283185307179586476925286766559));
+  return an < Real(0) ? an + Real(6.283185307179586476925286766559) : an;
+}
+template <typename Real> GRR_DEV Real angle_diff(Real a, Real b) {        // a - b, into (-pi, pi]
+  const Real d = angle_normalize(angle_normalize(a) - angle_normalize(b));
+  return d > Real(3.1415926535897932384626433832795) ? d - Real(6.283185307179586476925286766559) : d;
+}
+// value of active joint j as an IK solve returns it ([recalled] robot.NormalizeAngles after the solve)
+template <typename Real> GRR_DEV Real joint_out(unsigned spin_mask, int j, Real v) {
+  return (spin_mask >> j & 1u) ? angle_normalize(v) : v;
+}
+// joint-space difference a - b of active joint j as robot.distance measures it
+template <typename Real> GRR_DEV Real joint_diff(unsigned spin_mask, int j, Real a, Real b) {
+  return (spin_mask >> j & 1u) ? angle_diff(a, b) : a - b;
+}
 
 // ------------------------------------------------------------------------------------------
 // chain constants (kernel parameter, __grid_constant__: lives in the constant bank)
@@ -71,7 +95,7 @@ struct alignas(16) JointConst {
   Real sgn;        // +-1 for the short kinds (axis = sgn e_K)
   Real bmin, bmax; // joint box (+-inf for revolute joints with range >= 2 pi)
   int kind;        // 0 generic; 1/2/3: identity preceding rotation and axis = +-e_x / e_y / e_z
-  int pad;
+  int spin;        // 1: 'spin' joint (unbounded; wrapped distance, shorter-arc interpolation)
 };
 
 template <typename Real, int NJ>
@@ -79,6 +103,7 @@ struct ChainDev {
   int n, mode, nlinks_eps, max_iters;
   int small_angles;            // every joint limit inside [-pi/4, pi/4]: sincos needs no range reduction
   int axes_positive;           // every short-path joint has sgn = +1
+  unsigned spin_mask;          // bit j: active joint j is a 'spin' joint (0 for every shipped problem)
   Real tol, lambda;
   // near-tie margins of the single-precision edge phase (FLAG builds of lane_step / pair_advance; all 0 otherwise)
   Real fl_f, fl_f2, fl_x, fl_alam, fl_rel, fl_leaf, fl_nd, fl_dd, fl_curv, fl_curv1, fl_jac;

@@ -64,21 +64,24 @@ void fill_chain(const HostChain &h, ChainDev<Real, NJ> &d) {
         if (ident && fabs(fabs(a[k]) - 1.0) < 1e-14 && fabs(a[(k + 1) % 3]) < 1e-14 && fabs(a[(k + 2) % 3]) < 1e-14) kind = k + 1;
       d.jc[j].kind = kind;
       d.jc[j].sgn = (Real)(kind ? (a[kind - 1] > 0 ? 1.0 : -1.0) : 0.0);
-      d.jc[j].pad = 0;
+      d.jc[j].spin = h.spin[j] ? 1 : 0;
     }
-    const bool unbounded = (h.qmax[j] - h.qmin[j]) >= 2.0 * 3.14159265358979323846;
+    // 'spin' joints have no limits in the solver; their random starts are uniform in [0, 2 pi) ([recalled] Klamp't RobotCSpace)
+    const bool unbounded = h.spin[j] || (h.qmax[j] - h.qmin[j]) >= 2.0 * 3.14159265358979323846;
     d.bmin[j] = unbounded ? -std::numeric_limits<Real>::infinity() : (Real)h.qmin[j];
     d.bmax[j] = unbounded ? std::numeric_limits<Real>::infinity() : (Real)h.qmax[j];
     float lo = (float)h.qmin[j], hi = (float)h.qmax[j];
     if (unbounded) { lo = -3.14159265358979f; hi = 3.14159265358979f; }
+    if (h.spin[j]) { lo = 0.0f; hi = 6.28318530717959f; }
     d.slo[j] = lo; d.srange[j] = hi - lo;
     d.jc[j].bmin = d.bmin[j]; d.jc[j].bmax = d.bmax[j];
     for (int k = 0; k < 3; k++) d.jc[j].tp[k] = d.tp[j][k];
   }
+  d.spin_mask = spin_mask_of(h);
   d.small_angles = 1;
   d.axes_positive = 1;
   for (int j = 0; j < h.n && j < NJ; j++) {
-    if (!(h.qmin[j] >= -0.785 && h.qmax[j] <= 0.785)) d.small_angles = 0;
+    if (!(h.qmin[j] >= -0.785 && h.qmax[j] <= 0.785) || h.spin[j]) d.small_angles = 0;
     if (d.jc[j].kind != 0 && !(d.jc[j].sgn > 0)) d.axes_positive = 0;
   }
   for (int k = 0; k < 3; k++) d.ee[k] = (Real)h.ee_local[k];

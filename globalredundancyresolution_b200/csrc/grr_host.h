@@ -15,6 +15,7 @@ struct HostChain {
   double Rp[GRR_MAX_JOINTS * 9], tp[GRR_MAX_JOINTS * 3], axis[GRR_MAX_JOINTS * 3];
   double qmin[GRR_MAX_JOINTS], qmax[GRR_MAX_JOINTS];
   double ee_local[3], R_tail[9], R_goal[9];
+  int spin[GRR_MAX_JOINTS];      // 1: 'spin' joint (grr_chain_set_spin_joints)
   // near-tie margins of the exact edge build (grr_edges_build_exact), see flag_margins() in grr_fill.cuh
   double fl[10];
 };
@@ -22,12 +23,18 @@ struct HostChain {
 enum { FL_F = 0, FL_X = 1, FL_ALAM = 2, FL_REL = 3, FL_LEAF = 4, FL_ND = 5, FL_MAXIT = 6, FL_DD = 7, FL_CURV = 8 };
 
 void set_error(const char *fmt, ...);
+inline unsigned spin_mask_of(const HostChain &h) {
+  unsigned m = 0;
+  for (int j = 0; j < h.n; j++) if (h.spin[j]) m |= 1u << j;
+  return m;
+}
 
 // planar-y chain: every joint has identity preceding rotation and axis +-e_y, goal-link frame = last joint frame, free
 // orientation (the reference's planar_{2,3,5,10,20}R robots): the chains with the two-dimensional specialisation of the
 // lane pass, and the ones whose exact edge build is the single-precision pass + recheck
 inline bool is_planar_y_chain(const HostChain &h) {
   if (h.mode != GRR_FREE) return false;
+  for (int j = 0; j < h.n; j++) if (h.spin[j]) return false;
   for (int k = 0; k < 9; k++) if (fabs(h.R_tail[k] - ((k % 4 == 0) ? 1.0 : 0.0)) > 1e-14) return false;
   for (int j = 0; j < h.n; j++) {
     const double *R = h.Rp + 9 * j, *a = h.axis + 3 * j;

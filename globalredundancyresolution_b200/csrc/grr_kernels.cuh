@@ -41,12 +41,13 @@ struct LaneCounters {
 // double precision, 3 residual rows: CTAs of at most 192 lanes, two per SM (<= 170 registers: 141-160 used, no spills;
 // 256 lanes x 2 would cap the build at 128 registers, which the general pass does not fit without spilling).  Steady
 // state on one B200: config 3 sampling 12.6 ms (1 CTA of 256 per SM: 21.9 ms), config 2 sampling 8.0 ms.
-template <typename Real, int M, int MODE, bool PL>
+template <typename Real, int M, int MODE, bool PL, bool SPIN = false>
 __global__ void __launch_bounds__((sizeof(Real) == 8 && M == 3) ? 192 : 256, (sizeof(Real) == 8 && M == 3) ? 2 : 1)
 k_ik_instances(const __grid_constant__ ChainDev<Real, kMaxJ> c, long long total, int Nq, int Nqp,
                const Real *__restrict__ params, const int32_t *__restrict__ uid, unsigned long long seed, int sample_offset,
                Real *__restrict__ q, uint8_t *__restrict__ status, uint8_t *__restrict__ iters, Real *__restrict__ resid,
                unsigned long long *work, unsigned long long *counters) {
+  const unsigned kspin = SPIN ? c.spin_mask : 0u;      // compile-time 0 in the kernels of chains without spin joints
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int n = c.n, dw = (c.mode == 2 ? 6 : 3);
   LaneMem<Real, col_rows(M, PL)> mem;
@@ -96,7 +97,7 @@ k_ik_instances(const __grid_constant__ ChainDev<Real, kMaxJ> c, long long total,
     if (__all_sync(0xffffffffu, inst < 0)) break;
     PassOut<Real, M> o;
     if constexpr (PL) lane_pass_planar<Real, false>(c, tg, L, mem, nullptr, 0, o);
-    else lane_pass<Real, M, false>(c, tg, L, mem, nullptr, 0, o);
+    else lane_pass<Real, M, false, SPIN>(c, tg, L, mem, nullptr, 0, o);
     const int st = lane_step<Real, M, PL>(c, L, mem, o, inst >= 0);
     if (inst >= 0) {
       if (st != IK_RUNNING) {
@@ -106,7 +107,7 @@ k_ik_instances(const __grid_constant__ ChainDev<Real, kMaxJ> c, long long total,
           const int s = (int)(inst - node * Nq);
           base = node * n * (long long)Nqp + s; stride = Nqp; sidx = node * Nqp + s;
         } else { base = inst; stride = total; sidx = inst; }
-        for (int j = 0; j < n; j++) q[base + j * stride] = L.res[j * mem.T];
+        for (int j = 0; j < n; j++) q[base + j * stride] = joint_out(kspin, j, L.res[j * mem.T]);
         status[sidx] = (uint8_t)st;
         if (iters) iters[sidx] = (uint8_t)L.it;
         if (resid) resid[sidx] = L.resid;
@@ -128,7 +129,7 @@ k_ik_instances(const __grid_constant__ ChainDev<Real, kMaxJ> c, long long total,
 // computed for the whole graph beforehand by k_ik_instances; k_dedup_sweep then selects the
 // Nq - numAdjacent + numFailed of them the sweep would have run.  nadj[l] is written for that kernel.
 // ------------------------------------------------------------------------------------------
-template <typename Real, int M, bool PL>
+template <typename Real, int M, bool PL, bool SPIN = false>
 __global__ void __launch_bounds__(256)
 k_ik_level(const __grid_constant__ ChainDev<Real, kMaxJ> c, long long total, const int32_t *__restrict__ node_list, int Nq,
            int Nqr, const Real *__restrict__ params, const int32_t *__restrict__ uid,
@@ -136,6 +137,7 @@ k_ik_level(const __grid_constant__ ChainDev<Real, kMaxJ> c, long long total, con
            const Real *__restrict__ Qk, int Nqk, const int32_t *__restrict__ count, unsigned long long seed, int sample_offset,
            int seed_from_adjacent, Real *__restrict__ q_raw, uint8_t *__restrict__ status, int32_t *__restrict__ nadj,
            unsigned long long *work, unsigned long long *counters) {
+  const unsigned kspin = SPIN ? c.spin_mask : 0u;      // compile-time 0 in the kernels of chains without spin joints
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int n = c.n, dw = (c.mode == 2 ? 6 : 3);
   LaneMem<Real, col_rows(M, PL)> mem;
@@ -184,11 +186,11 @@ k_ik_level(const __grid_constant__ ChainDev<Real, kMaxJ> c, long long total, con
     if (__all_sync(0xffffffffu, li < 0)) break;
     PassOut<Real, M> o;
     if constexpr (PL) lane_pass_planar<Real, false>(c, tg, L, mem, nullptr, 0, o);
-    else lane_pass<Real, M, false>(c, tg, L, mem, nullptr, 0, o);
+    else lane_pass<Real, M, false, SPIN>(c, tg, L, mem, nullptr, 0, o);
     const int st = lane_step<Real, M, PL>(c, L, mem, o, li >= 0);
     if (li >= 0 && st != IK_RUNNING) {
       Real *dst = q_raw + (li * n) * (long long)Nqr + col;
-      for (int j = 0; j < n; j++) dst[(long long)j * Nqr] = L.res[j * mem.T];
+      for (int j = 0; j < n; j++) dst[(long long)j * Nqr] = joint_out(kspin, j, L.res[j * mem.T]);
       status[li * Nqr + col] = (uint8_t)st;
       cnt.iters += L.it; cnt.evals += L.evals;       // attempts / successes are counted by k_dedup_sweep
       li = -1;
@@ -233,7 +235,7 @@ __device__ __forceinline__ void st_release_(int32_t *p, int v) {
 // RUNNING total of the sweep, so node i also waits for node i - 1 (order[] is then the identity), reads the total node
 // i - 1 published and runs its random-start attempts itself, T at a time (they cannot be precomputed: their number is
 // known only now), each round filtered into the kept list before the next.
-template <typename Real, int M, bool PL, bool BIASED>
+template <typename Real, int M, bool PL, bool BIASED, bool SPIN = false>
 __global__ void __launch_bounds__(128)
 k_sweep_dataflow(const __grid_constant__ ChainDev<Real, kMaxJ> c, long long Nn, const int32_t *__restrict__ order, int Nq,
                  int Nqr, const Real *__restrict__ params, const int32_t *__restrict__ uid,
@@ -242,6 +244,7 @@ k_sweep_dataflow(const __grid_constant__ ChainDev<Real, kMaxJ> c, long long Nn, 
                  int sample_offset, int seed_from_adjacent, const Real *__restrict__ q_rand,
                  const uint8_t *__restrict__ st_rand, Real thresh, int32_t *ready, unsigned long long *work,
                  unsigned long long *counters, long long start_total, int nodes_with_configs, long long *total_after) {
+  const unsigned kspin = SPIN ? c.spin_mask : 0u;      // compile-time 0 in the kernels of chains without spin joints
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int n = c.n, dw = (c.mode == 2 ? 6 : 3);
   const int T = blockDim.x, tid = threadIdx.x, lane = tid & 31;
@@ -335,12 +338,12 @@ k_sweep_dataflow(const __grid_constant__ ChainDev<Real, kMaxJ> c, long long Nn, 
         if (__all_sync(0xffffffffu, s_run < 0)) break;
         PassOut<Real, M> o;
         if constexpr (PL) lane_pass_planar<Real, false>(c, tg, L, mem, nullptr, 0, o);
-        else lane_pass<Real, M, false>(c, tg, L, mem, nullptr, 0, o);
+        else lane_pass<Real, M, false, SPIN>(c, tg, L, mem, nullptr, 0, o);
         const int st = lane_step<Real, M, PL>(c, L, mem, o, s_run >= 0);
         if (s_run >= 0 && st != IK_RUNNING) {
           Real *dst = (kind == 0) ? cseed + s_run : crand + s_run;
           const int ds = (kind == 0) ? NqS : T;
-          for (int j = 0; j < n; j++) dst[j * ds] = L.res[j * mem.T];
+          for (int j = 0; j < n; j++) dst[j * ds] = joint_out(kspin, j, L.res[j * mem.T]);
           sst[s_run] = (uint8_t)st;
           cnt.iters += L.it; cnt.evals += L.evals;
           s_run = -1;
@@ -371,10 +374,10 @@ k_sweep_dataflow(const __grid_constant__ ChainDev<Real, kMaxJ> c, long long Nn, 
         Real d2 = 0;
         if (!vs_old) {
           const Real *b = cand_ptr(tidx, ts);
-          for (int j = 0; j < n; j++) { Real d = a[(long long)j * ss] - b[(long long)j * ts]; d2 += d * d; }
+          for (int j = 0; j < n; j++) { Real d = joint_diff(kspin, j, a[(long long)j * ss], b[(long long)j * ts]); d2 += d * d; }
           if (sqrt_(d2) < thresh) atomicOr(&close[sidx * Wc + (tidx >> 5)], 1u << (tidx & 31));
         } else {
-          for (int j = 0; j < n; j++) { Real d = a[(long long)j * ss] - out[j * Nqk + tidx]; d2 += d * d; }
+          for (int j = 0; j < n; j++) { Real d = joint_diff(kspin, j, a[(long long)j * ss], out[j * Nqk + tidx]); d2 += d * d; }
           if (sqrt_(d2) < thresh) cold[sidx] = 1;
         }
       }
@@ -536,9 +539,10 @@ struct PairLane {
 // lies within fl_nd of an integer (the rounding may go the other way in double precision).
 constexpr int kNdFlag = 1 << 30;
 template <typename Real, bool FLAG = false>
-GRR_DEV int pair_ndivs(int n, Real eps, const Real *qa, int sa, const Real *qb, int sb, Real fl_nd = Real(0)) {
+GRR_DEV int pair_ndivs(int n, unsigned spin, Real eps, const Real *qa, int sa, const Real *qb, int sb, Real fl_nd = Real(0)) {
   Real d2 = 0;
-  for (int j = 0; j < n; j++) { const Real d = qa[j * sa] - qb[j * sb]; d2 += d * d; }
+  if (spin) for (int j = 0; j < n; j++) { const Real d = joint_diff(spin, j, qa[j * sa], qb[j * sb]); d2 += d * d; }
+  else for (int j = 0; j < n; j++) { const Real d = qa[j * sa] - qb[j * sb]; d2 += d * d; }
   const Real r = sqrt_(d2) / eps, cr = ceil_(r);
   int nd = (int)cr;
   if (FLAG && (cr - r < fl_nd || r - (cr - Real(1)) < fl_nd)) nd |= kNdFlag;
@@ -559,8 +563,8 @@ GRR_DEV bool pair_arm(int ndivs, PairLane<Real> &P, LaneIK<Real, M> &L) {
 
 // Begin pair: distance -> Ndivs, arm the seed of k=1.  Returns false if the pair is decided already.
 template <typename Real, int M, bool FLAG = false, typename ChainT>
-GRR_DEV bool pair_begin(const ChainT &c, Real eps, PairLane<Real> &P, LaneIK<Real, M> &L) {
-  return pair_arm<Real, M>(pair_ndivs<Real, FLAG>(c.n, eps, P.qa, P.sa, P.qb, P.sb, c.fl_nd), P, L);
+GRR_DEV bool pair_begin(const ChainT &c, Real eps, PairLane<Real> &P, LaneIK<Real, M> &L, unsigned spin = 0u) {
+  return pair_arm<Real, M>(pair_ndivs<Real, FLAG>(c.n, spin, eps, P.qa, P.sa, P.qb, P.sb, c.fl_nd), P, L);
 }
 
 // One interpolated solve finished with IK_OK; s2 = |q_k - q_{k-1}|^2 was accumulated by the final
@@ -597,7 +601,7 @@ constexpr int kNeedClose = -2;     // pair_advance<.., COOP>: the closing leaf i
 // compute it, one joint per lane.
 template <bool FLAG = false, bool COOP = false, typename Real, int M, int MC, typename ChainT>
 GRR_DEV int pair_advance(const ChainT &c, LaneMem<Real, MC> &mem, Real s2, Real thr2, PairLane<Real> &P,
-                         LaneIK<Real, M> &L, bool skip_first_leaf = false) {
+                         LaneIK<Real, M> &L, bool skip_first_leaf = false, unsigned spin = 0u) {
   Real thr = 0;
   if (FLAG) {
     // margin of the leaf tests: round-off plus the ambiguity radii of the two solutions, the latter capped at half the
@@ -613,7 +617,8 @@ GRR_DEV int pair_advance(const ChainT &c, LaneMem<Real, MC> &mem, Real s2, Real 
     if (COOP) return kNeedClose;
     const int n = c.n, T = mem.T;
     Real e2 = 0;
-    for (int j = 0; j < n; j++) { const Real e = P.qb[j * P.sb] - L.res[j * T]; e2 += e * e; }
+    if (spin) for (int j = 0; j < n; j++) { const Real e = joint_diff(spin, j, P.qb[j * P.sb], L.res[j * T]); e2 += e * e; }
+    else for (int j = 0; j < n; j++) { const Real e = P.qb[j * P.sb] - L.res[j * T]; e2 += e * e; }
     return pair_close<FLAG>(c, e2, thr2, P, L);
   }
   { const int t = mem.o_prev; mem.o_prev = mem.o_xcur; mem.o_xcur = t; }   // IK_OK leaves the solution in xcur
@@ -659,7 +664,7 @@ __device__ __forceinline__ void warp_tie_service(const ChainT &c, LaneIK<Real, M
 // |qb - q_Ndivs|^2, one joint per lane (n <= 32), reading the requester's staged endpoint config and its solution in
 // shared memory.  Returns this lane's e2 (meaningful on requesting lanes).  All 32 lanes must call.
 template <typename Real, int M>
-__device__ __forceinline__ Real warp_close_service(int n, int T, const PairLane<Real> &P, const LaneIK<Real, M> &L, bool request) {
+__device__ __forceinline__ Real warp_close_service(int n, unsigned spin, int T, const PairLane<Real> &P, const LaneIK<Real, M> &L, bool request) {
   Real mine = 0;
 #ifdef __CUDA_ARCH__
   unsigned rq = __ballot_sync(0xffffffffu, request);
@@ -671,7 +676,7 @@ __device__ __forceinline__ Real warp_close_service(int n, int T, const PairLane<
     const Real *rs = reinterpret_cast<const Real *>(__shfl_sync(0xffffffffu, (unsigned long long)L.res, src));
     const int sb = __shfl_sync(0xffffffffu, P.sb, src);
     Real e = 0;
-    if (lane < n) { e = qb[lane * sb] - rs[lane * T]; e *= e; }
+    if (lane < n) { e = joint_diff(spin, lane, qb[lane * sb], rs[lane * T]); e *= e; }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) e += __shfl_xor_sync(0xffffffffu, e, o);
     if (lane == src) mine = e;
@@ -693,12 +698,13 @@ GRR_DEV void flag_push(unsigned long long *flist, unsigned long long fcap, long 
 }
 
 // explicit pairs, SoA qa[n][P], qb[n][P]  (validEdge, graph.py:1051-1053), work-fetching lanes
-template <typename Real, int M, bool PL>
+template <typename Real, int M, bool PL, bool SPIN = false>
 __global__ void __launch_bounds__(256)
 k_valid_edge_batch(const __grid_constant__ ChainDev<Real, kMaxJ> c, long long total, const Real *__restrict__ qa,
                    const Real *__restrict__ qb, const Real *__restrict__ wa, const Real *__restrict__ wb, Real epsilon,
                    uint8_t *__restrict__ valid, int32_t *__restrict__ info, unsigned long long *work,
                    unsigned long long *counters) {
+  const unsigned kspin = SPIN ? c.spin_mask : 0u;      // compile-time 0 in the kernels of chains without spin joints
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int n = c.n, dw = (c.mode == 2 ? 6 : 3);
   LaneMem<Real, col_rows(M, PL)> mem;
@@ -728,7 +734,7 @@ k_valid_edge_batch(const __grid_constant__ ChainDev<Real, kMaxJ> c, long long to
         for (int k = 0; k < dw; k++) { a6[k] = wa[t * dw + k]; b6[k] = wb[t * dw + k]; }
         winterp_begin<Real, M, kMaxJ>(c, a6, b6, W);
         P.qa = qa + t; P.qb = qb + t; P.sa = (int)total; P.sb = (int)total;
-        if (!pair_begin<Real, M>(c, eps, P, L)) verdict = 1;
+        if (!pair_begin<Real, M>(c, eps, P, L, kspin)) verdict = 1;
         else winterp_at<Real, M>(W, P.u_at(1), tg);
       }
     }
@@ -738,14 +744,14 @@ k_valid_edge_batch(const __grid_constant__ ChainDev<Real, kMaxJ> c, long long to
       PassOut<Real, M> o;
       const bool first = running && P.k == 1;
       if constexpr (PL) lane_pass_planar<Real, true>(c, tg, L, mem, first ? P.qa : mem.prev(), first ? P.sa : mem.T, o);
-      else lane_pass<Real, M, true>(c, tg, L, mem, first ? P.qa : mem.prev(), first ? P.sa : mem.T, o);
+      else lane_pass<Real, M, true, SPIN>(c, tg, L, mem, first ? P.qa : mem.prev(), first ? P.sa : mem.T, o);
       const int st = lane_step<Real, M, PL>(c, L, mem, o, running);
       if (running && st != IK_RUNNING) {
         P.solves++; P.iters += L.it;
         cnt.solves++; cnt.iters += L.it; cnt.evals += L.evals; cnt.ok += (st == IK_OK);
         if (st != IK_OK) { verdict = 0; fail = 1; }               // graph.py:964-966
         else {
-          verdict = pair_advance(c, mem, o.s2, thr2, P, L);
+          verdict = pair_advance(c, mem, o.s2, thr2, P, L, false, kspin);
           if (verdict == 0) fail = 2;
           if (verdict < 0) winterp_at<Real, M>(W, P.u_at(P.k), tg);
         }
@@ -769,13 +775,14 @@ k_valid_edge_batch(const __grid_constant__ ChainDev<Real, kMaxJ> c, long long to
 // shared-memory counter and run their pairs as independent lane machines; verdict bits are OR-ed into
 // a shared-memory Nq x Nq bitmask that is written out once.
 // ------------------------------------------------------------------------------------------
-template <typename Real, int M, bool PL, bool FLAG>
+template <typename Real, int M, bool PL, bool FLAG, bool SPIN = false>
 __global__ void __launch_bounds__(sizeof(Real) == 4 ? (M == 3 ? 512 : 384) : 256)
 k_edges_build(const __grid_constant__ ChainDev<Real, kMaxJ> c, const int32_t *__restrict__ wedges,
               const Real *__restrict__ params, const Real *__restrict__ q_kept, const int32_t *__restrict__ count,
               const int32_t *__restrict__ old_count, int Nq, int Nqp, Real epsilon, uint32_t *mask,
               uint32_t *__restrict__ edge_stats, unsigned long long *counters, unsigned long long *flist,
               unsigned long long fcap) {
+  const unsigned kspin = SPIN ? c.spin_mask : 0u;      // compile-time 0 in the kernels of chains without spin joints
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int n = c.n, dw = (c.mode == 2 ? 6 : 3);
   const int Wd = (Nq + 31) >> 5;
@@ -832,7 +839,7 @@ k_edges_build(const __grid_constant__ ChainDev<Real, kMaxJ> c, const int32_t *__
     {
       const unsigned ts = (unsigned)(((unsigned long long)threadIdx.x * total) / blockDim.x);
       const int ta = (int)(ts / (unsigned)cb), tb = (int)(ts - (unsigned)ta * (unsigned)cb);
-      const int nd = pair_ndivs<Real>(n, eps, sa + ta, Nqp, sb + tb, Nqp);
+      const int nd = pair_ndivs<Real>(n, kspin, eps, sa + ta, Nqp, sb + tb, Nqp);
       const unsigned sum = __reduce_add_sync(0xffffffffu, (unsigned)max(nd, 0));
       if ((threadIdx.x & 31) == 0) { atomicAdd(&s_ndsum, sum); atomicAdd(&s_ndcnt, 32u); }
     }
@@ -869,7 +876,7 @@ k_edges_build(const __grid_constant__ ChainDev<Real, kMaxJ> c, const int32_t *__
             if (iw == jw && ta <= tb) ok = false;                 // self-motion pairs: validEdge(q_i, q_j, x, x), i > j (solver.py:648-653)
           }
           if (ok) {
-            nd = pair_ndivs<Real, FLAG>(n, eps, sa + ta, Nqp, sb + tb, Nqp, c.fl_nd);
+            nd = pair_ndivs<Real, FLAG>(n, kspin, eps, sa + ta, Nqp, sb + tb, Nqp, c.fl_nd);
             if ((nd & ~kNdFlag) <= 0) {                           // dist == 0 -> valid, no solves
               if (!second) {
                 atomicOr(&smask[ta * Wd + (tb >> 5)], 1u << (tb & 31)); cnt.pairs++; cnt.valid++;
@@ -902,7 +909,7 @@ k_edges_build(const __grid_constant__ ChainDev<Real, kMaxJ> c, const int32_t *__
         PassOut<Real, M> o;
         const bool first = running && P.k == 1;
         if constexpr (PL) lane_pass_planar<Real, true>(c, tg, L, mem, first ? P.qa : mem.prev(), first ? P.sa : mem.T, o);
-        else lane_pass<Real, M, true>(c, tg, L, mem, first ? P.qa : mem.prev(), first ? P.sa : mem.T, o);
+        else lane_pass<Real, M, true, SPIN>(c, tg, L, mem, first ? P.qa : mem.prev(), first ? P.sa : mem.T, o);
         const int st = lane_step<Real, M, PL, FLAG>(c, L, mem, o, running);
         if constexpr (FLAG) warp_tie_service<Real, M, PL>(c, L, mem, running);
         constexpr bool COOP = sizeof(Real) == 4;                // (double precision keeps the sequential sum of the oracle)
@@ -911,12 +918,12 @@ k_edges_build(const __grid_constant__ ChainDev<Real, kMaxJ> c, const int32_t *__
           if (FLAG) pair_note_solve(P, L, st);
           if (st != IK_OK) verdict = 0;                         // graph.py:964-966
           else {
-            verdict = pair_advance<FLAG, COOP>(c, mem, o.s2, thr2, P, L);
+            verdict = pair_advance<FLAG, COOP>(c, mem, o.s2, thr2, P, L, false, kspin);
             if (verdict == -1) winterp_at<Real, M>(W, P.u_at(P.k), tg);
           }
         }
         if constexpr (COOP) {
-          const Real e2 = warp_close_service<Real, M>(n, mem.T, P, L, running && verdict == kNeedClose);
+          const Real e2 = warp_close_service<Real, M>(n, kspin, mem.T, P, L, running && verdict == kNeedClose);
           if (running && verdict == kNeedClose) verdict = pair_close<FLAG>(c, e2, thr2, P, L);
         }
       }
@@ -1015,7 +1022,7 @@ k_edges_build2(const __grid_constant__ ChainDev<float, kMaxJ> c, const int32_t *
     {
       const unsigned ts = (unsigned)(((unsigned long long)threadIdx.x * total) / blockDim.x);
       const int ta = (int)(ts / (unsigned)cb), tb = (int)(ts - (unsigned)ta * (unsigned)cb);
-      const int nd = pair_ndivs<Real>(n, eps, sa + ta, Nqp, sb + tb, Nqp);
+      const int nd = pair_ndivs<Real>(n, 0u, eps, sa + ta, Nqp, sb + tb, Nqp);
       const unsigned sum = __reduce_add_sync(0xffffffffu, (unsigned)max(nd, 0));
       if ((threadIdx.x & 31) == 0) { atomicAdd(&s_ndsum, sum); atomicAdd(&s_ndcnt, 32u); }
     }
@@ -1049,7 +1056,7 @@ k_edges_build2(const __grid_constant__ ChainDev<float, kMaxJ> c, const int32_t *
               if (iw == jw && ta <= tb) ok = false;                 // self-motion pairs i > j (solver.py:648-653)
             }
             if (ok) {
-              nd = pair_ndivs<Real, FLAG>(n, eps, sa + ta, Nqp, sb + tb, Nqp, c.fl_nd);
+              nd = pair_ndivs<Real, FLAG>(n, 0u, eps, sa + ta, Nqp, sb + tb, Nqp, c.fl_nd);
               if ((nd & ~kNdFlag) <= 0) {
                 if (!second) {
                   atomicOr(&smask[ta * Wd + (tb >> 5)], 1u << (tb & 31)); cnt.pairs++; cnt.valid++;
@@ -1202,7 +1209,7 @@ static __global__ void k_edges_bits(long long E, int words, const uint32_t *__re
 // double precision: 3 CTAs per SM for 3 residual rows (168 registers, 36 bytes of spills: 12 instead of 8 warps per SM hide
 // the FP64 latencies -- the kernel sat at 52 % issue utilisation with `stalled_wait` 1.6 per issue), 2 for 6 rows
 // (capping that build at 168 registers spills 1.6 KB per thread)
-template <typename Real, int M, bool PL, bool FLAG>
+template <typename Real, int M, bool PL, bool FLAG, bool SPIN = false>
 #ifndef GRR_F64M3_BLOCKS
 #define GRR_F64M3_BLOCKS 3
 #endif
@@ -1215,6 +1222,7 @@ k_edges_flat(const __grid_constant__ ChainDev<Real, kMaxJ> c, long long E, const
              const int32_t *__restrict__ old_count, int Nq, int Nqp, Real epsilon, uint32_t *mask,
              const unsigned long long *__restrict__ offs, unsigned long long *work, unsigned long long *counters,
              unsigned long long *flist, unsigned long long fcap) {
+  const unsigned kspin = SPIN ? c.spin_mask : 0u;      // compile-time 0 in the kernels of chains without spin joints
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int n = c.n, dw = (c.mode == 2 ? 6 : 3);
   const int Wd = (Nq + 31) >> 5;
@@ -1270,7 +1278,7 @@ k_edges_flat(const __grid_constant__ ChainDev<Real, kMaxJ> c, long long E, const
           if (iw == jw && ta <= tb) ok = false;                                       // self-motion pairs i > j (solver.py:648-653)
           if (ok) {
             // all lanes measure their pair together (a lane doing this alone ran with 1.5 of 32 lanes active)
-            nd = pair_ndivs<Real, FLAG>(n, eps, q_kept + (long long)iw * n * Nqp + ta, Nqp, q_kept + (long long)jw * n * Nqp + tb, Nqp, c.fl_nd);
+            nd = pair_ndivs<Real, FLAG>(n, kspin, eps, q_kept + (long long)iw * n * Nqp + ta, Nqp, q_kept + (long long)jw * n * Nqp + tb, Nqp, c.fl_nd);
             if ((nd & ~kNdFlag) <= 0) {                           // dist == 0 -> valid, no solves
               atomicOr(&mask[(e * Nq + ta) * Wd + (tb >> 5)], 1u << (tb & 31));
               cnt.pairs++; cnt.valid++;
@@ -1308,7 +1316,7 @@ k_edges_flat(const __grid_constant__ ChainDev<Real, kMaxJ> c, long long E, const
       PassOut<Real, M> o;
       const bool first = running && P.k == 1;
       if constexpr (PL) lane_pass_planar<Real, true>(c, tg, L, mem, first ? P.qa : mem.prev(), first ? P.sa : mem.T, o);
-      else lane_pass<Real, M, true>(c, tg, L, mem, first ? P.qa : mem.prev(), first ? P.sa : mem.T, o);
+      else lane_pass<Real, M, true, SPIN>(c, tg, L, mem, first ? P.qa : mem.prev(), first ? P.sa : mem.T, o);
       const int st = lane_step<Real, M, PL, FLAG>(c, L, mem, o, running);
       if constexpr (FLAG) warp_tie_service<Real, M, PL>(c, L, mem, running);
       if (running && st != IK_RUNNING) {
@@ -1316,7 +1324,7 @@ k_edges_flat(const __grid_constant__ ChainDev<Real, kMaxJ> c, long long E, const
         if (FLAG) pair_note_solve(P, L, st);
         if (st != IK_OK) verdict = 0;                             // graph.py:964-966
         else {
-          verdict = pair_advance<FLAG>(c, mem, o.s2, thr2, P, L);
+          verdict = pair_advance<FLAG>(c, mem, o.s2, thr2, P, L, false, kspin);
           if (verdict < 0) winterp_at<Real, M>(W, P.u_at(P.k), tg);
         }
       }
@@ -1341,12 +1349,13 @@ k_edges_flat(const __grid_constant__ ChainDev<Real, kMaxJ> c, long long E, const
 // the leaf before it was settled by the first pass) and runs the pair to its end.  k0 = 0 (Ndivs rounding): whole pair.
 // Persistent lanes pull list entries from a global counter.
 // ------------------------------------------------------------------------------------------
-template <typename Real, int M, bool PL>
+template <typename Real, int M, bool PL, bool SPIN = false>
 __global__ void __launch_bounds__(256)
 k_edges_recheck(const __grid_constant__ ChainDev<Real, kMaxJ> c, const int32_t *__restrict__ wedges,
                 const Real *__restrict__ params, const Real *__restrict__ q_kept, int Nq, int Nqp, Real epsilon, uint32_t *mask,
                 uint32_t *edge_stats, const unsigned long long *__restrict__ flist, unsigned long long fcap,
                 unsigned long long *work, unsigned long long *counters, int listed_mode) {
+  const unsigned kspin = SPIN ? c.spin_mask : 0u;      // compile-time 0 in the kernels of chains without spin joints
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int n = c.n, dw = (c.mode == 2 ? 6 : 3);
   const int Wd = (Nq + 31) >> 5;
@@ -1387,7 +1396,7 @@ k_edges_recheck(const __grid_constant__ ChainDev<Real, kMaxJ> c, const int32_t *
         winterp_begin<Real, M, kMaxJ>(c, a6, b6, W);
         P.qa = q_kept + (long long)iw * n * Nqp + a; P.qb = q_kept + (long long)jw * n * Nqp + b; P.sa = Nqp; P.sb = Nqp;
         flagged++;
-        if (!pair_begin<Real, M>(c, eps, P, L)) verdict = 1;
+        if (!pair_begin<Real, M>(c, eps, P, L, kspin)) verdict = 1;
         else {
           kstart = (k0 >= 2 && k0 <= P.ndivs) ? k0 - 1 : 1;
           P.k = kstart;
@@ -1403,13 +1412,13 @@ k_edges_recheck(const __grid_constant__ ChainDev<Real, kMaxJ> c, const int32_t *
       PassOut<Real, M> o;
       const bool first = running && P.k == 1;
       if constexpr (PL) lane_pass_planar<Real, true>(c, tg, L, mem, first ? P.qa : mem.prev(), first ? P.sa : mem.T, o);
-      else lane_pass<Real, M, true>(c, tg, L, mem, first ? P.qa : mem.prev(), first ? P.sa : mem.T, o);
+      else lane_pass<Real, M, true, SPIN>(c, tg, L, mem, first ? P.qa : mem.prev(), first ? P.sa : mem.T, o);
       const int st = lane_step<Real, M, PL>(c, L, mem, o, running);
       if (running && st != IK_RUNNING) {
         cnt.solves++; cnt.iters += L.it; cnt.evals += L.evals; cnt.ok += (st == IK_OK);
         if (st != IK_OK) verdict = 0;
         else {
-          verdict = pair_advance(c, mem, o.s2, thr2, P, L, P.k == kstart && kstart > 1);
+          verdict = pair_advance(c, mem, o.s2, thr2, P, L, P.k == kstart && kstart > 1, kspin);
           if (verdict < 0) winterp_at<Real, M>(W, P.u_at(P.k), tg);
         }
       }
@@ -1495,6 +1504,8 @@ struct Impl {
     return kHasPlanar && !off && is_planar_y(h);
   }
   static int mc(const HostChain &h) { return planar(h) ? 2 : M; }
+  // chains with 'spin' joints run the SPIN instantiations of the kernels (never planar: is_planar_y_chain)
+  static bool spin(const HostChain &h) { return spin_mask_of(h) != 0; }
 
   // persistent lanes: threads per CTA and CTAs so that every SM holds as many lanes as shared memory allows
   static void lane_geometry(const HostChain &h, size_t fixed_bytes, int max_threads, int &threads, int &ctas_per_sm) {
@@ -1534,8 +1545,10 @@ struct Impl {
     int rc;
     if constexpr (kHasPlanar) {
       if (planar(h)) rc = (mode == 0) ? launch(k_ik_instances<Real, M, 0, true>) : launch(k_ik_instances<Real, M, 1, true>);
+      else if (spin(h)) rc = (mode == 0) ? launch(k_ik_instances<Real, M, 0, false, true>) : launch(k_ik_instances<Real, M, 1, false, true>);
       else rc = (mode == 0) ? launch(k_ik_instances<Real, M, 0, false>) : launch(k_ik_instances<Real, M, 1, false>);
-    } else rc = (mode == 0) ? launch(k_ik_instances<Real, M, 0, false>) : launch(k_ik_instances<Real, M, 1, false>);
+    } else if (spin(h)) rc = (mode == 0) ? launch(k_ik_instances<Real, M, 0, false, true>) : launch(k_ik_instances<Real, M, 1, false, true>);
+    else rc = (mode == 0) ? launch(k_ik_instances<Real, M, 0, false>) : launch(k_ik_instances<Real, M, 1, false>);
     if (rc) return rc;
     return check_launch("k_ik_instances");
   }
@@ -1572,7 +1585,8 @@ struct Impl {
       return 0;
     };
     int rc;
-    if constexpr (kHasPlanar) rc = planar(h) ? launch(k_ik_level<Real, M, true>) : launch(k_ik_level<Real, M, false>);
+    if (spin(h)) rc = launch(k_ik_level<Real, M, false, true>);
+    else if constexpr (kHasPlanar) rc = planar(h) ? launch(k_ik_level<Real, M, true>) : launch(k_ik_level<Real, M, false>);
     else rc = launch(k_ik_level<Real, M, false>);
     if (rc) return rc;
     return check_launch("k_ik_level");
@@ -1613,8 +1627,10 @@ struct Impl {
     int rc;
     if constexpr (kHasPlanar) {
       if (planar(h)) rc = biased ? launch(k_sweep_dataflow<Real, M, true, true>) : launch(k_sweep_dataflow<Real, M, true, false>);
+      else if (spin(h)) rc = biased ? launch(k_sweep_dataflow<Real, M, false, true, true>) : launch(k_sweep_dataflow<Real, M, false, false, true>);
       else rc = biased ? launch(k_sweep_dataflow<Real, M, false, true>) : launch(k_sweep_dataflow<Real, M, false, false>);
-    } else rc = biased ? launch(k_sweep_dataflow<Real, M, false, true>) : launch(k_sweep_dataflow<Real, M, false, false>);
+    } else if (spin(h)) rc = biased ? launch(k_sweep_dataflow<Real, M, false, true, true>) : launch(k_sweep_dataflow<Real, M, false, false, true>);
+    else rc = biased ? launch(k_sweep_dataflow<Real, M, false, true>) : launch(k_sweep_dataflow<Real, M, false, false>);
     if (rc) return rc;
     return check_launch("k_sweep_dataflow");
   }
@@ -1643,7 +1659,8 @@ struct Impl {
       return 0;
     };
     int rc;
-    if constexpr (kHasPlanar) rc = planar(h) ? launch(k_valid_edge_batch<Real, M, true>) : launch(k_valid_edge_batch<Real, M, false>);
+    if (spin(h)) rc = launch(k_valid_edge_batch<Real, M, false, true>);
+    else if constexpr (kHasPlanar) rc = planar(h) ? launch(k_valid_edge_batch<Real, M, true>) : launch(k_valid_edge_batch<Real, M, false>);
     else rc = launch(k_valid_edge_batch<Real, M, false>);
     if (rc) return rc;
     return check_launch("k_valid_edge_batch");
@@ -1719,6 +1736,10 @@ struct Impl {
         return 0;
       };
       const bool pl = planar(h);
+      if (spin(h)) {
+        if (flist) { set_error("edges_build: the single-precision pass with near-tie flags is not built for chains with spin joints"); return -1; }
+        rc = launch(k_edges_build<Real, M, false, false, true>);
+      } else
       if constexpr (kHasPlanar && sizeof(Real) == 4) {
         // two lane machines per thread on the packed FP32 instructions (k_edges_build2): planar small-angle chains
         static const bool no_dual = getenv("GRR_DUAL") == nullptr;      // opt-in until validated on the GPU
@@ -1782,7 +1803,8 @@ struct Impl {
       return 0;
     };
     int rc;
-    if constexpr (kHasPlanar) rc = planar(h) ? launch(k_edges_recheck<Real, M, true>) : launch(k_edges_recheck<Real, M, false>);
+    if (spin(h)) rc = launch(k_edges_recheck<Real, M, false, true>);
+    else if constexpr (kHasPlanar) rc = planar(h) ? launch(k_edges_recheck<Real, M, true>) : launch(k_edges_recheck<Real, M, false>);
     else rc = launch(k_edges_recheck<Real, M, false>);
     if (rc) return rc;
     return check_launch("k_edges_recheck");
@@ -1821,6 +1843,10 @@ struct Impl {
     };
     int rc;
     const bool pl = planar(h);
+    if (spin(h)) {
+      if (flist) { set_error("edges_build: the single-precision pass with near-tie flags is not built for chains with spin joints"); return -1; }
+      rc = launch(k_edges_flat<Real, M, false, false, true>);
+    } else
     if constexpr (kHasPlanar && sizeof(Real) == 4) {
       if (pl) rc = flist ? launch(k_edges_flat<Real, M, true, true>) : launch(k_edges_flat<Real, M, true, false>);
       else rc = flist ? launch(k_edges_flat<Real, M, false, true>) : launch(k_edges_flat<Real, M, false, false>);

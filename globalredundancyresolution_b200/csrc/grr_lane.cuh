@@ -356,13 +356,16 @@ GRR_DEV void lane_pass_planar(const ChainT &c, const Target<Real, 3> &tg, const 
   else lane_pass_planar_<Real, WITH_REF, false, false>(c, tg, L, mem, xref, sref, o);
 }
 
-template <typename Real, int M, bool WITH_REF, typename ChainT>
-GRR_DEV void lane_pass(const ChainT &c, const Target<Real, M> &tg, const LaneIK<Real, M> &L,
-                                          const LaneMem<Real, M> &mem, const Real *xref, int sref, PassOut<Real, M> &o) {
+// The joint loop of the pass.  SPIN: the chain has 'spin' joints (c.spin_mask != 0) -- a compile-time property of the
+// kernel (the launchers pick the SPIN instantiations for such chains), so that the kernels every shipped problem runs are
+// the code they were before spin joints existed (a run-time test of jc.spin in the common loop, or both loops in one
+// kernel, cost the double-precision kernels of the 6-/7-joint arms 4-8 %).
+template <typename Real, int M, bool WITH_REF, bool SPIN, typename ChainT>
+GRR_DEV void lane_pass_chain_(const ChainT &c, const LaneIK<Real, M> &L, const LaneMem<Real, M> &mem, const Real *xref, int sref,
+                              PassOut<Real, M> &o, Real (&v)[3], Real (&G)[9]) {
   const int n = c.n;
   const XSrc<Real> &src = L.src;
-  Real v[3] = {c.ee[0], c.ee[1], c.ee[2]};
-  Real G[9];
+  v[0] = c.ee[0]; v[1] = c.ee[1]; v[2] = c.ee[2];
 #pragma unroll
   for (int k = 0; k < 9; k++) G[k] = c.Rtail[k];
 #pragma unroll
@@ -409,10 +412,23 @@ GRR_DEV void lane_pass(const ChainT &c, const Target<Real, M> &tg, const LaneIK<
     const Real rinv = sizeof(Real) == 4 ? rcp_ge1_(den) : Real(0);
     rtest.add(abs_(dir), rinv, den);
     rtestx.add(abs_(av - xo), rinv, den);
-    const Real xj = min_(max_(fma_(t, dir, av), jc.bmin), jc.bmax);
+    Real xj = min_(max_(fma_(t, dir, av), jc.bmin), jc.bmax);
+    Real dref = WITH_REF ? xj - rv : Real(0);
+    if constexpr (SPIN) {
+      if (jc.spin) {
+        // 'spin' joint (warp-uniform branch): an interpolated seed lies on the shorter arc a -> b and is normalised to
+        // [0, 2 pi) (robot.interpolate); the distance to the previous solution is the wrapped difference (robot.distance);
+        // the line search itself runs on the unbounded angle
+        if (src.lerp) {
+          const Real an = angle_normalize(av);
+          xj = angle_normalize(fma_(t, angle_diff(bv, an), an));
+        }
+        if (WITH_REF) dref = angle_diff(xj, rv);
+      }
+    }
     *px = xj; px -= T;
     xn2 += xj * xj;
-    if (WITH_REF) { const Real d = xj - rv; s2 += d * d; }
+    if (WITH_REF) s2 += dref * dref;
     Real s, co;
     sincos_joint(xj, &s, &co);
     Real col[M];
@@ -453,6 +469,13 @@ GRR_DEV void lane_pass(const ChainT &c, const Target<Real, M> &tg, const LaneIK<
   }
   o.xn2 = xn2; o.s2 = s2;
   o.pn2 = pn2; o.test = rtest.get(); o.testx = rtestx.get();
+}
+
+template <typename Real, int M, bool WITH_REF, bool SPIN = false, typename ChainT>
+GRR_DEV void lane_pass(const ChainT &c, const Target<Real, M> &tg, const LaneIK<Real, M> &L,
+                                          const LaneMem<Real, M> &mem, const Real *xref, int sref, PassOut<Real, M> &o) {
+  Real v[3], G[9];
+  lane_pass_chain_<Real, M, WITH_REF, SPIN>(c, L, mem, xref, sref, o, v, G);
   o.Fw[0] = v[0] - tg.x[0]; o.Fw[1] = v[1] - tg.x[1]; o.Fw[2] = v[2] - tg.x[2];
   Real f = o.Fw[0] * o.Fw[0] + o.Fw[1] * o.Fw[1] + o.Fw[2] * o.Fw[2];
   m3_Tvec(G, o.Fw, o.FL);

@@ -158,7 +158,8 @@ class RedundancyResolutionGraph:
             assert all(v >= 0 for v in self.activeDofs), "Invalid active DOF specified in JSON file"
         for l in (self.activeDofs if self.activeDofs is not None else range(robot.numLinks())):
             if robot.getJointType(l) == "spin":
-                raise NotImplementedError("spin joints are not supported on the device path")
+                self.spinJoints = True                                            # graph.py:556-561
+                break
         if orientation == "fixed":
             if eeorientation is None:
                 eeorientation = link.getTransform()[0]                            # graph.py:563-565

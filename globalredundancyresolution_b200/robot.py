@@ -17,6 +17,18 @@ import shlex
 import numpy as np
 
 
+def angle_normalize(a):
+    """[recalled] KrisLibrary AngleNormalize: into [0, 2 pi) (C fmod: the sign follows the dividend)."""
+    an = np.fmod(a, 2.0 * math.pi)
+    return np.where(an < 0, an + 2.0 * math.pi, an)
+
+
+def angle_diff(a, b):
+    """[recalled] KrisLibrary AngleDiff(a, b): a - b wrapped into (-pi, pi]."""
+    d = angle_normalize(angle_normalize(a) - angle_normalize(b))
+    return np.where(d > math.pi, d - 2.0 * math.pi, d)
+
+
 def _rot(axis, angle):
     a = np.asarray(axis, dtype=np.float64)
     a = a / np.linalg.norm(a)
@@ -91,13 +103,27 @@ class RobotChain:
     def getJointType(self, i):
         return self.joint_kind[i]
 
+    def _spin(self):
+        return np.asarray([k == "spin" for k in self.joint_kind], dtype=bool)
+
     def distance(self, a, b):
-        """robot.distance for 'normal' joints: L2 over all DOFs."""
-        return float(np.linalg.norm(np.asarray(a, dtype=np.float64) - np.asarray(b, dtype=np.float64)))
+        """robot.distance: L2 over all DOFs, with the wrapped angular difference for 'spin' joints."""
+        d = np.asarray(a, dtype=np.float64) - np.asarray(b, dtype=np.float64)
+        sp = self._spin()
+        if sp.any():
+            d[sp] = angle_diff(np.asarray(a, dtype=np.float64)[sp], np.asarray(b, dtype=np.float64)[sp])
+        return float(np.linalg.norm(d))
 
     def interpolate(self, a, b, u):
+        """robot.interpolate: per-DOF lerp; 'spin' joints move along the shorter arc and come out in [0, 2 pi)."""
         a = np.asarray(a, dtype=np.float64)
-        return [float(v) for v in a + u * (np.asarray(b, dtype=np.float64) - a)]
+        b = np.asarray(b, dtype=np.float64)
+        x = a + u * (b - a)
+        sp = self._spin()
+        if sp.any():
+            an = angle_normalize(a[sp])
+            x[sp] = angle_normalize(an + u * angle_diff(b[sp], an))
+        return [float(v) for v in x]
 
     # ---- kinematics (host, float64; used for setup and by the tests' closed-form checks) ----------
     def path_to(self, link):
@@ -159,6 +185,7 @@ class RobotChain:
             "Rp": np.asarray(Rp).reshape(-1, 9), "tp": np.asarray(tp).reshape(-1, 3),
             "axis": np.asarray(ax).reshape(-1, 3), "qmin": np.asarray(lo), "qmax": np.asarray(hi),
             "ee_local": ee, "R_tail": CR.reshape(9).copy(), "active": idx,
+            "spin": np.asarray([1 if self.joint_kind[i] == "spin" else 0 for i in idx], dtype=np.int32),
         }
 
     # ---- .rob files -------------------------------------------------------------------------------

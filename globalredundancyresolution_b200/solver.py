@@ -753,7 +753,7 @@ class RedundancyResolver(VisibilityMixin):
         both = (cnt[e[:, 0]] > 0) & (cnt[e[:, 1]] > 0)
         per_edge = self._bits_per_edge().cpu().numpy() if (self._dev is not None and self.Nq > 0) else np.zeros(self.E, dtype=np.int64)
         resolved = [(i, j) for (i, j) in self._edges_host if cnt[i] > 0 and cnt[j] > 0 and res.isResolvedEdge(i, j)]
-        sumd = sum(float(np.linalg.norm(np.asarray(res.Gw.node[i]["config"]) - np.asarray(res.Gw.node[j]["config"]))) for i, j in resolved)
+        sumd = sum(res.robot.distance(res.Gw.node[i]["config"], res.Gw.node[j]["config"]) for i, j in resolved)
         sumw = sum(res.workspaceDistance(res.Gw.node[i]["params"], res.Gw.node[j]["params"]) for i, j in resolved)
         out = {"workspace_nodes": self.Nw, "workspace_edges": self.E, "configs": int(cnt.sum()), "cspace_edges": int(per_edge.sum()),
                "nodes_with_configs": int((cnt > 0).sum()), "potential_edges": int(both.sum()),
@@ -1212,6 +1212,8 @@ class RedundancyResolver(VisibilityMixin):
         nodes of one level of the lower-neighbour DAG (the schedule of the seeded sampling sweep) are processed
         together with the same result: one batched IK launch and one batched validEdge launch per try and level.
         Ends with fromResolutionToGraph() like the reference.  Returns the mean path length per resolved edge."""
+        if self.resolution.chain.spin.any():
+            raise NotImplementedError("optimize() with spin joints (robot_average on wrapped angles) is not built")
         res = self.resolution
         lv = self._sweep_levels()
         level = lv["host"][3]

@@ -57,6 +57,8 @@ class VisibilityMixin:
     # ---- self-motion manifolds (solver.py:623-687) ------------------------------------------------------------------------
     def constructSelfMotionManifolds(self, k=None):
         """solver.py:672-687 for every workspace node.  Returns the device time in seconds."""
+        if self.resolution.chain.spin.any():
+            raise NotImplementedError("the visibility-graph variant with spin joints is not built (its distance sorts take plain differences)")
         torch = self.resolution._torch()
         res = self.resolution
         d = self._dev
@@ -101,6 +103,8 @@ class VisibilityMixin:
     def constructSelfMotionManifold(self, iw, k=None):
         """solver.py:623-669 for one workspace node; returns its number of components.  The manifolds of all nodes are
         independent, so the batch call does the work and this one reads its result (rebuilding when k changed)."""
+        if self.resolution.chain.spin.any():
+            raise NotImplementedError("the visibility-graph variant with spin joints is not built (its distance sorts take plain differences)")
         v = getattr(self, "_vis", None)
         if v is None or v["k"] != k:
             self.constructSelfMotionManifolds(k)
@@ -198,6 +202,8 @@ class VisibilityMixin:
     def _connect_visibility(self, edge_ids=None, max_tests=10, swap=0, mode=0):
         """testAndConnectQccs (mode 0) / parallelEdgeConnection (mode 1) on every workspace edge (or the listed ones); sets
         the bits of the connecting pairs in the roadmap's edge masks.  Returns nconn (device int32 per edge)."""
+        if self.resolution.chain.spin.any():
+            raise NotImplementedError("the visibility-graph variant with spin joints is not built (its distance sorts take plain differences)")
         torch = self.resolution._torch()
         d = self._dev
         v = self._vis_state()

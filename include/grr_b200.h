@@ -86,6 +86,11 @@ int grr_chain_destroy(grr_handle_t h);
 /* replaces IKTask.__init__ orientation selection (graph.py:59-80); R_goal9 may be NULL */
 int grr_task_set(grr_handle_t h, int mode, const double *R_goal9);
 int grr_chain_num_joints(grr_handle_t h);
+/* 'spin' joints (continuous rotation; Klamp't `joint spin`, flagged by the reference at graph.py:556-561): flags [host]
+ * [n], non-zero = spin, NULL = none.  For such a joint robot.distance (solver.py:805, graph.py:946,955) takes the wrapped
+ * angular difference, robot.interpolate (graph.py:962) the shorter arc normalised to [0, 2 pi), the IK solver treats it as
+ * unbounded, draws its random starts from [0, 2 pi) and returns it normalised to [0, 2 pi).  Call before any compute call. */
+int grr_chain_set_spin_joints(grr_handle_t h, const int32_t *flags);
 
 /* -- K: forward kinematics (Klamp't robot.setConfig + link.getTransform; graph.py:747-756,887-893)
  * q [dev] Real [n][P]; out_p [dev] Real [P][3]; out_R [dev] Real [P][9] (may be NULL). */

@@ -53,6 +53,7 @@ typedef struct {
   double ee_local[3];               /* constrained point in the last active joint's frame    */
   double R_tail[9];                 /* goal-link frame relative to the last active frame     */
   double R_goal[9];                 /* fixed-orientation goal (mode FIXED)                   */
+  int32_t spin[ORC_MAXJ];           /* 1: Klamp't `joint spin` (continuous rotation; graph.py:556-561) */
 } orc_chain;
 
 int orc_sizeof_chain(void) { return (int)sizeof(orc_chain); }
@@ -195,15 +196,30 @@ static void fk_all(const orc_chain *c, const double *q, double (*o)[3], double (
 /* public: EE point and goal-link rotation at q */
 void orc_fk(const orc_chain *c, const double *q, double *p, double *Rlink) { fk_all(c, q, NULL, NULL, p, Rlink); }
 
-/* Klamp't robot.distance(a,b) for 'joint normal' DOFs: L2 (solver.py:805,827,889; graph.py:946,955,967,971) */
+/* [recalled] KrisLibrary math/angle: AngleNormalize into [0, 2pi); AngleDiff(a,b) = a - b wrapped into (-pi, pi];
+ * AngleInterp(a,b,u) = AngleNormalize(a + u AngleDiff(b,a)).  Used for 'spin' joints only. */
+static double angle_normalize(double a) {
+  double an = fmod(a, 2 * M_PI);
+  return an < 0 ? an + 2 * M_PI : an;
+}
+static double angle_diff(double a, double b) {
+  double d = angle_normalize(angle_normalize(a) - angle_normalize(b));
+  return d > M_PI ? d - 2 * M_PI : d;
+}
+/* Klamp't robot.distance(a,b): L2 over the DOFs, 'joint normal' DOFs by plain difference, 'joint spin' DOFs by the
+ * wrapped angular difference (solver.py:805,827,889; graph.py:946,955,967,971) */
 double orc_distance(const orc_chain *c, const double *a, const double *b) {
   double s = 0;
-  for (int j = 0; j < c->n; j++) { double d = a[j] - b[j]; s += d * d; }
+  for (int j = 0; j < c->n; j++) { double d = c->spin[j] ? angle_diff(a[j], b[j]) : a[j] - b[j]; s += d * d; }
   return sqrt(s);
 }
-/* Klamp't robot.interpolate(a,b,u) for 'joint normal' DOFs: per-DOF lerp (graph.py:962) */
+/* Klamp't robot.interpolate(a,b,u): per-DOF lerp for 'joint normal' DOFs, shorter arc normalised to [0, 2pi) for
+ * 'joint spin' DOFs (graph.py:962) */
 static void interp_q(const orc_chain *c, const double *a, const double *b, double u, double *x) {
-  for (int j = 0; j < c->n; j++) x[j] = a[j] + u * (b[j] - a[j]);
+  for (int j = 0; j < c->n; j++) {
+    if (c->spin[j]) { double an = angle_normalize(a[j]); x[j] = angle_normalize(fma(u, angle_diff(b[j], an), an)); }
+    else x[j] = a[j] + u * (b[j] - a[j]);
+  }
 }
 
 /* ------------------------------------------------------------------------------------- */
@@ -334,7 +350,7 @@ int orc_ik_solve(const orc_chain *c, const double *w, double *x, orc_ikinfo *inf
   int evals = 0, iters = 0, status = ORC_FAIL_MAXIT;
   for (int j = 0; j < n; j++) {
     /* revolute joints with range >= 2pi are unbounded */
-    if (c->qmax[j] - c->qmin[j] >= 2 * M_PI) { bmin[j] = -INFINITY; bmax[j] = INFINITY; }
+    if (c->spin[j] || c->qmax[j] - c->qmin[j] >= 2 * M_PI) { bmin[j] = -INFINITY; bmax[j] = INFINITY; }
     else { bmin[j] = c->qmin[j]; bmax[j] = c->qmax[j]; }
     if (x[j] < bmin[j]) x[j] = bmin[j];
     if (x[j] > bmax[j]) x[j] = bmax[j];
@@ -417,6 +433,8 @@ int orc_ik_solve(const orc_chain *c, const double *w, double *x, orc_ikinfo *inf
     status = ORC_FAIL_MAXIT;
   }
 done:
+  /* [recalled] robot.NormalizeAngles after the solve: 'spin' joints come back in [0, 2pi) */
+  for (int j = 0; j < n; j++) if (c->spin[j]) x[j] = angle_normalize(x[j]);
   if (info) { info->status = status; info->iters = iters; info->evals = evals; info->resid = maxabs(F, m); }
   return status;
 }
@@ -466,6 +484,7 @@ void orc_random_seed(const orc_chain *c, uint64_t seed, uint32_t node_uid, uint3
     float u = (float)(r[j % 4] >> 8) * (1.0f / 16777216.0f);
     float lo = (float)c->qmin[j], hi = (float)c->qmax[j];
     if (c->qmax[j] - c->qmin[j] >= 2 * M_PI) { lo = -3.14159265358979f; hi = 3.14159265358979f; }
+    if (c->spin[j]) { lo = 0.0f; hi = 6.28318530717959f; }    /* [recalled] RobotCSpace sampling of a spin joint */
     q[j] = (double)fmaf(u, hi - lo, lo);
   }
 }

@@ -21,6 +21,7 @@ class Chain(C.Structure):
         ("Rp", C.c_double * (MAXJ * 9)), ("tp", C.c_double * (MAXJ * 3)), ("axis", C.c_double * (MAXJ * 3)),
         ("qmin", C.c_double * MAXJ), ("qmax", C.c_double * MAXJ),
         ("ee_local", C.c_double * 3), ("R_tail", C.c_double * 9), ("R_goal", C.c_double * 9),
+        ("spin", C.c_int32 * MAXJ),
     ]
 
 
@@ -89,6 +90,9 @@ class Oracle:
         c.ee_local[:] = list(f64(fold["ee_local"]).reshape(3))
         c.R_tail[:] = list(f64(fold["R_tail"]).reshape(9))
         c.R_goal[:] = list(np.eye(3).reshape(9) if R_goal is None else f64(R_goal).reshape(9))
+        sp = fold.get("spin") if hasattr(fold, "get") else None
+        if sp is not None:
+            c.spin[:n] = [int(v) for v in np.asarray(sp).reshape(-1)]
         self.c, self.n, self.mode = c, n, int(mode)
         self.m = 3 if mode == FREE else 6
         self.dw = 6 if mode == VARIABLE else 3

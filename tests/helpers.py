@@ -41,3 +41,23 @@ def reference_configs(rr, cap=None):
     exact = rr.exact_edges or rr.resolution.torch_dtype == torch.float64
     key = "Qs" if exact else "Q"
     return np.ascontiguousarray(np.transpose(rr._dev[key][:, :, :cap].double().cpu().numpy(), (0, 2, 1)))
+
+
+def spin_problem(name, jsonfile, Nw, method, spin_links, dtype="float32", lazy_chain=False, **over):
+    """small_problem with the named links turned into Klamp't 'spin' joints (continuous rotation, limits [0, 2 pi]) -- e.g.
+    the Jaco's joints 1, 4, 5, 6, which a URDF import declares `continuous`."""
+    from globalredundancyresolution_b200 import problems
+    from globalredundancyresolution_b200.graph import RedundancyResolutionGraph
+    over = dict(over)
+    over.update({"Nw": Nw, "workspace_graph": method})
+    pdef = problems.read_options(name, jsonfile, over)
+    robot = problems.load_robot(pdef["filename"])
+    for l in spin_links:
+        i = robot.link(l).index
+        assert i >= 0
+        robot.joint_kind[i] = "spin"
+        robot.qmin[i], robot.qmax[i] = 0.0, 2.0 * np.pi
+    res = RedundancyResolutionGraph(robot, dtype=dtype, lazy_chain=lazy_chain)
+    res.readJsonSetup(pdef)
+    res.sampleWorkspace(pdef["Nw"], method=pdef["workspace_graph"])
+    return pdef, res

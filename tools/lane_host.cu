@@ -39,12 +39,13 @@ static void run_pair(const ChainDev<Real, kMaxJ> &c, const Real *qa, const Real 
   winterp_begin<Real, M, kMaxJ>(c, a6, b6, W);
   P.qa = qa; P.qb = qb; P.sa = 1; P.sb = 1;
   int verdict = -1, fail = 0, maxit = 0, fstat = 0, fit = 0; double fres = 0;
-  if (!pair_begin<Real, M, FLAG>(c, eps, P, L)) verdict = 1;
+  if (!pair_begin<Real, M, FLAG>(c, eps, P, L, c.spin_mask)) verdict = 1;
   else winterp_at<Real, M>(W, P.u_at(1), tg);
   while (verdict < 0) {
     PassOut<Real, M> o;
     const bool first = P.k == 1;
     if constexpr (PL) lane_pass_planar<Real, true>(c, tg, L, mem, first ? P.qa : mem.prev(), first ? P.sa : mem.T, o);
+    else if (c.spin_mask) lane_pass<Real, M, true, true>(c, tg, L, mem, first ? P.qa : mem.prev(), first ? P.sa : mem.T, o);
     else lane_pass<Real, M, true>(c, tg, L, mem, first ? P.qa : mem.prev(), first ? P.sa : mem.T, o);
     const int st = lane_step<Real, M, PL, FLAG>(c, L, mem, o, true);
     if (st != IK_RUNNING) {
@@ -60,7 +61,7 @@ static void run_pair(const ChainDev<Real, kMaxJ> &c, const Real *qa, const Real 
       if (FLAG) pair_note_solve(P, L, st);
       if (st != IK_OK) { verdict = 0; fail = 1; fstat = st; fit = L.it; fres = (double)L.resid; }
       else {
-        verdict = pair_advance<FLAG>(c, mem, o.s2, thr2, P, L);
+        verdict = pair_advance<FLAG>(c, mem, o.s2, thr2, P, L, false, c.spin_mask);
         if (verdict == 0) fail = 2;
         if (verdict < 0) winterp_at<Real, M>(W, P.u_at(P.k), tg);
       }
@@ -94,6 +95,12 @@ static void run_all(const HostChain &h, long long P, const double *qa, const dou
 
 using namespace grr;
 
+// 'spin' joint flags applied to the chains of the following lane_host_pairs / lane_host_trace calls (NULL = none)
+static int g_spin[GRR_MAX_JOINTS];
+extern "C" void lane_host_set_spin(const int32_t *flags, int n) {
+  for (int j = 0; j < GRR_MAX_JOINTS; j++) g_spin[j] = (flags && j < n && flags[j]) ? 1 : 0;
+}
+
 // precision: 0 = float with near-tie flags, 1 = double, 2 = float without flags.  fl: 10 margins (see grr_fill.cuh) or
 // NULL = flag_margins(scale).  info [P][8] = {flag reasons, Ndivs, solves, iters, fail kind, longest solve, status * 100 + iterations and max|F| * 1e6 of the failing solve} (nullable).
 extern "C" int lane_host_pairs(const grr_chain_desc *d, const double *fl, double scale, long long P, const double *qa,
@@ -111,6 +118,7 @@ extern "C" int lane_host_pairs(const grr_chain_desc *d, const double *fl, double
   memcpy(h.ee_local, d->ee_local, sizeof h.ee_local);
   memcpy(h.R_tail, d->R_tail, sizeof h.R_tail);
   memcpy(h.R_goal, d->R_goal, sizeof h.R_goal);
+  memcpy(h.spin, g_spin, sizeof h.spin);
   flag_margins(h, scale);
   if (fl) memcpy(h.fl, fl, sizeof h.fl);
   const bool m6 = h.mode != GRR_FREE;
@@ -131,6 +139,7 @@ extern "C" int lane_host_trace(const grr_chain_desc *d, double scale, const doub
   memcpy(h.axis, d->axis, sizeof(double) * 3 * d->n); memcpy(h.qmin, d->qmin, sizeof(double) * d->n);
   memcpy(h.qmax, d->qmax, sizeof(double) * d->n); memcpy(h.ee_local, d->ee_local, sizeof h.ee_local);
   memcpy(h.R_tail, d->R_tail, sizeof h.R_tail); memcpy(h.R_goal, d->R_goal, sizeof h.R_goal);
+  memcpy(h.spin, g_spin, sizeof h.spin);
   flag_margins(h, scale);
   const bool m6 = h.mode != GRR_FREE, pl = !m6 && is_planar_y(h);
   const int n = h.n, dw = (h.mode == 2 ? 6 : 3);
