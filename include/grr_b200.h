@@ -16,6 +16,9 @@
  *   - all array arguments marked [dev] are caller-owned DEVICE pointers (e.g. torch tensors'
  *     data_ptr()); [host] are host pointers.  `stream` is a cudaStream_t (0 = default stream).
  *     Calls are asynchronous on `stream` unless stated otherwise.
+ *   - a handle serves ONE host thread and ONE stream at a time (its ring of device work counters and its scratch
+ *     buffer are not synchronised between callers): use one handle per concurrent stream, as the reference uses one
+ *     robot / IK solver per worker process (solver.py:2379-2400).
  *   - `dtype` selects the arithmetic type of the path and of every "Real" buffer:
  *     GRR_F32 (the product path, FP32 SIMT) or GRR_F64 (verification build of the same kernels).
  *   - rotation matrices are ROW-major 3x3.
