@@ -54,3 +54,43 @@ def test_reference_script_runs_unchanged(built, tmp_path):
     assert resolution2.resolvedCount == resolution.resolvedCount
     k = next(iter(rr.Qsubgraph))
     assert resolution2.Gw.node[k]["config"] == pytest.approx(resolution.Gw.node[k]["config"])
+
+
+@pytest.mark.parametrize("name,jf,Nw", [("planar_5R", "Rfree.json", 300), ("jaco", "baseline_cfg3.json", 200)])
+def test_verify_equals_the_reference_loop_on_the_oracle(built, name, jf, Nw):
+    """RedundancyResolutionGraph.verify (graph.py:704-718): the batched device re-test gives, edge by edge, what the
+    reference's loop gives with the CPU oracle's validEdge -- on a resolution whose `connected` marks were scrambled, so
+    that both repairs occur (marked but invalid -> unmarked and counted in numInvalid; unmarked but valid -> marked and
+    counted in numValid)."""
+    import sys
+    sys.path.insert(0, os.path.dirname(__file__))
+    from helpers import oracle_for
+    pdef, res, rr = grr.make_program(name, jf, overrides={"Nw": Nw, "Nq": 12})
+    rr.sampleConfigurationSpace(pdef["Nq"])
+    rr.solveCSP()
+    assert res.hasResolution()
+    o = oracle_for(res)
+    cand = [(i, j) for i, j in res.Gw.edges_iter() if res.isResolvedNode(i) and res.isResolvedNode(j)]
+    assert len(cand) > 20
+    truth = {}
+    for i, j in cand:
+        qa, qb = res.to_chain(np.asarray(res.Gw.node[i]["config"])), res.to_chain(np.asarray(res.Gw.node[j]["config"]))
+        truth[(i, j)] = bool(o.valid_edge(qa, qb, np.asarray(res.Gw.node[i]["params"], dtype=float),
+                                          np.asarray(res.Gw.node[j]["params"], dtype=float))[0])
+    assert any(truth.values())
+    rng = np.random.default_rng(1)
+    want_invalid = want_valid = 0
+    for (i, j) in cand:
+        mark = bool(rng.integers(0, 2))
+        if mark:
+            res.markConnected(i, j)
+        else:
+            res.Gw.edge[i][j].pop("connected", None)
+        want_invalid += int(mark and not truth[(i, j)])
+        want_valid += int((not mark) and truth[(i, j)])
+    numInvalid, numValid = res.verify()
+    assert (numInvalid, numValid) == (want_invalid, want_valid)
+    assert want_valid > 0
+    for (i, j) in cand:
+        assert res.isResolvedEdge(i, j) == truth[(i, j)]
+    assert res.verify() == (0, 0)                                   # idempotent
