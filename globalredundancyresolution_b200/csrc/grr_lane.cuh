@@ -241,6 +241,11 @@ GRR_DEV void joint_axis(Real s, Real co, Real sgn, Real *v, Real *G, Real *col) 
   }
 }
 
+// joints per trip of the double-precision planar pass (2 = the loop single precision uses; see lane_pass_planar_)
+#ifndef GRR_F64_PLANAR_UNROLL
+#define GRR_F64_PLANAR_UNROLL 5
+#endif
+
 // ---- the chain pass: executed by EVERY lane of the warp (uniform joint counter) ----------------
 template <typename Real, int M>
 struct PassOut {
@@ -318,6 +323,33 @@ GRR_DEV void lane_pass_planar_(const ChainT &c, const Target<Real, 3> &tg, const
   // load) and shared-memory operands are in flight while the current joint is computed, and no register
   // rotation is needed
   int j = n - 1;
+#ifdef __CUDA_ARCH__
+  if constexpr (sizeof(Real) == 8 && GRR_F64_PLANAR_UNROLL > 2) {
+    // Double precision: the kernels that run this pass (recheck of the exact build, sampling, seeded sweep) hold 4-8
+    // warps per SM and are bound by the latency of one joint's dependent chain (the sin / cos polynomials: ~15 dependent
+    // DFMAs), not by issue slots.  U joints per trip, operands of all U fetched first: the U polynomial evaluations are
+    // independent and overlap; only the short frame update (v, G) is serial.  Same operations per joint in the same
+    // order: results are bit-identical to the two-joint loop below.
+    constexpr int U = GRR_F64_PLANAR_UNROLL;
+#pragma unroll 1
+    for (; j >= U - 1; j -= U) {
+      JointConst<Real> jcu[U];
+      Real au[U], bu[U], ru[U];
+      Real *wu[U];
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        jcu[u] = c.jc[j - u];
+        au[u] = *pa; bu[u] = *pb; wu[u] = pb; ru[u] = WITH_REF ? *pr : Real(0);
+        pa -= sa; pb -= sb;
+        if (WITH_REF) pr -= sref;
+      }
+#pragma unroll
+      for (int u = 0; u < U; u++) joint(jcu[u], au[u], bu[u], ru[u], wu[u]);
+    }
+    // (the joints that are left, fewer than U, run in the two-joint loop below)
+  }
+#endif
+  if (sizeof(Real) == 4 || j >= 0) {
   JointConst<Real> jcA = c.jc[j], jcB;
   Real aA = *pa, bA = *pb, rA = WITH_REF ? *pr : Real(0), aB, bB, rB = 0;
   Real *wA = pb, *wB;
@@ -335,6 +367,7 @@ GRR_DEV void lane_pass_planar_(const ChainT &c, const Target<Real, 3> &tg, const
     joint(jcB, aB, bB, rB, wB);
   }
   if (j == 0) joint(jcA, aA, bA, rA, wA);
+  }
   o.xn2 = xn2; o.s2 = s2;
   if (!SMALL) { test = rtest.get(); testx = rtestx.get(); }
   o.pn2 = pn2; o.test = test; o.testx = testx;
