@@ -775,8 +775,19 @@ k_valid_edge_batch(const __grid_constant__ ChainDev<Real, kMaxJ> c, long long to
 // shared-memory counter and run their pairs as independent lane machines; verdict bits are OR-ed into
 // a shared-memory Nq x Nq bitmask that is written out once.
 // ------------------------------------------------------------------------------------------
-template <typename Real, int M, bool PL, bool FLAG, bool SPIN = false>
+// KT > 0: instantiation for CTAs of exactly KT lanes (planar chains; see lane_pass_planar_)
+template <typename Real, int M, bool PL, bool FLAG, bool SPIN = false, int KT = 0>
+#ifndef GRR_KT_MIN_BLOCKS
+#define GRR_KT_MIN_BLOCKS 2
+#endif
+// (the near-tie build of the KT instantiation may use the registers two CTAs of KT lanes leave it -- 153 instead of 119:
+// pass loop 140 -> 134 instructions, config 2 exact build 0.4086 -> 0.4058 s; the plain build is 2 % slower that way and keeps
+// the default bound)
+#if GRR_KT_MIN_BLOCKS
+__global__ void __launch_bounds__(KT > 0 && FLAG ? KT : (sizeof(Real) == 4 ? (M == 3 ? 512 : 384) : 256), KT > 0 && FLAG ? GRR_KT_MIN_BLOCKS : 0)
+#else
 __global__ void __launch_bounds__(sizeof(Real) == 4 ? (M == 3 ? 512 : 384) : 256)
+#endif
 k_edges_build(const __grid_constant__ ChainDev<Real, kMaxJ> c, const int32_t *__restrict__ wedges,
               const Real *__restrict__ params, const Real *__restrict__ q_kept, const int32_t *__restrict__ count,
               const int32_t *__restrict__ old_count, int Nq, int Nqp, Real epsilon, uint32_t *mask,
@@ -908,7 +919,7 @@ k_edges_build(const __grid_constant__ ChainDev<Real, kMaxJ> c, const int32_t *__
       if (__any_sync(0xffffffffu, running)) {
         PassOut<Real, M> o;
         const bool first = running && P.k == 1;
-        if constexpr (PL) lane_pass_planar<Real, true>(c, tg, L, mem, first ? P.qa : mem.prev(), first ? P.sa : mem.T, o);
+        if constexpr (PL) lane_pass_planar<Real, true, KT>(c, tg, L, mem, first ? P.qa : mem.prev(), first ? P.sa : mem.T, o);
         else lane_pass<Real, M, true, SPIN>(c, tg, L, mem, first ? P.qa : mem.prev(), first ? P.sa : mem.T, o);
         const int st = lane_step<Real, M, PL, FLAG>(c, L, mem, o, running);
         if constexpr (FLAG) warp_tie_service<Real, M, PL>(c, L, mem, running);
@@ -1743,6 +1754,7 @@ struct Impl {
       if constexpr (kHasPlanar && sizeof(Real) == 4) {
         // two lane machines per thread on the packed FP32 instructions (k_edges_build2): planar small-angle chains
         static const bool no_dual = getenv("GRR_DUAL") == nullptr;      // opt-in until validated on the GPU
+        static const bool no_kt = getenv("GRR_NO_KT") != nullptr;       // A/B switch: run-time lane stride in the planar pass
         if (pl && c.small_angles != 0 && c.axes_positive != 0 && !no_dual && threads >= 64) {
           const int threads2 = (threads / 2) / 32 * 32;
           const size_t smem2 = fixed + (size_t)threads2 * 2 * h.n * (4 + mc(h)) * sizeof(Real);
@@ -1754,7 +1766,8 @@ struct Impl {
           };
           rc = flist ? launch2(k_edges_build2<true>) : launch2(k_edges_build2<false>);
         } else
-        if (pl) rc = flist ? launch(k_edges_build<Real, M, true, true>) : launch(k_edges_build<Real, M, true, false>);
+        if (pl && threads == 192 && !no_kt) rc = flist ? launch(k_edges_build<Real, M, true, true, false, 192>) : launch(k_edges_build<Real, M, true, false, false, 192>);
+        else if (pl) rc = flist ? launch(k_edges_build<Real, M, true, true>) : launch(k_edges_build<Real, M, true, false>);
         else rc = flist ? launch(k_edges_build<Real, M, false, true>) : launch(k_edges_build<Real, M, false, false>);
       } else if constexpr (kHasPlanar) {
         rc = pl ? launch(k_edges_build<Real, M, true, false>) : launch(k_edges_build<Real, M, false, false>);

@@ -261,7 +261,9 @@ struct PassOut {
 // goal-link frame equals the last joint frame (the reference's planar_{2,3,5,10,20}R robots).  G stays a
 // rotation about y, kept as (cos, sin); columns have two in-plane components (x, z); the normal matrix is
 // 2x2.  Same algorithm, a third of the arithmetic.
-template <typename Real, bool WITH_REF, bool SMALL, bool POS, typename ChainT>
+// KT > 0: the lane count T of the CTA (the stride of the per-lane joint vectors) as a compile-time constant, so that the
+// column / trial-point addresses of the two joints of a trip are immediate offsets of one running pointer each
+template <typename Real, bool WITH_REF, bool SMALL, bool POS, int KT = 0, typename ChainT>
 GRR_DEV void lane_pass_planar_(const ChainT &c, const Target<Real, 3> &tg, const LaneIK<Real, 3> &L,
                                                   const LaneMem<Real, 2> &mem, const Real *xref, int sref,
                                                   PassOut<Real, 3> &o) {
@@ -273,7 +275,7 @@ GRR_DEV void lane_pass_planar_(const ChainT &c, const Target<Real, 3> &tg, const
   Real S11 = 0, S12 = 0, S22 = 0, xn2 = 0, s2 = 0;
   Real pn2 = 0, test = 0, testx = 0;
   RatioMax<Real> rtest, rtestx;           // (chains with joint ranges beyond +-pi/4)
-  const int T = mem.T;
+  const int T = KT > 0 ? KT : mem.T;
   const int sa = src.sa, sb = src.sb;
   const Real *pa = src.a + (n - 1) * sa;
   Real *pb = const_cast<Real *>(src.b) + (n - 1) * sb;      // written only by `first` lanes, whose b is mem.p()
@@ -380,13 +382,13 @@ GRR_DEV void lane_pass_planar_(const ChainT &c, const Target<Real, 3> &tg, const
   o.S[0] = S11; o.S[1] = S12; o.S[2] = S22;
   o.fmax = max_(max_(abs_(o.Fw[0]), abs_(o.Fw[1])), abs_(o.Fw[2]));
 }
-template <typename Real, bool WITH_REF, typename ChainT>
+template <typename Real, bool WITH_REF, int KT = 0, typename ChainT>
 GRR_DEV void lane_pass_planar(const ChainT &c, const Target<Real, 3> &tg, const LaneIK<Real, 3> &L,
                                                  const LaneMem<Real, 2> &mem, const Real *xref, int sref,
                                                  PassOut<Real, 3> &o) {
   // the shipped planar_{10,20}R robots: limits inside +-pi/4 and every axis +e_y
-  if (c.small_angles != 0 && c.axes_positive != 0) lane_pass_planar_<Real, WITH_REF, true, true>(c, tg, L, mem, xref, sref, o);
-  else lane_pass_planar_<Real, WITH_REF, false, false>(c, tg, L, mem, xref, sref, o);
+  if (c.small_angles != 0 && c.axes_positive != 0) lane_pass_planar_<Real, WITH_REF, true, true, KT>(c, tg, L, mem, xref, sref, o);
+  else lane_pass_planar_<Real, WITH_REF, false, false, KT>(c, tg, L, mem, xref, sref, o);
 }
 
 // The joint loop of the pass.  SPIN: the chain has 'spin' joints (c.spin_mask != 0) -- a compile-time property of the
