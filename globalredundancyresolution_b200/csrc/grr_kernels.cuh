@@ -1221,6 +1221,10 @@ static __global__ void k_edges_bits(long long E, int words, const uint32_t *__re
 // the FP64 latencies -- the kernel sat at 52 % issue utilisation with `stalled_wait` 1.6 per issue), 2 for 6 rows
 // (capping that build at 168 registers spills 1.6 KB per thread)
 template <typename Real, int M, bool PL, bool FLAG, bool SPIN = false>
+// the queue kernel always runs CTAs of 128 lanes: the lane stride of its passes is a compile-time constant (0 = run-time)
+#ifndef GRR_FLAT_KT
+#define GRR_FLAT_KT 128
+#endif
 #ifndef GRR_F64M3_BLOCKS
 #define GRR_F64M3_BLOCKS 3
 #endif
@@ -1326,8 +1330,8 @@ k_edges_flat(const __grid_constant__ ChainDev<Real, kMaxJ> c, long long E, const
     if (__any_sync(0xffffffffu, running)) {
       PassOut<Real, M> o;
       const bool first = running && P.k == 1;
-      if constexpr (PL) lane_pass_planar<Real, true>(c, tg, L, mem, first ? P.qa : mem.prev(), first ? P.sa : mem.T, o);
-      else lane_pass<Real, M, true, SPIN>(c, tg, L, mem, first ? P.qa : mem.prev(), first ? P.sa : mem.T, o);
+      if constexpr (PL) lane_pass_planar<Real, true, GRR_FLAT_KT>(c, tg, L, mem, first ? P.qa : mem.prev(), first ? P.sa : mem.T, o);
+      else lane_pass<Real, M, true, SPIN, GRR_FLAT_KT>(c, tg, L, mem, first ? P.qa : mem.prev(), first ? P.sa : mem.T, o);
       const int st = lane_step<Real, M, PL, FLAG>(c, L, mem, o, running);
       if constexpr (FLAG) warp_tie_service<Real, M, PL>(c, L, mem, running);
       if (running && st != IK_RUNNING) {
@@ -1842,6 +1846,7 @@ struct Impl {
     if (int rc = check_launch("k_scan_u64")) return rc;
     cudaMemsetAsync(work, 0, sizeof(unsigned long long), st);
     const int threads = 128;
+    static_assert(GRR_FLAT_KT == 0 || GRR_FLAT_KT == 128, "k_edges_flat is launched with 128 lanes per CTA");
     const size_t smem = (size_t)(threads / 32) * 32 * sizeof(int4) + (size_t)threads * h.n * (4 + mc(h)) * sizeof(Real);
     auto launch = [&](auto kern) -> int {
       if (set_smem(kern, smem, "k_edges_flat")) return -2;

@@ -395,7 +395,7 @@ GRR_DEV void lane_pass_planar(const ChainT &c, const Target<Real, 3> &tg, const 
 // kernel (the launchers pick the SPIN instantiations for such chains), so that the kernels every shipped problem runs are
 // the code they were before spin joints existed (a run-time test of jc.spin in the common loop, or both loops in one
 // kernel, cost the double-precision kernels of the 6-/7-joint arms 4-8 %).
-template <typename Real, int M, bool WITH_REF, bool SPIN, typename ChainT>
+template <typename Real, int M, bool WITH_REF, bool SPIN, int KT = 0, typename ChainT>
 GRR_DEV void lane_pass_chain_(const ChainT &c, const LaneIK<Real, M> &L, const LaneMem<Real, M> &mem, const Real *xref, int sref,
                               PassOut<Real, M> &o, Real (&v)[3], Real (&G)[9]) {
   const int n = c.n;
@@ -407,7 +407,7 @@ GRR_DEV void lane_pass_chain_(const ChainT &c, const LaneIK<Real, M> &L, const L
   for (int k = 0; k < M * (M + 1) / 2; k++) o.S[k] = 0;
   Real xn2 = 0, s2 = 0, pn2 = 0;
   RatioMax<Real> rtest, rtestx;
-  const int T = mem.T;
+  const int T = KT > 0 ? KT : mem.T;            // KT > 0: the CTA's lane count as a compile-time constant (immediate offsets)
   const int sa = src.sa, sb = src.sb;
   const Real *pa = src.a + (n - 1) * sa;
   Real *pb = const_cast<Real *>(src.b) + (n - 1) * sb;      // written only by `first` lanes, whose b is mem.p()
@@ -506,11 +506,11 @@ GRR_DEV void lane_pass_chain_(const ChainT &c, const LaneIK<Real, M> &L, const L
   o.pn2 = pn2; o.test = rtest.get(); o.testx = rtestx.get();
 }
 
-template <typename Real, int M, bool WITH_REF, bool SPIN = false, typename ChainT>
+template <typename Real, int M, bool WITH_REF, bool SPIN = false, int KT = 0, typename ChainT>
 GRR_DEV void lane_pass(const ChainT &c, const Target<Real, M> &tg, const LaneIK<Real, M> &L,
                                           const LaneMem<Real, M> &mem, const Real *xref, int sref, PassOut<Real, M> &o) {
   Real v[3], G[9];
-  lane_pass_chain_<Real, M, WITH_REF, SPIN>(c, L, mem, xref, sref, o, v, G);
+  lane_pass_chain_<Real, M, WITH_REF, SPIN, KT>(c, L, mem, xref, sref, o, v, G);
   o.Fw[0] = v[0] - tg.x[0]; o.Fw[1] = v[1] - tg.x[1]; o.Fw[2] = v[2] - tg.x[2];
   Real f = o.Fw[0] * o.Fw[0] + o.Fw[1] * o.Fw[1] + o.Fw[2] * o.Fw[2];
   m3_Tvec(G, o.Fw, o.FL);
