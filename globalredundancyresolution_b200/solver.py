@@ -1212,8 +1212,6 @@ class RedundancyResolver(VisibilityMixin):
         nodes of one level of the lower-neighbour DAG (the schedule of the seeded sampling sweep) are processed
         together with the same result: one batched IK launch and one batched validEdge launch per try and level.
         Ends with fromResolutionToGraph() like the reference.  Returns the mean path length per resolved edge."""
-        if self.resolution.chain.spin.any():
-            raise NotImplementedError("optimize() with spin joints (robot_average on wrapped angles) is not built")
         res = self.resolution
         lv = self._sweep_levels()
         level = lv["host"][3]
@@ -1232,6 +1230,11 @@ class RedundancyResolver(VisibilityMixin):
         cfg = {i: np.asarray(res.Gw.node[i]["config"], dtype=np.float64) for i in nodes}
         par = {i: res.Gw.node[i]["params"] for i in nodes}
         dist = lambda a, b: float(np.sqrt(((a - b) ** 2).sum()))      # robot.distance for 'normal' joints (K1)
+        lerp = lambda a, b, u: a + (b - a) * u                        # robot.interpolate for 'normal' joints (K2)
+        if res.spinJoints:
+            # spin joints: wrapped differences / shorter arcs, as robot_average gets them from robot.interpolate
+            dist = lambda a, b: res.robot.distance(a, b)
+            lerp = lambda a, b, u: np.asarray(res.robot.interpolate(a, b, u), dtype=np.float64)
         mean_len = 0.0
         for _ in range(int(numIters)):
             total = 0.0
@@ -1244,7 +1247,7 @@ class RedundancyResolver(VisibilityMixin):
                     qs = [cfg[w] for w in nbrs[v]]
                     r = qs[0]
                     for k in range(1, len(qs)):
-                        r = r + (qs[k] - r) * (1.0 / (k + 1))
+                        r = lerp(r, qs[k], 1.0 / (k + 1))
                     qavg[v] = r
                 pending = list(batch)
                 for _try in range(10):                                # solver.py:1956-1978
@@ -1276,7 +1279,7 @@ class RedundancyResolver(VisibilityMixin):
                                 q0[v] = q                             # committed after the level (neighbours are in other levels)
                     pending = [v for v in pending if v not in moved]
                     for v in pending:
-                        qavg[v] = q0[v] + (qavg[v] - q0[v]) * 0.5     # robot.interpolate(q0, qavg, 0.5)
+                        qavg[v] = lerp(q0[v], qavg[v], 0.5)           # robot.interpolate(q0, qavg, 0.5)
                 for v in batch:
                     cfg[v] = q0[v]
                     total += d0[v]

@@ -272,6 +272,10 @@ def _optimize_sequential(res, numIters, o=None):
             nbrs[i].append(j); nbrs[j].append(i)
     cfg = {i: np.asarray(res.Gw.node[i]["config"], dtype=np.float64) for i in nodes}
     dist = lambda a, b: float(np.sqrt(((a - b) ** 2).sum()))
+    lerp = lambda a, b, u: a + (b - a) * u
+    if res.spinJoints:                                 # robot.distance / robot.interpolate with spin joints (K1 / K2)
+        dist = lambda a, b: res.robot.distance(a, b)
+        lerp = lambda a, b, u: np.asarray(res.robot.interpolate(a, b, u), dtype=np.float64)
     for _ in range(numIters):
         for v in nodes:
             ws = sorted(nbrs[v])
@@ -281,7 +285,7 @@ def _optimize_sequential(res, numIters, o=None):
             d0 = sum(dist(q0, cfg[w]) for w in ws)
             qavg = cfg[ws[0]]
             for k in range(1, len(ws)):
-                qavg = qavg + (cfg[ws[k]] - qavg) * (1.0 / (k + 1))
+                qavg = lerp(qavg, cfg[ws[k]], 1.0 / (k + 1))
             for _try in range(10):
                 q = solve(qavg.tolist(), x)
                 if q is not None:
@@ -290,7 +294,7 @@ def _optimize_sequential(res, numIters, o=None):
                     if d <= d0 and all(valid_edge(q.tolist(), cfg[w].tolist(), x, res.Gw.node[w]["params"]) for w in ws):
                         cfg[v] = q
                         break
-                qavg = q0 + (qavg - q0) * 0.5
+                qavg = lerp(q0, qavg, 0.5)
     return cfg
 
 
@@ -319,3 +323,28 @@ def test_optimize_equals_sequential_sweep_and_feeds_the_roadmap(built):
         assert rr.Gw.node[i]["qlist"][rr.Qsubgraph[i]] == pytest.approx(after[i], abs=1e-12)
     for i, j in connected:
         assert rr.hasEdge(i, rr.Qsubgraph[i], j, rr.Qsubgraph[j])
+
+
+@pytest.mark.gpu
+def test_optimize_with_spin_joints_equals_sequential_sweep_on_the_oracle(built):
+    """optimize() on a chain with spin joints: robot_average (utils.py:118-136) goes through robot.interpolate, so the
+    neighbours' average and the halving steps move along shorter arcs and path lengths are wrapped distances; equal to the
+    reference's sequential loop run with the CPU oracle's solve / validEdge."""
+    from helpers import oracle_for, spin_problem
+    pdef, res = spin_problem("jaco", "baseline_cfg3.json", 200, "staggered_grid",
+                             ["jaco_link_1", "jaco_link_4", "jaco_link_5", "jaco_link_hand"])
+    rr = grr.RedundancyResolver(res, seed=5)
+    rr.sampleConfigurationSpace(10, order_independent=True)
+    rr.solveCSP(numInitialGuesses=4)
+    before = {i: list(d["config"]) for i, d in res.Gw.nodes_iter(data=True) if d.get("config", None) is not None}
+    connected = [(i, j) for i, j in res.Gw.edges_iter() if res.isResolvedEdge(i, j)]
+    assert len(connected) > 10 and res.spinJoints
+    want = _optimize_sequential(res, 2, o=oracle_for(res))
+    rr.optimize(2)
+    after = {i: res.Gw.node[i]["config"] for i in before}
+    for i in before:
+        np.testing.assert_allclose(after[i], want[i], rtol=0, atol=1e-8, err_msg="node %d" % i)
+    length = lambda cfgs: sum(res.robot.distance(cfgs[i], cfgs[j]) for i, j in connected)
+    assert length(after) <= length(before) + 1e-9
+    assert any(after[i] != before[i] for i in before)
+    assert res.verify()[0] == 0
