@@ -85,9 +85,9 @@ def lib():
     L.grr_ik_sample_sweep.argtypes = [vp, C.c_int, i64, vp, i32, i32, vp, vp, vp, vp, vp, vp, i32, vp, u64, i32, i32, vp, vp, dbl, vp,
                                       vp, vp, i32, i64, i32, vp]
     L.grr_edges_test_listed.argtypes = [vp, C.c_int, vp, vp, vp, i32, i32, dbl, vp, vp, vp, u64, vp, vp]
-    L.grr_manifold_knn_list.argtypes = [C.c_int, i64, vp, i32, i32, i32, vp, vp, i32, vp, u64, vp]
-    L.grr_manifold_components.argtypes = [C.c_int, i64, vp, i32, i32, i32, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, vp]
-    L.grr_qcc_candidates.argtypes = [C.c_int, i64, vp, i32, i32, i32, vp, vp, vp, vp, vp, vp, i32, u64, i32, vp, vp]
+    L.grr_manifold_knn_list.argtypes = [C.c_int, i64, vp, i32, i32, i32, vp, vp, i32, vp, u64, C.c_uint32, vp]
+    L.grr_manifold_components.argtypes = [C.c_int, i64, vp, i32, i32, i32, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, C.c_uint32, vp]
+    L.grr_qcc_candidates.argtypes = [C.c_int, i64, vp, i32, i32, i32, vp, vp, vp, vp, vp, vp, i32, u64, i32, vp, C.c_uint32, vp]
     L.grr_qcc_wave.argtypes = [i64, vp, vp, vp, i32, vp, i32, vp, i32, i32, i32, vp, u64, vp]
     L.grr_qcc_connect.argtypes = [i64, vp, vp, vp, i32, vp, i32, vp, i32, i32, vp, vp, vp, vp, vp]
     L.grr_pair_hash.argtypes = [u64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]
@@ -196,6 +196,11 @@ class ChainHandle:
             if self._flag_scale is not None:
                 check(L.grr_set_flag_scale(h, float(self._flag_scale)), "grr_set_flag_scale")
         return self._handle
+
+    @property
+    def spin_mask(self):
+        """bit j = chain joint j is a 'spin' joint (the visibility entry points take it as an argument)"""
+        return int(sum(1 << j for j in range(self.n) if self.spin[j]))
 
     @property
     def dw(self):
@@ -381,26 +386,26 @@ def csp_descent_sweep(node_list, Nq, adj_ptr, adj_node, adj_edge, mask, edge_act
           "grr_csp_descent_sweep")
 
 
-def manifold_knn_list(q, count, Nq, knn, plist, node_list=None):
+def manifold_knn_list(q, count, Nq, knn, plist, node_list=None, spin_mask=0):
     """Pairs the k-nearest branch of constructSelfMotionManifold may test (solver.py:635-643) -> plist."""
     Nn = q.shape[0] if node_list is None else node_list.shape[0]
     cap = (plist.shape[0] - 2) // 2
     check(lib().grr_manifold_knn_list(dtype_code(q.dtype), Nn, _ptr(node_list), q.shape[1], int(Nq), q.shape[2], _ptr(q), _ptr(count),
-                                      int(knn), _ptr(plist), cap, _stream(q.device)), "grr_manifold_knn_list")
+                                      int(knn), _ptr(plist), cap, int(spin_mask), _stream(q.device)), "grr_manifold_knn_list")
 
 
-def manifold_components(q, count, Nq, self_mask, knn, label, ncc, parents, members, cc_start, ntests=None, node_list=None):
+def manifold_components(q, count, Nq, self_mask, knn, label, ncc, parents, members, cc_start, ntests=None, node_list=None, spin_mask=0):
     """constructSelfMotionManifold (solver.py:623-669) replayed on the self mask's verdict bits."""
     Nn = q.shape[0] if node_list is None else node_list.shape[0]
     check(lib().grr_manifold_components(dtype_code(q.dtype), Nn, _ptr(node_list), q.shape[1], int(Nq), q.shape[2], _ptr(q), _ptr(count),
                                         _ptr(self_mask), int(knn), _ptr(label), _ptr(ncc), _ptr(parents), _ptr(members),
-                                        _ptr(cc_start), _ptr(ntests), _stream(q.device)), "grr_manifold_components")
+                                        _ptr(cc_start), _ptr(ntests), int(spin_mask), _stream(q.device)), "grr_manifold_components")
 
 
-def qcc_candidates(wedges, q, Nq, uid, ncc, members, cc_start, cc_off, max_tests, seed, swap, cand):
+def qcc_candidates(wedges, q, Nq, uid, ncc, members, cc_start, cc_off, max_tests, seed, swap, cand, spin_mask=0):
     check(lib().grr_qcc_candidates(dtype_code(q.dtype), wedges.shape[0], _ptr(wedges), q.shape[1], int(Nq), q.shape[2], _ptr(q),
                                    _ptr(uid), _ptr(ncc), _ptr(members), _ptr(cc_start), _ptr(cc_off), int(max_tests),
-                                   int(seed) & (2 ** 64 - 1), int(swap), _ptr(cand), _stream(q.device)), "grr_qcc_candidates")
+                                   int(seed) & (2 ** 64 - 1), int(swap), _ptr(cand), int(spin_mask), _stream(q.device)), "grr_qcc_candidates")
 
 
 def qcc_wave(wedges, ncc, cc_off, max_tests, cand, Nq, tested_mask, slot0, slot1, swap, plist):

@@ -329,7 +329,7 @@ static unsigned long long *scratch_cb(void *ctx, size_t words) { return scratch_
 extern "C" {
 
 const char *grr_last_error(void) { return g_err; }
-int grr_abi_version(void) { return 1; }
+int grr_abi_version(void) { return 2; }   // 2: spin joints (grr_chain_set_spin_joints, spin_mask of the visibility entry points)
 
 int grr_chain_create(const grr_chain_desc *d, int device, grr_handle_t *out) {
   if (!d || !out) { set_error("grr_chain_create: null argument"); return -1; }

@@ -27,10 +27,12 @@ static inline int vis_launch_ok(const char *what) {
 }
 
 template <typename Real>
-__device__ __forceinline__ double q_distance(int n, const Real *a, int sa, const Real *b, int sb) {
+__device__ __forceinline__ double q_distance(int n, unsigned spin, const Real *a, int sa, const Real *b, int sb) {
   double s = 0;
   for (int j = 0; j < n; j++) {
-    const double d = __dsub_rn((double)a[(long long)j * sa], (double)b[(long long)j * sb]);
+    // 'spin' joints: wrapped angular difference (robot.distance; same three functions as the oracle's restatement)
+    const double d = (spin >> j & 1u) ? angle_diff((double)a[(long long)j * sa], (double)b[(long long)j * sb])
+                                      : __dsub_rn((double)a[(long long)j * sa], (double)b[(long long)j * sb]);
     s = __dadd_rn(s, __dmul_rn(d, d));
   }
   return __dsqrt_rn(s);
@@ -79,7 +81,7 @@ __host__ __device__ __forceinline__ uint32_t pair_hash(uint32_t seed, uint32_t i
 // ------------------------------------------------------------------------------------------
 template <typename Real, int R>
 __global__ void __launch_bounds__(32)
-k_manifold(int n, int Nq, int Nqp, const Real *__restrict__ Q, const int32_t *__restrict__ count,
+k_manifold(int n, unsigned spin, int Nq, int Nqp, const Real *__restrict__ Q, const int32_t *__restrict__ count,
            const int32_t *__restrict__ node_list, const uint32_t *__restrict__ smask, int knn, int32_t *label_out,
            int32_t *ncc_out, int32_t *parents_out, int32_t *members_out, int32_t *cc_start_out, int32_t *ntests_out,
            unsigned long long *list, unsigned long long cap) {
@@ -101,7 +103,7 @@ k_manifold(int n, int Nq, int Nqp, const Real *__restrict__ Q, const int32_t *__
     for (int r = 0; r < R; r++) {
       const int j = lane + 32 * r;
       alive[r] = knn > 0 ? (j < c) : (j < i);
-      d[r] = alive[r] ? q_distance(n, q + i, Nqp, q + j, Nqp) : 0.0;
+      d[r] = alive[r] ? q_distance(n, spin, q + i, Nqp, q + j, Nqp) : 0.0;
     }
     const int rounds = knn > 0 ? min(knn, c) : i;
     for (int round = 0; round < rounds; round++) {
@@ -212,7 +214,7 @@ k_manifold(int n, int Nq, int Nqp, const Real *__restrict__ Q, const int32_t *__
 // ------------------------------------------------------------------------------------------
 template <typename Real>
 __global__ void __launch_bounds__(128)
-k_qcc_candidates(long long E, const int32_t *__restrict__ wedges, int n, int Nq, int Nqp, const Real *__restrict__ Q,
+k_qcc_candidates(long long E, const int32_t *__restrict__ wedges, int n, unsigned spin, int Nq, int Nqp, const Real *__restrict__ Q,
                  const int32_t *__restrict__ uid, const int32_t *__restrict__ ncc, const int32_t *__restrict__ members,
                  const int32_t *__restrict__ cc_start, const long long *__restrict__ cc_off, int T, uint32_t seed,
                  int swap, int32_t *__restrict__ cand) {
@@ -240,7 +242,7 @@ k_qcc_candidates(long long E, const int32_t *__restrict__ wedges, int n, int Nq,
       for (int t = lane; t < total; t += 32) {
         const int a = mi[a0 + t / nb], b = mj[b0 + t % nb];
         const unsigned key = ((unsigned)a << 16) | (unsigned)b;
-        const double d = q_distance(n, qi + a, Nqp, qj + b, Nqp);
+        const double d = q_distance(n, spin, qi + a, Nqp, qj + b, Nqp);
         if (have_last && !key_less(last_d, last_k, d, key)) continue;          // already selected
         if (bk == kNone || key_less(d, key, bd, bk)) { bd = d; bk = key; }
       }
@@ -260,7 +262,7 @@ k_qcc_candidates(long long E, const int32_t *__restrict__ wedges, int n, int Nq,
         for (int t = lane; t < total; t += 32) {
           const int a = mi[a0 + t / nb], b = mj[b0 + t % nb];
           const unsigned key = ((unsigned)a << 16) | (unsigned)b;
-          const double d = q_distance(n, qi + a, Nqp, qj + b, Nqp);
+          const double d = q_distance(n, spin, qi + a, Nqp, qj + b, Nqp);
           if (!key_less(last_d, last_k, d, key)) continue;                       // one of the T nearest
           const unsigned h = pair_hash(seed, ui, uj, key);
           if (have_h && !(h > last_h || (h == last_h && key > last_hk))) continue;
@@ -356,7 +358,7 @@ k_qcc_connect(long long E, const int32_t *__restrict__ wedges, const int32_t *__
 }
 
 template <typename Real>
-static int manifold_launch(int64_t Nn, const int32_t *node_list, int n, int Nq, int Nqp, const void *Q, const int32_t *count,
+static int manifold_launch(int64_t Nn, const int32_t *node_list, int n, unsigned spin, int Nq, int Nqp, const void *Q, const int32_t *count,
                            const uint32_t *smask, int knn, int32_t *label, int32_t *ncc, int32_t *parents, int32_t *members,
                            int32_t *cc_start, int32_t *ntests, unsigned long long *list, unsigned long long cap, cudaStream_t st) {
   const size_t smem = 6 * (size_t)Nq * sizeof(int32_t);
@@ -364,7 +366,7 @@ static int manifold_launch(int64_t Nn, const int32_t *node_list, int n, int Nq, 
     if (smem > 48 * 1024 && cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
       set_error("k_manifold: Nq=%d does not fit shared memory", Nq); return -2;
     }
-    kern<<<(unsigned)Nn, 32, smem, st>>>(n, Nq, Nqp, (const Real *)Q, count, node_list, smask, knn, label, ncc, parents, members,
+    kern<<<(unsigned)Nn, 32, smem, st>>>(n, spin, Nq, Nqp, (const Real *)Q, count, node_list, smask, knn, label, ncc, parents, members,
                                          cc_start, ntests, list, cap);
     return vis_launch_ok("k_manifold");
   };
@@ -382,14 +384,14 @@ using namespace grr;
 extern "C" {
 
 int grr_manifold_knn_list(int dtype, int64_t Nn, const int32_t *node_list, int32_t n, int32_t Nq, int32_t Nqp, const void *q_kept,
-                          const int32_t *count, int32_t knn, uint64_t *list, uint64_t cap, void *stream) {
+                          const int32_t *count, int32_t knn, uint64_t *list, uint64_t cap, uint32_t spin_mask, void *stream) {
   if (Nn <= 0) return 0;
   if (!q_kept || !count || !list || knn < 1 || n < 1 || Nq < 1 || Nqp < Nq || Nq > 65535) { set_error("grr_manifold_knn_list: bad argument"); return -1; }
   if (dtype == GRR_F32)
-    return manifold_launch<float>(Nn, node_list, n, Nq, Nqp, q_kept, count, nullptr, knn, nullptr, nullptr, nullptr, nullptr, nullptr,
+    return manifold_launch<float>(Nn, node_list, n, spin_mask, Nq, Nqp, q_kept, count, nullptr, knn, nullptr, nullptr, nullptr, nullptr, nullptr,
                                   nullptr, (unsigned long long *)list, cap, (cudaStream_t)stream);
   if (dtype == GRR_F64)
-    return manifold_launch<double>(Nn, node_list, n, Nq, Nqp, q_kept, count, nullptr, knn, nullptr, nullptr, nullptr, nullptr, nullptr,
+    return manifold_launch<double>(Nn, node_list, n, spin_mask, Nq, Nqp, q_kept, count, nullptr, knn, nullptr, nullptr, nullptr, nullptr, nullptr,
                                    nullptr, (unsigned long long *)list, cap, (cudaStream_t)stream);
   set_error("bad dtype %d", dtype);
   return -1;
@@ -397,15 +399,15 @@ int grr_manifold_knn_list(int dtype, int64_t Nn, const int32_t *node_list, int32
 
 int grr_manifold_components(int dtype, int64_t Nn, const int32_t *node_list, int32_t n, int32_t Nq, int32_t Nqp, const void *q_kept,
                             const int32_t *count, const uint32_t *self_mask, int32_t knn, int32_t *label, int32_t *ncc,
-                            int32_t *parents, int32_t *members, int32_t *cc_start, int32_t *ntests, void *stream) {
+                            int32_t *parents, int32_t *members, int32_t *cc_start, int32_t *ntests, uint32_t spin_mask, void *stream) {
   if (Nn <= 0) return 0;
   if (!q_kept || !count || !self_mask || !label || !ncc || !parents || !members || !cc_start || knn < 0 || n < 1 || Nq < 1 ||
       Nqp < Nq || Nq > 65535) { set_error("grr_manifold_components: bad argument"); return -1; }
   if (dtype == GRR_F32)
-    return manifold_launch<float>(Nn, node_list, n, Nq, Nqp, q_kept, count, self_mask, knn, label, ncc, parents, members, cc_start,
+    return manifold_launch<float>(Nn, node_list, n, spin_mask, Nq, Nqp, q_kept, count, self_mask, knn, label, ncc, parents, members, cc_start,
                                   ntests, nullptr, 0, (cudaStream_t)stream);
   if (dtype == GRR_F64)
-    return manifold_launch<double>(Nn, node_list, n, Nq, Nqp, q_kept, count, self_mask, knn, label, ncc, parents, members, cc_start,
+    return manifold_launch<double>(Nn, node_list, n, spin_mask, Nq, Nqp, q_kept, count, self_mask, knn, label, ncc, parents, members, cc_start,
                                    ntests, nullptr, 0, (cudaStream_t)stream);
   set_error("bad dtype %d", dtype);
   return -1;
@@ -413,17 +415,17 @@ int grr_manifold_components(int dtype, int64_t Nn, const int32_t *node_list, int
 
 int grr_qcc_candidates(int dtype, int64_t E, const int32_t *wedges, int32_t n, int32_t Nq, int32_t Nqp, const void *q_kept,
                        const int32_t *node_uid, const int32_t *ncc, const int32_t *members, const int32_t *cc_start,
-                       const int64_t *cc_off, int32_t max_tests, uint64_t seed, int32_t swap, int32_t *cand, void *stream) {
+                       const int64_t *cc_off, int32_t max_tests, uint64_t seed, int32_t swap, int32_t *cand, uint32_t spin_mask, void *stream) {
   if (E <= 0) return 0;
   if (!wedges || !q_kept || !ncc || !members || !cc_start || !cc_off || !cand || max_tests < 1 || Nq > 65535) {
     set_error("grr_qcc_candidates: bad argument"); return -1;
   }
   const uint32_t s32 = (uint32_t)seed ^ (uint32_t)(seed >> 32);
   if (dtype == GRR_F32)
-    k_qcc_candidates<float><<<(unsigned)E, 128, 0, (cudaStream_t)stream>>>(E, wedges, n, Nq, Nqp, (const float *)q_kept, node_uid, ncc,
+    k_qcc_candidates<float><<<(unsigned)E, 128, 0, (cudaStream_t)stream>>>(E, wedges, n, spin_mask, Nq, Nqp, (const float *)q_kept, node_uid, ncc,
                                                                           members, cc_start, (const long long *)cc_off, max_tests, s32, swap, cand);
   else if (dtype == GRR_F64)
-    k_qcc_candidates<double><<<(unsigned)E, 128, 0, (cudaStream_t)stream>>>(E, wedges, n, Nq, Nqp, (const double *)q_kept, node_uid, ncc,
+    k_qcc_candidates<double><<<(unsigned)E, 128, 0, (cudaStream_t)stream>>>(E, wedges, n, spin_mask, Nq, Nqp, (const double *)q_kept, node_uid, ncc,
                                                                            members, cc_start, (const long long *)cc_off, max_tests, s32, swap, cand);
   else { set_error("bad dtype %d", dtype); return -1; }
   return vis_launch_ok("k_qcc_candidates");

@@ -57,8 +57,6 @@ class VisibilityMixin:
     # ---- self-motion manifolds (solver.py:623-687) ------------------------------------------------------------------------
     def constructSelfMotionManifolds(self, k=None):
         """solver.py:672-687 for every workspace node.  Returns the device time in seconds."""
-        if self.resolution.chain.spin.any():
-            raise NotImplementedError("the visibility-graph variant with spin joints is not built (its distance sorts take plain differences)")
         torch = self.resolution._torch()
         res = self.resolution
         d = self._dev
@@ -79,7 +77,7 @@ class VisibilityMixin:
             cap = int(d["count"].sum().item()) * min(int(k), Nq)
             plist = self._new_list(cap)
             p, Q = self._listed_inputs(d)
-            _cabi.manifold_knn_list(Q, d["count"], Nq, int(k), plist)
+            _cabi.manifold_knn_list(Q, d["count"], Nq, int(k), plist, spin_mask=res.chain.spin_mask)
             res.chain.edges_test_listed(wself, p, Q, Nq, DEFAULT_EDGE_CHECK_TOLERANCE, smask, plist, d["counters_e"])
         v = {"k": k, "smask": smask,
              "label": torch.empty((self.Nw, Nq), dtype=torch.int32, device=dev),
@@ -89,7 +87,7 @@ class VisibilityMixin:
              "cc_start": torch.empty((self.Nw, Nq + 1), dtype=torch.int32, device=dev),
              "ntests": torch.zeros(self.Nw, dtype=torch.int32, device=dev)}
         _cabi.manifold_components(d["Qs"], d["count"], Nq, smask, 0 if k is None else int(k), v["label"], v["ncc"], v["parents"],
-                                  v["members"], v["cc_start"], v["ntests"])
+                                  v["members"], v["cc_start"], v["ntests"], spin_mask=res.chain.spin_mask)
         e1.record()
         torch.cuda.synchronize(dev)
         ce = (d["counters_e"] - before).cpu().numpy()
@@ -103,8 +101,6 @@ class VisibilityMixin:
     def constructSelfMotionManifold(self, iw, k=None):
         """solver.py:623-669 for one workspace node; returns its number of components.  The manifolds of all nodes are
         independent, so the batch call does the work and this one reads its result (rebuilding when k changed)."""
-        if self.resolution.chain.spin.any():
-            raise NotImplementedError("the visibility-graph variant with spin joints is not built (its distance sorts take plain differences)")
         v = getattr(self, "_vis", None)
         if v is None or v["k"] != k:
             self.constructSelfMotionManifolds(k)
@@ -170,7 +166,8 @@ class VisibilityMixin:
         ntests = torch.zeros(E, dtype=torch.int32, device=dev)
         if total == 0 or E == 0:
             return cc_off, conn[:0], nconn, ntests
-        _cabi.qcc_candidates(wedges, Q, Nq, uid, ncc, members, cc_start, cc_off, T, self.seed, swap, cand)
+        _cabi.qcc_candidates(wedges, Q, Nq, uid, ncc, members, cc_start, cc_off, T, self.seed, swap, cand,
+                             spin_mask=self.resolution.chain.spin_mask)
         vmask = torch.zeros((E, Nq, (Nq + 31) // 32), dtype=torch.int32, device=dev)
         for s0, s1 in ((0, 1), (1, T), (T, 2 * T)):
             if s1 <= s0:
@@ -202,8 +199,6 @@ class VisibilityMixin:
     def _connect_visibility(self, edge_ids=None, max_tests=10, swap=0, mode=0):
         """testAndConnectQccs (mode 0) / parallelEdgeConnection (mode 1) on every workspace edge (or the listed ones); sets
         the bits of the connecting pairs in the roadmap's edge masks.  Returns nconn (device int32 per edge)."""
-        if self.resolution.chain.spin.any():
-            raise NotImplementedError("the visibility-graph variant with spin joints is not built (its distance sorts take plain differences)")
         torch = self.resolution._torch()
         d = self._dev
         v = self._vis_state()
@@ -281,12 +276,12 @@ class VisibilityMixin:
             self._edges_launch_raw(wself, params, Qn, count, Nq, smask, stats, counters, None)
         else:
             plist = self._new_list(c * min(int(k), Nq))
-            _cabi.manifold_knn_list(Qn, count, Nq, int(k), plist)
+            _cabi.manifold_knn_list(Qn, count, Nq, int(k), plist, spin_mask=res.chain.spin_mask)
             res.chain.edges_test_listed(wself, params, Qn, Nq, DEFAULT_EDGE_CHECK_TOLERANCE, smask, plist, counters)
         out = {name: torch.empty(shape, dtype=torch.int32, device=dev)
                for name, shape in (("label", (1, Nq)), ("ncc", (1,)), ("parents", (1, Nq)), ("members", (1, Nq)), ("cc_start", (1, Nq + 1)))}
         _cabi.manifold_components(Qn, count, Nq, smask, 0 if k is None else int(k), out["label"], out["ncc"], out["parents"],
-                                  out["members"], out["cc_start"])
+                                  out["members"], out["cc_start"], spin_mask=res.chain.spin_mask)
         ncc = int(out["ncc"].item())
         mem, s = out["members"][0].cpu().numpy(), out["cc_start"][0].cpu().numpy()
         return [mem[s[i]:s[i + 1]].tolist() for i in range(ncc)], out["parents"][0, :c].cpu().tolist()

@@ -305,12 +305,13 @@ int grr_edges_test_listed(grr_handle_t h, int dtype, const int32_t *wedges, cons
  * neighbours in merge order, :661-668), members [Nw][Nq] = configs sorted by (component, id), cc_start [Nw][Nq+1] =
  * first position of each component in members, ntests [Nw] = validEdge calls the reference's loop makes (nullable).
  * grr_manifold_knn_list emits the pairs the knn branch may test ({node << 32 | i << 16 | j, 0}, list[0] += entries) for
- * grr_edges_test_listed on wedges[node] = (node, node).  Distances in IEEE double without contraction.  Nq <= 512. */
+ * grr_edges_test_listed on wedges[node] = (node, node).  Distances in IEEE double without contraction; spin_mask: bit j = chain
+ * joint j is a 'spin' joint (wrapped angular difference, see grr_chain_set_spin_joints; these calls take no handle).  Nq <= 512. */
 int grr_manifold_knn_list(int dtype, int64_t Nn, const int32_t *node_list, int32_t n, int32_t Nq, int32_t Nqp, const void *q_kept,
-                          const int32_t *count, int32_t knn, uint64_t *list, uint64_t cap, void *stream);
+                          const int32_t *count, int32_t knn, uint64_t *list, uint64_t cap, uint32_t spin_mask, void *stream);
 int grr_manifold_components(int dtype, int64_t Nn, const int32_t *node_list, int32_t n, int32_t Nq, int32_t Nqp, const void *q_kept,
                             const int32_t *count, const uint32_t *self_mask, int32_t knn, int32_t *label, int32_t *ncc,
-                            int32_t *parents, int32_t *members, int32_t *cc_start, int32_t *ntests, void *stream);
+                            int32_t *parents, int32_t *members, int32_t *cc_start, int32_t *ntests, uint32_t spin_mask, void *stream);
 
 /* testAndConnectQccs (grr/solver.py:517-561) / parallelEdgeConnection (:949-982) on E workspace edges.
  * grr_qcc_candidates: for every CC pair (ci, cj) of every edge, cand [dev] i32 [(cc_off[e] + ci*ncc[jw] + cj) * 2T + slot]:
@@ -330,7 +331,7 @@ int grr_manifold_components(int dtype, int64_t Nn, const int32_t *node_list, int
  * (inner config); list entries, tested_mask and mask stay in the orientation of wedges. */
 int grr_qcc_candidates(int dtype, int64_t E, const int32_t *wedges, int32_t n, int32_t Nq, int32_t Nqp, const void *q_kept,
                        const int32_t *node_uid, const int32_t *ncc, const int32_t *members, const int32_t *cc_start,
-                       const int64_t *cc_off, int32_t max_tests, uint64_t seed, int32_t swap, int32_t *cand, void *stream);
+                       const int64_t *cc_off, int32_t max_tests, uint64_t seed, int32_t swap, int32_t *cand, uint32_t spin_mask, void *stream);
 int grr_qcc_wave(int64_t E, const int32_t *wedges, const int32_t *ncc, const int64_t *cc_off, int32_t max_tests, const int32_t *cand,
                  int32_t Nq, const uint32_t *tested_mask, int32_t slot0, int32_t slot1, int32_t swap, uint64_t *list, uint64_t cap,
                  void *stream);

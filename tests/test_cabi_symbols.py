@@ -26,7 +26,7 @@ def test_every_declared_symbol_is_exported(built):
     for n in names:
         assert hasattr(L, n), "libgrr_b200.so does not export %s" % n
     assert sorted(_cabi.EXPORTS) == names
-    assert L.grr_abi_version() == 1
+    assert L.grr_abi_version() == 2
 
 
 def test_chain_create_validates_arguments(built):

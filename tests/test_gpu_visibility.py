@@ -15,13 +15,20 @@ pytestmark = pytest.mark.gpu
 PROBLEMS = [("planar_3R", "baseline_cfg1.json", {"Nw": 80}, 24, 3),
             ("planar_20R", "baseline_cfg2.json", {"Nw": 30, "domain": [[0.8, 0, 0.3], [1.4, 0, 0.9]]}, 40, 5),
             ("jaco", "baseline_cfg3.json", {"Nw": 60}, 24, 7),
-            ("robonaut2", "baseline_cfg5.json", {"Nw": 150}, 64, 9)]
-IDS = ["planar_3R", "planar_20R", "jaco-free", "robonaut2-fixed"]
+            ("robonaut2", "baseline_cfg5.json", {"Nw": 150}, 64, 9),
+            # joints 1, 4, 5, 6 as Klamp't 'spin' joints: the distance sorts take wrapped angular differences
+            ("jaco", "baseline_cfg3.json", {"Nw": 60}, 24, 7, ["jaco_link_1", "jaco_link_4", "jaco_link_5", "jaco_link_hand"])]
+IDS = ["planar_3R", "planar_20R", "jaco-free", "robonaut2-fixed", "jaco-spin"]
 
 
 def _sampled(prob, seed, Nq, visibility=False, k=None, connect=True):
-    name, jf, over, _, _ = prob
-    pdef, res, rr = grr.make_program(name, jf, overrides=over, seed=seed)
+    name, jf, over = prob[0], prob[1], prob[2]
+    if len(prob) > 5:
+        from helpers import spin_problem
+        pdef, res = spin_problem(name, jf, over["Nw"], "staggered_grid", prob[5])
+        rr = grr.RedundancyResolver(res, seed=seed)
+    else:
+        pdef, res, rr = grr.make_program(name, jf, overrides=over, seed=seed)
     rr.sampleConfigurationSpace(Nq, connect=connect, order_independent=True, visibility=visibility, k=k)
     return res, rr
 
