@@ -197,3 +197,31 @@ def test_gpu_seeded_sweep_and_api_with_spin_joints(built):
         assert res.validEdge(qa2, qb, x, x) == v0
         a_c, b_c = res.to_chain(np.asarray(qa)), res.to_chain(np.asarray(qb))
         assert v0 == bool(o.valid_edge(a_c, b_c, np.asarray(x, dtype=float), np.asarray(x, dtype=float))[0])
+
+
+def test_rob_file_with_spin_joints_round_trips_and_sets_the_flag(tmp_path):
+    """`joint spin <i>` lines of a .rob file (with infinite limits, as Klamp't writes them for continuous joints) survive
+    to_rob / from_rob, reach the chain description as spin flags, and readJsonSetup notes them (graph.py:556-561)."""
+    from globalredundancyresolution_b200.graph import RedundancyResolutionGraph
+    rob = R.synthetic_arm("jaco")
+    for name in JACO_SPIN:
+        i = rob.link(name).index
+        rob.joint_kind[i] = "spin"
+        rob.qmin[i], rob.qmax[i] = -np.inf, np.inf
+    text = rob.to_rob()
+    assert text.count("joint spin") == 4 and "inf" in text
+    path = tmp_path / "jaco_spin.rob"
+    path.write_text(text)
+    rob2 = R.RobotChain.from_rob(str(path))
+    assert [rob2.getJointType(i) for i in range(rob2.numLinks())] == ["spin", "normal", "normal", "spin", "spin", "spin"]
+    assert np.isinf(rob2.qmin[0]) and np.isinf(rob2.qmax[0])
+    res = RedundancyResolutionGraph(rob2, lazy_chain=True)
+    res.readJsonSetup({"link": "jaco_link_hand", "eelocal": [0, 0, -0.1], "orientation": "free", "useCollision": False,
+                       "domain": [[-1, -1, -0.5], [1.2, 1.2, 1.7]]})
+    assert res.spinJoints and list(res.fold["spin"]) == [1, 0, 0, 1, 1, 1] and res.chain.spin_mask == 0b111001
+    # the oracle treats such a joint as unbounded and samples it in [0, 2 pi)
+    o = oracle_for(res)
+    q = np.array([o.random_seed(3, 5, s) for s in range(200)]) if hasattr(o, "random_seed") else None
+    if q is not None:
+        sp = np.asarray(res.fold["spin"], dtype=bool)
+        assert ((q[:, sp] >= 0) & (q[:, sp] <= 2 * math.pi + 1e-6)).all() and q[:, sp].max() > math.pi
