@@ -2,7 +2,6 @@
 import numpy as np
 
 import globalredundancyresolution_b200 as grr
-from globalredundancyresolution_b200 import _cabi
 from oracle import oracle as O
 
 

@@ -1,6 +1,5 @@
 """The C-ABI library loads on a CPU-only box and exports every symbol include/grr_b200.h declares.
 No compute call is made here (no GPU)."""
-import ctypes as C
 import os
 import re
 

@@ -5,7 +5,6 @@ import pytest
 import globalredundancyresolution_b200 as grr
 from globalredundancyresolution_b200 import _cabi
 from helpers import oracle_for, reference_configs, unpack_mask
-from oracle import oracle as O
 
 torch = pytest.importorskip("torch")
 pytestmark = pytest.mark.gpu

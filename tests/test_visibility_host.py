@@ -1,6 +1,5 @@
 """The restatement of the reference's visibility-graph loops (oracle/visibility_oracle.py) on hand-made inputs, and the
 host-side hash that stands in for random.sample."""
-import numpy as np
 
 from oracle import visibility_oracle as V
 
