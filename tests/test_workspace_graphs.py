@@ -161,3 +161,21 @@ def test_random_workspace_graph_explicit_k():
     assert info["k"] == 4
     deg = np.bincount(edges.reshape(-1), minlength=100)
     assert deg.min() >= 4
+
+
+def test_random_workspace_graph_through_the_problem_options():
+    """`workspace_graph: "random"` of a problem file (README.md:84-97) reaches sampleWorkspace through load_problem, on the
+    CPU (the chain handle is only described, not created)."""
+    import globalredundancyresolution_b200 as grr
+    pdef, res = grr.load_problem("planar_20R", "baseline_cfg2.json", overrides={"Nw": 200, "workspace_graph": "random"},
+                                 lazy_chain=True)
+    assert pdef["workspace_graph"] == "random"
+    res.sampleWorkspace(pdef["Nw"], method=pdef["workspace_graph"])
+    assert res.Gw.number_of_nodes() == 200 and res.ws_info["k"] == int((1 + 1.0 / 2) * math.e * math.log(200))
+    deg = np.bincount(res.ws_edges.reshape(-1), minlength=200)
+    assert deg.min() >= res.ws_info["k"] and res.Gw.number_of_edges() == res.ws_edges.shape[0]
+    y = res.ws_params[:, 1]
+    assert (y == 0).all()                                          # the degenerate axis of the planar domain keeps its value
+    # explicit k and another seed
+    res.sampleWorkspace(100, k=3, method="random", seed=9)
+    assert res.Gw.number_of_nodes() == 100 and res.ws_info == {"k": 3, "seed": 9}
